@@ -1,0 +1,280 @@
+/*
+ * voxelrt.h — C ABI of libvoxelrt, the B200 (sm_100a) replacement for voxel-rs's
+ * GLSL ray-cast path. Everything below is plain C: opaque context, POD structs,
+ * raw pointers and sizes. No C++/torch types cross this boundary.
+ *
+ * Each entry point names the reference interface it replaces; paths are relative
+ * to the voxel-rs checkout (tim-oster/voxel-rs).
+ *
+ *   reference seam                                   replaced by
+ *   -----------------------------------------------  ---------------------------
+ *   graphics::Svo::new          src/graphics/svo.rs:109-149   vx_create + vx_set_textures + vx_set_materials
+ *   graphics::Svo::update       src/graphics/svo.rs:171-189   vx_svo_host_mirror + vx_svo_commit
+ *   graphics::Svo::get_stats    src/graphics/svo.rs:191-193   vx_stats
+ *   graphics::Svo::render       src/graphics/svo.rs:196-229   vx_render (+ vx_read_frame*)
+ *   graphics::Svo::raycast      src/graphics/svo.rs:233-255   vx_raycast
+ *   svo.test.glsl debug harness assets/shaders/svo.test.glsl  vx_debug_cast
+ *   Framebuffer::read_pixels    src/graphics/framebuffer.rs:97-105  vx_read_frame_rgba8
+ *
+ * Threading: calls on one VxCtx must be serialised by the caller (the reference
+ * issues all GL calls from the main thread, README.md:116-119). Internally the
+ * context owns three CUDA streams (render, upload, picker) ordered by events.
+ *
+ * Errors: the reference panics (unwrap / assert!, e.g. src/world/hds/esvo.rs:328-331).
+ * The FFI never unwinds: every call returns VX_OK or a negative VX_E_* code and
+ * vx_last_error() holds a human-readable message for the last failure on that ctx.
+ */
+#ifndef VOXELRT_H
+#define VOXELRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_OK            0
+#define VX_E_ARG        -1   /* bad argument (null pointer, size out of range) */
+#define VX_E_CAPACITY   -2   /* dirty range / frame / ray batch exceeds what vx_create reserved
+                                (reference: assert! in esvo.rs:328-331) */
+#define VX_E_CUDA       -3   /* CUDA runtime error; message has cudaGetErrorString */
+#define VX_E_NCCL       -4   /* NCCL error */
+#define VX_E_STATE      -5   /* call out of order (e.g. render before textures/materials/SVO) */
+
+typedef struct VxCtx VxCtx;
+
+/* ------------------------------------------------------------------ config -- */
+
+/* flags for VxConfig.flags */
+#define VX_FLAG_NO_L2_WINDOW   (1u << 0)  /* do not install the persisting-L2 access-policy window */
+#define VX_FLAG_KERNEL_SIMPLE  (1u << 1)  /* one-thread-per-pixel reference kernels instead of the
+                                             persistent work-fetching ones (A/B + debugging) */
+
+typedef struct VxConfig {
+    int32_t  device;              /* CUDA device ordinal this context owns */
+    uint32_t flags;
+    uint64_t svo_capacity_bytes;  /* = size_mb * 1000 * 1000 of graphics::Svo::new (svo.rs:133) */
+    uint32_t max_width;           /* largest framebuffer this ctx will render (0 => no frame buffer) */
+    uint32_t max_height;
+    uint64_t max_rays;            /* largest vx_raycast batch (reference caps at 100, svo_picker.rs:5) */
+} VxConfig;
+
+/* --------------------------------------------------------------- materials -- */
+
+/* = #[repr(C)] MaterialInstance, src/graphics/svo_registry.rs:29-40
+ * = GLSL struct Material, assets/shaders/svo.glsl:48-59 (std430, stride 32). -1 = no texture. */
+typedef struct VxMaterial {
+    float   specular_pow;
+    float   specular_strength;
+    int32_t tex_top;
+    int32_t tex_side;
+    int32_t tex_bottom;
+    int32_t tex_top_normal;
+    int32_t tex_side_normal;
+    int32_t tex_bottom_normal;
+} VxMaterial;
+
+/* ------------------------------------------------------------------ picker -- */
+
+/* = #[repr(C)] PickerTask, src/graphics/svo_picker.rs:13-19 (AlignedPoint3/AlignedVec3 are
+ * 16-byte aligned, src/graphics/macros.rs:64-90) = GLSL PickerTask, picker.glsl:19-23. 48 bytes. */
+typedef struct VxPickerTask {
+    float max_dst;  float _pad0[3];
+    float pos[3];   float _pad1;
+    float dir[3];   float _pad2;
+} VxPickerTask;
+
+/* = #[repr(C)] PickerResult, src/graphics/svo_picker.rs:21-32 = GLSL PickerResult,
+ * picker.glsl:9-14. inside_voxel is a GLSL bool (4 bytes, 0/1); Rust reads its first byte. */
+typedef struct VxPickerResult {
+    float    dst;
+    uint32_t inside_voxel;
+    float    _pad0[2];
+    float    pos[3];    float _pad1;
+    float    normal[3]; float _pad2;
+} VxPickerResult;
+
+/* ------------------------------------------------------------------ render -- */
+
+/* The ten uniforms of world.glsl:12-25 as set by graphics::Svo::render (svo.rs:201-215).
+ * `view` is the ALREADY INVERTED look_to_rh matrix (camera -> world), column-major, exactly the
+ * value the reference uploads as u_view (svo.rs:197,204) so device code never re-derives it.
+ * highlight_pos = NaN,NaN,NaN when no voxel is selected (svo.rs:211-215). */
+typedef struct VxRenderParams {
+    float    view[16];
+    float    fov_y_rad;
+    float    aspect_ratio;
+    float    ambient_intensity;
+    float    light_dir[3];
+    float    cam_pos[3];
+    float    highlight_pos[3];
+    uint32_t render_shadows;
+    float    shadow_distance;
+} VxRenderParams;
+
+/* Image-space shard for multi-GPU rendering: this ctx renders only tiles whose Morton-ordered
+ * tile index t satisfies t % world_size == rank. {0,1} renders the whole frame. */
+typedef struct VxShard {
+    uint32_t rank;
+    uint32_t world_size;
+} VxShard;
+
+/* Per-frame counters of the last vx_render / vx_raycast (device-accumulated). */
+typedef struct VxFrameStats {
+    uint64_t primary_rays;   /* rays traced from the camera (== pixels of this shard) */
+    uint64_t shadow_rays;    /* secondary rays actually cast (world.glsl:80-84) */
+    uint64_t steps;          /* traversal loop iterations (svo.esvo.glsl:152), both ray kinds */
+    uint64_t pushes;         /* PUSH phases (svo.esvo.glsl:281-311) */
+    uint64_t leaf_tests;     /* HIT blocks entered (svo.esvo.glsl:185-265) */
+    uint64_t tex_fetches;    /* texels read (1 per NEAREST sample, 8 per trilinear) */
+    float    kernel_ms;      /* CUDA-event time of the dominant kernel on its own stream */
+} VxFrameStats;
+
+/* = graphics::svo::Stats, src/graphics/svo.rs:75-83 */
+typedef struct VxStats {
+    uint64_t used_bytes;
+    uint64_t capacity_bytes;
+    uint32_t depth;
+} VxStats;
+
+/* A dirty byte range of the serialized SVO, relative to the RangeBuffer start
+ * (= world::hds::internal::Range, src/world/hds/internal.rs:150-154). In the GPU buffer the
+ * range lives at byte 24 + offset (4-byte octree_scale + 20-byte preamble, svo.esvo.glsl:3-6,
+ * esvo.rs:134,179-188). */
+typedef struct VxRange {
+    uint64_t offset;
+    uint64_t length;
+} VxRange;
+
+/* ---------------------------------------------------------- debug ray cast -- */
+
+/* = StackFrame, assets/shaders/svo.test.glsl:23-33 / src/graphics/svo_shader_tests.rs:51-63 */
+typedef struct VxDebugFrame {
+    float    t_min;
+    uint32_t ptr;
+    uint32_t idx;
+    uint32_t parent_octant_idx;
+    int32_t  scale;
+    int32_t  is_child;
+    int32_t  is_leaf;
+    int32_t  crossed_boundary;   /* CSVO only; always 0 for ESVO */
+    uint32_t next_ptr;           /* CSVO only; always 0 for ESVO */
+} VxDebugFrame;
+
+/* = OctreeResult, assets/shaders/svo.glsl:31-40 (plus lod, which svo.test.glsl drops) */
+typedef struct VxOctreeResult {
+    float    t;
+    uint32_t value;
+    int32_t  face_id;
+    float    pos[3];
+    float    uv[2];
+    float    color[4];
+    float    lod;
+    uint32_t inside_voxel;
+} VxOctreeResult;
+
+/* ------------------------------------------------------------- entry points -- */
+
+/* graphics::Svo::new (svo.rs:109-149): allocate device world buffer, pinned host mirror,
+ * framebuffer, picker buffers, streams. */
+int vx_create(const VxConfig* cfg, VxCtx** out);
+void vx_destroy(VxCtx* ctx);
+const char* vx_last_error(const VxCtx* ctx);   /* ctx may be NULL: returns the last create error */
+
+/* VoxelRegistry::build_material_buffer (svo_registry.rs:135-165): table indexed by BlockId. */
+int vx_set_materials(VxCtx* ctx, const VxMaterial* materials, uint32_t count);
+
+/* VoxelRegistry::build_texture_array / TextureArrayBuilder::build (svo_registry.rs:122-133,
+ * texture_array.rs:83-153): `rgba8` holds `layers` images of width*height RGBA8 texels, level 0
+ * only, ALREADY vertically flipped the way the reference flips on load (texture_array.rs:92,126,
+ * 155-176). mip_levels is clamped to min(mip_levels, ilog2(min(w,h))) like texture_array.rs:105;
+ * the library generates the chain on the GPU (2x2 box filter, round-to-nearest — the
+ * glGenerateMipmap stand-in, texture_array.rs:258-260). Sampler state is fixed to the
+ * reference's: S clamp, T repeat, MIN linear-mipmap-linear, MAG nearest (texture_array.rs:200-203). */
+int vx_set_textures(VxCtx* ctx, const uint8_t* rgba8, uint32_t width, uint32_t height,
+                    uint32_t layers, uint32_t mip_levels);
+
+/* Pinned host mirror of the whole GPU world buffer (capacity = svo_capacity_bytes). Byte 0 is
+ * the f32 octree_scale; the Rust side passes `mirror + 4` as `dst` to the unchanged
+ * Esvo::write_changes_to (svo.rs:180-181, esvo.rs:310-339). */
+uint8_t* vx_svo_host_mirror(VxCtx* ctx);
+
+/* graphics::Svo::update (svo.rs:171-189) after write_changes_to filled the mirror: waits for the
+ * frame in flight (the render_fence of svo.rs:178), then copies byte 0..24 (scale + preamble) and
+ * every dirty range (offset relative to RangeBuffer start) host->device with cudaMemcpyAsync on
+ * the upload stream; the next render/raycast waits on the upload event. `octree_scale` is written
+ * to mirror byte 0 by this call (svo.rs:173-175). n_dirty==0 with used_bytes>0 uploads nothing but
+ * still refreshes stats. */
+int vx_svo_commit(VxCtx* ctx, float octree_scale, const VxRange* dirty, uint32_t n_dirty,
+                  uint64_t used_bytes, uint32_t depth);
+
+/* Optional hint: RangeBuffer byte range of the world-root octree (octant_to_range[u64::MAX],
+ * esvo.rs:270) — pinned in L2 with a persisting access-policy window together with the preamble. */
+int vx_svo_set_hot_range(VxCtx* ctx, uint64_t offset, uint64_t length);
+
+/* Multi-GPU replicas: same as vx_svo_commit but the packed dirty payload comes from a device
+ * buffer that was just broadcast (NCCL) from rank 0: `packed` = n_dirty VxRange headers followed
+ * by the concatenated range bytes, first 24 bytes of the world buffer in `head24`. Applied by a
+ * scatter kernel on the upload stream. */
+int vx_svo_commit_packed_device(VxCtx* ctx, const void* packed_dev, uint32_t n_dirty,
+                                uint64_t payload_bytes, uint64_t used_bytes, uint32_t depth);
+/* Rank-0 helper: pack mirror ranges into `out` (host, pinned or not) in the layout above.
+ * Returns bytes written or a negative error; call with out==NULL to query the size. */
+int64_t vx_svo_pack_dirty(VxCtx* ctx, const VxRange* dirty, uint32_t n_dirty, void* out, uint64_t out_cap);
+
+int vx_stats(const VxCtx* ctx, VxStats* out);
+
+/* graphics::Svo::render (svo.rs:196-229) = world.glsl main(): one primary ray per pixel, shading,
+ * optional shadow ray, sky; writes the context's RGBA32F device framebuffer (row 0 = bottom row,
+ * world.glsl:112-115,140). Asynchronous on the render stream unless rgba32f_out != NULL, in which
+ * case the frame is copied to that HOST buffer (width*height*16 bytes) and the call returns after
+ * the copy completed. shard may be NULL (= whole frame). */
+int vx_render(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
+              const VxShard* shard, float* rgba32f_out);
+
+/* Block until the last vx_render finished (the reference's render_fence.wait(), svo.rs:178). */
+int vx_render_wait(VxCtx* ctx);
+
+/* Framebuffer::read_pixels (framebuffer.rs:97-105): RGBA8 = round(clamp(c,0,1)*255), row 0 = bottom. */
+int vx_read_frame_rgba8(VxCtx* ctx, uint8_t* rgba8_out);
+int vx_read_frame_rgba32f(VxCtx* ctx, float* rgba32f_out);
+/* Device pointer of the RGBA32F framebuffer of the last render (for zero-copy consumers /
+ * NCCL tile gather). Valid until vx_destroy. */
+int vx_frame_device_ptr(VxCtx* ctx, void** out_ptr, uint32_t* width, uint32_t* height);
+
+/* graphics::Svo::raycast (svo.rs:233-255) = picker.glsl main(): tasks/results are HOST arrays of n
+ * records; synchronous like the reference (fence place+wait, svo.rs:248-249). n is not capped at
+ * 100 (svo_picker.rs:5) — only by VxConfig.max_rays. */
+int vx_raycast(VxCtx* ctx, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results);
+
+/* Same kernel on DEVICE-resident task/result arrays (no copies, asynchronous on the picker
+ * stream; vx_raycast_wait to join). Used by benchmarks to time the kernel with inputs in HBM. */
+int vx_raycast_device(VxCtx* ctx, const VxPickerTask* tasks_dev, uint64_t n, VxPickerResult* results_dev);
+int vx_raycast_wait(VxCtx* ctx);
+
+/* svo.test.glsl main(): cast one ray and record every loop iteration (svo.esvo.glsl:175).
+ * frames_cap frames at most are stored; *n_frames receives the total count (stack_ptr + 1). */
+int vx_debug_cast(VxCtx* ctx, const float pos[3], const float dir[3], float max_dst,
+                  uint32_t cast_translucent, VxOctreeResult* result,
+                  VxDebugFrame* frames, uint32_t frames_cap, uint32_t* n_frames);
+
+/* Counters + kernel time of the last vx_render (which=0) or vx_raycast* (which=1). Implies a wait. */
+int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
+
+/* Runtime knobs for A/B measurements (no reference counterpart):
+ *   1 = simple one-thread-per-pixel kernels (0/1)      2 = 128-bit node fetches (0/1, default 1)
+ *   3 = count steps/pushes/leaf tests/texels (0/1)     4 = CTAs per SM of persistent kernels (0 = occupancy query)
+ *   5 = persisting-L2 access-policy window (0/1, default 1) */
+int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);
+
+/* How many kernels of this library were launched on this ctx since creation. */
+uint64_t vx_launch_count(const VxCtx* ctx);
+
+/* Library build id string (compile flags, arch). */
+const char* vx_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELRT_H */

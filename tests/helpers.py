@@ -1,0 +1,81 @@
+"""Shared scene builders for the tests. Mirrors the fixtures of the reference's own tests."""
+import numpy as np
+
+
+def shader_test_atlas():
+    """The 4x4 synthetic atlas of src/graphics/svo_shader_tests.rs:117-146, as given to add_rgba8 (row 0 = top)."""
+    R, G, T = (255, 0, 0, 255), (0, 255, 0, 255), (0, 0, 0, 0)
+    full = np.array([[R] * 4] * 4, dtype=np.uint8)
+    coords = np.array([[(51 * x, 153 - 51 * y, 0, 255) for x in range(4)] for y in range(4)], dtype=np.uint8)
+    t1 = np.array([[T, T, R, R]] * 4, dtype=np.uint8)
+    t2 = np.array([[T, T, G, G]] * 4, dtype=np.uint8)
+    return {"full": full, "coords": coords, "transparent_1": t1, "transparent_2": t2}
+
+
+def shader_test_registry(pkg):
+    """create_test_materials(), svo_shader_tests.rs:117-202: 1 mip level, materials 0..4 without normals."""
+    r = pkg.Registry(mip_levels=1)
+    for name, img in shader_test_atlas().items():
+        r.add_texture(name, img)
+    r.add_material(0)
+    r.add_material(1, all_sides="full")
+    r.add_material(2, all_sides="coords")
+    r.add_material(3, all_sides="transparent_1")
+    r.add_material(4, all_sides="transparent_2")
+    return r
+
+
+def shader_test_world(pkg, blocks, svo_pos=(0, 0, 0)):
+    """create_test_world(), svo_shader_tests.rs:78-115: pooled chunk storage, set_block, storage.compact(), one leaf."""
+    w = pkg.World()
+    w.set_leaf_blocks(svo_pos, blocks, uid=1, lod=5, compact=True)
+    w.serialize()
+    return w
+
+
+def svo_render_test_registry(pkg, atlas):
+    """create_voxel_registry(), src/graphics/svo.rs:323-338."""
+    r = pkg.Registry(mip_levels=6)
+    for name, stem in [("stone", "stone"), ("stone_normal", "stone_n"), ("dirt", "dirt"), ("dirt_normal", "dirt_n"),
+                       ("grass_side", "grass_side"), ("grass_side_normal", "grass_side_n"), ("grass_top", "grass_top"),
+                       ("grass_top_normal", "grass_top_n")]:
+        r.add_texture(name, atlas[stem])
+    r.add_material(0)
+    r.add_material(1, (70.0, 0.4), all_sides="stone", with_normals=True)
+    r.add_material(2, (14.0, 0.4), top="grass_top", side="grass_side", bottom="dirt", with_normals=True)
+    return r
+
+
+def svo_render_test_blocks():
+    """Scene of svo_tests::render, src/graphics/svo.rs:347-363."""
+    b = [(x, 0, z, 1) for x in range(5) for z in range(5)]
+    for z in (1, 3):
+        b += [(1, 1, z, 2), (3, 1, z, 2), (1, 3, z, 2), (3, 3, z, 2)]
+    return b
+
+
+def svo_render_test_params(pkg, width=640, height=490):
+    """RenderParams of svo_tests::render, src/graphics/svo.rs:371-383."""
+    return pkg.render_params(cam_pos=(2.5, 2.5, 7.5), cam_fwd=(0, 0, -1), cam_up=(0, 1, 0), fov_y_deg=72.0, aspect=width / height,
+                             ambient=0.3, selected_voxel=(1.0, 1.0, 3.0), render_shadows=True, shadow_distance=500.0)
+
+
+def oracle_scene(ora, world, registry):
+    tex, mips = registry.textures()
+    return ora.Scene(world.gpu_buffer(), registry.materials().tobytes(), tex, mips)
+
+
+def diff_images(a8, b8):
+    """diff_images(), src/graphics/framebuffer.rs:120-134: mean |dRGB| / 255."""
+    d = np.abs(a8[..., :3].astype(np.int64) - b8[..., :3].astype(np.int64)).sum()
+    return d / (255.0 * 3.0 * a8.shape[0] * a8.shape[1])
+
+
+def random_tasks(pkg, n, lo, hi, max_dst, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.zeros(n, dtype=pkg.TASK_DTYPE)
+    t["max_dst"] = max_dst
+    t["pos"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    t["dir"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return t

@@ -1,0 +1,142 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) and the host ESVO builder against the reference's own golden vectors
+(src/graphics/svo_shader_tests.rs esvo_tests, src/graphics/svo.rs svo_tests). CPU only."""
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import helpers
+from golden import reference_vectors as gv
+
+EPS = 1e-5   # assert_float_eq! default, src/graphics/macros.rs:105-114
+
+
+def close(a, b, eps=EPS):
+    # the reference compares f32 values against f32 literals
+    return np.all(np.abs(np.asarray(a, np.float32).astype(np.float64) - np.asarray(b, np.float32).astype(np.float64)) < eps)
+
+
+def check_result(res, exp, eps=EPS, name=""):
+    d = res.as_dict()
+    assert close(d["t"], exp["t"], eps), (name, d, exp)
+    assert d["value"] == exp["value"], (name, d, exp)
+    assert d["face_id"] == exp["face_id"], (name, d, exp)
+    assert close(d["pos"], exp["pos"], eps), (name, d, exp)
+    assert close(d["uv"], exp["uv"], eps), (name, d, exp)
+    assert close(d["color"], exp["color"], eps), (name, d, exp)
+    assert d["inside_voxel"] == exp["inside_voxel"], (name, d, exp)
+
+
+def check_frames(frames, n, exp):
+    assert n == len(exp)
+    for f, e in zip(frames, exp):
+        got = f.as_tuple()
+        assert close(got[0], e[0]), (got, e)
+        assert got[1:] == e[1:], (got, e)
+
+
+@pytest.fixture(scope="module")
+def reg(pkg):
+    return helpers.shader_test_registry(pkg)
+
+
+def scene_for(pkg, ora, reg, blocks, svo_pos=(0, 0, 0)):
+    w = helpers.shader_test_world(pkg, blocks, svo_pos)
+    return helpers.oracle_scene(ora, w, reg)
+
+
+def test_shader_svo_traversal(pkg, ora, reg):
+    g = gv.TRAVERSAL
+    s = scene_for(pkg, ora, reg, g["blocks"])
+    res, frames, n = s.debug_cast(g["pos"], g["dir"], g["max_dst"], g["cast_translucent"])
+    check_frames(frames, n, g["frames"])
+    check_result(res, g["result"])
+
+
+def test_cast_inside_outside_all_axes(pkg, ora, reg):
+    g = gv.ALL_AXES
+    s = scene_for(pkg, ora, reg, g["blocks"])
+    for name, pos, d, t, face, hit_pos, uv in g["cases"]:
+        exp = {"t": t, "value": g["value"], "face_id": face, "pos": hit_pos, "uv": uv, "color": g["color"], "inside_voxel": False}
+        res, _, _ = s.debug_cast(pos, d, 100.0, False)
+        check_result(res, exp, name=name + " inside")
+        dn = np.array(d, np.float32) / np.float32(np.linalg.norm(np.array(d, np.float32)))
+        exp2 = dict(exp, t=t + 1.0)
+        res, _, _ = s.debug_cast(tuple(np.array(pos, np.float32) - dn), d, 100.0, False)
+        check_result(res, exp2, name=name + " outside")
+
+
+def test_uv_coords_on_all_sides(pkg, ora, reg):
+    g = gv.UV_COORDS
+    s = scene_for(pkg, ora, reg, g["blocks"])
+    for i, (pos, d, uv, color) in enumerate(g["cases"]):
+        res, _, _ = s.debug_cast(pos, d, 32.0, False)
+        assert close(res.as_dict()["uv"], uv), (i, res.as_dict())
+        assert close(res.as_dict()["color"], color), (i, res.as_dict())
+
+
+def test_casting_against_translucent_leafs(pkg, ora, reg):
+    g = gv.TRANSLUCENT
+    s = scene_for(pkg, ora, reg, g["blocks"])
+    for name, pos, translucent, exp in g["cases"]:
+        res, _, _ = s.debug_cast(pos, g["dir"], 32.0, translucent)
+        d = res.as_dict()
+        if exp["t"] < 0:
+            check_result(res, exp, name=name)
+        else:
+            assert close(d["t"], exp["t"], 0.01) and close(d["pos"], exp["pos"], 0.01) and close(d["uv"], exp["uv"], 0.01), (name, d)
+            assert d["value"] == exp["value"] and d["face_id"] == exp["face_id"] and d["inside_voxel"] == exp["inside_voxel"], (name, d)
+            assert close(d["color"], exp["color"]), (name, d)
+
+
+def test_detect_inside_leaf_voxel(pkg, ora, reg):
+    g = gv.INSIDE_LEAF
+    s = scene_for(pkg, ora, reg, g["blocks"])
+    for name, pos, d, exp in g["cases"]:
+        res, _, _ = s.debug_cast(pos, d, 32.0, False)
+        check_result(res, exp, name=name)
+
+
+def test_check_at_higher_coordinates(pkg, ora, reg):
+    g = gv.HIGHER_COORDS
+    s = scene_for(pkg, ora, reg, g["blocks"], g["svo_pos"])
+    res, frames, n = s.debug_cast(g["pos"], g["dir"], g["max_dst"], g["cast_translucent"])
+    check_frames(frames, n, g["frames"])
+    check_result(res, g["result"])
+
+
+def test_picker_raycast_golden(pkg, ora):
+    """svo_tests::raycast, src/graphics/svo.rs:402-449 through picker.glsl semantics."""
+    g = gv.PICKER_RAYCAST
+    atlas = pkg.load_atlas()
+    reg = helpers.svo_render_test_registry(pkg, atlas)
+    w = pkg.World()
+    w.set_leaf_blocks((0, 0, 0), g["blocks"], compact=False)
+    w.serialize()
+    s = helpers.oracle_scene(ora, w, reg)
+    tasks = np.zeros(len(g["rays"]), dtype=pkg.TASK_DTYPE)
+    for i, (p, d, m) in enumerate(g["rays"]):
+        tasks[i]["pos"], tasks[i]["dir"], tasks[i]["max_dst"] = p, d, m
+    res, _ = s.raycast(tasks)
+    for r, (dst, inside, pos, normal) in zip(res, g["expected"]):
+        assert close(r["dst"], dst, 1e-4) and bool(r["inside_voxel"]) == inside
+        assert close(r["pos"], pos, 1e-4) and tuple(r["normal"]) == normal
+
+
+def test_render_expected_png(pkg, ora):
+    """svo_tests::render, src/graphics/svo.rs:342-399: 640x490, shadows, highlight, normal maps vs the reference's
+    expected PNG with the reference's own metric and default threshold (0.001; CI under llvmpipe uses 0.015)."""
+    atlas = pkg.load_atlas()
+    reg = helpers.svo_render_test_registry(pkg, atlas)
+    w = pkg.World()
+    w.set_leaf_blocks((0, 0, 0), helpers.svo_render_test_blocks(), compact=False)
+    w.serialize()
+    s = helpers.oracle_scene(ora, w, reg)
+    p = helpers.svo_render_test_params(pkg)
+    img, cnt = s.render(pkg.to_vx_render_params(p), 640, 490)
+    img8 = ora.to_rgba8(img)[::-1]   # Framebuffer::as_image flips vertically (framebuffer.rs:107-111)
+    exp = np.asarray(Image.open(os.path.join(os.path.dirname(__file__), "golden", "graphics_svo_render_expected.png")).convert("RGBA"))
+    diff = helpers.diff_images(img8, exp)
+    print("oracle vs reference expected PNG: diff =", diff, cnt)
+    assert diff < 0.001, diff

@@ -1,0 +1,545 @@
+"""voxel-rs_b200 — B200-native (sm_100a CUDA) replacement for voxel-rs's GLSL ray-cast path.
+
+Python surface = thin ctypes bindings over two in-tree shared libraries:
+
+  libvoxelrt.so        the product: CUDA kernels behind the C ABI of include/voxelrt.h
+  libvoxelrs_host.so   C++ mirror of the reference's Rust host interfaces (graphics::Svo,
+                       PickerBatch, VoxelRegistry, world::hds::esvo, systems::worldsvo coordinates)
+
+There is NO CPU fallback: every render / raycast goes through vx_* into CUDA kernels and raises
+if the extension is missing or no GPU is present. The directory name contains a '-', so import it
+through `__graft_entry__.load_pkg()` (importlib) rather than an `import` statement.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+
+
+class NativeMissing(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------ C structs --
+
+class VxConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("svo_capacity_bytes", C.c_uint64),
+                ("max_width", C.c_uint32), ("max_height", C.c_uint32), ("max_rays", C.c_uint64)]
+
+
+class VxMaterial(C.Structure):
+    _fields_ = [("specular_pow", C.c_float), ("specular_strength", C.c_float), ("tex_top", C.c_int32),
+                ("tex_side", C.c_int32), ("tex_bottom", C.c_int32), ("tex_top_normal", C.c_int32),
+                ("tex_side_normal", C.c_int32), ("tex_bottom_normal", C.c_int32)]
+
+
+class VxRenderParams(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("fov_y_rad", C.c_float), ("aspect_ratio", C.c_float),
+                ("ambient_intensity", C.c_float), ("light_dir", C.c_float * 3), ("cam_pos", C.c_float * 3),
+                ("highlight_pos", C.c_float * 3), ("render_shadows", C.c_uint32), ("shadow_distance", C.c_float)]
+
+
+class VxShard(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world_size", C.c_uint32)]
+
+
+class VxFrameStats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("steps", C.c_uint64), ("pushes", C.c_uint64),
+                ("leaf_tests", C.c_uint64), ("tex_fetches", C.c_uint64), ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class VxStats(C.Structure):
+    _fields_ = [("used_bytes", C.c_uint64), ("capacity_bytes", C.c_uint64), ("depth", C.c_uint32)]
+
+
+class VxRange(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("length", C.c_uint64)]
+
+
+class VxDebugFrame(C.Structure):
+    _fields_ = [("t_min", C.c_float), ("ptr", C.c_uint32), ("idx", C.c_uint32), ("parent_octant_idx", C.c_uint32),
+                ("scale", C.c_int32), ("is_child", C.c_int32), ("is_leaf", C.c_int32), ("crossed_boundary", C.c_int32),
+                ("next_ptr", C.c_uint32)]
+
+    def as_tuple(self):
+        return (self.t_min, self.ptr, self.idx, self.parent_octant_idx, self.scale, self.is_child, self.is_leaf)
+
+
+class VxOctreeResult(C.Structure):
+    _fields_ = [("t", C.c_float), ("value", C.c_uint32), ("face_id", C.c_int32), ("pos", C.c_float * 3), ("uv", C.c_float * 2),
+                ("color", C.c_float * 4), ("lod", C.c_float), ("inside_voxel", C.c_uint32)]
+
+    def as_dict(self):
+        return {"t": self.t, "value": self.value, "face_id": self.face_id, "pos": tuple(self.pos), "uv": tuple(self.uv),
+                "color": tuple(self.color), "lod": self.lod, "inside_voxel": bool(self.inside_voxel)}
+
+
+class VxhRenderParams(C.Structure):
+    """graphics::svo::RenderParams (src/graphics/svo.rs:85-106)."""
+    _fields_ = [("ambient_intensity", C.c_float), ("light_dir", C.c_float * 3), ("cam_pos", C.c_float * 3),
+                ("cam_fwd", C.c_float * 3), ("cam_up", C.c_float * 3), ("fov_y_rad", C.c_float), ("aspect_ratio", C.c_float),
+                ("has_selected_voxel", C.c_int32), ("selected_voxel", C.c_float * 3), ("render_shadows", C.c_int32),
+                ("shadow_distance", C.c_float)]
+
+
+# VxPickerTask / VxPickerResult as numpy record dtypes (48 bytes each, include/voxelrt.h)
+TASK_DTYPE = np.dtype({"names": ["max_dst", "pos", "dir"], "formats": ["<f4", ("<f4", 3), ("<f4", 3)], "offsets": [0, 16, 32], "itemsize": 48})
+RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "formats": ["<f4", "<u4", ("<f4", 3), ("<f4", 3)],
+                         "offsets": [0, 4, 16, 32], "itemsize": 48})
+
+VX_FLAG_NO_L2_WINDOW = 1
+VX_FLAG_KERNEL_SIMPLE = 2
+OPT_SIMPLE, OPT_VEC, OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW = 1, 2, 3, 4, 5
+
+# every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
+VX_SYMBOLS = [
+    "vx_create", "vx_destroy", "vx_last_error", "vx_set_materials", "vx_set_textures", "vx_svo_host_mirror", "vx_svo_commit",
+    "vx_svo_set_hot_range", "vx_svo_commit_packed_device", "vx_svo_pack_dirty", "vx_stats", "vx_render", "vx_render_wait",
+    "vx_read_frame_rgba8", "vx_read_frame_rgba32f", "vx_frame_device_ptr", "vx_raycast", "vx_raycast_device", "vx_raycast_wait",
+    "vx_debug_cast", "vx_frame_stats", "vx_set_option", "vx_launch_count", "vx_build_info",
+]
+
+_lib = None
+_host = None
+
+
+def _load(name):
+    path = os.path.join(_PKG, name)
+    if not os.path.exists(path):
+        raise NativeMissing(f"{path} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                            "There is no CPU fallback.")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+def lib():
+    """libvoxelrt.so with argtypes set. Raises NativeMissing if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = _load("libvoxelrt.so")
+    P = C.c_void_p
+    L.vx_create.argtypes = [C.POINTER(VxConfig), C.POINTER(P)]; L.vx_create.restype = C.c_int
+    L.vx_destroy.argtypes = [P]; L.vx_destroy.restype = None
+    L.vx_last_error.argtypes = [P]; L.vx_last_error.restype = C.c_char_p
+    L.vx_set_materials.argtypes = [P, C.POINTER(VxMaterial), C.c_uint32]; L.vx_set_materials.restype = C.c_int
+    L.vx_set_textures.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]; L.vx_set_textures.restype = C.c_int
+    L.vx_svo_host_mirror.argtypes = [P]; L.vx_svo_host_mirror.restype = P
+    L.vx_svo_commit.argtypes = [P, C.c_float, C.POINTER(VxRange), C.c_uint32, C.c_uint64, C.c_uint32]; L.vx_svo_commit.restype = C.c_int
+    L.vx_svo_set_hot_range.argtypes = [P, C.c_uint64, C.c_uint64]; L.vx_svo_set_hot_range.restype = C.c_int
+    L.vx_svo_commit_packed_device.argtypes = [P, P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32]; L.vx_svo_commit_packed_device.restype = C.c_int
+    L.vx_svo_pack_dirty.argtypes = [P, C.POINTER(VxRange), C.c_uint32, P, C.c_uint64]; L.vx_svo_pack_dirty.restype = C.c_int64
+    L.vx_stats.argtypes = [P, C.POINTER(VxStats)]; L.vx_stats.restype = C.c_int
+    L.vx_render.argtypes = [P, C.POINTER(VxRenderParams), C.c_uint32, C.c_uint32, C.POINTER(VxShard), P]; L.vx_render.restype = C.c_int
+    L.vx_render_wait.argtypes = [P]; L.vx_render_wait.restype = C.c_int
+    L.vx_read_frame_rgba8.argtypes = [P, P]; L.vx_read_frame_rgba8.restype = C.c_int
+    L.vx_read_frame_rgba32f.argtypes = [P, P]; L.vx_read_frame_rgba32f.restype = C.c_int
+    L.vx_frame_device_ptr.argtypes = [P, C.POINTER(P), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; L.vx_frame_device_ptr.restype = C.c_int
+    L.vx_raycast.argtypes = [P, P, C.c_uint64, P]; L.vx_raycast.restype = C.c_int
+    L.vx_raycast_device.argtypes = [P, P, C.c_uint64, P]; L.vx_raycast_device.restype = C.c_int
+    L.vx_raycast_wait.argtypes = [P]; L.vx_raycast_wait.restype = C.c_int
+    L.vx_debug_cast.argtypes = [P, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_uint32, C.POINTER(VxOctreeResult),
+                                C.POINTER(VxDebugFrame), C.c_uint32, C.POINTER(C.c_uint32)]
+    L.vx_debug_cast.restype = C.c_int
+    L.vx_frame_stats.argtypes = [P, C.c_int, C.POINTER(VxFrameStats)]; L.vx_frame_stats.restype = C.c_int
+    L.vx_set_option.argtypes = [P, C.c_uint32, C.c_uint64]; L.vx_set_option.restype = C.c_int
+    L.vx_launch_count.argtypes = [P]; L.vx_launch_count.restype = C.c_uint64
+    L.vx_build_info.argtypes = []; L.vx_build_info.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def host():
+    """libvoxelrs_host.so (C++ host mirror) with argtypes set."""
+    global _host
+    if _host is not None:
+        return _host
+    lib()  # dependency, loaded RTLD_GLOBAL first
+    H = _load("libvoxelrs_host.so")
+    P, u8p, u32, u64, i32, f = C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_float
+    sig = {
+        "vxh_last_error": ([], C.c_char_p),
+        "vxh_world_new": ([u32, i32, i32, i32, u32, C.c_int], P),
+        "vxh_world_free": ([P], None),
+        "vxh_world_generate": ([P, i32, i32, C.c_int], u64),
+        "vxh_world_height_at": ([P, i32, i32], i32),
+        "vxh_world_chunk_count": ([P], u64),
+        "vxh_world_set_leaf_blocks": ([P, u32, u32, u32, u64, P, u32, C.c_uint8, C.c_int], C.c_int),
+        "vxh_world_set_leaf_dense": ([P, u32, u32, u32, u64, P, C.c_uint8], C.c_int),
+        "vxh_world_edit_block": ([P, i32, i32, i32, u32], C.c_int),
+        "vxh_world_serialize": ([P], None),
+        "vxh_world_depth": ([P], u32),
+        "vxh_world_size_bytes": ([P], u64),
+        "vxh_world_write_to": ([P, u8p], u64),
+        "vxh_world_write_changes_to": ([P, u8p, u64, C.c_int], C.c_int),
+        "vxh_world_dirty_ranges": ([P, P, u32], u32),
+        "vxh_world_root_range": ([P, C.POINTER(u64), C.POINTER(u64)], None),
+        "vxh_world_root_info": ([P, C.POINTER(u64), P], None),
+        "vxh_world_cnv_block_pos": ([P, P, P], None),
+        "vxh_world_cnv_svo_pos": ([P, P, P], None),
+        "vxh_world_cnv_chunk_pos": ([P, i32, i32, i32, P], C.c_int),
+        "vxh_calculate_lod": ([i32, i32, i32, i32, i32, i32], C.c_uint8),
+        "vxh_kat_block_octree": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P], u64),
+        "vxh_serialize_dense": ([P, C.c_uint8, P, u64, P], u64),
+        "vxh_serialize_filled": ([P, C.c_uint8, P, u64, P], u64),
+        "vxh_esvo32_new": ([], P), "vxh_esvo32_free": ([P], None),
+        "vxh_esvo32_set_leaf": ([P, u32, u32, u32, u32, C.c_int, P], None),
+        "vxh_esvo32_move_leaf": ([P, u32, u32, u32, u32, u32, P, C.POINTER(u32)], C.c_int),
+        "vxh_esvo32_remove_leaf": ([P, u32, u32, C.POINTER(u32)], C.c_int),
+        "vxh_esvo32_serialize": ([P], None),
+        "vxh_esvo32_root_info": ([P, C.POINTER(u64), P], None),
+        "vxh_esvo32_bytes": ([P, P, u64], u64),
+        "vxh_esvo32_ranges": ([P, C.c_int, P, u32], u32),
+        "vxh_esvo32_range_of": ([P, u64, C.POINTER(VxRange)], C.c_int),
+        "vxh_esvo32_clear_updated": ([P], None),
+        "vxh_esvo32_write_to": ([P, P], u64),
+        "vxh_esvo32_write_changes_to": ([P, P, u64, C.c_int], C.c_int),
+        "vxh_rangebuf_new": ([], P), "vxh_rangebuf_free": ([P], None),
+        "vxh_rangebuf_insert": ([P, u64, P, u64], u64), "vxh_rangebuf_remove": ([P, u64], None),
+        "vxh_rangebuf_bytes": ([P, P, u64], u64), "vxh_rangebuf_ranges": ([P, C.c_int, P, u32], u32),
+        "vxh_picker_serialize": ([P, u32, P, u32, P, u64], u64),
+        "vxh_picker_deserialize": ([P, u32, P, u32, P, u64, P, P], None),
+        "vxh_registry_new": ([], P), "vxh_registry_free": ([P], None),
+        "vxh_registry_add_texture": ([P, C.c_char_p, u32, u32, P], C.c_int),
+        "vxh_registry_set_mip_levels": ([P, C.c_uint8], None),
+        "vxh_registry_add_material": ([P, u32, f, f, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int], C.c_int),
+        "vxh_registry_materials": ([P, P, u32], u32),
+        "vxh_registry_textures": ([P, P, u64, P], u64),
+        "vxh_look_to_rh_inverted": ([P, P, P, P], None),
+        "vxh_svo_new": ([P, u64, u32, u32, u64, C.c_int, u32], P), "vxh_svo_free": ([P], None),
+        "vxh_svo_ctx": ([P], P),
+        "vxh_svo_update": ([P, P], C.c_int),
+        "vxh_svo_stats": ([P, P], None),
+        "vxh_svo_render": ([P, C.POINTER(VxhRenderParams), u32, u32, C.POINTER(VxShard)], C.c_int),
+        "vxh_worldsvo_render": ([P, P, C.POINTER(VxhRenderParams), u32, u32, C.POINTER(VxShard)], C.c_int),
+        "vxh_svo_raycast": ([P, P, u32, P, u32, P, P], C.c_int),
+        "vxh_worldsvo_raycast": ([P, P, P, u32, P, u32, P, P], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(H, name)
+        fn.argtypes = args
+        fn.restype = res
+    _host = H
+    return H
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class VxError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------- world --
+
+class World:
+    """systems::worldsvo::Svo's CPU half: Esvo of SerializedChunks + SVO coordinate space (+ synthetic terrain)."""
+
+    def __init__(self, radius=0, center=(0, 0, 0), seed=1, no_lod=False):
+        self.h = host().vxh_world_new(radius, center[0], center[1], center[2], seed, int(no_lod))
+        self.radius, self.center = radius, tuple(center)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            host().vxh_world_free(self.h)
+            self.h = None
+
+    def generate(self, y0=0, y1=8, threads=0):
+        return host().vxh_world_generate(self.h, y0, y1, threads or (os.cpu_count() or 1))
+
+    def set_leaf_blocks(self, svo_pos, blocks, uid=1, lod=5, compact=False):
+        """blocks: iterable of (x, y, z, id) set through Chunk::set_block on pooled storage (expand_to(5))."""
+        arr = np.ascontiguousarray(np.array(list(blocks), dtype=np.uint32).reshape(-1, 4))
+        rc = host().vxh_world_set_leaf_blocks(self.h, svo_pos[0], svo_pos[1], svo_pos[2], uid, _ptr(arr), len(arr), lod, int(compact))
+        if rc:
+            raise VxError(host().vxh_last_error().decode())
+
+    def set_leaf_dense(self, svo_pos, blocks32, uid=1, lod=5):
+        arr = np.ascontiguousarray(blocks32, dtype=np.uint32).reshape(-1)
+        assert arr.size == 32 ** 3
+        rc = host().vxh_world_set_leaf_dense(self.h, svo_pos[0], svo_pos[1], svo_pos[2], uid, _ptr(arr), lod)
+        if rc:
+            raise VxError(host().vxh_last_error().decode())
+
+    def edit_block(self, wx, wy, wz, block_id):
+        host().vxh_world_edit_block(self.h, wx, wy, wz, block_id)
+
+    def serialize(self):
+        host().vxh_world_serialize(self.h)
+
+    @property
+    def depth(self):
+        return host().vxh_world_depth(self.h)
+
+    @property
+    def size_bytes(self):
+        return host().vxh_world_size_bytes(self.h)
+
+    @property
+    def chunk_count(self):
+        return host().vxh_world_chunk_count(self.h)
+
+    def height_at(self, x, z):
+        return host().vxh_world_height_at(self.h, x, z)
+
+    def dirty_ranges(self):
+        n = host().vxh_world_dirty_ranges(self.h, None, 0)
+        arr = (VxRange * max(n, 1))()
+        host().vxh_world_dirty_ranges(self.h, arr, n)
+        return [(arr[i].offset, arr[i].length) for i in range(n)]
+
+    def root_range(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        host().vxh_world_root_range(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def root_info(self):
+        off = C.c_uint64()
+        m = (C.c_uint8 * 3)()
+        host().vxh_world_root_info(self.h, C.byref(off), m)
+        return off.value, m[0], m[1], m[2]
+
+    def gpu_buffer(self):
+        """Bytes exactly as graphics::Svo::update lays them out: f32 2^-depth, preamble, RangeBuffer (svo.rs:173-181)."""
+        buf = np.zeros(4 + 20 + self.size_bytes, dtype=np.uint8)
+        buf[:4] = np.frombuffer(np.float32(2.0 ** -self.depth).tobytes(), dtype=np.uint8)
+        n = host().vxh_world_write_to(self.h, C.c_void_p(buf.ctypes.data + 4))
+        assert n == 20 + self.size_bytes or n == 0
+        return buf
+
+    def cnv_block_pos(self, p):
+        a, o = np.array(p, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        host().vxh_world_cnv_block_pos(self.h, _ptr(a), _ptr(o))
+        return o
+
+    def cnv_svo_pos(self, p):
+        a, o = np.array(p, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        host().vxh_world_cnv_svo_pos(self.h, _ptr(a), _ptr(o))
+        return o
+
+    def cnv_chunk_pos(self, c):
+        o = np.zeros(3, dtype=np.uint32)
+        ok = host().vxh_world_cnv_chunk_pos(self.h, c[0], c[1], c[2], _ptr(o))
+        return tuple(int(v) for v in o) if ok else None
+
+
+# ---------------------------------------------------------------- registry --
+
+class Registry:
+    """graphics::svo_registry::VoxelRegistry (src/graphics/svo_registry.rs:99-165)."""
+
+    def __init__(self, mip_levels=6):
+        self.h = host().vxh_registry_new()
+        host().vxh_registry_set_mip_levels(self.h, mip_levels)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            host().vxh_registry_free(self.h)
+            self.h = None
+
+    def add_texture(self, name, rgba_top_down):
+        img = np.ascontiguousarray(rgba_top_down, dtype=np.uint8)
+        hgt, wid = img.shape[0], img.shape[1]
+        if host().vxh_registry_add_texture(self.h, name.encode(), wid, hgt, _ptr(img)):
+            raise VxError(host().vxh_last_error().decode())
+        return self
+
+    def add_material(self, block, specular=(0.0, 0.0), top=None, side=None, bottom=None, all_sides=None, with_normals=False):
+        if all_sides is not None:
+            top = side = bottom = all_sides
+        enc = lambda s: s.encode() if s is not None else None
+        host().vxh_registry_add_material(self.h, block, specular[0], specular[1], enc(top), enc(side), enc(bottom), int(with_normals))
+        return self
+
+    def materials(self):
+        n = host().vxh_registry_materials(self.h, None, 0)
+        arr = (VxMaterial * max(n, 1))()
+        host().vxh_registry_materials(self.h, arr, n)
+        return np.frombuffer(bytes(arr), dtype=np.dtype([("specular_pow", "<f4"), ("specular_strength", "<f4"), ("tex", "<i4", 6)]))[:n].copy()
+
+    def textures(self):
+        dims = (C.c_uint32 * 4)()
+        n = host().vxh_registry_textures(self.h, None, 0, dims)
+        buf = np.zeros(n, dtype=np.uint8)
+        host().vxh_registry_textures(self.h, _ptr(buf), n, dims)
+        w, h, layers, mips = dims
+        return buf.reshape(layers, h, w, 4), mips
+
+
+# the 25 textures + 13 materials of src/gamelogic/content.rs:20-60, in registration order
+CONTENT_TEXTURES = [
+    ("dirt", "dirt"), ("dirt_normal", "dirt_n"), ("grass_side", "grass_side"), ("grass_side_normal", "grass_side_n"),
+    ("grass_top", "grass_top"), ("grass_top_normal", "grass_top_n"), ("stone", "stone"), ("stone_normal", "stone_n"),
+    ("stone_bricks", "stone_bricks"), ("stone_bricks_normal", "stone_bricks_n"), ("glass", "glass"), ("gravel", "gravel"),
+    ("gravel_normal", "gravel_n"), ("sand", "sand"), ("sand_normal", "sand_n"), ("water", "water"), ("oak_log", "oak_log"),
+    ("oak_log_normal", "oak_log_n"), ("oak_log_top", "oak_log_top"), ("oak_log_top_normal", "oak_log_top_n"),
+    ("oak_leaves", "oak_leaves"), ("oak_planks", "oak_planks"), ("oak_planks_normal", "oak_planks_n"),
+    ("cobblestone", "cobblestone"), ("cobblestone_normal", "cobblestone_n"),
+]
+
+
+def content_registry(atlas):
+    """blocks::new_registry() of src/gamelogic/content.rs:20-60. atlas: {png stem: HxWx4 uint8, top-down}."""
+    r = Registry(6)
+    for name, stem in CONTENT_TEXTURES:
+        r.add_texture(name, atlas[stem])
+    r.add_material(0)
+    r.add_material(1, (14.0, 0.4), top="grass_top", side="grass_side", bottom="dirt", with_normals=True)
+    r.add_material(2, (14.0, 0.4), all_sides="dirt", with_normals=True)
+    r.add_material(3, (70.0, 0.4), all_sides="stone", with_normals=True)
+    r.add_material(4, (70.0, 0.4), all_sides="stone_bricks", with_normals=True)
+    r.add_material(5, (70.0, 0.4), all_sides="glass")
+    r.add_material(6, (70.0, 0.4), all_sides="gravel", with_normals=True)
+    r.add_material(7, (70.0, 0.4), all_sides="sand", with_normals=True)
+    r.add_material(8, (70.0, 0.4), all_sides="water")
+    r.add_material(9, (70.0, 0.4), side="oak_log", top="oak_log_top", bottom="oak_log_top", with_normals=True)
+    r.add_material(10, (70.0, 0.4), all_sides="oak_leaves")
+    r.add_material(11, (70.0, 0.4), all_sides="oak_planks", with_normals=True)
+    r.add_material(12, (70.0, 0.4), all_sides="cobblestone", with_normals=True)
+    return r
+
+
+def load_atlas(path=None):
+    """The reference's 25 block textures as committed under tests/golden/atlas.npz (see make_fixtures.py)."""
+    path = path or os.path.join(ROOT, "tests", "golden", "atlas.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+# --------------------------------------------------------------------- Svo --
+
+def render_params(cam_pos, cam_fwd, cam_up=(0, 1, 0), fov_y_deg=72.0, aspect=1.0, ambient=0.3, light_dir=None, selected_voxel=None,
+                  render_shadows=True, shadow_distance=500.0):
+    """RenderParams as gamelogic::World::render builds them (src/gamelogic/world.rs:269-283)."""
+    p = VxhRenderParams()
+    if light_dir is None:
+        l = np.float32(-1.0) / np.sqrt(np.float32(3.0))
+        light_dir = (l, l, l)
+    p.ambient_intensity = ambient
+    p.light_dir = _f3(light_dir); p.cam_pos = _f3(cam_pos); p.cam_fwd = _f3(cam_fwd); p.cam_up = _f3(cam_up)
+    p.fov_y_rad = float(np.float32(np.deg2rad(np.float32(fov_y_deg))))
+    p.aspect_ratio = aspect
+    p.has_selected_voxel = int(selected_voxel is not None)
+    p.selected_voxel = _f3(selected_voxel if selected_voxel is not None else (0, 0, 0))
+    p.render_shadows = int(render_shadows)
+    p.shadow_distance = shadow_distance
+    return p
+
+
+def to_vx_render_params(p):
+    """What graphics::Svo::render uploads as uniforms (svo.rs:197-215) — used to feed the oracle the same inputs."""
+    q = VxRenderParams()
+    eye, d, up = np.array(p.cam_pos, np.float32), np.array(p.cam_fwd, np.float32), np.array(p.cam_up, np.float32)
+    out = np.zeros(16, np.float32)
+    host().vxh_look_to_rh_inverted(_ptr(eye), _ptr(d), _ptr(up), _ptr(out))
+    q.view = (C.c_float * 16)(*out)
+    q.fov_y_rad, q.aspect_ratio, q.ambient_intensity = p.fov_y_rad, p.aspect_ratio, p.ambient_intensity
+    q.light_dir = p.light_dir; q.cam_pos = p.cam_pos
+    nan = float("nan")
+    q.highlight_pos = _f3(p.selected_voxel) if p.has_selected_voxel else _f3((nan, nan, nan))
+    q.render_shadows = p.render_shadows
+    q.shadow_distance = p.shadow_distance
+    return q
+
+
+class Svo:
+    """graphics::Svo (src/graphics/svo.rs:56-255) through the C++ host mirror and the C ABI."""
+
+    def __init__(self, registry, size_mb=10, max_width=1920, max_height=1080, max_rays=100, device=0, flags=0):
+        self.h = host().vxh_svo_new(registry.h, size_mb, max_width, max_height, max_rays, device, flags)
+        if not self.h:
+            raise VxError(host().vxh_last_error().decode())
+        self.ctx = C.c_void_p(host().vxh_svo_ctx(self.h))
+        self.width = self.height = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            host().vxh_svo_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise VxError(f"rc={rc}: {lib().vx_last_error(self.ctx).decode()} | {host().vxh_last_error().decode()}")
+
+    def set_option(self, opt, value):
+        self._check(lib().vx_set_option(self.ctx, opt, value))
+
+    def update(self, world):
+        self._check(host().vxh_svo_update(self.h, world.h))
+
+    def get_stats(self):
+        o = (C.c_uint64 * 3)()
+        host().vxh_svo_stats(self.h, o)
+        return {"used_bytes": o[0], "capacity_bytes": o[1], "depth": o[2]}
+
+    def render(self, params, width, height, shard=None, world=None):
+        """world given => systems::worldsvo::Svo::render (camera in world space, worldsvo.rs:397-409)."""
+        sh = VxShard(*shard) if shard else None
+        shp = C.byref(sh) if sh else None
+        if world is not None:
+            self._check(host().vxh_worldsvo_render(self.h, world.h, C.byref(params), width, height, shp))
+        else:
+            self._check(host().vxh_svo_render(self.h, C.byref(params), width, height, shp))
+        self.width, self.height = width, height
+
+    def wait(self):
+        self._check(lib().vx_render_wait(self.ctx))
+
+    def read_rgba32f(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._check(lib().vx_read_frame_rgba32f(self.ctx, _ptr(out)))
+        return out
+
+    def read_rgba8(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._check(lib().vx_read_frame_rgba8(self.ctx, _ptr(out)))
+        return out
+
+    def raycast(self, rays=(), aabbs=(), world=None):
+        """rays: (pos3, dir3, max_dst); aabbs: (pos3, offset3, extents3). Returns (ray results [n,8], aabb results [m,6])."""
+        r = np.ascontiguousarray(np.array(rays, dtype=np.float32).reshape(-1, 7))
+        a = np.ascontiguousarray(np.array(aabbs, dtype=np.float32).reshape(-1, 9))
+        ro, ao = np.zeros((len(r), 8), np.float32), np.zeros((len(a), 6), np.float32)
+        if world is not None:
+            self._check(host().vxh_worldsvo_raycast(self.h, world.h, _ptr(r), len(r), _ptr(a), len(a), _ptr(ro), _ptr(ao)))
+        else:
+            self._check(host().vxh_svo_raycast(self.h, _ptr(r), len(r), _ptr(a), len(a), _ptr(ro), _ptr(ao)))
+        return ro, ao
+
+    def raycast_tasks(self, tasks):
+        """Raw vx_raycast on a TASK_DTYPE array; returns a RESULT_DTYPE array."""
+        tasks = np.ascontiguousarray(tasks)
+        assert tasks.dtype == TASK_DTYPE
+        res = np.zeros(len(tasks), dtype=RESULT_DTYPE)
+        self._check(lib().vx_raycast(self.ctx, _ptr(tasks), len(tasks), _ptr(res)))
+        return res
+
+    def debug_cast(self, pos, direction, max_dst, cast_translucent, frames_cap=100):
+        res = VxOctreeResult()
+        frames = (VxDebugFrame * frames_cap)()
+        n = C.c_uint32()
+        d = np.array(direction, dtype=np.float32)
+        d = d / np.sqrt(np.float32((d * d).sum(dtype=np.float32)))   # svo_shader_tests.rs:246 dir.normalize()
+        self._check(lib().vx_debug_cast(self.ctx, C.byref(_f3(pos)), C.byref(_f3(d)), max_dst, int(cast_translucent), C.byref(res),
+                                        frames, frames_cap, C.byref(n)))
+        return res, [frames[i] for i in range(min(n.value, frames_cap))], n.value
+
+    def frame_stats(self, which=0):
+        st = VxFrameStats()
+        self._check(lib().vx_frame_stats(self.ctx, which, C.byref(st)))
+        return st.as_dict()
+
+    def launch_count(self):
+        return lib().vx_launch_count(self.ctx)

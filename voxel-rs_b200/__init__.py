@@ -178,6 +178,7 @@ def host():
         "vxh_world_write_to": ([P, u8p], u64),
         "vxh_world_write_changes_to": ([P, u8p, u64, C.c_int], C.c_int),
         "vxh_world_dirty_ranges": ([P, P, u32], u32),
+        "vxh_world_mark_all_dirty": ([P], None),
         "vxh_world_root_range": ([P, C.POINTER(u64), C.POINTER(u64)], None),
         "vxh_world_root_info": ([P, C.POINTER(u64), P], None),
         "vxh_world_cnv_block_pos": ([P, P, P], None),
@@ -297,6 +298,9 @@ class World:
         arr = (VxRange * max(n, 1))()
         host().vxh_world_dirty_ranges(self.h, arr, n)
         return [(arr[i].offset, arr[i].length) for i in range(n)]
+
+    def mark_all_dirty(self):
+        host().vxh_world_mark_all_dirty(self.h)
 
     def root_range(self):
         a, b = C.c_uint64(), C.c_uint64()

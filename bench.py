@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the voxel-rs ray-cast hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): Mrays/s of primary + shadow rays actually cast, and ms/frame, at 4K (3840x2160) on the
+generated-terrain world of the reference's default shape (radius 20 chunks, LOD rule, camera (-24,80,174), fov 72 deg,
+sun (-1,-1,-1)/sqrt3, shadows on) = BASELINE.json configs[2]. A "step" is one frame.
+
+  value        rays/s with everything resident in HBM: per step = L2 flush + vx_render (+ for N>1: NCCL broadcast of the
+               frame's dirty SVO ranges, scatter, shard pack, NCCL gather to GPU 0, unpack)
+  e2e          the same frame through the C ABI with HOST buffers: dirty ranges copied into the pinned mirror and
+               uploaded (vx_svo_commit), vx_render, RGBA8 read-back to host (vx_read_frame_rgba8)
+  roofline     algorithmic node/texel/frame bytes per launch (SURVEY §8d formula, counts from a counting launch of the
+               same frame) / mean kernel time (CUDA events on the launching stream) vs measured HBM copy bandwidth
+  cpu_baseline the CPU oracle (a port of the GLSL, NOT the reference itself) on the host cores over a bounded sample
+
+--impl reference times that same CPU port (the reference is Rust + GLSL and cannot run here: no rustc, no GL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--radius", type=int, default=20)
+    ap.add_argument("--no-lod", action="store_true")
+    ap.add_argument("--no-shadows", action="store_true")
+    ap.add_argument("--simple", action="store_true", help="one-thread-per-pixel kernels (A/B)")
+    ap.add_argument("--vec-loads", action="store_true", help="128-bit node fetches instead of 32-bit (A/B)")
+    ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
+    ap.add_argument("--no-l2-window", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--picker", type=int, default=0, help="also time N incoherent picker rays (config 4 style) and print a second line")
+    return ap.parse_args()
+
+
+def build_world(pkg, args):
+    t = time.time()
+    world = pkg.World(radius=args.radius, center=(-1, 2, 5), seed=1, no_lod=args.no_lod)
+    world.generate(0, 8)
+    world.serialize()
+    return world, time.time() - t
+
+
+def frame_params(pkg, world, args):
+    p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, 0.0, 0.0), fov_y_deg=72.0, aspect=args.width / args.height,
+                          render_shadows=not args.no_shadows)   # yaw -90 deg, pitch 0 (src/main.rs:79-98)
+    import ctypes as C
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+    q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))   # systems::worldsvo::Svo::render, worldsvo.rs:397-409
+    return pkg.to_vx_render_params(q)
+
+
+def workload_name(args):
+    return (f"generated-terrain r={args.radius} chunks{' no-LOD' if args.no_lod else ' LOD'}, {args.width}x{args.height}, "
+            f"primary{'' if args.no_shadows else '+shadow'} rays, camera (-24,80,174) fov72 (BASELINE configs[2])")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _run(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(st, pixels):
+    """B = 4*N_iter + 4*N_push + 40*N_leaf + T*N_tex + 16*pixels (node words, child pointers, leaf ptr+value+material,
+    4 B per texel read, RGBA32F store)."""
+    return 4 * st["steps"] + 4 * st["pushes"] + 40 * st["leaf_tests"] + 4 * st["tex_fetches"] + 16 * pixels
+
+
+def cpu_sample_bands(height, frac=0.1, bands=27):
+    """Row bands spread evenly over the frame (sky, horizon and ground all represented)."""
+    rows = max(1, int(height * frac / bands))
+    return [(int(i * height / bands), min(height, int(i * height / bands) + rows)) for i in range(bands)]
+
+
+def cpu_render_sample(scene, vxp, args, threads, budget_s, frac=0.1):
+    """Times the CPU oracle on row bands of the SAME frame until the budget is used. Returns (rays/s, description)."""
+    bands = cpu_sample_bands(args.height, frac)
+    out = np.zeros((args.height, args.width, 4), np.float32)
+    rays, t_used, rows = 0, 0.0, 0
+    t_start = time.time()
+    for y0, y1 in bands:
+        t0 = time.time()
+        _, cnt = scene.render(vxp, args.width, args.height, y0, y1, threads=threads, out=out)
+        t_used += time.time() - t0
+        rays += cnt["primary_rays"] + cnt["shadow_rays"]
+        rows += y1 - y0
+        if time.time() - t_start > budget_s:
+            break
+    return rays / t_used, f"{rows} of {args.height} rows in bands spread over the frame ({rays} rays, {t_used:.1f} s)", rays, t_used
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference shaders (oracle/), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg, ora = graft.load_pkg(), graft.load_oracle()
+    world, _ = build_world(pkg, args)
+    reg = pkg.content_registry(pkg.load_atlas())
+    tex, mips = reg.textures()
+    scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+    vxp = frame_params(pkg, world, args)
+    threads = ora.max_threads()
+    per_step_budget = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_render_sample(scene, vxp, args, threads, per_step_budget)
+    tot_rays, tot_t, desc = 0, 0.0, ""
+    for _ in range(args.steps):
+        _, desc, rays, t = cpu_render_sample(scene, vxp, args, threads, per_step_budget)
+        tot_rays += rays; tot_t += t
+    value = tot_rays / tot_t / 1e6
+    full_frame_rays = None
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args), "note": "CPU port of the reference GLSL (oracle/), not the Rust+OpenGL "
+                                        "reference itself: no rustc / Mesa in this image (llvmpipe: not measurable on this box)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": "per step: " + desc},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the ray-cast path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world_size
+    dev = torch.device("cuda", local_rank)
+
+    graft.build()
+    pkg = graft.load_pkg()
+    world, gen_s = build_world(pkg, args)
+    reg = pkg.content_registry(pkg.load_atlas())
+    W, H = args.width, args.height
+    size_mb = int(world.size_bytes // 1_000_000 + 64)
+    svo = pkg.Svo(reg, size_mb=size_mb, max_width=W, max_height=H, max_rays=max(args.picker, 1024), device=local_rank,
+                  flags=(pkg.VX_FLAG_NO_L2_WINDOW if args.no_l2_window else 0))
+    # a real (non-legacy) torch stream shared with the library: torch ops, NCCL collectives and vx_* kernels order on it without
+    # host syncs, and torch.cuda.Event timings on it see the library's kernels (stream 0 would mean "keep the library's own streams")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
+    svo.set_option(pkg.OPT_SIMPLE, int(args.simple))
+    svo.set_option(pkg.OPT_VEC, int(args.vec_loads))
+    if args.refill:
+        svo.set_option(pkg.OPT_REFILL, args.refill)
+    if args.ctas_per_sm:
+        svo.set_option(pkg.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    svo.update(world)
+    vxp = frame_params(pkg, world, args)
+    shard = (rank, n_gpus)
+    pixels = W * H
+
+    # scripted per-frame dirty set: 4 chunk-sized ranges (half-full LOD-5 chunk ~ 112 KB) + the world root
+    root_off, root_len = world.root_range()
+    chunk_len = 2336 * 48
+    stride = max(chunk_len, ((world.size_bytes - chunk_len) // 4) // 48 * 48)
+    dirty = [(i * stride, min(chunk_len, world.size_bytes - i * stride)) for i in range(4) if i * stride < world.size_bytes]
+    dirty.append((root_off, root_len))
+    dirty_bytes = sum(l for _, l in dirty) + 24
+    octree_scale = float(np.float32(2.0 ** -world.depth))
+    packed_n = svo.pack_dirty(dirty, None)
+    packed_host = torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)
+    packed_dev = torch.empty(packed_n, dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    shard_bytes = [svo.shard_bytes(W, H, (r, n_gpus)) for r in range(n_gpus)]
+    if n_gpus > 1:
+        my_pack = torch.empty(shard_bytes[rank], dtype=torch.uint8, device=dev)
+        recv = [torch.empty(shard_bytes[r], dtype=torch.uint8, device=dev) for r in range(n_gpus)] if rank == 0 else None
+
+    def flush():
+        if not args.no_flush:
+            flush_buf.fill_(1)
+
+    def step_resident():
+        """One frame with every input already in HBM."""
+        flush()
+        if n_gpus > 1:
+            # per-frame changed-chunk ranges: rank 0's packed dirty set -> all GPUs over NVLink, applied by a scatter kernel
+            dist.broadcast(packed_dev, src=0)
+            svo.commit_packed_device(packed_dev.data_ptr(), len(dirty), dirty_bytes, world.size_bytes, world.depth)
+        svo.render_raw(vxp, W, H, shard=shard)
+        if n_gpus > 1:
+            svo.pack_shard(shard, my_pack.data_ptr())
+            # tiles to GPU 0 (grouped NCCL send/recv)
+            if rank == 0:
+                ops = [dist.P2POp(dist.irecv, recv[r], r) for r in range(1, n_gpus)]
+            else:
+                ops = [dist.P2POp(dist.isend, my_pack, 0)]
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+            if rank == 0:
+                for r in range(1, n_gpus):
+                    svo.unpack_shard((r, n_gpus), recv[r].data_ptr())
+
+    frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    mirror = svo.host_mirror(24 + world.size_bytes)
+    staged = [bytes(mirror[24 + o:24 + o + l]) for o, l in dirty]
+
+    def step_e2e():
+        """The same frame through the C ABI with host buffers: dirty bytes -> pinned mirror -> H2D, render, RGBA8 -> host."""
+        flush()
+        if rank == 0:
+            for (o, l), b in zip(dirty, staged):   # the host-side serializer writing its changes (write_changes_to)
+                mirror[24 + o:24 + o + l] = np.frombuffer(b, np.uint8)
+        if n_gpus > 1:
+            if rank == 0:
+                svo.pack_dirty(dirty, packed_host.numpy())
+                packed_dev.copy_(packed_host, non_blocking=True)
+            dist.broadcast(packed_dev, src=0)
+            svo.commit_packed_device(packed_dev.data_ptr(), len(dirty), dirty_bytes, world.size_bytes, world.depth)
+        else:
+            svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
+        svo.render_raw(vxp, W, H, shard=shard)
+        if n_gpus > 1:
+            svo.pack_shard(shard, my_pack.data_ptr())
+            if rank == 0:
+                ops = [dist.P2POp(dist.irecv, recv[r], r) for r in range(1, n_gpus)]
+            else:
+                ops = [dist.P2POp(dist.isend, my_pack, 0)]
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+            if rank == 0:
+                for r in range(1, n_gpus):
+                    svo.unpack_shard((r, n_gpus), recv[r].data_ptr())
+        if rank == 0:
+            import ctypes as C
+            svo._check(pkg.lib().vx_read_frame_rgba8(svo.ctx, C.c_void_p(frame8.data_ptr())))
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, per_step_events=False):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        l0 = svo.launch_count()
+        evs = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if n_gpus > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, svo.launch_count() - l0, t0, t1
+
+    # ---- counting launch (same frame, counters on): rays, steps, pushes, leaf tests, texels of THIS rank's shard
+    svo.set_option(pkg.OPT_COUNT, 1)
+    svo.render_raw(vxp, W, H, shard=shard)
+    st = svo.frame_stats(0)
+    svo.set_option(pkg.OPT_COUNT, 0)
+    rays_local = st["primary_rays"] + st["shadow_rays"]
+    if n_gpus > 1:
+        t = torch.tensor([rays_local, st["primary_rays"], st["shadow_rays"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        rays_total, prim_total, shad_total = (int(v) for v in t.tolist())
+    else:
+        rays_total, prim_total, shad_total = rays_local, st["primary_rays"], st["shadow_rays"]
+
+    # ---- kernel-only timing of the dominant kernel (events on its stream, L2 flushed before each launch)
+    kms = []
+    for i in range(args.warmup + min(args.steps, 10)):
+        flush()
+        svo.render_raw(vxp, W, H, shard=shard)
+        if i >= args.warmup:
+            kms.append(svo.frame_stats(0)["kernel_ms"])
+    kernel_ms = float(np.mean(kms))
+
+    # ---- the timed region
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches, t0, t1 = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = ms_total / args.steps
+    value = rays_total / (ms_per_step * 1e-3) / 1e6
+
+    e2e = None
+    if not args.skip_e2e:
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
+        e2e = {"value": rays_total / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16), "d2h_bytes_per_step": int(W * H * 4),
+               "path": "host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render -> vx_read_frame_rgba8 (D2H to pinned host)"}
+
+    if rank != 0:
+        if n_gpus > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    alg_bytes = algorithmic_bytes(st, pixels // n_gpus if n_gpus > 1 else pixels)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("render_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth),
+            "chunks": int(world.chunk_count), "rays_per_frame": rays_total, "primary_rays": prim_total, "shadow_rays": shad_total,
+            "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
+            "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 256 MiB device memset inside the timed region",
+            "kernel": "simple" if args.simple else "persistent", "node_loads": "128-bit" if args.vec_loads else "32-bit", "ctas_per_sm": args.ctas_per_sm or 6, "refill_threshold": args.refill or 24,
+            "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
+            "multi_gpu_step": "NCCL broadcast of packed dirty ranges + scatter, shard render, pack, NCCL send/recv to GPU 0, unpack" if n_gpus > 1 else None,
+        },
+        "frame_ms": ms_per_step,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel": "render_simple_kernel" if args.simple else "render_persistent_kernel",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "counts": {k: int(st[k]) for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")},
+                     "note": "latency/divergence-bound pointer chasing: the SVO is L2-resident after first touch, so the HBM fraction is small "
+                             "by construction (SURVEY §8d); see profiles/ for L2 hit rate and warp execution efficiency"},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.skip_cpu and n_gpus == 1:
+        ora = graft.load_oracle()
+        tex, mips = reg.textures()
+        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+        threads = ora.max_threads()
+        rps, desc, _, _ = cpu_render_sample(scene, vxp, args, threads, args.cpu_seconds, frac=1.0)
+        line["cpu_baseline"] = {"value": rps / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
+    print(json.dumps(line), flush=True)
+
+    if args.picker:
+        picker_line(pkg, svo, world, args, torch, stream, peak, peak_src)
+    if n_gpus > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def picker_line(pkg, svo, world, args, torch, stream, peak, peak_src):
+    """Config-4 style divergence stress: N random-origin random-direction picker rays, device-resident (second JSON line)."""
+    n = args.picker
+    rng = np.random.default_rng(0)
+    size = 32.0 * (2 * args.radius + 1)
+    tasks = np.zeros(n, dtype=pkg.TASK_DTYPE)
+    tasks["max_dst"] = -1.0
+    tasks["pos"] = rng.uniform(0, size, (n, 3)).astype(np.float32)
+    tasks["pos"][:, 1] = rng.uniform(32.0 * args.radius + 60, 32.0 * args.radius + 200, n).astype(np.float32)   # above the terrain
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    tasks["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    t_dev = torch.from_numpy(tasks.view(np.uint8).reshape(-1)).cuda()
+    r_dev = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    svo.set_option(pkg.OPT_COUNT, 1)
+    svo.raycast_device(t_dev.data_ptr(), n, r_dev.data_ptr())
+    st = svo.frame_stats(1)
+    svo.set_option(pkg.OPT_COUNT, 0)
+    ms = []
+    for i in range(args.warmup + args.steps):
+        svo.raycast_device(t_dev.data_ptr(), n, r_dev.data_ptr())
+        if i >= args.warmup:
+            ms.append(svo.frame_stats(1)["kernel_ms"])
+    k = float(np.mean(ms))
+    alg = 4 * st["steps"] + 4 * st["pushes"] + 8 * st["leaf_tests"] + 96 * n
+    print(json.dumps({"metric": "Mrays/s (picker, incoherent)", "value": n / (k * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": k, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{n} random picker rays over the r={args.radius} world (BASELINE configs[3] style)"},
+                      "roofline": {"bound": "hbm", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": alg / (k * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                   "counts": {kk: int(st[kk]) for kk in ("steps", "pushes", "leaf_tests")}}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -259,6 +259,20 @@ int vx_debug_cast(VxCtx* ctx, const float pos[3], const float dir[3], float max_
                   uint32_t cast_translucent, VxOctreeResult* result,
                   VxDebugFrame* frames, uint32_t frames_cap, uint32_t* n_frames);
 
+/* ---- multi-GPU plumbing (no reference counterpart: the reference is single-GPU) ----
+ * One process per GPU. Each rank renders its VxShard into its own full-size framebuffer; the shard's
+ * pixels are then packed into a contiguous device buffer ([owned macro block][16 rows][32 px] RGBA32F),
+ * moved to rank 0 by the caller's collective (NCCL over NVLink) and unpacked into rank 0's framebuffer. */
+uint64_t vx_shard_bytes(uint32_t width, uint32_t height, const VxShard* shard);   /* packed size of one shard */
+int vx_pack_shard(VxCtx* ctx, const VxShard* shard, void* packed_dev);            /* frame -> packed, on the render stream */
+int vx_unpack_shard(VxCtx* ctx, const VxShard* shard, const void* packed_dev);    /* packed -> frame, on the render stream */
+
+/* Run this context's work on caller-owned CUDA streams (cudaStream_t passed as void*) so that it orders
+ * with the caller's collectives without host synchronisation. NULL keeps the library's own stream. */
+int vx_set_streams(VxCtx* ctx, void* render_stream, void* upload_stream, void* picker_stream);
+/* The cudaStream_t a kind of work is issued on: 0 = render, 1 = upload, 2 = picker. */
+int vx_stream(VxCtx* ctx, int which, void** out_stream);
+
 /* Counters + kernel time of the last vx_render (which=0) or vx_raycast* (which=1). Implies a wait. */
 int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
 

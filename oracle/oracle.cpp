@@ -25,8 +25,11 @@
 // expected PNG.
 //
 // Numeric convention (shared with the CUDA kernels, see DESIGN.md "Numerics"): IEEE-754 binary32,
-// round-to-nearest-even, NO fused multiply-add (build with -ffp-contract=off), IEEE division and
-// sqrt, min/max as the GLSL spec writes them (min(x,y) = y<x ? y : x; max(x,y) = x<y ? y : x),
+// round-to-nearest-even, no compiler-chosen contraction (build with -ffp-contract=off); a fused
+// multiply-add is used in exactly the three places where the shader's own comment asks for one
+// ("calculating the next interception distance is one FMA-operation per axis", svo.esvo.glsl:97-99):
+// t_corner (:159), the leaf entry corner (:197) and t_center (:275) — written as explicit fmaf().
+// IEEE division and sqrt, min/max as the GLSL spec writes them (min(x,y) = y<x ? y : x; max(x,y) = x<y ? y : x),
 // exp2(integer) built from exponent bits, findMSB = 31 - clz.
 #include <cmath>
 #include <cstdint>
@@ -262,7 +265,7 @@ static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bo
         if (max_dst >= 0 && t_min > max_dst) return;                    // :153-156
         if (cnt) cnt->steps++;
 
-        vec3 t_corner = v3(pos.x * t_coef.x - t_bias.x, pos.y * t_coef.y - t_bias.y, pos.z * t_coef.z - t_bias.z);  // :159
+        vec3 t_corner = v3(fmaf(pos.x, t_coef.x, -t_bias.x), fmaf(pos.y, t_coef.y, -t_bias.y), fmaf(pos.z, t_coef.z, -t_bias.z));  // :159 (FMA, :97-99)
         float tc_max = gl_min(gl_min(t_corner.x, t_corner.y), t_corner.z);   // :161
 
         uint32_t octant_idx = (uint32_t)(idx ^ octant_mask);            // :164
@@ -291,8 +294,8 @@ static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bo
                 next_ptr = next_ptr + 4 + octant_idx;                   // :191
                 uint32_t value = s.desc(next_ptr);                      // :194
 
-                vec3 tcn = v3((pos.x + scale_exp2) * t_coef.x - t_bias.x, (pos.y + scale_exp2) * t_coef.y - t_bias.y,
-                              (pos.z + scale_exp2) * t_coef.z - t_bias.z);       // :197
+                vec3 tcn = v3(fmaf(pos.x + scale_exp2, t_coef.x, -t_bias.x), fmaf(pos.y + scale_exp2, t_coef.y, -t_bias.y),
+                              fmaf(pos.z + scale_exp2, t_coef.z, -t_bias.z));    // :197 (FMA)
                 float tc_min = gl_max(gl_max(tcn.x, tcn.y), tcn.z);     // :199
 
                 vec3 p = pos;                                           // :202-205
@@ -344,8 +347,8 @@ static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bo
                 last_leaf_value = value;
             } else {
                 float half_scale = scale_exp2 * 0.5f;                   // :274
-                vec3 t_center = v3(half_scale * t_coef.x + t_corner.x, half_scale * t_coef.y + t_corner.y,
-                                   half_scale * t_coef.z + t_corner.z);   // :275
+                vec3 t_center = v3(fmaf(half_scale, t_coef.x, t_corner.x), fmaf(half_scale, t_coef.y, t_corner.y),
+                                   fmaf(half_scale, t_coef.z, t_corner.z));   // :275 (FMA)
                 float tv_max = gl_min(t_max, tc_max);                   // :278
                 if (t_min <= tv_max) {                                  // :280  phase: PUSH
                     if (cnt) cnt->pushes++;

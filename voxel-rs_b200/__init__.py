@@ -95,7 +95,7 @@ RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "for
 
 VX_FLAG_NO_L2_WINDOW = 1
 VX_FLAG_KERNEL_SIMPLE = 2
-OPT_SIMPLE, OPT_VEC, OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW = 1, 2, 3, 4, 5
+OPT_SIMPLE, OPT_VEC, OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL = 1, 2, 3, 4, 5, 6
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
 VX_SYMBOLS = [
@@ -103,6 +103,7 @@ VX_SYMBOLS = [
     "vx_svo_set_hot_range", "vx_svo_commit_packed_device", "vx_svo_pack_dirty", "vx_stats", "vx_render", "vx_render_wait",
     "vx_read_frame_rgba8", "vx_read_frame_rgba32f", "vx_frame_device_ptr", "vx_raycast", "vx_raycast_device", "vx_raycast_wait",
     "vx_debug_cast", "vx_frame_stats", "vx_set_option", "vx_launch_count", "vx_build_info",
+    "vx_shard_bytes", "vx_pack_shard", "vx_unpack_shard", "vx_set_streams", "vx_stream",
 ]
 
 _lib = None
@@ -150,6 +151,11 @@ def lib():
     L.vx_set_option.argtypes = [P, C.c_uint32, C.c_uint64]; L.vx_set_option.restype = C.c_int
     L.vx_launch_count.argtypes = [P]; L.vx_launch_count.restype = C.c_uint64
     L.vx_build_info.argtypes = []; L.vx_build_info.restype = C.c_char_p
+    L.vx_shard_bytes.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(VxShard)]; L.vx_shard_bytes.restype = C.c_uint64
+    L.vx_pack_shard.argtypes = [P, C.POINTER(VxShard), P]; L.vx_pack_shard.restype = C.c_int
+    L.vx_unpack_shard.argtypes = [P, C.POINTER(VxShard), P]; L.vx_unpack_shard.restype = C.c_int
+    L.vx_set_streams.argtypes = [P, P, P, P]; L.vx_set_streams.restype = C.c_int
+    L.vx_stream.argtypes = [P, C.c_int, C.POINTER(P)]; L.vx_stream.restype = C.c_int
     _lib = L
     return L
 
@@ -539,6 +545,65 @@ class Svo:
         self._check(lib().vx_debug_cast(self.ctx, C.byref(_f3(pos)), C.byref(_f3(d)), max_dst, int(cast_translucent), C.byref(res),
                                         frames, frames_cap, C.byref(n)))
         return res, [frames[i] for i in range(min(n.value, frames_cap))], n.value
+
+    # ---- raw C-ABI helpers used by bench.py and the multi-GPU path ----
+    def render_raw(self, vx_params, width, height, shard=None, out=None):
+        """vx_render with an already-built VxRenderParams (no host-mirror work in the call)."""
+        sh = VxShard(*shard) if shard else None
+        self._check(lib().vx_render(self.ctx, C.byref(vx_params), width, height, C.byref(sh) if sh else None,
+                                    _ptr(out) if out is not None else None))
+        self.width, self.height = width, height
+
+    def commit(self, octree_scale, ranges, used_bytes, depth):
+        """vx_svo_commit: ranges = [(offset, length)] relative to the RangeBuffer, bytes already in the host mirror."""
+        arr = (VxRange * max(len(ranges), 1))(*[VxRange(o, l) for o, l in ranges])
+        self._check(lib().vx_svo_commit(self.ctx, octree_scale, arr, len(ranges), used_bytes, depth))
+
+    def host_mirror(self, nbytes):
+        """numpy view of the first nbytes of the pinned host mirror of the GPU world buffer."""
+        p = lib().vx_svo_host_mirror(self.ctx)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def pack_dirty(self, ranges, out):
+        arr = (VxRange * max(len(ranges), 1))(*[VxRange(o, l) for o, l in ranges])
+        n = lib().vx_svo_pack_dirty(self.ctx, arr, len(ranges), _ptr(out) if out is not None else None, out.nbytes if out is not None else 0)
+        if n < 0:
+            self._check(int(n))
+        return int(n)
+
+    def commit_packed_device(self, dev_ptr, n_ranges, payload_bytes, used_bytes, depth):
+        self._check(lib().vx_svo_commit_packed_device(self.ctx, C.c_void_p(dev_ptr), n_ranges, payload_bytes, used_bytes, depth))
+
+    def shard_bytes(self, width, height, shard):
+        sh = VxShard(*shard)
+        return lib().vx_shard_bytes(width, height, C.byref(sh))
+
+    def pack_shard(self, shard, dev_ptr):
+        sh = VxShard(*shard)
+        self._check(lib().vx_pack_shard(self.ctx, C.byref(sh), C.c_void_p(dev_ptr)))
+
+    def unpack_shard(self, shard, dev_ptr):
+        sh = VxShard(*shard)
+        self._check(lib().vx_unpack_shard(self.ctx, C.byref(sh), C.c_void_p(dev_ptr)))
+
+    def set_streams(self, render=None, upload=None, picker=None):
+        self._check(lib().vx_set_streams(self.ctx, C.c_void_p(render), C.c_void_p(upload), C.c_void_p(picker)))
+
+    def stream(self, which=0):
+        p = C.c_void_p()
+        self._check(lib().vx_stream(self.ctx, which, C.byref(p)))
+        return p.value
+
+    def frame_device_ptr(self):
+        p, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(lib().vx_frame_device_ptr(self.ctx, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def raycast_device(self, tasks_ptr, n, results_ptr):
+        self._check(lib().vx_raycast_device(self.ctx, C.c_void_p(tasks_ptr), n, C.c_void_p(results_ptr)))
+
+    def raycast_wait(self):
+        self._check(lib().vx_raycast_wait(self.ctx))
 
     def frame_stats(self, which=0):
         st = VxFrameStats()

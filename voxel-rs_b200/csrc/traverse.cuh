@@ -5,18 +5,24 @@
 //   trace_ray         assets/shaders/world.glsl:27-90
 //   get_sky_color     assets/shaders/world.glsl:92-108
 //   textureLod state  src/graphics/texture_array.rs:200-203
-// Not a transliteration: the traversal is a per-lane step machine (ray_init / ray_step) so that
-// persistent warps can swap rays in and out between steps, and the node state is kept as
-// (rec, desc) = (record of the CURRENT octant, 16-bit child/leaf masks of its children) instead of
-// the shader's (ptr, parent_octant_idx). (rec, desc) is a pure function of (ptr, parent_octant_idx)
-// over an immutable buffer, so PUSH/POP/HIT visit exactly the same nodes in exactly the same
-// iterations, but every iteration that is not a PUSH or a leaf test runs without touching memory
-// (the shader re-reads its descriptor word each iteration, svo.esvo.glsl:168), and a PUSH issues its
-// two loads (child masks + child pointer) independently instead of back to back.
+// Not a transliteration:
+//  * the traversal is a per-lane step machine (ray_init / ray_step) that persistent warps drive in
+//    lock-step, swapping finished rays for new ones between steps;
+//  * ray_step only walks the tree (PUSH / ADVANCE / POP). When it reaches a leaf candidate it returns
+//    RAY_LEAF and the caller evaluates the leaf (value, face, uv, texture, translucency) OUTSIDE the
+//    hot loop, where the lanes of a warp that sit on a leaf do it together; a rejected (translucent)
+//    leaf re-enters the same iteration at its ADVANCE phase (`after_leaf`);
+//  * node state is (rec, desc) = (record of the CURRENT octant, 16-bit child/leaf masks of its
+//    children) instead of the shader's (ptr, parent_octant_idx). It is a pure function of
+//    (ptr, parent_octant_idx) over an immutable buffer, so PUSH/POP/HIT visit exactly the same nodes
+//    in exactly the same iterations, but an iteration that is not a PUSH or a leaf test touches no
+//    memory (the shader re-reads its descriptor word every iteration, svo.esvo.glsl:168), and a
+//    PUSH issues its two loads (child masks + child pointer) independently instead of back to back.
 //
-// Numerics (DESIGN.md "Numerics"): this TU is compiled with --fmad=false; all float ops are IEEE
-// single, round-to-nearest, in the operation order of the shader, so geometry results are bit-exact
-// against oracle/oracle.cpp.
+// Numerics (DESIGN.md "Numerics"): this TU is compiled with --fmad=false; float ops are IEEE single,
+// round-to-nearest, in the shader's operation order, with an explicit fused multiply-add in exactly the
+// three places the shader's comment asks for one (svo.esvo.glsl:97-99): t_corner (:159), the leaf
+// entry corner (:197) and t_center (:275). Geometry results are bit-exact against oracle/oracle.cpp.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -27,15 +33,27 @@ namespace vx {
 #define VX_MAX_SCALE 23
 #define VX_EPSILON 0.00000011920929f
 
-// GLSL min/max as specified (min(x,y) = y<x ? y : x), to pin NaN/-0 behaviour on both sides.
+// GLSL min/max as specified (min(x,y) = y<x ? y : x); used where a NaN / signed-zero choice could reach an output.
 __device__ __forceinline__ float gl_min(float x, float y) { return (y < x) ? y : x; }
 __device__ __forceinline__ float gl_max(float x, float y) { return (x < y) ? y : x; }
 __device__ __forceinline__ float gl_clamp(float x, float lo, float hi) { return gl_min(gl_max(x, lo), hi); }
 __device__ __forceinline__ float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+// Inside the traversal the t values are finite and only ever compared, so the single-instruction FMNMX gives the
+// same decisions as the GLSL form (they differ only in which zero / NaN is returned).
+__device__ __forceinline__ float tmin2(float x, float y) { return fminf(x, y); }
+__device__ __forceinline__ float tmax2(float x, float y) { return fmaxf(x, y); }
 
 struct Material {   // = VxMaterial / svo.glsl:48-59
     float specular_pow, specular_strength;
     int tex_top, tex_side, tex_bottom, tex_top_normal, tex_side_normal, tex_bottom_normal;
+};
+
+// Texture array description, kept in device memory so that the (single, out-of-line) sampler can take a pointer.
+struct TexInfo {
+    const uint32_t* texels;  // RGBA8 texels, all mip levels of all layers; level l starts at off[l]
+    uint32_t w, h, layers, levels;
+    uint32_t off[16];
+    unsigned long long opaque_layers;   // bit L set: every texel of every level of layer L has alpha > 0 (L < 64)
 };
 
 // Everything a kernel needs to read the scene. Passed by value as a kernel parameter.
@@ -44,9 +62,7 @@ struct Scene {
     uint32_t desc_words;                 // capacity in words (loads are clamped to it)
     const Material* __restrict__ materials;
     uint32_t n_materials;
-    const uint32_t* __restrict__ texels; // RGBA8 texels, all mip levels of all layers; level l at tex_off[l]
-    uint32_t tex_w, tex_h, tex_layers, tex_levels;
-    uint32_t tex_off[16];
+    const TexInfo* __restrict__ tex;
     uint32_t stack_levels;               // entries of the per-thread traversal stack (= SVO depth + 1, <= 23)
 };
 
@@ -68,7 +84,32 @@ struct Stack {
     }
 };
 
-enum : int { RAY_CONTINUE = 0, RAY_HIT = 1, RAY_MISS = 2 };
+// Shared-memory scratch of one CTA: traversal stacks, the unorm8 -> float table and per-thread cold state.
+struct Smem {
+    Stack stack;
+    const float* unorm;   // unorm[b] = b / 255.0f (IEEE division done once per CTA instead of once per channel fetch)
+    float* cold;          // COLD_WORDS floats per thread, [k * blockDim.x + tid]
+};
+#define VX_COLD_WORDS 8
+__host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, uint32_t threads) {
+    return ((size_t)3 * stack_levels * threads + 256 + (size_t)VX_COLD_WORDS * threads) * 4;
+}
+__device__ __forceinline__ Smem make_smem(const Scene& s, uint32_t* base) {
+    Smem m;
+    const uint32_t n = blockDim.x;
+    m.stack.stride = n; m.stack.levels = s.stack_levels;
+    m.stack.rec = base;
+    m.stack.desc = base + (size_t)s.stack_levels * n;
+    m.stack.t_max = reinterpret_cast<float*>(base + 2 * (size_t)s.stack_levels * n);
+    float* lut = reinterpret_cast<float*>(base + 3 * (size_t)s.stack_levels * n);
+    for (uint32_t i = threadIdx.x; i < 256; i += n) lut[i] = (float)i / 255.0f;
+    m.unorm = lut;
+    m.cold = lut + 256;
+    __syncthreads();
+    return m;
+}
+
+enum : int { RAY_CONTINUE = 0, RAY_LEAF = 1, RAY_MISS = 2 };
 
 // Per-ray registers.
 struct Ray {
@@ -81,8 +122,7 @@ struct Ray {
     float scale_exp2;
     float max_dst;            // already scaled; < 0 = unlimited
     int scale;
-    int idx;
-    int octant_mask;
+    int idx;                  // bits 0-2: idx, bits 4-6: octant_mask
     int steps;
     uint32_t rec, desc;
     uint32_t last_leaf_value;
@@ -90,15 +130,13 @@ struct Ray {
     uint32_t inside_voxel;
 };
 
-// Result of an accepted leaf (OctreeResult, svo.glsl:31-40)
-struct Hit {
-    float t;
+// Geometry of a leaf candidate (svo.esvo.glsl:190-224, 233)
+struct Leaf {
     uint32_t value;
     int face_id;
-    float posx, posy, posz;
     float u, v;
-    float r, g, b, a;
-    float lod;
+    float dst;
+    float qx, qy, qz, se;   // un-mirrored voxel corner and edge length in [1,2) space
 };
 
 __device__ __forceinline__ uint32_t ld_desc(const Scene& s, uint32_t i) {
@@ -148,50 +186,50 @@ __device__ __forceinline__ int ifloor_clamped(float x) {
 __device__ __forceinline__ int imod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
 __device__ __forceinline__ int iclamp(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
 
-__device__ __forceinline__ float4 fetch_texel(const Scene& s, uint32_t level, int layer, int i, int j) {
-    uint32_t wl = s.tex_w >> level, hl = s.tex_h >> level;
-    wl = wl ? wl : 1; hl = hl ? hl : 1;
-    uint32_t t = __ldg(s.texels + s.tex_off[level] + ((uint32_t)layer * hl + (uint32_t)j) * wl + (uint32_t)i);
-    return make_float4((float)(t & 0xffu) / 255.0f, (float)((t >> 8) & 0xffu) / 255.0f, (float)((t >> 16) & 0xffu) / 255.0f,
-                       (float)(t >> 24) / 255.0f);
+__device__ __forceinline__ float4 fetch_texel(const TexInfo* ti, const float* unorm, uint32_t level, uint32_t wl, uint32_t hl, int layer, int i, int j) {
+    const uint32_t t = __ldg(ti->texels + ti->off[level] + ((uint32_t)layer * hl + (uint32_t)j) * wl + (uint32_t)i);
+    return make_float4(unorm[t & 0xffu], unorm[(t >> 8) & 0xffu], unorm[(t >> 16) & 0xffu], unorm[t >> 24]);
 }
 
-__device__ __forceinline__ float4 sample_linear(const Scene& s, uint32_t level, int layer, float u, float v) {
-    int wl = (int)(s.tex_w >> level), hl = (int)(s.tex_h >> level);
+__device__ __forceinline__ float4 sample_linear(const TexInfo* ti, const float* unorm, uint32_t level, int layer, float u, float v) {
+    int wl = (int)(ti->w >> level), hl = (int)(ti->h >> level);
     wl = wl ? wl : 1; hl = hl ? hl : 1;
-    float uu = u * (float)wl - 0.5f, vv = v * (float)hl - 0.5f;
-    int i0 = ifloor_clamped(uu), j0 = ifloor_clamped(vv);
+    const float uu = u * (float)wl - 0.5f, vv = v * (float)hl - 0.5f;
+    const int i0 = ifloor_clamped(uu), j0 = ifloor_clamped(vv);
     float a = uu - floorf(uu), b = vv - floorf(vv);
     if (!(a == a)) a = 0.0f;
     if (!(b == b)) b = 0.0f;
-    int i0c = iclamp(i0, 0, wl - 1), i1c = iclamp(i0 + 1, 0, wl - 1);   // WRAP_S clamp
-    int j0w = imod(j0, hl), j1w = imod(j0 + 1, hl);                      // WRAP_T repeat
-    float4 t00 = fetch_texel(s, level, layer, i0c, j0w), t10 = fetch_texel(s, level, layer, i1c, j0w);
-    float4 t01 = fetch_texel(s, level, layer, i0c, j1w), t11 = fetch_texel(s, level, layer, i1c, j1w);
+    const int i0c = iclamp(i0, 0, wl - 1), i1c = iclamp(i0 + 1, 0, wl - 1);   // WRAP_S clamp
+    const int j0w = imod(j0, hl), j1w = imod(j0 + 1, hl);                      // WRAP_T repeat
+    const float4 t00 = fetch_texel(ti, unorm, level, wl, hl, layer, i0c, j0w), t10 = fetch_texel(ti, unorm, level, wl, hl, layer, i1c, j0w);
+    const float4 t01 = fetch_texel(ti, unorm, level, wl, hl, layer, i0c, j1w), t11 = fetch_texel(ti, unorm, level, wl, hl, layer, i1c, j1w);
     return make_float4(mixf(mixf(t00.x, t10.x, a), mixf(t01.x, t11.x, a), b), mixf(mixf(t00.y, t10.y, a), mixf(t01.y, t11.y, a), b),
                        mixf(mixf(t00.z, t10.z, a), mixf(t01.z, t11.z, a), b), mixf(mixf(t00.w, t10.w, a), mixf(t01.w, t11.w, a), b));
 }
 
 // textureLod with MIN=LINEAR_MIPMAP_LINEAR, MAG=NEAREST: lod <= 0 -> NEAREST level 0, else trilinear.
-__device__ __forceinline__ float4 texture_lod(const Scene& s, float u, float v, int tex_id, float lod, unsigned long long& fetches) {
-    int layer = iclamp(tex_id, 0, (int)s.tex_layers - 1);
+// Deliberately ONE out-of-line copy: it is called a handful of times per pixel (leaf colour, shadow alpha, normal
+// map) against hundreds of traversal steps, and inlining it three times is what blew the instruction cache.
+// Returns the number of texels read in *fetches (added).
+__device__ __noinline__ float4 texture_lod(const TexInfo* ti, const float* unorm, float u, float v, int tex_id, float lod, uint32_t* fetches) {
+    const int layer = iclamp(tex_id, 0, (int)ti->layers - 1);
     if (!(lod > 0.0f)) {
-        int i = iclamp(ifloor_clamped(u * (float)s.tex_w), 0, (int)s.tex_w - 1);
-        int j = imod(ifloor_clamped(v * (float)s.tex_h), (int)s.tex_h);
-        fetches += 1;
-        return fetch_texel(s, 0, layer, i, j);
+        const int i = iclamp(ifloor_clamped(u * (float)ti->w), 0, (int)ti->w - 1);
+        const int j = imod(ifloor_clamped(v * (float)ti->h), (int)ti->h);
+        *fetches += 1;
+        return fetch_texel(ti, unorm, 0, ti->w, ti->h, layer, i, j);
     }
-    float maxl = (float)(s.tex_levels - 1);
-    float l = gl_min(lod, maxl);
-    float fl = floorf(l);
-    uint32_t d1 = (uint32_t)fl;
-    uint32_t d2 = (d1 + 1 < s.tex_levels) ? d1 + 1 : s.tex_levels - 1;
-    float f = l - fl;
-    float4 c1 = sample_linear(s, d1, layer, u, v);
-    fetches += 4;
+    const float maxl = (float)(ti->levels - 1);
+    const float l = gl_min(lod, maxl);
+    const float fl = floorf(l);
+    const uint32_t d1 = (uint32_t)fl;
+    const uint32_t d2 = (d1 + 1 < ti->levels) ? d1 + 1 : ti->levels - 1;
+    const float f = l - fl;
+    const float4 c1 = sample_linear(ti, unorm, d1, layer, u, v);
+    *fetches += 4;
     if (d2 == d1 || f == 0.0f) return c1;
-    float4 c2 = sample_linear(s, d2, layer, u, v);
-    fetches += 4;
+    const float4 c2 = sample_linear(ti, unorm, d2, layer, u, v);
+    *fetches += 4;
     return make_float4(mixf(c1.x, c2.x, f), mixf(c1.y, c2.y, f), mixf(c1.z, c2.z, f), mixf(c1.w, c2.w, f));
 }
 
@@ -213,21 +251,22 @@ __device__ __forceinline__ void ray_init(Ray& r, const Scene& s, float octree_sc
     r.tcx = 1.0f / -fabsf(dx); r.tcy = 1.0f / -fabsf(dy); r.tcz = 1.0f / -fabsf(dz);
     r.tbx = r.tcx * r.rox; r.tby = r.tcy * r.roy; r.tbz = r.tcz * r.roz;
 
-    r.octant_mask = 0;
-    if (dx > 0) { r.octant_mask ^= 1; r.tbx = 3.0f * r.tcx - r.tbx; }
-    if (dy > 0) { r.octant_mask ^= 2; r.tby = 3.0f * r.tcy - r.tby; }
-    if (dz > 0) { r.octant_mask ^= 4; r.tbz = 3.0f * r.tcz - r.tbz; }
+    int octant_mask = 0;
+    if (dx > 0) { octant_mask ^= 1; r.tbx = 3.0f * r.tcx - r.tbx; }
+    if (dy > 0) { octant_mask ^= 2; r.tby = 3.0f * r.tcy - r.tby; }
+    if (dz > 0) { octant_mask ^= 4; r.tbz = 3.0f * r.tcz - r.tbz; }
 
-    float t_min = gl_max(gl_max(2.0f * r.tcx - r.tbx, 2.0f * r.tcy - r.tby), 2.0f * r.tcz - r.tbz);
-    r.t_min = gl_max(0.0f, t_min);
-    r.t_max = gl_min(gl_min(r.tcx - r.tbx, r.tcy - r.tby), r.tcz - r.tbz);
+    const float t_min = tmax2(tmax2(2.0f * r.tcx - r.tbx, 2.0f * r.tcy - r.tby), 2.0f * r.tcz - r.tbz);
+    r.t_min = tmax2(0.0f, t_min);
+    r.t_max = tmin2(tmin2(r.tcx - r.tbx, r.tcy - r.tby), r.tcz - r.tbz);
     r.h = r.t_max;
 
-    r.idx = 0;
+    int idx = 0;
     r.px = 1.0f; r.py = 1.0f; r.pz = 1.0f;
-    if (r.t_min < 1.5f * r.tcx - r.tbx) { r.idx ^= 1; r.px = 1.5f; }
-    if (r.t_min < 1.5f * r.tcy - r.tby) { r.idx ^= 2; r.py = 1.5f; }
-    if (r.t_min < 1.5f * r.tcz - r.tbz) { r.idx ^= 4; r.pz = 1.5f; }
+    if (r.t_min < 1.5f * r.tcx - r.tbx) { idx ^= 1; r.px = 1.5f; }
+    if (r.t_min < 1.5f * r.tcy - r.tby) { idx ^= 2; r.py = 1.5f; }
+    if (r.t_min < 1.5f * r.tcz - r.tbz) { idx ^= 4; r.pz = 1.5f; }
+    r.idx = idx | (octant_mask << 4);
 
     r.scale = VX_MAX_SCALE - 1;
     r.scale_exp2 = 0.5f;
@@ -237,141 +276,147 @@ __device__ __forceinline__ void ray_init(Ray& r, const Scene& s, float octree_sc
     r.inside_voxel = 0;
 
     // state (ptr=0, parent_octant_idx=0): the preamble's child 0 = world root (esvo.rs:179-188)
-    uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
+    const uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
     r.desc = w0 & 0xffffu;
     r.rec = (w4 & 0x80000000u) ? (4u + (w4 & 0x7fffffffu)) : w4;
 }
 
-// One iteration of the loop at svo.esvo.glsl:152-392.
-//   TRANSLUCENT = cast_translucent; when false the texture is never sampled (picker.glsl never reads
-//   res.color and the accept test at :242 is then independent of alpha).
-template <bool TRANSLUCENT, bool VEC, bool COUNT>
-__device__ __forceinline__ int ray_step(Ray& r, const Scene& s, const Stack& st, float inv_octree_scale, Hit& hit, Counters& cnt) {
-    if (r.max_dst >= 0.0f && r.t_min > r.max_dst) return RAY_MISS;   // :153
-    if (r.steps >= VX_MAX_STEPS) return RAY_MISS;                    // :152
-    r.steps++;
-    if (COUNT) cnt.steps++;
+// One iteration of the loop at svo.esvo.glsl:152-392, minus the leaf evaluation.
+//   returns RAY_LEAF when the current child is a leaf with t_min > 0 (:185): the caller evaluates it with leaf_geom()
+//   and either finishes the ray or calls ray_step again with after_leaf = true, which resumes THAT iteration at its
+//   ADVANCE phase (:324) after the bookkeeping of a rejected translucent leaf (:264-265).
+//   LIMITED: the ray has a max_dst (:153); render rays do not.
+template <bool LIMITED, bool VEC, bool COUNT>
+__device__ __forceinline__ int ray_step(Ray& r, const Scene& s, const Stack& st, Counters& cnt, bool after_leaf = false) {
+    if (!after_leaf) {
+        if (LIMITED && r.max_dst >= 0.0f && r.t_min > r.max_dst) return RAY_MISS;   // :153
+        if (r.steps >= VX_MAX_STEPS) return RAY_MISS;                                // :152
+        r.steps++;
+        if (COUNT) cnt.steps++;
+    }
+    const float tcornx = __fmaf_rn(r.px, r.tcx, -r.tbx), tcorny = __fmaf_rn(r.py, r.tcy, -r.tby), tcornz = __fmaf_rn(r.pz, r.tcz, -r.tbz);   // :159
+    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                                                                                // :161
 
-    const float tcornx = r.px * r.tcx - r.tbx, tcorny = r.py * r.tcy - r.tby, tcornz = r.pz * r.tcz - r.tbz;   // :159
-    const float tc_max = gl_min(gl_min(tcornx, tcorny), tcornz);                                                // :161
+    if (!after_leaf) {
+        const uint32_t octant_idx = (uint32_t)((r.idx ^ (r.idx >> 4)) & 7);   // :164  idx ^ octant_mask
+        const uint32_t bit = 1u << octant_idx;
+        const bool is_child = (r.desc & (bit << 8)) != 0;                     // :172
+        const bool is_leaf = (r.desc & bit) != 0;                             // :173
 
-    const uint32_t octant_idx = (uint32_t)(r.idx ^ r.octant_mask);   // :164
-    const uint32_t bit = 1u << octant_idx;
-    const bool is_child = (r.desc & (bit << 8)) != 0;                // :172
-    const bool is_leaf = (r.desc & bit) != 0;                        // :173
-
-    if (is_child && r.t_min <= r.t_max) {                            // :178
-        if (is_leaf && r.t_min == 0.0f) r.inside_voxel = 1;          // :180
-        if (is_leaf && r.t_min > 0.0f) {                             // :185  HIT
-            if (COUNT) cnt.leaf_tests++;
-            const uint32_t value = ld_desc(s, r.rec + 4 + octant_idx);   // :190-194
-
-            const float se = r.scale_exp2;
-            const float tnx = (r.px + se) * r.tcx - r.tbx, tny = (r.py + se) * r.tcy - r.tby, tnz = (r.pz + se) * r.tcz - r.tbz;   // :197
-            const float tc_min = gl_max(gl_max(tnx, tny), tnz);      // :199
-
-            float qx = r.px, qy = r.py, qz = r.pz;                   // :202-205
-            if (r.octant_mask & 1) qx = 3.0f - se - qx;
-            if (r.octant_mask & 2) qy = 3.0f - se - qy;
-            if (r.octant_mask & 4) qz = 3.0f - se - qz;
-
-            const float inv_se = 1.0f / se;                          // exact: se is a power of two
-            int face_id; float u, v;                                 // :210-224
-            if (tc_min == tnx) {
-                face_id = (__float_as_int(r.rdx) >> 31) & 1;
-                u = ((r.roz + r.rdz * tnx) - qz) * inv_se; v = ((r.roy + r.rdy * tnx) - qy) * inv_se;
-                if (r.rdx > 0) u = 1 - u;
-            } else if (tc_min == tny) {
-                face_id = 2 | ((__float_as_int(r.rdy) >> 31) & 1);
-                u = ((r.rox + r.rdx * tny) - qx) * inv_se; v = ((r.roz + r.rdz * tny) - qz) * inv_se;
-                if (r.rdy > 0) v = 1 - v;
-            } else {
-                face_id = 4 | ((__float_as_int(r.rdz) >> 31) & 1);
-                u = ((r.rox + r.rdx * tnz) - qx) * inv_se; v = ((r.roy + r.rdy * tnz) - qy) * inv_se;
-                if (r.rdz < 0) u = 1 - u;
+        if (is_child && r.t_min <= r.t_max) {                                 // :178
+            if (is_leaf) {
+                if (r.t_min > 0.0f) return RAY_LEAF;                          // :185
+                if (r.t_min == 0.0f) r.inside_voxel = 1;                      // :180
             }
-
-            const float dst = r.t_min * inv_octree_scale;            // :233 (exact: scale is a power of two)
-            bool accept;
-            if (TRANSLUCENT) {
-                const Material* m = s.materials + (value < s.n_materials ? value : s.n_materials - 1);   // :227-230
-                int tex_id = __ldg(&m->tex_side);
-                if (face_id == 3) tex_id = __ldg(&m->tex_top);
-                else if (face_id == 2) tex_id = __ldg(&m->tex_bottom);
-                float sm = gl_clamp((dst - 15.0f) / (25.0f - 15.0f), 0.0f, 1.0f);   // :235
-                sm = (sm * sm) * (3.0f - 2.0f * sm);
-                const float tex_lod = (sm * (dst - 15.0f)) * 0.05f;
-                unsigned long long nf = 0;
-                const float4 c = texture_lod(s, u, v, tex_id, tex_lod, nf);          // :237
-                if (COUNT) cnt.tex_fetches += nf;
-                const bool first_of_kind = r.adjacent_leaf_count == 0 || value != r.last_leaf_value;   // :241
-                accept = (c.w > 0.0f) && first_of_kind;              // :242
-                hit.r = c.x; hit.g = c.y; hit.b = c.z; hit.a = c.w; hit.lod = tex_lod;
-            } else {
-                accept = true;                                       // (!cast_translucent) && adjacent_leaf_count==0
-                hit.r = hit.g = hit.b = hit.a = 0.0f; hit.lod = 0.0f;
-            }
-            if (accept) {
-                hit.t = dst; hit.face_id = face_id; hit.u = u; hit.v = v; hit.value = value;
-                float hx = gl_min(gl_max(r.rox + r.t_min * r.rdx, qx + VX_EPSILON), qx + se - VX_EPSILON);   // :252-254
-                float hy = gl_min(gl_max(r.roy + r.t_min * r.rdy, qy + VX_EPSILON), qy + se - VX_EPSILON);
-                float hz = gl_min(gl_max(r.roz + r.t_min * r.rdz, qz + VX_EPSILON), qz + se - VX_EPSILON);
-                hit.posx = (hx - 1.0f) * inv_octree_scale; hit.posy = (hy - 1.0f) * inv_octree_scale; hit.posz = (hz - 1.0f) * inv_octree_scale;   // :257-258
-                return RAY_HIT;
-            }
-            ++r.adjacent_leaf_count;                                 // :264-265
-            r.last_leaf_value = value;
-        } else {
-            const float half_scale = r.scale_exp2 * 0.5f;            // :274
-            const float tcx_ = half_scale * r.tcx + tcornx, tcy_ = half_scale * r.tcy + tcorny, tcz_ = half_scale * r.tcz + tcornz;   // :275
-            const float tv_max = gl_min(r.t_max, tc_max);            // :278
-            if (r.t_min <= tv_max) {                                 // :280  PUSH
+            // :266-312 — also taken by a leaf at t_min == 0 (origin inside a voxel), see SURVEY Appendix B
+            const float half_scale = r.scale_exp2 * 0.5f;                     // :274
+            const float tv_max = tmin2(r.t_max, tc_max);                      // :278
+            if (r.t_min <= tv_max) {                                          // :280  PUSH
                 if (COUNT) cnt.pushes++;
-                if (tc_max < r.h) {                                  // :284-288
+                if (tc_max < r.h) {                                           // :284-288
                     const uint32_t sl = st.slot(r.scale);
                     st.rec[sl] = r.rec; st.desc[sl] = r.desc; st.t_max[sl] = r.t_max;
                 }
-                r.h = tc_max;                                        // :289
+                r.h = tc_max;                                                 // :289
                 uint32_t nd, nr;
-                fetch_child<VEC>(s, r.rec, octant_idx, nd, nr);      // :292 (+ the :168 read of the next iterations)
+                fetch_child<VEC>(s, r.rec, octant_idx, nd, nr);               // :292 (+ the :168 read of the next iterations)
                 r.rec = nr; r.desc = nd;
-                --r.scale; r.scale_exp2 = half_scale;                // :295-297
-                r.idx = 0;                                           // :301-304
-                if (r.t_min < tcx_) { r.idx ^= 1; r.px += r.scale_exp2; }
-                if (r.t_min < tcy_) { r.idx ^= 2; r.py += r.scale_exp2; }
-                if (r.t_min < tcz_) { r.idx ^= 4; r.pz += r.scale_exp2; }
-                r.t_max = tv_max;                                    // :307
-                return RAY_CONTINUE;                                 // :310
+                const float tcx_ = __fmaf_rn(half_scale, r.tcx, tcornx), tcy_ = __fmaf_rn(half_scale, r.tcy, tcorny),
+                            tcz_ = __fmaf_rn(half_scale, r.tcz, tcornz);      // :275
+                --r.scale; r.scale_exp2 = half_scale;                         // :295-297
+                int idx = 0;                                                  // :301-304
+                if (r.t_min < tcx_) { idx ^= 1; r.px += half_scale; }
+                if (r.t_min < tcy_) { idx ^= 2; r.py += half_scale; }
+                if (r.t_min < tcz_) { idx ^= 4; r.pz += half_scale; }
+                r.idx = (r.idx & 0x70) | idx;
+                r.t_max = tv_max;                                             // :307
+                return RAY_CONTINUE;                                          // :310
             }
+        } else {
+            r.adjacent_leaf_count = 0;                                        // :315-316
+            r.last_leaf_value = 0xffffffffu;
         }
-    } else {
-        r.adjacent_leaf_count = 0;                                   // :315-316
-        r.last_leaf_value = 0xffffffffu;
     }
 
-    int step_mask = 0;                                               // :324-327  ADVANCE
+    int step_mask = 0;                                                        // :324-327  ADVANCE
     if (tc_max >= tcornx) { step_mask ^= 1; r.px -= r.scale_exp2; }
     if (tc_max >= tcorny) { step_mask ^= 2; r.py -= r.scale_exp2; }
     if (tc_max >= tcornz) { step_mask ^= 4; r.pz -= r.scale_exp2; }
-    r.t_min = tc_max;                                                // :330
-    r.idx ^= step_mask;                                              // :331
+    r.t_min = tc_max;                                                         // :330
+    r.idx ^= step_mask;                                                       // :331
 
-    if ((r.idx & step_mask) != 0) {                                  // :335  POP
-        uint32_t differing_bits = 0;                                 // :347-350
+    if ((r.idx & step_mask) != 0) {                                           // :335  POP
+        uint32_t differing_bits = 0;                                          // :347-350
         if (step_mask & 1) differing_bits |= __float_as_uint(r.px) ^ __float_as_uint(r.px + r.scale_exp2);
         if (step_mask & 2) differing_bits |= __float_as_uint(r.py) ^ __float_as_uint(r.py + r.scale_exp2);
         if (step_mask & 4) differing_bits |= __float_as_uint(r.pz) ^ __float_as_uint(r.pz + r.scale_exp2);
-        r.scale = 31 - __clz(differing_bits);                        // :360 findMSB
-        r.scale_exp2 = __int_as_float((r.scale - VX_MAX_SCALE + 127) << 23);   // :361 exp2(scale - 23)
-        if (r.scale >= VX_MAX_SCALE) return RAY_MISS;                // :365
-        const uint32_t sl = st.slot(r.scale);                        // :370-372
+        r.scale = 31 - __clz(differing_bits);                                 // :360 findMSB
+        r.scale_exp2 = __int_as_float((r.scale - VX_MAX_SCALE + 127) << 23);  // :361 exp2(scale - 23)
+        if (r.scale >= VX_MAX_SCALE) return RAY_MISS;                         // :365
+        const uint32_t sl = st.slot(r.scale);                                 // :370-372
         r.rec = st.rec[sl]; r.desc = st.desc[sl]; r.t_max = st.t_max[sl];
         const int shx = __float_as_int(r.px) >> r.scale, shy = __float_as_int(r.py) >> r.scale, shz = __float_as_int(r.pz) >> r.scale;   // :377-382
         r.px = __int_as_float(shx << r.scale); r.py = __int_as_float(shy << r.scale); r.pz = __int_as_float(shz << r.scale);
-        r.idx = (shx & 1) | ((shy & 1) << 1) | ((shz & 1) << 2);     // :388
-        r.h = 0.0f;                                                  // :390
+        r.idx = (r.idx & 0x70) | (shx & 1) | ((shy & 1) << 1) | ((shz & 1) << 2);   // :388
+        r.h = 0.0f;                                                           // :390
     }
     return RAY_CONTINUE;
+}
+
+// HIT block geometry, svo.esvo.glsl:190-224 + :233, for the leaf candidate ray_step stopped at.
+template <bool COUNT>
+__device__ __forceinline__ void leaf_geom(const Ray& r, const Scene& s, float inv_octree_scale, Leaf& g, Counters& cnt) {
+    if (COUNT) cnt.leaf_tests++;
+    const int octant_mask = r.idx >> 4;
+    const uint32_t octant_idx = (uint32_t)((r.idx ^ octant_mask) & 7);
+    g.value = ld_desc(s, r.rec + 4 + octant_idx);                             // :190-194
+    const float se = r.scale_exp2;
+    const float tnx = __fmaf_rn(r.px + se, r.tcx, -r.tbx), tny = __fmaf_rn(r.py + se, r.tcy, -r.tby), tnz = __fmaf_rn(r.pz + se, r.tcz, -r.tbz);   // :197
+    const float tc_min = tmax2(tmax2(tnx, tny), tnz);                         // :199
+    float qx = r.px, qy = r.py, qz = r.pz;                                    // :202-205
+    if (octant_mask & 1) qx = 3.0f - se - qx;
+    if (octant_mask & 2) qy = 3.0f - se - qy;
+    if (octant_mask & 4) qz = 3.0f - se - qz;
+    const float inv_se = 1.0f / se;                                           // exact: se is a power of two
+    if (tc_min == tnx) {                                                      // :210-224
+        g.face_id = (__float_as_int(r.rdx) >> 31) & 1;
+        g.u = ((r.roz + r.rdz * tnx) - qz) * inv_se; g.v = ((r.roy + r.rdy * tnx) - qy) * inv_se;
+        if (r.rdx > 0) g.u = 1 - g.u;
+    } else if (tc_min == tny) {
+        g.face_id = 2 | ((__float_as_int(r.rdy) >> 31) & 1);
+        g.u = ((r.rox + r.rdx * tny) - qx) * inv_se; g.v = ((r.roz + r.rdz * tny) - qz) * inv_se;
+        if (r.rdy > 0) g.v = 1 - g.v;
+    } else {
+        g.face_id = 4 | ((__float_as_int(r.rdz) >> 31) & 1);
+        g.u = ((r.rox + r.rdx * tnz) - qx) * inv_se; g.v = ((r.roy + r.rdy * tnz) - qy) * inv_se;
+        if (r.rdz < 0) g.u = 1 - g.u;
+    }
+    g.dst = r.t_min * inv_octree_scale;                                       // :233 (exact: scale is a power of two)
+    g.qx = qx; g.qy = qy; g.qz = qz; g.se = se;
+}
+
+// res.pos, svo.esvo.glsl:252-258
+__device__ __forceinline__ void leaf_pos(const Ray& r, const Leaf& g, float inv_octree_scale, float& x, float& y, float& z) {
+    const float hx = gl_min(gl_max(r.rox + r.t_min * r.rdx, g.qx + VX_EPSILON), g.qx + g.se - VX_EPSILON);
+    const float hy = gl_min(gl_max(r.roy + r.t_min * r.rdy, g.qy + VX_EPSILON), g.qy + g.se - VX_EPSILON);
+    const float hz = gl_min(gl_max(r.roz + r.t_min * r.rdz, g.qz + VX_EPSILON), g.qz + g.se - VX_EPSILON);
+    x = (hx - 1.0f) * inv_octree_scale; y = (hy - 1.0f) * inv_octree_scale; z = (hz - 1.0f) * inv_octree_scale;
+}
+
+// Material texture for the hit face + custom LOD, svo.esvo.glsl:227-235
+__device__ __forceinline__ void leaf_texture(const Scene& s, const Leaf& g, int& tex_id, float& tex_lod) {
+    const Material* m = s.materials + (g.value < s.n_materials ? g.value : s.n_materials - 1);
+    tex_id = __ldg(&m->tex_side);
+    if (g.face_id == 3) tex_id = __ldg(&m->tex_top);
+    else if (g.face_id == 2) tex_id = __ldg(&m->tex_bottom);
+    float sm = gl_clamp((g.dst - 15.0f) / (25.0f - 15.0f), 0.0f, 1.0f);
+    sm = (sm * sm) * (3.0f - 2.0f * sm);
+    tex_lod = (sm * (g.dst - 15.0f)) * 0.05f;
+}
+
+__device__ __forceinline__ bool layer_is_opaque(const TexInfo* ti, int tex_id) {
+    const int layer = iclamp(tex_id, 0, (int)__ldg(&ti->layers) - 1);
+    return layer < 64 && ((__ldg(&ti->opaque_layers) >> layer) & 1ull);
 }
 
 // ---------------------------------------------------------------- shading --
@@ -405,7 +450,7 @@ __device__ __forceinline__ void primary_ray(const RenderUniforms& u, uint32_t gx
     const float ly = ((m[1] * uvx + m[5] * uvy) + m[9] * -1.0f) + m[13];
     const float lz = ((m[2] * uvx + m[6] * uvy) + m[10] * -1.0f) + m[14];
     const float lw = ((m[3] * uvx + m[7] * uvy) + m[11] * -1.0f) + m[15];
-    float vx_ = lx / lw - ox, vy_ = ly / lw - oy, vz_ = lz / lw - oz;
+    const float vx_ = lx / lw - ox, vy_ = ly / lw - oy, vz_ = lz / lw - oz;
     const float l = sqrtf(dot3(vx_, vy_, vz_, vx_, vy_, vz_));
     dx = vx_ / l; dy = vy_ / l; dz = vz_ / l;
 }
@@ -433,22 +478,23 @@ struct Shade {
     bool want_shadow;
 };
 
-// world.glsl:37-84 up to (not including) the shadow ray.
-__device__ __forceinline__ void shade_hit(const Scene& s, const RenderUniforms& u, const Hit& h, Shade& o, unsigned long long& fetches) {
+// world.glsl:37-84 up to (not including) the shadow ray. (r,g,b,a) of `o` must hold res.color on entry.
+__device__ __forceinline__ void shade_hit(const Scene& s, const float* unorm, const RenderUniforms& u, const Leaf& g, float tex_lod, float posx,
+                                          float posy, float posz, Shade& o, uint32_t* fetches) {
     o.done = false; o.want_shadow = false;
-    if (floorf(h.posx) == floorf(u.hx) && floorf(h.posy) == floorf(u.hy) && floorf(h.posz) == floorf(u.hz)) {   // :37
+    if (floorf(posx) == floorf(u.hx) && floorf(posy) == floorf(u.hy) && floorf(posz) == floorf(u.hz)) {   // :37
         const float thickness = 1.0f / 16.0f;
-        const float lx = fabsf(h.u - 0.5f) * 2.0f, ly = fabsf(h.v - 0.5f) * 2.0f;
+        const float lx = fabsf(g.u - 0.5f) * 2.0f, ly = fabsf(g.v - 0.5f) * 2.0f;
         if (gl_max(lx, ly) > 1.0f - thickness) { o.r = o.g = o.b = o.a = 1.0f; o.done = true; return; }
     }
-    const Material* m = s.materials + (h.value < s.n_materials ? h.value : s.n_materials - 1);   // :48
+    const Material* m = s.materials + (g.value < s.n_materials ? g.value : s.n_materials - 1);   // :48
     int tex_normal_id = __ldg(&m->tex_side_normal);
-    if (h.face_id == 3) tex_normal_id = __ldg(&m->tex_top_normal);
-    else if (h.face_id == 2) tex_normal_id = __ldg(&m->tex_bottom_normal);
+    if (g.face_id == 3) tex_normal_id = __ldg(&m->tex_top_normal);
+    else if (g.face_id == 2) tex_normal_id = __ldg(&m->tex_bottom_normal);
 
     // FACE_NORMALS / FACE_TANGENTS / FACE_BITANGENTS (svo.glsl:2-29) from the face id
-    const int axis = h.face_id >> 1;
-    const float sgn = (h.face_id & 1) ? 1.0f : -1.0f;
+    const int axis = g.face_id >> 1;
+    const float sgn = (g.face_id & 1) ? 1.0f : -1.0f;
     float nx = axis == 0 ? sgn : 0.0f, ny = axis == 1 ? sgn : 0.0f, nz = axis == 2 ? sgn : 0.0f;
     float tx, ty = 0.0f, tz, bx = 0.0f, by, bz;
     if (axis == 0) { tx = 0.0f; tz = -sgn; by = 1.0f; bz = 0.0f; }          // x-: (0,0,1)  x+: (0,0,-1); bitangent (0,1,0)
@@ -456,7 +502,7 @@ __device__ __forceinline__ void shade_hit(const Scene& s, const RenderUniforms& 
     else { tx = sgn; tz = 0.0f; by = 1.0f; bz = 0.0f; }                     // z-: (-1,0,0) z+: (1,0,0); bitangent (0,1,0)
 
     if (tex_normal_id != -1) {                                       // :59-67
-        const float4 t = texture_lod(s, h.u, h.v, tex_normal_id, h.lod, fetches);
+        const float4 t = texture_lod(s.tex, unorm, g.u, g.v, tex_normal_id, tex_lod, fetches);
         float ex = t.x * 2 - 1, ey = t.z * 2 - 1, ez = t.y * 2 - 1;  // .xzy
         const float l = sqrtf(dot3(ex, ey, ez, ex, ey, ez));
         ex = ex / l; ey = ey / l; ez = ez / l;
@@ -466,24 +512,22 @@ __device__ __forceinline__ void shade_hit(const Scene& s, const RenderUniforms& 
     const float ilx = -u.lx, ily = -u.ly, ilz = -u.lz;
     const float dni = dot3(nx, ny, nz, ilx, ily, ilz);
     const float diffuse = gl_max(dni, 0.0f);                         // :70
-    float vx_ = h.posx - u.cx, vy_ = h.posy - u.cy, vz_ = h.posz - u.cz;   // :73
+    float vx_ = posx - u.cx, vy_ = posy - u.cy, vz_ = posz - u.cz;   // :73
     const float vl = sqrtf(dot3(vx_, vy_, vz_, vx_, vy_, vz_));
     vx_ = vx_ / vl; vy_ = vy_ / vl; vz_ = vz_ / vl;
     const float rx = ilx - (2.0f * dni) * nx, ry = ily - (2.0f * dni) * ny, rz = ilz - (2.0f * dni) * nz;   // :74
     const float specular = powf(gl_max(dot3(vx_, vy_, vz_, rx, ry, rz), 0.0f), __ldg(&m->specular_pow)) * __ldg(&m->specular_strength);   // :75
-    o.r = h.r; o.g = h.g; o.b = h.b; o.a = h.a;
     o.lit = diffuse + specular;
-    if (u.render_shadows && h.t < u.shadow_distance) {               // :80
+    if (u.render_shadows && g.dst < u.shadow_distance) {             // :80
         o.want_shadow = true;
-        o.sox = h.posx + nx * 0.001f; o.soy = h.posy + ny * 0.001f; o.soz = h.posz + nz * 0.001f;   // :82
+        o.sox = posx + nx * 0.001f; o.soy = posy + ny * 0.001f; o.soz = posz + nz * 0.001f;   // :82
     }
 }
 
 // world.glsl:87-89
-__device__ __forceinline__ float4 shade_finish(const RenderUniforms& u, const Shade& o, float shadow) {
-    if (o.done) return make_float4(o.r, o.g, o.b, o.a);
-    const float light = gl_clamp(u.ambient + o.lit * shadow, 0.0f, 1.0f);
-    return make_float4(o.r * light, o.g * light, o.b * light, o.a);
+__device__ __forceinline__ float4 shade_finish(const RenderUniforms& u, float r, float g, float b, float a, float lit, float shadow) {
+    const float light = gl_clamp(u.ambient + lit * shadow, 0.0f, 1.0f);
+    return make_float4(r * light, g * light, b * light, a);
 }
 
 }  // namespace vx

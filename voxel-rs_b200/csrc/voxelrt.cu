@@ -1,10 +1,10 @@
-// voxelrt.cu — kernels and C ABI of libvoxelrt (see include/voxelrt.h for the reference seams).
+// voxelrt.cu — C ABI of libvoxelrt (include/voxelrt.h): context, streams, uploads and kernel launches.
+// Device code lives in traverse.cuh (step machine, shading) and kernels.cuh (__global__ entry points).
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared -Xcompiler -fPIC
 // (--fmad=false is part of the numeric contract, see traverse.cuh).
 #include <cuda_runtime.h>
 
-#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,367 +13,7 @@
 #include <vector>
 
 #include "../../include/voxelrt.h"
-#include "traverse.cuh"
-
-namespace vx {
-
-// ================================================================ kernels ==
-
-// Decodes a 2-D Morton code (x in even bits).
-__device__ __forceinline__ uint32_t compact1by1(uint32_t v) {
-    v &= 0x55555555u;
-    v = (v ^ (v >> 1)) & 0x33333333u;
-    v = (v ^ (v >> 2)) & 0x0f0f0f0fu;
-    v = (v ^ (v >> 4)) & 0x00ff00ffu;
-    v = (v ^ (v >> 8)) & 0x0000ffffu;
-    return v;
-}
-
-#define VX_TILES_PER_FETCH 4u
-
-struct RenderArgs {
-    Scene scene;
-    RenderUniforms u;
-    float4* frame;            // RGBA32F, row 0 = bottom (world.glsl:140)
-    Counters* counters;
-    unsigned int* work_counter;   // persistent kernels: next unclaimed work item
-    uint32_t tiles_x, tiles_y;    // frame size in 8x4-pixel warp tiles
-    uint32_t macro_x, macro_y;    // frame size in 4x4-tile (32x16 pixel) macro blocks
-    uint32_t shard_rank, shard_size;
-};
-
-// Tile order: macro blocks of 4x4 warp tiles row-major over the frame, Morton order inside a block,
-// so consecutive tile indices are spatial neighbours (coherent rays for neighbouring warps) and only
-// edge blocks contain tiles outside the frame. Shards own whole macro blocks, interleaved.
-__device__ __forceinline__ bool tile_coords(const RenderArgs& a, uint32_t t, uint32_t& tx, uint32_t& ty) {
-    const uint32_t macro = t >> 4, within = t & 15u;
-    const uint32_t mx = macro % a.macro_x, my = macro / a.macro_x;
-    tx = mx * 4 + compact1by1(within); ty = my * 4 + compact1by1(within >> 1);
-    if (a.shard_size > 1 && (macro % a.shard_size) != a.shard_rank) return false;
-    return tx < a.tiles_x && ty < a.tiles_y;
-}
-
-__device__ __forceinline__ Stack make_stack(const Scene& s, uint32_t* smem) {
-    Stack st;
-    st.stride = blockDim.x; st.levels = s.stack_levels;
-    st.rec = smem;
-    st.desc = smem + (size_t)st.levels * st.stride;
-    st.t_max = reinterpret_cast<float*>(smem + 2 * (size_t)st.levels * st.stride);
-    return st;
-}
-
-__device__ __forceinline__ void flush_counters(Counters* g, const Counters& c) {
-    // warp-aggregate then one atomic per warp and counter
-    unsigned long long v[6] = {c.primary_rays, c.shadow_rays, c.steps, c.pushes, c.leaf_tests, c.tex_fetches};
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(g);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        unsigned long long x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(dst + k, x);
-    }
-}
-
-// ---- simple render kernel: one thread per pixel, whole pipeline inline (A/B baseline) -------------
-// Block = 128 threads = 4 warps, each warp an 8x4 pixel tile; blockIdx enumerates groups of 4 tiles in
-// tile order (tile_coords).
-template <bool VEC, bool COUNT>
-__global__ void __launch_bounds__(128) render_simple_kernel(RenderArgs a) {
-    extern __shared__ uint32_t smem[];
-    const Stack st = make_stack(a.scene, smem);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t tx, ty;
-    const bool have_tile = tile_coords(a, blockIdx.x * 4 + warp, tx, ty);
-    const uint32_t gx = tx * 8 + (lane & 7), gy = ty * 4 + (lane >> 3);
-    Counters cnt = {0, 0, 0, 0, 0, 0};
-    if (have_tile && gx < a.u.width && gy < a.u.height) {
-        const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
-        const float inv_scale = 1.0f / octree_scale;
-        float ox, oy, oz, dx, dy, dz;
-        primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-        Ray r; Hit h;
-        ray_init(r, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f);
-        cnt.primary_rays = 1;
-        int status;
-        while ((status = ray_step<true, VEC, COUNT>(r, a.scene, st, inv_scale, h, cnt)) == RAY_CONTINUE) {}
-        float4 color;
-        if (status == RAY_HIT) {
-            Shade sh;
-            shade_hit(a.scene, a.u, h, sh, cnt.tex_fetches);
-            float shadow = 1.0f;
-            if (!sh.done && sh.want_shadow) {
-                cnt.shadow_rays = 1;
-                Hit h2;
-                ray_init(r, a.scene, octree_scale, sh.sox, sh.soy, sh.soz, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f);
-                while ((status = ray_step<true, VEC, COUNT>(r, a.scene, st, inv_scale, h2, cnt)) == RAY_CONTINUE) {}
-                shadow = (status == RAY_HIT) ? 0.0f : 1.0f;
-            }
-            color = shade_finish(a.u, sh, shadow);
-        } else {
-            color = sky_color(dx, dy, dz);
-        }
-        a.frame[(size_t)gy * a.u.width + gx] = color;
-    }
-    flush_counters(a.counters, cnt);
-}
-
-// ---- persistent render kernel -----------------------------------------------------------------------
-// One resident CTA set (grid = SMs x CTAs/SM), every warp loops: lane 0 claims the next Morton-ordered
-// 8x4 pixel tile with one atomicAdd (warp-level work fetch), all 32 lanes trace their primary rays in
-// lock-step through the shared step machine; a lane whose primary ray hits is shaded in place and
-// re-armed with its SHADOW ray, so primary and shadow rays of one tile share the same traversal loop
-// (no second pass, no per-pixel state in memory). When fewer than REFILL lanes are still busy and the
-// warp holds a whole tile of finished lanes... the tile is written and the next one fetched.
-template <bool VEC, bool COUNT>
-__global__ void __launch_bounds__(128) render_persistent_kernel(RenderArgs a) {
-    extern __shared__ uint32_t smem[];
-    const Stack st = make_stack(a.scene, smem);
-    const uint32_t lane = threadIdx.x & 31;
-    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
-    const float inv_scale = 1.0f / octree_scale;
-    const uint32_t n_tiles = a.macro_x * a.macro_y * 16u;
-    Counters cnt = {0, 0, 0, 0, 0, 0};
-    uint32_t batch = 0, batch_left = 0;   // tiles are claimed VX_TILES_PER_FETCH at a time (one atomic per 4 tiles)
-
-    for (;;) {
-        // ---- warp-level work fetch: lane 0 claims the next run of tiles, the warp shares it by shuffle
-        if (batch_left == 0) {
-            if (lane == 0) batch = atomicAdd(a.work_counter, (unsigned)VX_TILES_PER_FETCH);
-            batch = __shfl_sync(0xffffffffu, batch, 0);
-            batch_left = VX_TILES_PER_FETCH;
-        }
-        const uint32_t t = batch + (VX_TILES_PER_FETCH - batch_left);
-        --batch_left;
-        if (t >= n_tiles) break;
-        uint32_t tx, ty;
-        if (!tile_coords(a, t, tx, ty)) continue;
-        const uint32_t gx = tx * 8 + (lane & 7), gy = ty * 4 + (lane >> 3);
-        const bool live = gx < a.u.width && gy < a.u.height;
-
-        Ray r; Hit h; Shade sh;
-        float ox, oy, oz, dx = 0, dy = 0, dz = 0;
-        // phase: 0 = primary in flight, 1 = shadow in flight, 2 = finished
-        int phase = 2;
-        float4 color = make_float4(0, 0, 0, 0);
-        if (live) {
-            primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-            ray_init(r, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f);
-            phase = 0;
-            cnt.primary_rays++;
-        }
-        // ---- lock-step traversal; warp vote ends the loop when every lane is finished
-        while (__any_sync(0xffffffffu, phase != 2)) {
-            if (phase != 2) {
-                const int status = ray_step<true, VEC, COUNT>(r, a.scene, st, inv_scale, h, cnt);
-                if (status != RAY_CONTINUE) {
-                    if (phase == 0) {
-                        if (status == RAY_HIT) {
-                            shade_hit(a.scene, a.u, h, sh, cnt.tex_fetches);
-                            if (!sh.done && sh.want_shadow) {
-                                ray_init(r, a.scene, octree_scale, sh.sox, sh.soy, sh.soz, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f);
-                                phase = 1;
-                                cnt.shadow_rays++;
-                            } else {
-                                color = shade_finish(a.u, sh, 1.0f);
-                                phase = 2;
-                            }
-                        } else {
-                            color = sky_color(dx, dy, dz);
-                            phase = 2;
-                        }
-                    } else {
-                        color = shade_finish(a.u, sh, status == RAY_HIT ? 0.0f : 1.0f);
-                        phase = 2;
-                    }
-                }
-            }
-        }
-        if (live) __stcs(a.frame + (size_t)gy * a.u.width + gx, color);   // streaming store: the frame is write-once
-    }
-    flush_counters(a.counters, cnt);
-}
-
-// ---- picker kernel: picker.glsl main(), one thread per task ------------------------------------------
-struct RaycastArgs {
-    Scene scene;
-    const float4* tasks;      // VxPickerTask = 3 x float4
-    float4* results;          // VxPickerResult = 3 x float4
-    unsigned long long n;
-    Counters* counters;
-};
-
-template <bool VEC, bool COUNT>
-__global__ void __launch_bounds__(128) raycast_kernel(RaycastArgs a) {
-    extern __shared__ uint32_t smem[];
-    const Stack st = make_stack(a.scene, smem);
-    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
-    const float inv_scale = 1.0f / octree_scale;
-    Counters cnt = {0, 0, 0, 0, 0, 0};
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const float4 t0 = __ldg(a.tasks + 3 * i), t1 = __ldg(a.tasks + 3 * i + 1), t2 = __ldg(a.tasks + 3 * i + 2);
-        Ray r; Hit h;
-        ray_init(r, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x);
-        cnt.primary_rays++;
-        int status;
-        while ((status = ray_step<false, VEC, COUNT>(r, a.scene, st, inv_scale, h, cnt)) == RAY_CONTINUE) {}
-        float4 o0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f), o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
-        if (status == RAY_HIT && h.t > 0.0f) {                         // picker.glsl:40
-            o0.x = h.t; o0.y = __uint_as_float(r.inside_voxel);
-            o1 = make_float4(h.posx, h.posy, h.posz, 0.0f);
-            const int axis = h.face_id >> 1;
-            const float sgn = (h.face_id & 1) ? 1.0f : -1.0f;          // FACE_NORMALS, svo.glsl:2-9
-            o2 = make_float4(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f, 0.0f);
-        }
-        __stcs(a.results + 3 * i, o0); __stcs(a.results + 3 * i + 1, o1); __stcs(a.results + 3 * i + 2, o2);
-    }
-    flush_counters(a.counters, cnt);
-}
-
-// ---- debug cast: svo.test.glsl main(), one thread, records every iteration ----------------------------
-struct DebugArgs {
-    Scene scene;
-    float pos[3], dir[3];
-    float max_dst;
-    uint32_t cast_translucent;
-    VxOctreeResult* result;
-    VxDebugFrame* frames;
-    uint32_t frames_cap;
-    uint32_t* n_frames;
-};
-
-// The step machine does not carry the shader's (ptr, parent_octant_idx); the debug kernel shadows
-// them (plus their stacks) next to it to emit reference-format frames.
-template <bool TRANSLUCENT>
-__device__ void debug_cast_impl(const DebugArgs& a, const Stack& st) {
-    const Scene& s = a.scene;
-    const float octree_scale = __uint_as_float(__ldg(s.desc - 1));
-    const float inv_scale = 1.0f / octree_scale;
-    Ray r; Hit h;
-    Counters cnt = {0, 0, 0, 0, 0, 0};
-    ray_init(r, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst);
-    uint32_t ptr = 0, pidx = 0;
-    uint32_t ptr_stack[VX_MAX_SCALE + 1], pidx_stack[VX_MAX_SCALE + 1];
-    for (int i = 0; i <= VX_MAX_SCALE; ++i) { ptr_stack[i] = 0; pidx_stack[i] = 0; }
-    uint32_t n = 0;
-    int status;
-    for (;;) {
-        // the frame the shader would emit at :175 for this iteration (if it gets that far)
-        const bool will_run = !(r.max_dst >= 0.0f && r.t_min > r.max_dst) && r.steps < VX_MAX_STEPS;
-        const uint32_t oi = (uint32_t)(r.idx ^ r.octant_mask);
-        const int scale_before = r.scale;
-        const uint32_t rec_before = r.rec;
-        if (will_run) {
-            if (n < a.frames_cap) {
-                VxDebugFrame& f = a.frames[n];
-                f.t_min = r.t_min * inv_scale; f.ptr = ptr; f.idx = oi; f.parent_octant_idx = pidx; f.scale = r.scale;
-                f.is_child = (r.desc & ((1u << oi) << 8)) != 0; f.is_leaf = (r.desc & (1u << oi)) != 0;
-                f.crossed_boundary = 0; f.next_ptr = 0;
-            }
-            ++n;
-        }
-        const float h_before = r.h;
-        const float tcx = r.px * r.tcx - r.tbx, tcy = r.py * r.tcy - r.tby, tcz = r.pz * r.tcz - r.tbz;
-        const float tc_max = gl_min(gl_min(tcx, tcy), tcz);
-        status = ray_step<TRANSLUCENT, false, false>(r, s, st, inv_scale, h, cnt);
-        if (status != RAY_CONTINUE) break;
-        if (r.scale == scale_before - 1) {            // PUSH happened
-            if (tc_max < h_before) { ptr_stack[scale_before] = ptr; pidx_stack[scale_before] = pidx; }
-            ptr = rec_before; pidx = oi;
-        } else if (r.scale > scale_before) {          // POP happened
-            ptr = ptr_stack[r.scale]; pidx = pidx_stack[r.scale];
-        }
-    }
-    VxOctreeResult& o = *a.result;
-    o.t = -1.0f; o.value = 0; o.face_id = 0; o.pos[0] = o.pos[1] = o.pos[2] = 0; o.uv[0] = o.uv[1] = 0;
-    o.color[0] = o.color[1] = o.color[2] = o.color[3] = 0; o.lod = 0; o.inside_voxel = r.inside_voxel;
-    if (status == RAY_HIT) {
-        o.t = h.t; o.value = h.value; o.face_id = h.face_id; o.pos[0] = h.posx; o.pos[1] = h.posy; o.pos[2] = h.posz;
-        o.uv[0] = h.u; o.uv[1] = h.v; o.lod = h.lod;
-        if (TRANSLUCENT) { o.color[0] = h.r; o.color[1] = h.g; o.color[2] = h.b; o.color[3] = h.a; }
-    }
-    *a.n_frames = n;
-}
-
-__global__ void debug_cast_kernel(DebugArgs a) {
-    extern __shared__ uint32_t smem[];
-    const Stack st = make_stack(a.scene, smem);
-    if (a.cast_translucent) {
-        debug_cast_impl<true>(a, st);
-    } else {
-        debug_cast_impl<false>(a, st);
-        // cast_translucent=false still samples the texture in the shader (svo.esvo.glsl:237) and reports
-        // its colour; reproduce that for the debug record only.
-        VxOctreeResult& o = *a.result;
-        if (o.t >= 0.0f) {
-            const Scene& s = a.scene;
-            const Material* m = s.materials + (o.value < s.n_materials ? o.value : s.n_materials - 1);
-            int tex_id = m->tex_side;
-            if (o.face_id == 3) tex_id = m->tex_top; else if (o.face_id == 2) tex_id = m->tex_bottom;
-            float sm = gl_clamp((o.t - 15.0f) / (25.0f - 15.0f), 0.0f, 1.0f);
-            sm = (sm * sm) * (3.0f - 2.0f * sm);
-            const float tex_lod = (sm * (o.t - 15.0f)) * 0.05f;
-            unsigned long long nf = 0;
-            const float4 c = texture_lod(s, o.uv[0], o.uv[1], tex_id, tex_lod, nf);
-            o.color[0] = c.x; o.color[1] = c.y; o.color[2] = c.z; o.color[3] = c.w; o.lod = tex_lod;
-        }
-    }
-}
-
-// ---- small utility kernels -----------------------------------------------------------------------------
-
-// glGenerateMipmap stand-in: level l+1 texel = rounded mean of the 2x2 block below (texture_array.rs:258-260)
-__global__ void mip_kernel(const uint32_t* src, uint32_t* dst, uint32_t pw, uint32_t ph, uint32_t cw, uint32_t ch, uint32_t layers) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cw * ch * layers) return;
-    const uint32_t x = i % cw, y = (i / cw) % ch, layer = i / (cw * ch);
-    const uint32_t x0 = 2 * x, x1 = (2 * x + 1 < pw) ? 2 * x + 1 : pw - 1, y0 = 2 * y, y1 = (2 * y + 1 < ph) ? 2 * y + 1 : ph - 1;
-    const uint32_t* b = src + (size_t)layer * pw * ph;
-    const uint32_t t00 = b[y0 * pw + x0], t10 = b[y0 * pw + x1], t01 = b[y1 * pw + x0], t11 = b[y1 * pw + x1];
-    uint32_t out = 0;
-    for (int c = 0; c < 4; ++c) {
-        const uint32_t sum = ((t00 >> (8 * c)) & 0xff) + ((t10 >> (8 * c)) & 0xff) + ((t01 >> (8 * c)) & 0xff) + ((t11 >> (8 * c)) & 0xff);
-        out |= ((sum + 2) >> 2) << (8 * c);
-    }
-    dst[i] = out;
-}
-
-// glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) of the RGBA32F attachment (framebuffer.rs:97-105)
-__global__ void rgba8_kernel(const float4* frame, uint32_t* out, unsigned long long n) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 c = frame[i];
-    const float v[4] = {c.x, c.y, c.z, c.w};
-    uint32_t p = 0;
-    for (int k = 0; k < 4; ++k) {
-        float f = v[k];
-        if (!(f == f)) f = 0.0f;
-        f = gl_clamp(f, 0.0f, 1.0f);
-        p |= (uint32_t)(int)(f * 255.0f + 0.5f) << (8 * k);
-    }
-    out[i] = p;
-}
-
-// Applies a packed dirty set (n VxRange headers, then payload) to the world buffer (replica update).
-__global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes) {
-    const VxRange* hdr = reinterpret_cast<const VxRange*>(packed);
-    const uint8_t* payload = packed + (size_t)n_ranges * sizeof(VxRange);
-    // payload = [24 head bytes][range 0 bytes][range 1 bytes]...; one block sweeps the whole payload
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < payload_bytes; i += stride) {
-        if (i < 24) { world[i] = payload[i]; continue; }
-        // find the range containing payload byte i (ranges are few; linear scan)
-        unsigned long long off = 24;
-        for (uint32_t k = 0; k < n_ranges; ++k) {
-            const unsigned long long len = hdr[k].length;
-            if (i < off + len) { world[24 + hdr[k].offset + (i - off)] = payload[i]; break; }
-            off += len;
-        }
-    }
-}
-
-}  // namespace vx
+#include "kernels.cuh"
 
 // ================================================================== host ==
 
@@ -387,6 +27,7 @@ struct VxCtx {
     std::string err;
 
     cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr;
+    cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
     cudaEvent_t t0_render = nullptr, t1_render = nullptr, t0_picker = nullptr, t1_picker = nullptr;
 
@@ -401,8 +42,7 @@ struct VxCtx {
     Material* d_materials = nullptr;
     uint32_t n_materials = 0;
     uint32_t* d_texels = nullptr;
-    uint32_t tex_w = 0, tex_h = 0, tex_layers = 0, tex_levels = 0;
-    uint32_t tex_off[16] = {};
+    TexInfo* d_texinfo = nullptr;     // texture array description read by the device-side sampler
 
     float4* d_frame = nullptr;
     uint32_t* d_frame8 = nullptr;
@@ -412,7 +52,7 @@ struct VxCtx {
     float4* d_results = nullptr;
 
     Counters* d_counters = nullptr;   // [0] render, [1] raycast
-    unsigned int* d_work = nullptr;
+    unsigned long long* d_work = nullptr;   // [0] render strip counter (low 32 bits used), [1] picker run counter
     VxFrameStats last_render{}, last_raycast{};
     bool render_timed = false, raycast_timed = false;
 
@@ -420,7 +60,7 @@ struct VxCtx {
     uint64_t launches = 0;
 
     // options (vx_set_option)
-    uint64_t opt_simple = 0, opt_vec = 1, opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1;
+    uint64_t opt_simple = 0, opt_vec = 0, opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 24;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -443,13 +83,12 @@ static Scene make_scene(const VxCtx* c) {
     s.desc = reinterpret_cast<const uint32_t*>(c->d_world + 4);
     s.desc_words = (uint32_t)((c->cfg.svo_capacity_bytes - 4) / 4);
     s.materials = c->d_materials; s.n_materials = c->n_materials;
-    s.texels = c->d_texels; s.tex_w = c->tex_w; s.tex_h = c->tex_h; s.tex_layers = c->tex_layers; s.tex_levels = c->tex_levels;
-    for (int i = 0; i < 16; ++i) s.tex_off[i] = c->tex_off[i];
+    s.tex = c->d_texinfo;
     uint32_t levels = c->stats.depth + 1;
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     return s;
 }
-static size_t stack_smem_bytes(const Scene& s, uint32_t threads) { return (size_t)3 * s.stack_levels * threads * 4; }
+static size_t stack_smem_bytes(const Scene& s, uint32_t threads) { return smem_bytes(s.stack_levels, threads); }
 
 extern "C" {
 
@@ -533,6 +172,7 @@ void vx_destroy(VxCtx* c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_materials) cudaFree(c->d_materials);
     if (c->d_texels) cudaFree(c->d_texels);
+    if (c->d_texinfo) cudaFree(c->d_texinfo);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
     if (c->d_tasks) cudaFree(c->d_tasks);
@@ -541,6 +181,8 @@ void vx_destroy(VxCtx* c) {
     if (c->d_work) cudaFree(c->d_work);
     cudaEvent_t evs[] = {c->e_upload, c->e_render, c->e_picker, c->t0_render, c->t1_render, c->t0_picker, c->t1_picker};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    // only streams the library created are destroyed (caller-owned ones installed by vx_set_streams are not)
+    if (c->own_streams[0]) { c->s_render = c->own_streams[0]; c->s_upload = c->own_streams[1]; c->s_picker = c->own_streams[2]; }
     cudaStream_t ss[] = {c->s_render, c->s_upload, c->s_picker};
     for (cudaStream_t s : ss) if (s) cudaStreamDestroy(s);
     delete c;
@@ -549,6 +191,7 @@ void vx_destroy(VxCtx* c) {
 // Runtime knobs for A/B measurements (not part of the reference surface).
 //   1 = simple kernels (0/1)   2 = 128-bit node fetches (0/1)   3 = count steps/pushes/leaf tests (0/1)
 //   4 = CTAs per SM for persistent kernels (0 = occupancy query)   5 = L2 access-policy window (0/1)
+//   6 = refill threshold of the persistent kernels (1..32 lanes still walking)
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
     if (!ctx) return VX_E_ARG;
     switch (option) {
@@ -557,6 +200,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 3: ctx->opt_count = value; break;
         case 4: ctx->opt_ctas_per_sm = value; break;
         case 5: ctx->opt_l2_window = value; break;
+        case 6: ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value); break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -602,10 +246,22 @@ int vx_set_textures(VxCtx* c, const uint8_t* rgba8, uint32_t width, uint32_t hei
         mip_kernel<<<(n + 255) / 256, 256, 0, c->s_upload>>>(c->d_texels + off[l - 1], c->d_texels + off[l], pw, ph, cw, ch, layers);
         c->launches++;
     }
+    // texture array description + per-layer "every texel is opaque" bits (lets shadow rays skip the sampler)
+    TexInfo ti{};
+    ti.texels = c->d_texels; ti.w = width; ti.h = height; ti.layers = layers; ti.levels = levels;
+    for (int i = 0; i < 16; ++i) ti.off[i] = off[i];
+    ti.opaque_layers = layers >= 64 ? ~0ull : ((1ull << layers) - 1ull);
+    if (!c->d_texinfo) CU(c, cudaMalloc(&c->d_texinfo, sizeof(TexInfo)));
+    CU(c, cudaMemcpyAsync(c->d_texinfo, &ti, sizeof(TexInfo), cudaMemcpyHostToDevice, c->s_upload));
+    for (uint32_t l = 0; l < levels; ++l) {
+        uint32_t wl = width >> l, hl = height >> l;
+        wl = wl ? wl : 1; hl = hl ? hl : 1;
+        const uint32_t n = wl * hl * layers;
+        opaque_kernel<<<(n + 255) / 256, 256, 0, c->s_upload>>>(c->d_texels + off[l], wl * hl, layers, &c->d_texinfo->opaque_layers);
+        c->launches++;
+    }
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->s_upload));
-    c->tex_w = width; c->tex_h = height; c->tex_layers = layers; c->tex_levels = levels;
-    for (int i = 0; i < 16; ++i) c->tex_off[i] = off[i];
     return VX_OK;
 }
 
@@ -770,16 +426,17 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
     a.u.width = width; a.u.height = height;
     a.frame = c->d_frame;
     a.counters = c->d_counters;
-    a.work_counter = c->d_work;
+    a.work_counter = reinterpret_cast<unsigned int*>(c->d_work);
     a.tiles_x = (width + 7) / 8; a.tiles_y = (height + 3) / 4;
     a.macro_x = (a.tiles_x + 3) / 4; a.macro_y = (a.tiles_y + 3) / 4;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
+    a.refill_threshold = (uint32_t)c->opt_refill;
 
     const int threads = 128;
     const size_t smem = stack_smem_bytes(a.scene, threads);
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->s_render));
-    CU(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->s_render));
+    CU(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->s_render));
     const bool vec = c->opt_vec != 0, count = c->opt_count != 0;
     CU(c, cudaEventRecord(c->t0_render, c->s_render));
     if (c->opt_simple) {
@@ -789,8 +446,14 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
         CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<blocks, threads, smem, c->s_render>>>(a);
     } else {
-        auto k = vec ? (count ? render_persistent_kernel<true, true> : render_persistent_kernel<true, false>)
-                     : (count ? render_persistent_kernel<false, true> : render_persistent_kernel<false, false>);
+        // opt_ctas_per_sm picks the register budget variant: <=5 -> 96 regs, 6/7 -> 80 regs, >=8 -> 64 regs (default 6)
+        const int minb = c->opt_ctas_per_sm == 0 ? 6 : (c->opt_ctas_per_sm <= 5 ? 5 : (c->opt_ctas_per_sm <= 7 ? 6 : 8));
+        void (*k)(RenderArgs) = nullptr;
+#define VX_PICK(V, C)                                                                                     \
+    (minb == 5 ? render_persistent_kernel<V, C, 5> : (minb == 6 ? render_persistent_kernel<V, C, 6> : render_persistent_kernel<V, C, 8>))
+        if (vec) k = count ? VX_PICK(true, true) : VX_PICK(true, false);
+        else k = count ? VX_PICK(false, true) : VX_PICK(false, false);
+#undef VX_PICK
         CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = 0;
         rc = persistent_grid(c, (const void*)k, threads, smem, &grid);
@@ -850,6 +513,8 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     a.scene = make_scene(c);
     a.tasks = tasks_dev; a.results = results_dev; a.n = n;
     a.counters = c->d_counters + 1;
+    a.work_counter = c->d_work + 1;
+    a.refill_threshold = (uint32_t)c->opt_refill;
     const int threads = 128;
     const size_t smem = stack_smem_bytes(a.scene, threads);
     const bool vec = c->opt_vec != 0, count = c->opt_count != 0;
@@ -861,6 +526,7 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     const uint64_t need = (n + threads - 1) / threads;
     if ((uint64_t)grid > need) grid = (int)need;
     CU(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(Counters), c->s_picker));
+    CU(c, cudaMemsetAsync(c->d_work + 1, 0, sizeof(unsigned long long), c->s_picker));
     CU(c, cudaEventRecord(c->t0_picker, c->s_picker));
     k<<<grid, threads, smem, c->s_picker>>>(a);
     c->launches++;
@@ -930,6 +596,61 @@ int vx_debug_cast(VxCtx* c, const float pos[3], const float dir[3], float max_ds
     CU(c, cudaStreamSynchronize(c->s_picker));
     if (n_frames) *n_frames = n;
     cudaFree(d_res); cudaFree(d_frames); cudaFree(d_n);
+    return VX_OK;
+}
+
+static void shard_geometry(uint32_t width, uint32_t height, const VxShard* shard, uint32_t* macro_x, uint32_t* n_macros, uint32_t* owned) {
+    const uint32_t tiles_x = (width + 7) / 8, tiles_y = (height + 3) / 4;
+    *macro_x = (tiles_x + 3) / 4;
+    *n_macros = *macro_x * ((tiles_y + 3) / 4);
+    const uint32_t size = shard ? shard->world_size : 1, rank = shard ? shard->rank : 0;
+    *owned = *n_macros > rank ? (*n_macros - rank + size - 1) / size : 0;
+}
+
+uint64_t vx_shard_bytes(uint32_t width, uint32_t height, const VxShard* shard) {
+    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return 0;
+    uint32_t mx, n, owned;
+    shard_geometry(width, height, shard, &mx, &n, &owned);
+    return (uint64_t)owned * 512 * sizeof(float4);
+}
+
+static int shard_copy(VxCtx* c, const VxShard* shard, void* packed_dev, bool pack) {
+    if (!c || !packed_dev || !c->frame_w) return fail(c, VX_E_ARG, "vx_%s_shard: null argument / nothing rendered", pack ? "pack" : "unpack");
+    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return fail(c, VX_E_ARG, "vx_%s_shard: bad shard", pack ? "pack" : "unpack");
+    CU(c, cudaSetDevice(c->cfg.device));
+    uint32_t mx, n, owned;
+    shard_geometry(c->frame_w, c->frame_h, shard, &mx, &n, &owned);
+    if (!owned) return VX_OK;
+    const uint32_t size = shard ? shard->world_size : 1, rank = shard ? shard->rank : 0;
+    if (pack) shard_copy_kernel<true><<<owned, 128, 0, c->s_render>>>(c->d_frame, (float4*)packed_dev, c->frame_w, c->frame_h, mx, n, rank, size);
+    else shard_copy_kernel<false><<<owned, 128, 0, c->s_render>>>(c->d_frame, (float4*)packed_dev, c->frame_w, c->frame_h, mx, n, rank, size);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->e_render, c->s_render));
+    return VX_OK;
+}
+int vx_pack_shard(VxCtx* c, const VxShard* shard, void* packed_dev) { return shard_copy(c, shard, packed_dev, true); }
+int vx_unpack_shard(VxCtx* c, const VxShard* shard, const void* packed_dev) { return shard_copy(c, shard, const_cast<void*>(packed_dev), false); }
+
+int vx_set_streams(VxCtx* c, void* render_stream, void* upload_stream, void* picker_stream) {
+    if (!c) return VX_E_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaDeviceSynchronize());
+    if (!c->own_streams[0]) { c->own_streams[0] = c->s_render; c->own_streams[1] = c->s_upload; c->own_streams[2] = c->s_picker; }
+    c->s_render = render_stream ? (cudaStream_t)render_stream : c->own_streams[0];
+    c->s_upload = upload_stream ? (cudaStream_t)upload_stream : c->own_streams[1];
+    c->s_picker = picker_stream ? (cudaStream_t)picker_stream : c->own_streams[2];
+    // re-arm the ordering events on the new streams
+    CU(c, cudaEventRecord(c->e_upload, c->s_upload));
+    CU(c, cudaEventRecord(c->e_render, c->s_render));
+    CU(c, cudaEventRecord(c->e_picker, c->s_picker));
+    install_l2_window(c);
+    return VX_OK;
+}
+
+int vx_stream(VxCtx* c, int which, void** out_stream) {
+    if (!c || !out_stream || which < 0 || which > 2) return VX_E_ARG;
+    *out_stream = which == 0 ? (void*)c->s_render : which == 1 ? (void*)c->s_upload : (void*)c->s_picker;
     return VX_OK;
 }
 

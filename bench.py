@@ -46,8 +46,6 @@ def parse():
     ap.add_argument("--radius", type=int, default=20)
     ap.add_argument("--no-lod", action="store_true")
     ap.add_argument("--no-shadows", action="store_true")
-    ap.add_argument("--simple", action="store_true", help="one-thread-per-pixel kernels (A/B)")
-    ap.add_argument("--vec-loads", action="store_true", help="128-bit node fetches instead of 32-bit (A/B)")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
     ap.add_argument("--no-l2-window", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
@@ -222,8 +220,6 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
-    svo.set_option(pkg.OPT_SIMPLE, int(args.simple))
-    svo.set_option(pkg.OPT_VEC, int(args.vec_loads))
     if args.refill:
         svo.set_option(pkg.OPT_REFILL, args.refill)
     if args.ctas_per_sm:
@@ -350,13 +346,16 @@ def main():
         rays_total, prim_total, shad_total = rays_local, st["primary_rays"], st["shadow_rays"]
 
     # ---- kernel-only timing of the dominant kernel (events on its stream, L2 flushed before each launch)
-    kms = []
+    kms, parts = [], []
     for i in range(args.warmup + min(args.steps, 10)):
         flush()
         svo.render_raw(vxp, W, H, shard=shard)
         if i >= args.warmup:
-            kms.append(svo.frame_stats(0)["kernel_ms"])
+            fs = svo.frame_stats(0)
+            kms.append(fs["kernel_ms"])
+            parts.append((fs["trace_ms"], fs["shade_ms"], fs["shadow_ms"]))
     kernel_ms = float(np.mean(kms))
+    split_ms = dict(zip(("trace_primary", "shade", "trace_shadow"), (round(float(v), 4) for v in np.mean(np.array(parts), axis=0))))
 
     # ---- the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -395,14 +394,15 @@ def main():
             "chunks": int(world.chunk_count), "rays_per_frame": rays_total, "primary_rays": prim_total, "shadow_rays": shad_total,
             "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
             "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 256 MiB device memset inside the timed region",
-            "kernel": "simple" if args.simple else "persistent", "node_loads": "128-bit" if args.vec_loads else "32-bit", "ctas_per_sm": args.ctas_per_sm or 6, "refill_threshold": args.refill or 24,
+            "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)", "ctas_per_sm": args.ctas_per_sm or 8,
+            "refill_threshold": args.refill or 1,
             "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
             "multi_gpu_step": "NCCL broadcast of packed dirty ranges + scatter, shard render, pack, NCCL send/recv to GPU 0, unpack" if n_gpus > 1 else None,
         },
         "frame_ms": ms_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": "render_simple_kernel" if args.simple else "render_persistent_kernel",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "peak_source": peak_src, "kernel": "trace_primary_kernel + shade_kernel + trace_shadow_kernel (one frame)",
+                     "kernel_ms": kernel_ms, "kernel_ms_split": split_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "counts": {k: int(st[k]) for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")},
                      "note": "latency/divergence-bound pointer chasing: the SVO is L2-resident after first touch, so the HBM fraction is small "
                              "by construction (SURVEY §8d); see profiles/ for L2 hit rate and warp execution efficiency"},

@@ -48,8 +48,6 @@ typedef struct VxCtx VxCtx;
 
 /* flags for VxConfig.flags */
 #define VX_FLAG_NO_L2_WINDOW   (1u << 0)  /* do not install the persisting-L2 access-policy window */
-#define VX_FLAG_KERNEL_SIMPLE  (1u << 1)  /* one-thread-per-pixel reference kernels instead of the
-                                             persistent work-fetching ones (A/B + debugging) */
 
 typedef struct VxConfig {
     int32_t  device;              /* CUDA device ordinal this context owns */
@@ -128,7 +126,10 @@ typedef struct VxFrameStats {
     uint64_t pushes;         /* PUSH phases (svo.esvo.glsl:281-311) */
     uint64_t leaf_tests;     /* HIT blocks entered (svo.esvo.glsl:185-265) */
     uint64_t tex_fetches;    /* texels read (1 per NEAREST sample, 8 per trilinear) */
-    float    kernel_ms;      /* CUDA-event time of the dominant kernel on its own stream */
+    float    kernel_ms;      /* CUDA-event time of the frame's kernels (trace + shade + shadow) / the picker kernel */
+    float    trace_ms;       /* vx_render only: primary-ray trace kernel */
+    float    shade_ms;       /* vx_render only: shading kernel */
+    float    shadow_ms;      /* vx_render only: shadow-ray trace kernel */
 } VxFrameStats;
 
 /* = graphics::svo::Stats, src/graphics/svo.rs:75-83 */
@@ -277,9 +278,12 @@ int vx_stream(VxCtx* ctx, int which, void** out_stream);
 int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
 
 /* Runtime knobs for A/B measurements (no reference counterpart):
- *   1 = simple one-thread-per-pixel kernels (0/1)      2 = 128-bit node fetches (0/1, default 1)
- *   3 = count steps/pushes/leaf tests/texels (0/1)     4 = CTAs per SM of persistent kernels (0 = occupancy query)
- *   5 = persisting-L2 access-policy window (0/1, default 1) */
+ *   3 = count steps/pushes/leaf tests/texels (0/1)     4 = CTAs per SM of the persistent trace kernels (0 = default 8;
+ *                                                          <=5 / 6-7 / >=8 select the 96 / 80 / 64-register builds)
+ *   5 = persisting-L2 access-policy window (0/1, default 1)
+ *   6 = refill threshold of the persistent trace kernels: a warp leaves its walk loop to finish/refill rays when fewer
+ *       than this many lanes are still walking (1..32; default 1 = run all rays of the warp to their end, then
+ *       refill all 32 lanes — measured fastest on coherent frames, profiles/r01_v1_*) */
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);
 
 /* How many kernels of this library were launched on this ctx since creation. */

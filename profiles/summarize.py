@@ -100,7 +100,11 @@ def main():
             pass
         summary.append(d)
     if want_source:
+        seen = set()
         for k in source(rep):
+            if k["name"] in seen:
+                continue
+            seen.add(k["name"])
             h = {n: i for i, n in enumerate(k["hdr"])}
             rows = k["rows"]
             tot_s = sum(int(r[h["# Samples"]]) for r in rows) or 1

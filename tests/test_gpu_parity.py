@@ -121,11 +121,11 @@ def test_picker_random_rays_bit_exact(pkg, ora, reg):
             tasks["dir"][::17, 1] = 0.0          # exercise the epsilon clamp (svo.esvo.glsl:85-89)
             tasks["pos"][::5] = np.floor(tasks["pos"][::5]) + 0.5
             want, ocnt = s.raycast(tasks)
-            for vec in (1, 0):
-                svo.set_option(pkg.OPT_VEC, vec)
+            for refill in (8, 1, 32):
+                svo.set_option(pkg.OPT_REFILL, refill)
                 svo.set_option(pkg.OPT_COUNT, 1)
                 got = svo.raycast_tasks(tasks)
-                assert got.tobytes() == want.tobytes(), (name, max_dst, vec, int((got["dst"] != want["dst"]).sum()))
+                assert got.tobytes() == want.tobytes(), (name, max_dst, refill, int((got["dst"] != want["dst"]).sum()))
                 st = svo.frame_stats(1)
                 assert st["steps"] == ocnt["steps"] and st["pushes"] == ocnt["pushes"] and st["leaf_tests"] == ocnt["leaf_tests"], (st, ocnt)
         svo.close()
@@ -197,10 +197,10 @@ def test_render_terrain_variants(pkg, ora, terrain):
     p = terrain_params(pkg, w, h)
     svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
     frames = {}
-    for simple in (0, 1):
-        for vec in (0, 1):
-            svo.set_option(pkg.OPT_SIMPLE, simple)
-            svo.set_option(pkg.OPT_VEC, vec)
+    for simple, vec in ((8, 0), (1, 5), (32, 6), (20, 8)):   # (refill threshold, CTAs/SM = register-budget build)
+        if True:
+            svo.set_option(pkg.OPT_REFILL, simple)
+            svo.set_option(pkg.OPT_CTAS_PER_SM, vec)
             svo.set_option(pkg.OPT_COUNT, 1)
             got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
             assert_frames_match(got, got8, want, want8)
@@ -208,7 +208,7 @@ def test_render_terrain_variants(pkg, ora, terrain):
             for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
                 assert st[k] == cnt[k], (simple, vec, k, st, cnt)
             frames[(simple, vec)] = got
-    base = frames[(0, 1)]
+    base = frames[(8, 0)]
     for k, f in frames.items():
         assert f.tobytes() == base.tobytes(), k
     assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]   # trilinear path exercised

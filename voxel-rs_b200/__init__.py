@@ -48,7 +48,8 @@ class VxShard(C.Structure):
 
 class VxFrameStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("steps", C.c_uint64), ("pushes", C.c_uint64),
-                ("leaf_tests", C.c_uint64), ("tex_fetches", C.c_uint64), ("kernel_ms", C.c_float)]
+                ("leaf_tests", C.c_uint64), ("tex_fetches", C.c_uint64), ("kernel_ms", C.c_float), ("trace_ms", C.c_float),
+                ("shade_ms", C.c_float), ("shadow_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -94,8 +95,7 @@ RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "for
                          "offsets": [0, 4, 16, 32], "itemsize": 48})
 
 VX_FLAG_NO_L2_WINDOW = 1
-VX_FLAG_KERNEL_SIMPLE = 2
-OPT_SIMPLE, OPT_VEC, OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL = 1, 2, 3, 4, 5, 6
+OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL = 3, 4, 5, 6
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
 VX_SYMBOLS = [

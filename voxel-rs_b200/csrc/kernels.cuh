@@ -1,42 +1,50 @@
 // kernels.cuh — the __global__ entry points of libvoxelrt (sm_100a).
 //
-//   render_persistent_kernel  world.glsl main(): persistent warps, warp-level work fetch, per-lane ray refill
-//   render_simple_kernel      same pixels, one thread per pixel start to finish (A/B baseline)
-//   raycast_kernel            picker.glsl main(): batched rays, same refill scheme
-//   debug_cast_kernel         svo.test.glsl main(): one ray, per-iteration frames
-//   mip / rgba8 / shard copy / dirty-range scatter / texture-opacity utility kernels
+// A frame (world.glsl main()) is a WAVEFRONT of three kernels on one stream:
+//   trace_primary_kernel   primary rays: ray generation + ESVO traversal only -> one 32-byte hit record per pixel
+//   shade_kernel           one thread per pixel, straight-line: texture colour, highlight, normal map, lighting, sky;
+//                          writes final pixels, and for lit pixels appends a shadow-ray record to a compacted list
+//   trace_shadow_kernel    shadow rays of that list: the same traversal loop -> final pixel
+// and the picker (picker.glsl main()) is the same traversal loop over a task array (trace_picker_kernel).
+// Why not one fused kernel: the fused version was measured instruction-cache bound (profiles/r01_v0_*: the largest
+// stall reason was no_instruction; 55-70 KB of SASS against a 32 KB L1.5 / ~6 KB L0 I-cache, with warps of one SM
+// at unrelated places of it). Split this way the traversal kernels are a few KB of SASS that stay in the L0 cache,
+// and the big straight-line shading code is walked by all warps of an SM together.
+//
+// The traversal kernels are persistent: grid = SMs x resident CTAs, every warp loops
+//   refill   idle lanes take the next rays of the warp's current run of 128 (pixels of a 32x4 strip / list entries /
+//            tasks); when the run is used up lane 0 claims the next one with one atomicAdd and broadcasts it by shuffle;
+//   walk     all lanes step their ray in lock-step; a warp vote after every step leaves the loop once fewer than
+//            `refill_threshold` lanes are still walking;
+//   events   finished lanes write their result and become idle.
 #pragma once
 #include "../../include/voxelrt.h"
 #include "traverse.cuh"
 
 namespace vx {
 
-// Decodes a 2-D Morton code (x in even bits).
-__device__ __forceinline__ uint32_t compact1by1(uint32_t v) {
-    v &= 0x55555555u;
-    v = (v ^ (v >> 1)) & 0x33333333u;
-    v = (v ^ (v >> 2)) & 0x0f0f0f0fu;
-    v = (v ^ (v >> 4)) & 0x00ff00ffu;
-    v = (v ^ (v >> 8)) & 0x0000ffffu;
-    return v;
-}
-
 struct RenderArgs {
     Scene scene;
     RenderUniforms u;
-    float4* frame;                // RGBA32F, row 0 = bottom (world.glsl:140)
+    float4* frame;                // RGBA32F, row 0 = bottom (world.glsl:140); may be a peer GPU's memory (write-only here)
+    float4* hit0;                 // per pixel slot: {dst, value, u, v}
+    float4* hit1;                 // per pixel slot: {pos.x, pos.y, pos.z, flags}  flags: bits 0-2 face, bit 3 hit
+    float4* sh0;                  // shadow list: {origin.xyz, diffuse+specular}
+    float4* sh1;                  // shadow list: res.color
+    uint32_t* sh_pix;             // shadow list: pixel index (y * width + x)
+    unsigned int* shadow_count;   // entries in the shadow list
     Counters* counters;
-    unsigned int* work_counter;   // persistent kernels: next unclaimed strip
-    uint32_t tiles_x, tiles_y;    // frame size in 8x4-pixel warp tiles
-    uint32_t macro_x, macro_y;    // frame size in 4x4-tile (32x16 pixel) macro blocks
+    unsigned int* work_counter;   // persistent kernels: next unclaimed run
+    uint32_t macro_x, macro_y;    // frame size in 32x16-pixel macro blocks
     uint32_t shard_rank, shard_size;
-    uint32_t refill_threshold;    // leave the traversal loop when fewer lanes than this are still walking
+    uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
 };
 
 // Work units. The frame is cut into macro blocks of 32x16 pixels (row-major over the frame; a shard owns every
 // shard_size-th block). A macro block is 4 strips of 32x4 pixels, a strip is 4 warp tiles of 8x4 pixels laid side by
 // side, and pixel p of a strip is lane p%32 of tile p/32: consecutive work indices, consecutive pixels of a warp and
 // consecutive tiles of a strip are all spatial neighbours (coherent rays, shared nodes in L1).
+// Pixel slot (index into hit0/hit1) = strip * 128 + p.
 __device__ __forceinline__ bool strip_origin(const RenderArgs& a, uint32_t strip, uint32_t& x0, uint32_t& y0) {
     const uint32_t macro = strip >> 2;
     if (a.shard_size > 1 && (macro % a.shard_size) != a.shard_rank) return false;
@@ -62,7 +70,7 @@ __device__ __forceinline__ void flush_counters(Counters* g, const Counters& c) {
     }
 }
 
-// texels the shader's textureLod reads for this lod (for the counters when the fetch itself is skipped)
+// texels the shader's textureLod reads for this lod (the counters follow the shader, which samples at every leaf test)
 __device__ __forceinline__ uint32_t logical_texels(const TexInfo* ti, float lod) {
     if (!(lod > 0.0f)) return 1;
     const uint32_t levels = __ldg(&ti->levels);
@@ -71,75 +79,72 @@ __device__ __forceinline__ uint32_t logical_texels(const TexInfo* ti, float lod)
     const uint32_t d1 = (uint32_t)fl, d2 = (d1 + 1 < levels) ? d1 + 1 : levels - 1;
     return (d2 == d1 || l - fl == 0.0f) ? 4 : 8;
 }
+__device__ __forceinline__ float lod_of_dst(float dst) {   // svo.esvo.glsl:235
+    float sm = gl_clamp((dst - 15.0f) / (25.0f - 15.0f), 0.0f, 1.0f);
+    sm = (sm * sm) * (3.0f - 2.0f * sm);
+    return (sm * (dst - 15.0f)) * 0.05f;
+}
 
-// Evaluates the leaf a render ray stopped at (svo.esvo.glsl:185-265 with cast_translucent = true).
-// need_color = false (shadow rays): only "alpha > 0" matters, and for layers whose every texel is opaque that is
-// known without touching the texture.
+// Translucency rule of a render ray at a leaf whose material is not known to be opaque (svo.esvo.glsl:227-242, 264-265):
+// samples the texel and applies "alpha > 0 and first of its kind". Out of line and rare (glass, leaves, water).
+__device__ __noinline__ bool translucent_leaf_accepts(const TexInfo* tex, const Material* materials, uint32_t n_materials, const float* unorm,
+                                                      uint32_t value, int face_id, float u, float v, float dst, uint32_t last_leaf) {
+    const Material* m = materials + (value < n_materials ? value : n_materials - 1);
+    int tex_id = __ldg(&m->tex_side);
+    if (face_id == 3) tex_id = __ldg(&m->tex_top);
+    else if (face_id == 2) tex_id = __ldg(&m->tex_bottom);
+    uint32_t nf = 0;
+    const float4 c = texture_lod(tex, unorm, u, v, tex_id, lod_of_dst(dst), &nf);
+    const bool first_of_kind = value != last_leaf;   // adjacent_leaf_count == 0 <=> last_leaf == 0xffffffff (never a block id)
+    return c.w > 0.0f && first_of_kind;
+}
+
+// Render-ray leaf candidate (cast_translucent = true). Returns true when the leaf is the hit; fills g (and value).
 template <bool COUNT>
-__device__ __forceinline__ bool render_leaf(Ray& r, const Scene& s, const float* unorm, float inv_scale, bool need_color, Leaf& g, float& tex_lod,
-                                            float4& color, Counters& cnt) {
-    leaf_geom<COUNT>(r, s, inv_scale, g, cnt);
-    int tex_id;
-    leaf_texture(s, g, tex_id, tex_lod);
-    bool alpha_pos;
-    if (need_color || !layer_is_opaque(s.tex, tex_id)) {
-        uint32_t nf = 0;
-        color = texture_lod(s.tex, unorm, g.u, g.v, tex_id, tex_lod, &nf);          // :237
-        if (COUNT) cnt.tex_fetches += nf;
-        alpha_pos = color.w > 0.0f;
-    } else {
-        if (COUNT) cnt.tex_fetches += logical_texels(s.tex, tex_lod);
-        alpha_pos = true;
-    }
-    const bool first_of_kind = r.adjacent_leaf_count == 0 || g.value != r.last_leaf_value;   // :241
-    if (alpha_pos && first_of_kind) return true;                                     // :242
-    ++r.adjacent_leaf_count;                                                         // :264-265
-    r.last_leaf_value = g.value;
+__device__ __forceinline__ bool render_leaf(const Walk& w, const Scene& s, const Smem& sm, float inv_scale, uint32_t& last_leaf, Leaf& g, Counters& cnt) {
+    g.value = leaf_value(w, s);
+    if (COUNT) { cnt.leaf_tests++; cnt.tex_fetches += logical_texels(s.tex, lod_of_dst(w.t_min * inv_scale)); }
+    const bool opaque = g.value < 64u && ((s.opaque_materials >> g.value) & 1ull);
+    const float* c = sm.cold;
+    leaf_geom(w, c[0], c[VX_THREADS], c[2 * VX_THREADS], c[3 * VX_THREADS], c[4 * VX_THREADS], c[5 * VX_THREADS], inv_scale, g);
+    if (opaque) return true;
+    if (translucent_leaf_accepts(s.tex, s.materials, s.n_materials, sm.unorm, g.value, g.face_id, g.u, g.v, g.dst, last_leaf)) return true;
+    last_leaf = g.value;                                                      // :264-265
     return false;
 }
 
-// ---- persistent render kernel ----------------------------------------------------------------------------------------
-// grid = SMs x resident CTAs/SM, 4 warps per CTA. Every warp runs this loop until the frame is done:
-//   refill   idle lanes take the next pixels of the warp's current strip (32x4 px); when the strip is used up lane 0
-//            claims the next one with a single atomicAdd and broadcasts it by shuffle (warp-level work fetch);
-//   walk     all lanes step their ray (primary or shadow — same code, no divergence between the two kinds) in lock-step;
-//            a warp vote after every step leaves the loop once fewer than `refill_threshold` lanes are still walking;
-//   events   lanes that stopped at a leaf candidate evaluate it together (value, face, uv, material, texture, alpha);
-//            accepted primary hits are shaded in place and re-armed as shadow rays, finished pixels are written with a
-//            streaming 16-byte store and the lane becomes idle again.
-#define PH_IDLE 0
-#define PH_PRIMARY 1
-#define PH_SHADOW 2
+// Walk-loop exit vote: keep stepping while at least `thresh` lanes are still walking. thresh == 1 (the default: run every
+// ray of the warp to its end, then refill all 32 lanes at once) needs no population count.
+__device__ __forceinline__ bool keep_walking(bool walking, int thresh) {
+    if (thresh <= 1) return __any_sync(0xffffffffu, walking);
+    return __popc(__ballot_sync(0xffffffffu, walking)) >= thresh;
+}
 
-// MINB = resident CTAs per SM the register allocator must allow (5 -> 96 regs, 6 -> 80, 8 -> 64): occupancy against
-// spills is an empirical trade, so the variants are all built and chosen at run time (vx_set_option 4).
-template <bool VEC, bool COUNT, int MINB>
-__global__ void __launch_bounds__(128, MINB) render_persistent_kernel(RenderArgs a) {
+// ---- primary rays ------------------------------------------------------------------------------------------------------
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene, smem_raw);
-    const uint32_t lane = threadIdx.x & 31, tid = threadIdx.x, nthr = blockDim.x;
+    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
     const float inv_scale = 1.0f / octree_scale;
     const uint32_t n_strips = a.macro_x * a.macro_y * 4u;
-    float* cold = sm.cold + tid;   // cold[k * nthr]: 0-3 colour, 4 lit, 5-7 primary direction
+    float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
-    // warp-uniform work state
-    uint32_t strip_x0 = 0, strip_y0 = 0, next_px = 128;
+    uint32_t strip = 0, strip_x0 = 0, strip_y0 = 0, next_px = 128;   // warp-uniform
     bool more_work = true;
-    // lane state
-    int phase = PH_IDLE, ev = RAY_CONTINUE;
-    bool after_leaf = false;
-    uint32_t pix = 0;
-    Ray r;
+    bool active = false;
+    int ev = RAY_CONTINUE;
+    uint32_t slot = 0, last_leaf = 0xffffffffu;
+    Walk w;
 
     for (;;) {
         // ---------------------------------------------------------------- refill
-        unsigned want = __ballot_sync(0xffffffffu, phase == PH_IDLE);
+        unsigned want = __ballot_sync(0xffffffffu, !active);
         while (want && more_work) {
             if (next_px >= 128) {
-                uint32_t strip = 0;
                 if (lane == 0) strip = atomicAdd(a.work_counter, 1u);
                 strip = __shfl_sync(0xffffffffu, strip, 0);
                 if (strip >= n_strips) { more_work = false; break; }
@@ -152,137 +157,205 @@ __global__ void __launch_bounds__(128, MINB) render_persistent_kernel(RenderArgs
                 uint32_t gx, gy;
                 strip_pixel(strip_x0, strip_y0, next_px + my_rank, gx, gy);
                 if (gx < a.u.width && gy < a.u.height) {
-                    float ox, oy, oz, dx, dy, dz;
+                    float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-                    cold[5 * nthr] = dx; cold[6 * nthr] = dy; cold[7 * nthr] = dz;
-                    ray_init(r, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f);
-                    pix = gy * a.u.width + gx;
-                    phase = PH_PRIMARY; ev = RAY_CONTINUE; after_leaf = false;
-                    cnt.primary_rays++;
+                    walk_init(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
+                    cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
+                    cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
+                    slot = strip * 128u + next_px + my_rank;
+                    active = true; ev = RAY_CONTINUE; last_leaf = 0xffffffffu;
+                    if (COUNT) cnt.primary_rays++;
                 }
             }
             next_px += n_take;
-            want = __ballot_sync(0xffffffffu, phase == PH_IDLE);
+            want = __ballot_sync(0xffffffffu, !active);
         }
-        const unsigned busy = __ballot_sync(0xffffffffu, phase != PH_IDLE);
+        const unsigned busy = __ballot_sync(0xffffffffu, active);
         if (!busy) break;
         const int thresh = min((int)a.refill_threshold, __popc(busy));
 
         // ---------------------------------------------------------------- walk
         for (;;) {
-            if (phase != PH_IDLE && ev == RAY_CONTINUE) {
-                ev = ray_step<false, VEC, COUNT>(r, a.scene, sm.stack, cnt, after_leaf);
-                after_leaf = false;
-            }
-            if (__popc(__ballot_sync(0xffffffffu, phase != PH_IDLE && ev == RAY_CONTINUE)) < thresh) break;
+            if (active && ev == RAY_CONTINUE) ev = walk_step<false, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
+            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
         }
 
         // ---------------------------------------------------------------- events
         if (ev == RAY_LEAF) {
-            Leaf g; float tex_lod; float4 c;
-            if (render_leaf<COUNT>(r, a.scene, sm.unorm, inv_scale, phase == PH_PRIMARY, g, tex_lod, c, cnt)) {
-                if (phase == PH_PRIMARY) {
-                    float px, py, pz;
-                    leaf_pos(r, g, inv_scale, px, py, pz);
-                    Shade sh;
-                    sh.r = c.x; sh.g = c.y; sh.b = c.z; sh.a = c.w;
-                    uint32_t nf = 0;
-                    shade_hit(a.scene, sm.unorm, a.u, g, tex_lod, px, py, pz, sh, &nf);
-                    if (COUNT) cnt.tex_fetches += nf;
-                    if (sh.done) {
-                        __stcs(a.frame + pix, make_float4(sh.r, sh.g, sh.b, sh.a));
-                        phase = PH_IDLE;
-                    } else if (sh.want_shadow) {
-                        cold[0] = sh.r; cold[nthr] = sh.g; cold[2 * nthr] = sh.b; cold[3 * nthr] = sh.a; cold[4 * nthr] = sh.lit;
-                        ray_init(r, a.scene, octree_scale, sh.sox, sh.soy, sh.soz, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f);
-                        phase = PH_SHADOW;
-                        cnt.shadow_rays++;
-                    } else {
-                        __stcs(a.frame + pix, shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f));
-                        phase = PH_IDLE;
-                    }
-                } else {   // the shadow ray is blocked
-                    __stcs(a.frame + pix, shade_finish(a.u, cold[0], cold[nthr], cold[2 * nthr], cold[3 * nthr], cold[4 * nthr], 0.0f));
-                    phase = PH_IDLE;
-                }
+            Leaf g;
+            if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
+                float px, py, pz;
+                leaf_pos(w.t_min, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS], g,
+                         inv_scale, px, py, pz);
+                __stcs(a.hit0 + slot, make_float4(g.dst, __uint_as_float(g.value), g.u, g.v));
+                __stcs(a.hit1 + slot, make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id)));
+                active = false; ev = RAY_CONTINUE;
             } else {
-                after_leaf = true;   // translucent / repeated leaf: resume this iteration at ADVANCE
+                ev = walk_skip_leaf<VX_THREADS>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
-            ev = RAY_CONTINUE;
         } else if (ev == RAY_MISS) {
-            if (phase == PH_PRIMARY) __stcs(a.frame + pix, sky_color(cold[5 * nthr], cold[6 * nthr], cold[7 * nthr]));
-            else __stcs(a.frame + pix, shade_finish(a.u, cold[0], cold[nthr], cold[2 * nthr], cold[3 * nthr], cold[4 * nthr], 1.0f));
-            phase = PH_IDLE;
-            ev = RAY_CONTINUE;
+            __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            active = false; ev = RAY_CONTINUE;
         }
     }
-    flush_counters(a.counters, cnt);
+    if (COUNT) flush_counters(a.counters, cnt);
 }
 
-// ---- simple render kernel: one thread per pixel, whole pipeline sequentially (A/B baseline) --------------------------
-// Block = 128 threads = 4 warps = the 4 tiles of one 32x4 strip; blockIdx = strip index.
-template <bool VEC, bool COUNT>
-__device__ __forceinline__ bool trace_render_ray(Ray& r, const Scene& s, const Smem& sm, float inv_scale, bool need_color, Leaf& g, float& tex_lod,
-                                                 float4& c, Counters& cnt) {
-    bool after_leaf = false;
-    for (;;) {
-        const int ev = ray_step<false, VEC, COUNT>(r, s, sm.stack, cnt, after_leaf);
-        after_leaf = false;
-        if (ev == RAY_CONTINUE) continue;
-        if (ev == RAY_MISS) return false;
-        if (render_leaf<COUNT>(r, s, sm.unorm, inv_scale, need_color, g, tex_lod, c, cnt)) return true;
-        after_leaf = true;
-    }
-}
-
-template <bool VEC, bool COUNT>
-__global__ void __launch_bounds__(128) render_simple_kernel(RenderArgs a) {
+// ---- shading ---------------------------------------------------------------------------------------------------------------
+// grid = owned strips, block = 128 threads = the 128 pixels of one 32x4 strip (4 warp tiles of 8x4).
+template <bool COUNT>
+__global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene, smem_raw);
-    uint32_t x0, y0, gx = 0, gy = 0;
-    const bool have = strip_origin(a, blockIdx.x, x0, y0);
+    const Smem sm = make_smem(0, smem_raw, false);
+    __shared__ unsigned int s_warp_count[VX_THREADS / 32];
+    __shared__ unsigned int s_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t strip = (a.shard_size > 1) ? (((blockIdx.x >> 2) * a.shard_size + a.shard_rank) << 2 | (blockIdx.x & 3u)) : blockIdx.x;
+    uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
+    const bool have = (strip >> 2) < a.macro_x * a.macro_y && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
+    const bool live = have && gx < a.u.width && gy < a.u.height;
     Counters cnt = {0, 0, 0, 0, 0, 0};
-    if (have && gx < a.u.width && gy < a.u.height) {
-        const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
-        const float inv_scale = 1.0f / octree_scale;
-        float ox, oy, oz, dx, dy, dz;
-        primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-        Ray r; Leaf g; float tex_lod; float4 c;
-        ray_init(r, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f);
-        cnt.primary_rays = 1;
-        float4 color;
-        if (trace_render_ray<VEC, COUNT>(r, a.scene, sm, inv_scale, true, g, tex_lod, c, cnt)) {
-            float px, py, pz;
-            leaf_pos(r, g, inv_scale, px, py, pz);
+    bool want_shadow = false;
+    float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
+    const uint32_t pix = gy * a.u.width + gx;
+    if (live) {
+        const uint32_t slot = strip * 128u + threadIdx.x;
+        const float4 h1 = __ldcs(a.hit1 + slot);
+        const uint32_t flags = __float_as_uint(h1.w);
+        if (flags & 8u) {
+            const float4 h0 = __ldcs(a.hit0 + slot);
+            Leaf g;
+            g.dst = h0.x; g.value = __float_as_uint(h0.y); g.u = h0.z; g.v = h0.w; g.face_id = (int)(flags & 7u);
+            int tex_id; float tex_lod;
+            leaf_texture(a.scene, g, tex_id, tex_lod);
+            uint32_t nf = 0;
+            const float4 c = texture_lod(a.scene.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // svo.esvo.glsl:237 (counted by the trace kernel)
             Shade sh;
             sh.r = c.x; sh.g = c.y; sh.b = c.z; sh.a = c.w;
-            uint32_t nf = 0;
-            shade_hit(a.scene, sm.unorm, a.u, g, tex_lod, px, py, pz, sh, &nf);
+            nf = 0;
+            shade_hit(a.scene, sm.unorm, a.u, g, tex_lod, h1.x, h1.y, h1.z, sh, &nf);
             if (COUNT) cnt.tex_fetches += nf;
             if (sh.done) {
-                color = make_float4(sh.r, sh.g, sh.b, sh.a);
+                __stcs(a.frame + pix, make_float4(sh.r, sh.g, sh.b, sh.a));
+            } else if (sh.want_shadow) {
+                want_shadow = true;
+                s0 = make_float4(sh.sox, sh.soy, sh.soz, sh.lit);
+                s1 = make_float4(sh.r, sh.g, sh.b, sh.a);
             } else {
-                float shadow = 1.0f;
-                if (sh.want_shadow) {
-                    cnt.shadow_rays = 1;
-                    ray_init(r, a.scene, octree_scale, sh.sox, sh.soy, sh.soz, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f);
-                    Leaf g2; float lod2; float4 c2;
-                    shadow = trace_render_ray<VEC, COUNT>(r, a.scene, sm, inv_scale, false, g2, lod2, c2, cnt) ? 0.0f : 1.0f;
-                }
-                color = shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, shadow);
+                __stcs(a.frame + pix, shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f));
             }
         } else {
-            color = sky_color(dx, dy, dz);
+            float ox, oy, oz, dx, dy, dz;
+            primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
+            __stcs(a.frame + pix, sky_color(dx, dy, dz));
         }
-        a.frame[(size_t)gy * a.u.width + gx] = color;
     }
-    flush_counters(a.counters, cnt);
+    // compact the shadow rays of this strip into the global list: one atomicAdd per CTA, strip order kept inside it
+    const unsigned m = __ballot_sync(0xffffffffu, want_shadow);
+    if (lane == 0) s_warp_count[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int k = 0; k < VX_THREADS / 32; ++k) tot += s_warp_count[k];
+        s_base = tot ? atomicAdd(a.shadow_count, tot) : 0u;
+    }
+    __syncthreads();
+    if (want_shadow) {
+        unsigned off = s_base + __popc(m & ((1u << lane) - 1u));
+        for (uint32_t k = 0; k < warp; ++k) off += s_warp_count[k];
+        a.sh0[off] = s0; a.sh1[off] = s1; a.sh_pix[off] = pix;
+    }
+    if (COUNT) flush_counters(a.counters, cnt);
+}
+
+// ---- shadow rays -------------------------------------------------------------------------------------------------------------
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderArgs a) {
+    extern __shared__ uint32_t smem_raw[];
+    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
+    const float inv_scale = 1.0f / octree_scale;
+    const uint32_t n = *a.shadow_count;
+    float* cold = sm.cold;
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+
+    uint32_t run_base = 0, next = 128, run_len = 128;   // warp-uniform
+    bool more_work = true;
+    bool active = false;
+    int ev = RAY_CONTINUE;
+    uint32_t entry = 0, last_leaf = 0xffffffffu;
+    float lit = 0.0f;
+    Walk w;
+
+    for (;;) {
+        unsigned want = __ballot_sync(0xffffffffu, !active);
+        while (want && more_work) {
+            if (next >= run_len) {
+                if (lane == 0) run_base = atomicAdd(a.work_counter, 128u);
+                run_base = __shfl_sync(0xffffffffu, run_base, 0);
+                if (run_base >= n) { more_work = false; break; }
+                run_len = min(128u, n - run_base);
+                next = 0;
+            }
+            const uint32_t n_take = min((uint32_t)__popc(want), run_len - next);
+            const uint32_t my_rank = __popc(want & lanemask_lt);
+            if (((want >> lane) & 1u) && my_rank < n_take) {
+                entry = run_base + next + my_rank;
+                const float4 s0 = __ldcs(a.sh0 + entry);
+                float rox, roy, roz, rdx, rdy, rdz;
+                walk_init(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
+                cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
+                cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
+                lit = s0.w;
+                active = true; ev = RAY_CONTINUE; last_leaf = 0xffffffffu;
+                if (COUNT) cnt.shadow_rays++;
+            }
+            next += n_take;
+            want = __ballot_sync(0xffffffffu, !active);
+        }
+        const unsigned busy = __ballot_sync(0xffffffffu, active);
+        if (!busy) break;
+        const int thresh = min((int)a.refill_threshold, __popc(busy));
+
+        for (;;) {
+            if (active && ev == RAY_CONTINUE) ev = walk_step<false, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
+            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
+        }
+
+        if (ev != RAY_CONTINUE) {
+            bool done = true;
+            float shadow = 1.0f;                                     // world.glsl:83: res.t < 0 -> 1
+            if (ev == RAY_LEAF) {
+                Leaf g;
+                // fully opaque materials block the sun whatever the texel is; others go through the translucency rule
+                const uint32_t value = leaf_value(w, a.scene);
+                if (value < 64u && ((a.scene.opaque_materials >> value) & 1ull)) {
+                    if (COUNT) { cnt.leaf_tests++; cnt.tex_fetches += logical_texels(a.scene.tex, lod_of_dst(w.t_min * inv_scale)); }
+                    shadow = 0.0f;
+                } else if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
+                    shadow = 0.0f;
+                } else {
+                    ev = walk_skip_leaf<VX_THREADS>(w, a.scene, sm.stack);
+                    done = false;
+                }
+            }
+            if (done) {
+                const float4 c = __ldcs(a.sh1 + entry);
+                const uint32_t pix = __ldcs(a.sh_pix + entry);
+                __stcs(a.frame + pix, shade_finish(a.u, c.x, c.y, c.z, c.w, lit, shadow));
+                active = false; ev = RAY_CONTINUE;
+            }
+        }
+    }
+    if (COUNT) flush_counters(a.counters, cnt);
 }
 
 // ---- picker kernel: picker.glsl main() -------------------------------------------------------------------------------
-// Same scheme as the render kernel: warps claim runs of 128 consecutive tasks, lanes refill from the run as their ray
-// ends, so a warp is not held hostage by its longest ray (16 M random rays differ in length by 100x).
+// Same scheme: warps claim runs of 128 consecutive tasks, lanes refill from the run as their ray ends, so a warp is not
+// held hostage by its longest ray (16 M random rays differ in length by 100x).
 struct RaycastArgs {
     Scene scene;
     const float4* tasks;      // VxPickerTask = 3 x float4
@@ -293,28 +366,15 @@ struct RaycastArgs {
     uint32_t refill_threshold;
 };
 
-__device__ __forceinline__ void write_picker_result(float4* results, unsigned long long i, const Ray& r, const Leaf* g, float inv_scale) {
-    float4 o0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f), o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
-    if (g && g->dst > 0.0f) {                                          // picker.glsl:40 (res.t > 0)
-        float px, py, pz;
-        leaf_pos(r, *g, inv_scale, px, py, pz);
-        o0.x = g->dst; o0.y = __uint_as_float(r.inside_voxel);
-        o1 = make_float4(px, py, pz, 0.0f);
-        const int axis = g->face_id >> 1;
-        const float sgn = (g->face_id & 1) ? 1.0f : -1.0f;             // FACE_NORMALS, svo.glsl:2-9
-        o2 = make_float4(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f, 0.0f);
-    }
-    __stcs(results + 3 * i, o0); __stcs(results + 3 * i + 1, o1); __stcs(results + 3 * i + 2, o2);
-}
-
-template <bool VEC, bool COUNT>
-__global__ void __launch_bounds__(128) raycast_kernel(RaycastArgs a) {
+template <bool COUNT>
+__global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene, smem_raw);
+    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
     const float inv_scale = 1.0f / octree_scale;
+    float* cold = sm.cold;
     Counters cnt = {0, 0, 0, 0, 0, 0};
     unsigned long long run_base = 0;
     uint32_t next = 128, run_len = 128;
@@ -322,7 +382,8 @@ __global__ void __launch_bounds__(128) raycast_kernel(RaycastArgs a) {
     bool active = false;
     int ev = RAY_CONTINUE;
     unsigned long long my_task = 0;
-    Ray r;
+    uint32_t last_leaf = 0xffffffffu;
+    Walk w;
 
     for (;;) {
         unsigned want = __ballot_sync(0xffffffffu, !active);
@@ -338,10 +399,13 @@ __global__ void __launch_bounds__(128) raycast_kernel(RaycastArgs a) {
             const uint32_t my_rank = __popc(want & lanemask_lt);
             if (((want >> lane) & 1u) && my_rank < n_take) {
                 my_task = run_base + next + my_rank;
-                const float4 t0 = __ldg(a.tasks + 3 * my_task), t1 = __ldg(a.tasks + 3 * my_task + 1), t2 = __ldg(a.tasks + 3 * my_task + 2);
-                ray_init(r, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x);
+                const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
+                float rox, roy, roz, rdx, rdy, rdz;
+                walk_init(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
+                cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
+                cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 active = true; ev = RAY_CONTINUE;
-                cnt.primary_rays++;
+                if (COUNT) cnt.primary_rays++;
             }
             next += n_take;
             want = __ballot_sync(0xffffffffu, !active);
@@ -350,22 +414,33 @@ __global__ void __launch_bounds__(128) raycast_kernel(RaycastArgs a) {
         if (!busy) break;
         const int thresh = min((int)a.refill_threshold, __popc(busy));
         for (;;) {
-            if (active && ev == RAY_CONTINUE) ev = ray_step<true, VEC, COUNT>(r, a.scene, sm.stack, cnt);
-            if (__popc(__ballot_sync(0xffffffffu, active && ev == RAY_CONTINUE)) < thresh) break;
+            if (active && ev == RAY_CONTINUE) ev = walk_step<true, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
+            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
         }
-        if (ev == RAY_LEAF) {
+        if (ev != RAY_CONTINUE) {
             // cast_translucent = false: the first leaf is the hit whatever its texel is (svo.esvo.glsl:241-242); the picker
-            // never reads the colour (picker.glsl:40-44), so the texture is not sampled at all.
-            Leaf g;
-            leaf_geom<COUNT>(r, a.scene, inv_scale, g, cnt);
-            write_picker_result(a.results, my_task, r, &g, inv_scale);
-            active = false; ev = RAY_CONTINUE;
-        } else if (ev == RAY_MISS) {
-            write_picker_result(a.results, my_task, r, nullptr, inv_scale);
+            // never reads value or colour (picker.glsl:40-44), so neither the leaf word nor the texture is fetched.
+            float4 o0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f), o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
+            if (ev == RAY_LEAF) {
+                if (COUNT) cnt.leaf_tests++;
+                Leaf g;
+                leaf_geom(w, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS], inv_scale, g);
+                if (g.dst > 0.0f) {                                        // picker.glsl:40 (res.t > 0)
+                    float px, py, pz;
+                    leaf_pos(w.t_min, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS],
+                             g, inv_scale, px, py, pz);
+                    o0.x = g.dst; o0.y = __uint_as_float((w.idx >> 8) & 1u);
+                    o1 = make_float4(px, py, pz, 0.0f);
+                    const int axis = g.face_id >> 1;
+                    const float sgn = (g.face_id & 1) ? 1.0f : -1.0f;      // FACE_NORMALS, svo.glsl:2-9
+                    o2 = make_float4(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f, 0.0f);
+                }
+            }
+            __stcs(a.results + 3 * my_task, o0); __stcs(a.results + 3 * my_task + 1, o1); __stcs(a.results + 3 * my_task + 2, o2);
             active = false; ev = RAY_CONTINUE;
         }
     }
-    flush_counters(a.counters, cnt);
+    if (COUNT) flush_counters(a.counters, cnt);
 }
 
 // ---- debug cast: svo.test.glsl main(), one thread, records every iteration --------------------------------------------
@@ -380,71 +455,69 @@ struct DebugArgs {
     uint32_t* n_frames;
 };
 
-// The step machine does not carry the shader's (ptr, parent_octant_idx); the debug kernel shadows them (plus their
-// stacks) next to it to emit reference-format frames.
-__global__ void debug_cast_kernel(DebugArgs a) {
+// The step function does not carry the shader's (ptr, parent_octant_idx); the debug kernel shadows them (plus their
+// stacks) next to it to emit reference-format frames. Launched <<<1, VX_THREADS>>>; thread 0 casts.
+__global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene, smem_raw);
+    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    if (threadIdx.x != 0) return;
     const Scene& s = a.scene;
     const float octree_scale = __uint_as_float(__ldg(s.desc - 1));
     const float inv_scale = 1.0f / octree_scale;
-    Ray r;
+    Walk w;
     Counters cnt = {0, 0, 0, 0, 0, 0};
-    ray_init(r, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst);
+    float rox, roy, roz, rdx, rdy, rdz;
+    walk_init(w, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst, rox, roy, roz, rdx, rdy, rdz);
     uint32_t ptr = 0, pidx = 0;
     uint32_t ptr_stack[VX_MAX_SCALE + 1], pidx_stack[VX_MAX_SCALE + 1];
     for (int i = 0; i <= VX_MAX_SCALE; ++i) { ptr_stack[i] = 0; pidx_stack[i] = 0; }
-    uint32_t n = 0;
-    bool after_leaf = false, hit = false;
+    uint32_t n = 0, last_leaf = 0xffffffffu;
+    bool hit = false;
     Leaf g; float tex_lod = 0.0f; float4 color = make_float4(0, 0, 0, 0);
     for (;;) {
-        const uint32_t oi = (uint32_t)((r.idx ^ (r.idx >> 4)) & 7);
-        const int scale_before = r.scale;
-        const uint32_t rec_before = r.rec;
-        if (!after_leaf) {
-            // the frame the shader emits at :175 for this iteration (if it gets past :152-156)
-            const bool will_run = !(r.max_dst >= 0.0f && r.t_min > r.max_dst) && r.steps < VX_MAX_STEPS;
-            if (will_run) {
-                if (n < a.frames_cap) {
-                    VxDebugFrame& f = a.frames[n];
-                    f.t_min = r.t_min * inv_scale; f.ptr = ptr; f.idx = oi; f.parent_octant_idx = pidx; f.scale = r.scale;
-                    f.is_child = (r.desc & ((1u << oi) << 8)) != 0; f.is_leaf = (r.desc & (1u << oi)) != 0;
-                    f.crossed_boundary = 0; f.next_ptr = 0;
-                }
-                ++n;
+        const uint32_t oi = (w.idx ^ (w.idx >> 4)) & 7u;
+        const int scale_before = w.scale;
+        const uint32_t rec_before = w.rec;
+        // the frame the shader emits at :175 for this iteration (if it gets past :152-156)
+        if (w.budget > 0 && !(w.t_min > w.limit)) {
+            if (n < a.frames_cap) {
+                VxDebugFrame& f = a.frames[n];
+                f.t_min = w.t_min * inv_scale; f.ptr = ptr; f.idx = oi; f.parent_octant_idx = pidx; f.scale = w.scale;
+                f.is_child = ((w.desc >> oi) & 0x100u) != 0; f.is_leaf = ((w.desc >> oi) & 1u) != 0;
+                f.crossed_boundary = 0; f.next_ptr = 0;
             }
+            ++n;
         }
-        const float h_before = r.h;
-        const float tcx = __fmaf_rn(r.px, r.tcx, -r.tbx), tcy = __fmaf_rn(r.py, r.tcy, -r.tby), tcz = __fmaf_rn(r.pz, r.tcz, -r.tbz);
+        const float h_before = w.h;
+        const float tcx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcy = __fmaf_rn(w.py, w.tcy, -w.tby), tcz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
         const float tc_max = tmin2(tmin2(tcx, tcy), tcz);
-        const int ev = ray_step<true, false, false>(r, s, sm.stack, cnt, after_leaf);
-        after_leaf = false;
-        if (ev == RAY_MISS) break;
+        int ev = walk_step<true, false, VX_THREADS>(w, s, sm.stack, last_leaf, cnt);
         if (ev == RAY_LEAF) {
-            leaf_geom<false>(r, s, inv_scale, g, cnt);
+            g.value = leaf_value(w, s);
+            leaf_geom(w, rox, roy, roz, rdx, rdy, rdz, inv_scale, g);
             int tex_id;
             leaf_texture(s, g, tex_id, tex_lod);
             uint32_t nf = 0;
             color = texture_lod(s.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // the shader samples in both modes (:237)
-            const bool first_of_kind = r.adjacent_leaf_count == 0 || g.value != r.last_leaf_value;
+            const bool first_of_kind = g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
-            ++r.adjacent_leaf_count; r.last_leaf_value = g.value;
-            after_leaf = true;
-            continue;
+            last_leaf = g.value;
+            ev = walk_skip_leaf<VX_THREADS>(w, s, sm.stack);
         }
-        if (r.scale == scale_before - 1) {            // PUSH happened
+        if (ev == RAY_MISS) break;
+        if (w.scale == scale_before - 1) {            // PUSH happened
             if (tc_max < h_before) { ptr_stack[scale_before] = ptr; pidx_stack[scale_before] = pidx; }
             ptr = rec_before; pidx = oi;
-        } else if (r.scale > scale_before) {          // POP happened
-            ptr = ptr_stack[r.scale]; pidx = pidx_stack[r.scale];
+        } else if (w.scale > scale_before) {          // POP happened
+            ptr = ptr_stack[w.scale]; pidx = pidx_stack[w.scale];
         }
     }
     VxOctreeResult& o = *a.result;
     o.t = -1.0f; o.value = 0; o.face_id = 0; o.pos[0] = o.pos[1] = o.pos[2] = 0; o.uv[0] = o.uv[1] = 0;
-    o.color[0] = o.color[1] = o.color[2] = o.color[3] = 0; o.lod = 0; o.inside_voxel = r.inside_voxel;
+    o.color[0] = o.color[1] = o.color[2] = o.color[3] = 0; o.lod = 0; o.inside_voxel = (w.idx >> 8) & 1u;
     if (hit) {
         o.t = g.dst; o.value = g.value; o.face_id = g.face_id;
-        leaf_pos(r, g, inv_scale, o.pos[0], o.pos[1], o.pos[2]);
+        leaf_pos(w.t_min, rox, roy, roz, rdx, rdy, rdz, g, inv_scale, o.pos[0], o.pos[1], o.pos[2]);
         o.uv[0] = g.u; o.uv[1] = g.v; o.lod = tex_lod;
         o.color[0] = color.x; o.color[1] = color.y; o.color[2] = color.z; o.color[3] = color.w;
     }
@@ -514,11 +587,11 @@ __global__ void __launch_bounds__(128) shard_copy_kernel(float4* frame, float4* 
 }
 
 // Applies a packed dirty set (n VxRange headers, then [24 head bytes][range 0 bytes][range 1 bytes]...) to the world
-// buffer of a replica. Byte-granular because ranges are only 4-byte aligned relative to each other.
+// buffer of a replica. Word-granular: every range offset/length is a multiple of 4.
 __global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes) {
     const VxRange* hdr = reinterpret_cast<const VxRange*>(packed);
     const uint32_t* payload = reinterpret_cast<const uint32_t*>(packed + (size_t)n_ranges * sizeof(VxRange));
-    uint32_t* w32 = reinterpret_cast<uint32_t*>(world);   // world + 0 is 8-byte aligned; every range offset/length is a multiple of 4
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(world);
     const unsigned long long words = payload_bytes / 4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {

@@ -58,122 +58,47 @@ struct TexInfo {
 
 // Everything a kernel needs to read the scene. Passed by value as a kernel parameter.
 struct Scene {
-    const uint32_t* __restrict__ desc;   // descriptors[] = world buffer + 4 bytes; desc[ptr] 16-B aligned when ptr % 4 == 1
-    uint32_t desc_words;                 // capacity in words (loads are clamped to it)
+    const uint32_t* __restrict__ desc;   // descriptors[] = world buffer + 4 bytes
+    uint32_t desc_words;                 // capacity in words
+    uint32_t max_rec;                    // desc_words - 12: largest record index whose 12 words are inside the buffer
     const Material* __restrict__ materials;
     uint32_t n_materials;
     const TexInfo* __restrict__ tex;
     uint32_t stack_levels;               // entries of the per-thread traversal stack (= SVO depth + 1, <= 23)
+    unsigned long long opaque_materials; // bit m set (m < 64): every texel of the three face textures of material m has alpha > 0,
+                                         // so a leaf of that material is accepted by the translucency rule (:241-242) without sampling
 };
 
 struct Counters {   // = VxFrameStats counters
     unsigned long long primary_rays, shadow_rays, steps, pushes, leaf_tests, tex_fetches;
 };
 
-// Per-thread traversal stack in SHARED memory, one column per thread: slot s of thread t lives at
-// base[s * stride + t]. Consecutive lanes hit consecutive banks whatever their (divergent) slot is.
-struct Stack {
-    uint32_t* rec;     // record of the octant at that level
-    uint32_t* desc;    // its child/leaf masks
-    float* t_max;
-    uint32_t stride;   // = blockDim.x
-    uint32_t levels;
-    __device__ __forceinline__ uint32_t slot(int scale) const {
-        uint32_t s = (uint32_t)(VX_MAX_SCALE - 1 - scale);
-        return (s < levels ? s : levels - 1) * stride + threadIdx.x;
-    }
-};
-
-// Shared-memory scratch of one CTA: traversal stacks, the unorm8 -> float table and per-thread cold state.
-struct Smem {
-    Stack stack;
-    const float* unorm;   // unorm[b] = b / 255.0f (IEEE division done once per CTA instead of once per channel fetch)
-    float* cold;          // COLD_WORDS floats per thread, [k * blockDim.x + tid]
-};
+// Shared-memory scratch of one CTA of VX_THREADS threads:
+//   stack   per-thread traversal stack, one column per thread: slot L word k of thread t at stack[(L*3 + k) * VX_THREADS + t]
+//           (k = 0 record, 1 child/leaf masks, 2 t_max). Consecutive lanes hit consecutive banks whatever their slot is.
+//   unorm   unorm[b] = b / 255.0f (IEEE division done once per CTA instead of once per channel fetch)
+//   cold    VX_COLD_WORDS floats per thread, [k * VX_THREADS + t]: ray origin/direction and other per-ray values that the
+//           hot loop never touches
+#define VX_THREADS 128
 #define VX_COLD_WORDS 8
-__host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, uint32_t threads) {
-    return ((size_t)3 * stack_levels * threads + 256 + (size_t)VX_COLD_WORDS * threads) * 4;
+struct Smem {
+    uint32_t* stack;
+    const float* unorm;
+    float* cold;
+};
+__host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, bool with_stack = true) {
+    return ((with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0) + 256 + (size_t)VX_COLD_WORDS * VX_THREADS) * 4;
 }
-__device__ __forceinline__ Smem make_smem(const Scene& s, uint32_t* base) {
+__device__ __forceinline__ Smem make_smem(uint32_t stack_levels, uint32_t* base, bool with_stack = true) {
     Smem m;
-    const uint32_t n = blockDim.x;
-    m.stack.stride = n; m.stack.levels = s.stack_levels;
-    m.stack.rec = base;
-    m.stack.desc = base + (size_t)s.stack_levels * n;
-    m.stack.t_max = reinterpret_cast<float*>(base + 2 * (size_t)s.stack_levels * n);
-    float* lut = reinterpret_cast<float*>(base + 3 * (size_t)s.stack_levels * n);
-    for (uint32_t i = threadIdx.x; i < 256; i += n) lut[i] = (float)i / 255.0f;
+    const size_t stack_words = with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0;
+    m.stack = base + threadIdx.x;
+    float* lut = reinterpret_cast<float*>(base + stack_words);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)i / 255.0f;
     m.unorm = lut;
-    m.cold = lut + 256;
+    m.cold = lut + 256 + threadIdx.x;
     __syncthreads();
     return m;
-}
-
-enum : int { RAY_CONTINUE = 0, RAY_LEAF = 1, RAY_MISS = 2 };
-
-// Per-ray registers.
-struct Ray {
-    float rox, roy, roz;      // origin in [1,2) space
-    float rdx, rdy, rdz;      // direction (epsilon-clamped)
-    float tcx, tcy, tcz;      // t_coef
-    float tbx, tby, tbz;      // t_bias
-    float px, py, pz;         // pos
-    float t_min, t_max, h;
-    float scale_exp2;
-    float max_dst;            // already scaled; < 0 = unlimited
-    int scale;
-    int idx;                  // bits 0-2: idx, bits 4-6: octant_mask
-    int steps;
-    uint32_t rec, desc;
-    uint32_t last_leaf_value;
-    int adjacent_leaf_count;
-    uint32_t inside_voxel;
-};
-
-// Geometry of a leaf candidate (svo.esvo.glsl:190-224, 233)
-struct Leaf {
-    uint32_t value;
-    int face_id;
-    float u, v;
-    float dst;
-    float qx, qy, qz, se;   // un-mirrored voxel corner and edge length in [1,2) space
-};
-
-__device__ __forceinline__ uint32_t ld_desc(const Scene& s, uint32_t i) {
-    i = i < s.desc_words ? i : s.desc_words - 1;   // robust-buffer-access style clamp
-    return __ldg(s.desc + i);
-}
-
-// 128-bit read-only load of 4 consecutive descriptor words; i must be 4-word aligned relative to a
-// record start (ptr % 4 == 1), which holds for every octant record the reference serializer emits.
-__device__ __forceinline__ uint4 ld_desc4(const Scene& s, uint32_t i) {
-    i = (i + 3 < s.desc_words) ? i : s.desc_words - 4;
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(s.desc + i));
-    return r;
-}
-
-__device__ __forceinline__ uint32_t sel4(const uint4& v, uint32_t k) {
-    uint32_t lo = (k & 1) ? v.y : v.x, hi = (k & 1) ? v.w : v.z;
-    return (k & 2) ? hi : lo;
-}
-
-// Child masks + child record pointer of child `oi` of the octant whose record is `rec`
-// (= the shader's descriptors[ptr + idx/2] field and get_octant_ptr, svo.esvo.glsl:9-16,168-171).
-template <bool VEC>
-__device__ __forceinline__ void fetch_child(const Scene& s, uint32_t rec, uint32_t oi, uint32_t& out_desc, uint32_t& out_rec) {
-    uint32_t wh, wb;
-    if (VEC && (rec & 3u) == 1u) {
-        uint4 hdr = ld_desc4(s, rec);
-        uint4 body = ld_desc4(s, rec + 4 + (oi & 4u));
-        wh = sel4(hdr, oi >> 1);
-        wb = sel4(body, oi & 3u);
-    } else {
-        wh = ld_desc(s, rec + (oi >> 1));
-        wb = ld_desc(s, rec + 4 + oi);
-    }
-    out_desc = (oi & 1u) ? (wh >> 16) : (wh & 0xffffu);
-    out_rec = (wb & 0x80000000u) ? (rec + 4 + oi + (wb & 0x7fffffffu)) : wb;
 }
 
 // ---------------------------------------------------------------- textures --
@@ -233,173 +158,212 @@ __device__ __noinline__ float4 texture_lod(const TexInfo* ti, const float* unorm
     return make_float4(mixf(c1.x, c2.x, f), mixf(c1.y, c2.y, f), mixf(c1.z, c2.z, f), mixf(c1.w, c2.w, f));
 }
 
-// -------------------------------------------------------------- traversal --
+enum : int { RAY_CONTINUE = 0, RAY_LEAF = 1, RAY_MISS = 2 };
 
-// svo.esvo.glsl:52-149. (ox,oy,oz) in SVO voxel space.
-__device__ __forceinline__ void ray_init(Ray& r, const Scene& s, float octree_scale, float ox, float oy, float oz, float dx, float dy,
-                                         float dz, float max_dst) {
-    r.rox = ox * octree_scale + 1.0f; r.roy = oy * octree_scale + 1.0f; r.roz = oz * octree_scale + 1.0f;
-    r.max_dst = max_dst * octree_scale;
+// Hot per-ray state of the traversal (registers). The ray's origin/direction are NOT part of it: they are only needed
+// when a leaf is evaluated and live in the per-thread cold area of shared memory (Smem::cold, slots 0-5).
+struct Walk {
+    float tcx, tcy, tcz;      // t_coef
+    float tbx, tby, tbz;      // t_bias
+    float px, py, pz;         // pos (mirrored space, [1,2))
+    float t_min, t_max, h;
+    float se;                 // scale_exp2 = 2^(scale-23)
+    float limit;              // max_dst in [1,2) space, +inf when unlimited (:153)
+    uint32_t rec, desc;       // record of the current octant, child/leaf masks of its children (bits 0-7 leaf, 8-15 child)
+    uint32_t idx;             // bits 0-2: child index in mirrored space; bits 4-6: octant_mask; bit 8: inside_voxel
+    int scale;
+    int budget;               // MAX_STEPS - iterations done (:152)
+};
+
+// Geometry of a leaf candidate (svo.esvo.glsl:190-224, 233)
+struct Leaf {
+    uint32_t value;
+    int face_id;
+    float u, v;
+    float dst;
+    float qx, qy, qz, se;   // un-mirrored voxel corner and edge length in [1,2) space
+};
+
+__device__ __forceinline__ uint32_t ld_desc(const Scene& s, uint32_t i) {
+    i = i < s.desc_words ? i : s.desc_words - 1;   // robust-buffer-access style clamp
+    return __ldg(s.desc + i);
+}
+
+// svo.esvo.glsl:52-149. (ox,oy,oz) in SVO voxel space. Also returns the [1,2)-space origin and the epsilon-clamped
+// direction (the leaf evaluation needs them, :210-224, :252-258).
+__device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_scale, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          float max_dst, float& rox, float& roy, float& roz, float& rdx, float& rdy, float& rdz) {
+    rox = ox * octree_scale + 1.0f; roy = oy * octree_scale + 1.0f; roz = oz * octree_scale + 1.0f;
+    const float md = max_dst * octree_scale;
+    w.limit = (md >= 0.0f) ? md : __int_as_float(0x7f800000);   // "max_dst >= 0 && t_min > max_dst" == "t_min > limit"
 
     const int sign_mask = (int)0x80000000u;
     const int eps_bits = __float_as_int(VX_EPSILON) & ~sign_mask;
     if (fabsf(dx) < VX_EPSILON) dx = __int_as_float(eps_bits | (__float_as_int(dx) & sign_mask));
     if (fabsf(dy) < VX_EPSILON) dy = __int_as_float(eps_bits | (__float_as_int(dy) & sign_mask));
     if (fabsf(dz) < VX_EPSILON) dz = __int_as_float(eps_bits | (__float_as_int(dz) & sign_mask));
-    r.rdx = dx; r.rdy = dy; r.rdz = dz;
+    rdx = dx; rdy = dy; rdz = dz;
 
-    r.tcx = 1.0f / -fabsf(dx); r.tcy = 1.0f / -fabsf(dy); r.tcz = 1.0f / -fabsf(dz);
-    r.tbx = r.tcx * r.rox; r.tby = r.tcy * r.roy; r.tbz = r.tcz * r.roz;
+    w.tcx = 1.0f / -fabsf(dx); w.tcy = 1.0f / -fabsf(dy); w.tcz = 1.0f / -fabsf(dz);
+    w.tbx = w.tcx * rox; w.tby = w.tcy * roy; w.tbz = w.tcz * roz;
 
-    int octant_mask = 0;
-    if (dx > 0) { octant_mask ^= 1; r.tbx = 3.0f * r.tcx - r.tbx; }
-    if (dy > 0) { octant_mask ^= 2; r.tby = 3.0f * r.tcy - r.tby; }
-    if (dz > 0) { octant_mask ^= 4; r.tbz = 3.0f * r.tcz - r.tbz; }
+    uint32_t octant_mask = 0;
+    if (dx > 0) { octant_mask ^= 1; w.tbx = 3.0f * w.tcx - w.tbx; }
+    if (dy > 0) { octant_mask ^= 2; w.tby = 3.0f * w.tcy - w.tby; }
+    if (dz > 0) { octant_mask ^= 4; w.tbz = 3.0f * w.tcz - w.tbz; }
 
-    const float t_min = tmax2(tmax2(2.0f * r.tcx - r.tbx, 2.0f * r.tcy - r.tby), 2.0f * r.tcz - r.tbz);
-    r.t_min = tmax2(0.0f, t_min);
-    r.t_max = tmin2(tmin2(r.tcx - r.tbx, r.tcy - r.tby), r.tcz - r.tbz);
-    r.h = r.t_max;
+    const float t_min = tmax2(tmax2(2.0f * w.tcx - w.tbx, 2.0f * w.tcy - w.tby), 2.0f * w.tcz - w.tbz);
+    w.t_min = tmax2(0.0f, t_min);
+    w.t_max = tmin2(tmin2(w.tcx - w.tbx, w.tcy - w.tby), w.tcz - w.tbz);
+    w.h = w.t_max;
 
-    int idx = 0;
-    r.px = 1.0f; r.py = 1.0f; r.pz = 1.0f;
-    if (r.t_min < 1.5f * r.tcx - r.tbx) { idx ^= 1; r.px = 1.5f; }
-    if (r.t_min < 1.5f * r.tcy - r.tby) { idx ^= 2; r.py = 1.5f; }
-    if (r.t_min < 1.5f * r.tcz - r.tbz) { idx ^= 4; r.pz = 1.5f; }
-    r.idx = idx | (octant_mask << 4);
+    uint32_t idx = 0;
+    w.px = 1.0f; w.py = 1.0f; w.pz = 1.0f;
+    if (w.t_min < 1.5f * w.tcx - w.tbx) { idx ^= 1; w.px = 1.5f; }
+    if (w.t_min < 1.5f * w.tcy - w.tby) { idx ^= 2; w.py = 1.5f; }
+    if (w.t_min < 1.5f * w.tcz - w.tbz) { idx ^= 4; w.pz = 1.5f; }
+    w.idx = idx | (octant_mask << 4);
 
-    r.scale = VX_MAX_SCALE - 1;
-    r.scale_exp2 = 0.5f;
-    r.steps = 0;
-    r.last_leaf_value = 0xffffffffu;
-    r.adjacent_leaf_count = 0;
-    r.inside_voxel = 0;
+    w.scale = VX_MAX_SCALE - 1;
+    w.se = 0.5f;
+    w.budget = VX_MAX_STEPS;
 
     // state (ptr=0, parent_octant_idx=0): the preamble's child 0 = world root (esvo.rs:179-188)
     const uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
-    r.desc = w0 & 0xffffu;
-    r.rec = (w4 & 0x80000000u) ? (4u + (w4 & 0x7fffffffu)) : w4;
+    w.desc = w0 & 0xffffu;
+    const uint32_t root = (w4 & 0x80000000u) ? (4u + (w4 & 0x7fffffffu)) : w4;
+    w.rec = root < s.max_rec ? root : s.max_rec;
 }
 
-// One iteration of the loop at svo.esvo.glsl:152-392, minus the leaf evaluation.
-//   returns RAY_LEAF when the current child is a leaf with t_min > 0 (:185): the caller evaluates it with leaf_geom()
-//   and either finishes the ray or calls ray_step again with after_leaf = true, which resumes THAT iteration at its
-//   ADVANCE phase (:324) after the bookkeeping of a rejected translucent leaf (:264-265).
-//   LIMITED: the ray has a max_dst (:153); render rays do not.
-template <bool LIMITED, bool VEC, bool COUNT>
-__device__ __forceinline__ int ray_step(Ray& r, const Scene& s, const Stack& st, Counters& cnt, bool after_leaf = false) {
-    if (!after_leaf) {
-        if (LIMITED && r.max_dst >= 0.0f && r.t_min > r.max_dst) return RAY_MISS;   // :153
-        if (r.steps >= VX_MAX_STEPS) return RAY_MISS;                                // :152
-        r.steps++;
-        if (COUNT) cnt.steps++;
-    }
-    const float tcornx = __fmaf_rn(r.px, r.tcx, -r.tbx), tcorny = __fmaf_rn(r.py, r.tcy, -r.tby), tcornz = __fmaf_rn(r.pz, r.tcz, -r.tbz);   // :159
-    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                                                                                // :161
-
-    if (!after_leaf) {
-        const uint32_t octant_idx = (uint32_t)((r.idx ^ (r.idx >> 4)) & 7);   // :164  idx ^ octant_mask
-        const uint32_t bit = 1u << octant_idx;
-        const bool is_child = (r.desc & (bit << 8)) != 0;                     // :172
-        const bool is_leaf = (r.desc & bit) != 0;                             // :173
-
-        if (is_child && r.t_min <= r.t_max) {                                 // :178
-            if (is_leaf) {
-                if (r.t_min > 0.0f) return RAY_LEAF;                          // :185
-                if (r.t_min == 0.0f) r.inside_voxel = 1;                      // :180
-            }
-            // :266-312 — also taken by a leaf at t_min == 0 (origin inside a voxel), see SURVEY Appendix B
-            const float half_scale = r.scale_exp2 * 0.5f;                     // :274
-            const float tv_max = tmin2(r.t_max, tc_max);                      // :278
-            if (r.t_min <= tv_max) {                                          // :280  PUSH
-                if (COUNT) cnt.pushes++;
-                if (tc_max < r.h) {                                           // :284-288
-                    const uint32_t sl = st.slot(r.scale);
-                    st.rec[sl] = r.rec; st.desc[sl] = r.desc; st.t_max[sl] = r.t_max;
-                }
-                r.h = tc_max;                                                 // :289
-                uint32_t nd, nr;
-                fetch_child<VEC>(s, r.rec, octant_idx, nd, nr);               // :292 (+ the :168 read of the next iterations)
-                r.rec = nr; r.desc = nd;
-                const float tcx_ = __fmaf_rn(half_scale, r.tcx, tcornx), tcy_ = __fmaf_rn(half_scale, r.tcy, tcorny),
-                            tcz_ = __fmaf_rn(half_scale, r.tcz, tcornz);      // :275
-                --r.scale; r.scale_exp2 = half_scale;                         // :295-297
-                int idx = 0;                                                  // :301-304
-                if (r.t_min < tcx_) { idx ^= 1; r.px += half_scale; }
-                if (r.t_min < tcy_) { idx ^= 2; r.py += half_scale; }
-                if (r.t_min < tcz_) { idx ^= 4; r.pz += half_scale; }
-                r.idx = (r.idx & 0x70) | idx;
-                r.t_max = tv_max;                                             // :307
-                return RAY_CONTINUE;                                          // :310
-            }
-        } else {
-            r.adjacent_leaf_count = 0;                                        // :315-316
-            r.last_leaf_value = 0xffffffffu;
-        }
-    }
-
-    int step_mask = 0;                                                        // :324-327  ADVANCE
-    if (tc_max >= tcornx) { step_mask ^= 1; r.px -= r.scale_exp2; }
-    if (tc_max >= tcorny) { step_mask ^= 2; r.py -= r.scale_exp2; }
-    if (tc_max >= tcornz) { step_mask ^= 4; r.pz -= r.scale_exp2; }
-    r.t_min = tc_max;                                                         // :330
-    r.idx ^= step_mask;                                                       // :331
-
-    if ((r.idx & step_mask) != 0) {                                           // :335  POP
+// One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate.
+//   RAY_LEAF: the current child is a leaf with t_min > 0 (:185). The caller evaluates it and either finishes the ray or
+//             calls walk_advance() (the ADVANCE/POP tail of THIS iteration, :324-391) and goes on stepping.
+//   `stk` = this thread's column of the shared-memory stack: slot L word k lives at stk[(L*3 + k) * STRIDE].
+// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
+// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
+template <int STRIDE>
+__device__ __forceinline__ bool walk_advance(Walk& w, const uint32_t* stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
+    uint32_t step_mask = 0;                                                   // :324-327  ADVANCE
+    if (tc_max >= tcornx) { step_mask ^= 1; w.px -= w.se; }
+    if (tc_max >= tcorny) { step_mask ^= 2; w.py -= w.se; }
+    if (tc_max >= tcornz) { step_mask ^= 4; w.pz -= w.se; }
+    w.t_min = tc_max;                                                         // :330
+    w.idx ^= step_mask;                                                       // :331
+    if ((w.idx & step_mask) != 0) {                                           // :335  POP
         uint32_t differing_bits = 0;                                          // :347-350
-        if (step_mask & 1) differing_bits |= __float_as_uint(r.px) ^ __float_as_uint(r.px + r.scale_exp2);
-        if (step_mask & 2) differing_bits |= __float_as_uint(r.py) ^ __float_as_uint(r.py + r.scale_exp2);
-        if (step_mask & 4) differing_bits |= __float_as_uint(r.pz) ^ __float_as_uint(r.pz + r.scale_exp2);
-        r.scale = 31 - __clz(differing_bits);                                 // :360 findMSB
-        r.scale_exp2 = __int_as_float((r.scale - VX_MAX_SCALE + 127) << 23);  // :361 exp2(scale - 23)
-        if (r.scale >= VX_MAX_SCALE) return RAY_MISS;                         // :365
-        const uint32_t sl = st.slot(r.scale);                                 // :370-372
-        r.rec = st.rec[sl]; r.desc = st.desc[sl]; r.t_max = st.t_max[sl];
-        const int shx = __float_as_int(r.px) >> r.scale, shy = __float_as_int(r.py) >> r.scale, shz = __float_as_int(r.pz) >> r.scale;   // :377-382
-        r.px = __int_as_float(shx << r.scale); r.py = __int_as_float(shy << r.scale); r.pz = __int_as_float(shz << r.scale);
-        r.idx = (r.idx & 0x70) | (shx & 1) | ((shy & 1) << 1) | ((shz & 1) << 2);   // :388
-        r.h = 0.0f;                                                           // :390
+        if (step_mask & 1) differing_bits |= __float_as_uint(w.px) ^ __float_as_uint(w.px + w.se);
+        if (step_mask & 2) differing_bits |= __float_as_uint(w.py) ^ __float_as_uint(w.py + w.se);
+        if (step_mask & 4) differing_bits |= __float_as_uint(w.pz) ^ __float_as_uint(w.pz + w.se);
+        const int scale = 31 - __clz(differing_bits);                         // :360 findMSB
+        w.scale = scale;
+        w.se = __int_as_float((scale - VX_MAX_SCALE + 127) << 23);            // :361 exp2(scale - 23)
+        if (scale >= VX_MAX_SCALE) return false;                              // :365
+        uint32_t lvl = (uint32_t)(VX_MAX_SCALE - 1 - scale);                  // :370-372
+        lvl = lvl < stack_levels ? lvl : stack_levels - 1;
+        const uint32_t* sl = stk + lvl * (3 * STRIDE);
+        w.rec = sl[0]; w.desc = sl[STRIDE]; w.t_max = __uint_as_float(sl[2 * STRIDE]);
+        const uint32_t keep = 0xffffffffu << scale;                           // :377-382 floor(pos) at the new scale
+        const uint32_t bx = __float_as_uint(w.px), by = __float_as_uint(w.py), bz = __float_as_uint(w.pz);
+        w.px = __uint_as_float(bx & keep); w.py = __uint_as_float(by & keep); w.pz = __uint_as_float(bz & keep);
+        w.idx = (w.idx & ~7u) | ((bx >> scale) & 1u) | (((by >> scale) & 1u) << 1) | (((bz >> scale) & 1u) << 2);   // :388
+        w.h = 0.0f;                                                           // :390
     }
-    return RAY_CONTINUE;
+    return true;
 }
 
-// HIT block geometry, svo.esvo.glsl:190-224 + :233, for the leaf candidate ray_step stopped at.
-template <bool COUNT>
-__device__ __forceinline__ void leaf_geom(const Ray& r, const Scene& s, float inv_octree_scale, Leaf& g, Counters& cnt) {
-    if (COUNT) cnt.leaf_tests++;
-    const int octant_mask = r.idx >> 4;
-    const uint32_t octant_idx = (uint32_t)((r.idx ^ octant_mask) & 7);
-    g.value = ld_desc(s, r.rec + 4 + octant_idx);                             // :190-194
-    const float se = r.scale_exp2;
-    const float tnx = __fmaf_rn(r.px + se, r.tcx, -r.tbx), tny = __fmaf_rn(r.py + se, r.tcy, -r.tby), tnz = __fmaf_rn(r.pz + se, r.tcz, -r.tbz);   // :197
+template <bool LIMITED, bool COUNT, int STRIDE>
+__device__ __forceinline__ int walk_step(Walk& w, const Scene& s, uint32_t* stk, uint32_t& last_leaf, Counters& cnt) {
+    if (w.budget-- <= 0) return RAY_MISS;                                     // :152
+    if (LIMITED && w.t_min > w.limit) return RAY_MISS;                        // :153
+    if (COUNT) cnt.steps++;
+    const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
+    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
+    const uint32_t ci = (w.idx ^ (w.idx >> 4)) & 7u;                          // :164  idx ^ octant_mask
+    const uint32_t d = w.desc >> ci;                                          // bit 0: is_leaf, bit 8: is_child (:172-173)
+    if ((d & 0x100u) && w.t_min <= w.t_max) {                                 // :178
+        if (d & 1u) {
+            if (w.t_min > 0.0f) return RAY_LEAF;                              // :185
+            if (w.t_min == 0.0f) w.idx |= 0x100u;                             // :180 inside_voxel
+        }
+        // :266-312 — also taken by a leaf at t_min == 0 (origin inside a voxel), see SURVEY Appendix B
+        const float tv_max = tmin2(w.t_max, tc_max);                          // :278
+        if (w.t_min <= tv_max) {                                              // :280  PUSH
+            if (COUNT) cnt.pushes++;
+            if (tc_max < w.h) {                                               // :284-288
+                uint32_t lvl = (uint32_t)(VX_MAX_SCALE - 1 - w.scale);
+                lvl = lvl < s.stack_levels ? lvl : s.stack_levels - 1;
+                uint32_t* sl = stk + lvl * (3 * STRIDE);
+                sl[0] = w.rec; sl[STRIDE] = w.desc; sl[2 * STRIDE] = __float_as_uint(w.t_max);
+            }
+            w.h = tc_max;                                                     // :289
+            const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));          // child masks of the new octant (the :168 read of later iterations)
+            const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));            // :292 get_octant_ptr
+            const float half = w.se * 0.5f;                                   // :274
+            const float tcx_ = __fmaf_rn(half, w.tcx, tcornx), tcy_ = __fmaf_rn(half, w.tcy, tcorny), tcz_ = __fmaf_rn(half, w.tcz, tcornz);   // :275
+            --w.scale; w.se = half;                                           // :295-297
+            uint32_t idx = 0;                                                 // :301-304
+            if (w.t_min < tcx_) { idx ^= 1; w.px += half; }
+            if (w.t_min < tcy_) { idx ^= 2; w.py += half; }
+            if (w.t_min < tcz_) { idx ^= 4; w.pz += half; }
+            w.idx = (w.idx & ~7u) | idx;
+            w.t_max = tv_max;                                                 // :307
+            w.desc = wh >> ((ci & 1u) << 4);                                  // bits above 15 are never looked at
+            const uint32_t nr = (wb & 0x80000000u) ? (w.rec + 4u + ci + (wb & 0x7fffffffu)) : wb;
+            w.rec = nr < s.max_rec ? nr : s.max_rec;
+            return RAY_CONTINUE;                                              // :310
+        }
+    } else {
+        last_leaf = 0xffffffffu;                                              // :315-316 (adjacent_leaf_count = 0)
+    }
+    return walk_advance<STRIDE>(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? RAY_CONTINUE : RAY_MISS;
+}
+
+// ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
+template <int STRIDE>
+__device__ __forceinline__ int walk_skip_leaf(Walk& w, const Scene& s, const uint32_t* stk) {
+    const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
+    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
+    return walk_advance<STRIDE>(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? RAY_CONTINUE : RAY_MISS;
+}
+
+__device__ __forceinline__ uint32_t leaf_value(const Walk& w, const Scene& s) {   // :190-194
+    return __ldg(s.desc + (w.rec + 4u + ((w.idx ^ (w.idx >> 4)) & 7u)));
+}
+
+// HIT block geometry, svo.esvo.glsl:197-224 + :233, for the leaf candidate walk_step stopped at.
+__device__ __forceinline__ void leaf_geom(const Walk& w, float rox, float roy, float roz, float rdx, float rdy, float rdz, float inv_octree_scale, Leaf& g) {
+    const uint32_t octant_mask = (w.idx >> 4) & 7u;
+    const float se = w.se;
+    const float tnx = __fmaf_rn(w.px + se, w.tcx, -w.tbx), tny = __fmaf_rn(w.py + se, w.tcy, -w.tby), tnz = __fmaf_rn(w.pz + se, w.tcz, -w.tbz);   // :197
     const float tc_min = tmax2(tmax2(tnx, tny), tnz);                         // :199
-    float qx = r.px, qy = r.py, qz = r.pz;                                    // :202-205
+    float qx = w.px, qy = w.py, qz = w.pz;                                    // :202-205
     if (octant_mask & 1) qx = 3.0f - se - qx;
     if (octant_mask & 2) qy = 3.0f - se - qy;
     if (octant_mask & 4) qz = 3.0f - se - qz;
-    const float inv_se = 1.0f / se;                                           // exact: se is a power of two
+    const float inv_se = __int_as_float(0x7f000000 - __float_as_int(se));     // 1 / se, exact: se is a power of two in [2^-23, 1/2]
     if (tc_min == tnx) {                                                      // :210-224
-        g.face_id = (__float_as_int(r.rdx) >> 31) & 1;
-        g.u = ((r.roz + r.rdz * tnx) - qz) * inv_se; g.v = ((r.roy + r.rdy * tnx) - qy) * inv_se;
-        if (r.rdx > 0) g.u = 1 - g.u;
+        g.face_id = (__float_as_int(rdx) >> 31) & 1;
+        g.u = ((roz + rdz * tnx) - qz) * inv_se; g.v = ((roy + rdy * tnx) - qy) * inv_se;
+        if (rdx > 0) g.u = 1 - g.u;
     } else if (tc_min == tny) {
-        g.face_id = 2 | ((__float_as_int(r.rdy) >> 31) & 1);
-        g.u = ((r.rox + r.rdx * tny) - qx) * inv_se; g.v = ((r.roz + r.rdz * tny) - qz) * inv_se;
-        if (r.rdy > 0) g.v = 1 - g.v;
+        g.face_id = 2 | ((__float_as_int(rdy) >> 31) & 1);
+        g.u = ((rox + rdx * tny) - qx) * inv_se; g.v = ((roz + rdz * tny) - qz) * inv_se;
+        if (rdy > 0) g.v = 1 - g.v;
     } else {
-        g.face_id = 4 | ((__float_as_int(r.rdz) >> 31) & 1);
-        g.u = ((r.rox + r.rdx * tnz) - qx) * inv_se; g.v = ((r.roy + r.rdy * tnz) - qy) * inv_se;
-        if (r.rdz < 0) g.u = 1 - g.u;
+        g.face_id = 4 | ((__float_as_int(rdz) >> 31) & 1);
+        g.u = ((rox + rdx * tnz) - qx) * inv_se; g.v = ((roy + rdy * tnz) - qy) * inv_se;
+        if (rdz < 0) g.u = 1 - g.u;
     }
-    g.dst = r.t_min * inv_octree_scale;                                       // :233 (exact: scale is a power of two)
+    g.dst = w.t_min * inv_octree_scale;                                       // :233 (exact: scale is a power of two)
     g.qx = qx; g.qy = qy; g.qz = qz; g.se = se;
 }
 
 // res.pos, svo.esvo.glsl:252-258
-__device__ __forceinline__ void leaf_pos(const Ray& r, const Leaf& g, float inv_octree_scale, float& x, float& y, float& z) {
-    const float hx = gl_min(gl_max(r.rox + r.t_min * r.rdx, g.qx + VX_EPSILON), g.qx + g.se - VX_EPSILON);
-    const float hy = gl_min(gl_max(r.roy + r.t_min * r.rdy, g.qy + VX_EPSILON), g.qy + g.se - VX_EPSILON);
-    const float hz = gl_min(gl_max(r.roz + r.t_min * r.rdz, g.qz + VX_EPSILON), g.qz + g.se - VX_EPSILON);
+__device__ __forceinline__ void leaf_pos(float t_min, float rox, float roy, float roz, float rdx, float rdy, float rdz, const Leaf& g,
+                                         float inv_octree_scale, float& x, float& y, float& z) {
+    const float hx = gl_min(gl_max(rox + t_min * rdx, g.qx + VX_EPSILON), g.qx + g.se - VX_EPSILON);
+    const float hy = gl_min(gl_max(roy + t_min * rdy, g.qy + VX_EPSILON), g.qy + g.se - VX_EPSILON);
+    const float hz = gl_min(gl_max(roz + t_min * rdz, g.qz + VX_EPSILON), g.qz + g.se - VX_EPSILON);
     x = (hx - 1.0f) * inv_octree_scale; y = (hy - 1.0f) * inv_octree_scale; z = (hz - 1.0f) * inv_octree_scale;
 }
 
@@ -444,13 +408,21 @@ __device__ __forceinline__ void primary_ray(const RenderUniforms& u, uint32_t gx
     uvx *= u.aspect;
     uvx *= u.tan_half_fov; uvy *= u.tan_half_fov;
     const float* m = u.view;
-    const float rw = m[15];
-    ox = m[12] / rw; oy = m[13] / rw; oz = m[14] / rw;
     const float lx = ((m[0] * uvx + m[4] * uvy) + m[8] * -1.0f) + m[12];
     const float ly = ((m[1] * uvx + m[5] * uvy) + m[9] * -1.0f) + m[13];
     const float lz = ((m[2] * uvx + m[6] * uvy) + m[10] * -1.0f) + m[14];
-    const float lw = ((m[3] * uvx + m[7] * uvy) + m[11] * -1.0f) + m[15];
-    const float vx_ = lx / lw - ox, vy_ = ly / lw - oy, vz_ = lz / lw - oz;
+    float vx_, vy_, vz_;
+    if (m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f && m[15] == 1.0f) {
+        // affine view matrix (every look_to_rh inverse): both w components are exactly 1 and x / 1 == x, so the six
+        // perspective divisions of world.glsl:123-129 are the identity. Warp-uniform branch.
+        ox = m[12]; oy = m[13]; oz = m[14];
+        vx_ = lx - ox; vy_ = ly - oy; vz_ = lz - oz;
+    } else {
+        const float rw = m[15];
+        ox = m[12] / rw; oy = m[13] / rw; oz = m[14] / rw;
+        const float lw = ((m[3] * uvx + m[7] * uvy) + m[11] * -1.0f) + m[15];
+        vx_ = lx / lw - ox; vy_ = ly / lw - oy; vz_ = lz / lw - oz;
+    }
     const float l = sqrtf(dot3(vx_, vy_, vz_, vx_, vy_, vz_));
     dx = vx_ / l; dy = vy_ / l; dz = vz_ / l;
 }

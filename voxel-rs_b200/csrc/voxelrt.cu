@@ -43,10 +43,22 @@ struct VxCtx {
     uint32_t n_materials = 0;
     uint32_t* d_texels = nullptr;
     TexInfo* d_texinfo = nullptr;     // texture array description read by the device-side sampler
+    uint32_t tex_layers = 0;
 
     float4* d_frame = nullptr;
     uint32_t* d_frame8 = nullptr;
     uint32_t frame_w = 0, frame_h = 0;
+    float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_set_frame_target)
+
+    // wavefront buffers of the render path (kernels.cuh), sized for the padded pixel count of the largest frame seen
+    float4 *d_hit0 = nullptr, *d_hit1 = nullptr, *d_sh0 = nullptr, *d_sh1 = nullptr;
+    uint32_t* d_sh_pix = nullptr;
+    size_t wave_slots = 0;
+    cudaEvent_t t_wave[4] = {nullptr, nullptr, nullptr, nullptr};   // trace / shade / shadow boundaries of the last frame
+
+    std::vector<VxMaterial> h_materials;
+    unsigned long long opaque_layers = 0;   // per texture layer: every texel of every level has alpha > 0
+    unsigned long long opaque_materials = 0;
 
     float4* d_tasks = nullptr;
     float4* d_results = nullptr;
@@ -60,7 +72,7 @@ struct VxCtx {
     uint64_t launches = 0;
 
     // options (vx_set_option)
-    uint64_t opt_simple = 0, opt_vec = 0, opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 24;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -82,13 +94,30 @@ static Scene make_scene(const VxCtx* c) {
     Scene s{};
     s.desc = reinterpret_cast<const uint32_t*>(c->d_world + 4);
     s.desc_words = (uint32_t)((c->cfg.svo_capacity_bytes - 4) / 4);
+    s.max_rec = s.desc_words - 12;
+    s.opaque_materials = c->opaque_materials;
     s.materials = c->d_materials; s.n_materials = c->n_materials;
     s.tex = c->d_texinfo;
     uint32_t levels = c->stats.depth + 1;
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     return s;
 }
-static size_t stack_smem_bytes(const Scene& s, uint32_t threads) { return smem_bytes(s.stack_levels, threads); }
+static size_t stack_smem_bytes(const Scene& s) { return smem_bytes(s.stack_levels); }
+
+// bit m: material m (< 64) has only fully opaque face textures (tex id -1 samples layer 0 like the GL layer clamp does)
+static void update_opaque_materials(VxCtx* c) {
+    c->opaque_materials = 0;
+    if (!c->d_texels || c->h_materials.empty()) return;
+    for (size_t m = 0; m < c->h_materials.size() && m < 64; ++m) {
+        const int ids[3] = {c->h_materials[m].tex_top, c->h_materials[m].tex_side, c->h_materials[m].tex_bottom};
+        bool ok = true;
+        for (int id : ids) {
+            int layer = id < 0 ? 0 : (id >= (int)c->tex_layers ? (int)c->tex_layers - 1 : id);
+            ok = ok && layer < 64 && ((c->opaque_layers >> layer) & 1ull);
+        }
+        if (ok) c->opaque_materials |= 1ull << m;
+    }
+}
 
 extern "C" {
 
@@ -102,7 +131,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);
 
 int vx_create(const VxConfig* cfg, VxCtx** out) {
     if (!cfg || !out) return fail(nullptr, VX_E_ARG, "vx_create: null argument");
-    if (cfg->svo_capacity_bytes < 64) return fail(nullptr, VX_E_ARG, "vx_create: svo_capacity_bytes too small");
+    if (cfg->svo_capacity_bytes < 256) return fail(nullptr, VX_E_ARG, "vx_create: svo_capacity_bytes too small");
     if (cfg->svo_capacity_bytes > (1ull << 34)) return fail(nullptr, VX_E_ARG, "vx_create: svo_capacity_bytes > 16 GiB (u32 word pointers)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -133,6 +162,7 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaEventCreateWithFlags(&c->e_picker, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0_render)); CUC(cudaEventCreate(&c->t1_render));
     CUC(cudaEventCreate(&c->t0_picker)); CUC(cudaEventCreate(&c->t1_picker));
+    for (int i = 0; i < 4; ++i) CUC(cudaEventCreate(&c->t_wave[i]));
     const size_t cap = (size_t)cfg->svo_capacity_bytes;
     CUC(cudaMalloc(&c->d_world_raw, cap + 64));
     c->d_world = c->d_world_raw + 8;
@@ -156,7 +186,6 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaEventRecord(c->e_upload, c->s_upload));
     CUC(cudaStreamSynchronize(c->s_upload));
     c->stats.capacity_bytes = cap;
-    c->opt_simple = (cfg->flags & VX_FLAG_KERNEL_SIMPLE) ? 1 : 0;
     c->opt_l2_window = (cfg->flags & VX_FLAG_NO_L2_WINDOW) ? 0 : 1;
 #undef CUC
     *out = c;
@@ -175,6 +204,12 @@ void vx_destroy(VxCtx* c) {
     if (c->d_texinfo) cudaFree(c->d_texinfo);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
+    if (c->d_hit0) cudaFree(c->d_hit0);
+    if (c->d_hit1) cudaFree(c->d_hit1);
+    if (c->d_sh0) cudaFree(c->d_sh0);
+    if (c->d_sh1) cudaFree(c->d_sh1);
+    if (c->d_sh_pix) cudaFree(c->d_sh_pix);
+    for (cudaEvent_t ev : c->t_wave) if (ev) cudaEventDestroy(ev);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_results) cudaFree(c->d_results);
     if (c->d_counters) cudaFree(c->d_counters);
@@ -189,14 +224,11 @@ void vx_destroy(VxCtx* c) {
 }
 
 // Runtime knobs for A/B measurements (not part of the reference surface).
-//   1 = simple kernels (0/1)   2 = 128-bit node fetches (0/1)   3 = count steps/pushes/leaf tests (0/1)
-//   4 = CTAs per SM for persistent kernels (0 = occupancy query)   5 = L2 access-policy window (0/1)
-//   6 = refill threshold of the persistent kernels (1..32 lanes still walking)
+//   3 = count steps/pushes/leaf tests (0/1)   4 = CTAs per SM for the persistent trace kernels (0 = default)
+//   5 = L2 access-policy window (0/1)         6 = refill threshold of the persistent kernels (1..32 lanes still walking)
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
     if (!ctx) return VX_E_ARG;
     switch (option) {
-        case 1: ctx->opt_simple = value; break;
-        case 2: ctx->opt_vec = value; break;
         case 3: ctx->opt_count = value; break;
         case 4: ctx->opt_ctas_per_sm = value; break;
         case 5: ctx->opt_l2_window = value; break;
@@ -215,6 +247,8 @@ int vx_set_materials(VxCtx* c, const VxMaterial* materials, uint32_t count) {
     CU(c, cudaMalloc(&c->d_materials, (size_t)count * sizeof(Material)));
     CU(c, cudaMemcpy(c->d_materials, materials, (size_t)count * sizeof(Material), cudaMemcpyHostToDevice));
     c->n_materials = count;
+    c->h_materials.assign(materials, materials + count);
+    update_opaque_materials(c);
     return VX_OK;
 }
 
@@ -262,6 +296,9 @@ int vx_set_textures(VxCtx* c, const uint8_t* rgba8, uint32_t width, uint32_t hei
     }
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->s_upload));
+    CU(c, cudaMemcpy(&c->opaque_layers, &c->d_texinfo->opaque_layers, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    c->tex_layers = layers;
+    update_opaque_materials(c);
     return VX_OK;
 }
 
@@ -404,6 +441,26 @@ static int persistent_grid(VxCtx* c, const void* kernel, int threads, size_t sme
     return VX_OK;
 }
 
+// (Re)allocates the wavefront buffers for `slots` pixel slots (padded pixel count of the frame).
+static int ensure_wave_buffers(VxCtx* c, size_t slots) {
+    if (slots <= c->wave_slots) return VX_OK;
+    CU(c, cudaStreamSynchronize(c->s_render));
+    float4** bufs[] = {&c->d_hit0, &c->d_hit1, &c->d_sh0, &c->d_sh1};
+    for (float4** b : bufs) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+        CU(c, cudaMalloc(b, slots * sizeof(float4)));
+    }
+    if (c->d_sh_pix) cudaFree(c->d_sh_pix);
+    c->d_sh_pix = nullptr;
+    CU(c, cudaMalloc(&c->d_sh_pix, slots * sizeof(uint32_t)));
+    c->wave_slots = slots;
+    return VX_OK;
+}
+
+// register budget variant of the persistent trace kernels: CTAs/SM the allocator must allow (vx_set_option 4)
+static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->opt_ctas_per_sm <= 5 ? 5 : (c->opt_ctas_per_sm <= 7 ? 6 : 8)); }
+
 int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, float* rgba32f_out) {
     if (!c || !p || !width || !height) return fail(c, VX_E_ARG, "vx_render: null/empty argument");
     if (!c->d_frame || (uint64_t)width * height > (uint64_t)c->cfg.max_width * c->cfg.max_height)
@@ -424,44 +481,64 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
     a.u.hx = p->highlight_pos[0]; a.u.hy = p->highlight_pos[1]; a.u.hz = p->highlight_pos[2];
     a.u.render_shadows = p->render_shadows; a.u.shadow_distance = p->shadow_distance;
     a.u.width = width; a.u.height = height;
-    a.frame = c->d_frame;
+    a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
+    const uint32_t n_macros = a.macro_x * a.macro_y;
+    rc = ensure_wave_buffers(c, (size_t)n_macros * 512);
+    if (rc) return rc;
+    a.frame = c->frame_target ? c->frame_target : c->d_frame;
+    a.hit0 = c->d_hit0; a.hit1 = c->d_hit1; a.sh0 = c->d_sh0; a.sh1 = c->d_sh1; a.sh_pix = c->d_sh_pix;
     a.counters = c->d_counters;
-    a.work_counter = reinterpret_cast<unsigned int*>(c->d_work);
-    a.tiles_x = (width + 7) / 8; a.tiles_y = (height + 3) / 4;
-    a.macro_x = (a.tiles_x + 3) / 4; a.macro_y = (a.tiles_y + 3) / 4;
+    unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work);   // [0] primary strips, [2] shadow runs, [4] shadow list length
+    a.shadow_count = work + 4;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
     a.refill_threshold = (uint32_t)c->opt_refill;
+    const uint32_t owned = n_macros > a.shard_rank ? (n_macros - a.shard_rank + a.shard_size - 1) / a.shard_size : 0;
 
-    const int threads = 128;
-    const size_t smem = stack_smem_bytes(a.scene, threads);
+    const size_t smem = stack_smem_bytes(a.scene);
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->s_render));
-    CU(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->s_render));
-    const bool vec = c->opt_vec != 0, count = c->opt_count != 0;
-    CU(c, cudaEventRecord(c->t0_render, c->s_render));
-    if (c->opt_simple) {
-        const uint32_t blocks = a.macro_x * a.macro_y * 4;
-        auto k = vec ? (count ? render_simple_kernel<true, true> : render_simple_kernel<true, false>)
-                     : (count ? render_simple_kernel<false, true> : render_simple_kernel<false, false>);
-        CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, threads, smem, c->s_render>>>(a);
-    } else {
-        // opt_ctas_per_sm picks the register budget variant: <=5 -> 96 regs, 6/7 -> 80 regs, >=8 -> 64 regs (default 6)
-        const int minb = c->opt_ctas_per_sm == 0 ? 6 : (c->opt_ctas_per_sm <= 5 ? 5 : (c->opt_ctas_per_sm <= 7 ? 6 : 8));
-        void (*k)(RenderArgs) = nullptr;
-#define VX_PICK(V, C)                                                                                     \
-    (minb == 5 ? render_persistent_kernel<V, C, 5> : (minb == 6 ? render_persistent_kernel<V, C, 6> : render_persistent_kernel<V, C, 8>))
-        if (vec) k = count ? VX_PICK(true, true) : VX_PICK(true, false);
-        else k = count ? VX_PICK(false, true) : VX_PICK(false, false);
+    CU(c, cudaMemsetAsync(c->d_work, 0, 32, c->s_render));
+    const bool count = c->opt_count != 0;
+    const int minb = pick_minb(c);
+    void (*k1)(RenderArgs) = nullptr;
+    void (*k3)(RenderArgs) = nullptr;
+#define VX_PICK(K, C) (minb == 5 ? K<C, 5> : (minb == 6 ? K<C, 6> : K<C, 8>))
+    if (count) { k1 = VX_PICK(trace_primary_kernel, true); k3 = VX_PICK(trace_shadow_kernel, true); }
+    else { k1 = VX_PICK(trace_primary_kernel, false); k3 = VX_PICK(trace_shadow_kernel, false); }
 #undef VX_PICK
-        CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(c, cudaEventRecord(c->t0_render, c->s_render));
+    CU(c, cudaEventRecord(c->t_wave[0], c->s_render));
+    if (owned) {
+        // 1. primary rays -> hit records
+        CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = 0;
-        rc = persistent_grid(c, (const void*)k, threads, smem, &grid);
+        rc = persistent_grid(c, (const void*)k1, VX_THREADS, smem, &grid);
         if (rc) return rc;
-        k<<<grid, threads, smem, c->s_render>>>(a);
+        a.work_counter = work;
+        k1<<<grid, VX_THREADS, smem, c->s_render>>>(a);
+        c->launches++;
+        CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
+        // 2. shading -> final pixels + shadow ray list
+        const size_t smem2 = smem_bytes(0, false);
+        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
+        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
+        c->launches++;
+        CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
+        // 3. shadow rays -> final pixels (world.glsl:80-84)
+        if (p->render_shadows) {
+            CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rc = persistent_grid(c, (const void*)k3, VX_THREADS, smem, &grid);
+            if (rc) return rc;
+            a.work_counter = work + 2;
+            k3<<<grid, VX_THREADS, smem, c->s_render>>>(a);
+            c->launches++;
+        }
+        CU(c, cudaGetLastError());
+    } else {
+        CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
+        CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
     }
-    c->launches++;
-    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->t_wave[3], c->s_render));
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
@@ -513,22 +590,20 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     a.scene = make_scene(c);
     a.tasks = tasks_dev; a.results = results_dev; a.n = n;
     a.counters = c->d_counters + 1;
-    a.work_counter = c->d_work + 1;
+    a.work_counter = c->d_work + 4;
     a.refill_threshold = (uint32_t)c->opt_refill;
-    const int threads = 128;
-    const size_t smem = stack_smem_bytes(a.scene, threads);
-    const bool vec = c->opt_vec != 0, count = c->opt_count != 0;
-    auto k = vec ? (count ? raycast_kernel<true, true> : raycast_kernel<true, false>) : (count ? raycast_kernel<false, true> : raycast_kernel<false, false>);
+    const size_t smem = stack_smem_bytes(a.scene);
+    auto k = c->opt_count ? trace_picker_kernel<true> : trace_picker_kernel<false>;
     CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = 0;
-    int rc = persistent_grid(c, (const void*)k, threads, smem, &grid);
+    int rc = persistent_grid(c, (const void*)k, VX_THREADS, smem, &grid);
     if (rc) return rc;
-    const uint64_t need = (n + threads - 1) / threads;
+    const uint64_t need = (n + VX_THREADS - 1) / VX_THREADS;
     if ((uint64_t)grid > need) grid = (int)need;
     CU(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(Counters), c->s_picker));
-    CU(c, cudaMemsetAsync(c->d_work + 1, 0, sizeof(unsigned long long), c->s_picker));
+    CU(c, cudaMemsetAsync(c->d_work + 4, 0, sizeof(unsigned long long), c->s_picker));
     CU(c, cudaEventRecord(c->t0_picker, c->s_picker));
-    k<<<grid, threads, smem, c->s_picker>>>(a);
+    k<<<grid, VX_THREADS, smem, c->s_picker>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->t1_picker, c->s_picker));
@@ -586,7 +661,7 @@ int vx_debug_cast(VxCtx* c, const float pos[3], const float dir[3], float max_ds
     a.max_dst = max_dst; a.cast_translucent = cast_translucent;
     a.result = d_res; a.frames = d_frames; a.frames_cap = cap; a.n_frames = d_n;
     CU(c, cudaStreamWaitEvent(c->s_picker, c->e_upload, 0));
-    debug_cast_kernel<<<1, 1, stack_smem_bytes(a.scene, 1), c->s_picker>>>(a);
+    debug_cast_kernel<<<1, VX_THREADS, stack_smem_bytes(a.scene), c->s_picker>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
     uint32_t n = 0;
@@ -669,6 +744,11 @@ int vx_frame_stats(VxCtx* c, int which, VxFrameStats* out) {
         float ms = 0;
         CU(c, cudaEventElapsedTime(&ms, which == 0 ? c->t0_render : c->t0_picker, which == 0 ? c->t1_render : c->t1_picker));
         st.kernel_ms = ms;
+        if (which == 0) {
+            CU(c, cudaEventElapsedTime(&st.trace_ms, c->t_wave[0], c->t_wave[1]));
+            CU(c, cudaEventElapsedTime(&st.shade_ms, c->t_wave[1], c->t_wave[2]));
+            CU(c, cudaEventElapsedTime(&st.shadow_ms, c->t_wave[2], c->t_wave[3]));
+        }
     }
     *out = st;
     return VX_OK;

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-shadows", action="store_true")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
     ap.add_argument("--no-l2-window", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render kernels "
+                    "(fused, default) or by pack + NCCL send/recv + unpack")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -239,38 +241,26 @@ def main():
     octree_scale = float(np.float32(2.0 ** -world.depth))
     packed_n = svo.pack_dirty(dirty, None)
     packed_host = torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)
-    packed_dev = torch.empty(packed_n, dtype=torch.uint8, device=dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    shard_bytes = [svo.shard_bytes(W, H, (r, n_gpus)) for r in range(n_gpus)]
-    if n_gpus > 1:
-        my_pack = torch.empty(shard_bytes[rank], dtype=torch.uint8, device=dev)
-        recv = [torch.empty(shard_bytes[r], dtype=torch.uint8, device=dev) for r in range(n_gpus)] if rank == 0 else None
+    sf = pkg.sharded.ShardedFrame(svo, rank, n_gpus, dist=dist if n_gpus > 1 else None, torch=torch, device=dev, gather=args.gather)
+    sf.configure(W, H, max_dirty_bytes=packed_n)
+    if rank == 0:
+        svo.pack_dirty(dirty, packed_host.numpy())
+        if n_gpus > 1:
+            sf.packed_dirty[:packed_n].copy_(packed_host)
 
     def flush():
         if not args.no_flush:
             flush_buf.fill_(1)
 
     def step_resident():
-        """One frame with every input already in HBM."""
+        """One frame with every input already in HBM (rank 0 holds the packed dirty set on the device)."""
         flush()
-        if n_gpus > 1:
-            # per-frame changed-chunk ranges: rank 0's packed dirty set -> all GPUs over NVLink, applied by a scatter kernel
-            dist.broadcast(packed_dev, src=0)
-            svo.commit_packed_device(packed_dev.data_ptr(), len(dirty), dirty_bytes, world.size_bytes, world.depth)
-        svo.render_raw(vxp, W, H, shard=shard)
-        if n_gpus > 1:
-            svo.pack_shard(shard, my_pack.data_ptr())
-            # tiles to GPU 0 (grouped NCCL send/recv)
-            if rank == 0:
-                ops = [dist.P2POp(dist.irecv, recv[r], r) for r in range(1, n_gpus)]
-            else:
-                ops = [dist.P2POp(dist.isend, my_pack, 0)]
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
-            if rank == 0:
-                for r in range(1, n_gpus):
-                    svo.unpack_shard((r, n_gpus), recv[r].data_ptr())
+        # per-frame changed-chunk ranges: rank 0's packed dirty set -> all GPUs over NVLink, applied by a scatter kernel
+        sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth)
+        sf.render(vxp)
+        sf.finish()   # tiles in GPU 0's framebuffer (p2p: stored there by the render kernels; nccl: pack/send/recv/unpack)
 
     frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
     mirror = svo.host_mirror(24 + world.size_bytes)
@@ -285,23 +275,11 @@ def main():
         if n_gpus > 1:
             if rank == 0:
                 svo.pack_dirty(dirty, packed_host.numpy())
-                packed_dev.copy_(packed_host, non_blocking=True)
-            dist.broadcast(packed_dev, src=0)
-            svo.commit_packed_device(packed_dev.data_ptr(), len(dirty), dirty_bytes, world.size_bytes, world.depth)
+            sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_host)
         else:
             svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
-        svo.render_raw(vxp, W, H, shard=shard)
-        if n_gpus > 1:
-            svo.pack_shard(shard, my_pack.data_ptr())
-            if rank == 0:
-                ops = [dist.P2POp(dist.irecv, recv[r], r) for r in range(1, n_gpus)]
-            else:
-                ops = [dist.P2POp(dist.isend, my_pack, 0)]
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
-            if rank == 0:
-                for r in range(1, n_gpus):
-                    svo.unpack_shard((r, n_gpus), recv[r].data_ptr())
+        sf.render(vxp)
+        sf.finish()
         if rank == 0:
             import ctypes as C
             svo._check(pkg.lib().vx_read_frame_rgba8(svo.ctx, C.c_void_p(frame8.data_ptr())))
@@ -374,16 +352,25 @@ def main():
     if rank != 0:
         if n_gpus > 1:
             dist.barrier()
+            sf.close()
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes(st, pixels // n_gpus if n_gpus > 1 else pixels)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("render_kernel_dram_bytes_per_launch")
+            tj = json.load(f)
+        if n_gpus == 1 and (W, H) == (3840, 2160) and not args.no_shadows:   # the ncu capture is of this exact frame
+            traffic = tj.get("render_kernel_dram_bytes_per_launch")
+            wi = tj.get("warp_instructions_per_frame")
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            bound_ms = wi / (sms * 4 * mhz * 1e6) * 1e3
+            issue = {"bound": "instruction issue (the binding resource, DESIGN.md §6)", "warp_instructions_per_frame": wi,
+                     "issue_slots_per_s": sms * 4 * mhz * 1e6, "bound_ms": bound_ms, "frac": bound_ms / kernel_ms, "source": tj.get("source")}
     except Exception:
         pass
     line = {
@@ -397,12 +384,14 @@ def main():
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)", "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
             "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
-            "multi_gpu_step": "NCCL broadcast of packed dirty ranges + scatter, shard render, pack, NCCL send/recv to GPU 0, unpack" if n_gpus > 1 else None,
+            "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
+                               ("finished pixels stored by the render kernels straight into GPU 0's framebuffer over NVLink peer memory, "
+                                "4-byte all-reduce as the frame barrier" if args.gather == "p2p" else "pack, NCCL send/recv to GPU 0, unpack")),
         },
         "frame_ms": ms_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "trace_primary_kernel + shade_kernel + trace_shadow_kernel (one frame)",
-                     "kernel_ms": kernel_ms, "kernel_ms_split": split_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "kernel_ms": kernel_ms, "kernel_ms_split": split_ms, "issue": issue, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "counts": {k: int(st[k]) for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")},
                      "note": "latency/divergence-bound pointer chasing: the SVO is L2-resident after first touch, so the HBM fraction is small "
                              "by construction (SURVEY §8d); see profiles/ for L2 hit rate and warp execution efficiency"},
@@ -424,6 +413,7 @@ def main():
         picker_line(pkg, svo, world, args, torch, stream, peak, peak_src)
     if n_gpus > 1:
         dist.barrier()
+        sf.close()
         dist.destroy_process_group()
 
 

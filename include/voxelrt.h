@@ -268,6 +268,17 @@ uint64_t vx_shard_bytes(uint32_t width, uint32_t height, const VxShard* shard); 
 int vx_pack_shard(VxCtx* ctx, const VxShard* shard, void* packed_dev);            /* frame -> packed, on the render stream */
 int vx_unpack_shard(VxCtx* ctx, const VxShard* shard, const void* packed_dev);    /* packed -> frame, on the render stream */
 
+/* Fused tile gather over NVLink peer memory: a non-root rank maps the root GPU's framebuffer (CUDA IPC) and installs it as
+ * its frame target; its shade / shadow kernels then store every finished pixel of the shard straight into the root's frame
+ * (write-only 16-byte stores, no pack / send / recv / unpack), overlapping the transfer with tracing. The root learns that
+ * the frame is complete from the caller's barrier on the render streams.
+ *   vx_frame_ipc_handle   root: 64-byte cudaIpcMemHandle_t of this ctx's framebuffer
+ *   vx_open_peer_frame    other ranks: map that handle and write finished pixels there from now on
+ *   vx_close_peer_frame   back to the local framebuffer, unmap */
+int vx_frame_ipc_handle(VxCtx* ctx, uint8_t handle_out[64]);
+int vx_open_peer_frame(VxCtx* ctx, const uint8_t handle[64]);
+int vx_close_peer_frame(VxCtx* ctx);
+
 /* Run this context's work on caller-owned CUDA streams (cudaStream_t passed as void*) so that it orders
  * with the caller's collectives without host synchronisation. NULL keeps the library's own stream. */
 int vx_set_streams(VxCtx* ctx, void* render_stream, void* upload_stream, void* picker_stream);

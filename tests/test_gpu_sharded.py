@@ -1,0 +1,105 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): two ranks over NCCL render a tile-sharded frame with per-frame
+dirty-range broadcast; rank 0's framebuffer must be byte-identical to the single-GPU frame of the same (edited) world, for
+both gather modes — "p2p" (render kernels store into GPU 0's framebuffer over NVLink peer memory) and "nccl" (pack/send/recv)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+W, H = 1000, 562
+
+
+def _worker(rank, world_size, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_pkg()
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world_size, device_id=dev)
+    try:
+        reg = pkg.content_registry(pkg.load_atlas())
+        world = pkg.World(radius=5, center=(-1, 2, 5), seed=1)
+        world.generate(0, 8)
+        world.serialize()
+        svo = pkg.Svo(reg, size_mb=world.size_bytes // 1_000_000 + 16, max_width=W, max_height=H, max_rays=16, device=rank)
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
+        world.mark_all_dirty()
+        svo.update(world)          # every replica starts from the same SVO
+        p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, -0.3, 0.0), fov_y_deg=72.0, aspect=W / H)
+        q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+        q.cam_pos = (ctypes.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+        vxp = pkg.to_vx_render_params(q)
+
+        # rank 0 edits the world; the other replicas only ever see the broadcast
+        meta = [None]
+        packed_host = None
+        if rank == 0:
+            hgt = world.height_at(-10, 174)
+            for dy in range(1, 9):
+                world.edit_block(-10, hgt + dy, 174, 4)
+            world.serialize()
+            new = world.gpu_buffer()
+            mirror = svo.host_mirror(len(new))
+            old = mirror.copy()
+            mirror[:] = new
+            diff = np.nonzero(new[24:len(old)] != old[24:])[0]
+            lo, hi = int(diff.min()) // 4 * 4, (int(diff.max()) // 4 + 1) * 4
+            ranges = [(lo, hi - lo)]
+            n = svo.pack_dirty(ranges, None)
+            packed_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            svo.pack_dirty(ranges, packed_host.numpy())
+            meta = [(len(ranges), n - 16 * len(ranges), world.size_bytes, world.depth)]
+        dist.broadcast_object_list(meta, src=0)
+        n_ranges, payload, used, depth = meta[0]
+
+        frames = {}
+        for gather in ("p2p", "nccl"):
+            sf = pkg.sharded.ShardedFrame(svo, rank, world_size, dist=dist, torch=torch, device=dev, gather=gather)
+            sf.configure(W, H, max_dirty_bytes=16 * n_ranges + payload)
+            for _ in range(2):   # twice: the second frame checks the frame-to-frame ordering of peer stores
+                sf.broadcast_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
+                sf.render(vxp)
+                sf.finish()
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                svo.width, svo.height = W, H
+                frames[gather] = svo.read_rgba32f()
+            dist.barrier()
+            sf.close()
+        if rank == 0:
+            # single-GPU frame of the edited world on the same context (its replica got the same dirty ranges)
+            svo.render_raw(vxp, W, H)
+            full = svo.read_rgba32f()
+            np.save(os.path.join(out_dir, "full.npy"), full)
+            for k, f in frames.items():
+                np.save(os.path.join(out_dir, f"{k}.npy"), f)
+        svo.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_sharded_frame(pkg, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = np.load(tmp_path / "full.npy")
+    assert np.isfinite(full).all()
+    for k in ("p2p", "nccl"):
+        f = np.load(tmp_path / f"{k}.npy")
+        assert f.tobytes() == full.tobytes(), (k, int((f != full).any(axis=2).sum()))

@@ -104,6 +104,7 @@ VX_SYMBOLS = [
     "vx_read_frame_rgba8", "vx_read_frame_rgba32f", "vx_frame_device_ptr", "vx_raycast", "vx_raycast_device", "vx_raycast_wait",
     "vx_debug_cast", "vx_frame_stats", "vx_set_option", "vx_launch_count", "vx_build_info",
     "vx_shard_bytes", "vx_pack_shard", "vx_unpack_shard", "vx_set_streams", "vx_stream",
+    "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame",
 ]
 
 _lib = None
@@ -156,6 +157,9 @@ def lib():
     L.vx_unpack_shard.argtypes = [P, C.POINTER(VxShard), P]; L.vx_unpack_shard.restype = C.c_int
     L.vx_set_streams.argtypes = [P, P, P, P]; L.vx_set_streams.restype = C.c_int
     L.vx_stream.argtypes = [P, C.c_int, C.POINTER(P)]; L.vx_stream.restype = C.c_int
+    L.vx_frame_ipc_handle.argtypes = [P, P]; L.vx_frame_ipc_handle.restype = C.c_int
+    L.vx_open_peer_frame.argtypes = [P, P]; L.vx_open_peer_frame.restype = C.c_int
+    L.vx_close_peer_frame.argtypes = [P]; L.vx_close_peer_frame.restype = C.c_int
     _lib = L
     return L
 
@@ -594,6 +598,18 @@ class Svo:
         self._check(lib().vx_stream(self.ctx, which, C.byref(p)))
         return p.value
 
+    def frame_ipc_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self._check(lib().vx_frame_ipc_handle(self.ctx, buf))
+        return bytes(buf)
+
+    def open_peer_frame(self, handle):
+        buf = (C.c_uint8 * 64)(*handle)
+        self._check(lib().vx_open_peer_frame(self.ctx, buf))
+
+    def close_peer_frame(self):
+        self._check(lib().vx_close_peer_frame(self.ctx))
+
     def frame_device_ptr(self):
         p, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()
         self._check(lib().vx_frame_device_ptr(self.ctx, C.byref(p), C.byref(w), C.byref(h)))
@@ -612,3 +628,6 @@ class Svo:
 
     def launch_count(self):
         return lib().vx_launch_count(self.ctx)
+
+
+from . import sharded  # noqa: E402,F401  (multi-GPU tile shards: voxelrs_b200.sharded.ShardedFrame)

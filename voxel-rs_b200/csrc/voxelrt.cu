@@ -196,6 +196,7 @@ void vx_destroy(VxCtx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
+    if (c->frame_target) cudaIpcCloseMemHandle(c->frame_target);
     if (c->d_world_raw) cudaFree(c->d_world_raw);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -706,6 +707,38 @@ static int shard_copy(VxCtx* c, const VxShard* shard, void* packed_dev, bool pac
 }
 int vx_pack_shard(VxCtx* c, const VxShard* shard, void* packed_dev) { return shard_copy(c, shard, packed_dev, true); }
 int vx_unpack_shard(VxCtx* c, const VxShard* shard, const void* packed_dev) { return shard_copy(c, shard, const_cast<void*>(packed_dev), false); }
+
+int vx_frame_ipc_handle(VxCtx* c, uint8_t handle_out[64]) {
+    if (!c || !handle_out || !c->d_frame) return fail(c, VX_E_ARG, "vx_frame_ipc_handle: null argument / no framebuffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(c, cudaIpcGetMemHandle(&h, c->d_frame));
+    std::memcpy(handle_out, &h, 64);
+    return VX_OK;
+}
+
+int vx_open_peer_frame(VxCtx* c, const uint8_t handle[64]) {
+    if (!c || !handle) return fail(c, VX_E_ARG, "vx_open_peer_frame: null argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->frame_target) return fail(c, VX_E_STATE, "vx_open_peer_frame: a peer frame is already open");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->frame_target = (float4*)p;
+    return VX_OK;
+}
+
+int vx_close_peer_frame(VxCtx* c) {
+    if (!c) return VX_E_ARG;
+    if (!c->frame_target) return VX_OK;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_render));
+    CU(c, cudaIpcCloseMemHandle(c->frame_target));
+    c->frame_target = nullptr;
+    return VX_OK;
+}
 
 int vx_set_streams(VxCtx* c, void* render_stream, void* upload_stream, void* picker_stream) {
     if (!c) return VX_E_ARG;

@@ -52,10 +52,14 @@ def parse():
                     "(fused, default) or by pack + NCCL send/recv + unpack")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--bands", type=int, default=3, help="e2e: bands of vx_render_read_rgba8 (render/read-back overlap)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--picker", type=int, default=0, help="also time N incoherent picker rays (config 4 style) and print a second line")
+    ap.add_argument("--workload", default="frame", choices=["frame", "picker"], help="frame = BASELINE configs[2] (the metric's config, default); "
+                    "picker = configs[3], 16 Mi incoherent picker rays against an r=40 no-LOD world")
+    ap.add_argument("--rays", type=int, default=1 << 24, help="picker workload: number of rays")
+    ap.add_argument("--max-dst", type=float, default=-1.0, help="picker workload: max_dst of every task (-1 = unlimited)")
     return ap.parse_args()
 
 
@@ -193,6 +197,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "picker":
+        return run_picker(args)
 
     import torch
     import torch.distributed as dist
@@ -214,7 +220,7 @@ def main():
     reg = pkg.content_registry(pkg.load_atlas())
     W, H = args.width, args.height
     size_mb = int(world.size_bytes // 1_000_000 + 64)
-    svo = pkg.Svo(reg, size_mb=size_mb, max_width=W, max_height=H, max_rays=max(args.picker, 1024), device=local_rank,
+    svo = pkg.Svo(reg, size_mb=size_mb, max_width=W, max_height=H, max_rays=1024, device=local_rank,
                   flags=(pkg.VX_FLAG_NO_L2_WINDOW if args.no_l2_window else 0))
     # a real (non-legacy) torch stream shared with the library: torch ops, NCCL collectives and vx_* kernels order on it without
     # host syncs, and torch.cuda.Event timings on it see the library's kernels (stream 0 would mean "keep the library's own streams")
@@ -278,6 +284,10 @@ def main():
             sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_host)
         else:
             svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
+        if n_gpus == 1:
+            # render + read-back pipelined by the library: finished bands are copied to the host while the next is traced
+            svo.render_read_rgba8(vxp, W, H, frame8.data_ptr(), bands=args.bands)
+            return
         sf.render(vxp)
         sf.finish()
         if rank == 0:
@@ -347,7 +357,9 @@ def main():
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
         e2e = {"value": rays_total / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16), "d2h_bytes_per_step": int(W * H * 4),
-               "path": "host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render -> vx_read_frame_rgba8 (D2H to pinned host)"}
+               "path": ("host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8 (%d bands: trace/shade overlapped with the "
+                        "RGBA8 D2H copy into pinned host memory)" % args.bands) if n_gpus == 1 else
+                       "host dirty ranges -> pack -> H2D -> NCCL broadcast -> scatter -> sharded render -> tiles to GPU 0 -> vx_read_frame_rgba8 (D2H)"}
 
     if rank != 0:
         if n_gpus > 1:
@@ -409,44 +421,167 @@ def main():
         line["cpu_baseline"] = {"value": rps / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
     print(json.dumps(line), flush=True)
 
-    if args.picker:
-        picker_line(pkg, svo, world, args, torch, stream, peak, peak_src)
     if n_gpus > 1:
         dist.barrier()
         sf.close()
         dist.destroy_process_group()
 
 
-def picker_line(pkg, svo, world, args, torch, stream, peak, peak_src):
-    """Config-4 style divergence stress: N random-origin random-direction picker rays, device-resident (second JSON line)."""
-    n = args.picker
-    rng = np.random.default_rng(0)
-    size = 32.0 * (2 * args.radius + 1)
+def picker_tasks(pkg, world, radius, n, seed=0, max_dst=-1.0):
+    """BASELINE configs[3]: uniform random origins in the world AABB above the terrain band, uniform random directions."""
+    rng = np.random.default_rng(seed)
+    size = 32.0 * (2 * radius + 1)
     tasks = np.zeros(n, dtype=pkg.TASK_DTYPE)
-    tasks["max_dst"] = -1.0
-    tasks["pos"] = rng.uniform(0, size, (n, 3)).astype(np.float32)
-    tasks["pos"][:, 1] = rng.uniform(32.0 * args.radius + 60, 32.0 * args.radius + 200, n).astype(np.float32)   # above the terrain
+    tasks["max_dst"] = max_dst
+    pos = rng.uniform(0, size, (n, 3)).astype(np.float32)
+    origin = world.cnv_block_pos((0.0, 0.0, 0.0))                      # SVO-space position of world block (0,0,0)
+    pos[:, 1] = origin[1] + rng.uniform(60.0, 260.0, n).astype(np.float32)   # terrain heights are 20..200 (gamelogic/world.rs:56-78)
+    tasks["pos"] = pos
     d = rng.normal(size=(n, 3)).astype(np.float32)
     tasks["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
-    t_dev = torch.from_numpy(tasks.view(np.uint8).reshape(-1)).cuda()
-    r_dev = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    return tasks
+
+
+def run_picker(args):
+    """--workload picker = BASELINE configs[3]: N incoherent picker rays (picker.glsl) against a large no-LOD world whose SVO
+    exceeds L2 — the divergence / HBM stress case. Rays are split into contiguous ranges over the ranks (no collective)."""
+    import torch
+    import torch.distributed as dist
+    world_size = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the ray-cast path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    graft.build()
+    pkg = graft.load_pkg()
+    radius = args.radius if args.radius != 20 else 40
+    t0 = time.time()
+    world = pkg.World(radius=radius, center=(-1, 2, 5), seed=1, no_lod=True)
+    world.generate(0, 8)
+    world.serialize()
+    gen_s = time.time() - t0
+    reg = pkg.content_registry(pkg.load_atlas())
+    n_total = args.rays
+    n = n_total // world_size
+    svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=32, max_height=16, max_rays=n, device=local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
+    if args.refill:
+        svo.set_option(pkg.OPT_REFILL_PICKER, args.refill)
+    svo.update(world)
+    tasks = picker_tasks(pkg, world, radius, n_total, max_dst=args.max_dst)[rank * n:(rank + 1) * n]
+    t_host = torch.from_numpy(tasks.view(np.uint8).reshape(-1)).pin_memory()
+    r_host = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
+    t_dev = t_host.to(dev)
+    r_dev = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
     svo.set_option(pkg.OPT_COUNT, 1)
     svo.raycast_device(t_dev.data_ptr(), n, r_dev.data_ptr())
     st = svo.frame_stats(1)
     svo.set_option(pkg.OPT_COUNT, 0)
-    ms = []
-    for i in range(args.warmup + args.steps):
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        l0 = svo.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world_size > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / args.steps, svo.launch_count() - l0, t0, time.time()
+
+    def step_resident():
+        flush_buf.fill_(1)
+        svo.raycast_device(t_dev.data_ptr(), n, r_dev.data_ptr())
+
+    def step_e2e():
+        flush_buf.fill_(1)
+        import ctypes as C
+        svo._check(pkg.lib().vx_raycast(svo.ctx, C.c_void_p(t_host.data_ptr()), n, C.c_void_p(r_host.data_ptr())))
+
+    kms = []
+    for i in range(args.warmup + min(args.steps, 10)):
+        flush_buf.fill_(1)
         svo.raycast_device(t_dev.data_ptr(), n, r_dev.data_ptr())
         if i >= args.warmup:
-            ms.append(svo.frame_stats(1)["kernel_ms"])
-    k = float(np.mean(ms))
-    alg = 4 * st["steps"] + 4 * st["pushes"] + 8 * st["leaf_tests"] + 96 * n
-    print(json.dumps({"metric": "Mrays/s (picker, incoherent)", "value": n / (k * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": k, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"{n} random picker rays over the r={args.radius} world (BASELINE configs[3] style)"},
-                      "roofline": {"bound": "hbm", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                   "frac": alg / (k * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                                   "counts": {kk: int(st[kk]) for kk in ("steps", "pushes", "leaf_tests")}}}), flush=True)
+            kms.append(svo.frame_stats(1)["kernel_ms"])
+    kernel_ms = float(np.mean(kms))
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches, t0, t1 = timed(step_resident)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    e2e_ms = None
+    if not args.skip_e2e:
+        e2e_ms, _, _, _ = timed(step_e2e)
+    if rank != 0:
+        if world_size > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    alg = 4 * st["steps"] + 4 * st["pushes"] + 96 * n      # node words + child pointers + 48-B task in + 48-B result out (SURVEY §8d; the picker reads no leaf word)
+    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("picker_kernel_dram_bytes_per_launch") if (world_size == 1 and n_total == 1 << 24) else None
+    except Exception:
+        pass
+    hits = None
+    line = {
+        "metric": "Mrays/s (picker rays)", "value": n_total / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{n_total} random-origin random-direction picker rays, generated-terrain r={radius} no-LOD world (BASELINE configs[3])",
+                   "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "chunks": int(world.chunk_count), "max_dst": args.max_dst,
+                   "parallelism": f"contiguous ray ranges over {world_size} GPU(s), SVO replicated, no collective", "refill_threshold": args.refill or 24,
+                   "l2": "flushed between steps (256 MiB fill in the timed region); the SVO itself is larger than L2", "world_gen_s": round(gen_s, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "kernel": "trace_picker_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg),
+                     "counts": {k: int(st[k]) for k in ("steps", "pushes", "leaf_tests")}},
+        "clocks": clocks, "gpu_launches": int(launches),
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(48 * n),
+                       "d2h_bytes_per_step": int(48 * n), "path": "vx_raycast: pinned host tasks -> H2D -> trace_picker_kernel -> D2H results (synchronous, like the reference's fence)"}
+    if not args.skip_cpu and world_size == 1:
+        ora = graft.load_oracle()
+        tex, mips = reg.textures()
+        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+        threads = ora.max_threads()
+        m = min(n, 1 << 18)
+        scene.raycast(tasks[:4096], threads=threads)
+        tc = time.time()
+        reps = 0
+        while time.time() - tc < args.cpu_seconds and reps < 64:
+            want, _ = scene.raycast(tasks[:m], threads=threads)
+            reps += 1
+        dt = time.time() - tc
+        line["cpu_baseline"] = {"value": m * reps / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                "sample": f"first {m} rays of the same batch x {reps} passes ({dt:.1f} s)"}
+        got = r_dev[:m * 48].cpu().numpy().view(pkg.RESULT_DTYPE)
+        line["config"]["sample_parity"] = "byte-identical to the oracle on the CPU sample" if got.tobytes() == want.tobytes() else "MISMATCH vs oracle"
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -234,6 +234,13 @@ int vx_stats(const VxCtx* ctx, VxStats* out);
 int vx_render(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
               const VxShard* shard, float* rgba32f_out);
 
+/* graphics::Svo::render + Framebuffer::read_pixels (svo.rs:196-229 + framebuffer.rs:97-105) in one pipelined call: the frame is
+ * rendered in `bands` bands of macro-block rows; each finished band is converted to RGBA8 and copied to the HOST buffer
+ * rgba8_out (width*height*4 bytes, row 0 = bottom; pinned memory for the copy to overlap) while the next band is traced.
+ * Returns when the whole frame is in rgba8_out. bands is clamped to 1..16. */
+int vx_render_read_rgba8(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
+                         const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
+
 /* Block until the last vx_render finished (the reference's render_fence.wait(), svo.rs:178). */
 int vx_render_wait(VxCtx* ctx);
 
@@ -292,9 +299,11 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *   3 = count steps/pushes/leaf tests/texels (0/1)     4 = CTAs per SM of the persistent trace kernels (0 = default 8;
  *                                                          <=5 / 6-7 / >=8 select the 96 / 80 / 64-register builds)
  *   5 = persisting-L2 access-policy window (0/1, default 1)
- *   6 = refill threshold of the persistent trace kernels: a warp leaves its walk loop to finish/refill rays when fewer
+ *   6 = refill threshold of the render trace kernels: a warp leaves its walk loop to finish/refill rays when fewer
  *       than this many lanes are still walking (1..32; default 1 = run all rays of the warp to their end, then
- *       refill all 32 lanes — measured fastest on coherent frames, profiles/r01_v1_*) */
+ *       refill all 32 lanes — measured fastest on coherent frames, profiles/r01_v1_*)
+ *   7 = the same for the picker kernel (default 24: incoherent rays differ in length by 100x; 4.85 vs 2.84 Grays/s
+ *       against threshold 1 on 16 Mi random rays, profiles/r01_v2_*) */
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);
 
 /* How many kernels of this library were launched on this ctx since creation. */

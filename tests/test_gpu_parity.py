@@ -121,8 +121,8 @@ def test_picker_random_rays_bit_exact(pkg, ora, reg):
             tasks["dir"][::17, 1] = 0.0          # exercise the epsilon clamp (svo.esvo.glsl:85-89)
             tasks["pos"][::5] = np.floor(tasks["pos"][::5]) + 0.5
             want, ocnt = s.raycast(tasks)
-            for refill in (8, 1, 32):
-                svo.set_option(pkg.OPT_REFILL, refill)
+            for refill in (24, 1, 32):
+                svo.set_option(pkg.OPT_REFILL_PICKER, refill)
                 svo.set_option(pkg.OPT_COUNT, 1)
                 got = svo.raycast_tasks(tasks)
                 assert got.tobytes() == want.tobytes(), (name, max_dst, refill, int((got["dst"] != want["dst"]).sum()))
@@ -296,3 +296,27 @@ def test_sharded_frames_tile_the_image(pkg, terrain):
         acc[same] = full[same]
         assert acc.tobytes() == full.tobytes(), n
     svo.close()
+
+
+def test_pipelined_render_readback(pkg, terrain):
+    """vx_render_read_rgba8 (banded render overlapped with the RGBA8 copy to the host) returns exactly the bytes of
+    vx_render + vx_read_frame_rgba8, for any band count, ragged frame sizes and shards."""
+    import torch
+    world, reg = terrain
+    for (w, h) in ((333, 190), (640, 368)):
+        p = terrain_params(pkg, w, h)
+        svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+        svo.render(p, w, h, world=world)
+        want = svo.read_rgba8()
+        q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+        q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+        vxp = pkg.to_vx_render_params(q)
+        out = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        for bands in (1, 2, 4, 7, 16, 99):
+            out.fill_(7)
+            svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=bands)
+            assert out.numpy().tobytes() == want.tobytes(), (w, h, bands)
+        # shard 1 of 3: owned pixels equal the full frame, the others keep what the previous full render left in the device frame
+        svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=3, shard=(1, 3))
+        assert out.numpy().tobytes() == want.tobytes()
+        svo.close()

@@ -95,7 +95,7 @@ RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "for
                          "offsets": [0, 4, 16, 32], "itemsize": 48})
 
 VX_FLAG_NO_L2_WINDOW = 1
-OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL = 3, 4, 5, 6
+OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER = 3, 4, 5, 6, 7
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
 VX_SYMBOLS = [
@@ -104,7 +104,7 @@ VX_SYMBOLS = [
     "vx_read_frame_rgba8", "vx_read_frame_rgba32f", "vx_frame_device_ptr", "vx_raycast", "vx_raycast_device", "vx_raycast_wait",
     "vx_debug_cast", "vx_frame_stats", "vx_set_option", "vx_launch_count", "vx_build_info",
     "vx_shard_bytes", "vx_pack_shard", "vx_unpack_shard", "vx_set_streams", "vx_stream",
-    "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame",
+    "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame", "vx_render_read_rgba8",
 ]
 
 _lib = None
@@ -138,6 +138,8 @@ def lib():
     L.vx_svo_pack_dirty.argtypes = [P, C.POINTER(VxRange), C.c_uint32, P, C.c_uint64]; L.vx_svo_pack_dirty.restype = C.c_int64
     L.vx_stats.argtypes = [P, C.POINTER(VxStats)]; L.vx_stats.restype = C.c_int
     L.vx_render.argtypes = [P, C.POINTER(VxRenderParams), C.c_uint32, C.c_uint32, C.POINTER(VxShard), P]; L.vx_render.restype = C.c_int
+    L.vx_render_read_rgba8.argtypes = [P, C.POINTER(VxRenderParams), C.c_uint32, C.c_uint32, C.POINTER(VxShard), P, C.c_uint32]
+    L.vx_render_read_rgba8.restype = C.c_int
     L.vx_render_wait.argtypes = [P]; L.vx_render_wait.restype = C.c_int
     L.vx_read_frame_rgba8.argtypes = [P, P]; L.vx_read_frame_rgba8.restype = C.c_int
     L.vx_read_frame_rgba32f.argtypes = [P, P]; L.vx_read_frame_rgba32f.restype = C.c_int
@@ -556,6 +558,13 @@ class Svo:
         sh = VxShard(*shard) if shard else None
         self._check(lib().vx_render(self.ctx, C.byref(vx_params), width, height, C.byref(sh) if sh else None,
                                     _ptr(out) if out is not None else None))
+        self.width, self.height = width, height
+
+    def render_read_rgba8(self, vx_params, width, height, out_ptr, bands=4, shard=None):
+        """vx_render_read_rgba8 into host memory at out_ptr (pinned for overlap)."""
+        sh = VxShard(*shard) if shard else None
+        self._check(lib().vx_render_read_rgba8(self.ctx, C.byref(vx_params), width, height, C.byref(sh) if sh else None,
+                                               C.c_void_p(out_ptr), bands))
         self.width, self.height = width, height
 
     def commit(self, octree_scale, ranges, used_bytes, depth):

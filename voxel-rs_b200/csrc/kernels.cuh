@@ -36,6 +36,8 @@ struct RenderArgs {
     Counters* counters;
     unsigned int* work_counter;   // persistent kernels: next unclaimed run
     uint32_t macro_x, macro_y;    // frame size in 32x16-pixel macro blocks
+    uint32_t macro0, n_macros;    // this launch covers macro blocks [macro0, macro0 + n_macros) (a band of macro rows, or the frame)
+    uint32_t first_owned;         // first macro block >= macro0 owned by this shard
     uint32_t shard_rank, shard_size;
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
 };
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
     const float inv_scale = 1.0f / octree_scale;
-    const uint32_t n_strips = a.macro_x * a.macro_y * 4u;
+    const uint32_t n_strips = a.n_macros * 4u;
     float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 if (lane == 0) strip = atomicAdd(a.work_counter, 1u);
                 strip = __shfl_sync(0xffffffffu, strip, 0);
                 if (strip >= n_strips) { more_work = false; break; }
+                strip += a.macro0 * 4u;
                 if (!strip_origin(a, strip, strip_x0, strip_y0)) continue;
                 next_px = 0;
             }
@@ -210,9 +213,9 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t strip = (a.shard_size > 1) ? (((blockIdx.x >> 2) * a.shard_size + a.shard_rank) << 2 | (blockIdx.x & 3u)) : blockIdx.x;
+    const uint32_t strip = ((a.first_owned + (blockIdx.x >> 2) * a.shard_size) << 2) | (blockIdx.x & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
-    const bool have = (strip >> 2) < a.macro_x * a.macro_y && strip_origin(a, strip, x0, y0);
+    const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
     const bool live = have && gx < a.u.width && gy < a.u.height;
     Counters cnt = {0, 0, 0, 0, 0, 0};

@@ -21,12 +21,14 @@ using namespace vx;
 
 static thread_local std::string g_create_error;
 
+struct GridCacheEntry;
 struct VxCtx {
     VxConfig cfg{};
     int sm_count = 0;
     std::string err;
 
-    cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr;
+    cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr, s_copy = nullptr;
+    cudaEvent_t e_band[16] = {};
     cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
     cudaEvent_t t0_render = nullptr, t1_render = nullptr, t0_picker = nullptr, t1_picker = nullptr;
@@ -70,9 +72,10 @@ struct VxCtx {
 
     VxStats stats{};
     uint64_t launches = 0;
+    std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -157,6 +160,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaStreamCreateWithFlags(&c->s_render, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_upload, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_picker, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) CUC(cudaEventCreateWithFlags(&c->e_band[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_upload, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_render, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_picker, cudaEventDisableTiming));
@@ -182,7 +187,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     }
     CUC(cudaMalloc(&c->d_counters, 2 * sizeof(Counters)));
     CUC(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(Counters), c->s_upload));
-    CUC(cudaMalloc(&c->d_work, 64));
+    CUC(cudaMalloc(&c->d_work, 64 + 16 * 32));   // [0..7] u64: picker run counter at [4]; then 16 bands x 8 u32 render counters
+    CUC(cudaMemsetAsync(c->d_work, 0, 64 + 16 * 32, c->s_upload));
     CUC(cudaEventRecord(c->e_upload, c->s_upload));
     CUC(cudaStreamSynchronize(c->s_upload));
     c->stats.capacity_bytes = cap;
@@ -211,6 +217,8 @@ void vx_destroy(VxCtx* c) {
     if (c->d_sh1) cudaFree(c->d_sh1);
     if (c->d_sh_pix) cudaFree(c->d_sh_pix);
     for (cudaEvent_t ev : c->t_wave) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->e_band) if (ev) cudaEventDestroy(ev);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_results) cudaFree(c->d_results);
     if (c->d_counters) cudaFree(c->d_counters);
@@ -226,7 +234,7 @@ void vx_destroy(VxCtx* c) {
 
 // Runtime knobs for A/B measurements (not part of the reference surface).
 //   3 = count steps/pushes/leaf tests (0/1)   4 = CTAs per SM for the persistent trace kernels (0 = default)
-//   5 = L2 access-policy window (0/1)         6 = refill threshold of the persistent kernels (1..32 lanes still walking)
+//   5 = L2 access-policy window (0/1)         6 / 7 = refill threshold of the render / picker trace kernels (1..32 lanes still walking)
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
     if (!ctx) return VX_E_ARG;
     switch (option) {
@@ -234,6 +242,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 4: ctx->opt_ctas_per_sm = value; break;
         case 5: ctx->opt_l2_window = value; break;
         case 6: ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value); break;
+        case 7: ctx->opt_refill_picker = value < 1 ? 1 : (value > 32 ? 32 : value); break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -425,6 +434,7 @@ int vx_stats(const VxCtx* c, VxStats* out) {
     return VX_OK;
 }
 
+static int persistent_grid_query(VxCtx* c, const void* kernel, int threads, size_t smem, int* grid);
 static int check_scene(VxCtx* c, const char* who) {
     if (!c->have_svo) return fail(c, VX_E_STATE, "%s: no SVO committed (vx_svo_commit)", who);
     if (!c->d_materials) return fail(c, VX_E_STATE, "%s: no materials (vx_set_materials)", who);
@@ -432,7 +442,21 @@ static int check_scene(VxCtx* c, const char* who) {
     return VX_OK;
 }
 
+// Sets the dynamic shared memory limit of a persistent kernel and sizes its grid (SMs x resident CTAs). Both are cached per
+// (kernel, smem, CTAs/SM option): cudaFuncSetAttribute + the occupancy query cost tens of microseconds per launch otherwise.
+struct GridCacheEntry { const void* kernel; size_t smem; uint64_t opt; int grid; };
 static int persistent_grid(VxCtx* c, const void* kernel, int threads, size_t smem, int* grid) {
+    for (const GridCacheEntry& e : c->grid_cache)
+        if (e.kernel == kernel && e.smem == smem && e.opt == c->opt_ctas_per_sm) { *grid = e.grid; return VX_OK; }
+    {
+        cudaError_t e_ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e_ != cudaSuccess) return fail(c, VX_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e_));
+    }
+    int rc_ = persistent_grid_query(c, kernel, threads, smem, grid);
+    if (rc_ == VX_OK) c->grid_cache.push_back(GridCacheEntry{kernel, smem, c->opt_ctas_per_sm, *grid});
+    return rc_;
+}
+static int persistent_grid_query(VxCtx* c, const void* kernel, int threads, size_t smem, int* grid) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (e != cudaSuccess) return fail(c, VX_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
@@ -462,17 +486,72 @@ static int ensure_wave_buffers(VxCtx* c, size_t slots) {
 // register budget variant of the persistent trace kernels: CTAs/SM the allocator must allow (vx_set_option 4)
 static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->opt_ctas_per_sm <= 5 ? 5 : (c->opt_ctas_per_sm <= 7 ? 6 : 8)); }
 
-int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, float* rgba32f_out) {
-    if (!c || !p || !width || !height) return fail(c, VX_E_ARG, "vx_render: null/empty argument");
+// One wavefront (trace -> shade -> shadow) over the macro-block rows [row0, row1) of the frame, on the render stream.
+// `band` selects the set of work counters (each band of a frame needs its own zeroed set).
+static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band, uint32_t row0, uint32_t row1, bool timed) {
+    a.macro0 = row0 * a.macro_x;
+    a.n_macros = (row1 - row0) * a.macro_x;
+    const uint32_t size = a.shard_size, rank = a.shard_rank;
+    a.first_owned = a.macro0 + ((rank + size - (a.macro0 % size)) % size);
+    const uint32_t band_end = a.macro0 + a.n_macros;
+    const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + size - 1) / size : 0;
+    unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work) + 16 + band * 8;   // [0] primary strips, [2] shadow runs, [4] shadow list length
+    a.shadow_count = work + 4;
+    const size_t smem = stack_smem_bytes(a.scene);
+    const bool count = c->opt_count != 0;
+    const int minb = pick_minb(c);
+    void (*k1)(RenderArgs) = nullptr;
+    void (*k3)(RenderArgs) = nullptr;
+#define VX_PICK(K, C) (minb == 5 ? K<C, 5> : (minb == 6 ? K<C, 6> : K<C, 8>))
+    if (count) { k1 = VX_PICK(trace_primary_kernel, true); k3 = VX_PICK(trace_shadow_kernel, true); }
+    else { k1 = VX_PICK(trace_primary_kernel, false); k3 = VX_PICK(trace_shadow_kernel, false); }
+#undef VX_PICK
+    if (timed) CU(c, cudaEventRecord(c->t_wave[0], c->s_render));
+    if (owned) {
+        // 1. primary rays -> hit records
+        int grid = 0;
+        int rc = persistent_grid(c, (const void*)k1, VX_THREADS, smem, &grid);
+        if (rc) return rc;
+        const int need = (int)owned * 4;   // one warp-run of 128 pixels per strip; never more CTAs than strips
+        a.work_counter = work;
+        k1<<<grid < need ? grid : need, VX_THREADS, smem, c->s_render>>>(a);
+        c->launches++;
+        if (timed) CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
+        // 2. shading -> final pixels + shadow ray list
+        const size_t smem2 = smem_bytes(0, false);
+        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
+        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
+        c->launches++;
+        if (timed) CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
+        // 3. shadow rays -> final pixels (world.glsl:80-84)
+        if (shadows) {
+            rc = persistent_grid(c, (const void*)k3, VX_THREADS, smem, &grid);
+            if (rc) return rc;
+            a.work_counter = work + 2;
+            k3<<<grid < need ? grid : need, VX_THREADS, smem, c->s_render>>>(a);
+            c->launches++;
+        }
+        CU(c, cudaGetLastError());
+    } else if (timed) {
+        CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
+        CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
+    }
+    if (timed) CU(c, cudaEventRecord(c->t_wave[3], c->s_render));
+    return VX_OK;
+}
+
+#define VX_MAX_BANDS 16
+
+// Argument checks + everything of RenderArgs that does not depend on the band.
+static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, RenderArgs& a, const char* who) {
+    if (!c || !p || !width || !height) return fail(c, VX_E_ARG, "%s: null/empty argument", who);
     if (!c->d_frame || (uint64_t)width * height > (uint64_t)c->cfg.max_width * c->cfg.max_height)
-        return fail(c, VX_E_CAPACITY, "vx_render: %ux%u exceeds the %ux%u framebuffer reserved at vx_create", width, height, c->cfg.max_width,
+        return fail(c, VX_E_CAPACITY, "%s: %ux%u exceeds the %ux%u framebuffer reserved at vx_create", who, width, height, c->cfg.max_width,
                     c->cfg.max_height);
-    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return fail(c, VX_E_ARG, "vx_render: bad shard");
-    int rc = check_scene(c, "vx_render");
+    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return fail(c, VX_E_ARG, "%s: bad shard", who);
+    int rc = check_scene(c, who);
     if (rc) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
-
-    RenderArgs a{};
     a.scene = make_scene(c);
     std::memcpy(a.u.view, p->view, sizeof(a.u.view));
     a.u.tan_half_fov = tanf(p->fov_y_rad * 0.5f);                         // world.glsl:115, hoisted
@@ -483,63 +562,26 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
     a.u.render_shadows = p->render_shadows; a.u.shadow_distance = p->shadow_distance;
     a.u.width = width; a.u.height = height;
     a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
-    const uint32_t n_macros = a.macro_x * a.macro_y;
-    rc = ensure_wave_buffers(c, (size_t)n_macros * 512);
+    rc = ensure_wave_buffers(c, (size_t)a.macro_x * a.macro_y * 512);
     if (rc) return rc;
     a.frame = c->frame_target ? c->frame_target : c->d_frame;
     a.hit0 = c->d_hit0; a.hit1 = c->d_hit1; a.sh0 = c->d_sh0; a.sh1 = c->d_sh1; a.sh_pix = c->d_sh_pix;
     a.counters = c->d_counters;
-    unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work);   // [0] primary strips, [2] shadow runs, [4] shadow list length
-    a.shadow_count = work + 4;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
     a.refill_threshold = (uint32_t)c->opt_refill;
-    const uint32_t owned = n_macros > a.shard_rank ? (n_macros - a.shard_rank + a.shard_size - 1) / a.shard_size : 0;
-
-    const size_t smem = stack_smem_bytes(a.scene);
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->s_render));
-    CU(c, cudaMemsetAsync(c->d_work, 0, 32, c->s_render));
-    const bool count = c->opt_count != 0;
-    const int minb = pick_minb(c);
-    void (*k1)(RenderArgs) = nullptr;
-    void (*k3)(RenderArgs) = nullptr;
-#define VX_PICK(K, C) (minb == 5 ? K<C, 5> : (minb == 6 ? K<C, 6> : K<C, 8>))
-    if (count) { k1 = VX_PICK(trace_primary_kernel, true); k3 = VX_PICK(trace_shadow_kernel, true); }
-    else { k1 = VX_PICK(trace_primary_kernel, false); k3 = VX_PICK(trace_shadow_kernel, false); }
-#undef VX_PICK
+    CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32, c->s_render));
+    return VX_OK;
+}
+
+int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, float* rgba32f_out) {
+    RenderArgs a{};
+    int rc = prepare_render(c, p, width, height, shard, a, "vx_render");
+    if (rc) return rc;
     CU(c, cudaEventRecord(c->t0_render, c->s_render));
-    CU(c, cudaEventRecord(c->t_wave[0], c->s_render));
-    if (owned) {
-        // 1. primary rays -> hit records
-        CU(c, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = 0;
-        rc = persistent_grid(c, (const void*)k1, VX_THREADS, smem, &grid);
-        if (rc) return rc;
-        a.work_counter = work;
-        k1<<<grid, VX_THREADS, smem, c->s_render>>>(a);
-        c->launches++;
-        CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
-        // 2. shading -> final pixels + shadow ray list
-        const size_t smem2 = smem_bytes(0, false);
-        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
-        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
-        c->launches++;
-        CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
-        // 3. shadow rays -> final pixels (world.glsl:80-84)
-        if (p->render_shadows) {
-            CU(c, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            rc = persistent_grid(c, (const void*)k3, VX_THREADS, smem, &grid);
-            if (rc) return rc;
-            a.work_counter = work + 2;
-            k3<<<grid, VX_THREADS, smem, c->s_render>>>(a);
-            c->launches++;
-        }
-        CU(c, cudaGetLastError());
-    } else {
-        CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
-        CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
-    }
-    CU(c, cudaEventRecord(c->t_wave[3], c->s_render));
+    rc = launch_wavefront(c, a, p->render_shadows != 0, 0, 0, a.macro_y, true);
+    if (rc) return rc;
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
@@ -548,6 +590,42 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
         CU(c, cudaMemcpyAsync(rgba32f_out, c->d_frame, (size_t)width * height * sizeof(float4), cudaMemcpyDeviceToHost, c->s_render));
         CU(c, cudaStreamSynchronize(c->s_render));
     }
+    return VX_OK;
+}
+
+// vx_render + Framebuffer::read_pixels in one call, pipelined: the frame is rendered in `bands` bands of macro-block rows
+// (bottom to top); as soon as a band is finished it is converted to RGBA8 and copied to the host on the copy stream while the
+// next band is being traced, so only the last band's copy is exposed. rgba8_out should be pinned (cudaHostAlloc /
+// cudaHostRegister) for the overlap to happen. Returns when the whole frame is in rgba8_out.
+int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
+                         uint32_t bands) {
+    if (!rgba8_out) return fail(c, VX_E_ARG, "vx_render_read_rgba8: null output");
+    RenderArgs a{};
+    int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
+    if (rc) return rc;
+    if (c->frame_target) return fail(c, VX_E_STATE, "vx_render_read_rgba8: a peer frame is open (pixels are not written locally)");
+    if (bands < 1) bands = 1;
+    if (bands > VX_MAX_BANDS) bands = VX_MAX_BANDS;
+    if (bands > a.macro_y) bands = a.macro_y;
+    CU(c, cudaEventRecord(c->t0_render, c->s_render));
+    for (uint32_t b = bands; b-- > 0;) {   // top of the image first: sky-heavy bands finish early and their copies start early
+        const uint32_t row0 = (uint32_t)((uint64_t)a.macro_y * b / bands), row1 = (uint32_t)((uint64_t)a.macro_y * (b + 1) / bands);
+        rc = launch_wavefront(c, a, p->render_shadows != 0, b, row0, row1, false);
+        if (rc) return rc;
+        const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
+        const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
+        rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame + px0, c->d_frame8 + px0, n);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        CU(c, cudaEventRecord(c->e_band[b], c->s_render));
+        CU(c, cudaStreamWaitEvent(c->s_copy, c->e_band[b], 0));
+        CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
+    }
+    CU(c, cudaEventRecord(c->t1_render, c->s_render));
+    CU(c, cudaEventRecord(c->e_render, c->s_render));
+    c->frame_w = width; c->frame_h = height;
+    c->render_timed = false;
+    CU(c, cudaStreamSynchronize(c->s_copy));
     return VX_OK;
 }
 
@@ -592,10 +670,9 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     a.tasks = tasks_dev; a.results = results_dev; a.n = n;
     a.counters = c->d_counters + 1;
     a.work_counter = c->d_work + 4;
-    a.refill_threshold = (uint32_t)c->opt_refill;
+    a.refill_threshold = (uint32_t)c->opt_refill_picker;
     const size_t smem = stack_smem_bytes(a.scene);
     auto k = c->opt_count ? trace_picker_kernel<true> : trace_picker_kernel<false>;
-    CU(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = 0;
     int rc = persistent_grid(c, (const void*)k, VX_THREADS, smem, &grid);
     if (rc) return rc;

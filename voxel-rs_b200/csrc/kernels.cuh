@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
-    uint32_t strip = 0, strip_x0 = 0, strip_y0 = 0, next_px = 128;   // warp-uniform
+    // warp-uniform work state: the unit of work fetch is one warp tile (8x4 pixels = 32 rays, a quarter of a strip), so that a
+    // shard of a frame (1/8 of 4K = 32 k tiles over 4.7 k resident warps) still load-balances
+    uint32_t tile = 0, strip_x0 = 0, strip_y0 = 0, next_px = 32, tile_px0 = 0;
+    const uint32_t n_tiles = n_strips * 4u;
     bool more_work = true;
     bool active = false;
     int ev = RAY_CONTINUE;
@@ -146,26 +149,27 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         // ---------------------------------------------------------------- refill
         unsigned want = __ballot_sync(0xffffffffu, !active);
         while (want && more_work) {
-            if (next_px >= 128) {
-                if (lane == 0) strip = atomicAdd(a.work_counter, 1u);
-                strip = __shfl_sync(0xffffffffu, strip, 0);
-                if (strip >= n_strips) { more_work = false; break; }
-                strip += a.macro0 * 4u;
-                if (!strip_origin(a, strip, strip_x0, strip_y0)) continue;
+            if (next_px >= 32) {
+                if (lane == 0) tile = atomicAdd(a.work_counter, 1u);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile >= n_tiles) { more_work = false; break; }
+                tile += a.macro0 * 16u;
+                if (!strip_origin(a, tile >> 2, strip_x0, strip_y0)) continue;
+                tile_px0 = (tile & 3u) * 32u;
                 next_px = 0;
             }
-            const uint32_t n_take = min((uint32_t)__popc(want), 128u - next_px);
+            const uint32_t n_take = min((uint32_t)__popc(want), 32u - next_px);
             const uint32_t my_rank = __popc(want & lanemask_lt);
             if (((want >> lane) & 1u) && my_rank < n_take) {
                 uint32_t gx, gy;
-                strip_pixel(strip_x0, strip_y0, next_px + my_rank, gx, gy);
+                strip_pixel(strip_x0, strip_y0, tile_px0 + next_px + my_rank, gx, gy);
                 if (gx < a.u.width && gy < a.u.height) {
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
                     walk_init(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
-                    slot = strip * 128u + next_px + my_rank;
+                    slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
                     active = true; ev = RAY_CONTINUE; last_leaf = 0xffffffffu;
                     if (COUNT) cnt.primary_rays++;
                 }
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
     float* cold = sm.cold;
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
-    uint32_t run_base = 0, next = 128, run_len = 128;   // warp-uniform
+    uint32_t run_base = 0, next = 32, run_len = 32;   // warp-uniform; runs of 32 list entries (one warp round) keep small shards balanced
     bool more_work = true;
     bool active = false;
     int ev = RAY_CONTINUE;
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         unsigned want = __ballot_sync(0xffffffffu, !active);
         while (want && more_work) {
             if (next >= run_len) {
-                if (lane == 0) run_base = atomicAdd(a.work_counter, 128u);
+                if (lane == 0) run_base = atomicAdd(a.work_counter, 32u);
                 run_base = __shfl_sync(0xffffffffu, run_base, 0);
                 if (run_base >= n) { more_work = false; break; }
-                run_len = min(128u, n - run_base);
+                run_len = min(32u, n - run_base);
                 next = 0;
             }
             const uint32_t n_take = min((uint32_t)__popc(want), run_len - next);

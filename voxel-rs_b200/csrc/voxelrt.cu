@@ -512,7 +512,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
         int grid = 0;
         int rc = persistent_grid(c, (const void*)k1, VX_THREADS, smem, &grid);
         if (rc) return rc;
-        const int need = (int)owned * 4;   // one warp-run of 128 pixels per strip; never more CTAs than strips
+        const int need = (int)owned * 4;   // 16 warp tiles per macro block, 4 warps per CTA: never more CTAs than there is work for
         a.work_counter = work;
         k1<<<grid < need ? grid : need, VX_THREADS, smem, c->s_render>>>(a);
         c->launches++;

@@ -320,3 +320,68 @@ def test_pipelined_render_readback(pkg, terrain):
         svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=3, shard=(1, 3))
         assert out.numpy().tobytes() == want.tobytes()
         svo.close()
+
+
+# ---------------------------------------------------------------------------------------------- full BASELINE sizes --
+
+def test_full_size_4k_frame_vs_oracle(pkg, ora):
+    """BASELINE configs[2] at its real size: r=20 LOD world, 3840x2160, primary + shadow rays. The oracle renders the whole
+    frame on the host cores in about a second, so this is a direct comparison, not a property test: RGB8 within 1 LSB on
+    all 8.3 M pixels, ray / step / push / leaf / texel counters identical, hit mask identical."""
+    import bench
+    args = type("A", (), dict(radius=20, no_lod=False, width=3840, height=2160, no_shadows=False))()
+    world, _ = bench.build_world(pkg, args)
+    reg = pkg.content_registry(pkg.load_atlas())
+    vxp = bench.frame_params(pkg, world, args)
+    W, H = args.width, args.height
+    svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=W, max_height=H, max_rays=16)
+    world.mark_all_dirty()
+    svo.update(world)
+    svo.set_option(pkg.OPT_COUNT, 1)
+    svo.render_raw(vxp, W, H)
+    st = svo.frame_stats(0)
+    got, got8 = svo.read_rgba32f(), svo.read_rgba8()
+    want, cnt = helpers.oracle_scene(ora, world, reg).render(vxp, W, H)
+    want8 = ora.to_rgba8(want)
+    d8 = np.abs(got8.astype(np.int16) - want8.astype(np.int16))
+    assert d8.max() <= 1, (int(d8.max()), int((d8 > 1).sum()))
+    assert float(np.abs(got - want).max()) <= 2e-6
+    for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+        assert st[k] == cnt[k], (k, st[k], cnt[k])
+    assert st["primary_rays"] == W * H and st["shadow_rays"] > 5_000_000
+    # determinism + partition at full size: 8 shards rendered one after the other rebuild the identical frame
+    svo.set_option(pkg.OPT_COUNT, 0)
+    svo.render_raw(vxp, W, H)
+    assert svo.read_rgba32f().tobytes() == got.tobytes()
+    svo.render_raw(bench.frame_params(pkg, world, type("A", (), dict(radius=20, no_lod=False, width=W, height=H, no_shadows=True))()), W, H)
+    for r in range(8):
+        svo.render_raw(vxp, W, H, shard=(r, 8))
+    assert svo.read_rgba32f().tobytes() == got.tobytes()
+    svo.close()
+
+
+def test_full_size_16m_picker_rays_vs_oracle(pkg, ora):
+    """BASELINE configs[3] at its real size: 16 Mi random picker rays against the r=40 no-LOD world (1 GB SVO, depth 12).
+    Every one of the 16 Mi 48-byte results is byte-identical to the oracle's; counters identical."""
+    import bench
+    world = pkg.World(radius=40, center=(-1, 2, 5), seed=1, no_lod=True)
+    world.generate(0, 8)
+    world.serialize()
+    assert world.depth == 12 and world.size_bytes > 900_000_000
+    reg = pkg.content_registry(pkg.load_atlas())
+    n = 1 << 24
+    svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=32, max_height=16, max_rays=n)
+    world.mark_all_dirty()
+    svo.update(world)
+    scene = helpers.oracle_scene(ora, world, reg)
+    for max_dst in (-1.0, 30.0):
+        tasks = bench.picker_tasks(pkg, world, 40, n, seed=0, max_dst=max_dst)
+        svo.set_option(pkg.OPT_COUNT, 1)
+        got = svo.raycast_tasks(tasks)
+        st = svo.frame_stats(1)
+        want, cnt = scene.raycast(tasks)
+        assert got.tobytes() == want.tobytes(), (max_dst, int((got["dst"] != want["dst"]).sum()))
+        assert st["steps"] == cnt["steps"] and st["pushes"] == cnt["pushes"] and st["leaf_tests"] == cnt["leaf_tests"]
+        hits = int((got["dst"] > 0).sum())
+        assert 0 < hits < n
+    svo.close()

@@ -115,11 +115,20 @@ __device__ __forceinline__ bool render_leaf(const Walk& w, const Scene& s, const
     return false;
 }
 
-// Walk-loop exit vote: keep stepping while at least `thresh` lanes are still walking. thresh == 1 (the default: run every
-// ray of the warp to its end, then refill all 32 lanes at once) needs no population count.
-__device__ __forceinline__ bool keep_walking(bool walking, int thresh) {
-    if (thresh <= 1) return __any_sync(0xffffffffu, walking);
-    return __popc(__ballot_sync(0xffffffffu, walking)) >= thresh;
+// The walk loop of a warp: every lane with a live ray steps it; the warp leaves the loop when fewer than `thresh` lanes are
+// still walking. thresh == 1 (run every ray of the warp to its end, then refill all 32 lanes at once) needs no population
+// count and gets its own copy of the loop.
+template <bool LIMITED, bool COUNT>
+__device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt, int thresh) {
+    if (thresh <= 1) {
+        do {
+            if (w.state > 0) walk_step<LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+        } while (__any_sync(0xffffffffu, w.state > 0));
+    } else {
+        do {
+            if (w.state > 0) walk_step<LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+        } while (__popc(__ballot_sync(0xffffffffu, w.state > 0)) >= thresh);
+    }
 }
 
 // ---- primary rays ------------------------------------------------------------------------------------------------------
@@ -140,14 +149,13 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     uint32_t tile = 0, strip_x0 = 0, strip_y0 = 0, next_px = 32, tile_px0 = 0;
     const uint32_t n_tiles = n_strips * 4u;
     bool more_work = true;
-    bool active = false;
-    int ev = RAY_CONTINUE;
     uint32_t slot = 0, last_leaf = 0xffffffffu;
     Walk w;
+    w.state = ST_IDLE;
 
     for (;;) {
         // ---------------------------------------------------------------- refill
-        unsigned want = __ballot_sync(0xffffffffu, !active);
+        unsigned want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         while (want && more_work) {
             if (next_px >= 32) {
                 if (lane == 0) tile = atomicAdd(a.work_counter, 1u);
@@ -170,25 +178,21 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
-                    active = true; ev = RAY_CONTINUE; last_leaf = 0xffffffffu;
+                    last_leaf = 0xffffffffu;
                     if (COUNT) cnt.primary_rays++;
                 }
             }
             next_px += n_take;
-            want = __ballot_sync(0xffffffffu, !active);
+            want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         }
-        const unsigned busy = __ballot_sync(0xffffffffu, active);
+        const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        const int thresh = min((int)a.refill_threshold, __popc(busy));
 
         // ---------------------------------------------------------------- walk
-        for (;;) {
-            if (active && ev == RAY_CONTINUE) ev = walk_step<false, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
-            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
-        }
+        walk_warp<false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
-        if (ev == RAY_LEAF) {
+        if (state_at_leaf(w.state)) {
             Leaf g;
             if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
                 float px, py, pz;
@@ -196,13 +200,13 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                          inv_scale, px, py, pz);
                 __stcs(a.hit0 + slot, make_float4(g.dst, __uint_as_float(g.value), g.u, g.v));
                 __stcs(a.hit1 + slot, make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id)));
-                active = false; ev = RAY_CONTINUE;
+                w.state = ST_IDLE;
             } else {
-                ev = walk_skip_leaf<VX_THREADS>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
+                walk_skip_leaf(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
-        } else if (ev == RAY_MISS) {
+        } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-            active = false; ev = RAY_CONTINUE;
+            w.state = ST_IDLE;
         }
     }
     if (COUNT) flush_counters(a.counters, cnt);
@@ -291,14 +295,13 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
 
     uint32_t run_base = 0, next = 32, run_len = 32;   // warp-uniform; runs of 32 list entries (one warp round) keep small shards balanced
     bool more_work = true;
-    bool active = false;
-    int ev = RAY_CONTINUE;
     uint32_t entry = 0, last_leaf = 0xffffffffu;
     float lit = 0.0f;
     Walk w;
+    w.state = ST_IDLE;
 
     for (;;) {
-        unsigned want = __ballot_sync(0xffffffffu, !active);
+        unsigned want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         while (want && more_work) {
             if (next >= run_len) {
                 if (lane == 0) run_base = atomicAdd(a.work_counter, 32u);
@@ -317,25 +320,20 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 lit = s0.w;
-                active = true; ev = RAY_CONTINUE; last_leaf = 0xffffffffu;
+                last_leaf = 0xffffffffu;
                 if (COUNT) cnt.shadow_rays++;
             }
             next += n_take;
-            want = __ballot_sync(0xffffffffu, !active);
+            want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         }
-        const unsigned busy = __ballot_sync(0xffffffffu, active);
+        const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        const int thresh = min((int)a.refill_threshold, __popc(busy));
+        walk_warp<false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
 
-        for (;;) {
-            if (active && ev == RAY_CONTINUE) ev = walk_step<false, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
-            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
-        }
-
-        if (ev != RAY_CONTINUE) {
+        if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;
             float shadow = 1.0f;                                     // world.glsl:83: res.t < 0 -> 1
-            if (ev == RAY_LEAF) {
+            if (state_at_leaf(w.state)) {
                 Leaf g;
                 // fully opaque materials block the sun whatever the texel is; others go through the translucency rule
                 const uint32_t value = leaf_value(w, a.scene);
@@ -345,7 +343,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 } else if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
                     shadow = 0.0f;
                 } else {
-                    ev = walk_skip_leaf<VX_THREADS>(w, a.scene, sm.stack);
+                    walk_skip_leaf(w, a.scene, sm.stack);
                     done = false;
                 }
             }
@@ -353,7 +351,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 const float4 c = __ldcs(a.sh1 + entry);
                 const uint32_t pix = __ldcs(a.sh_pix + entry);
                 __stcs(a.frame + pix, shade_finish(a.u, c.x, c.y, c.z, c.w, lit, shadow));
-                active = false; ev = RAY_CONTINUE;
+                w.state = ST_IDLE;
             }
         }
     }
@@ -386,14 +384,13 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
     unsigned long long run_base = 0;
     uint32_t next = 128, run_len = 128;
     bool more_work = true;
-    bool active = false;
-    int ev = RAY_CONTINUE;
     unsigned long long my_task = 0;
     uint32_t last_leaf = 0xffffffffu;
     Walk w;
+    w.state = ST_IDLE;
 
     for (;;) {
-        unsigned want = __ballot_sync(0xffffffffu, !active);
+        unsigned want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         while (want && more_work) {
             if (next >= run_len) {
                 if (lane == 0) run_base = atomicAdd(a.work_counter, 128ull);
@@ -411,24 +408,19 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 walk_init(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
-                active = true; ev = RAY_CONTINUE;
                 if (COUNT) cnt.primary_rays++;
             }
             next += n_take;
-            want = __ballot_sync(0xffffffffu, !active);
+            want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         }
-        const unsigned busy = __ballot_sync(0xffffffffu, active);
+        const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        const int thresh = min((int)a.refill_threshold, __popc(busy));
-        for (;;) {
-            if (active && ev == RAY_CONTINUE) ev = walk_step<true, COUNT, VX_THREADS>(w, a.scene, sm.stack, last_leaf, cnt);
-            if (!keep_walking(active && ev == RAY_CONTINUE, thresh)) break;
-        }
-        if (ev != RAY_CONTINUE) {
+        walk_warp<true, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        if (w.state <= 0 && w.state != ST_IDLE) {
             // cast_translucent = false: the first leaf is the hit whatever its texel is (svo.esvo.glsl:241-242); the picker
             // never reads value or colour (picker.glsl:40-44), so neither the leaf word nor the texture is fetched.
             float4 o0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f), o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
-            if (ev == RAY_LEAF) {
+            if (state_at_leaf(w.state)) {
                 if (COUNT) cnt.leaf_tests++;
                 Leaf g;
                 leaf_geom(w, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS], inv_scale, g);
@@ -444,7 +436,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 }
             }
             __stcs(a.results + 3 * my_task, o0); __stcs(a.results + 3 * my_task + 1, o1); __stcs(a.results + 3 * my_task + 2, o2);
-            active = false; ev = RAY_CONTINUE;
+            w.state = ST_IDLE;
         }
     }
     if (COUNT) flush_counters(a.counters, cnt);
@@ -486,7 +478,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         const int scale_before = w.scale;
         const uint32_t rec_before = w.rec;
         // the frame the shader emits at :175 for this iteration (if it gets past :152-156)
-        if (w.budget > 0 && !(w.t_min > w.limit)) {
+        if (w.state > 0 && !(w.t_min > w.limit)) {
             if (n < a.frames_cap) {
                 VxDebugFrame& f = a.frames[n];
                 f.t_min = w.t_min * inv_scale; f.ptr = ptr; f.idx = oi; f.parent_octant_idx = pidx; f.scale = w.scale;
@@ -498,8 +490,9 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         const float h_before = w.h;
         const float tcx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcy = __fmaf_rn(w.py, w.tcy, -w.tby), tcz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
         const float tc_max = tmin2(tmin2(tcx, tcy), tcz);
-        int ev = walk_step<true, false, VX_THREADS>(w, s, sm.stack, last_leaf, cnt);
-        if (ev == RAY_LEAF) {
+        if (w.state <= 0) break;                      // MAX_STEPS used up (:152)
+        walk_step<true, false>(w, s, sm.stack, last_leaf, cnt);
+        if (state_at_leaf(w.state)) {
             g.value = leaf_value(w, s);
             leaf_geom(w, rox, roy, roz, rdx, rdy, rdz, inv_scale, g);
             int tex_id;
@@ -509,9 +502,9 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
             const bool first_of_kind = g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
             last_leaf = g.value;
-            ev = walk_skip_leaf<VX_THREADS>(w, s, sm.stack);
+            walk_skip_leaf(w, s, sm.stack);
         }
-        if (ev == RAY_MISS) break;
+        if (w.state == ST_MISS) break;
         if (w.scale == scale_before - 1) {            // PUSH happened
             if (tc_max < h_before) { ptr_stack[scale_before] = ptr; pidx_stack[scale_before] = pidx; }
             ptr = rec_before; pidx = oi;

@@ -6,12 +6,12 @@
 //   get_sky_color     assets/shaders/world.glsl:92-108
 //   textureLod state  src/graphics/texture_array.rs:200-203
 // Not a transliteration:
-//  * the traversal is a per-lane step machine (ray_init / ray_step) that persistent warps drive in
+//  * the traversal is a per-lane step machine (walk_init / walk_step) that persistent warps drive in
 //    lock-step, swapping finished rays for new ones between steps;
-//  * ray_step only walks the tree (PUSH / ADVANCE / POP). When it reaches a leaf candidate it returns
-//    RAY_LEAF and the caller evaluates the leaf (value, face, uv, texture, translucency) OUTSIDE the
-//    hot loop, where the lanes of a warp that sit on a leaf do it together; a rejected (translucent)
-//    leaf re-enters the same iteration at its ADVANCE phase (`after_leaf`);
+//  * walk_step only walks the tree (PUSH / ADVANCE / POP). When it reaches a leaf candidate it parks the
+//    ray (state <= ST_LEAF) and the caller evaluates the leaf (value, face, uv, texture, translucency)
+//    OUTSIDE the hot loop, where the lanes of a warp that sit on a leaf do it together; a rejected
+//    (translucent) leaf finishes the same iteration at its ADVANCE phase (walk_skip_leaf);
 //  * node state is (rec, desc) = (record of the CURRENT octant, 16-bit child/leaf masks of its
 //    children) instead of the shader's (ptr, parent_octant_idx). It is a pure function of
 //    (ptr, parent_octant_idx) over an immutable buffer, so PUSH/POP/HIT visit exactly the same nodes
@@ -82,7 +82,7 @@ struct Counters {   // = VxFrameStats counters
 #define VX_THREADS 128
 #define VX_COLD_WORDS 8
 struct Smem {
-    uint32_t* stack;
+    uint32_t stack;        // shared-space byte address of this thread's stack column
     const float* unorm;
     float* cold;
 };
@@ -92,7 +92,8 @@ __host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, bool with_st
 __device__ __forceinline__ Smem make_smem(uint32_t stack_levels, uint32_t* base, bool with_stack = true) {
     Smem m;
     const size_t stack_words = with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0;
-    m.stack = base + threadIdx.x;
+    m.stack = (uint32_t)__cvta_generic_to_shared(base + threadIdx.x);
+    asm volatile("" : "+r"(m.stack));   // opaque from here on: one live register instead of a per-iteration recomputation
     float* lut = reinterpret_cast<float*>(base + stack_words);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)i / 255.0f;
     m.unorm = lut;
@@ -158,7 +159,6 @@ __device__ __noinline__ float4 texture_lod(const TexInfo* ti, const float* unorm
     return make_float4(mixf(c1.x, c2.x, f), mixf(c1.y, c2.y, f), mixf(c1.z, c2.z, f), mixf(c1.w, c2.w, f));
 }
 
-enum : int { RAY_CONTINUE = 0, RAY_LEAF = 1, RAY_MISS = 2 };
 
 // Hot per-ray state of the traversal (registers). The ray's origin/direction are NOT part of it: they are only needed
 // when a leaf is evaluated and live in the per-thread cold area of shared memory (Smem::cold, slots 0-5).
@@ -172,7 +172,7 @@ struct Walk {
     uint32_t rec, desc;       // record of the current octant, child/leaf masks of its children (bits 0-7 leaf, 8-15 child)
     uint32_t idx;             // bits 0-2: child index in mirrored space; bits 4-6: octant_mask; bit 8: inside_voxel
     int scale;
-    int budget;               // MAX_STEPS - iterations done (:152)
+    int state;                // see ST_*: > 0 walking (iterations left of MAX_STEPS), 0 budget used up, < 0 stopped
 };
 
 // Geometry of a leaf candidate (svo.esvo.glsl:190-224, 233)
@@ -226,7 +226,7 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
 
     w.scale = VX_MAX_SCALE - 1;
     w.se = 0.5f;
-    w.budget = VX_MAX_STEPS;
+    w.state = VX_MAX_STEPS;
 
     // state (ptr=0, parent_octant_idx=0): the preamble's child 0 = world root (esvo.rs:179-188)
     const uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
@@ -235,14 +235,32 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
     w.rec = root < s.max_rec ? root : s.max_rec;
 }
 
-// One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate.
-//   RAY_LEAF: the current child is a leaf with t_min > 0 (:185). The caller evaluates it and either finishes the ray or
-//             calls walk_advance() (the ADVANCE/POP tail of THIS iteration, :324-391) and goes on stepping.
-//   `stk` = this thread's column of the shared-memory stack: slot L word k lives at stk[(L*3 + k) * STRIDE].
-// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
-// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
-template <int STRIDE>
-__device__ __forceinline__ bool walk_advance(Walk& w, const uint32_t* stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
+// Per-thread traversal stack access. `stk` is the SHARED-space byte address of this thread's column (Smem::stack_addr),
+// kept in one register and made opaque to the compiler (it otherwise re-derives it from %tid and the CTA's shared window
+// in every loop iteration: 6 instructions, 6 % of the trace kernels — profiles/r01_v3_frame_wavefront.md).
+__device__ __forceinline__ void stack_store(uint32_t stk, uint32_t lvl, uint32_t rec, uint32_t desc, float t_max) {
+    const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(rec) : "memory");
+    asm volatile("st.shared.u32 [%0+512], %1;" ::"r"(a), "r"(desc) : "memory");
+    asm volatile("st.shared.f32 [%0+1024], %1;" ::"r"(a), "f"(t_max) : "memory");
+}
+__device__ __forceinline__ void stack_load(uint32_t stk, uint32_t lvl, uint32_t& rec, uint32_t& desc, float& t_max) {
+    const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rec) : "r"(a) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+512];" : "=r"(desc) : "r"(a) : "memory");
+    asm volatile("ld.shared.f32 %0, [%1+1024];" : "=f"(t_max) : "r"(a) : "memory");
+}
+static_assert(VX_THREADS == 128, "stack_store/stack_load hard-code the 512-byte word stride of a 128-thread CTA");
+
+// Ray state word (Walk::state): > 0 = walking, value = iterations left of the MAX_STEPS budget (:152);
+// 0 = budget used up (a miss, :392); ST_MISS = left the octree / beyond max_dst; ST_IDLE = no ray in this lane;
+// <= ST_LEAF = stopped at a leaf candidate with (ST_LEAF - state) iterations of budget left.
+enum : int { ST_MISS = -2, ST_IDLE = -3, ST_LEAF = -4 };
+__device__ __forceinline__ bool state_at_leaf(int st) { return st <= ST_LEAF; }
+__device__ __forceinline__ bool state_missed(int st) { return st == 0 || st == ST_MISS; }
+
+// ADVANCE / POP (svo.esvo.glsl:324-391). Returns false when the ray left the octree (:365).
+__device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
     uint32_t step_mask = 0;                                                   // :324-327  ADVANCE
     if (tc_max >= tcornx) { step_mask ^= 1; w.px -= w.se; }
     if (tc_max >= tcorny) { step_mask ^= 2; w.py -= w.se; }
@@ -258,10 +276,8 @@ __device__ __forceinline__ bool walk_advance(Walk& w, const uint32_t* stk, uint3
         w.scale = scale;
         w.se = __int_as_float((scale - VX_MAX_SCALE + 127) << 23);            // :361 exp2(scale - 23)
         if (scale >= VX_MAX_SCALE) return false;                              // :365
-        uint32_t lvl = (uint32_t)(VX_MAX_SCALE - 1 - scale);                  // :370-372
-        lvl = lvl < stack_levels ? lvl : stack_levels - 1;
-        const uint32_t* sl = stk + lvl * (3 * STRIDE);
-        w.rec = sl[0]; w.desc = sl[STRIDE]; w.t_max = __uint_as_float(sl[2 * STRIDE]);
+        const uint32_t lvl = min((uint32_t)(VX_MAX_SCALE - 1 - scale), stack_levels - 1u);   // :370-372
+        stack_load(stk, lvl, w.rec, w.desc, w.t_max);
         const uint32_t keep = 0xffffffffu << scale;                           // :377-382 floor(pos) at the new scale
         const uint32_t bx = __float_as_uint(w.px), by = __float_as_uint(w.py), bz = __float_as_uint(w.pz);
         w.px = __uint_as_float(bx & keep); w.py = __uint_as_float(by & keep); w.pz = __uint_as_float(bz & keep);
@@ -271,10 +287,16 @@ __device__ __forceinline__ bool walk_advance(Walk& w, const uint32_t* stk, uint3
     return true;
 }
 
-template <bool LIMITED, bool COUNT, int STRIDE>
-__device__ __forceinline__ int walk_step(Walk& w, const Scene& s, uint32_t* stk, uint32_t& last_leaf, Counters& cnt) {
-    if (w.budget-- <= 0) return RAY_MISS;                                     // :152
-    if (LIMITED && w.t_min > w.limit) return RAY_MISS;                        // :153
+// One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate. Call only with
+// w.state > 0. On return w.state is: the remaining budget (keep stepping while > 0), ST_LEAF (the current child is a leaf
+// with t_min > 0, :185 — the caller evaluates it and either finishes the ray or calls walk_skip_leaf(), the ADVANCE/POP tail
+// of THIS iteration, and goes on stepping), or ST_MISS.
+// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
+// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
+template <bool LIMITED, bool COUNT>
+__device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt) {
+    --w.state;                                                                // :152
+    if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
     if (COUNT) cnt.steps++;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
@@ -282,19 +304,15 @@ __device__ __forceinline__ int walk_step(Walk& w, const Scene& s, uint32_t* stk,
     const uint32_t d = w.desc >> ci;                                          // bit 0: is_leaf, bit 8: is_child (:172-173)
     if ((d & 0x100u) && w.t_min <= w.t_max) {                                 // :178
         if (d & 1u) {
-            if (w.t_min > 0.0f) return RAY_LEAF;                              // :185
+            if (w.t_min > 0.0f) { w.state = ST_LEAF - w.state; return; }      // :185
             if (w.t_min == 0.0f) w.idx |= 0x100u;                             // :180 inside_voxel
         }
         // :266-312 — also taken by a leaf at t_min == 0 (origin inside a voxel), see SURVEY Appendix B
         const float tv_max = tmin2(w.t_max, tc_max);                          // :278
         if (w.t_min <= tv_max) {                                              // :280  PUSH
             if (COUNT) cnt.pushes++;
-            if (tc_max < w.h) {                                               // :284-288
-                uint32_t lvl = (uint32_t)(VX_MAX_SCALE - 1 - w.scale);
-                lvl = lvl < s.stack_levels ? lvl : s.stack_levels - 1;
-                uint32_t* sl = stk + lvl * (3 * STRIDE);
-                sl[0] = w.rec; sl[STRIDE] = w.desc; sl[2 * STRIDE] = __float_as_uint(w.t_max);
-            }
+            if (tc_max < w.h)                                                 // :284-288
+                stack_store(stk, min((uint32_t)(VX_MAX_SCALE - 1 - w.scale), s.stack_levels - 1u), w.rec, w.desc, w.t_max);
             w.h = tc_max;                                                     // :289
             const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));          // child masks of the new octant (the :168 read of later iterations)
             const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));            // :292 get_octant_ptr
@@ -309,21 +327,22 @@ __device__ __forceinline__ int walk_step(Walk& w, const Scene& s, uint32_t* stk,
             w.t_max = tv_max;                                                 // :307
             w.desc = wh >> ((ci & 1u) << 4);                                  // bits above 15 are never looked at
             const uint32_t nr = (wb & 0x80000000u) ? (w.rec + 4u + ci + (wb & 0x7fffffffu)) : wb;
-            w.rec = nr < s.max_rec ? nr : s.max_rec;
-            return RAY_CONTINUE;                                              // :310
+            w.rec = min(nr, s.max_rec);
+            return;                                                           // :310
         }
     } else {
         last_leaf = 0xffffffffu;                                              // :315-316 (adjacent_leaf_count = 0)
     }
-    return walk_advance<STRIDE>(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? RAY_CONTINUE : RAY_MISS;
+    if (!walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
 }
 
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
-template <int STRIDE>
-__device__ __forceinline__ int walk_skip_leaf(Walk& w, const Scene& s, const uint32_t* stk) {
+// The rejected leaf used up no extra iteration: the budget stored in the leaf state is restored.
+__device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t stk) {
+    const int budget = ST_LEAF - w.state;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
-    return walk_advance<STRIDE>(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? RAY_CONTINUE : RAY_MISS;
+    w.state = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
 }
 
 __device__ __forceinline__ uint32_t leaf_value(const Walk& w, const Scene& s) {   // :190-194

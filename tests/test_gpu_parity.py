@@ -385,3 +385,58 @@ def test_full_size_16m_picker_rays_vs_oracle(pkg, ora):
         hits = int((got["dst"] > 0).sum())
         assert 0 < hits < n
     svo.close()
+
+
+# -------------------------------------------------------------------------------------------------- edge cases --
+
+def test_edge_cases(pkg, ora, reg):
+    """Empty / degenerate inputs: zero rays, one ray, a 1x1 and a 1-pixel-wide frame, rays that start outside the octree and
+    never enter it, axis-parallel directions (epsilon clamp), a ray budget that runs out (MAX_STEPS, svo.esvo.glsl:152)."""
+    w = helpers.shader_test_world(pkg, [(x, 0, z, 1) for x in range(32) for z in range(32)] + [(5, 5, 5, 2), (31, 31, 31, 1)])
+    s = helpers.oracle_scene(ora, w, reg)
+    svo = make_svo(pkg, reg, w, size_mb=2, w=64, h=64, rays=4096)
+    # zero rays: nothing to do, no error
+    assert len(svo.raycast_tasks(np.zeros(0, dtype=pkg.TASK_DTYPE))) == 0
+    # single rays, incl. pathological ones
+    cases = [((16.0, 40.0, 16.0), (0.0, -1.0, 0.0), -1.0),      # straight down, two zero components -> epsilon clamp
+             ((-50.0, 10.0, 16.0), (-1.0, 0.0, 0.0), -1.0),     # outside, pointing away
+             ((16.0, 1.5, 16.0), (1.0, 0.0, 0.0), -1.0),        # skimming 0.5 above the floor along +x
+             ((5.5, 5.5, 5.5), (0.0, 1.0, 0.0), -1.0),          # origin inside a voxel
+             ((16.0, 40.0, 16.0), (0.0, -1.0, 0.0), 0.0),       # max_dst = 0
+             ((1e6, 1e6, 1e6), (-1.0, -1.0, -1.0), -1.0),       # far outside, pointing at the world
+             ((16.0, float("nan"), 16.0), (0.0, -1.0, 0.0), -1.0)]
+    for pos, d, md in cases:
+        t = np.zeros(1, dtype=pkg.TASK_DTYPE)
+        t["pos"], t["dir"], t["max_dst"] = pos, np.array(d, np.float32) / np.linalg.norm(d), md
+        want, _ = s.raycast(t)
+        got = svo.raycast_tasks(t)
+        if np.isnan(pos).any():
+            # NaN in -> the shader's result is undefined; require the same non-NaN fields and NaN in the same places (the bit
+            # pattern of a generated NaN differs between x86 and the GPU)
+            for f in ("dst", "inside_voxel", "pos", "normal"):
+                assert np.array_equal(got[f], want[f], equal_nan=True), (f, got, want)
+            continue
+        assert got.tobytes() == want.tobytes(), (pos, d, md, got, want)
+    # ragged tiny frames
+    for (fw, fh) in ((1, 1), (1, 64), (64, 1), (33, 17)):
+        p = pkg.render_params(cam_pos=(16.0, 20.0, 50.0), cam_fwd=(0.0, -0.4, -1.0), fov_y_deg=72.0, aspect=fw / fh)
+        got, got8, want, want8, _ = render_both(pkg, ora, reg, w, p, fw, fh, svo=svo)
+        assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1 and got.shape == (fh, fw, 4)
+    svo.close()
+    # MAX_STEPS: a checkerboard at voxel level makes a grazing ray take > 1000 iterations -> reported as a miss by both
+    blocks = [(x, y, z, 1) for x in range(32) for y in range(32) for z in range(32) if (x + y + z) % 2 == 0 and y < 2]
+    w2 = helpers.shader_test_world(pkg, blocks, svo_pos=(3, 3, 3))
+    s2 = helpers.oracle_scene(ora, w2, reg)
+    svo2 = make_svo(pkg, reg, w2, size_mb=4, w=8, h=8, rays=1 << 16)
+    tasks = helpers.random_tasks(pkg, 1 << 16, 0.0, 128.0, -1.0, seed=5)
+    tasks["pos"][:, 1] = 98.5 + 0.01 * np.arange(1 << 16, dtype=np.float32) / (1 << 16)   # just above the board (chunk y = 96..128)
+    tasks["dir"][:, 1] = -1e-3
+    tasks["dir"] /= np.linalg.norm(tasks["dir"], axis=1, keepdims=True)
+    svo2.set_option(pkg.OPT_COUNT, 1)
+    want, cnt = s2.raycast(tasks)
+    got = svo2.raycast_tasks(tasks)
+    st = svo2.frame_stats(1)
+    assert got.tobytes() == want.tobytes()
+    assert st["steps"] == cnt["steps"]
+    print("max-steps scene: mean iterations per ray", cnt["steps"] / len(tasks))
+    svo2.close()

@@ -16,6 +16,7 @@ while [ $# -gt 0 ]; do
     sweepe) IFS=';' read -ra OPTS <<< "$2"; for opt in "${OPTS[@]}"; do echo "== $opt"; python bench.py --steps 10 --warmup 3 --skip-cpu $opt 2>&1 | python -c "$fmt"; done; shift 2;;
     ncu) ncu --set full --clock-control none --import-source on -k regex:"trace_|shade_" -s 6 -c 3 -f -o gpurun_out/prof_$2 python bench.py --steps 2 --warmup 1 --skip-cpu --skip-e2e $3 > gpurun_out/ncu_$2.log 2>&1; tail -3 gpurun_out/ncu_$2.log; shift 3;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$2.csv python bench.py --steps 8 --warmup 3 --skip-cpu > gpurun_out/launches_$2.log 2>&1; tail -2 gpurun_out/launches_$2.log | cut -c1-300; shift 2;;
+    sanitize) compute-sanitizer --tool $2 --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or edge or pipelined or sharded_frames or dirty" > gpurun_out/sanitizer_$2.log 2>&1; echo "sanitizer $2 rc=$?"; tail -5 gpurun_out/sanitizer_$2.log; shift 2;;
     mtest) python -m pytest tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | tail -15; shift;;
     scale1) echo "== N=$2 $3"; python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $2 --steps 20 --warmup 5 --skip-cpu $3 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM\|^$\|NCCL version" | tee -a gpurun_out/scale_lines.jsonl | python -c "$fmt"; shift 3;;
     scale) for opt in "" "--gather nccl"; do echo "== N=$2 $opt $3"; python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $2 --steps 20 --warmup 5 --skip-cpu $opt $3 2>&1 | grep -v "^W\|^\*\*\*" | python -c "$fmt"; done; shift 3;;

@@ -96,7 +96,7 @@ __device__ __noinline__ bool translucent_leaf_accepts(const TexInfo* tex, const 
     if (face_id == 3) tex_id = __ldg(&m->tex_top);
     else if (face_id == 2) tex_id = __ldg(&m->tex_bottom);
     uint32_t nf = 0;
-    const float4 c = texture_lod(tex, unorm, u, v, tex_id, lod_of_dst(dst), &nf);
+    const float4 c = texture_lod<4>(tex, unorm, u, v, tex_id, lod_of_dst(dst), &nf);
     const bool first_of_kind = value != last_leaf;   // adjacent_leaf_count == 0 <=> last_leaf == 0xffffffff (never a block id)
     return c.w > 0.0f && first_of_kind;
 }
@@ -135,7 +135,7 @@ __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk,
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
 template <bool COUNT>
 __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(0, smem_raw, false);
+    const Smem sm = make_smem(a.scene.unorm, 0, smem_raw, false);
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -233,15 +233,15 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     if (live) {
         const uint32_t slot = strip * 128u + threadIdx.x;
         const float4 h1 = __ldcs(a.hit1 + slot);
+        const float4 h0 = __ldcs(a.hit0 + slot);   // issued together with h1 (a miss leaves its hit0 slot unwritten: loaded, never used)
         const uint32_t flags = __float_as_uint(h1.w);
         if (flags & 8u) {
-            const float4 h0 = __ldcs(a.hit0 + slot);
             Leaf g;
             g.dst = h0.x; g.value = __float_as_uint(h0.y); g.u = h0.z; g.v = h0.w; g.face_id = (int)(flags & 7u);
             int tex_id; float tex_lod;
             leaf_texture(a.scene, g, tex_id, tex_lod);
             uint32_t nf = 0;
-            const float4 c = texture_lod(a.scene.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // svo.esvo.glsl:237 (counted by the trace kernel)
+            const float4 c = texture_lod<4>(a.scene.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // svo.esvo.glsl:237 (counted by the trace kernel)
             Shade sh;
             sh.r = c.x; sh.g = c.y; sh.b = c.z; sh.a = c.w;
             nf = 0;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
@@ -374,7 +374,7 @@ struct RaycastArgs {
 template <bool COUNT>
 __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
@@ -458,7 +458,7 @@ struct DebugArgs {
 // stacks) next to it to emit reference-format frames. Launched <<<1, VX_THREADS>>>; thread 0 casts.
 __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene.stack_levels, smem_raw);
+    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     if (threadIdx.x != 0) return;
     const Scene& s = a.scene;
     const float octree_scale = __uint_as_float(__ldg(s.desc - 1));
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
             int tex_id;
             leaf_texture(s, g, tex_id, tex_lod);
             uint32_t nf = 0;
-            color = texture_lod(s.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // the shader samples in both modes (:237)
+            color = texture_lod<4>(s.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // the shader samples in both modes (:237)
             const bool first_of_kind = g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
             last_leaf = g.value;
@@ -525,6 +525,9 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
 }
 
 // ---- small utility kernels ---------------------------------------------------------------------------------------------
+
+// unorm[b] = b / 255.0f with an IEEE division (what unpacking an RGBA8 texel means), once per context
+__global__ void unorm_kernel(float* table) { table[threadIdx.x] = (float)threadIdx.x / 255.0f; }
 
 // glGenerateMipmap stand-in: level l+1 texel = rounded mean of the 2x2 block below (texture_array.rs:258-260)
 __global__ void mip_kernel(const uint32_t* src, uint32_t* dst, uint32_t pw, uint32_t ph, uint32_t cw, uint32_t ch, uint32_t layers) {

@@ -64,6 +64,7 @@ struct Scene {
     const Material* __restrict__ materials;
     uint32_t n_materials;
     const TexInfo* __restrict__ tex;
+    const float* __restrict__ unorm;     // 256-entry b / 255.0f table in global memory (copied into shared memory per CTA)
     uint32_t stack_levels;               // entries of the per-thread traversal stack (= SVO depth + 1, <= 23)
     unsigned long long opaque_materials; // bit m set (m < 64): every texel of the three face textures of material m has alpha > 0,
                                          // so a leaf of that material is accepted by the translucency rule (:241-242) without sampling
@@ -89,13 +90,13 @@ struct Smem {
 __host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, bool with_stack = true) {
     return ((with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0) + 256 + (size_t)VX_COLD_WORDS * VX_THREADS) * 4;
 }
-__device__ __forceinline__ Smem make_smem(uint32_t stack_levels, uint32_t* base, bool with_stack = true) {
+__device__ __forceinline__ Smem make_smem(const float* unorm_table, uint32_t stack_levels, uint32_t* base, bool with_stack = true) {
     Smem m;
     const size_t stack_words = with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0;
     m.stack = (uint32_t)__cvta_generic_to_shared(base + threadIdx.x);
     asm volatile("" : "+r"(m.stack));   // opaque from here on: one live register instead of a per-iteration recomputation
     float* lut = reinterpret_cast<float*>(base + stack_words);
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)i / 255.0f;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __ldg(unorm_table + i);
     m.unorm = lut;
     m.cold = lut + 256 + threadIdx.x;
     __syncthreads();
@@ -137,13 +138,18 @@ __device__ __forceinline__ float4 sample_linear(const TexInfo* ti, const float* 
 // Deliberately ONE out-of-line copy: it is called a handful of times per pixel (leaf colour, shadow alpha, normal
 // map) against hundreds of traversal steps, and inlining it three times is what blew the instruction cache.
 // Returns the number of texels read in *fetches (added).
+// NCH = how many channels the caller uses (4 = rgba, 3 = rgb: the normal map's alpha is never read, world.glsl:60): the
+// unused channel's table look-ups and lerps are dead code in that instantiation.
+template <int NCH>
 __device__ __noinline__ float4 texture_lod(const TexInfo* ti, const float* unorm, float u, float v, int tex_id, float lod, uint32_t* fetches) {
     const int layer = iclamp(tex_id, 0, (int)ti->layers - 1);
     if (!(lod > 0.0f)) {
         const int i = iclamp(ifloor_clamped(u * (float)ti->w), 0, (int)ti->w - 1);
         const int j = imod(ifloor_clamped(v * (float)ti->h), (int)ti->h);
         *fetches += 1;
-        return fetch_texel(ti, unorm, 0, ti->w, ti->h, layer, i, j);
+        float4 r = fetch_texel(ti, unorm, 0, ti->w, ti->h, layer, i, j);
+        if (NCH < 4) r.w = 0.0f;
+        return r;
     }
     const float maxl = (float)(ti->levels - 1);
     const float l = gl_min(lod, maxl);
@@ -151,12 +157,13 @@ __device__ __noinline__ float4 texture_lod(const TexInfo* ti, const float* unorm
     const uint32_t d1 = (uint32_t)fl;
     const uint32_t d2 = (d1 + 1 < ti->levels) ? d1 + 1 : ti->levels - 1;
     const float f = l - fl;
-    const float4 c1 = sample_linear(ti, unorm, d1, layer, u, v);
+    float4 c1 = sample_linear(ti, unorm, d1, layer, u, v);
+    if (NCH < 4) c1.w = 0.0f;
     *fetches += 4;
     if (d2 == d1 || f == 0.0f) return c1;
     const float4 c2 = sample_linear(ti, unorm, d2, layer, u, v);
     *fetches += 4;
-    return make_float4(mixf(c1.x, c2.x, f), mixf(c1.y, c2.y, f), mixf(c1.z, c2.z, f), mixf(c1.w, c2.w, f));
+    return make_float4(mixf(c1.x, c2.x, f), mixf(c1.y, c2.y, f), mixf(c1.z, c2.z, f), NCH < 4 ? 0.0f : mixf(c1.w, c2.w, f));
 }
 
 
@@ -493,7 +500,7 @@ __device__ __forceinline__ void shade_hit(const Scene& s, const float* unorm, co
     else { tx = sgn; tz = 0.0f; by = 1.0f; bz = 0.0f; }                     // z-: (-1,0,0) z+: (1,0,0); bitangent (0,1,0)
 
     if (tex_normal_id != -1) {                                       // :59-67
-        const float4 t = texture_lod(s.tex, unorm, g.u, g.v, tex_normal_id, tex_lod, fetches);
+        const float4 t = texture_lod<3>(s.tex, unorm, g.u, g.v, tex_normal_id, tex_lod, fetches);
         float ex = t.x * 2 - 1, ey = t.z * 2 - 1, ez = t.y * 2 - 1;  // .xzy
         const float l = sqrtf(dot3(ex, ey, ez, ex, ey, ez));
         ex = ex / l; ey = ey / l; ez = ez / l;

@@ -45,6 +45,7 @@ struct VxCtx {
     uint32_t n_materials = 0;
     uint32_t* d_texels = nullptr;
     TexInfo* d_texinfo = nullptr;     // texture array description read by the device-side sampler
+    float* d_unorm = nullptr;         // b / 255.0f table
     uint32_t tex_layers = 0;
 
     float4* d_frame = nullptr;
@@ -101,6 +102,7 @@ static Scene make_scene(const VxCtx* c) {
     s.opaque_materials = c->opaque_materials;
     s.materials = c->d_materials; s.n_materials = c->n_materials;
     s.tex = c->d_texinfo;
+    s.unorm = c->d_unorm;
     uint32_t levels = c->stats.depth + 1;
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     return s;
@@ -185,6 +187,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
         CUC(cudaMalloc(&c->d_tasks, (size_t)cfg->max_rays * 48));
         CUC(cudaMalloc(&c->d_results, (size_t)cfg->max_rays * 48));
     }
+    CUC(cudaMalloc(&c->d_unorm, 256 * sizeof(float)));
+    unorm_kernel<<<1, 256, 0, c->s_upload>>>(c->d_unorm);
     CUC(cudaMalloc(&c->d_counters, 2 * sizeof(Counters)));
     CUC(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(Counters), c->s_upload));
     CUC(cudaMalloc(&c->d_work, 64 + 16 * 32));   // [0..7] u64: picker run counter at [4]; then 16 bands x 8 u32 render counters
@@ -209,6 +213,7 @@ void vx_destroy(VxCtx* c) {
     if (c->d_materials) cudaFree(c->d_materials);
     if (c->d_texels) cudaFree(c->d_texels);
     if (c->d_texinfo) cudaFree(c->d_texinfo);
+    if (c->d_unorm) cudaFree(c->d_unorm);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
     if (c->d_hit0) cudaFree(c->d_hit0);
@@ -608,8 +613,27 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     if (bands > VX_MAX_BANDS) bands = VX_MAX_BANDS;
     if (bands > a.macro_y) bands = a.macro_y;
     CU(c, cudaEventRecord(c->t0_render, c->s_render));
-    for (uint32_t b = bands; b-- > 0;) {   // top of the image first: sky-heavy bands finish early and their copies start early
-        const uint32_t row0 = (uint32_t)((uint64_t)a.macro_y * b / bands), row1 = (uint32_t)((uint64_t)a.macro_y * (b + 1) / bands);
+    // Band sizes shrink geometrically in render order (top of the image first, ratio VX_BAND_RATIO): the copy of band k runs
+    // under the tracing of band k+1, so only the copy of the LAST, smallest band is exposed. The ratio is the measured
+    // copy-time / render-time of a 4K frame on this box (33 MB at ~33 GB/s vs 1.5 ms).
+    const double ratio = 0.6;
+    double wsum = 0.0, wk = 1.0;
+    for (uint32_t k = 0; k < bands; ++k) { wsum += wk; wk *= ratio; }
+    uint32_t edge[VX_MAX_BANDS + 1];
+    {
+        double acc = 0.0; wk = 1.0;
+        edge[0] = a.macro_y;                                   // render order k = 0 is the top band: rows [edge[k+1], edge[k])
+        for (uint32_t k = 0; k < bands; ++k) {
+            acc += wk; wk *= ratio;
+            uint32_t e = a.macro_y - (uint32_t)((double)a.macro_y * acc / wsum + 0.5);
+            if (k + 1 == bands) e = 0;
+            if (e > edge[k]) e = edge[k];
+            edge[k + 1] = e;
+        }
+    }
+    for (uint32_t b = 0; b < bands; ++b) {
+        const uint32_t row0 = edge[b + 1], row1 = edge[b];
+        if (row1 == row0) continue;
         rc = launch_wavefront(c, a, p->render_shadows != 0, b, row0, row1, false);
         if (rc) return rc;
         const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;

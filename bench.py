@@ -254,7 +254,10 @@ def main():
     if rank == 0:
         svo.pack_dirty(dirty, packed_host.numpy())
         if n_gpus > 1:
-            sf.packed_dirty[:packed_n].copy_(packed_host)
+            for b in sf.dirty_bufs:
+                b[:packed_n].copy_(packed_host)
+    # the dirty ranges of frame i+1 are broadcast (side stream) while frame i renders: prime the pipeline with frame 1's
+    sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth)
 
     def flush():
         if not args.no_flush:
@@ -263,10 +266,13 @@ def main():
     def step_resident():
         """One frame with every input already in HBM (rank 0 holds the packed dirty set on the device)."""
         flush()
-        # per-frame changed-chunk ranges: rank 0's packed dirty set -> all GPUs over NVLink, applied by a scatter kernel
-        sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth)
+        # per-frame changed-chunk ranges: rank 0's packed dirty set -> all GPUs over NVLink (NCCL broadcast, issued one frame
+        # ahead on a side stream), applied here by a scatter kernel; then the next frame's set starts travelling
+        sf.apply_dirty()
+        sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth)
         sf.render(vxp)
         sf.finish()   # tiles in GPU 0's framebuffer (p2p: stored there by the render kernels; nccl: pack/send/recv/unpack)
+        sf.release()
 
     frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
     mirror = svo.host_mirror(24 + world.size_bytes)
@@ -279,6 +285,8 @@ def main():
             for (o, l), b in zip(dirty, staged):   # the host-side serializer writing its changes (write_changes_to)
                 mirror[24 + o:24 + o + l] = np.frombuffer(b, np.uint8)
         if n_gpus > 1:
+            # host-resident inputs cannot be sent a frame ahead: pack -> H2D -> broadcast -> scatter sit in front of the frame
+            sf.apply_dirty()          # drain the set the resident loop left in flight (first e2e step only)
             if rank == 0:
                 svo.pack_dirty(dirty, packed_host.numpy())
             sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_host)
@@ -293,6 +301,7 @@ def main():
         if rank == 0:
             import ctypes as C
             svo._check(pkg.lib().vx_read_frame_rgba8(svo.ctx, C.c_void_p(frame8.data_ptr())))
+        sf.release()
 
     def barrier():
         if n_gpus > 1:
@@ -397,8 +406,9 @@ def main():
             "refill_threshold": args.refill or 1,
             "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
-                               ("finished pixels stored by the render kernels straight into GPU 0's framebuffer over NVLink peer memory, "
-                                "4-byte all-reduce as the frame barrier" if args.gather == "p2p" else "pack, NCCL send/recv to GPU 0, unpack")),
+                               ("finished pixels stored by the shade/shadow kernels straight into GPU 0's framebuffer over NVLink peer memory, "
+                                "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"
+                                if args.gather == "p2p" else "pack, NCCL send/recv to GPU 0, unpack")),
         },
         "frame_ms": ms_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

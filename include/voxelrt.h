@@ -286,6 +286,22 @@ int vx_frame_ipc_handle(VxCtx* ctx, uint8_t handle_out[64]);
 int vx_open_peer_frame(VxCtx* ctx, const uint8_t handle[64]);
 int vx_close_peer_frame(VxCtx* ctx);
 
+/* Frame flags for the peer-memory gather: 63 32-bit frame counters per context; the root's are mapped by its peers (same IPC
+ * scheme as the framebuffer), so ranks order their frames without a collective:
+ *   vx_frame_signal(slot, v)     on the render stream: publish everything this GPU wrote so far (its pixels in the root's
+ *                                frame), then raise flag `slot` (of the root if peer flags are open, else local) to v
+ *   vx_frame_wait(first, n, v)   on the render stream: wait until flags [first, first+n) are all >= v
+ *   vx_frame_gate(slot, v)       the next vx_render waits for flag `slot` >= v BETWEEN its trace and shade kernels: primary
+ *                                rays of frame i+1 overlap the root's consumption of frame i, pixels are held back
+ *   vx_frame_sync_errors         number of waits that gave up (~2 s): a lost peer is an error, not a hang */
+int vx_sync_ipc_handle(VxCtx* ctx, uint8_t handle_out[64]);
+int vx_open_peer_sync(VxCtx* ctx, const uint8_t handle[64]);
+int vx_close_peer_sync(VxCtx* ctx);
+int vx_frame_signal(VxCtx* ctx, uint32_t slot, uint32_t value);
+int vx_frame_wait(VxCtx* ctx, uint32_t first_slot, uint32_t n_slots, uint32_t value);
+int vx_frame_gate(VxCtx* ctx, uint32_t slot, uint32_t value);
+int vx_frame_sync_errors(VxCtx* ctx, uint32_t* out);
+
 /* Run this context's work on caller-owned CUDA streams (cudaStream_t passed as void*) so that it orders
  * with the caller's collectives without host synchronisation. NULL keeps the library's own stream. */
 int vx_set_streams(VxCtx* ctx, void* render_stream, void* upload_stream, void* picker_stream);

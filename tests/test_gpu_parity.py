@@ -423,20 +423,35 @@ def test_edge_cases(pkg, ora, reg):
         got, got8, want, want8, _ = render_both(pkg, ora, reg, w, p, fw, fh, svo=svo)
         assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1 and got.shape == (fh, fw, 4)
     svo.close()
-    # MAX_STEPS: a checkerboard at voxel level makes a grazing ray take > 1000 iterations -> reported as a miss by both
-    blocks = [(x, y, z, 1) for x in range(32) for y in range(32) for z in range(32) if (x + y + z) % 2 == 0 and y < 2]
-    w2 = helpers.shader_test_world(pkg, blocks, svo_pos=(3, 3, 3))
+    # MAX_STEPS (svo.esvo.glsl:18,152,392): 32 chunks in a row, each with isolated voxels on every other cell of its floor. A ray
+    # skimming the empty row between them must descend to voxel level every two cells: ~2 iterations per voxel. From x = 0.5 the
+    # wall at x = 1023 is more than 1000 iterations away and is NOT found (budget exhausted -> miss); from x = 900.5 it is hit.
+    w2 = pkg.World()
+    dust = [(x, 0, z, 1) for x in range(0, 32, 2) for z in range(0, 32, 2)]
+    for cx in range(32):
+        blocks = list(dust) + ([(31, y, z, 2) for y in range(4) for z in range(4)] if cx == 31 else [])
+        w2.set_leaf_blocks((cx, 0, 0), blocks, uid=100 + cx, lod=5, compact=True)
+    w2.serialize()
     s2 = helpers.oracle_scene(ora, w2, reg)
-    svo2 = make_svo(pkg, reg, w2, size_mb=4, w=8, h=8, rays=1 << 16)
-    tasks = helpers.random_tasks(pkg, 1 << 16, 0.0, 128.0, -1.0, seed=5)
-    tasks["pos"][:, 1] = 98.5 + 0.01 * np.arange(1 << 16, dtype=np.float32) / (1 << 16)   # just above the board (chunk y = 96..128)
-    tasks["dir"][:, 1] = -1e-3
-    tasks["dir"] /= np.linalg.norm(tasks["dir"], axis=1, keepdims=True)
+    svo2 = make_svo(pkg, reg, w2, size_mb=4, w=64, h=64, rays=1 << 12)
+    for x0, frames, hit in ((0.5, 1000, False), (512.5, 1000, False), (900.5, None, True)):
+        o = s2.debug_cast((x0, 0.5, 1.5), (1.0, 0.0, 0.0), -1.0, False, frames_cap=4)
+        c = svo2.debug_cast((x0, 0.5, 1.5), (1.0, 0.0, 0.0), -1.0, False, frames_cap=4)
+        assert_same_cast(o, c)
+        assert (c[0].t > 0) == hit and (frames is None or c[2] == frames), (x0, c[2], c[0].t)
+    tasks = np.zeros(1 << 12, dtype=pkg.TASK_DTYPE)
+    tasks["max_dst"] = -1.0
+    tasks["pos"] = np.stack([np.linspace(0.5, 1000.5, 1 << 12), np.full(1 << 12, 0.5), 1.5 + 2.0 * (np.arange(1 << 12) % 16)], axis=1)
+    tasks["dir"] = (1.0, 0.0, 0.0)
     svo2.set_option(pkg.OPT_COUNT, 1)
     want, cnt = s2.raycast(tasks)
     got = svo2.raycast_tasks(tasks)
     st = svo2.frame_stats(1)
     assert got.tobytes() == want.tobytes()
-    assert st["steps"] == cnt["steps"]
-    print("max-steps scene: mean iterations per ray", cnt["steps"] / len(tasks))
+    assert st["steps"] == cnt["steps"] and cnt["steps"] > 500 * len(tasks)
+    assert 0 < (got["dst"] > 0).sum() < len(tasks)          # some rays run out of budget, some reach the wall
+    # a frame looking down the row: pixels whose rays exhaust the budget are sky in both implementations
+    p = pkg.render_params(cam_pos=(0.5, 0.6, 1.5), cam_fwd=(1.0, -0.0005, 0.0), fov_y_deg=20.0, aspect=1.0)
+    got, got8, want, want8, _ = render_both(pkg, ora, reg, w2, p, 64, 64, svo=svo2)
+    assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
     svo2.close()

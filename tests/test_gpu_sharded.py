@@ -65,15 +65,21 @@ def _worker(rank, world_size, port, out_dir):
         for gather in ("p2p", "nccl"):
             sf = pkg.sharded.ShardedFrame(svo, rank, world_size, dist=dist, torch=torch, device=dev, gather=gather)
             sf.configure(W, H, max_dirty_bytes=16 * n_ranges + payload)
-            for _ in range(2):   # twice: the second frame checks the frame-to-frame ordering of peer stores
-                sf.broadcast_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
+            # three frames: the later ones exercise the frame-to-frame ordering (gate / signal / wait / release flags) and the
+            # one-frame-ahead dirty broadcast on the side stream
+            sf.prefetch_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
+            for i in range(3):
+                sf.apply_dirty()
+                if i < 2:
+                    sf.prefetch_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
                 sf.render(vxp)
                 sf.finish()
+                if rank == 0 and i == 2:
+                    svo.width, svo.height = W, H
+                    frames[gather] = svo.read_rgba32f()
+                sf.release()
             torch.cuda.synchronize()
-            dist.barrier()
-            if rank == 0:
-                svo.width, svo.height = W, H
-                frames[gather] = svo.read_rgba32f()
+            assert svo.frame_sync_errors() == 0, "a frame-flag wait timed out"
             dist.barrier()
             sf.close()
         if rank == 0:

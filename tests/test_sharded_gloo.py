@@ -120,6 +120,7 @@ def _worker(rank, world_size, port, result_path):
         vxp = pkg.to_vx_render_params(q)
         sf.render(vxp)
         sf.finish()
+        sf.release()
         if rank == 0:
             tex, mips = reg.textures()
             full, _ = ora.Scene(replica, reg.materials().tobytes(), tex, mips).render(vxp, W, H)

@@ -105,6 +105,8 @@ VX_SYMBOLS = [
     "vx_debug_cast", "vx_frame_stats", "vx_set_option", "vx_launch_count", "vx_build_info",
     "vx_shard_bytes", "vx_pack_shard", "vx_unpack_shard", "vx_set_streams", "vx_stream",
     "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame", "vx_render_read_rgba8",
+    "vx_sync_ipc_handle", "vx_open_peer_sync", "vx_close_peer_sync", "vx_frame_signal", "vx_frame_wait", "vx_frame_gate",
+    "vx_frame_sync_errors",
 ]
 
 _lib = None
@@ -162,6 +164,13 @@ def lib():
     L.vx_frame_ipc_handle.argtypes = [P, P]; L.vx_frame_ipc_handle.restype = C.c_int
     L.vx_open_peer_frame.argtypes = [P, P]; L.vx_open_peer_frame.restype = C.c_int
     L.vx_close_peer_frame.argtypes = [P]; L.vx_close_peer_frame.restype = C.c_int
+    L.vx_sync_ipc_handle.argtypes = [P, P]; L.vx_sync_ipc_handle.restype = C.c_int
+    L.vx_open_peer_sync.argtypes = [P, P]; L.vx_open_peer_sync.restype = C.c_int
+    L.vx_close_peer_sync.argtypes = [P]; L.vx_close_peer_sync.restype = C.c_int
+    L.vx_frame_signal.argtypes = [P, C.c_uint32, C.c_uint32]; L.vx_frame_signal.restype = C.c_int
+    L.vx_frame_wait.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32]; L.vx_frame_wait.restype = C.c_int
+    L.vx_frame_gate.argtypes = [P, C.c_uint32, C.c_uint32]; L.vx_frame_gate.restype = C.c_int
+    L.vx_frame_sync_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_frame_sync_errors.restype = C.c_int
     _lib = L
     return L
 
@@ -618,6 +627,31 @@ class Svo:
 
     def close_peer_frame(self):
         self._check(lib().vx_close_peer_frame(self.ctx))
+
+    def sync_ipc_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self._check(lib().vx_sync_ipc_handle(self.ctx, buf))
+        return bytes(buf)
+
+    def open_peer_sync(self, handle):
+        self._check(lib().vx_open_peer_sync(self.ctx, (C.c_uint8 * 64)(*handle)))
+
+    def close_peer_sync(self):
+        self._check(lib().vx_close_peer_sync(self.ctx))
+
+    def frame_signal(self, slot, value):
+        self._check(lib().vx_frame_signal(self.ctx, slot, value))
+
+    def frame_wait(self, first_slot, n_slots, value):
+        self._check(lib().vx_frame_wait(self.ctx, first_slot, n_slots, value))
+
+    def frame_gate(self, slot, value):
+        self._check(lib().vx_frame_gate(self.ctx, slot, value))
+
+    def frame_sync_errors(self):
+        n = C.c_uint32()
+        self._check(lib().vx_frame_sync_errors(self.ctx, C.byref(n)))
+        return n.value
 
     def frame_device_ptr(self):
         p, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()

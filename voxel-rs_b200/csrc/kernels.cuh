@@ -524,6 +524,30 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     *a.n_frames = n;
 }
 
+// ---- cross-GPU frame flags (multi-GPU tile gather over peer memory) ----------------------------------------------------------
+// A flag is a 32-bit frame counter in GPU 0's memory. signal: everything this GPU wrote before (its pixels in GPU 0's frame)
+// is made visible system-wide, then the flag is raised. wait: spin (acquire, system scope) until every flag of the range
+// reached `value`; gives up after ~2 s and records it in flags[63] so that a lost peer shows up as an error, not as a hang.
+__global__ void flag_signal_kernel(unsigned int* flag, unsigned int value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsigned int count, unsigned int value, unsigned int* error_word) {
+    const unsigned int i = threadIdx.x;
+    if (i < count) {
+        unsigned int v = 0;
+        unsigned int spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + first + i) : "memory");
+            if ((int)(v - value) >= 0) break;
+            __nanosleep(200);
+            if (++spins > (1u << 23)) { atomicAdd(error_word, 1u); break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
 // ---- small utility kernels ---------------------------------------------------------------------------------------------
 
 // unorm[b] = b / 255.0f with an IEEE division (what unpacking an RGBA8 texel means), once per context

@@ -51,7 +51,11 @@ struct VxCtx {
     float4* d_frame = nullptr;
     uint32_t* d_frame8 = nullptr;
     uint32_t frame_w = 0, frame_h = 0;
-    float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_set_frame_target)
+    float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_open_peer_frame)
+    unsigned int* d_flags = nullptr;      // 64 frame flags of this ctx (the root's are mapped by its peers); [63] = wait timeouts
+    unsigned int* flags_target = nullptr; // the flags this ctx signals / gates on: d_flags, or the root's (vx_open_peer_sync)
+    bool gate_armed = false;              // next vx_render: wait for flags_target[gate_slot] >= gate_value between trace and shade
+    unsigned int gate_slot = 0, gate_value = 0;
 
     // wavefront buffers of the render path (kernels.cuh), sized for the padded pixel count of the largest frame seen
     float4 *d_hit0 = nullptr, *d_hit1 = nullptr, *d_sh0 = nullptr, *d_sh1 = nullptr;
@@ -187,6 +191,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
         CUC(cudaMalloc(&c->d_tasks, (size_t)cfg->max_rays * 48));
         CUC(cudaMalloc(&c->d_results, (size_t)cfg->max_rays * 48));
     }
+    CUC(cudaMalloc(&c->d_flags, 64 * sizeof(unsigned int)));
+    CUC(cudaMemsetAsync(c->d_flags, 0, 64 * sizeof(unsigned int), c->s_upload));
     CUC(cudaMalloc(&c->d_unorm, 256 * sizeof(float)));
     unorm_kernel<<<1, 256, 0, c->s_upload>>>(c->d_unorm);
     CUC(cudaMalloc(&c->d_counters, 2 * sizeof(Counters)));
@@ -207,6 +213,8 @@ void vx_destroy(VxCtx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     if (c->frame_target) cudaIpcCloseMemHandle(c->frame_target);
+    if (c->flags_target) cudaIpcCloseMemHandle(c->flags_target);
+    if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_world_raw) cudaFree(c->d_world_raw);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -522,6 +530,13 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
         k1<<<grid < need ? grid : need, VX_THREADS, smem, c->s_render>>>(a);
         c->launches++;
         if (timed) CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
+        // (multi-GPU, peer frame) the pixels go to GPU 0's framebuffer: not before GPU 0 released the previous frame
+        if (c->gate_armed) {
+            unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
+            flag_wait_kernel<<<1, 32, 0, c->s_render>>>(f, c->gate_slot, 1, c->gate_value, c->d_flags + 63);
+            c->launches++;
+            c->gate_armed = false;
+        }
         // 2. shading -> final pixels + shadow ray list
         const size_t smem2 = smem_bytes(0, false);
         if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
@@ -838,6 +853,71 @@ int vx_close_peer_frame(VxCtx* c) {
     CU(c, cudaStreamSynchronize(c->s_render));
     CU(c, cudaIpcCloseMemHandle(c->frame_target));
     c->frame_target = nullptr;
+    return VX_OK;
+}
+
+int vx_sync_ipc_handle(VxCtx* c, uint8_t handle_out[64]) {
+    if (!c || !handle_out) return fail(c, VX_E_ARG, "vx_sync_ipc_handle: null argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(c, cudaIpcGetMemHandle(&h, c->d_flags));
+    std::memcpy(handle_out, &h, 64);
+    return VX_OK;
+}
+
+int vx_open_peer_sync(VxCtx* c, const uint8_t handle[64]) {
+    if (!c || !handle) return fail(c, VX_E_ARG, "vx_open_peer_sync: null argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->flags_target) return fail(c, VX_E_STATE, "vx_open_peer_sync: peer flags are already open");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->flags_target = (unsigned int*)p;
+    return VX_OK;
+}
+
+int vx_close_peer_sync(VxCtx* c) {
+    if (!c) return VX_E_ARG;
+    if (!c->flags_target) return VX_OK;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_render));
+    CU(c, cudaIpcCloseMemHandle(c->flags_target));
+    c->flags_target = nullptr;
+    return VX_OK;
+}
+
+int vx_frame_signal(VxCtx* c, uint32_t slot, uint32_t value) {
+    if (!c || slot >= 63) return fail(c, VX_E_ARG, "vx_frame_signal: bad slot");
+    CU(c, cudaSetDevice(c->cfg.device));
+    unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
+    flag_signal_kernel<<<1, 1, 0, c->s_render>>>(f + slot, value);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return VX_OK;
+}
+
+int vx_frame_wait(VxCtx* c, uint32_t first_slot, uint32_t n_slots, uint32_t value) {
+    if (!c || n_slots == 0 || n_slots > 32 || first_slot + n_slots > 63) return fail(c, VX_E_ARG, "vx_frame_wait: bad slot range");
+    CU(c, cudaSetDevice(c->cfg.device));
+    unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
+    flag_wait_kernel<<<1, 32, 0, c->s_render>>>(f, first_slot, n_slots, value, c->d_flags + 63);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return VX_OK;
+}
+
+int vx_frame_gate(VxCtx* c, uint32_t slot, uint32_t value) {
+    if (!c || slot >= 63) return fail(c, VX_E_ARG, "vx_frame_gate: bad slot");
+    c->gate_armed = true; c->gate_slot = slot; c->gate_value = value;
+    return VX_OK;
+}
+
+int vx_frame_sync_errors(VxCtx* c, uint32_t* out) {
+    if (!c || !out) return VX_E_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_render));
+    CU(c, cudaMemcpy(out, c->d_flags + 63, 4, cudaMemcpyDeviceToHost));
     return VX_OK;
 }
 

@@ -81,7 +81,16 @@ def apply_packed_host(world_buffer, packed, n_ranges):
 
 
 class ShardedFrame:
-    """One rank's side of the sharded frame. `dist` is torch.distributed (already initialised) or None for world_size 1."""
+    """One rank's side of the sharded frame. `dist` is torch.distributed (already initialised) or None for world_size 1.
+
+    Frame protocol, gather="p2p" (flags are 32-bit frame counters in GPU 0's memory, mapped by every rank, slot r = rank r is
+    done with the frame, slot 0 = GPU 0 released the frame to be overwritten):
+        every rank   apply_dirty (scatter kernel) -> trace primary rays -> [rank != 0: wait flag 0 >= frame-1] -> shade / shadow
+                     (pixels stored into GPU 0's framebuffer) -> [rank != 0: signal flag rank = frame]
+        rank 0       wait flags 1..n-1 >= frame -> consumer reads the frame -> release(): signal flag 0 = frame
+    The dirty ranges of the NEXT frame travel meanwhile: prefetch_dirty() runs the NCCL broadcast on a side stream into one
+    of two staging buffers, so it overlaps the current frame instead of sitting in front of the next one.
+    """
 
     def __init__(self, engine, rank, world_size, dist=None, torch=None, device=None, gather="p2p"):
         self.engine, self.rank, self.world_size, self.dist, self.torch, self.device = engine, rank, world_size, dist, torch, device
@@ -89,24 +98,33 @@ class ShardedFrame:
         self.shard = (rank, world_size)
         self.width = self.height = 0
         self._peer_open = False
-        self._flag = None
-        self._frame_open = False   # a collective since the last finish() already ordered this frame after rank 0's readers
+        self.frame_no = 0
+        self._cuda = device is not None and getattr(device, "type", "cpu") == "cuda"
+        self._staged = []      # FIFO of (buffer index, n_ranges, payload, used, depth) broadcast but not yet applied
+        self._next_buf = 0
 
     # ---- setup -----------------------------------------------------------------------------------------------------------
     def configure(self, width, height, max_dirty_bytes):
-        """Collective. Sizes the staging buffers; in p2p mode exchanges GPU 0's framebuffer handle and maps it."""
+        """Collective. Sizes the staging buffers; in p2p mode exchanges GPU 0's framebuffer + flag handles and maps them."""
         t = self.torch
         self.width, self.height = width, height
         self.tiles = TileShards(width, height, self.world_size)
         if self.world_size == 1:
             return
-        self.packed_dirty = t.empty(max_dirty_bytes, dtype=t.uint8, device=self.device)
-        self._flag = t.zeros(1, dtype=t.int32, device=self.device)
+        self.dirty_bufs = [t.empty(max_dirty_bytes, dtype=t.uint8, device=self.device) for _ in range(2)]
+        self.packed_dirty = self.dirty_bufs[0]
+        if self._cuda:
+            self.side = t.cuda.Stream(device=self.device)
+            self.ev_staged = [t.cuda.Event() for _ in range(2)]     # broadcast into buffer k finished
+            self.ev_applied = [t.cuda.Event() for _ in range(2)]    # scatter out of buffer k finished
+            for e in self.ev_applied:
+                e.record(t.cuda.current_stream(self.device))
         if self.gather == "p2p":
-            box = [self.engine.frame_ipc_handle() if self.rank == 0 else None]
+            box = [(self.engine.frame_ipc_handle(), self.engine.sync_ipc_handle()) if self.rank == 0 else None]
             self.dist.broadcast_object_list(box, src=0)
             if self.rank != 0:
-                self.engine.open_peer_frame(box[0])
+                self.engine.open_peer_frame(box[0][0])
+                self.engine.open_peer_sync(box[0][1])
                 self._peer_open = True
         else:
             self.my_pack = t.empty(self.tiles.shard_bytes(self.rank), dtype=t.uint8, device=self.device)
@@ -116,39 +134,67 @@ class ShardedFrame:
     def close(self):
         if self._peer_open:
             self.engine.close_peer_frame()
+            self.engine.close_peer_sync()
             self._peer_open = False
 
     # ---- per frame -------------------------------------------------------------------------------------------------------
-    def broadcast_dirty(self, n_ranges, payload_bytes, used_bytes, depth, packed_host=None):
-        """Collective. Rank 0's packed dirty set (already in self.packed_dirty, or given as a pinned host tensor) -> every
-        replica, applied by the scatter kernel on the render stream's upload side."""
+    def prefetch_dirty(self, n_ranges, payload_bytes, used_bytes, depth, packed_host=None):
+        """Collective. Starts moving rank 0's packed dirty set (a pinned host tensor, or already in self.dirty_bufs[next]) to
+        every replica: NCCL broadcast on the side stream into the next staging buffer. apply_dirty() consumes it."""
         if self.world_size == 1:
             return
+        t = self.torch
+        k = self._next_buf
+        self._next_buf ^= 1
         total = 16 * n_ranges + payload_bytes
-        buf = self.packed_dirty[:total]
-        if self.rank == 0 and packed_host is not None:
-            buf.copy_(packed_host[:total], non_blocking=True)
-        self.dist.broadcast(buf, src=0)
-        self._frame_open = True
-        self.engine.commit_packed_device(buf.data_ptr(), n_ranges, payload_bytes, used_bytes, depth)
+        buf = self.dirty_bufs[k][:total]
+        if self._cuda:
+            self.side.wait_event(self.ev_applied[k])          # the scatter that last read this buffer is done
+            with t.cuda.stream(self.side):
+                if self.rank == 0 and packed_host is not None:
+                    buf.copy_(packed_host[:total], non_blocking=True)
+                self.dist.broadcast(buf, src=0)
+                self.ev_staged[k].record(self.side)
+        else:
+            if self.rank == 0 and packed_host is not None:
+                buf.copy_(packed_host[:total])
+            self.dist.broadcast(buf, src=0)
+        self._staged.append((k, n_ranges, payload_bytes, used_bytes, depth))
+
+    def apply_dirty(self):
+        """Applies the oldest prefetched dirty set to this rank's replica (scatter kernel, stream-ordered before the frame)."""
+        if self.world_size == 1 or not self._staged:
+            return
+        k, n_ranges, payload_bytes, used_bytes, depth = self._staged.pop(0)
+        if self._cuda:
+            cur = self.torch.cuda.current_stream(self.device)
+            cur.wait_event(self.ev_staged[k])
+        self.engine.commit_packed_device(self.dirty_bufs[k].data_ptr(), n_ranges, payload_bytes, used_bytes, depth)
+        if self._cuda:
+            self.ev_applied[k].record(cur)
+
+    def broadcast_dirty(self, n_ranges, payload_bytes, used_bytes, depth, packed_host=None):
+        """Collective. prefetch_dirty + apply_dirty back to back (no overlap with the previous frame)."""
+        self.prefetch_dirty(n_ranges, payload_bytes, used_bytes, depth, packed_host=packed_host)
+        self.apply_dirty()
 
     def render(self, vx_params):
-        """This rank's tiles. In p2p mode the pixels land in GPU 0's framebuffer as they are finished, so the frame may only
-        start once rank 0 is done reading the previous one: the dirty-range broadcast (root = rank 0) orders that; a frame
-        without one takes a 4-byte all-reduce instead."""
-        if self.gather == "p2p" and not self._frame_open:
-            self.dist.all_reduce(self._flag)
-        self._frame_open = False
+        """This rank's tiles. In p2p mode the pixels land in GPU 0's framebuffer as they are finished; shading is gated on
+        GPU 0 having released the previous frame (its primary rays are traced meanwhile)."""
+        self.frame_no += 1
+        if self.gather == "p2p" and self.rank != 0:
+            self.engine.frame_gate(0, self.frame_no - 1)
         self.engine.render_raw(vx_params, self.width, self.height, shard=self.shard)
 
     def finish(self):
-        """Collective. After it returns (stream-ordered), GPU 0's framebuffer holds the whole frame."""
+        """After it returns (stream-ordered), GPU 0's framebuffer holds the whole frame. Collective only in nccl mode."""
         if self.world_size == 1:
             return
         if self.gather == "p2p":
-            # the stores were issued by the render kernels themselves; one 4-byte all-reduce orders every rank's render
-            # stream before rank 0 reads the frame
-            self.dist.all_reduce(self._flag)
+            if self.rank != 0:
+                self.engine.frame_signal(self.rank, self.frame_no)
+            else:
+                self.engine.frame_wait(1, self.world_size - 1, self.frame_no)
             return
         self.engine.pack_shard(self.shard, self.my_pack.data_ptr())
         if self.rank == 0:
@@ -160,3 +206,8 @@ class ShardedFrame:
         if self.rank == 0:
             for r in range(1, self.world_size):
                 self.engine.unpack_shard((r, self.world_size), self.recv[r].data_ptr())
+
+    def release(self):
+        """Rank 0, after everything that reads the gathered frame has been enqueued: lets the other ranks overwrite it."""
+        if self.gather == "p2p" and self.rank == 0:
+            self.engine.frame_signal(0, self.frame_no)

@@ -145,7 +145,7 @@ def cpu_sample_bands(height, frac=0.1, bands=27):
 
 def cpu_render_sample(scene, vxp, args, threads, budget_s, frac=0.1):
     """Times the CPU oracle on row bands of the SAME frame until the budget is used. Returns (rays/s, description)."""
-    bands = cpu_sample_bands(args.height, frac)
+    bands = cpu_sample_bands(args.height, frac) if frac < 1.0 else [(0, args.height)]   # whole frame: one call, no per-band overhead
     out = np.zeros((args.height, args.width, 4), np.float32)
     rays, t_used, rows = 0, 0.0, 0
     t_start = time.time()
@@ -172,12 +172,16 @@ def run_reference(args):
     scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
     vxp = frame_params(pkg, world, args)
     threads = ora.max_threads()
-    per_step_budget = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_render_sample(scene, vxp, args, threads, per_step_budget)
+    # one step = the whole frame on all host threads (about a third of a second at 4K on 16 threads); if the box is so slow
+    # that K+W frames would take more than ~3 minutes, fall back to a 10 % row sample per step
+    t0 = time.time()
+    cpu_render_sample(scene, vxp, args, threads, 1e9, frac=1.0)
+    frac = 1.0 if (time.time() - t0) * (args.steps + args.warmup) < 180.0 else 0.1
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_render_sample(scene, vxp, args, threads, 1e9, frac=frac)
     tot_rays, tot_t, desc = 0, 0.0, ""
     for _ in range(args.steps):
-        _, desc, rays, t = cpu_render_sample(scene, vxp, args, threads, per_step_budget)
+        _, desc, rays, t = cpu_render_sample(scene, vxp, args, threads, 1e9, frac=frac)
         tot_rays += rays; tot_t += t
     value = tot_rays / tot_t / 1e6
     full_frame_rays = None

@@ -38,8 +38,10 @@ struct RenderArgs {
     uint32_t macro_x, macro_y;    // frame size in 32x16-pixel macro blocks
     uint32_t macro0, n_macros;    // this launch covers macro blocks [macro0, macro0 + n_macros) (a band of macro rows, or the frame)
     uint32_t first_owned;         // first macro block >= macro0 owned by this shard
+    uint32_t n_owned;             // macro blocks of [macro0, macro0 + n_macros) owned by this shard
     uint32_t shard_rank, shard_size;
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
+    uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
 };
 
 // Work units. The frame is cut into macro blocks of 32x16 pixels (row-major over the frame; a shard owns every
@@ -140,14 +142,17 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
     const float inv_scale = 1.0f / octree_scale;
-    const uint32_t n_strips = a.n_macros * 4u;
     float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
     // warp-uniform work state: the unit of work fetch is one warp tile (8x4 pixels = 32 rays, a quarter of a strip), so that a
     // shard of a frame (1/8 of 4K = 32 k tiles over 4.7 k resident warps) still load-balances
+    // Only the macro blocks this shard owns are enumerated (work index w -> owned macro block w / 16): a shard of 1/8 of
+    // the frame performs 1/8 of the work-counter atomics (enumerating all tiles and skipping 7 of 8 made the single
+    // counter the bottleneck of the sharded kernel, profiles/r01_scaling_before_owned_tiles.jsonl).
     uint32_t tile = 0, strip_x0 = 0, strip_y0 = 0, next_px = 32, tile_px0 = 0;
-    const uint32_t n_tiles = n_strips * 4u;
+    uint32_t work = 0, work_end = 0;   // claimed run of work indices [work, work_end): a.fetch_tiles per atomicAdd
+    const uint32_t n_tiles = a.n_owned * 16u;
     bool more_work = true;
     uint32_t slot = 0, last_leaf = 0xffffffffu;
     Walk w;
@@ -158,10 +163,14 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         unsigned want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         while (want && more_work) {
             if (next_px >= 32) {
-                if (lane == 0) tile = atomicAdd(a.work_counter, 1u);
-                tile = __shfl_sync(0xffffffffu, tile, 0);
-                if (tile >= n_tiles) { more_work = false; break; }
-                tile += a.macro0 * 16u;
+                if (work >= work_end) {
+                    if (lane == 0) work = atomicAdd(a.work_counter, a.fetch_tiles);
+                    work = __shfl_sync(0xffffffffu, work, 0);
+                    work_end = min(work + a.fetch_tiles, n_tiles);
+                    if (work >= n_tiles) { more_work = false; break; }
+                }
+                tile = work++;
+                tile = (a.first_owned + (tile >> 4) * a.shard_size) * 16u + (tile & 15u);
                 if (!strip_origin(a, tile >> 2, strip_x0, strip_y0)) continue;
                 tile_px0 = (tile & 3u) * 32u;
                 next_px = 0;

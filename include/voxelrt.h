@@ -48,6 +48,10 @@ typedef struct VxCtx VxCtx;
 
 /* flags for VxConfig.flags */
 #define VX_FLAG_NO_L2_WINDOW   (1u << 0)  /* do not install the persisting-L2 access-policy window */
+#define VX_FLAG_SVO_CSVO       (1u << 2)  /* the world buffer holds the CSVO format (world::hds::csvo, the reference's default
+                                             feature `use-csvo`, Cargo.toml:39-45) instead of ESVO: = the SvoType argument of
+                                             graphics::Svo::new (svo.rs:109). Buffer = f32 2^-depth, u32 root offset, bytes
+                                             (svo.csvo.glsl:1-5); dirty ranges live at byte 8 + offset */
 
 typedef struct VxConfig {
     int32_t  device;              /* CUDA device ordinal this context owns */

@@ -95,6 +95,8 @@ RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "for
                          "offsets": [0, 4, 16, 32], "itemsize": 48})
 
 VX_FLAG_NO_L2_WINDOW = 1
+VX_FLAG_SVO_CSVO = 4
+FORMAT_ESVO, FORMAT_CSVO = 0, 1
 OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER = 3, 4, 5, 6, 7
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
@@ -187,6 +189,9 @@ def host():
         "vxh_last_error": ([], C.c_char_p),
         "vxh_world_new": ([u32, i32, i32, i32, u32, C.c_int], P),
         "vxh_world_free": ([P], None),
+        "vxh_world_set_format": ([P, C.c_int], None),
+        "vxh_world_format": ([P], C.c_int),
+        "vxh_world_header_bytes": ([P], u64),
         "vxh_world_generate": ([P, i32, i32, C.c_int], u64),
         "vxh_world_height_at": ([P, i32, i32], i32),
         "vxh_world_chunk_count": ([P], u64),
@@ -207,6 +212,10 @@ def host():
         "vxh_world_cnv_chunk_pos": ([P, i32, i32, i32, P], C.c_int),
         "vxh_calculate_lod": ([i32, i32, i32, i32, i32, i32], C.c_uint8),
         "vxh_kat_block_octree": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P], u64),
+        "vxh_kat_csvo_octant": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P, u32, C.POINTER(u32)], u64),
+        "vxh_csvo_dense_equals_generic": ([P, C.c_uint8], C.c_int),
+        "vxh_world_csvo_root_offset": ([P], u64),
+        "vxh_world_range_bytes": ([P, P, u64], u64),
         "vxh_serialize_dense": ([P, C.c_uint8, P, u64, P], u64),
         "vxh_serialize_filled": ([P, C.c_uint8, P, u64, P], u64),
         "vxh_esvo32_new": ([], P), "vxh_esvo32_free": ([P], None),
@@ -267,9 +276,20 @@ class VxError(RuntimeError):
 class World:
     """systems::worldsvo::Svo's CPU half: Esvo of SerializedChunks + SVO coordinate space (+ synthetic terrain)."""
 
-    def __init__(self, radius=0, center=(0, 0, 0), seed=1, no_lod=False):
+    def __init__(self, radius=0, center=(0, 0, 0), seed=1, no_lod=False, fmt=FORMAT_ESVO):
         self.h = host().vxh_world_new(radius, center[0], center[1], center[2], seed, int(no_lod))
-        self.radius, self.center = radius, tuple(center)
+        self.radius, self.center, self.fmt = radius, tuple(center), fmt
+        host().vxh_world_set_format(self.h, fmt)
+
+    @property
+    def header_bytes(self):
+        """Bytes in front of the RangeBuffer image inside the GPU buffer (24 ESVO, 8 CSVO)."""
+        return host().vxh_world_header_bytes(self.h)
+
+    @property
+    def svo_flags(self):
+        """VxConfig.flags bits a graphics::Svo for this world needs."""
+        return VX_FLAG_SVO_CSVO if self.fmt == FORMAT_CSVO else 0
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -336,10 +356,11 @@ class World:
 
     def gpu_buffer(self):
         """Bytes exactly as graphics::Svo::update lays them out: f32 2^-depth, preamble, RangeBuffer (svo.rs:173-181)."""
-        buf = np.zeros(4 + 20 + self.size_bytes, dtype=np.uint8)
+        hb = self.header_bytes
+        buf = np.zeros(hb + self.size_bytes + (4 if self.fmt == FORMAT_CSVO else 0), dtype=np.uint8)   # CSVO: one spare word for read_uint at the end
         buf[:4] = np.frombuffer(np.float32(2.0 ** -self.depth).tobytes(), dtype=np.uint8)
         n = host().vxh_world_write_to(self.h, C.c_void_p(buf.ctypes.data + 4))
-        assert n == 20 + self.size_bytes or n == 0
+        assert n == hb - 4 + self.size_bytes or n == 0
         return buf
 
     def cnv_block_pos(self, p):

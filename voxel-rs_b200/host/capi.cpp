@@ -28,6 +28,9 @@ void* vxh_world_new(uint32_t radius, int32_t cx, int32_t cy, int32_t cz, uint32_
     w->terrain.seed = seed; w->no_lod = no_lod != 0;
     return w;
 }
+// SVO_TYPE of the world (0 = ESVO, 1 = CSVO); must be chosen before the first chunk is set.
+void vxh_world_set_format(void* w, int format) { ((WorldSvo*)w)->format = format ? SvoFormat::Csvo : SvoFormat::Esvo; }
+int vxh_world_format(void* w) { return (int)((WorldSvo*)w)->format; }
 void vxh_world_free(void* w) { delete (WorldSvo*)w; }
 uint64_t vxh_world_generate(void* w, int32_t y0, int32_t y1, int threads) { return ((WorldSvo*)w)->generate(y0, y1, threads); }
 int32_t vxh_world_height_at(void* w, int32_t x, int32_t z) { return ((WorldSvo*)w)->terrain.height_at(x, z); }
@@ -48,7 +51,8 @@ int vxh_world_set_leaf_blocks(void* wp, uint32_t sx, uint32_t sy, uint32_t sz, u
         else storage.set_leaf(Position{e[0], e[1], e[2]}, e[3]);
     }
     if (compact) storage.compact();
-    w->esvo.set_leaf(Position{sx, sy, sz}, SerializedChunk::from_octree(0, 0, 0, uid, storage, lod), true);
+    if (w->format == SvoFormat::Csvo) w->csvo.set_leaf(Position{sx, sy, sz}, CsvoChunk::from_octree(uid, storage, lod), true);
+    else w->esvo.set_leaf(Position{sx, sy, sz}, SerializedChunk::from_octree(0, 0, 0, uid, storage, lod), true);
     return 0;
     VXH_CATCH(-1)
 }
@@ -57,7 +61,8 @@ int vxh_world_set_leaf_blocks(void* wp, uint32_t sx, uint32_t sy, uint32_t sz, u
 int vxh_world_set_leaf_dense(void* wp, uint32_t sx, uint32_t sy, uint32_t sz, uint64_t uid, const uint32_t* blocks, uint8_t lod) {
     VXH_TRY
     WorldSvo* w = (WorldSvo*)wp;
-    w->esvo.set_leaf(Position{sx, sy, sz}, SerializedChunk::from_dense(0, 0, 0, uid, blocks, lod), true);
+    if (w->format == SvoFormat::Csvo) w->csvo.set_leaf(Position{sx, sy, sz}, CsvoChunk::from_dense(uid, blocks, lod), true);
+    else w->esvo.set_leaf(Position{sx, sy, sz}, SerializedChunk::from_dense(0, 0, 0, uid, blocks, lod), true);
     return 0;
     VXH_CATCH(-1)
 }
@@ -73,27 +78,28 @@ int vxh_world_edit_block(void* wp, int32_t wx, int32_t wy, int32_t wz, uint32_t 
     VXH_CATCH(-1)
 }
 
-void vxh_world_serialize(void* w) { ((WorldSvo*)w)->esvo.serialize(); }
-uint32_t vxh_world_depth(void* w) { return ((WorldSvo*)w)->esvo.depth(); }
-uint64_t vxh_world_size_bytes(void* w) { return ((WorldSvo*)w)->esvo.size_in_bytes(); }
-uint64_t vxh_world_write_to(void* w, uint8_t* dst) { return ((WorldSvo*)w)->esvo.write_to(dst); }
+void vxh_world_serialize(void* w) { ((WorldSvo*)w)->serialize(); }
+uint32_t vxh_world_depth(void* w) { return ((WorldSvo*)w)->depth(); }
+uint64_t vxh_world_size_bytes(void* w) { return ((WorldSvo*)w)->size_in_bytes(); }
+uint64_t vxh_world_header_bytes(void* w) { return ((WorldSvo*)w)->header_bytes(); }
+uint64_t vxh_world_write_to(void* w, uint8_t* dst) { return ((WorldSvo*)w)->write_to(dst); }
 int vxh_world_write_changes_to(void* w, uint8_t* dst, uint64_t dst_len, int reset) {
-    return ((WorldSvo*)w)->esvo.write_changes_to(dst, dst_len, reset != 0) ? 0 : -1;
+    return ((WorldSvo*)w)->write_changes_to(dst, dst_len, reset != 0) ? 0 : -1;
 }
 uint32_t vxh_world_dirty_ranges(void* w, VxRange* out, uint32_t cap) {
-    auto& rs = ((WorldSvo*)w)->esvo.buffer.updated_ranges;
+    auto& rs = ((WorldSvo*)w)->range_buffer().updated_ranges;
     for (uint32_t i = 0; i < rs.size() && i < cap; ++i) out[i] = VxRange{rs[i].start, rs[i].length};
     return (uint32_t)rs.size();
 }
 // Marks the whole RangeBuffer dirty so that the next write_changes_to / Svo::update re-uploads everything (a fresh
 // graphics::Svo attached to an already serialized world; the reference never re-attaches, it owns one GL buffer).
 void vxh_world_mark_all_dirty(void* w) {
-    auto& b = ((WorldSvo*)w)->esvo.buffer;
+    auto& b = ((WorldSvo*)w)->range_buffer();
     b.updated_ranges.clear();
     if (!b.bytes.empty()) b.updated_ranges.push_back(Range{0, b.bytes.size()});
 }
 void vxh_world_root_range(void* w, uint64_t* off, uint64_t* len) {
-    Range r = ((WorldSvo*)w)->esvo.root_range();
+    Range r = ((WorldSvo*)w)->root_range();
     *off = r.start; *len = r.length;
 }
 void vxh_world_root_info(void* w, uint64_t* buf_offset, uint8_t masks_depth[3]) {
@@ -135,6 +141,42 @@ uint64_t vxh_kat_block_octree(const uint32_t* xyzid, uint32_t n, uint8_t expand_
     result[0] = r.child_mask; result[1] = r.leaf_mask; result[2] = r.depth;
     for (uint64_t i = 0; i < dst.size() && i < cap; ++i) out[i] = dst[i];
     return dst.size();
+}
+
+// CSVO: Octree<BlockId> built the same way, SerializedChunk::serialize_octant(root, tree.depth() - depth_minus, 0, materials)
+// (csvo.rs:592-712). Returns node bytes written (or needed); *n_materials receives the material count.
+uint64_t vxh_kat_csvo_octant(const uint32_t* xyzid, uint32_t n, uint8_t expand_to, int compact, uint8_t depth_minus, uint8_t* out, uint64_t cap,
+                             uint32_t* materials, uint32_t materials_cap, uint32_t* n_materials) {
+    Octree<BlockId> t;
+    for (uint32_t i = 0; i < n; ++i) t.set_leaf(Position{xyzid[4 * i], xyzid[4 * i + 1], xyzid[4 * i + 2]}, xyzid[4 * i + 3]);
+    t.expand_to(expand_to);
+    if (compact) t.compact();
+    std::vector<BlockId> mats;
+    if (!t.root) { *n_materials = 0; return 0; }
+    const uint32_t root = *t.root;
+    std::vector<uint8_t> dst = csvo_serialize_octant(t, root, (uint8_t)(t.depth() - depth_minus), 0, mats);
+    for (uint64_t i = 0; i < dst.size() && i < cap; ++i) out[i] = dst[i];
+    for (uint32_t i = 0; i < mats.size() && i < materials_cap; ++i) materials[i] = mats[i];
+    *n_materials = (uint32_t)mats.size();
+    return dst.size();
+}
+// CSVO dense fast path vs Chunk::fill_with + generic serializer on the same 32^3 array: returns 1 when nodes and materials agree
+int vxh_csvo_dense_equals_generic(const uint32_t* blocks, uint8_t lod) {
+    Octree<BlockId> t;
+    t.construct_octants_with(5, [blocks](Position p) -> std::optional<BlockId> {
+        BlockId b = blocks[(size_t)p.x + 32 * ((size_t)p.y + 32 * (size_t)p.z)];
+        if (b == 0) return std::nullopt;
+        return b;
+    });
+    CsvoChunk a = CsvoChunk::from_octree(1, t, lod), b = CsvoChunk::from_dense(1, blocks, lod);
+    return a.has_buffer == b.has_buffer && a.lod == b.lod && a.buffer == b.buffer && a.materials == b.materials;
+}
+// RangeBuffer image + root offset of the world's Csvo (csvo.rs:330-391)
+uint64_t vxh_world_csvo_root_offset(void* w) { auto& r = ((WorldSvo*)w)->csvo.root_info; return r ? (uint64_t)*r : ~0ull; }
+uint64_t vxh_world_range_bytes(void* w, uint8_t* out, uint64_t cap) {
+    auto& b = ((WorldSvo*)w)->range_buffer().bytes;
+    for (uint64_t i = 0; i < b.size() && i < cap; ++i) out[i] = b[i];
+    return b.size();
 }
 
 // dense fast path vs Chunk::fill_with + generic serializer on the same 32^3 array
@@ -322,7 +364,8 @@ void vxh_svo_free(void* s) { delete (Svo*)s; }
 void* vxh_svo_ctx(void* s) { return ((Svo*)s)->ctx(); }
 int vxh_svo_update(void* s, void* world) {
     VXH_TRY
-    ((Svo*)s)->update(((WorldSvo*)world)->esvo);
+    WorldSvo* w = (WorldSvo*)world;
+    if (w->format == SvoFormat::Csvo) ((Svo*)s)->update(w->csvo); else ((Svo*)s)->update(w->esvo);
     return 0;
     VXH_CATCH(-1)
 }

@@ -1,4 +1,5 @@
-// esvo.cpp — dense-chunk fast path of the ESVO serializer (see esvo.hpp).
+// esvo.cpp — dense-chunk fast paths of the ESVO and CSVO serializers (see esvo.hpp, csvo.hpp).
+#include "csvo.hpp"
 #include "esvo.hpp"
 
 namespace vxh {
@@ -75,7 +76,54 @@ struct DenseChunk {
     }
 };
 
+// csvo.rs:434-535 for the octant of edge 2^k at cell (x,y,z) with `depth` levels left to serialize.
+static std::vector<uint8_t> csvo_ser(const DenseChunk& c, uint32_t k, uint32_t x, uint32_t y, uint32_t z, uint8_t depth, uint16_t material_offset,
+                                     std::vector<BlockId>& materials) {
+    std::vector<uint8_t> buffer;
+    if (depth == 1) {
+        uint8_t leaf_mask = 0;
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            uint32_t cx = 2 * x + (idx & 1), cy = 2 * y + ((idx >> 1) & 1), cz = 2 * z + ((idx >> 2) & 1);
+            if (!c.occupied(k - 1, cx, cy, cz)) continue;
+            materials.push_back(k == 1 ? c.at(cx, cy, cz) : c.pick(k - 1, cx, cy, cz));
+            leaf_mask |= (uint8_t)(1u << idx);
+        }
+        buffer.push_back(leaf_mask);
+        return buffer;
+    }
+    std::vector<std::pair<uint8_t, std::vector<uint8_t>>> children;
+    for (uint32_t idx = 0; idx < 8; ++idx) {
+        uint32_t cx = 2 * x + (idx & 1), cy = 2 * y + ((idx >> 1) & 1), cz = 2 * z + ((idx >> 2) & 1);
+        if (!c.occupied(k - 1, cx, cy, cz)) continue;
+        children.push_back({(uint8_t)idx, csvo_ser(c, k - 1, cx, cy, cz, (uint8_t)(depth - 1), (uint16_t)materials.size(), materials)});
+    }
+    if (depth == 2) {
+        buffer.push_back(0);
+        if (!children.empty()) { buffer.push_back((uint8_t)material_offset); buffer.push_back((uint8_t)(material_offset >> 8)); }
+        for (auto& ch : children) { buffer[0] |= (uint8_t)(1u << ch.first); buffer.insert(buffer.end(), ch.second.begin(), ch.second.end()); }
+    } else if (depth == 3) {
+        buffer.assign(1 + children.size(), 0);
+        uint8_t running = 0;
+        for (size_t i = 0; i < children.size(); ++i) {
+            buffer[0] |= (uint8_t)(1u << children[i].first);
+            buffer[1 + i] = running;
+            running = (uint8_t)(running + children[i].second.size());
+        }
+        for (auto& ch : children) buffer.insert(buffer.end(), ch.second.begin(), ch.second.end());
+    } else {
+        csvo_emit_internal(buffer, children);
+    }
+    return buffer;
+}
+
 }  // namespace
+
+bool csvo_serialize_dense_chunk(const BlockId* blocks, uint8_t depth, std::vector<uint8_t>& nodes, std::vector<BlockId>& materials) {
+    DenseChunk c(blocks);
+    if (!c.occupied(5, 0, 0, 0)) return false;
+    nodes = csvo_ser(c, 5, 0, 0, 0, depth, 0, materials);
+    return true;
+}
 
 SerializationResult serialize_dense_chunk(const BlockId* blocks, std::vector<uint32_t>& dst, uint8_t lod) {
     DenseChunk c(blocks);

@@ -196,8 +196,10 @@ public:
     // graphics::Svo::update, svo.rs:171-189: octree_scale = 2^-depth at byte 0, wait for the frame in
     // flight, write_changes_to(mirror + 4, len - 1), refresh stats. The dirty list is read BEFORE
     // write_changes_to resets it (the accessor SURVEY §8b asks the Rust shim to add).
-    template <typename T>
-    void update(Esvo<T>& svo) {
+    // W = Esvo<T> or Csvo (the reference's `T: WorldSvo<U>`); the context must have been created with the matching
+    // SVO type (VX_FLAG_SVO_CSVO in `flags` = the reference's SvoType argument of graphics::Svo::new, svo.rs:109).
+    template <typename W>
+    void update(W& svo) {
         VxStats st{};
         vx_stats(ctx_, &st);
         uint8_t* mirror = vx_svo_host_mirror(ctx_);

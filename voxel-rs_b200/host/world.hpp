@@ -21,6 +21,7 @@
 #include <tuple>
 #include <vector>
 
+#include "csvo.hpp"
 #include "esvo.hpp"
 #include "picker.hpp"
 
@@ -160,9 +161,13 @@ struct Terrain {
 
 // The world-level SVO: owns the Esvo of chunks and the world<->SVO mapping (systems::worldsvo::Svo
 // without the job system / GPU handle, worldsvo.rs:48-60,90-151,198-218).
+enum class SvoFormat : int { Esvo = 0, Csvo = 1 };   // the reference's compile-time SVO_TYPE (Cargo features use-esvo / use-csvo)
+
 class WorldSvo {
 public:
+    SvoFormat format = SvoFormat::Esvo;
     Esvo<SerializedChunk> esvo;
+    Csvo csvo;
     SvoCoordSpace space;
     Terrain terrain;
     std::map<std::tuple<int32_t, int32_t, int32_t>, LeafId> leaf_ids;
@@ -212,13 +217,33 @@ public:
         leaf_ids[{p.x, p.y, p.z}] = r.first;
         return true;
     }
+    bool set_chunk(ChunkPos p, CsvoChunk&& cc) {
+        Position sp;
+        if (!space.cnv_chunk_pos(p, sp)) return false;
+        auto r = csvo.set_leaf(sp, std::move(cc), true);
+        leaf_ids[{p.x, p.y, p.z}] = r.first;
+        return true;
+    }
 
     void remove_chunk(ChunkPos p) {   // worldsvo.rs:101-108
         auto it = leaf_ids.find({p.x, p.y, p.z});
         if (it == leaf_ids.end()) return;
-        esvo.remove_leaf(it->second);
+        if (format == SvoFormat::Csvo) csvo.remove_leaf(it->second); else esvo.remove_leaf(it->second);
         leaf_ids.erase(it);
     }
+
+    // format dispatch of the WorldSvo<T> trait surface (src/world/hds/common.rs:3-15)
+    void serialize() { if (format == SvoFormat::Csvo) csvo.serialize(); else esvo.serialize(); }
+    uint8_t depth() const { return format == SvoFormat::Csvo ? csvo.depth() : esvo.depth(); }
+    size_t size_in_bytes() const { return format == SvoFormat::Csvo ? csvo.size_in_bytes() : esvo.size_in_bytes(); }
+    size_t write_to(uint8_t* dst) const { return format == SvoFormat::Csvo ? csvo.write_to(dst) : esvo.write_to(dst); }
+    bool write_changes_to(uint8_t* dst, size_t dst_len, bool reset) {
+        return format == SvoFormat::Csvo ? csvo.write_changes_to(dst, dst_len, reset) : esvo.write_changes_to(dst, dst_len, reset);
+    }
+    RangeBuffer& range_buffer() { return format == SvoFormat::Csvo ? csvo.buffer : esvo.buffer; }
+    Range root_range() const { return format == SvoFormat::Csvo ? csvo.root_range() : esvo.root_range(); }
+    // bytes in front of the RangeBuffer image inside the GPU buffer: f32 scale + 20-byte preamble (ESVO) / + u32 root offset (CSVO)
+    size_t header_bytes() const { return format == SvoFormat::Csvo ? 8 : 24; }
 
     uint8_t lod_for(ChunkPos p) const { return no_lod ? 5 : calculate_lod(space.center, p); }
 
@@ -227,6 +252,7 @@ public:
         std::vector<BlockId> blocks;
         Column col = make_column(p.x, p.z);
         if (!fill_chunk(p, col, blocks)) { remove_chunk(p); return false; }
+        if (format == SvoFormat::Csvo) return set_chunk(p, CsvoChunk::from_dense(chunk_uid(p), blocks.data(), lod_for(p)));
         return set_chunk(p, SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p)));
     }
 
@@ -235,7 +261,7 @@ public:
     // (chunkloader.rs:116-120). Chunk serialisation runs on `threads` workers like the reference's job
     // system (worldsvo.rs:90-99); insertion into the world octree stays on the calling thread.
     size_t generate(int32_t y0, int32_t y1, int threads) {
-        struct Job { ChunkPos p; SerializedChunk sc; bool ok = false; };
+        struct Job { ChunkPos p; SerializedChunk sc; CsvoChunk cc; bool ok = false; };
         std::vector<std::pair<int64_t, std::pair<int32_t, int32_t>>> cols;
         int32_t r = (int32_t)space.dst;
         for (int32_t dz = -r; dz <= r; ++dz)
@@ -259,7 +285,8 @@ public:
                     if (!space.cnv_chunk_pos(p, sp)) continue;
                     if (!fill_chunk(p, col, blocks)) continue;
                     Job j; j.p = p; j.ok = true;
-                    j.sc = SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p));
+                    if (format == SvoFormat::Csvo) j.cc = CsvoChunk::from_dense(chunk_uid(p), blocks.data(), lod_for(p));
+                    else j.sc = SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p));
                     per_col[i].push_back(std::move(j));
                 }
             }
@@ -270,7 +297,8 @@ public:
         size_t loaded = 0;
         for (auto& v : per_col)
             for (auto& j : v)
-                if (j.ok && j.sc.has_data() && set_chunk(j.p, std::move(j.sc))) ++loaded;
+                if (j.ok && (format == SvoFormat::Csvo ? (j.cc.has_data() && set_chunk(j.p, std::move(j.cc)))
+                                                        : (j.sc.has_data() && set_chunk(j.p, std::move(j.sc))))) ++loaded;
         return loaded;
     }
 };

@@ -66,7 +66,7 @@ def lib():
     L.vxo_texture_destroy.argtypes = [P]; L.vxo_texture_destroy.restype = None
     L.vxo_texture_levels.argtypes = [P]; L.vxo_texture_levels.restype = C.c_uint32
     L.vxo_texture_level.argtypes = [P, C.c_uint32, P]; L.vxo_texture_level.restype = C.c_uint64
-    scene = [P, C.c_uint64, P, C.c_uint32, P]
+    scene = [P, C.c_uint64, P, C.c_uint32, P, C.c_int]
     L.vxo_debug_cast.argtypes = scene + [C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), C.c_float, C.c_uint32,
                                          C.POINTER(OctreeResult), C.POINTER(DebugFrame), C.c_uint32, C.POINTER(C.c_uint32)]
     L.vxo_debug_cast.restype = None
@@ -87,8 +87,9 @@ def _ptr(a):
 class Scene:
     """World bytes (GPU-buffer layout) + material table + texture array, held for oracle calls."""
 
-    def __init__(self, world_bytes, materials, textures_level0, mip_levels):
+    def __init__(self, world_bytes, materials, textures_level0, mip_levels, fmt=0):
         """materials: bytes-like of n*32 (VxMaterial records); textures_level0: [layers, h, w, 4] uint8, v-flipped as uploaded."""
+        self.fmt = int(fmt)   # 0 = ESVO, 1 = CSVO (the shader's SVO_TYPE)
         self.world = np.ascontiguousarray(world_bytes, dtype=np.uint8)
         self.materials = np.ascontiguousarray(np.frombuffer(bytes(materials), dtype=np.uint8))
         self.n_materials = len(self.materials) // 32
@@ -103,7 +104,7 @@ class Scene:
             self.tex = None
 
     def _args(self):
-        return (_ptr(self.world), len(self.world), _ptr(self.materials), self.n_materials, self.tex)
+        return (_ptr(self.world), len(self.world), _ptr(self.materials), self.n_materials, self.tex, self.fmt)
 
     def mip_level(self, level):
         n = lib().vxo_texture_level(self.tex, level, None)

@@ -195,8 +195,18 @@ struct Scene {
     const Material* materials;
     uint32_t n_materials;
     const Texture* tex;
+    int format = 0;              // 0 = ESVO (svo.esvo.glsl), 1 = CSVO (svo.csvo.glsl): the shader's `#define SVO_TYPE`
     float octree_scale() const { float f; std::memcpy(&f, world, 4); return f; }
     uint32_t desc(uint32_t i) const { uint32_t v; std::memcpy(&v, world + 4 + (uint64_t)i * 4, 4); return v; }
+    // CSVO: `uint root_ptr` at byte 4, `uint descriptors[]` from byte 8 (svo.csvo.glsl:1-5). A word that does not lie
+    // completely inside the buffer reads as 0 (robust-buffer-access policy shared with the CUDA kernels: out-of-spec
+    // descents — a ray origin inside a voxel — walk through bytes that are not nodes).
+    uint32_t csvo_root_ptr() const { uint32_t v; std::memcpy(&v, world + 4, 4); return v; }
+    uint32_t csvo_word(uint32_t i) const {
+        const uint64_t off = 8 + (uint64_t)i * 4;
+        if (off + 4 > world_len) return 0;
+        uint32_t v; std::memcpy(&v, world + off, 4); return v;
+    }
 };
 
 // svo.esvo.glsl:9-16
@@ -212,9 +222,20 @@ static const float EPSILON = 0.00000011920929f;  // svo.esvo.glsl:24
 
 struct Trace { DebugFrame* frames; uint32_t cap; int32_t stack_ptr; };
 
+static void intersect_octree_csvo(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent, OctreeResult& res, Counters* cnt,
+                                  Trace* trace);
+static void intersect_octree_esvo(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent, OctreeResult& res, Counters* cnt,
+                                  Trace* trace);
+// svo.glsl:65-74: the shader includes one of the two traversals by `#define SVO_TYPE`
+static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent, OctreeResult& res, Counters* cnt,
+                             Trace* trace) {
+    if (s.format == 1) intersect_octree_csvo(s, ro, rd, max_dst, cast_translucent, res, cnt, trace);
+    else intersect_octree_esvo(s, ro, rd, max_dst, cast_translucent, res, cnt, trace);
+}
+
 // svo.esvo.glsl:50-393. `trace` (optional) reproduces OCTREE_RAYTRACE_DEBUG_FN of svo.test.glsl.
-static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent,
-                             OctreeResult& res, Counters* cnt, Trace* trace) {
+static void intersect_octree_esvo(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent,
+                                  OctreeResult& res, Counters* cnt, Trace* trace) {
     const float octree_scale = s.octree_scale();
     uint32_t ptr_stack[MAX_SCALE + 1];
     uint32_t parent_octant_idx_stack[MAX_SCALE + 1];
@@ -397,6 +418,255 @@ static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bo
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ CSVO (svo.csvo.glsl) --
+
+// bitfieldInsert(0u, 0xffffffffu, 0, bits): the low `bits` bits set. GLSL leaves bits < 0 / > 32 undefined; here 0 / all.
+static inline uint32_t low_bits(int bits) { return bits <= 0 ? 0u : (bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u)); }
+
+// svo.csvo.glsl:25-35
+static inline uint32_t csvo_read_uint(const Scene& s, uint32_t ptr) {
+    const uint32_t index = ptr / 4, mod = ptr % 4;
+    const uint32_t lshift = (4 - mod) * 8;
+    const uint32_t mask = low_bits((int)lshift);
+    const uint32_t v0 = (s.csvo_word(index) >> (mod * 8)) & mask;
+    const uint32_t v1 = lshift >= 32 ? 0u : ((s.csvo_word(index + 1) << lshift) & ~mask);   // `x << 32` is undefined in GLSL; & ~mask is 0 then
+    return v0 | v1;
+}
+static inline uint32_t csvo_read_ushort(const Scene& s, uint32_t ptr) { return csvo_read_uint(s, ptr) & 0xffffu; }   // :39-42
+static inline uint32_t csvo_read_byte(const Scene& s, uint32_t ptr) { return (s.csvo_word(ptr / 4) >> ((ptr % 4) * 8)) & 0xffu; }   // :45-49
+
+static const uint32_t INVALID_PTR = 0xffffffffu;
+
+// svo.csvo.glsl:53-133
+static uint32_t csvo_read_next_ptr(const Scene& s, uint32_t ptr, uint32_t depth, uint32_t idx, bool& crossed_boundary) {
+    crossed_boundary = false;
+    if (depth > 3) {                                                    // internal nodes
+        const uint32_t header_mask = csvo_read_ushort(s, ptr);
+        const uint32_t child_mask = (header_mask >> (idx * 2)) & 3u;
+        if (child_mask == 0) return INVALID_PTR;
+        const uint32_t offset_mask = (1u << (idx * 2)) - 1u;
+        const uint32_t preceding_mask = header_mask & offset_mask;
+        uint32_t offset = 0, ptr_bytes = 0;
+        for (int k = 0; k < 8; ++k) {
+            offset += (1u << ((preceding_mask >> (k * 2)) & 3u)) >> 1;
+            ptr_bytes += (1u << ((header_mask >> (k * 2)) & 3u)) >> 1;
+        }
+        uint32_t ptr_offset = csvo_read_uint(s, ptr + 2 + offset);
+        ptr_offset &= low_bits((int)(1u << (child_mask - 1)) * 8);      // keep the pointer's own 1 / 2 / 4 bytes
+        if ((ptr_offset & (1u << 31)) != 0) {                           // absolute pointer (32-bit pointers only)
+            crossed_boundary = true;
+            return ptr_offset ^ (1u << 31);
+        }
+        return ptr + 2 + ptr_bytes + ptr_offset;
+    }
+    const uint32_t header_mask = csvo_read_byte(s, ptr);
+    const uint32_t child_mask = (header_mask >> idx) & 1u;
+    if (child_mask == 0) return INVALID_PTR;
+    const uint32_t offset = (uint32_t)__builtin_popcount(header_mask & ((1u << idx) - 1u));
+    if (depth == 3) {                                                   // pre-leaf nodes
+        const uint32_t ptr_bytes = (uint32_t)__builtin_popcount(header_mask);
+        const uint32_t ptr_offset = csvo_read_byte(s, ptr + 1 + offset);
+        return ptr + 1 + ptr_bytes + ptr_offset;
+    }
+    return ptr + 1 + 2 + offset;                                        // leaf nodes: 1-byte mask + 2-byte material offset
+}
+
+// svo.csvo.glsl:136-150
+static uint32_t csvo_read_leaf(const Scene& s, uint32_t material_section_ptr, uint32_t pre_leaf_ptr, uint32_t ptr, uint32_t idx) {
+    const uint32_t material_section_offset = csvo_read_ushort(s, pre_leaf_ptr + 1);
+    const int leaf_index = (int)(ptr - (pre_leaf_ptr + 3));
+    const int bit_mark = leaf_index * 8 + (int)idx;
+    const uint32_t v0 = csvo_read_uint(s, pre_leaf_ptr + 3) & low_bits(bit_mark < 32 ? bit_mark : 32);
+    const uint32_t v1 = csvo_read_uint(s, pre_leaf_ptr + 3 + 4) & low_bits(bit_mark - 32 > 0 ? bit_mark - 32 : 0);
+    const uint32_t preceding_leaves = (uint32_t)(__builtin_popcount(v0) + __builtin_popcount(v1));
+    return csvo_read_uint(s, material_section_ptr + material_section_offset * 4 + preceding_leaves * 4);
+}
+
+// svo.csvo.glsl:171-509. Same ray marching as the ESVO variant; node decode, the (ptr, depth) state, the per-chunk material
+// section and the absolute-pointer crossing differ. The debug frame carries `depth` in parent_octant_idx (svo.csvo.glsl:246).
+// Stack slots: the shader indexes three 24-entry arrays with `scale`; an out-of-spec descent (origin inside a voxel keeps
+// PUSHing through bytes that are not nodes) can leave that range, which GLSL leaves undefined. Policy shared with the CUDA
+// kernel: slot = min(22 - scale, levels - 1) with levels = depth + 3.
+static void intersect_octree_csvo(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent, OctreeResult& res, Counters* cnt,
+                                  Trace* trace) {
+    const float octree_scale = s.octree_scale();
+    uint32_t ptr_stack[MAX_SCALE + 1], depth_stack[MAX_SCALE + 1];
+    float t_max_stack[MAX_SCALE + 1];
+    for (int i = 0; i <= MAX_SCALE; ++i) { ptr_stack[i] = 0; depth_stack[i] = 0; t_max_stack[i] = 0; }
+
+    ro.x *= octree_scale; ro.y *= octree_scale; ro.z *= octree_scale;   // :173
+    max_dst *= octree_scale;                                            // :174
+    res.t = -1; res.value = 0; res.face_id = 0;                         // :177-183
+    res.pos[0] = res.pos[1] = res.pos[2] = 0; res.uv[0] = res.uv[1] = 0;
+    res.color[0] = res.color[1] = res.color[2] = res.color[3] = 0; res.lod = 0; res.inside_voxel = 0;
+    ro.x += 1; ro.y += 1; ro.z += 1;                                    // :187
+
+    uint32_t ptr = s.csvo_root_ptr();                                   // :190
+    int scale = MAX_SCALE - 1;                                          // :195
+    float scale_exp2 = 0.5f;
+    uint32_t last_leaf_value = 0xffffffffu;                             // :201-202
+    int adjacent_leaf_count = 0;
+
+    const int32_t sign_mask = (int32_t)0x80000000u;                     // :206-210
+    const int32_t eps_bits = f2i(EPSILON) & ~sign_mask;
+    if (fabsf(rd.x) < EPSILON) rd.x = i2f(eps_bits | (f2i(rd.x) & sign_mask));
+    if (fabsf(rd.y) < EPSILON) rd.y = i2f(eps_bits | (f2i(rd.y) & sign_mask));
+    if (fabsf(rd.z) < EPSILON) rd.z = i2f(eps_bits | (f2i(rd.z) & sign_mask));
+
+    vec3 t_coef = v3(1.0f / -fabsf(rd.x), 1.0f / -fabsf(rd.y), 1.0f / -fabsf(rd.z));   // :226
+    vec3 t_bias = v3(t_coef.x * ro.x, t_coef.y * ro.y, t_coef.z * ro.z);
+    int octant_mask = 0;                                                // :242-245
+    if (rd.x > 0) { octant_mask ^= 1; t_bias.x = 3.0f * t_coef.x - t_bias.x; }
+    if (rd.y > 0) { octant_mask ^= 2; t_bias.y = 3.0f * t_coef.y - t_bias.y; }
+    if (rd.z > 0) { octant_mask ^= 4; t_bias.z = 3.0f * t_coef.z - t_bias.z; }
+    float t_min = gl_max(gl_max(2.0f * t_coef.x - t_bias.x, 2.0f * t_coef.y - t_bias.y), 2.0f * t_coef.z - t_bias.z);
+    t_min = gl_max(0.0f, t_min);
+    float t_max = gl_min(gl_min(t_coef.x - t_bias.x, t_coef.y - t_bias.y), t_coef.z - t_bias.z);
+    float h = t_max;
+    int idx = 0;
+    vec3 pos = v3(1.0f, 1.0f, 1.0f);
+    if (t_min < 1.5f * t_coef.x - t_bias.x) { idx ^= 1; pos.x = 1.5f; }
+    if (t_min < 1.5f * t_coef.y - t_bias.y) { idx ^= 2; pos.y = 1.5f; }
+    if (t_min < 1.5f * t_coef.z - t_bias.z) { idx ^= 4; pos.z = 1.5f; }
+
+    uint32_t depth = 127 - ((f2u(octree_scale) >> 23) & 0xff);          // max depth from the exponent of the scale
+    const int levels = (int)depth + 3 < MAX_SCALE + 1 ? (int)depth + 3 : MAX_SCALE + 1;
+    auto slot = [levels](int sc) { int l = MAX_SCALE - 1 - sc; return l < 0 ? 0 : (l < levels ? l : levels - 1); };
+    uint32_t material_section_ptr = INVALID_PTR;
+    uint32_t pre_leaf_pointer = INVALID_PTR;
+
+    for (int i = 0; i < MAX_STEPS; ++i) {
+        if (max_dst >= 0 && t_min > max_dst) return;
+        if (cnt) cnt->steps++;
+
+        vec3 t_corner = v3(fmaf(pos.x, t_coef.x, -t_bias.x), fmaf(pos.y, t_coef.y, -t_bias.y), fmaf(pos.z, t_coef.z, -t_bias.z));
+        float tc_max = gl_min(gl_min(t_corner.x, t_corner.y), t_corner.z);
+        uint32_t octant_idx = (uint32_t)(idx ^ octant_mask);
+
+        bool crossed_boundary = false;
+        uint32_t next_ptr = csvo_read_next_ptr(s, ptr, depth, octant_idx, crossed_boundary);
+        bool is_child = next_ptr != INVALID_PTR;
+        bool is_leaf = is_child && depth < 2;
+        if (depth == 2) pre_leaf_pointer = ptr;
+
+        if (trace) {
+            trace->stack_ptr += 1;
+            if ((uint32_t)trace->stack_ptr < trace->cap) {
+                DebugFrame& f = trace->frames[trace->stack_ptr];
+                f.t_min = t_min / octree_scale; f.ptr = ptr; f.idx = octant_idx; f.parent_octant_idx = depth;
+                f.scale = scale; f.is_child = is_child; f.is_leaf = is_leaf; f.crossed_boundary = crossed_boundary; f.next_ptr = next_ptr;
+            }
+        }
+
+        if (is_child && t_min <= t_max) {
+            if (is_leaf && t_min == 0) res.inside_voxel = 1;
+            if (is_leaf && t_min > 0) {                                 // phase: HIT
+                if (cnt) cnt->leaf_tests++;
+                uint32_t value = csvo_read_leaf(s, material_section_ptr, pre_leaf_pointer, ptr, octant_idx);
+                vec3 tcn = v3(fmaf(pos.x + scale_exp2, t_coef.x, -t_bias.x), fmaf(pos.y + scale_exp2, t_coef.y, -t_bias.y),
+                              fmaf(pos.z + scale_exp2, t_coef.z, -t_bias.z));
+                float tc_min = gl_max(gl_max(tcn.x, tcn.y), tcn.z);
+                vec3 p = pos;
+                if ((octant_mask & 1) != 0) p.x = 3.0f - scale_exp2 - p.x;
+                if ((octant_mask & 2) != 0) p.y = 3.0f - scale_exp2 - p.y;
+                if ((octant_mask & 4) != 0) p.z = 3.0f - scale_exp2 - p.z;
+                int face_id; float uvx, uvy;
+                if (tc_min == tcn.x) {
+                    face_id = (f2i(rd.x) >> 31) & 1;
+                    uvx = ((ro.z + rd.z * tcn.x) - p.z) / scale_exp2; uvy = ((ro.y + rd.y * tcn.x) - p.y) / scale_exp2;
+                    if (rd.x > 0) uvx = 1 - uvx;
+                } else if (tc_min == tcn.y) {
+                    face_id = 2 | ((f2i(rd.y) >> 31) & 1);
+                    uvx = ((ro.x + rd.x * tcn.y) - p.x) / scale_exp2; uvy = ((ro.z + rd.z * tcn.y) - p.z) / scale_exp2;
+                    if (rd.y > 0) uvy = 1 - uvy;
+                } else {
+                    face_id = 4 | ((f2i(rd.z) >> 31) & 1);
+                    uvx = ((ro.x + rd.x * tcn.z) - p.x) / scale_exp2; uvy = ((ro.y + rd.y * tcn.z) - p.y) / scale_exp2;
+                    if (rd.z < 0) uvx = 1 - uvx;
+                }
+                const Material& mat = s.materials[value < s.n_materials ? value : s.n_materials - 1];
+                int tex_id = mat.tex_side;
+                if (face_id == 3) tex_id = mat.tex_top;
+                else if (face_id == 2) tex_id = mat.tex_bottom;
+                float dst = t_min / octree_scale;
+                float sm = gl_clamp((dst - 15.0f) / (25.0f - 15.0f), 0.0f, 1.0f);
+                sm = (sm * sm) * (3.0f - 2.0f * sm);
+                float tex_lod = (sm * (dst - 15.0f)) * 0.05f;
+                float tex_color[4];
+                texture_lod(*s.tex, uvx, uvy, tex_id, tex_lod, tex_color, cnt);
+                bool first_of_kind = adjacent_leaf_count == 0 || value != last_leaf_value;
+                if ((tex_color[3] > 0 || !cast_translucent) && first_of_kind) {
+                    res.t = dst; res.face_id = face_id; res.uv[0] = uvx; res.uv[1] = uvy; res.value = value;
+                    for (int k = 0; k < 4; ++k) res.color[k] = tex_color[k];
+                    res.lod = tex_lod;
+                    res.pos[0] = gl_min(gl_max(ro.x + t_min * rd.x, p.x + EPSILON), p.x + scale_exp2 - EPSILON);
+                    res.pos[1] = gl_min(gl_max(ro.y + t_min * rd.y, p.y + EPSILON), p.y + scale_exp2 - EPSILON);
+                    res.pos[2] = gl_min(gl_max(ro.z + t_min * rd.z, p.z + EPSILON), p.z + scale_exp2 - EPSILON);
+                    for (int k = 0; k < 3; ++k) { res.pos[k] -= 1; res.pos[k] /= octree_scale; }
+                    return;
+                }
+                ++adjacent_leaf_count;
+                last_leaf_value = value;
+            } else {
+                float half_scale = scale_exp2 * 0.5f;
+                vec3 t_center = v3(fmaf(half_scale, t_coef.x, t_corner.x), fmaf(half_scale, t_coef.y, t_corner.y),
+                                   fmaf(half_scale, t_coef.z, t_corner.z));
+                float tv_max = gl_min(t_max, tc_max);
+                if (t_min <= tv_max) {                                  // phase: PUSH
+                    if (cnt) cnt->pushes++;
+                    if (tc_max < h) { ptr_stack[slot(scale)] = ptr; depth_stack[slot(scale)] = depth; t_max_stack[slot(scale)] = t_max; }
+                    h = tc_max;
+                    --depth;
+                    ptr = next_ptr;
+                    if (crossed_boundary) {                             // entering a chunk record: [lod][material bytes][materials][nodes]
+                        uint32_t child_lod = csvo_read_byte(s, ptr);
+                        uint32_t material_bytes = csvo_read_uint(s, ptr + 1);
+                        ptr += 5;
+                        material_section_ptr = ptr;
+                        ptr += material_bytes;
+                        depth = child_lod;
+                    }
+                    --scale;
+                    scale_exp2 = half_scale;
+                    idx = 0;
+                    if (t_min < t_center.x) { idx ^= 1; pos.x += scale_exp2; }
+                    if (t_min < t_center.y) { idx ^= 2; pos.y += scale_exp2; }
+                    if (t_min < t_center.z) { idx ^= 4; pos.z += scale_exp2; }
+                    t_max = tv_max;
+                    continue;
+                }
+            }
+        } else {
+            adjacent_leaf_count = 0;
+            last_leaf_value = 0xffffffffu;
+        }
+
+        int step_mask = 0;                                              // phase: ADVANCE
+        if (tc_max >= t_corner.x) { step_mask ^= 1; pos.x -= scale_exp2; }
+        if (tc_max >= t_corner.y) { step_mask ^= 2; pos.y -= scale_exp2; }
+        if (tc_max >= t_corner.z) { step_mask ^= 4; pos.z -= scale_exp2; }
+        t_min = tc_max;
+        idx ^= step_mask;
+        if ((idx & step_mask) != 0) {                                   // phase: POP
+            uint32_t differing_bits = 0;
+            if ((step_mask & 1) != 0) differing_bits |= f2u(pos.x) ^ f2u(pos.x + scale_exp2);
+            if ((step_mask & 2) != 0) differing_bits |= f2u(pos.y) ^ f2u(pos.y + scale_exp2);
+            if ((step_mask & 4) != 0) differing_bits |= f2u(pos.z) ^ f2u(pos.z + scale_exp2);
+            scale = find_msb(differing_bits);
+            scale_exp2 = exp2i(scale - MAX_SCALE);
+            if (scale >= MAX_SCALE) return;
+            ptr = ptr_stack[slot(scale)];
+            depth = depth_stack[slot(scale)];
+            t_max = t_max_stack[slot(scale)];
+            int shx = f2i(pos.x) >> scale, shy = f2i(pos.y) >> scale, shz = f2i(pos.z) >> scale;
+            pos.x = i2f(shx << scale); pos.y = i2f(shy << scale); pos.z = i2f(shz << scale);
+            idx = (shx & 1) | ((shy & 1) << 1) | ((shz & 1) << 2);
+            h = 0;
+        }
+    }
+}
+
 struct RenderParams {
     float view[16];
     float fov_y_rad, aspect_ratio, ambient_intensity;
@@ -529,18 +799,20 @@ uint64_t vxo_texture_level(const VxoTexture* t, uint32_t level, uint8_t* out) {
     return v.size();
 }
 
-static vxo::Scene make_scene(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex) {
+static vxo::Scene make_scene(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
+                             int svo_format) {
     vxo::Scene s;
     s.world = world; s.world_len = world_len;
     s.materials = (const vxo::Material*)materials; s.n_materials = n_materials; s.tex = &tex->t;
+    s.format = svo_format;
     return s;
 }
 
 // svo.test.glsl main()
-void vxo_debug_cast(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
+void vxo_debug_cast(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex, int svo_format,
                     const float pos[3], const float dir[3], float max_dst, uint32_t cast_translucent,
                     vxo::OctreeResult* result, vxo::DebugFrame* frames, uint32_t frames_cap, uint32_t* n_frames) {
-    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex);
+    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
     vxo::Trace tr{frames, frames_cap, -1};
     vxo::intersect_octree(s, vxo::v3(pos[0], pos[1], pos[2]), vxo::v3(dir[0], dir[1], dir[2]), max_dst, cast_translucent != 0,
                           *result, nullptr, &tr);
@@ -551,9 +823,9 @@ struct VxoTask { float max_dst, _p0[3], pos[3], _p1, dir[3], _p2; };
 struct VxoResult { float dst; uint32_t inside_voxel; float _p0[2], pos[3], _p1, normal[3], _p2; };
 
 // picker.glsl main() for tasks [0,n). threads<=0 -> all cores.
-void vxo_raycast(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
+void vxo_raycast(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex, int svo_format,
                  const VxoTask* tasks, uint64_t n, VxoResult* results, vxo::Counters* counters, int threads) {
-    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex);
+    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
     vxo::Counters total{};
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -587,10 +859,10 @@ void vxo_raycast(const uint8_t* world, uint64_t world_len, const void* materials
 }
 
 // world.glsl main() over rows [y0,y1) of a w x h image; out is the FULL image (w*h*4 floats, row 0 = bottom).
-void vxo_render(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
+void vxo_render(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex, int svo_format,
                 const vxo::RenderParams* params, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, float* out,
                 vxo::Counters* counters, int threads) {
-    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex);
+    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
     const float tan_half_fov = tanf(params->fov_y_rad * 0.5f);
     vxo::Counters total{};
 #ifdef _OPENMP
@@ -614,9 +886,9 @@ void vxo_render(const uint8_t* world, uint64_t world_len, const void* materials,
 
 // Per-pixel primary-hit record for parity diffing of hit voxel / material / face / distance.
 struct VxoHit { float t; uint32_t value; int32_t face_id; float pos[3]; uint32_t near_boundary; };
-void vxo_primary_hits(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
+void vxo_primary_hits(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex, int svo_format,
                       const vxo::RenderParams* params, uint32_t w, uint32_t h, VxoHit* out, int threads) {
-    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex);
+    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
     const float tan_half_fov = tanf(params->fov_y_rad * 0.5f);
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);

@@ -102,3 +102,27 @@ PICKER_RAYCAST = {
         (-1.0, False, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)),
     ],
 }
+
+
+# ---------------------------------------------------------------------------------------------------------- CSVO ----
+# src/graphics/svo_shader_tests.rs:756-1224 csvo_tests. cast_inside_outside_all_axes, uv_coords_on_all_sides,
+# casting_against_translucent_leafs and detect_inside_leaf_voxel (:806-1176) are line for line the ESVO cases above (same
+# scenes, same expected results); the two step traces differ because the node encoding does.
+# Frames: (t_min, ptr, idx, depth [in StackFrame.parent_octant_idx], scale, is_child, is_leaf, crossed_boundary, next_ptr).
+U32_MAX = 4294967295
+
+# svo_shader_tests.rs:763-804  csvo_tests::shader_svo_traversal
+CSVO_TRAVERSAL = dict(TRAVERSAL, frames=[
+    (0.0, 21, 0, 6, 22, 1, 0, 1, 0), (0.0, 9, 0, 5, 21, 0, 0, 0, U32_MAX), (16.0, 9, 1, 5, 21, 1, 0, 0, 12),
+    (16.0, 12, 0, 4, 20, 0, 0, 0, U32_MAX), (24.0, 12, 1, 4, 20, 1, 0, 0, 15), (24.0, 15, 0, 3, 19, 0, 0, 0, U32_MAX),
+    (28.0, 15, 1, 3, 19, 1, 0, 0, 17), (28.0, 17, 0, 2, 18, 0, 0, 0, U32_MAX), (30.0, 17, 1, 2, 18, 1, 0, 0, 20),
+    (30.0, 20, 0, 1, 17, 0, 0, 0, U32_MAX), (31.0, 20, 1, 1, 17, 1, 1, 0, 23),
+])
+
+# svo_shader_tests.rs:1177-1223  csvo_tests::check_at_higher_coordinates
+CSVO_HIGHER_COORDS = dict(HIGHER_COORDS, frames=[
+    (0.0, 21814, 7, 9, 22, 1, 0, 0, 21826), (0.0, 21826, 7, 8, 21, 1, 0, 0, 21829), (0.0, 21829, 7, 7, 20, 1, 0, 0, 21832),
+    (0.0, 21832, 7, 6, 19, 1, 0, 1, 0), (0.0, 20485, 0, 5, 18, 1, 0, 0, 20494), (0.0, 20494, 4, 4, 17, 1, 0, 0, 20662),
+    (0.0, 20662, 7, 3, 16, 1, 0, 0, 20736), (0.0, 20736, 0, 2, 15, 1, 0, 0, 20739), (0.0, 20739, 6, 1, 14, 0, 0, 0, U32_MAX),
+    (0.9593506, 20739, 4, 1, 14, 1, 1, 0, 20744),
+])

@@ -25,9 +25,9 @@ def shader_test_registry(pkg):
     return r
 
 
-def shader_test_world(pkg, blocks, svo_pos=(0, 0, 0)):
+def shader_test_world(pkg, blocks, svo_pos=(0, 0, 0), fmt=0):
     """create_test_world(), svo_shader_tests.rs:78-115: pooled chunk storage, set_block, storage.compact(), one leaf."""
-    w = pkg.World()
+    w = pkg.World(fmt=fmt)
     w.set_leaf_blocks(svo_pos, blocks, uid=1, lod=5, compact=True)
     w.serialize()
     return w
@@ -62,7 +62,7 @@ def svo_render_test_params(pkg, width=640, height=490):
 
 def oracle_scene(ora, world, registry):
     tex, mips = registry.textures()
-    return ora.Scene(world.gpu_buffer(), registry.materials().tobytes(), tex, mips)
+    return ora.Scene(world.gpu_buffer(), registry.materials().tobytes(), tex, mips, fmt=getattr(world, "fmt", 0))
 
 
 def diff_images(a8, b8):

@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--radius", type=int, default=20)
     ap.add_argument("--no-lod", action="store_true")
+    ap.add_argument("--format", default="esvo", choices=["esvo", "csvo"], help="SVO type of the world buffer: esvo = the north_star path "
+                    "(default); csvo = the reference's default feature (world::hds::csvo + svo.csvo.glsl)")
     ap.add_argument("--no-shadows", action="store_true")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
     ap.add_argument("--no-l2-window", action="store_true")
@@ -65,7 +67,8 @@ def parse():
 
 def build_world(pkg, args):
     t = time.time()
-    world = pkg.World(radius=args.radius, center=(-1, 2, 5), seed=1, no_lod=args.no_lod)
+    world = pkg.World(radius=args.radius, center=(-1, 2, 5), seed=1, no_lod=args.no_lod,
+                      fmt=pkg.FORMAT_CSVO if getattr(args, "format", "esvo") == "csvo" else pkg.FORMAT_ESVO)
     world.generate(0, 8)
     world.serialize()
     return world, time.time() - t
@@ -81,7 +84,7 @@ def frame_params(pkg, world, args):
 
 
 def workload_name(args):
-    return (f"generated-terrain r={args.radius} chunks{' no-LOD' if args.no_lod else ' LOD'}, {args.width}x{args.height}, "
+    return (f"generated-terrain r={args.radius} chunks{' no-LOD' if args.no_lod else ' LOD'}{' (CSVO format)' if getattr(args, 'format', 'esvo') == 'csvo' else ''}, {args.width}x{args.height}, "
             f"primary{'' if args.no_shadows else '+shadow'} rays, camera (-24,80,174) fov72 (BASELINE configs[2])")
 
 
@@ -169,7 +172,7 @@ def run_reference(args):
     world, _ = build_world(pkg, args)
     reg = pkg.content_registry(pkg.load_atlas())
     tex, mips = reg.textures()
-    scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+    scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
     vxp = frame_params(pkg, world, args)
     threads = ora.max_threads()
     # one step = the whole frame on all host threads (about a third of a second at 4K on 16 threads); if the box is so slow
@@ -225,7 +228,7 @@ def main():
     W, H = args.width, args.height
     size_mb = int(world.size_bytes // 1_000_000 + 64)
     svo = pkg.Svo(reg, size_mb=size_mb, max_width=W, max_height=H, max_rays=1024, device=local_rank,
-                  flags=(pkg.VX_FLAG_NO_L2_WINDOW if args.no_l2_window else 0))
+                  flags=(pkg.VX_FLAG_NO_L2_WINDOW if args.no_l2_window else 0) | world.svo_flags)
     # a real (non-legacy) torch stream shared with the library: torch ops, NCCL collectives and vx_* kernels order on it without
     # host syncs, and torch.cuda.Event timings on it see the library's kernels (stream 0 would mean "keep the library's own streams")
     stream = torch.cuda.Stream(device=dev)
@@ -247,7 +250,8 @@ def main():
     stride = max(chunk_len, ((world.size_bytes - chunk_len) // 4) // 48 * 48)
     dirty = [(i * stride, min(chunk_len, world.size_bytes - i * stride)) for i in range(4) if i * stride < world.size_bytes]
     dirty.append((root_off, root_len))
-    dirty_bytes = sum(l for _, l in dirty) + 24
+    HB = world.header_bytes   # 24 (ESVO: scale + preamble) or 8 (CSVO: scale + root offset)
+    dirty_bytes = sum(l for _, l in dirty) + HB
     octree_scale = float(np.float32(2.0 ** -world.depth))
     packed_n = svo.pack_dirty(dirty, None)
     packed_host = torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)
@@ -279,15 +283,15 @@ def main():
         sf.release()
 
     frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
-    mirror = svo.host_mirror(24 + world.size_bytes)
-    staged = [bytes(mirror[24 + o:24 + o + l]) for o, l in dirty]
+    mirror = svo.host_mirror(HB + world.size_bytes)
+    staged = [bytes(mirror[HB + o:HB + o + l]) for o, l in dirty]
 
     def step_e2e():
         """The same frame through the C ABI with host buffers: dirty bytes -> pinned mirror -> H2D, render, RGBA8 -> host."""
         flush()
         if rank == 0:
             for (o, l), b in zip(dirty, staged):   # the host-side serializer writing its changes (write_changes_to)
-                mirror[24 + o:24 + o + l] = np.frombuffer(b, np.uint8)
+                mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
         if n_gpus > 1:
             # host-resident inputs cannot be sent a frame ahead: pack -> H2D -> broadcast -> scatter sit in front of the frame
             sf.apply_dirty()          # drain the set the resident loop left in flight (first e2e step only)
@@ -402,7 +406,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth),
+            "workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "svo_format": args.format,
             "chunks": int(world.chunk_count), "rays_per_frame": rays_total, "primary_rays": prim_total, "shadow_rays": shad_total,
             "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
             "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 160 MiB device fill (> 126 MB L2) inside the timed region",
@@ -429,7 +433,7 @@ def main():
     if not args.skip_cpu and n_gpus == 1:
         ora = graft.load_oracle()
         tex, mips = reg.textures()
-        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
         threads = ora.max_threads()
         rps, desc, _, _ = cpu_render_sample(scene, vxp, args, threads, args.cpu_seconds, frac=1.0)
         line["cpu_baseline"] = {"value": rps / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
@@ -472,14 +476,14 @@ def run_picker(args):
     pkg = graft.load_pkg()
     radius = args.radius if args.radius != 20 else 40
     t0 = time.time()
-    world = pkg.World(radius=radius, center=(-1, 2, 5), seed=1, no_lod=True)
+    world = pkg.World(radius=radius, center=(-1, 2, 5), seed=1, no_lod=True, fmt=pkg.FORMAT_CSVO if args.format == "csvo" else pkg.FORMAT_ESVO)
     world.generate(0, 8)
     world.serialize()
     gen_s = time.time() - t0
     reg = pkg.content_registry(pkg.load_atlas())
     n_total = args.rays
     n = n_total // world_size
-    svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=32, max_height=16, max_rays=n, device=local_rank)
+    svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=32, max_height=16, max_rays=n, device=local_rank, flags=world.svo_flags)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
@@ -578,7 +582,7 @@ def run_picker(args):
     if not args.skip_cpu and world_size == 1:
         ora = graft.load_oracle()
         tex, mips = reg.textures()
-        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips)
+        scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
         threads = ora.max_threads()
         m = min(n, 1 << 18)
         scene.raycast(tasks[:4096], threads=threads)

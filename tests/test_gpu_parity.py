@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 def make_svo(pkg, reg, world, size_mb=8, w=640, h=490, rays=1 << 20, flags=0):
-    svo = pkg.Svo(reg, size_mb=size_mb, max_width=w, max_height=h, max_rays=rays, flags=flags)
+    svo = pkg.Svo(reg, size_mb=size_mb, max_width=w, max_height=h, max_rays=rays, flags=flags | world.svo_flags)
     world.mark_all_dirty()   # a fresh GPU buffer needs the whole RangeBuffer, not just the changes since the last update
     svo.update(world)
     return svo
@@ -30,8 +30,8 @@ def reg(pkg):
     return helpers.shader_test_registry(pkg)
 
 
-def cast_both(pkg, ora, reg, blocks, pos, d, max_dst, translucent, svo_pos=(0, 0, 0)):
-    w = helpers.shader_test_world(pkg, blocks, svo_pos)
+def cast_both(pkg, ora, reg, blocks, pos, d, max_dst, translucent, svo_pos=(0, 0, 0), fmt=0):
+    w = helpers.shader_test_world(pkg, blocks, svo_pos, fmt=fmt)
     s = helpers.oracle_scene(ora, w, reg)
     svo = make_svo(pkg, reg, w, size_mb=2, w=8, h=8, rays=16)
     o_res, o_frames, o_n = s.debug_cast(pos, d, max_dst, translucent)
@@ -455,3 +455,92 @@ def test_edge_cases(pkg, ora, reg):
     got, got8, want, want8, _ = render_both(pkg, ora, reg, w2, p, 64, 64, svo=svo2)
     assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
     svo2.close()
+
+
+# ------------------------------------------------------------------------------------------------------------- CSVO --
+
+def test_csvo_golden_traces_and_results_on_gpu(pkg, ora, reg):
+    """The CSVO kernels (VX_FLAG_SVO_CSVO) against the oracle and the reference's csvo_tests goldens
+    (svo_shader_tests.rs:756-1224): step traces with byte pointers / depth / crossed_boundary / next_ptr, and all result cases."""
+    from test_oracle_golden import check_frames_csvo
+    for g in (gv.CSVO_TRAVERSAL, gv.CSVO_HIGHER_COORDS):
+        o, c = cast_both(pkg, ora, reg, g["blocks"], g["pos"], g["dir"], g["max_dst"], g["cast_translucent"], g.get("svo_pos", (0, 0, 0)), fmt=1)
+        assert_same_cast(o, c)
+        check_frames_csvo(c[1], c[2], g["frames"])
+        check_result(c[0], g["result"])
+    g = gv.ALL_AXES
+    for name, pos, d, t, face, hit_pos, uv in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 100.0, False, fmt=1)
+        assert_same_cast(o, c)
+        check_result(c[0], {"t": t, "value": 1, "face_id": face, "pos": hit_pos, "uv": uv, "color": g["color"], "inside_voxel": False}, name=name)
+    g = gv.UV_COORDS
+    for pos, d, uv, color in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 32.0, False, fmt=1)
+        assert_same_cast(o, c)
+        assert close(c[0].as_dict()["uv"], uv) and close(c[0].as_dict()["color"], color)
+    g = gv.TRANSLUCENT
+    for name, pos, translucent, exp in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, g["dir"], 32.0, translucent, fmt=1)
+        assert_same_cast(o, c)
+        assert c[0].as_dict()["value"] == exp["value"] and c[0].as_dict()["face_id"] == exp["face_id"], name
+    g = gv.INSIDE_LEAF
+    for name, pos, d, exp in g["cases"]:
+        o, c = cast_both(pkg, ora, reg, g["blocks"], pos, d, 32.0, False, fmt=1)
+        assert_same_cast(o, c)
+        check_result(c[0], exp, name=name)
+
+
+def test_csvo_picker_random_rays_bit_exact(pkg, ora, reg):
+    """200k incoherent rays per scene on CSVO buffers, origins inside voxels included (the out-of-spec descent follows the
+    oracle's stated policy): results byte-identical, counters identical."""
+    for name, blocks, svo_pos in small_scenes(pkg):
+        w = helpers.shader_test_world(pkg, blocks, svo_pos, fmt=1)
+        s = helpers.oracle_scene(ora, w, reg)
+        svo = make_svo(pkg, reg, w, size_mb=4, w=8, h=8, rays=1 << 18)
+        size = 32 * (max(svo_pos) + 1)
+        for max_dst, seed in ((-1.0, 1), (30.0, 2)):
+            tasks = helpers.random_tasks(pkg, 200_000, -8.0, size + 8.0, max_dst, seed)
+            tasks["dir"][::17, 1] = 0.0
+            tasks["pos"][::5] = np.floor(tasks["pos"][::5]) + 0.5
+            want, ocnt = s.raycast(tasks)
+            svo.set_option(pkg.OPT_COUNT, 1)
+            got = svo.raycast_tasks(tasks)
+            assert got.tobytes() == want.tobytes(), (name, max_dst, int((got["dst"] != want["dst"]).sum()))
+            st = svo.frame_stats(1)
+            assert st["steps"] == ocnt["steps"] and st["pushes"] == ocnt["pushes"] and st["leaf_tests"] == ocnt["leaf_tests"], (st, ocnt)
+        svo.close()
+
+
+def test_csvo_render_terrain(pkg, ora):
+    """Generated terrain with LOD chunks serialized as CSVO: frame (shading, trilinear textures, shadows, highlight) within
+    1 LSB of the oracle's CSVO shader, counters equal; dirty-range update through the 8-byte CSVO header; and the same
+    frame as the ESVO path wherever no ray starts inside a voxel."""
+    reg = pkg.content_registry(pkg.load_atlas())
+    frames = {}
+    for fmt in (1, 0):
+        world = pkg.World(radius=5, center=(-1, 2, 5), seed=1, fmt=fmt)
+        world.generate(0, 8)
+        world.serialize()
+        w, h = 480, 270
+        p = terrain_params(pkg, w, h, selected=(-20.0, 50.0, 174.0))
+        svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+        svo.set_option(pkg.OPT_COUNT, 1)
+        got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
+        assert_frames_match(got, got8, want, want8)
+        st = svo.frame_stats(0)
+        for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+            assert st[k] == cnt[k], (fmt, k, st, cnt)
+        frames[fmt] = got
+        if fmt == 1:
+            for step in range(2):   # edit -> re-serialize -> partial update -> same as the oracle on the new buffer
+                hgt = world.height_at(-10 + step, 174)
+                for dy in range(1, 6):
+                    world.edit_block(-10 + step, hgt + dy, 174, 4)
+                world.serialize()
+                assert sum(l for _, l in world.dirty_ranges()) < world.size_bytes
+                svo.update(world)
+                got, got8, want, want8, _ = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
+                assert_frames_match(got, got8, want, want8)
+        svo.close()
+    differing = (np.abs(frames[0] - frames[1]).max(axis=2) > 0).mean()
+    assert differing < 1e-3, differing

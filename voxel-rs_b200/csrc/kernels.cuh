@@ -104,9 +104,9 @@ __device__ __noinline__ bool translucent_leaf_accepts(const TexInfo* tex, const 
 }
 
 // Render-ray leaf candidate (cast_translucent = true). Returns true when the leaf is the hit; fills g (and value).
-template <bool COUNT>
+template <int FMT, bool COUNT>
 __device__ __forceinline__ bool render_leaf(const Walk& w, const Scene& s, const Smem& sm, float inv_scale, uint32_t& last_leaf, Leaf& g, Counters& cnt) {
-    g.value = leaf_value(w, s);
+    g.value = leaf_value<FMT>(w, s);
     if (COUNT) { cnt.leaf_tests++; cnt.tex_fetches += logical_texels(s.tex, lod_of_dst(w.t_min * inv_scale)); }
     const bool opaque = g.value < 64u && ((s.opaque_materials >> g.value) & 1ull);
     const float* c = sm.cold;
@@ -120,27 +120,31 @@ __device__ __forceinline__ bool render_leaf(const Walk& w, const Scene& s, const
 // The walk loop of a warp: every lane with a live ray steps it; the warp leaves the loop when fewer than `thresh` lanes are
 // still walking. thresh == 1 (run every ray of the warp to its end, then refill all 32 lanes at once) needs no population
 // count and gets its own copy of the loop.
-template <bool LIMITED, bool COUNT>
+template <int FMT, bool LIMITED, bool COUNT>
 __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt, int thresh) {
     if (thresh <= 1) {
         do {
-            if (w.state > 0) walk_step<LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
         } while (__any_sync(0xffffffffu, w.state > 0));
     } else {
         do {
-            if (w.state > 0) walk_step<LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
         } while (__popc(__ballot_sync(0xffffffffu, w.state > 0)) >= thresh);
     }
 }
 
+// octree_scale = the f32 at byte 0 of the world buffer: one word (ESVO) / two words (CSVO: scale, root_ptr) before descriptors[]
+template <int FMT>
+__device__ __forceinline__ float load_octree_scale(const Scene& s) { return __uint_as_float(__ldg(s.desc - (FMT == VX_FMT_CSVO ? 2 : 1))); }
+
 // ---- primary rays ------------------------------------------------------------------------------------------------------
-template <bool COUNT, int MINB>
+template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
     const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
-    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
+    const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
     float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 if (gx < a.u.width && gy < a.u.height) {
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-                    walk_init(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
+                    walk_init<FMT>(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
@@ -198,12 +202,12 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         if (state_at_leaf(w.state)) {
             Leaf g;
-            if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
+            if (render_leaf<FMT, COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
                 float px, py, pz;
                 leaf_pos(w.t_min, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS], g,
                          inv_scale, px, py, pz);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 __stcs(a.hit1 + slot, make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id)));
                 w.state = ST_IDLE;
             } else {
-                walk_skip_leaf(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
+                walk_skip_leaf<FMT>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
         } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -290,13 +294,13 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
 }
 
 // ---- shadow rays -------------------------------------------------------------------------------------------------------------
-template <bool COUNT, int MINB>
+template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
     const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
-    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
+    const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
     const uint32_t n = *a.shadow_count;
     float* cold = sm.cold;
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 entry = run_base + next + my_rank;
                 const float4 s0 = __ldcs(a.sh0 + entry);
                 float rox, roy, roz, rdx, rdy, rdz;
-                walk_init(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
+                walk_init<FMT>(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 lit = s0.w;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;
@@ -345,14 +349,14 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
             if (state_at_leaf(w.state)) {
                 Leaf g;
                 // fully opaque materials block the sun whatever the texel is; others go through the translucency rule
-                const uint32_t value = leaf_value(w, a.scene);
+                const uint32_t value = leaf_value<FMT>(w, a.scene);
                 if (value < 64u && ((a.scene.opaque_materials >> value) & 1ull)) {
                     if (COUNT) { cnt.leaf_tests++; cnt.tex_fetches += logical_texels(a.scene.tex, lod_of_dst(w.t_min * inv_scale)); }
                     shadow = 0.0f;
-                } else if (render_leaf<COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
+                } else if (render_leaf<FMT, COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
                     shadow = 0.0f;
                 } else {
-                    walk_skip_leaf(w, a.scene, sm.stack);
+                    walk_skip_leaf<FMT>(w, a.scene, sm.stack);
                     done = false;
                 }
             }
@@ -380,13 +384,13 @@ struct RaycastArgs {
     uint32_t refill_threshold;
 };
 
-template <bool COUNT>
+template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a) {
     extern __shared__ uint32_t smem_raw[];
     const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
-    const float octree_scale = __uint_as_float(__ldg(a.scene.desc - 1));
+    const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
     float* cold = sm.cold;
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 my_task = run_base + next + my_rank;
                 const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
                 float rox, roy, roz, rdx, rdy, rdz;
-                walk_init(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
+                walk_init<FMT>(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 if (COUNT) cnt.primary_rays++;
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<true, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
         if (w.state <= 0 && w.state != ST_IDLE) {
             // cast_translucent = false: the first leaf is the hit whatever its texel is (svo.esvo.glsl:241-242); the picker
             // never reads value or colour (picker.glsl:40-44), so neither the leaf word nor the texture is fetched.
@@ -465,17 +469,18 @@ struct DebugArgs {
 
 // The step function does not carry the shader's (ptr, parent_octant_idx); the debug kernel shadows them (plus their
 // stacks) next to it to emit reference-format frames. Launched <<<1, VX_THREADS>>>; thread 0 casts.
+template <int FMT>
 __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     extern __shared__ uint32_t smem_raw[];
     const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
     if (threadIdx.x != 0) return;
     const Scene& s = a.scene;
-    const float octree_scale = __uint_as_float(__ldg(s.desc - 1));
+    const float octree_scale = load_octree_scale<FMT>(s);
     const float inv_scale = 1.0f / octree_scale;
     Walk w;
     Counters cnt = {0, 0, 0, 0, 0, 0};
     float rox, roy, roz, rdx, rdy, rdz;
-    walk_init(w, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst, rox, roy, roz, rdx, rdy, rdz);
+    walk_init<FMT>(w, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst, rox, roy, roz, rdx, rdy, rdz);
     uint32_t ptr = 0, pidx = 0;
     uint32_t ptr_stack[VX_MAX_SCALE + 1], pidx_stack[VX_MAX_SCALE + 1];
     for (int i = 0; i <= VX_MAX_SCALE; ++i) { ptr_stack[i] = 0; pidx_stack[i] = 0; }
@@ -490,9 +495,19 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         if (w.state > 0 && !(w.t_min > w.limit)) {
             if (n < a.frames_cap) {
                 VxDebugFrame& f = a.frames[n];
-                f.t_min = w.t_min * inv_scale; f.ptr = ptr; f.idx = oi; f.parent_octant_idx = pidx; f.scale = w.scale;
-                f.is_child = ((w.desc >> oi) & 0x100u) != 0; f.is_leaf = ((w.desc >> oi) & 1u) != 0;
-                f.crossed_boundary = 0; f.next_ptr = 0;
+                f.t_min = w.t_min * inv_scale; f.idx = oi; f.scale = w.scale;
+                if (FMT == VX_FMT_CSVO) {   // svo.csvo.glsl:246: (ptr, depth) ride in (ptr, parent_octant_idx); next_ptr is INVALID_PTR for no child
+                    const bool child = csvo_has_child(w.hdr, w.desc, oi);
+                    bool crossed = false;
+                    const uint32_t np = child ? csvo_next_ptr(s, w.rec, w.desc, w.hdr, oi, crossed) : 0xffffffffu;
+                    f.ptr = w.rec; f.parent_octant_idx = w.desc;
+                    f.is_child = np != 0xffffffffu; f.is_leaf = f.is_child && w.desc < 2u;
+                    f.crossed_boundary = crossed; f.next_ptr = np;
+                } else {
+                    f.ptr = ptr; f.parent_octant_idx = pidx;
+                    f.is_child = ((w.desc >> oi) & 0x100u) != 0; f.is_leaf = ((w.desc >> oi) & 1u) != 0;
+                    f.crossed_boundary = 0; f.next_ptr = 0;
+                }
             }
             ++n;
         }
@@ -500,9 +515,9 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         const float tcx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcy = __fmaf_rn(w.py, w.tcy, -w.tby), tcz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
         const float tc_max = tmin2(tmin2(tcx, tcy), tcz);
         if (w.state <= 0) break;                      // MAX_STEPS used up (:152)
-        walk_step<true, false>(w, s, sm.stack, last_leaf, cnt);
+        walk_step<FMT, true, false>(w, s, sm.stack, last_leaf, cnt);
         if (state_at_leaf(w.state)) {
-            g.value = leaf_value(w, s);
+            g.value = leaf_value<FMT>(w, s);
             leaf_geom(w, rox, roy, roz, rdx, rdy, rdz, inv_scale, g);
             int tex_id;
             leaf_texture(s, g, tex_id, tex_lod);
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
             const bool first_of_kind = g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
             last_leaf = g.value;
-            walk_skip_leaf(w, s, sm.stack);
+            walk_skip_leaf<FMT>(w, s, sm.stack);
         }
         if (w.state == ST_MISS) break;
         if (w.scale == scale_before - 1) {            // PUSH happened
@@ -624,18 +639,18 @@ __global__ void __launch_bounds__(128) shard_copy_kernel(float4* frame, float4* 
 
 // Applies a packed dirty set (n VxRange headers, then [24 head bytes][range 0 bytes][range 1 bytes]...) to the world
 // buffer of a replica. Word-granular: every range offset/length is a multiple of 4.
-__global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes) {
+__global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes, uint32_t head_words) {
     const VxRange* hdr = reinterpret_cast<const VxRange*>(packed);
     const uint32_t* payload = reinterpret_cast<const uint32_t*>(packed + (size_t)n_ranges * sizeof(VxRange));
     uint32_t* w32 = reinterpret_cast<uint32_t*>(world);
     const unsigned long long words = payload_bytes / 4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
-        if (i < 6) { w32[i] = payload[i]; continue; }
-        unsigned long long off = 6;
+        if (i < head_words) { w32[i] = payload[i]; continue; }
+        unsigned long long off = head_words;
         for (uint32_t k = 0; k < n_ranges; ++k) {
             const unsigned long long len = hdr[k].length / 4;
-            if (i < off + len) { w32[6 + hdr[k].offset / 4 + (i - off)] = payload[i]; break; }
+            if (i < off + len) { w32[head_words + hdr[k].offset / 4 + (i - off)] = payload[i]; break; }
             off += len;
         }
     }

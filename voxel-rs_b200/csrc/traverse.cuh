@@ -58,8 +58,9 @@ struct TexInfo {
 
 // Everything a kernel needs to read the scene. Passed by value as a kernel parameter.
 struct Scene {
-    const uint32_t* __restrict__ desc;   // descriptors[] = world buffer + 4 bytes
+    const uint32_t* __restrict__ desc;   // descriptors[]: world buffer + 4 bytes (ESVO, svo.esvo.glsl:3-6) / + 8 bytes (CSVO, svo.csvo.glsl:1-5)
     uint32_t desc_words;                 // capacity in words
+    uint32_t format;                     // VX_FMT_ESVO / VX_FMT_CSVO (host-side dispatch only; kernels are compiled per format)
     uint32_t max_rec;                    // desc_words - 12: largest record index whose 12 words are inside the buffer
     const Material* __restrict__ materials;
     uint32_t n_materials;
@@ -69,6 +70,9 @@ struct Scene {
     unsigned long long opaque_materials; // bit m set (m < 64): every texel of the three face textures of material m has alpha > 0,
                                          // so a leaf of that material is accepted by the translucency rule (:241-242) without sampling
 };
+
+#define VX_FMT_ESVO 0
+#define VX_FMT_CSVO 1
 
 struct Counters {   // = VxFrameStats counters
     unsigned long long primary_rays, shadow_rays, steps, pushes, leaf_tests, tex_fetches;
@@ -176,7 +180,10 @@ struct Walk {
     float t_min, t_max, h;
     float se;                 // scale_exp2 = 2^(scale-23)
     float limit;              // max_dst in [1,2) space, +inf when unlimited (:153)
-    uint32_t rec, desc;       // record of the current octant, child/leaf masks of its children (bits 0-7 leaf, 8-15 child)
+    uint32_t rec, desc;       // ESVO: record of the current octant, child/leaf masks of its children (bits 0-7 leaf, 8-15 child)
+                              // CSVO: byte pointer of the current node, remaining depth (the shader's ptr / depth)
+    uint32_t hdr;             // CSVO: the node's header (u16 when depth > 3, else u8), re-read whenever (ptr, depth) changes
+    uint32_t mat_ptr, preleaf;   // CSVO: material_section_ptr, pre_leaf_pointer (svo.csvo.glsl:222-223; not stacked, like the shader)
     uint32_t idx;             // bits 0-2: child index in mirrored space; bits 4-6: octant_mask; bit 8: inside_voxel
     int scale;
     int state;                // see ST_*: > 0 walking (iterations left of MAX_STEPS), 0 budget used up, < 0 stopped
@@ -196,8 +203,60 @@ __device__ __forceinline__ uint32_t ld_desc(const Scene& s, uint32_t i) {
     return __ldg(s.desc + i);
 }
 
-// svo.esvo.glsl:52-149. (ox,oy,oz) in SVO voxel space. Also returns the [1,2)-space origin and the epsilon-clamped
+// ------------------------------------------------------------------------------------ CSVO node decode (svo.csvo.glsl) --
+// Byte-packed nodes addressed by byte pointers into descriptors[]. A word that is not inside the buffer reads as 0 (the
+// robust-access policy the oracle states too: a ray that starts inside a voxel descends through bytes that are not nodes).
+__device__ __forceinline__ uint32_t csvo_word(const Scene& s, uint32_t i) { return i < s.desc_words ? __ldg(s.desc + i) : 0u; }
+__device__ __forceinline__ uint32_t csvo_read_uint(const Scene& s, uint32_t ptr) {     // :25-35, = the 32 bits starting at byte ptr
+    const uint32_t i = ptr >> 2;
+    return __funnelshift_r(csvo_word(s, i), csvo_word(s, i + 1), (ptr & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t csvo_read_ushort(const Scene& s, uint32_t ptr) { return csvo_read_uint(s, ptr) & 0xffffu; }   // :39-42
+__device__ __forceinline__ uint32_t csvo_read_byte(const Scene& s, uint32_t ptr) { return (csvo_word(s, ptr >> 2) >> ((ptr & 3u) * 8u)) & 0xffu; }   // :45-49
+// bitfieldInsert(0u, 0xffffffffu, 0, bits), with the oracle's definition outside [0, 32]
+__device__ __forceinline__ uint32_t low_bits(int bits) { return bits <= 0 ? 0u : (bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u)); }
+
+// Header of the node at (ptr, depth): what read_next_ptr looks at first (:57-58, :108-109).
+__device__ __forceinline__ uint32_t csvo_header(const Scene& s, uint32_t ptr, uint32_t depth) {
+    return depth > 3u ? csvo_read_ushort(s, ptr) : csvo_read_byte(s, ptr);
+}
+// is the child there? (child_mask != 0, :60-62 / :111)
+__device__ __forceinline__ bool csvo_has_child(uint32_t hdr, uint32_t depth, uint32_t idx) {
+    return depth > 3u ? ((hdr >> (idx * 2u)) & 3u) != 0u : ((hdr >> idx) & 1u) != 0u;
+}
+// bytes of the pointers whose 2-bit tags are set in `tags` (sum of (1 << tag) >> 1, :68-87): tag 1 -> 1, 2 -> 2, 3 -> 4
+__device__ __forceinline__ uint32_t csvo_tag_bytes(uint32_t tags) {
+    const uint32_t lo = tags & 0x5555u, hi = (tags >> 1) & 0x5555u;
+    return __popc(lo & ~hi) + 2u * __popc(hi & ~lo) + 4u * __popc(hi & lo);
+}
+// read_next_ptr (:53-133) for a child that is known to be present.
+__device__ __forceinline__ uint32_t csvo_next_ptr(const Scene& s, uint32_t ptr, uint32_t depth, uint32_t hdr, uint32_t idx, bool& crossed_boundary) {
+    crossed_boundary = false;
+    if (depth > 3u) {                                                          // internal nodes
+        const uint32_t child_mask = (hdr >> (idx * 2u)) & 3u;
+        const uint32_t offset = csvo_tag_bytes(hdr & ((1u << (idx * 2u)) - 1u));
+        const uint32_t ptr_bytes = csvo_tag_bytes(hdr);
+        uint32_t ptr_offset = csvo_read_uint(s, ptr + 2u + offset);
+        ptr_offset &= low_bits((int)(1u << (child_mask - 1u)) * 8);           // the pointer's own 1 / 2 / 4 bytes
+        if (ptr_offset & 0x80000000u) { crossed_boundary = true; return ptr_offset ^ 0x80000000u; }   // absolute: a chunk record
+        return ptr + 2u + ptr_bytes + ptr_offset;
+    }
+    const uint32_t offset = __popc(hdr & ((1u << idx) - 1u));
+    if (depth == 3u) return ptr + 1u + __popc(hdr) + csvo_read_byte(s, ptr + 1u + offset);   // pre-leaf nodes
+    return ptr + 3u + offset;                                                  // leaf nodes: mask + u16 material offset
+}
+// read_leaf (:136-150)
+__device__ __forceinline__ uint32_t csvo_read_leaf(const Scene& s, uint32_t material_section_ptr, uint32_t pre_leaf_ptr, uint32_t ptr, uint32_t idx) {
+    const uint32_t material_section_offset = csvo_read_ushort(s, pre_leaf_ptr + 1u);
+    const int bit_mark = (int)(ptr - (pre_leaf_ptr + 3u)) * 8 + (int)idx;
+    const uint32_t v0 = csvo_read_uint(s, pre_leaf_ptr + 3u) & low_bits(min(bit_mark, 32));
+    const uint32_t v1 = csvo_read_uint(s, pre_leaf_ptr + 7u) & low_bits(max(bit_mark - 32, 0));
+    return csvo_read_uint(s, material_section_ptr + material_section_offset * 4u + (__popc(v0) + __popc(v1)) * 4u);
+}
+
+// svo.esvo.glsl:52-149 / svo.csvo.glsl:171-223. (ox,oy,oz) in SVO voxel space. Also returns the [1,2)-space origin and the epsilon-clamped
 // direction (the leaf evaluation needs them, :210-224, :252-258).
+template <int FMT>
 __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_scale, float ox, float oy, float oz, float dx, float dy, float dz,
                                           float max_dst, float& rox, float& roy, float& roz, float& rdx, float& rdy, float& rdz) {
     rox = ox * octree_scale + 1.0f; roy = oy * octree_scale + 1.0f; roz = oz * octree_scale + 1.0f;
@@ -235,6 +294,13 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
     w.se = 0.5f;
     w.state = VX_MAX_STEPS;
 
+    if (FMT == VX_FMT_CSVO) {
+        w.rec = __ldg(s.desc - 1);                                             // root_ptr, svo.csvo.glsl:190
+        w.desc = 127u - ((__float_as_uint(octree_scale) >> 23) & 0xffu);       // depth from the exponent of octree_scale, :221
+        w.hdr = csvo_header(s, w.rec, w.desc);
+        w.mat_ptr = 0xffffffffu; w.preleaf = 0xffffffffu;                      // INVALID_PTR, :222-223
+        return;
+    }
     // state (ptr=0, parent_octant_idx=0): the preamble's child 0 = world root (esvo.rs:179-188)
     const uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
     w.desc = w0 & 0xffffu;
@@ -266,8 +332,9 @@ enum : int { ST_MISS = -2, ST_IDLE = -3, ST_LEAF = -4 };
 __device__ __forceinline__ bool state_at_leaf(int st) { return st <= ST_LEAF; }
 __device__ __forceinline__ bool state_missed(int st) { return st == 0 || st == ST_MISS; }
 
-// ADVANCE / POP (svo.esvo.glsl:324-391). Returns false when the ray left the octree (:365).
-__device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
+// ADVANCE / POP (svo.esvo.glsl:324-391 = svo.csvo.glsl:440-507). Returns 0 when the ray left the octree (:365), 1 after an
+// ADVANCE, 2 after a POP (the node changed: (rec, desc) = the shader's (ptr, parent_octant_idx) resp. (ptr, depth)).
+__device__ __forceinline__ int walk_advance(Walk& w, uint32_t stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
     uint32_t step_mask = 0;                                                   // :324-327  ADVANCE
     if (tc_max >= tcornx) { step_mask ^= 1; w.px -= w.se; }
     if (tc_max >= tcorny) { step_mask ^= 2; w.py -= w.se; }
@@ -282,7 +349,7 @@ __device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t sta
         const int scale = 31 - __clz(differing_bits);                         // :360 findMSB
         w.scale = scale;
         w.se = __int_as_float((scale - VX_MAX_SCALE + 127) << 23);            // :361 exp2(scale - 23)
-        if (scale >= VX_MAX_SCALE) return false;                              // :365
+        if (scale >= VX_MAX_SCALE) return 0;                                  // :365
         const uint32_t lvl = min((uint32_t)(VX_MAX_SCALE - 1 - scale), stack_levels - 1u);   // :370-372
         stack_load(stk, lvl, w.rec, w.desc, w.t_max);
         const uint32_t keep = 0xffffffffu << scale;                           // :377-382 floor(pos) at the new scale
@@ -290,8 +357,9 @@ __device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t sta
         w.px = __uint_as_float(bx & keep); w.py = __uint_as_float(by & keep); w.pz = __uint_as_float(bz & keep);
         w.idx = (w.idx & ~7u) | ((bx >> scale) & 1u) | (((by >> scale) & 1u) << 1) | (((bz >> scale) & 1u) << 2);   // :388
         w.h = 0.0f;                                                           // :390
+        return 2;
     }
-    return true;
+    return 1;
 }
 
 // One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate. Call only with
@@ -300,7 +368,7 @@ __device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t sta
 // of THIS iteration, and goes on stepping), or ST_MISS.
 // The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
 // record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
-template <bool LIMITED, bool COUNT>
+template <int FMT, bool LIMITED, bool COUNT>
 __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt) {
     --w.state;                                                                // :152
     if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
@@ -308,9 +376,18 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
     const uint32_t ci = (w.idx ^ (w.idx >> 4)) & 7u;                          // :164  idx ^ octant_mask
-    const uint32_t d = w.desc >> ci;                                          // bit 0: is_leaf, bit 8: is_child (:172-173)
-    if ((d & 0x100u) && w.t_min <= w.t_max) {                                 // :178
-        if (d & 1u) {
+    bool is_child, is_leaf;
+    if (FMT == VX_FMT_CSVO) {
+        is_child = csvo_has_child(w.hdr, w.desc, ci);                         // svo.csvo.glsl:239-241
+        is_leaf = w.desc < 2u;                                                // (only looked at when is_child)
+        if (w.desc == 2u) w.preleaf = w.rec;                                  // :243-245
+    } else {
+        const uint32_t d = w.desc >> ci;                                      // bit 0: is_leaf, bit 8: is_child (:172-173)
+        is_child = (d & 0x100u) != 0u;
+        is_leaf = (d & 1u) != 0u;
+    }
+    if (is_child && w.t_min <= w.t_max) {                                     // :178
+        if (is_leaf) {
             if (w.t_min > 0.0f) { w.state = ST_LEAF - w.state; return; }      // :185
             if (w.t_min == 0.0f) w.idx |= 0x100u;                             // :180 inside_voxel
         }
@@ -321,10 +398,29 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
             if (tc_max < w.h)                                                 // :284-288
                 stack_store(stk, min((uint32_t)(VX_MAX_SCALE - 1 - w.scale), s.stack_levels - 1u), w.rec, w.desc, w.t_max);
             w.h = tc_max;                                                     // :289
-            const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));          // child masks of the new octant (the :168 read of later iterations)
-            const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));            // :292 get_octant_ptr
             const float half = w.se * 0.5f;                                   // :274
             const float tcx_ = __fmaf_rn(half, w.tcx, tcornx), tcy_ = __fmaf_rn(half, w.tcy, tcorny), tcz_ = __fmaf_rn(half, w.tcz, tcornz);   // :275
+            if (FMT == VX_FMT_CSVO) {
+                bool crossed;
+                uint32_t np = csvo_next_ptr(s, w.rec, w.desc, w.hdr, ci, crossed);
+                uint32_t nd = w.desc - 1u;                                    // svo.csvo.glsl:401-402 (unsigned: wraps like the shader's uint)
+                if (crossed) {                                                // :404-411 entering a chunk record
+                    const uint32_t child_lod = csvo_read_byte(s, np);
+                    const uint32_t material_bytes = csvo_read_uint(s, np + 1u);
+                    np += 5u;
+                    w.mat_ptr = np;
+                    np += material_bytes;
+                    nd = child_lod;
+                }
+                w.rec = np; w.desc = nd;
+                w.hdr = csvo_header(s, np, nd);
+            } else {
+                const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));      // child masks of the new octant (the :168 read of later iterations)
+                const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));        // :292 get_octant_ptr
+                w.desc = wh >> ((ci & 1u) << 4);                              // bits above 15 are never looked at
+                const uint32_t nr = (wb & 0x80000000u) ? (w.rec + 4u + ci + (wb & 0x7fffffffu)) : wb;
+                w.rec = min(nr, s.max_rec);
+            }
             --w.scale; w.se = half;                                           // :295-297
             uint32_t idx = 0;                                                 // :301-304
             if (w.t_min < tcx_) { idx ^= 1; w.px += half; }
@@ -332,28 +428,33 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
             if (w.t_min < tcz_) { idx ^= 4; w.pz += half; }
             w.idx = (w.idx & ~7u) | idx;
             w.t_max = tv_max;                                                 // :307
-            w.desc = wh >> ((ci & 1u) << 4);                                  // bits above 15 are never looked at
-            const uint32_t nr = (wb & 0x80000000u) ? (w.rec + 4u + ci + (wb & 0x7fffffffu)) : wb;
-            w.rec = min(nr, s.max_rec);
             return;                                                           // :310
         }
     } else {
         last_leaf = 0xffffffffu;                                              // :315-316 (adjacent_leaf_count = 0)
     }
-    if (!walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
+    const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
+    if (adv == 0) w.state = ST_MISS;
+    else if (FMT == VX_FMT_CSVO && adv == 2) w.hdr = csvo_header(s, w.rec, w.desc);
 }
 
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
 // The rejected leaf used up no extra iteration: the budget stored in the leaf state is restored.
+template <int FMT>
 __device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t stk) {
     const int budget = ST_LEAF - w.state;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
-    w.state = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
+    const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
+    w.state = adv ? budget : ST_MISS;
+    if (FMT == VX_FMT_CSVO && adv == 2) w.hdr = csvo_header(s, w.rec, w.desc);
 }
 
-__device__ __forceinline__ uint32_t leaf_value(const Walk& w, const Scene& s) {   // :190-194
-    return __ldg(s.desc + (w.rec + 4u + ((w.idx ^ (w.idx >> 4)) & 7u)));
+template <int FMT>
+__device__ __forceinline__ uint32_t leaf_value(const Walk& w, const Scene& s) {   // svo.esvo.glsl:190-194 / svo.csvo.glsl:259
+    const uint32_t ci = (w.idx ^ (w.idx >> 4)) & 7u;
+    if (FMT == VX_FMT_CSVO) return csvo_read_leaf(s, w.mat_ptr, w.preleaf, w.rec, ci);
+    return __ldg(s.desc + (w.rec + 4u + ci));
 }
 
 // HIT block geometry, svo.esvo.glsl:197-224 + :233, for the leaf candidate walk_step stopped at.

@@ -33,6 +33,8 @@ struct VxCtx {
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
     cudaEvent_t t0_render = nullptr, t1_render = nullptr, t0_picker = nullptr, t1_picker = nullptr;
 
+    uint32_t fmt = VX_FMT_ESVO;       // SVO type of the world buffer (VX_FLAG_SVO_CSVO)
+    size_t head = 24;                 // bytes in front of the RangeBuffer image: f32 scale + 20-B preamble (ESVO) / + u32 root offset (CSVO)
     uint8_t* d_world_raw = nullptr;   // allocation; GL byte 0 lives at d_world_raw + 8 so that records are 16-B aligned
     uint8_t* d_world = nullptr;
     uint8_t* h_mirror = nullptr;      // pinned, capacity bytes
@@ -100,14 +102,16 @@ static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
 
 static Scene make_scene(const VxCtx* c) {
     Scene s{};
-    s.desc = reinterpret_cast<const uint32_t*>(c->d_world + 4);
-    s.desc_words = (uint32_t)((c->cfg.svo_capacity_bytes - 4) / 4);
+    const size_t desc_off = c->fmt == VX_FMT_CSVO ? 8 : 4;   // descriptors[] follows octree_scale (and root_ptr), svo.esvo.glsl:3-6 / svo.csvo.glsl:1-5
+    s.desc = reinterpret_cast<const uint32_t*>(c->d_world + desc_off);
+    s.desc_words = (uint32_t)((c->cfg.svo_capacity_bytes - desc_off) / 4);
+    s.format = c->fmt;
     s.max_rec = s.desc_words - 12;
     s.opaque_materials = c->opaque_materials;
     s.materials = c->d_materials; s.n_materials = c->n_materials;
     s.tex = c->d_texinfo;
     s.unorm = c->d_unorm;
-    uint32_t levels = c->stats.depth + 1;
+    uint32_t levels = c->stats.depth + (c->fmt == VX_FMT_CSVO ? 3 : 1);   // CSVO: the oracle's stack policy for out-of-spec descents
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     return s;
 }
@@ -142,6 +146,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     if (!cfg || !out) return fail(nullptr, VX_E_ARG, "vx_create: null argument");
     if (cfg->svo_capacity_bytes < 256) return fail(nullptr, VX_E_ARG, "vx_create: svo_capacity_bytes too small");
     if (cfg->svo_capacity_bytes > (1ull << 34)) return fail(nullptr, VX_E_ARG, "vx_create: svo_capacity_bytes > 16 GiB (u32 word pointers)");
+    if ((cfg->flags & VX_FLAG_SVO_CSVO) && cfg->svo_capacity_bytes > (1ull << 31))
+        return fail(nullptr, VX_E_ARG, "vx_create: a CSVO buffer is limited to 2 GiB (31-bit byte pointers, csvo.rs:82,121)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -202,6 +208,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaEventRecord(c->e_upload, c->s_upload));
     CUC(cudaStreamSynchronize(c->s_upload));
     c->stats.capacity_bytes = cap;
+    c->fmt = (cfg->flags & VX_FLAG_SVO_CSVO) ? VX_FMT_CSVO : VX_FMT_ESVO;
+    c->head = c->fmt == VX_FMT_CSVO ? 8 : 24;
     c->opt_l2_window = (cfg->flags & VX_FLAG_NO_L2_WINDOW) ? 0 : 1;
 #undef CUC
     *out = c;
@@ -346,7 +354,7 @@ static void install_l2_window(VxCtx* c) {
             size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
         }
-        attr.accessPolicyWindow.base_ptr = c->d_world + 24 + c->hot_off;
+        attr.accessPolicyWindow.base_ptr = c->d_world + c->head + c->hot_off;
         attr.accessPolicyWindow.num_bytes = bytes;
         attr.accessPolicyWindow.hitRatio = 1.0f;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -365,14 +373,14 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
     uint64_t total = 0;
     for (uint32_t i = 0; i < n_dirty; ++i) {
         // reference: assert!(start + length < dst_len) with dst_len = capacity - 1 relative to byte 4 (esvo.rs:328-331, svo.rs:180-181)
-        if (dirty[i].offset + dirty[i].length + 24 > cap)
+        if (dirty[i].offset + dirty[i].length + c->head > cap)
             return fail(c, VX_E_CAPACITY, "dst is not large enough: len=%llu range_start=%llu range_length=%llu", (unsigned long long)cap,
                         (unsigned long long)dirty[i].offset, (unsigned long long)dirty[i].length);
         total += dirty[i].length;
     }
     CU(c, cudaSetDevice(c->cfg.device));
     std::memcpy(c->h_mirror, &octree_scale, 4);                                  // svo.rs:173-175
-    const bool staged = total + 24 <= c->stage_cap;
+    const bool staged = total + c->head <= c->stage_cap;
     // the staging block is reused: the previous upload must have drained it (normally long done)
     if (n_dirty && staged) CU(c, cudaStreamSynchronize(c->s_upload));
     // do not tear a frame / ray batch in flight (render_fence.wait(), svo.rs:178) — on the GPU timeline, not the CPU's
@@ -383,18 +391,18 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
             // the caller may rewrite the mirror as soon as we return: snapshot the dirty bytes into the pinned
             // staging block and copy from there asynchronously
             size_t off = 0;
-            std::memcpy(c->h_stage, c->h_mirror, 24);
-            CU(c, cudaMemcpyAsync(c->d_world, c->h_stage, 24, cudaMemcpyHostToDevice, c->s_upload));
-            off = 24;
+            std::memcpy(c->h_stage, c->h_mirror, c->head);
+            CU(c, cudaMemcpyAsync(c->d_world, c->h_stage, c->head, cudaMemcpyHostToDevice, c->s_upload));
+            off = c->head;
             for (uint32_t i = 0; i < n_dirty; ++i) {
-                std::memcpy(c->h_stage + off, c->h_mirror + 24 + dirty[i].offset, dirty[i].length);
-                CU(c, cudaMemcpyAsync(c->d_world + 24 + dirty[i].offset, c->h_stage + off, dirty[i].length, cudaMemcpyHostToDevice, c->s_upload));
+                std::memcpy(c->h_stage + off, c->h_mirror + c->head + dirty[i].offset, dirty[i].length);
+                CU(c, cudaMemcpyAsync(c->d_world + c->head + dirty[i].offset, c->h_stage + off, dirty[i].length, cudaMemcpyHostToDevice, c->s_upload));
                 off += dirty[i].length;
             }
         } else {
-            CU(c, cudaMemcpyAsync(c->d_world, c->h_mirror, 24, cudaMemcpyHostToDevice, c->s_upload));
+            CU(c, cudaMemcpyAsync(c->d_world, c->h_mirror, c->head, cudaMemcpyHostToDevice, c->s_upload));
             for (uint32_t i = 0; i < n_dirty; ++i)
-                CU(c, cudaMemcpyAsync(c->d_world + 24 + dirty[i].offset, c->h_mirror + 24 + dirty[i].offset, dirty[i].length,
+                CU(c, cudaMemcpyAsync(c->d_world + c->head + dirty[i].offset, c->h_mirror + c->head + dirty[i].offset, dirty[i].length,
                                       cudaMemcpyHostToDevice, c->s_upload));
             CU(c, cudaStreamSynchronize(c->s_upload));   // bulk (re)load straight from the mirror: must finish before the caller reuses it
         }
@@ -408,9 +416,9 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
 
 int64_t vx_svo_pack_dirty(VxCtx* c, const VxRange* dirty, uint32_t n_dirty, void* out, uint64_t out_cap) {
     if (!c || (n_dirty && !dirty)) return VX_E_ARG;
-    uint64_t need = (uint64_t)n_dirty * sizeof(VxRange) + 24;
+    uint64_t need = (uint64_t)n_dirty * sizeof(VxRange) + c->head;
     for (uint32_t i = 0; i < n_dirty; ++i) {
-        if (dirty[i].offset + dirty[i].length + 24 > c->cfg.svo_capacity_bytes) return fail(c, VX_E_CAPACITY, "vx_svo_pack_dirty: range outside buffer");
+        if (dirty[i].offset + dirty[i].length + c->head > c->cfg.svo_capacity_bytes) return fail(c, VX_E_CAPACITY, "vx_svo_pack_dirty: range outside buffer");
         need += dirty[i].length;
     }
     if (!out) return (int64_t)need;
@@ -418,9 +426,9 @@ int64_t vx_svo_pack_dirty(VxCtx* c, const VxRange* dirty, uint32_t n_dirty, void
     uint8_t* p = (uint8_t*)out;
     std::memcpy(p, dirty, (size_t)n_dirty * sizeof(VxRange));
     p += (size_t)n_dirty * sizeof(VxRange);
-    std::memcpy(p, c->h_mirror, 24);
-    p += 24;
-    for (uint32_t i = 0; i < n_dirty; ++i) { std::memcpy(p, c->h_mirror + 24 + dirty[i].offset, dirty[i].length); p += dirty[i].length; }
+    std::memcpy(p, c->h_mirror, c->head);
+    p += c->head;
+    for (uint32_t i = 0; i < n_dirty; ++i) { std::memcpy(p, c->h_mirror + c->head + dirty[i].offset, dirty[i].length); p += dirty[i].length; }
     return (int64_t)need;
 }
 
@@ -431,7 +439,7 @@ int vx_svo_commit_packed_device(VxCtx* c, const void* packed_dev, uint32_t n_dir
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
     const unsigned long long pb = payload_bytes;   // 24 head bytes + range bytes
     const int blocks = (int)((pb + 255) / 256 < 4096 ? (pb + 255) / 256 : 4096);
-    scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, (const uint8_t*)packed_dev, n_dirty, pb);
+    scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, (const uint8_t*)packed_dev, n_dirty, pb, (uint32_t)(c->head / 4));
     c->launches++;
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
@@ -516,9 +524,14 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
     const int minb = pick_minb(c);
     void (*k1)(RenderArgs) = nullptr;
     void (*k3)(RenderArgs) = nullptr;
-#define VX_PICK(K, C) (minb == 5 ? K<C, 5> : (minb == 6 ? K<C, 6> : K<C, 8>))
-    if (count) { k1 = VX_PICK(trace_primary_kernel, true); k3 = VX_PICK(trace_shadow_kernel, true); }
-    else { k1 = VX_PICK(trace_primary_kernel, false); k3 = VX_PICK(trace_shadow_kernel, false); }
+#define VX_PICK(K, F, C) (minb == 5 ? K<F, C, 5> : (minb == 6 ? K<F, C, 6> : K<F, C, 8>))
+    if (c->fmt == VX_FMT_CSVO) {
+        if (count) { k1 = VX_PICK(trace_primary_kernel, VX_FMT_CSVO, true); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_CSVO, true); }
+        else { k1 = VX_PICK(trace_primary_kernel, VX_FMT_CSVO, false); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_CSVO, false); }
+    } else {
+        if (count) { k1 = VX_PICK(trace_primary_kernel, VX_FMT_ESVO, true); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_ESVO, true); }
+        else { k1 = VX_PICK(trace_primary_kernel, VX_FMT_ESVO, false); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_ESVO, false); }
+    }
 #undef VX_PICK
     if (timed) CU(c, cudaEventRecord(c->t_wave[0], c->s_render));
     if (owned) {
@@ -717,7 +730,8 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     a.work_counter = c->d_work + 4;
     a.refill_threshold = (uint32_t)c->opt_refill_picker;
     const size_t smem = stack_smem_bytes(a.scene);
-    auto k = c->opt_count ? trace_picker_kernel<true> : trace_picker_kernel<false>;
+    auto k = c->fmt == VX_FMT_CSVO ? (c->opt_count ? trace_picker_kernel<VX_FMT_CSVO, true> : trace_picker_kernel<VX_FMT_CSVO, false>)
+                                   : (c->opt_count ? trace_picker_kernel<VX_FMT_ESVO, true> : trace_picker_kernel<VX_FMT_ESVO, false>);
     int grid = 0;
     int rc = persistent_grid(c, (const void*)k, VX_THREADS, smem, &grid);
     if (rc) return rc;
@@ -784,7 +798,8 @@ int vx_debug_cast(VxCtx* c, const float pos[3], const float dir[3], float max_ds
     a.max_dst = max_dst; a.cast_translucent = cast_translucent;
     a.result = d_res; a.frames = d_frames; a.frames_cap = cap; a.n_frames = d_n;
     CU(c, cudaStreamWaitEvent(c->s_picker, c->e_upload, 0));
-    debug_cast_kernel<<<1, VX_THREADS, stack_smem_bytes(a.scene), c->s_picker>>>(a);
+    if (c->fmt == VX_FMT_CSVO) debug_cast_kernel<VX_FMT_CSVO><<<1, VX_THREADS, stack_smem_bytes(a.scene), c->s_picker>>>(a);
+    else debug_cast_kernel<VX_FMT_ESVO><<<1, VX_THREADS, stack_smem_bytes(a.scene), c->s_picker>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
     uint32_t n = 0;

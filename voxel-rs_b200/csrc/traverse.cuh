@@ -206,7 +206,9 @@ __device__ __forceinline__ uint32_t ld_desc(const Scene& s, uint32_t i) {
 // ------------------------------------------------------------------------------------ CSVO node decode (svo.csvo.glsl) --
 // Byte-packed nodes addressed by byte pointers into descriptors[]. A word that is not inside the buffer reads as 0 (the
 // robust-access policy the oracle states too: a ray that starts inside a voxel descends through bytes that are not nodes).
-__device__ __forceinline__ uint32_t csvo_word(const Scene& s, uint32_t i) { return i < s.desc_words ? __ldg(s.desc + i) : 0u; }
+// (desc[desc_words] is a zero guard word: the allocation is 64 bytes larger than the capacity and nothing ever writes there,
+// so "outside reads 0" is one min instead of a compare, a predicated load and a select.)
+__device__ __forceinline__ uint32_t csvo_word(const Scene& s, uint32_t i) { return __ldg(s.desc + min(i, s.desc_words)); }
 __device__ __forceinline__ uint32_t csvo_read_uint(const Scene& s, uint32_t ptr) {     // :25-35, = the 32 bits starting at byte ptr
     const uint32_t i = ptr >> 2;
     return __funnelshift_r(csvo_word(s, i), csvo_word(s, i + 1), (ptr & 3u) * 8u);
@@ -218,7 +220,7 @@ __device__ __forceinline__ uint32_t low_bits(int bits) { return bits <= 0 ? 0u :
 
 // Header of the node at (ptr, depth): what read_next_ptr looks at first (:57-58, :108-109).
 __device__ __forceinline__ uint32_t csvo_header(const Scene& s, uint32_t ptr, uint32_t depth) {
-    return depth > 3u ? csvo_read_ushort(s, ptr) : csvo_read_byte(s, ptr);
+    return csvo_read_uint(s, ptr) & (depth > 3u ? 0xffffu : 0xffu);   // one code path for both header sizes (no divergence between node kinds)
 }
 // is the child there? (child_mask != 0, :60-62 / :111)
 __device__ __forceinline__ bool csvo_has_child(uint32_t hdr, uint32_t depth, uint32_t idx) {

@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--no-shadows", action="store_true")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
     ap.add_argument("--no-l2-window", action="store_true")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render kernels "
-                    "(fused, default) or by pack + NCCL send/recv + unpack")
+    ap.add_argument("--gather", default="p2p8", choices=["p2p8", "p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render "
+                    "kernels as RGBA8 pixels (default) or RGBA32F pixels (p2p), or by pack + NCCL send/recv + unpack (nccl)")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--bands", type=int, default=3, help="e2e: bands of vx_render_read_rgba8 (render/read-back overlap)")
@@ -414,9 +414,10 @@ def main():
             "refill_threshold": args.refill or 1,
             "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
-                               ("finished pixels stored by the shade/shadow kernels straight into GPU 0's framebuffer over NVLink peer memory, "
+                               ("finished pixels stored by the shade/shadow kernels straight into GPU 0's %s framebuffer over NVLink peer memory, "
                                 "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"
-                                if args.gather == "p2p" else "pack, NCCL send/recv to GPU 0, unpack")),
+                                % ("RGBA8" if args.gather == "p2p8" else "RGBA32F")
+                                if args.gather != "nccl" else "pack, NCCL send/recv to GPU 0, unpack")),
         },
         "frame_ms": ms_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -288,7 +288,11 @@ int vx_unpack_shard(VxCtx* ctx, const VxShard* shard, const void* packed_dev);  
  *   vx_close_peer_frame   back to the local framebuffer, unmap */
 int vx_frame_ipc_handle(VxCtx* ctx, uint8_t handle_out[64]);
 int vx_open_peer_frame(VxCtx* ctx, const uint8_t handle[64]);
-int vx_close_peer_frame(VxCtx* ctx);
+int vx_close_peer_frame(VxCtx* ctx);   /* closes both the RGBA32F and the RGBA8 peer frame */
+/* The same for the RGBA8 frame, used with vx_set_option(8, 1) on every rank: pixels then cross NVLink as 4 bytes instead of
+ * 16 (what vx_read_frame_rgba8 hands out anyway); vx_read_frame_rgba32f is not available in that mode. */
+int vx_frame8_ipc_handle(VxCtx* ctx, uint8_t handle_out[64]);
+int vx_open_peer_frame8(VxCtx* ctx, const uint8_t handle[64]);
 
 /* Frame flags for the peer-memory gather: 63 32-bit frame counters per context; the root's are mapped by its peers (same IPC
  * scheme as the framebuffer), so ranks order their frames without a collective:
@@ -322,6 +326,9 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *   6 = refill threshold of the render trace kernels: a warp leaves its walk loop to finish/refill rays when fewer
  *       than this many lanes are still walking (1..32; default 1 = run all rays of the warp to their end, then
  *       refill all 32 lanes — measured fastest on coherent frames, profiles/r01_v1_*)
+ *   8 = RGBA8 output (0/1, default 0): the shade / shadow kernels store round(clamp(c)*255) pixels into the RGBA8 frame
+ *       instead of the RGBA32F one — bit-identical to rendering RGBA32F and converting (framebuffer.rs:97-105), a quarter of
+ *       the frame bytes (multi-GPU gather, read-back)
  *   7 = the same for the picker kernel (default 24: incoherent rays differ in length by 100x; 4.85 vs 2.84 Grays/s
  *       against threshold 1 on 16 Mi random rays, profiles/r01_v2_*) */
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);

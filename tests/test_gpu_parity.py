@@ -316,6 +316,16 @@ def test_pipelined_render_readback(pkg, terrain):
             out.fill_(7)
             svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=bands)
             assert out.numpy().tobytes() == want.tobytes(), (w, h, bands)
+        # RGBA8 output mode (vx_set_option 8): the kernels store the rounded pixels themselves — same bytes, no conversion pass
+        svo.set_option(pkg.OPT_RGBA8_OUT, 1)
+        svo.render(p, w, h, world=world)
+        assert svo.read_rgba8().tobytes() == want.tobytes()
+        out.fill_(9)
+        svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=3)
+        assert out.numpy().tobytes() == want.tobytes()
+        with pytest.raises(pkg.VxError):
+            svo.read_rgba32f()
+        svo.set_option(pkg.OPT_RGBA8_OUT, 0)
         # shard 1 of 3: owned pixels equal the full frame, the others keep what the previous full render left in the device frame
         svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=3, shard=(1, 3))
         assert out.numpy().tobytes() == want.tobytes()

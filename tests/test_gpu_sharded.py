@@ -62,7 +62,7 @@ def _worker(rank, world_size, port, out_dir):
         n_ranges, payload, used, depth = meta[0]
 
         frames = {}
-        for gather in ("p2p", "nccl"):
+        for gather in ("p2p", "nccl", "p2p8"):
             sf = pkg.sharded.ShardedFrame(svo, rank, world_size, dist=dist, torch=torch, device=dev, gather=gather)
             sf.configure(W, H, max_dirty_bytes=16 * n_ranges + payload)
             # three frames: the later ones exercise the frame-to-frame ordering (gate / signal / wait / release flags) and the
@@ -76,7 +76,7 @@ def _worker(rank, world_size, port, out_dir):
                 sf.finish()
                 if rank == 0 and i == 2:
                     svo.width, svo.height = W, H
-                    frames[gather] = svo.read_rgba32f()
+                    frames[gather] = svo.read_rgba8() if gather == "p2p8" else svo.read_rgba32f()
                 sf.release()
             torch.cuda.synchronize()
             assert svo.frame_sync_errors() == 0, "a frame-flag wait timed out"
@@ -87,6 +87,7 @@ def _worker(rank, world_size, port, out_dir):
             svo.render_raw(vxp, W, H)
             full = svo.read_rgba32f()
             np.save(os.path.join(out_dir, "full.npy"), full)
+            np.save(os.path.join(out_dir, "full8.npy"), svo.read_rgba8())
             for k, f in frames.items():
                 np.save(os.path.join(out_dir, f"{k}.npy"), f)
         svo.close()
@@ -109,3 +110,5 @@ def test_two_gpus_sharded_frame(pkg, tmp_path):
     for k in ("p2p", "nccl"):
         f = np.load(tmp_path / f"{k}.npy")
         assert f.tobytes() == full.tobytes(), (k, int((f != full).any(axis=2).sum()))
+    full8, f8 = np.load(tmp_path / "full8.npy"), np.load(tmp_path / "p2p8.npy")
+    assert f8.tobytes() == full8.tobytes(), int((f8 != full8).any(axis=2).sum())   # RGBA8 gather == RGBA32F frame read through glReadPixels rounding

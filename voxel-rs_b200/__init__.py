@@ -97,7 +97,7 @@ RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "for
 VX_FLAG_NO_L2_WINDOW = 1
 VX_FLAG_SVO_CSVO = 4
 FORMAT_ESVO, FORMAT_CSVO = 0, 1
-OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER = 3, 4, 5, 6, 7
+OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER, OPT_RGBA8_OUT = 3, 4, 5, 6, 7, 8
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
 VX_SYMBOLS = [
@@ -108,7 +108,7 @@ VX_SYMBOLS = [
     "vx_shard_bytes", "vx_pack_shard", "vx_unpack_shard", "vx_set_streams", "vx_stream",
     "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame", "vx_render_read_rgba8",
     "vx_sync_ipc_handle", "vx_open_peer_sync", "vx_close_peer_sync", "vx_frame_signal", "vx_frame_wait", "vx_frame_gate",
-    "vx_frame_sync_errors",
+    "vx_frame_sync_errors", "vx_frame8_ipc_handle", "vx_open_peer_frame8",
 ]
 
 _lib = None
@@ -166,6 +166,8 @@ def lib():
     L.vx_frame_ipc_handle.argtypes = [P, P]; L.vx_frame_ipc_handle.restype = C.c_int
     L.vx_open_peer_frame.argtypes = [P, P]; L.vx_open_peer_frame.restype = C.c_int
     L.vx_close_peer_frame.argtypes = [P]; L.vx_close_peer_frame.restype = C.c_int
+    L.vx_frame8_ipc_handle.argtypes = [P, P]; L.vx_frame8_ipc_handle.restype = C.c_int
+    L.vx_open_peer_frame8.argtypes = [P, P]; L.vx_open_peer_frame8.restype = C.c_int
     L.vx_sync_ipc_handle.argtypes = [P, P]; L.vx_sync_ipc_handle.restype = C.c_int
     L.vx_open_peer_sync.argtypes = [P, P]; L.vx_open_peer_sync.restype = C.c_int
     L.vx_close_peer_sync.argtypes = [P]; L.vx_close_peer_sync.restype = C.c_int
@@ -641,6 +643,14 @@ class Svo:
         buf = (C.c_uint8 * 64)()
         self._check(lib().vx_frame_ipc_handle(self.ctx, buf))
         return bytes(buf)
+
+    def frame8_ipc_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self._check(lib().vx_frame8_ipc_handle(self.ctx, buf))
+        return bytes(buf)
+
+    def open_peer_frame8(self, handle):
+        self._check(lib().vx_open_peer_frame8(self.ctx, (C.c_uint8 * 64)(*handle)))
 
     def open_peer_frame(self, handle):
         buf = (C.c_uint8 * 64)(*handle)

@@ -27,6 +27,8 @@ struct RenderArgs {
     Scene scene;
     RenderUniforms u;
     float4* frame;                // RGBA32F, row 0 = bottom (world.glsl:140); may be a peer GPU's memory (write-only here)
+    uint32_t* frame8;             // non-null: finished pixels are stored as RGBA8 here INSTEAD (glReadPixels rounding, framebuffer.rs:97-105);
+                                  // may be a peer GPU's memory — a quarter of the NVLink bytes of the RGBA32F gather
     float4* hit0;                 // per pixel slot: {dst, value, u, v}
     float4* hit1;                 // per pixel slot: {pos.x, pos.y, pos.z, flags}  flags: bits 0-2 face, bit 3 hit
     float4* sh0;                  // shadow list: {origin.xyz, diffuse+specular}
@@ -136,6 +138,25 @@ __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk,
 // octree_scale = the f32 at byte 0 of the world buffer: one word (ESVO) / two words (CSVO: scale, root_ptr) before descriptors[]
 template <int FMT>
 __device__ __forceinline__ float load_octree_scale(const Scene& s) { return __uint_as_float(__ldg(s.desc - (FMT == VX_FMT_CSVO ? 2 : 1))); }
+
+// round(clamp(c, 0, 1) * 255) per channel: what glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) returns for the RGBA32F attachment
+__device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
+    const float v[4] = {c.x, c.y, c.z, c.w};
+    uint32_t p = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float f = v[k];
+        if (!(f == f)) f = 0.0f;
+        f = gl_clamp(f, 0.0f, 1.0f);
+        p |= (uint32_t)(int)(f * 255.0f + 0.5f) << (8 * k);
+    }
+    return p;
+}
+// A finished pixel leaves the kernel: 16-byte streaming store into the RGBA32F frame, or 4 bytes into the RGBA8 frame.
+__device__ __forceinline__ void store_pixel(const RenderArgs& a, uint32_t pix, float4 c) {
+    if (a.frame8) __stcs(a.frame8 + pix, pack_rgba8(c));
+    else __stcs(a.frame + pix, c);
+}
 
 // ---- primary rays ------------------------------------------------------------------------------------------------------
 template <int FMT, bool COUNT, int MINB>
@@ -261,18 +282,18 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
             shade_hit(a.scene, sm.unorm, a.u, g, tex_lod, h1.x, h1.y, h1.z, sh, &nf);
             if (COUNT) cnt.tex_fetches += nf;
             if (sh.done) {
-                __stcs(a.frame + pix, make_float4(sh.r, sh.g, sh.b, sh.a));
+                store_pixel(a, pix, make_float4(sh.r, sh.g, sh.b, sh.a));
             } else if (sh.want_shadow) {
                 want_shadow = true;
                 s0 = make_float4(sh.sox, sh.soy, sh.soz, sh.lit);
                 s1 = make_float4(sh.r, sh.g, sh.b, sh.a);
             } else {
-                __stcs(a.frame + pix, shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f));
+                store_pixel(a, pix, shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f));
             }
         } else {
             float ox, oy, oz, dx, dy, dz;
             primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-            __stcs(a.frame + pix, sky_color(dx, dy, dz));
+            store_pixel(a, pix, sky_color(dx, dy, dz));
         }
     }
     // compact the shadow rays of this strip into the global list: one atomicAdd per CTA, strip order kept inside it
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
             if (done) {
                 const float4 c = __ldcs(a.sh1 + entry);
                 const uint32_t pix = __ldcs(a.sh_pix + entry);
-                __stcs(a.frame + pix, shade_finish(a.u, c.x, c.y, c.z, c.w, lit, shadow));
+                store_pixel(a, pix, shade_finish(a.u, c.x, c.y, c.z, c.w, lit, shadow));
                 w.state = ST_IDLE;
             }
         }
@@ -605,16 +626,7 @@ __global__ void opaque_kernel(const uint32_t* texels, uint32_t per_layer, uint32
 __global__ void rgba8_kernel(const float4* frame, uint32_t* out, unsigned long long n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 c = frame[i];
-    const float v[4] = {c.x, c.y, c.z, c.w};
-    uint32_t p = 0;
-    for (int k = 0; k < 4; ++k) {
-        float f = v[k];
-        if (!(f == f)) f = 0.0f;
-        f = gl_clamp(f, 0.0f, 1.0f);
-        p |= (uint32_t)(int)(f * 255.0f + 0.5f) << (8 * k);
-    }
-    out[i] = p;
+    out[i] = pack_rgba8(frame[i]);
 }
 
 // Shard <-> contiguous buffer. One CTA of 128 threads moves one 32x16-pixel macro block (4 pixels per thread as

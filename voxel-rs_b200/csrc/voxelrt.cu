@@ -54,6 +54,7 @@ struct VxCtx {
     uint32_t* d_frame8 = nullptr;
     uint32_t frame_w = 0, frame_h = 0;
     float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_open_peer_frame)
+    uint32_t* frame8_target = nullptr;    // RGBA8 output mode (vx_set_option 8): d_frame8, or a peer GPU's RGBA8 frame (vx_open_peer_frame)
     unsigned int* d_flags = nullptr;      // 64 frame flags of this ctx (the root's are mapped by its peers); [63] = wait timeouts
     unsigned int* flags_target = nullptr; // the flags this ctx signals / gates on: d_flags, or the root's (vx_open_peer_sync)
     bool gate_armed = false;              // next vx_render: wait for flags_target[gate_slot] >= gate_value between trace and shade
@@ -82,7 +83,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -221,6 +222,7 @@ void vx_destroy(VxCtx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     if (c->frame_target) cudaIpcCloseMemHandle(c->frame_target);
+    if (c->frame8_target) cudaIpcCloseMemHandle(c->frame8_target);
     if (c->flags_target) cudaIpcCloseMemHandle(c->flags_target);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_world_raw) cudaFree(c->d_world_raw);
@@ -264,6 +266,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 5: ctx->opt_l2_window = value; break;
         case 6: ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value); break;
         case 7: ctx->opt_refill_picker = value < 1 ? 1 : (value > 32 ? 32 : value); break;
+        case 8: ctx->opt_rgba8_out = value ? 1 : 0; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -604,6 +607,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     rc = ensure_wave_buffers(c, (size_t)a.macro_x * a.macro_y * 512);
     if (rc) return rc;
     a.frame = c->frame_target ? c->frame_target : c->d_frame;
+    a.frame8 = c->opt_rgba8_out ? (c->frame8_target ? c->frame8_target : c->d_frame8) : nullptr;
     a.hit0 = c->d_hit0; a.hit1 = c->d_hit1; a.sh0 = c->d_sh0; a.sh1 = c->d_sh1; a.sh_pix = c->d_sh_pix;
     a.counters = c->d_counters;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
@@ -642,7 +646,7 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     RenderArgs a{};
     int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
     if (rc) return rc;
-    if (c->frame_target) return fail(c, VX_E_STATE, "vx_render_read_rgba8: a peer frame is open (pixels are not written locally)");
+    if (c->frame_target || c->frame8_target) return fail(c, VX_E_STATE, "vx_render_read_rgba8: a peer frame is open (pixels are not written locally)");
     if (bands < 1) bands = 1;
     if (bands > VX_MAX_BANDS) bands = VX_MAX_BANDS;
     if (bands > a.macro_y) bands = a.macro_y;
@@ -672,9 +676,11 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
         if (rc) return rc;
         const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
         const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
-        rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame + px0, c->d_frame8 + px0, n);
-        c->launches++;
-        CU(c, cudaGetLastError());
+        if (!c->opt_rgba8_out) {
+            rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame + px0, c->d_frame8 + px0, n);
+            c->launches++;
+            CU(c, cudaGetLastError());
+        }
         CU(c, cudaEventRecord(c->e_band[b], c->s_render));
         CU(c, cudaStreamWaitEvent(c->s_copy, c->e_band[b], 0));
         CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
@@ -696,6 +702,7 @@ int vx_render_wait(VxCtx* c) {
 
 int vx_read_frame_rgba32f(VxCtx* c, float* out) {
     if (!c || !out || !c->frame_w) return fail(c, VX_E_ARG, "vx_read_frame_rgba32f: nothing rendered / null");
+    if (c->opt_rgba8_out) return fail(c, VX_E_STATE, "vx_read_frame_rgba32f: the context renders RGBA8 only (vx_set_option 8)");
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaMemcpyAsync(out, c->d_frame, (size_t)c->frame_w * c->frame_h * sizeof(float4), cudaMemcpyDeviceToHost, c->s_render));
     CU(c, cudaStreamSynchronize(c->s_render));
@@ -706,9 +713,11 @@ int vx_read_frame_rgba8(VxCtx* c, uint8_t* out) {
     if (!c || !out || !c->frame_w) return fail(c, VX_E_ARG, "vx_read_frame_rgba8: nothing rendered / null");
     CU(c, cudaSetDevice(c->cfg.device));
     const unsigned long long n = (unsigned long long)c->frame_w * c->frame_h;
-    rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame, c->d_frame8, n);
-    c->launches++;
-    CU(c, cudaGetLastError());
+    if (!c->opt_rgba8_out) {   // in RGBA8 output mode the kernels already stored the rounded pixels
+        rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame, c->d_frame8, n);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
     CU(c, cudaMemcpyAsync(out, c->d_frame8, n * 4, cudaMemcpyDeviceToHost, c->s_render));
     CU(c, cudaStreamSynchronize(c->s_render));
     return VX_OK;
@@ -855,6 +864,27 @@ int vx_frame_ipc_handle(VxCtx* c, uint8_t handle_out[64]) {
     return VX_OK;
 }
 
+int vx_frame8_ipc_handle(VxCtx* c, uint8_t handle_out[64]) {
+    if (!c || !handle_out || !c->d_frame8) return fail(c, VX_E_ARG, "vx_frame8_ipc_handle: null argument / no framebuffer");
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(c, cudaIpcGetMemHandle(&h, c->d_frame8));
+    std::memcpy(handle_out, &h, 64);
+    return VX_OK;
+}
+
+int vx_open_peer_frame8(VxCtx* c, const uint8_t handle[64]) {
+    if (!c || !handle) return fail(c, VX_E_ARG, "vx_open_peer_frame8: null argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->frame8_target) return fail(c, VX_E_STATE, "vx_open_peer_frame8: a peer RGBA8 frame is already open");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->frame8_target = (uint32_t*)p;
+    return VX_OK;
+}
+
 int vx_open_peer_frame(VxCtx* c, const uint8_t handle[64]) {
     if (!c || !handle) return fail(c, VX_E_ARG, "vx_open_peer_frame: null argument");
     CU(c, cudaSetDevice(c->cfg.device));
@@ -869,11 +899,12 @@ int vx_open_peer_frame(VxCtx* c, const uint8_t handle[64]) {
 
 int vx_close_peer_frame(VxCtx* c) {
     if (!c) return VX_E_ARG;
-    if (!c->frame_target) return VX_OK;
+    if (!c->frame_target && !c->frame8_target) return VX_OK;
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->s_render));
-    CU(c, cudaIpcCloseMemHandle(c->frame_target));
-    c->frame_target = nullptr;
+    if (c->frame_target) CU(c, cudaIpcCloseMemHandle(c->frame_target));
+    if (c->frame8_target) CU(c, cudaIpcCloseMemHandle(c->frame8_target));
+    c->frame_target = nullptr; c->frame8_target = nullptr;
     return VX_OK;
 }
 

@@ -8,6 +8,8 @@ One process per GPU (torch.distributed). Per frame:
   3. the tiles end up in GPU 0's framebuffer, either
        gather="p2p"   fused: non-root ranks map GPU 0's framebuffer (CUDA IPC) and their shade / shadow kernels store the
                       finished pixels straight into it over NVLink — no pack, no collective, only a barrier at the end;
+       gather="p2p8"  the same with RGBA8 pixels (vx_set_option 8): what Framebuffer::read_pixels hands out anyway, 4 instead of
+                      16 bytes per pixel into GPU 0 — at 8 GPUs the RGBA32F gather is bound by GPU 0's NVLink ingress;
        gather="nccl"  pack the shard, grouped NCCL send/recv to rank 0, unpack (baseline; also what the gloo CPU test runs).
 
 The reference has no counterpart (single GPU). This module is host-side plumbing only: it never touches pixels
@@ -119,11 +121,15 @@ class ShardedFrame:
             self.ev_applied = [t.cuda.Event() for _ in range(2)]    # scatter out of buffer k finished
             for e in self.ev_applied:
                 e.record(t.cuda.current_stream(self.device))
-        if self.gather == "p2p":
-            box = [(self.engine.frame_ipc_handle(), self.engine.sync_ipc_handle()) if self.rank == 0 else None]
+        if self.gather in ("p2p", "p2p8"):
+            eight = self.gather == "p2p8"
+            if eight:
+                self.engine.set_option(8, 1)       # every rank (rank 0 too) stores RGBA8 pixels: a quarter of the NVLink bytes
+            box = [((self.engine.frame8_ipc_handle() if eight else self.engine.frame_ipc_handle()), self.engine.sync_ipc_handle())
+                   if self.rank == 0 else None]
             self.dist.broadcast_object_list(box, src=0)
             if self.rank != 0:
-                self.engine.open_peer_frame(box[0][0])
+                (self.engine.open_peer_frame8 if eight else self.engine.open_peer_frame)(box[0][0])
                 self.engine.open_peer_sync(box[0][1])
                 self._peer_open = True
         else:
@@ -136,6 +142,8 @@ class ShardedFrame:
             self.engine.close_peer_frame()
             self.engine.close_peer_sync()
             self._peer_open = False
+        if self.gather == "p2p8":
+            self.engine.set_option(8, 0)
 
     # ---- per frame -------------------------------------------------------------------------------------------------------
     def prefetch_dirty(self, n_ranges, payload_bytes, used_bytes, depth, packed_host=None):
@@ -182,7 +190,7 @@ class ShardedFrame:
         """This rank's tiles. In p2p mode the pixels land in GPU 0's framebuffer as they are finished; shading is gated on
         GPU 0 having released the previous frame (its primary rays are traced meanwhile)."""
         self.frame_no += 1
-        if self.gather == "p2p" and self.rank != 0:
+        if self.gather in ("p2p", "p2p8") and self.rank != 0:
             self.engine.frame_gate(0, self.frame_no - 1)
         self.engine.render_raw(vx_params, self.width, self.height, shard=self.shard)
 
@@ -190,7 +198,7 @@ class ShardedFrame:
         """After it returns (stream-ordered), GPU 0's framebuffer holds the whole frame. Collective only in nccl mode."""
         if self.world_size == 1:
             return
-        if self.gather == "p2p":
+        if self.gather in ("p2p", "p2p8"):
             if self.rank != 0:
                 self.engine.frame_signal(self.rank, self.frame_no)
             else:
@@ -209,5 +217,5 @@ class ShardedFrame:
 
     def release(self):
         """Rank 0, after everything that reads the gathered frame has been enqueued: lets the other ranks overwrite it."""
-        if self.gather == "p2p" and self.rank == 0:
+        if self.gather in ("p2p", "p2p8") and self.rank == 0:
             self.engine.frame_signal(0, self.frame_no)

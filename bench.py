@@ -316,6 +316,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    issue_ms = []
+
     def timed(step_fn, steps, warmup, per_step_events=False):
         for _ in range(warmup):
             step_fn()
@@ -328,6 +330,7 @@ def main():
         for _ in range(steps):
             step_fn()
         e1.record(stream)
+        issue_ms.append((time.time() - t0) * 1e3 / steps)   # host time to ISSUE a step (no sync): close to ms/step = launch-bound
         barrier()
         t1 = time.time()
         ms = e0.elapsed_time(e1)
@@ -428,6 +431,7 @@ def main():
                              "by construction (SURVEY §8d); see profiles/ for L2 hit rate and warp execution efficiency"},
         "clocks": clocks,
         "gpu_launches": int(launches),
+        "host_issue_ms_per_step": round(issue_ms[0], 4) if issue_ms else None,
     }
     if e2e:
         line["e2e"] = e2e

@@ -6,7 +6,7 @@ for l in sys.stdin:
     l=l.strip()
     if l.startswith("{"):
         d=json.loads(l); r=d.get("roofline",{})
-        print(round(d["value"]),d["unit"],round(d["ms_per_step"],3),"ms/step kernel_ms",round(r.get("kernel_ms",0),3), r.get("kernel_ms_split"), "frac",round(r.get("frac",0),4), "e2e", round((d.get("e2e") or {}).get("value") or 0), round((d.get("e2e") or {}).get("ms_per_step") or 0,3))
+        print(round(d["value"]),d["unit"],round(d["ms_per_step"],3),"ms/step kernel_ms",round(r.get("kernel_ms",0),3), r.get("kernel_ms_split"), "frac",round(r.get("frac",0),4), "e2e", round((d.get("e2e") or {}).get("value") or 0), round((d.get("e2e") or {}).get("ms_per_step") or 0,3), "issue_ms", d.get("host_issue_ms_per_step"))
     else: print(l)
 '
 while [ $# -gt 0 ]; do

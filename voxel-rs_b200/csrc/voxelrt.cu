@@ -41,6 +41,9 @@ struct VxCtx {
     uint8_t* h_stage = nullptr;       // pinned staging ring for async dirty uploads
     size_t stage_cap = 0;
     uint64_t hot_off = 0, hot_len = 0;
+    bool l2_installed = false;
+    uint64_t l2_off = 0, l2_len = 0, l2_opt = 0;
+    cudaStream_t l2_render = nullptr, l2_picker = nullptr;
     bool have_svo = false;
 
     Material* d_materials = nullptr;
@@ -346,6 +349,11 @@ int vx_svo_set_hot_range(VxCtx* c, uint64_t offset, uint64_t length) {
 
 // Persisting-L2 access-policy window over [preamble .. world-root octree] on the render/picker streams.
 static void install_l2_window(VxCtx* c) {
+    // (re)installed only when the window or the streams changed: cudaDeviceSetLimit + two stream attributes per commit were
+    // tens of microseconds of host time on every frame of the multi-GPU loop
+    if (c->l2_installed && c->l2_off == c->hot_off && c->l2_len == c->hot_len && c->l2_opt == c->opt_l2_window && c->l2_render == c->s_render &&
+        c->l2_picker == c->s_picker) return;
+    c->l2_installed = true; c->l2_off = c->hot_off; c->l2_len = c->hot_len; c->l2_opt = c->opt_l2_window; c->l2_render = c->s_render; c->l2_picker = c->s_picker;
     cudaStreamAttrValue attr{};
     if (c->opt_l2_window && c->hot_len) {
         int max_win = 0, max_persist = 0;

@@ -271,6 +271,26 @@ int vx_debug_cast(VxCtx* ctx, const float pos[3], const float dir[3], float max_
                   uint32_t cast_translucent, VxOctreeResult* result,
                   VxDebugFrame* frames, uint32_t frames_cap, uint32_t* n_frames);
 
+/* ---- chunk serialization on the GPU (reference: SerializedChunk::new + serialize_octant,
+ * src/world/hds/esvo.rs:353-383, 439-512, run by the job system in src/systems/worldsvo.rs:90-99) ----
+ * blocks: n_chunks dense 32^3 BlockId arrays (index x + 32*(y + 32*z), 0 = air), HOST or DEVICE memory. lods: one byte per chunk
+ * (0 = full detail), host memory, may be NULL. The records of chunk i (12-word octant records, depth-first, byte-identical to the
+ * host serializer) land at infos_out[i].offset_bytes of the context's scratch buffer; chunks are laid out in completion order.
+ * child_mask / leaf_mask / depth = the SerializationResult of the chunk's root octant (what Esvo::serialize_root needs,
+ * esvo.rs:151-175). records_out (host, optional) receives the *total_bytes of records. */
+typedef struct VxChunkInfo {
+    uint64_t offset_bytes;
+    uint64_t length_bytes;
+    uint8_t  child_mask, leaf_mask, depth, _pad[5];
+} VxChunkInfo;
+int vx_serialize_chunks_esvo(VxCtx* ctx, const uint32_t* blocks, uint32_t n_chunks, const uint8_t* lods, VxChunkInfo* infos_out,
+                             void* records_out, uint64_t records_capacity, uint64_t* total_bytes);
+/* Device pointer of the records of the last vx_serialize_chunks_esvo and its kernel time (CUDA events). */
+int vx_serialize_chunks_result(VxCtx* ctx, void** records_dev, float* kernel_ms);
+/* Copies `length` bytes of device memory (records built on the GPU) into the world buffer at RangeBuffer offset `range_offset`,
+ * ordered like vx_svo_commit (after the frame in flight, before the next one): dirty chunks without a host round trip. */
+int vx_svo_write_device(VxCtx* ctx, uint64_t range_offset, const void* src_dev, uint64_t length);
+
 /* ---- multi-GPU plumbing (no reference counterpart: the reference is single-GPU) ----
  * One process per GPU. Each rank renders its VxShard into its own full-size framebuffer; the shard's
  * pixels are then packed into a contiguous device buffer ([owned macro block][16 rows][32 px] RGBA32F),

@@ -554,3 +554,54 @@ def test_csvo_render_terrain(pkg, ora):
         svo.close()
     differing = (np.abs(frames[0] - frames[1]).max(axis=2) > 0).mean()
     assert differing < 1e-3, differing
+
+
+# ------------------------------------------------------------------------------------- chunk serialization on the GPU --
+
+def test_gpu_chunk_serialization_matches_host(pkg):
+    """vx_serialize_chunks_esvo against the host serializer (itself pinned on esvo.rs:561-1228): random chunks
+    of every density at every LOD, then every chunk of a generated-terrain world against the bytes the host put into its
+    RangeBuffer; the chunk's SerializationResult (child mask, leaf mask, depth) included."""
+    reg = helpers.shader_test_registry(pkg)
+    svo = pkg.Svo(reg, size_mb=1, max_width=8, max_height=8, max_rays=8)
+    rng = np.random.default_rng(21)
+    blocks, lods = [], []
+    for density in (0.0, 0.0005, 0.02, 0.3, 0.9, 1.0):
+        for lod in (0, 1, 2, 3, 4, 5):
+            blocks.append(((rng.random(32768) < density) * rng.integers(1, 1 << 20, 32768)).astype(np.uint32))
+            lods.append(lod)
+    corner = np.zeros(32768, np.uint32); corner[31] = 1; corner[31 * 32] = 2; corner[31 * 1024] = 3      # the reference's KAT chunk
+    blocks.append(corner); lods.append(5)
+    blocks = np.stack(blocks)
+    infos, rec, ms = svo.serialize_chunks(blocks, lods)
+    assert ms > 0
+    # ranges are disjoint and tile the output
+    order = np.argsort(infos["offset_bytes"], kind="stable")
+    nz = [i for i in order if infos["length_bytes"][i] > 0]
+    assert sum(int(infos["length_bytes"][i]) for i in nz) == len(rec)
+    end = 0
+    for i in nz:
+        assert int(infos["offset_bytes"][i]) == end
+        end += int(infos["length_bytes"][i])
+    out = np.zeros(4681 * 12, dtype=np.uint32)
+    res = (C.c_uint8 * 3)()
+    for i in range(len(blocks)):
+        n = pkg.host().vxh_serialize_dense(blocks[i].ctypes.data, lods[i], out.ctypes.data, len(out), res)
+        o, l = int(infos["offset_bytes"][i]), int(infos["length_bytes"][i])
+        assert l == n * 4, (i, lods[i], l, n * 4)
+        assert rec[o:o + l].tobytes() == out[:n].tobytes(), (i, lods[i])
+        assert (infos["child_mask"][i], infos["leaf_mask"][i], infos["depth"][i]) == tuple(res), (i, lods[i])
+    # a whole generated world: the GPU redoes what the host's job system did for every chunk
+    world = pkg.World(radius=8, center=(-1, 2, 5), seed=1)      # LOD 5 within 6 chunks of the centre, LOD 4 beyond (chunkloader.rs:127-134)
+    world.generate(0, 8)
+    world.serialize()
+    image = world.range_bytes()
+    chunks = world.chunks()
+    cb = [world.chunk_blocks(c) for c in chunks]
+    infos, rec, _ = svo.serialize_chunks(np.stack([b for b, _ in cb]), [l for _, l in cb])
+    assert len(chunks) > 100 and len({l for _, l in cb}) > 1          # several LODs present
+    for c, info in zip(chunks, infos):
+        off, length = world.chunk_range(c)
+        assert int(info["length_bytes"]) == length
+        assert rec[int(info["offset_bytes"]):int(info["offset_bytes"]) + length].tobytes() == image[off:off + length].tobytes(), tuple(c)
+    svo.close()

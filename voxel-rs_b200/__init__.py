@@ -63,6 +63,15 @@ class VxRange(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("length", C.c_uint64)]
 
 
+class VxChunkInfo(C.Structure):
+    _fields_ = [("offset_bytes", C.c_uint64), ("length_bytes", C.c_uint64), ("child_mask", C.c_uint8), ("leaf_mask", C.c_uint8),
+                ("depth", C.c_uint8), ("_pad", C.c_uint8 * 5)]
+
+
+CHUNK_INFO_DTYPE = np.dtype([("offset_bytes", "<u8"), ("length_bytes", "<u8"), ("child_mask", "u1"), ("leaf_mask", "u1"), ("depth", "u1"),
+                             ("_pad", "u1", 5)])
+
+
 class VxDebugFrame(C.Structure):
     _fields_ = [("t_min", C.c_float), ("ptr", C.c_uint32), ("idx", C.c_uint32), ("parent_octant_idx", C.c_uint32),
                 ("scale", C.c_int32), ("is_child", C.c_int32), ("is_leaf", C.c_int32), ("crossed_boundary", C.c_int32),
@@ -109,6 +118,7 @@ VX_SYMBOLS = [
     "vx_frame_ipc_handle", "vx_open_peer_frame", "vx_close_peer_frame", "vx_render_read_rgba8",
     "vx_sync_ipc_handle", "vx_open_peer_sync", "vx_close_peer_sync", "vx_frame_signal", "vx_frame_wait", "vx_frame_gate",
     "vx_frame_sync_errors", "vx_frame8_ipc_handle", "vx_open_peer_frame8",
+    "vx_serialize_chunks_esvo", "vx_serialize_chunks_result", "vx_svo_write_device",
 ]
 
 _lib = None
@@ -166,6 +176,9 @@ def lib():
     L.vx_frame_ipc_handle.argtypes = [P, P]; L.vx_frame_ipc_handle.restype = C.c_int
     L.vx_open_peer_frame.argtypes = [P, P]; L.vx_open_peer_frame.restype = C.c_int
     L.vx_close_peer_frame.argtypes = [P]; L.vx_close_peer_frame.restype = C.c_int
+    L.vx_serialize_chunks_esvo.argtypes = [P, P, C.c_uint32, P, P, P, C.c_uint64, C.POINTER(C.c_uint64)]; L.vx_serialize_chunks_esvo.restype = C.c_int
+    L.vx_serialize_chunks_result.argtypes = [P, C.POINTER(P), C.POINTER(C.c_float)]; L.vx_serialize_chunks_result.restype = C.c_int
+    L.vx_svo_write_device.argtypes = [P, C.c_uint64, P, C.c_uint64]; L.vx_svo_write_device.restype = C.c_int
     L.vx_frame8_ipc_handle.argtypes = [P, P]; L.vx_frame8_ipc_handle.restype = C.c_int
     L.vx_open_peer_frame8.argtypes = [P, P]; L.vx_open_peer_frame8.restype = C.c_int
     L.vx_sync_ipc_handle.argtypes = [P, P]; L.vx_sync_ipc_handle.restype = C.c_int
@@ -216,6 +229,9 @@ def host():
         "vxh_kat_block_octree": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P], u64),
         "vxh_kat_csvo_octant": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P, u32, C.POINTER(u32)], u64),
         "vxh_csvo_dense_equals_generic": ([P, C.c_uint8], C.c_int),
+        "vxh_world_chunk_list": ([P, P, u64], u64),
+        "vxh_world_fill_chunk": ([P, i32, i32, i32, P], C.c_int),
+        "vxh_world_chunk_range": ([P, i32, i32, i32, C.POINTER(VxRange)], C.c_int),
         "vxh_world_csvo_root_offset": ([P], u64),
         "vxh_world_range_bytes": ([P, P, u64], u64),
         "vxh_serialize_dense": ([P, C.c_uint8, P, u64, P], u64),
@@ -335,6 +351,30 @@ class World:
 
     def height_at(self, x, z):
         return host().vxh_world_height_at(self.h, x, z)
+
+    def chunks(self):
+        """World chunk coordinates of the loaded chunks."""
+        n = host().vxh_world_chunk_list(self.h, None, 0)
+        a = np.zeros((n, 3), dtype=np.int32)
+        host().vxh_world_chunk_list(self.h, _ptr(a), n)
+        return a
+
+    def chunk_blocks(self, c):
+        """(dense 32^3 uint32 block array, lod) the chunk was serialized from (terrain + edits)."""
+        b = np.zeros(32768, dtype=np.uint32)
+        lod = host().vxh_world_fill_chunk(self.h, int(c[0]), int(c[1]), int(c[2]), _ptr(b))
+        return b, lod
+
+    def chunk_range(self, c):
+        r = VxRange()
+        ok = host().vxh_world_chunk_range(self.h, int(c[0]), int(c[1]), int(c[2]), C.byref(r))
+        return (r.offset, r.length) if ok else None
+
+    def range_bytes(self):
+        n = host().vxh_world_range_bytes(self.h, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        host().vxh_world_range_bytes(self.h, _ptr(out), n)
+        return out
 
     def dirty_ranges(self):
         n = host().vxh_world_dirty_ranges(self.h, None, 0)
@@ -643,6 +683,23 @@ class Svo:
         buf = (C.c_uint8 * 64)()
         self._check(lib().vx_frame_ipc_handle(self.ctx, buf))
         return bytes(buf)
+
+    def serialize_chunks(self, blocks, lods=None, want_records=True, blocks_ptr=None, n_chunks=None):
+        """vx_serialize_chunks_esvo. blocks: (n, 32768) uint32 host array, or pass blocks_ptr (device pointer) + n_chunks.
+        Returns (infos [CHUNK_INFO_DTYPE], records uint8 array or None, kernel_ms)."""
+        if blocks_ptr is None:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint32).reshape(-1, 32768)
+            n_chunks, blocks_ptr = len(blocks), blocks.ctypes.data
+        infos = np.zeros(n_chunks, dtype=CHUNK_INFO_DTYPE)
+        lods_a = np.ascontiguousarray(lods, dtype=np.uint8) if lods is not None else None
+        total = C.c_uint64()
+        cap = n_chunks * 4681 * 48 if want_records else 0
+        rec = np.zeros(cap, dtype=np.uint8) if want_records else None
+        self._check(lib().vx_serialize_chunks_esvo(self.ctx, C.c_void_p(blocks_ptr), n_chunks, _ptr(lods_a) if lods_a is not None else None,
+                                                   _ptr(infos), _ptr(rec) if rec is not None else None, cap, C.byref(total)))
+        ms = C.c_float()
+        self._check(lib().vx_serialize_chunks_result(self.ctx, None, C.byref(ms)))
+        return infos, (rec[:total.value] if rec is not None else None), ms.value
 
     def frame8_ipc_handle(self):
         buf = (C.c_uint8 * 64)()

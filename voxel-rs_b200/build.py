@@ -33,7 +33,7 @@ def _newer(target, sources):
 
 def build_cuda(force=False, verbose=False):
     src = os.path.join(PKG, "csrc", "voxelrt.cu")
-    deps = [src, os.path.join(PKG, "csrc", "traverse.cuh"), os.path.join(PKG, "csrc", "kernels.cuh"), os.path.join(ROOT, "include", "voxelrt.h")]
+    deps = [src, os.path.join(PKG, "csrc", "traverse.cuh"), os.path.join(PKG, "csrc", "kernels.cuh"), os.path.join(PKG, "csrc", "chunks.cuh"), os.path.join(ROOT, "include", "voxelrt.h")]
     out = os.path.join(PKG, "libvoxelrt.so")
     if not force and not _newer(out, deps):
         return out

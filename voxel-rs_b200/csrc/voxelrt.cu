@@ -14,6 +14,7 @@
 
 #include "../../include/voxelrt.h"
 #include "kernels.cuh"
+#include "chunks.cuh"
 
 // ================================================================== host ==
 
@@ -80,6 +81,13 @@ struct VxCtx {
     unsigned long long* d_work = nullptr;   // [0] render strip counter (low 32 bits used), [1] picker run counter
     VxFrameStats last_render{}, last_raycast{};
     bool render_timed = false, raycast_timed = false;
+
+    // chunk serialization scratch (vx_serialize_chunks_esvo)
+    uint32_t* d_chunk_in = nullptr; size_t chunk_in_cap = 0;
+    uint32_t* d_chunk_out = nullptr; size_t chunk_out_cap = 0;
+    ChunkOut* d_chunk_info = nullptr; uint8_t* d_chunk_lod = nullptr; size_t chunk_n_cap = 0;
+    cudaEvent_t t0_chunk = nullptr, t1_chunk = nullptr;
+    float last_chunk_ms = 0.0f;
 
     VxStats stats{};
     uint64_t launches = 0;
@@ -228,6 +236,12 @@ void vx_destroy(VxCtx* c) {
     if (c->frame8_target) cudaIpcCloseMemHandle(c->frame8_target);
     if (c->flags_target) cudaIpcCloseMemHandle(c->flags_target);
     if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_chunk_in) cudaFree(c->d_chunk_in);
+    if (c->d_chunk_out) cudaFree(c->d_chunk_out);
+    if (c->d_chunk_info) cudaFree(c->d_chunk_info);
+    if (c->d_chunk_lod) cudaFree(c->d_chunk_lod);
+    if (c->t0_chunk) cudaEventDestroy(c->t0_chunk);
+    if (c->t1_chunk) cudaEventDestroy(c->t1_chunk);
     if (c->d_world_raw) cudaFree(c->d_world_raw);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -913,6 +927,94 @@ int vx_close_peer_frame(VxCtx* c) {
     if (c->frame_target) CU(c, cudaIpcCloseMemHandle(c->frame_target));
     if (c->frame8_target) CU(c, cudaIpcCloseMemHandle(c->frame8_target));
     c->frame_target = nullptr; c->frame8_target = nullptr;
+    return VX_OK;
+}
+
+// ---- chunk serialization on the GPU ---------------------------------------------------------------------
+static_assert(sizeof(ChunkOut) == sizeof(VxChunkInfo), "VxChunkInfo layout");
+
+int vx_serialize_chunks_esvo(VxCtx* c, const uint32_t* blocks, uint32_t n_chunks, const uint8_t* lods, VxChunkInfo* infos_out, void* records_out,
+                             uint64_t records_capacity, uint64_t* total_bytes) {
+    if (!c || !blocks || !n_chunks || !infos_out) return fail(c, VX_E_ARG, "vx_serialize_chunks_esvo: null/empty argument");
+    if (n_chunks > 16384) return fail(c, VX_E_CAPACITY, "vx_serialize_chunks_esvo: at most 16384 chunks per call");
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = c->s_upload;
+    if (!c->t0_chunk) { CU(c, cudaEventCreate(&c->t0_chunk)); CU(c, cudaEventCreate(&c->t1_chunk)); }
+    cudaPointerAttributes pa{};
+    const bool on_device = cudaPointerGetAttributes(&pa, blocks) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const size_t in_bytes = (size_t)n_chunks * 32768 * 4;
+    const uint32_t* d_in = blocks;
+    if (!on_device) {
+        if (c->chunk_in_cap < in_bytes) {
+            if (c->d_chunk_in) cudaFree(c->d_chunk_in);
+            c->d_chunk_in = nullptr; c->chunk_in_cap = 0;
+            CU(c, cudaMalloc(&c->d_chunk_in, in_bytes));
+            c->chunk_in_cap = in_bytes;
+        }
+        CU(c, cudaMemcpyAsync(c->d_chunk_in, blocks, in_bytes, cudaMemcpyHostToDevice, st));
+        d_in = c->d_chunk_in;
+    }
+    const size_t out_bytes = (size_t)n_chunks * 4681 * 48;   // every octant of every chunk present: the worst case
+    if (c->chunk_out_cap < out_bytes) {
+        if (c->d_chunk_out) cudaFree(c->d_chunk_out);
+        c->d_chunk_out = nullptr; c->chunk_out_cap = 0;
+        CU(c, cudaMalloc(&c->d_chunk_out, out_bytes));
+        c->chunk_out_cap = out_bytes;
+    }
+    if (c->chunk_n_cap < n_chunks) {
+        if (c->d_chunk_info) cudaFree(c->d_chunk_info);
+        if (c->d_chunk_lod) cudaFree(c->d_chunk_lod);
+        c->d_chunk_info = nullptr; c->d_chunk_lod = nullptr; c->chunk_n_cap = 0;
+        CU(c, cudaMalloc(&c->d_chunk_info, (size_t)n_chunks * sizeof(ChunkOut)));
+        CU(c, cudaMalloc(&c->d_chunk_lod, n_chunks));
+        c->chunk_n_cap = n_chunks;
+    }
+    if (lods) CU(c, cudaMemcpyAsync(c->d_chunk_lod, lods, n_chunks, cudaMemcpyHostToDevice, st));
+    unsigned long long* bump = c->d_work + 6;                       // [6] bump pointer (words), [7] overflow count
+    CU(c, cudaMemsetAsync(bump, 0, 16, st));
+    CU(c, cudaFuncSetAttribute(serialize_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem)));
+    CU(c, cudaEventRecord(c->t0_chunk, st));
+    serialize_chunks_kernel<<<n_chunks, VX_CHUNK_THREADS, sizeof(ChunkSmem), st>>>(d_in, lods ? c->d_chunk_lod : nullptr, n_chunks, c->d_chunk_out,
+                                                                                   (unsigned long long)(c->chunk_out_cap / 4), bump,
+                                                                                   c->d_chunk_info, reinterpret_cast<unsigned int*>(bump + 1));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->t1_chunk, st));
+    unsigned long long h[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(h, bump, 16, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(infos_out, c->d_chunk_info, (size_t)n_chunks * sizeof(ChunkOut), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    CU(c, cudaEventElapsedTime(&c->last_chunk_ms, c->t0_chunk, c->t1_chunk));
+    if ((unsigned int)h[1]) return fail(c, VX_E_CAPACITY, "vx_serialize_chunks_esvo: output scratch overflow");
+    const uint64_t total = h[0] * 4ull;
+    if (total_bytes) *total_bytes = total;
+    if (records_out) {
+        if (total > records_capacity) return fail(c, VX_E_CAPACITY, "vx_serialize_chunks_esvo: %llu bytes of records, %llu given", (unsigned long long)total,
+                                                  (unsigned long long)records_capacity);
+        CU(c, cudaMemcpyAsync(records_out, c->d_chunk_out, total, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+    }
+    return VX_OK;
+}
+
+int vx_serialize_chunks_result(VxCtx* c, void** records_dev, float* kernel_ms) {
+    if (!c) return VX_E_ARG;
+    if (records_dev) *records_dev = c->d_chunk_out;
+    if (kernel_ms) *kernel_ms = c->last_chunk_ms;
+    return VX_OK;
+}
+
+int vx_svo_write_device(VxCtx* c, uint64_t range_offset, const void* src_dev, uint64_t length) {
+    if (!c || !src_dev) return fail(c, VX_E_ARG, "vx_svo_write_device: null argument");
+    if (range_offset + length + c->head > c->cfg.svo_capacity_bytes)
+        return fail(c, VX_E_CAPACITY, "dst is not large enough: len=%llu range_start=%llu range_length=%llu", (unsigned long long)c->cfg.svo_capacity_bytes,
+                    (unsigned long long)range_offset, (unsigned long long)length);
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));
+    CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
+    CU(c, cudaMemcpyAsync(c->d_world + c->head + range_offset, src_dev, length, cudaMemcpyDeviceToDevice, c->s_upload));
+    CU(c, cudaEventRecord(c->e_upload, c->s_upload));
     return VX_OK;
 }
 

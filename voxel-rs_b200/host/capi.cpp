@@ -67,6 +67,34 @@ int vxh_world_set_leaf_dense(void* wp, uint32_t sx, uint32_t sy, uint32_t sz, ui
     VXH_CATCH(-1)
 }
 
+// The loaded chunks (world chunk coordinates), the dense 32^3 block array + LOD each one was serialized from, and where its
+// records live in the RangeBuffer: what a device-side serializer needs to redo the host's work and be compared with it.
+uint64_t vxh_world_chunk_list(void* wp, int32_t* xyz, uint64_t cap) {
+    WorldSvo* w = (WorldSvo*)wp;
+    uint64_t i = 0;
+    for (auto& kv : w->leaf_ids) {
+        if (i < cap) { xyz[3 * i] = std::get<0>(kv.first); xyz[3 * i + 1] = std::get<1>(kv.first); xyz[3 * i + 2] = std::get<2>(kv.first); }
+        ++i;
+    }
+    return i;
+}
+int vxh_world_fill_chunk(void* wp, int32_t cx, int32_t cy, int32_t cz, uint32_t* blocks) {   // returns the chunk's LOD, -1 if empty
+    WorldSvo* w = (WorldSvo*)wp;
+    ChunkPos p{cx, cy, cz};
+    std::vector<BlockId> b;
+    if (!w->fill_chunk(p, w->make_column(cx, cz), b)) return -1;
+    std::memcpy(blocks, b.data(), b.size() * sizeof(BlockId));
+    return (int)w->lod_for(p);
+}
+int vxh_world_chunk_range(void* wp, int32_t cx, int32_t cy, int32_t cz, VxRange* out) {
+    WorldSvo* w = (WorldSvo*)wp;
+    auto& m = w->range_buffer().id_to_range;
+    auto it = m.find(WorldSvo::chunk_uid(ChunkPos{cx, cy, cz}));
+    if (it == m.end()) return 0;
+    *out = VxRange{it->second.start, it->second.length};
+    return 1;
+}
+
 // world-space block edit on top of the terrain: re-serialises the owning chunk (dirty-range producer)
 int vxh_world_edit_block(void* wp, int32_t wx, int32_t wy, int32_t wz, uint32_t id) {
     VXH_TRY

@@ -58,8 +58,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--workload", default="frame", choices=["frame", "picker"], help="frame = BASELINE configs[2] (the metric's config, default); "
-                    "picker = configs[3], 16 Mi incoherent picker rays against an r=40 no-LOD world")
+    ap.add_argument("--workload", default="frame", choices=["frame", "picker", "serialize"], help="frame = BASELINE configs[2] (the metric's config, "
+                    "default); picker = configs[3], 16 Mi incoherent picker rays against an r=40 no-LOD world; serialize = SURVEY §8f n3, ESVO "
+                    "serialization of every chunk of the r=20 world on the GPU")
     ap.add_argument("--rays", type=int, default=1 << 24, help="picker workload: number of rays")
     ap.add_argument("--max-dst", type=float, default=-1.0, help="picker workload: max_dst of every task (-1 = unlimited)")
     return ap.parse_args()
@@ -206,6 +207,8 @@ def main():
         return run_reference(args)
     if args.workload == "picker":
         return run_picker(args)
+    if args.workload == "serialize":
+        return run_serialize(args)
 
     import torch
     import torch.distributed as dist
@@ -448,6 +451,81 @@ def main():
         dist.barrier()
         sf.close()
         dist.destroy_process_group()
+
+
+def run_serialize(args):
+    """--workload serialize = SURVEY §8f n3: every chunk of the generated r=20 world (dense 32^3 BlockId arrays + the LOD rule)
+    through vx_serialize_chunks_esvo. value = chunks/s with the block arrays resident in HBM; e2e = host block arrays -> H2D ->
+    kernel -> chunk infos back (records stay on the GPU, where the ray caster reads them); cpu_baseline = the host serializer
+    (the C++ restatement of SerializedChunk::new, pinned on esvo.rs:561-1228) on all host threads. Single GPU."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — no CPU fallback")
+    graft.build()
+    pkg = graft.load_pkg()
+    world, gen_s = build_world(pkg, args)
+    chunks = world.chunks()
+    cb = [world.chunk_blocks(c) for c in chunks]
+    blocks = np.stack([b for b, _ in cb])
+    lods = np.array([l for _, l in cb], dtype=np.uint8)
+    n = len(chunks)
+    reg = pkg.content_registry(pkg.load_atlas())
+    svo = pkg.Svo(reg, size_mb=1, max_width=8, max_height=8, max_rays=8)
+    b_host = torch.from_numpy(blocks.view(np.uint8).reshape(-1)).pin_memory()
+    b_dev = b_host.cuda()
+    flush_buf = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
+    infos, rec, _ = svo.serialize_chunks(blocks, lods)
+    out_bytes = len(rec)
+    # parity of the whole batch against the host's RangeBuffer image
+    image = world.range_bytes()
+    ok = all(rec[int(i["offset_bytes"]):int(i["offset_bytes"] + i["length_bytes"])].tobytes() ==
+             image[world.chunk_range(c)[0]:world.chunk_range(c)[0] + world.chunk_range(c)[1]].tobytes() for c, i in zip(chunks, infos))
+
+    def run(ptr, steps, warmup):
+        kms = []
+        for i in range(warmup + steps):
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            _, _, ms = svo.serialize_chunks(None, lods, want_records=False, blocks_ptr=ptr, n_chunks=n)
+            t = (time.time() - t0) * 1e3
+            if i >= warmup:
+                kms.append((ms, t))
+        return float(np.mean([k for k, _ in kms])), float(np.mean([t for _, t in kms]))
+
+    sampler = ClockSampler(0)
+    t0 = time.time()
+    kernel_ms, _ = run(b_dev.data_ptr(), args.steps, args.warmup)
+    clocks = sampler.stop(t0, time.time())
+    _, e2e_ms = run(b_host.data_ptr(), max(3, args.steps // 3), 2)
+    peak, peak_src = measured_peaks()
+    alg = blocks.nbytes + out_bytes                       # every block id read once, every record written once
+    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    threads = os.cpu_count() or 1
+    tc = time.time(); reps = 0
+    while time.time() - tc < min(args.cpu_seconds, 10.0) or reps < 2:
+        pkg.host().vxh_serialize_dense_batch(blocks.ctypes.data, n, lods.ctypes.data, threads)
+        reps += 1
+    cpu_s = (time.time() - tc) / reps
+    line = {
+        "metric": "chunks/s (ESVO chunk serialization)", "value": n / (kernel_ms * 1e-3), "unit": "chunks/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": f"ESVO serialization of the {n} chunks of the generated-terrain r={args.radius} world with the LOD rule (SURVEY §8f n3)",
+                   "in_bytes": int(blocks.nbytes), "out_bytes": int(out_bytes), "l2": "flushed before every launch (160 MiB fill)",
+                   "parity": "byte-identical to the host serializer's RangeBuffer image" if ok else "MISMATCH vs host serializer", "world_gen_s": round(gen_s, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "serialize_chunks_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg)},
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "chunks/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(blocks.nbytes + n),
+                "d2h_bytes_per_step": int(n * 24), "path": "pinned host block arrays -> H2D -> serialize_chunks_kernel -> chunk infos to host (records stay in HBM)"},
+        "cpu_baseline": {"value": n / cpu_s, "unit": "chunks/s", "cores": threads, "kind": "port",
+                         "sample": f"the same {n} chunks through the host serializer on {threads} threads x {reps} passes"},
+        "clocks": clocks, "gpu_launches": int(args.steps),
+    }
+    print(json.dumps(line), flush=True)
+    svo.close()
 
 
 def picker_tasks(pkg, world, radius, n, seed=0, max_dst=-1.0):

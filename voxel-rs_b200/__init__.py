@@ -229,6 +229,7 @@ def host():
         "vxh_kat_block_octree": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P], u64),
         "vxh_kat_csvo_octant": ([P, u32, C.c_uint8, C.c_int, C.c_uint8, P, u64, P, u32, C.POINTER(u32)], u64),
         "vxh_csvo_dense_equals_generic": ([P, C.c_uint8], C.c_int),
+        "vxh_serialize_dense_batch": ([P, u32, P, C.c_int], u64),
         "vxh_world_chunk_list": ([P, P, u64], u64),
         "vxh_world_fill_chunk": ([P, i32, i32, i32, P], C.c_int),
         "vxh_world_chunk_range": ([P, i32, i32, i32, C.POINTER(VxRange)], C.c_int),

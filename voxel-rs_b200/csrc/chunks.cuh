@@ -58,10 +58,17 @@ __global__ void __launch_bounds__(VX_CHUNK_THREADS) serialize_chunks_kernel(cons
     const uint32_t D = (lod == 0u || lod > 5u) ? 5u : lod;   // record levels: cell levels 5 .. 6 - D; their children at level 5 - D are the leaves
     const uint32_t kr = 6u - D, kl = 5u - D;
 
-    // 1. voxel occupancy: one warp per row of 32 voxels, a ballot per row
-    for (uint32_t row = warp; row < 1024u; row += VX_CHUNK_THREADS / 32) {
-        const unsigned m = __ballot_sync(0xffffffffu, __ldg(b + row * 32u + lane) != 0u);
-        if (lane == 0) sm.occ0[row] = m;
+    // 1. voxel occupancy: one warp per row of 32 voxels, a ballot per row; 8 rows are in flight per warp (the 128 KB of block
+    //    ids are the bulk of the kernel's HBM traffic: one outstanding 128-byte load per warp left the memory system idle)
+    for (uint32_t row0 = warp * 8u; row0 < 1024u; row0 += (VX_CHUNK_THREADS / 32) * 8u) {
+        uint32_t v[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) v[j] = __ldcs(b + (row0 + j) * 32u + lane);
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            const unsigned m = __ballot_sync(0xffffffffu, v[j] != 0u);
+            if (lane == 0) sm.occ0[row0 + j] = m;
+        }
     }
     __syncthreads();
     // 2. child masks, level 1 from the voxel bits, levels 2..5 from the level below

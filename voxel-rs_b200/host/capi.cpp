@@ -5,6 +5,8 @@
 #include <memory>
 #include <string>
 
+#include <atomic>
+#include <thread>
 #include "esvo.hpp"
 #include "picker.hpp"
 #include "svo.hpp"
@@ -93,6 +95,28 @@ int vxh_world_chunk_range(void* wp, int32_t cx, int32_t cy, int32_t cz, VxRange*
     if (it == m.end()) return 0;
     *out = VxRange{it->second.start, it->second.length};
     return 1;
+}
+
+// The CPU side of the chunk-serialization comparison: n dense chunks through serialize_dense_chunk on `threads` workers (the
+// reference runs SerializedChunk::new on its job-system threads, worldsvo.rs:90-99). Returns the total bytes of records.
+uint64_t vxh_serialize_dense_batch(const uint32_t* blocks, uint32_t n, const uint8_t* lods, int threads) {
+    if (threads < 1) threads = 1;
+    std::atomic<uint32_t> next{0};
+    std::atomic<uint64_t> total{0};
+    auto worker = [&]() {
+        std::vector<uint32_t> dst;
+        for (;;) {
+            uint32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            dst.clear();
+            serialize_dense_chunk(blocks + (size_t)i * 32768, dst, lods ? lods[i] : 0);
+            total.fetch_add(dst.size() * 4);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+    return total.load();
 }
 
 // world-space block edit on top of the terrain: re-serialises the owning chunk (dirty-range producer)

@@ -347,6 +347,12 @@ def main():
     svo.set_option(pkg.OPT_COUNT, 1)
     svo.render_raw(vxp, W, H, shard=shard)
     st = svo.frame_stats(0)
+    # the same frame without shadow rays: the primary-ray kernel's own step / push / leaf counts (the shadow kernel's = the difference)
+    import ctypes as C
+    vxp_ns = pkg.VxRenderParams.from_buffer_copy(bytes(vxp))
+    vxp_ns.render_shadows = 0
+    svo.render_raw(vxp_ns, W, H, shard=shard)
+    st_p = svo.frame_stats(0)
     svo.set_option(pkg.OPT_COUNT, 0)
     rays_local = st["primary_rays"] + st["shadow_rays"]
     if n_gpus > 1:
@@ -394,6 +400,20 @@ def main():
     peak, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes(st, pixels // n_gpus if n_gpus > 1 else pixels)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    # per kernel: node words + child pointers + leaf words, plus the wavefront records each kernel reads / writes
+    hits = st_p["leaf_tests"]                       # opaque worlds: one accepted leaf per hit pixel (upper bound otherwise)
+    px_local = st["primary_rays"]
+    shadow_entries = st["shadow_rays"]
+    k_alg = {
+        "trace_primary": 4 * st_p["steps"] + 4 * st_p["pushes"] + 4 * st_p["leaf_tests"] + 32 * min(hits, px_local) + 16 * max(px_local - hits, 0),
+        "shade": 32 * min(hits, px_local) + 16 * max(px_local - hits, 0) + 32 * min(hits, px_local) + 4 * st_p["tex_fetches"] +
+                 36 * shadow_entries + 16 * (px_local - shadow_entries),
+        "trace_shadow": 36 * shadow_entries + 4 * (st["steps"] - st_p["steps"]) + 4 * (st["pushes"] - st_p["pushes"]) +
+                        4 * (st["leaf_tests"] - st_p["leaf_tests"]) + 16 * shadow_entries,
+    }
+    per_kernel = {k: {"algorithmic_bytes_per_launch": int(v), "ms": split_ms[k], "achieved_gbs": round(v / (split_ms[k] * 1e-3) / 1e9, 1),
+                      "frac": round(v / (split_ms[k] * 1e-3) / 1e9 / peak, 4)} for k, v in k_alg.items() if split_ms[k] > 0}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
     traffic, issue = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -427,8 +447,9 @@ def main():
         },
         "frame_ms": ms_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": "trace_primary_kernel + shade_kernel + trace_shadow_kernel (one frame)",
+                     "peak_source": peak_src, "kernel": "trace_primary_kernel + shade_kernel + trace_shadow_kernel (one frame; SURVEY §8d formula)",
                      "kernel_ms": kernel_ms, "kernel_ms_split": split_ms, "issue": issue, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "dominant_kernel": (dict(per_kernel[dom], kernel=dom + "_kernel") if dom else None), "per_kernel": per_kernel,
                      "counts": {k: int(st[k]) for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")},
                      "note": "latency/divergence-bound pointer chasing: the SVO is L2-resident after first touch, so the HBM fraction is small "
                              "by construction (SURVEY §8d); see profiles/ for L2 hit rate and warp execution efficiency"},

@@ -605,3 +605,34 @@ def test_gpu_chunk_serialization_matches_host(pkg):
         assert int(info["length_bytes"]) == length
         assert rec[int(info["offset_bytes"]):int(info["offset_bytes"]) + length].tobytes() == image[off:off + length].tobytes(), tuple(c)
     svo.close()
+
+
+def test_world_rebuilt_from_gpu_serialized_chunks(pkg, terrain):
+    """Integration of the device-side serializer: the chunk records of a committed world are wiped on the GPU and put back from
+    vx_serialize_chunks_esvo output with vx_svo_write_device (device to device, no host round trip) at the ranges the host's
+    RangeBuffer assigned — the frame is byte-identical to the one rendered from the host-serialized buffer."""
+    import torch
+    world, reg = terrain
+    w, h = 480, 270
+    p = terrain_params(pkg, w, h)
+    svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
+    svo.render(p, w, h, world=world)
+    want = svo.read_rgba32f()
+    chunks = world.chunks()
+    zeros = torch.zeros(4681 * 48, dtype=torch.uint8, device="cuda")
+    for c in chunks:                                   # wipe every chunk's records (the world root stays): nothing to hit
+        off, length = world.chunk_range(c)
+        svo.svo_write_device(off, zeros.data_ptr(), length)
+    svo.render(p, w, h, world=world)
+    wiped = svo.read_rgba32f()
+    assert (wiped != want).any(axis=2).mean() > 0.3
+    cb = [world.chunk_blocks(c) for c in chunks]
+    infos, _, _ = svo.serialize_chunks(np.stack([b for b, _ in cb]), [l for _, l in cb], want_records=False)
+    base = svo.serialize_records_ptr()
+    for c, info in zip(chunks, infos):
+        off, length = world.chunk_range(c)
+        assert int(info["length_bytes"]) == length
+        svo.svo_write_device(off, base + int(info["offset_bytes"]), length)
+    svo.render(p, w, h, world=world)
+    assert svo.read_rgba32f().tobytes() == want.tobytes()
+    svo.close()

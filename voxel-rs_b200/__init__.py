@@ -702,6 +702,15 @@ class Svo:
         self._check(lib().vx_serialize_chunks_result(self.ctx, None, C.byref(ms)))
         return infos, (rec[:total.value] if rec is not None else None), ms.value
 
+    def serialize_records_ptr(self):
+        """Device pointer of the records of the last serialize_chunks call."""
+        p = C.c_void_p()
+        self._check(lib().vx_serialize_chunks_result(self.ctx, C.byref(p), None))
+        return p.value
+
+    def svo_write_device(self, range_offset, src_dev_ptr, length):
+        self._check(lib().vx_svo_write_device(self.ctx, range_offset, C.c_void_p(src_dev_ptr), length))
+
     def frame8_ipc_handle(self):
         buf = (C.c_uint8 * 64)()
         self._check(lib().vx_frame8_ipc_handle(self.ctx, buf))

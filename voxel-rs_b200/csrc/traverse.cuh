@@ -1,7 +1,8 @@
-// traverse.cuh — device-side ESVO ray traversal + shading for sm_100a.
+// traverse.cuh — device-side SVO ray traversal (ESVO and CSVO node formats) + shading for sm_100a.
 //
 // Behavioural contract = voxel-rs shaders (paths relative to tim-oster/voxel-rs):
-//   intersect_octree  assets/shaders/svo.esvo.glsl:50-393
+//   intersect_octree  assets/shaders/svo.esvo.glsl:50-393  (walk_step<VX_FMT_ESVO>)
+//   intersect_octree  assets/shaders/svo.csvo.glsl:171-509 (walk_step<VX_FMT_CSVO>, csvo_* node decode :25-150)
 //   trace_ray         assets/shaders/world.glsl:27-90
 //   get_sky_color     assets/shaders/world.glsl:92-108
 //   textureLod state  src/graphics/texture_array.rs:200-203

@@ -1,7 +1,7 @@
 // kernels.cuh — the __global__ entry points of libvoxelrt (sm_100a).
 //
 // A frame (world.glsl main()) is a WAVEFRONT of three kernels on one stream:
-//   trace_primary_kernel   primary rays: ray generation + ESVO traversal only -> one 32-byte hit record per pixel
+//   trace_primary_kernel   primary rays: ray generation + SVO traversal only -> one 32-byte hit record per pixel
 //   shade_kernel           one thread per pixel, straight-line: texture colour, highlight, normal map, lighting, sky;
 //                          writes final pixels, and for lit pixels appends a shadow-ray record to a compacted list
 //   trace_shadow_kernel    shadow rays of that list: the same traversal loop -> final pixel
@@ -12,11 +12,13 @@
 // and the big straight-line shading code is walked by all warps of an SM together.
 //
 // The traversal kernels are persistent: grid = SMs x resident CTAs, every warp loops
-//   refill   idle lanes take the next rays of the warp's current run of 128 (pixels of a 32x4 strip / list entries /
-//            tasks); when the run is used up lane 0 claims the next one with one atomicAdd and broadcasts it by shuffle;
+//   refill   idle lanes take the next rays of the warp's current run (the 32 pixels of an 8x4 warp tile / 32 shadow-list
+//            entries / 128 picker tasks); when the run is used up lane 0 claims the next one with one atomicAdd and
+//            broadcasts it by shuffle;
 //   walk     all lanes step their ray in lock-step; a warp vote after every step leaves the loop once fewer than
 //            `refill_threshold` lanes are still walking;
 //   events   finished lanes write their result and become idle.
+// All of them are compiled per node format (template <int FMT>: VX_FMT_ESVO / VX_FMT_CSVO).
 #pragma once
 #include "../../include/voxelrt.h"
 #include "traverse.cuh"

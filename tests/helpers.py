@@ -79,3 +79,25 @@ def random_tasks(pkg, n, lo, hi, max_dst, seed=0):
     d = rng.normal(size=(n, 3)).astype(np.float32)
     t["dir"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     return t
+
+
+MC_CENTER = (-69, 1, 52)   # engine chunk at the middle of the fixture area
+
+
+def mc_world(pkg, fmt=0):
+    """The reference's bundled Minecraft world (tests/golden/mc_world.npz, made by make_mc_fixture.py) as a world SVO:
+    166 engine chunks around MC_CENTER at full detail, set the way systems::worldsvo::Svo::set_chunk does."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_world.npz"))
+    w = pkg.World(radius=6, center=MC_CENTER, seed=1, fmt=fmt)   # 9 x 8 columns: the corner (4, 4) is inside the radius-6 disc
+    for uid, (c, b) in enumerate(zip(z["coords"], z["blocks"])):
+        sp = w.cnv_chunk_pos(tuple(int(v) for v in c))
+        assert sp is not None
+        w.set_leaf_dense(sp, b.astype(np.uint32), uid=1000 + uid, lod=5)
+    w.serialize()
+    return w
+
+
+def mc_params(pkg, w, h, shadows=False):
+    """Fixed camera of the BASELINE configs[0] frame: over the water, looking at a wooded island (leaves, logs, grass, sand)."""
+    return pkg.render_params(cam_pos=(-2090.0, 75.0, 1690.0), cam_fwd=(0.6, -0.4, 1.0), fov_y_deg=72.0, aspect=w / h, render_shadows=shadows)

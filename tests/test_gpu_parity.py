@@ -636,3 +636,38 @@ def test_world_rebuilt_from_gpu_serialized_chunks(pkg, terrain):
     svo.render(p, w, h, world=world)
     assert svo.read_rgba32f().tobytes() == want.tobytes()
     svo.close()
+
+
+# ------------------------------------------------------------------ BASELINE configs[0]: the bundled Minecraft world --
+
+def test_mc_world_1280x720_primary_frame(pkg, ora):
+    """configs[0]: fixed test world from assets/worlds (tests/golden/mc_world.npz), SVO serialized on the CPU, one 1280x720
+    primary-ray frame from a fixed camera, no shadows, diffed against the reference shader's restatement: RGB8 within 1 LSB,
+    ray / step / push / leaf / texel counters identical. Then the same frame with shadow rays, the CSVO build of the same
+    world, and 200 k random picker rays through forest and water (translucent pass-through) byte-identical."""
+    reg = pkg.content_registry(pkg.load_atlas())
+    W, H = 1280, 720
+    for fmt in (0, 1):
+        world = helpers.mc_world(pkg, fmt)
+        svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=W, h=H, rays=1 << 18)
+        svo.set_option(pkg.OPT_COUNT, 1)
+        for shadows in (False, True):
+            p = helpers.mc_params(pkg, W, H, shadows=shadows)
+            got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, W, H, svo=svo, use_world=True)
+            assert_frames_match(got, got8, want, want8)
+            st = svo.frame_stats(0)
+            for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+                assert st[k] == cnt[k], (fmt, shadows, k, st, cnt)
+            assert cnt["primary_rays"] == W * H and (cnt["shadow_rays"] > 0) == shadows
+        # picker rays from inside the fixture's volume (SVO space: chunks 1..9 x 4..6 x 1..8 of the 13^3 window)
+        s = helpers.oracle_scene(ora, world, reg)
+        rng = np.random.default_rng(17)
+        tasks = helpers.random_tasks(pkg, 200_000, 0.0, 1.0, -1.0, seed=17)
+        tasks["pos"] = np.stack([rng.uniform(64, 288, 200_000), rng.uniform(5 * 32 + 20, 6 * 32 + 40, 200_000), rng.uniform(64, 256, 200_000)],
+                                axis=1).astype(np.float32)
+        tasks["max_dst"][::2] = 48.0
+        want_r, ocnt = s.raycast(tasks)
+        got_r = svo.raycast_tasks(tasks)
+        assert got_r.tobytes() == want_r.tobytes(), (fmt, int((got_r["dst"] != want_r["dst"]).sum()))
+        assert 0.2 < (got_r["dst"] > 0).mean() < 0.95
+        svo.close()

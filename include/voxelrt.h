@@ -241,7 +241,8 @@ int vx_render(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t
 /* graphics::Svo::render + Framebuffer::read_pixels (svo.rs:196-229 + framebuffer.rs:97-105) in one pipelined call: the frame is
  * rendered in `bands` bands of macro-block rows; each finished band is converted to RGBA8 and copied to the HOST buffer
  * rgba8_out (width*height*4 bytes, row 0 = bottom; pinned memory for the copy to overlap) while the next band is traced.
- * Returns when the whole frame is in rgba8_out. bands is clamped to 1..16. */
+ * Returns when the whole frame is in rgba8_out. bands is clamped to 1..16. The kernels store the RGBA8 pixels directly
+ * (bit-identical to vx_render + vx_read_frame_rgba8); the RGBA32F frame is NOT produced by this call. */
 int vx_render_read_rgba8(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
                          const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
 

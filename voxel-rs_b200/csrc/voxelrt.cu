@@ -39,7 +39,8 @@ struct VxCtx {
     uint8_t* d_world_raw = nullptr;   // allocation; GL byte 0 lives at d_world_raw + 8 so that records are 16-B aligned
     uint8_t* d_world = nullptr;
     uint8_t* h_mirror = nullptr;      // pinned, capacity bytes
-    uint8_t* h_stage = nullptr;       // pinned staging ring for async dirty uploads
+    uint8_t* h_stage = nullptr;       // pinned staging block for async dirty uploads
+    uint8_t* d_stage = nullptr;       // its device twin (allocated on first use)
     size_t stage_cap = 0;
     uint64_t hot_off = 0, hot_len = 0;
     bool l2_installed = false;
@@ -56,6 +57,7 @@ struct VxCtx {
 
     float4* d_frame = nullptr;
     uint32_t* d_frame8 = nullptr;
+    bool frame32_stale = false;       // the last frame was rendered as RGBA8 only (vx_render_read_rgba8 / option 8)
     uint32_t frame_w = 0, frame_h = 0;
     float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_open_peer_frame)
     uint32_t* frame8_target = nullptr;    // RGBA8 output mode (vx_set_option 8): d_frame8, or a peer GPU's RGBA8 frame (vx_open_peer_frame)
@@ -245,6 +247,7 @@ void vx_destroy(VxCtx* c) {
     if (c->d_world_raw) cudaFree(c->d_world_raw);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_materials) cudaFree(c->d_materials);
     if (c->d_texels) cudaFree(c->d_texels);
     if (c->d_texinfo) cudaFree(c->d_texinfo);
@@ -405,7 +408,9 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
     }
     CU(c, cudaSetDevice(c->cfg.device));
     std::memcpy(c->h_mirror, &octree_scale, 4);                                  // svo.rs:173-175
-    const bool staged = total + c->head <= c->stage_cap;
+    bool word_aligned = true;   // the scatter kernel moves 32-bit words (every range the serializers produce is word-aligned for ESVO)
+    for (uint32_t i = 0; i < n_dirty; ++i) word_aligned = word_aligned && (dirty[i].offset % 4 == 0) && (dirty[i].length % 4 == 0);
+    const bool staged = word_aligned && total + c->head + (uint64_t)n_dirty * sizeof(VxRange) <= c->stage_cap;
     // the staging block is reused: the previous upload must have drained it (normally long done)
     if (n_dirty && staged) CU(c, cudaStreamSynchronize(c->s_upload));
     // do not tear a frame / ray batch in flight (render_fence.wait(), svo.rs:178) — on the GPU timeline, not the CPU's
@@ -413,17 +418,26 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
     if (n_dirty) {
         if (staged) {
-            // the caller may rewrite the mirror as soon as we return: snapshot the dirty bytes into the pinned
-            // staging block and copy from there asynchronously
-            size_t off = 0;
-            std::memcpy(c->h_stage, c->h_mirror, c->head);
-            CU(c, cudaMemcpyAsync(c->d_world, c->h_stage, c->head, cudaMemcpyHostToDevice, c->s_upload));
-            off = c->head;
+            // the caller may rewrite the mirror as soon as we return: snapshot the dirty bytes into the pinned staging block,
+            // packed as [n VxRange headers | head bytes | range bytes...], move it with ONE async DMA and let the scatter kernel
+            // put the ranges in place (one copy + one launch instead of a DMA per range)
+            const size_t hdr_bytes = (size_t)n_dirty * sizeof(VxRange);
+            if (hdr_bytes + c->head + total > c->stage_cap) return fail(c, VX_E_CAPACITY, "vx_svo_commit: %u dirty ranges do not fit the staging block", n_dirty);
+            if (!c->d_stage) CU(c, cudaMalloc(&c->d_stage, c->stage_cap));
+            std::memcpy(c->h_stage, dirty, hdr_bytes);
+            size_t off = hdr_bytes;
+            std::memcpy(c->h_stage + off, c->h_mirror, c->head);
+            off += c->head;
             for (uint32_t i = 0; i < n_dirty; ++i) {
                 std::memcpy(c->h_stage + off, c->h_mirror + c->head + dirty[i].offset, dirty[i].length);
-                CU(c, cudaMemcpyAsync(c->d_world + c->head + dirty[i].offset, c->h_stage + off, dirty[i].length, cudaMemcpyHostToDevice, c->s_upload));
                 off += dirty[i].length;
             }
+            CU(c, cudaMemcpyAsync(c->d_stage, c->h_stage, off, cudaMemcpyHostToDevice, c->s_upload));
+            const unsigned long long pb = c->head + total;
+            const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
+            scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, c->d_stage, n_dirty, pb, (uint32_t)(c->head / 4));
+            c->launches++;
+            CU(c, cudaGetLastError());
         } else {
             CU(c, cudaMemcpyAsync(c->d_world, c->h_mirror, c->head, cudaMemcpyHostToDevice, c->s_upload));
             for (uint32_t i = 0; i < n_dirty; ++i)
@@ -647,6 +661,7 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
     CU(c, cudaEventRecord(c->t0_render, c->s_render));
     rc = launch_wavefront(c, a, p->render_shadows != 0, 0, 0, a.macro_y, true);
     if (rc) return rc;
+    c->frame32_stale = c->opt_rgba8_out != 0;
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
@@ -669,6 +684,8 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
     if (rc) return rc;
     if (c->frame_target || c->frame8_target) return fail(c, VX_E_STATE, "vx_render_read_rgba8: a peer frame is open (pixels are not written locally)");
+    a.frame8 = c->d_frame8;   // the caller wants RGBA8: the shade / shadow kernels store the rounded pixels themselves (same bytes as
+                              // converting the RGBA32F frame, a quarter of the frame traffic, no conversion pass)
     if (bands < 1) bands = 1;
     if (bands > VX_MAX_BANDS) bands = VX_MAX_BANDS;
     if (bands > a.macro_y) bands = a.macro_y;
@@ -698,11 +715,6 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
         if (rc) return rc;
         const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
         const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
-        if (!c->opt_rgba8_out) {
-            rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame + px0, c->d_frame8 + px0, n);
-            c->launches++;
-            CU(c, cudaGetLastError());
-        }
         CU(c, cudaEventRecord(c->e_band[b], c->s_render));
         CU(c, cudaStreamWaitEvent(c->s_copy, c->e_band[b], 0));
         CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
@@ -711,6 +723,7 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
     c->render_timed = false;
+    c->frame32_stale = true;
     CU(c, cudaStreamSynchronize(c->s_copy));
     return VX_OK;
 }
@@ -724,7 +737,8 @@ int vx_render_wait(VxCtx* c) {
 
 int vx_read_frame_rgba32f(VxCtx* c, float* out) {
     if (!c || !out || !c->frame_w) return fail(c, VX_E_ARG, "vx_read_frame_rgba32f: nothing rendered / null");
-    if (c->opt_rgba8_out) return fail(c, VX_E_STATE, "vx_read_frame_rgba32f: the context renders RGBA8 only (vx_set_option 8)");
+    if (c->opt_rgba8_out || c->frame32_stale)
+        return fail(c, VX_E_STATE, "vx_read_frame_rgba32f: the last frame was rendered as RGBA8 only (vx_set_option 8 / vx_render_read_rgba8)");
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaMemcpyAsync(out, c->d_frame, (size_t)c->frame_w * c->frame_h * sizeof(float4), cudaMemcpyDeviceToHost, c->s_render));
     CU(c, cudaStreamSynchronize(c->s_render));
@@ -735,7 +749,7 @@ int vx_read_frame_rgba8(VxCtx* c, uint8_t* out) {
     if (!c || !out || !c->frame_w) return fail(c, VX_E_ARG, "vx_read_frame_rgba8: nothing rendered / null");
     CU(c, cudaSetDevice(c->cfg.device));
     const unsigned long long n = (unsigned long long)c->frame_w * c->frame_h;
-    if (!c->opt_rgba8_out) {   // in RGBA8 output mode the kernels already stored the rounded pixels
+    if (!c->opt_rgba8_out && !c->frame32_stale) {   // in RGBA8 output mode the kernels already stored the rounded pixels
         rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_render>>>(c->d_frame, c->d_frame8, n);
         c->launches++;
         CU(c, cudaGetLastError());

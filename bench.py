@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-shadows", action="store_true")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
     ap.add_argument("--no-l2-window", action="store_true")
+    ap.add_argument("--tma", action="store_true", help="shade kernel writes whole framebuffer strips with TMA bulk copies instead of per-thread 16-byte stores (A/B)")
     ap.add_argument("--gather", default="p2p8", choices=["p2p8", "p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render "
                     "kernels as RGBA8 pixels (default) or RGBA32F pixels (p2p), or by pack + NCCL send/recv + unpack (nccl)")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
@@ -242,6 +243,8 @@ def main():
         svo.set_option(pkg.OPT_REFILL, args.refill)
     if args.ctas_per_sm:
         svo.set_option(pkg.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    if args.tma:
+        svo.set_option(pkg.OPT_TMA, 1)
     svo.update(world)
     vxp = frame_params(pkg, world, args)
     shard = (rank, n_gpus)
@@ -438,7 +441,7 @@ def main():
             "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 160 MiB device fill (> 126 MB L2) inside the timed region",
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)", "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
-            "l2_window": not args.no_l2_window, "world_gen_s": round(gen_s, 2),
+            "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2),
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
                                ("finished pixels stored by the shade/shadow kernels straight into GPU 0's %s framebuffer over NVLink peer memory, "
                                 "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"

@@ -197,8 +197,10 @@ def test_render_terrain_variants(pkg, ora, terrain):
     p = terrain_params(pkg, w, h)
     svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
     frames = {}
-    for simple, vec in ((8, 0), (1, 5), (32, 6), (20, 8)):   # (refill threshold, CTAs/SM = register-budget build)
+    # (refill threshold, CTAs/SM = register-budget build, TMA bulk-copy write-back of whole framebuffer strips; 270 rows leave a ragged strip)
+    for simple, vec, tma in ((8, 0, 0), (1, 5, 1), (32, 6, 0), (20, 8, 1)):
         if True:
+            svo.set_option(pkg.OPT_TMA, tma)
             svo.set_option(pkg.OPT_REFILL, simple)
             svo.set_option(pkg.OPT_CTAS_PER_SM, vec)
             svo.set_option(pkg.OPT_COUNT, 1)
@@ -207,8 +209,8 @@ def test_render_terrain_variants(pkg, ora, terrain):
             st = svo.frame_stats(0)
             for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
                 assert st[k] == cnt[k], (simple, vec, k, st, cnt)
-            frames[(simple, vec)] = got
-    base = frames[(8, 0)]
+            frames[(simple, vec, tma)] = got
+    base = frames[(8, 0, 0)]
     for k, f in frames.items():
         assert f.tobytes() == base.tobytes(), k
     assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]   # trilinear path exercised

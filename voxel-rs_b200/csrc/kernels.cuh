@@ -46,6 +46,8 @@ struct RenderArgs {
     uint32_t shard_rank, shard_size;
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
+    uint32_t tma_writeback;       // shade_kernel: stage the strip's pixels in shared memory and write them back with bulk async
+                                  // copies (TMA engine, cp.async.bulk -> SASS UBLKCP), one 512-byte row per copy
 };
 
 // Work units. The frame is cut into macro blocks of 32x16 pixels (row-major over the frame; a shard owns every
@@ -266,6 +268,11 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     bool want_shadow = false;
     float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
     const uint32_t pix = gy * a.u.width + gx;
+    // TMA write-back of the strip (framebuffer tile = 4 rows x 32 pixels x 16 B): only whole strips of a local RGBA32F frame;
+    // a pixel that still waits for its shadow ray gets res.color here and is overwritten by trace_shadow_kernel afterwards
+    __shared__ __align__(128) float4 s_tile[VX_THREADS];
+    const bool tile_store = a.tma_writeback && !a.frame8 && have && x0 + 32u <= a.u.width && y0 + 4u <= a.u.height;   // CTA-uniform
+    float4* const tile_slot = s_tile + ((threadIdx.x >> 3) & 3u) * 32u + (threadIdx.x >> 5) * 8u + (threadIdx.x & 7u);
     if (live) {
         const uint32_t slot = strip * 128u + threadIdx.x;
         const float4 h1 = __ldcs(a.hit1 + slot);
@@ -283,21 +290,28 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
             nf = 0;
             shade_hit(a.scene, sm.unorm, a.u, g, tex_lod, h1.x, h1.y, h1.z, sh, &nf);
             if (COUNT) cnt.tex_fetches += nf;
+            float4 outc;
             if (sh.done) {
-                store_pixel(a, pix, make_float4(sh.r, sh.g, sh.b, sh.a));
+                outc = make_float4(sh.r, sh.g, sh.b, sh.a);
             } else if (sh.want_shadow) {
                 want_shadow = true;
                 s0 = make_float4(sh.sox, sh.soy, sh.soz, sh.lit);
                 s1 = make_float4(sh.r, sh.g, sh.b, sh.a);
+                outc = s1;
             } else {
-                store_pixel(a, pix, shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f));
+                outc = shade_finish(a.u, sh.r, sh.g, sh.b, sh.a, sh.lit, 1.0f);
             }
+            if (tile_store) *tile_slot = outc;
+            else if (!want_shadow) store_pixel(a, pix, outc);
         } else {
             float ox, oy, oz, dx, dy, dz;
             primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-            store_pixel(a, pix, sky_color(dx, dy, dz));
+            const float4 outc = sky_color(dx, dy, dz);
+            if (tile_store) *tile_slot = outc;
+            else store_pixel(a, pix, outc);
         }
     }
+    if (tile_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the async (TMA) proxy
     // compact the shadow rays of this strip into the global list: one atomicAdd per CTA, strip order kept inside it
     const unsigned m = __ballot_sync(0xffffffffu, want_shadow);
     if (lane == 0) s_warp_count[warp] = __popc(m);
@@ -306,6 +320,14 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
         unsigned tot = 0;
         for (int k = 0; k < VX_THREADS / 32; ++k) tot += s_warp_count[k];
         s_base = tot ? atomicAdd(a.shadow_count, tot) : 0u;
+    }
+    if (tile_store && threadIdx.x >= 32 && threadIdx.x < 36) {   // one bulk copy per row of the tile (lanes 0-3 of warp 1; warp 0 does the atomic)
+        const uint32_t row = threadIdx.x - 32u;
+        const float4* dst = a.frame + (size_t)(y0 + row) * a.u.width + x0;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_tile + row * 32u);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(dst), "r"(src) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (want_shadow) {

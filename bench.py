@@ -5,8 +5,8 @@
     python bench.py --impl reference --gpus N --steps K --warmup W
 
 Metric (BASELINE.json): Mrays/s of primary + shadow rays actually cast, and ms/frame, at 4K (3840x2160) on the
-generated-terrain world of the reference's default shape (radius 20 chunks, LOD rule, camera (-24,80,174), fov 72 deg,
-sun (-1,-1,-1)/sqrt3, shadows on) = BASELINE.json configs[2]. A "step" is one frame.
+reference's generated-terrain world (its own generator restated: Perlin seed 1 + splines; default radius 20 chunks, LOD rule,
+camera (-24,80,174) looking along -z, fov 72 deg, sun (-1,-1,-1)/sqrt3, shadows on) = BASELINE.json configs[2]. A "step" is one frame.
 
   value        rays/s with everything resident in HBM: per step = L2 flush + vx_render (+ for N>1: NCCL broadcast of the
                frame's dirty SVO ranges, scatter, shard pack, NCCL gather to GPU 0, unpack)
@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--radius", type=int, default=20)
+    ap.add_argument("--terrain", choices=["reference", "standin"], default="reference",
+                    help="reference = the reference's own generator (Generator::new(1, cfg): noise 0.8.2 Perlin + splines, pinned by its KATs and "
+                         "end-to-end image); standin = hash-gradient noise of the same shape (the world of the profiles up to r01_v5)")
     ap.add_argument("--no-lod", action="store_true")
     ap.add_argument("--format", default="esvo", choices=["esvo", "csvo"], help="SVO type of the world buffer: esvo = the north_star path "
                     "(default); csvo = the reference's default feature (world::hds::csvo + svo.csvo.glsl)")
@@ -67,9 +70,13 @@ def parse():
     return ap.parse_args()
 
 
+def terrain_name(args):
+    return "the reference's generator, seed 1" if args.terrain == "reference" else "stand-in noise"
+
+
 def build_world(pkg, args):
     t = time.time()
-    world = pkg.World(radius=args.radius, center=(-1, 2, 5), seed=1, no_lod=args.no_lod,
+    world = pkg.World(radius=args.radius, center=(-1, 2, 5), seed=1, no_lod=args.no_lod, terrain=args.terrain,
                       fmt=pkg.FORMAT_CSVO if getattr(args, "format", "esvo") == "csvo" else pkg.FORMAT_ESVO)
     world.generate(0, 8)
     world.serialize()
@@ -77,8 +84,12 @@ def build_world(pkg, args):
 
 
 def frame_params(pkg, world, args):
-    p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, 0.0, 0.0), fov_y_deg=72.0, aspect=args.width / args.height,
-                          render_shadows=not args.no_shadows)   # yaw -90 deg, pitch 0 (src/main.rs:79-98)
+    # default player rotation "0 -90 0" (src/main.rs:82-87) through Entity::get_forward (physics.rs:21-27) in f32 = (-4.4e-8, 0, -1): the
+    # view of the reference's end-to-end image. The stand-in world keeps the +x view its profiles were taken with.
+    yaw = np.float32(np.deg2rad(np.float32(-90.0)))
+    fwd = (float(np.cos(yaw)), 0.0, float(np.sin(yaw))) if args.terrain == "reference" else (1.0, 0.0, 0.0)
+    p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=fwd, fov_y_deg=72.0, aspect=args.width / args.height,
+                          render_shadows=not args.no_shadows)
     import ctypes as C
     q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
     q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))   # systems::worldsvo::Svo::render, worldsvo.rs:397-409
@@ -86,7 +97,7 @@ def frame_params(pkg, world, args):
 
 
 def workload_name(args):
-    return (f"generated-terrain r={args.radius} chunks{' no-LOD' if args.no_lod else ' LOD'}{' (CSVO format)' if getattr(args, 'format', 'esvo') == 'csvo' else ''}, {args.width}x{args.height}, "
+    return (f"generated-terrain ({terrain_name(args)}) r={args.radius} chunks{' no-LOD' if args.no_lod else ' LOD'}{' (CSVO format)' if getattr(args, 'format', 'esvo') == 'csvo' else ''}, {args.width}x{args.height}, "
             f"primary{'' if args.no_shadows else '+shadow'} rays, camera (-24,80,174) fov72 (BASELINE configs[2])")
 
 
@@ -537,7 +548,7 @@ def run_serialize(args):
         "metric": "chunks/s (ESVO chunk serialization)", "value": n / (kernel_ms * 1e-3), "unit": "chunks/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": {"workload": f"ESVO serialization of the {n} chunks of the generated-terrain r={args.radius} world with the LOD rule (SURVEY §8f n3)",
+        "config": {"workload": f"ESVO serialization of the {n} chunks of the generated-terrain ({terrain_name(args)}) r={args.radius} world with the LOD rule (SURVEY §8f n3)",
                    "in_bytes": int(blocks.nbytes), "out_bytes": int(out_bytes), "l2": "flushed before every launch (160 MiB fill)",
                    "parity": "byte-identical to the host serializer's RangeBuffer image" if ok else "MISMATCH vs host serializer", "world_gen_s": round(gen_s, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -583,7 +594,8 @@ def run_picker(args):
     pkg = graft.load_pkg()
     radius = args.radius if args.radius != 20 else 40
     t0 = time.time()
-    world = pkg.World(radius=radius, center=(-1, 2, 5), seed=1, no_lod=True, fmt=pkg.FORMAT_CSVO if args.format == "csvo" else pkg.FORMAT_ESVO)
+    world = pkg.World(radius=radius, center=(-1, 2, 5), seed=1, no_lod=True, terrain=args.terrain,
+                      fmt=pkg.FORMAT_CSVO if args.format == "csvo" else pkg.FORMAT_ESVO)
     world.generate(0, 8)
     world.serialize()
     gen_s = time.time() - t0
@@ -674,7 +686,7 @@ def run_picker(args):
         "metric": "Mrays/s (picker rays)", "value": n_total / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{n_total} random-origin random-direction picker rays, generated-terrain r={radius} no-LOD world (BASELINE configs[3])",
+        "config": {"workload": f"{n_total} random-origin random-direction picker rays, generated-terrain ({terrain_name(args)}) r={radius} no-LOD world (BASELINE configs[3])",
                    "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "chunks": int(world.chunk_count), "max_dst": args.max_dst,
                    "parallelism": f"contiguous ray ranges over {world_size} GPU(s), SVO replicated, no collective", "refill_threshold": args.refill or 24,
                    "l2": "flushed between steps (160 MiB fill in the timed region); the SVO itself is larger than L2", "world_gen_s": round(gen_s, 2)},

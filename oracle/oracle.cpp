@@ -97,8 +97,11 @@ struct Texture {
     std::vector<std::vector<uint8_t>> mips;  // [level][layer*wl*hl*4]
 };
 
-// glGenerateMipmap stand-in (texture_array.rs:258-260; driver-defined in the reference): each texel
-// of level l+1 is the rounded mean of the 2x2 block below it.
+// glGenerateMipmap stand-in (texture_array.rs:258-260; the filter is implementation-defined in OpenGL): each texel of level
+// l+1 is the mean of the 2x2 block below it, rounded as floor(mean + 1/4), i.e. (sum + 1) >> 2. That rounding is the one that
+// reproduces the reference's own golden image of the mip-mapped far field (assets/tests/gamelogic_world_end_to_end_expected.png,
+// tests/test_oracle_golden.py::test_world_end_to_end_png): mean |dRGB| 0.00045 with 79 % of the pixels identical and 98.5 %
+// within 1 LSB, against 0.0053 with round-to-nearest ((sum + 2) >> 2), 0.0057 with truncation and 0.0028 with round-half-even.
 static void build_mips(Texture& t) {
     for (uint32_t l = 1; l < t.levels; ++l) {
         uint32_t pw = t.w >> (l - 1), ph = t.h >> (l - 1);
@@ -116,7 +119,7 @@ static void build_mips(Texture& t) {
                         size_t base = (size_t)layer * pw * ph;
                         uint32_t s = src[(base + (size_t)y0 * pw + x0) * 4 + c] + src[(base + (size_t)y0 * pw + x1) * 4 + c] +
                                      src[(base + (size_t)y1 * pw + x0) * 4 + c] + src[(base + (size_t)y1 * pw + x1) * 4 + c];
-                        t.mips[l][(((size_t)layer * ch + y) * cw + x) * 4 + c] = (uint8_t)((s + 2) >> 2);
+                        t.mips[l][(((size_t)layer * ch + y) * cw + x) * 4 + c] = (uint8_t)((s + 1) >> 2);
                     }
     }
 }

@@ -101,3 +101,34 @@ def mc_world(pkg, fmt=0):
 def mc_params(pkg, w, h, shadows=False):
     """Fixed camera of the BASELINE configs[0] frame: over the water, looking at a wooded island (leaves, logs, grass, sand)."""
     return pkg.render_params(cam_pos=(-2090.0, 75.0, 1690.0), cam_fwd=(0.6, -0.4, 1.0), fov_y_deg=72.0, aspect=w / h, render_shadows=shadows)
+
+
+# ---- the reference's generated world (gamelogic::world tests::end_to_end, src/gamelogic/world.rs:461-498) ----
+
+E2E_SIZE = (1024, 768)
+
+
+def e2e_world(pkg, fmt=0):
+    """World::new(.., 72.0, true, 15, false, None, 800) after loading finished: Generator::new(1, cfg) terrain (noise 0.8.2 Perlin +
+    splines), chunk disc of radius 15 around the player's chunk, y-chunks 0..8, LOD rule."""
+    w = pkg.World(radius=15, center=(-1, 2, 5), seed=1, fmt=fmt, terrain="reference")
+    w.generate(0, 8)
+    w.serialize()
+    return w
+
+
+def e2e_params(pkg):
+    """player at (-24, 80, 174), euler_rotation (0, -90 deg, 0) -> Entity::get_forward (physics.rs:21-27); World::render
+    (gamelogic/world.rs:269-281): ambient 0.3, sun (-1,-1,-1) normalised, shadows on, shadow distance 500."""
+    import math
+    yaw = np.float32(math.radians(-90.0))
+    fwd = (float(np.cos(yaw, dtype=np.float32)), 0.0, float(np.sin(yaw, dtype=np.float32)))
+    w, h = E2E_SIZE
+    return pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=fwd, cam_up=(0, 1, 0), fov_y_deg=72.0, aspect=w / h, ambient=0.3,
+                             render_shadows=True, shadow_distance=500.0)
+
+
+def e2e_expected():
+    import os
+    from PIL import Image
+    return np.asarray(Image.open(os.path.join(os.path.dirname(__file__), "golden", "gamelogic_world_end_to_end_expected.png")).convert("RGBA"))

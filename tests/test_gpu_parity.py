@@ -174,6 +174,32 @@ def test_render_reference_scene(pkg, ora):
     assert diff < 0.001
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_world_end_to_end_png(pkg, ora, fmt):
+    """tests::end_to_end, src/gamelogic/world.rs:461-498: the reference's generated world (Perlin terrain, radius 15, LOD rule),
+    1024x768 with shadows, through the C ABI — vs the oracle (+-1 LSB, counters equal) and vs the reference's committed image with the
+    reference's metric and default threshold 0.001 (both world formats: the image does not depend on SVO_TYPE)."""
+    w = helpers.e2e_world(pkg, fmt=fmt)
+    reg = pkg.content_registry(pkg.load_atlas())
+    p = helpers.e2e_params(pkg)
+    width, height = helpers.E2E_SIZE
+    svo = make_svo(pkg, reg, w, size_mb=w.size_bytes // 1_000_000 + 8, w=width, h=height, rays=16)
+    svo.set_option(pkg.OPT_COUNT, 1)
+    got, got8, want, want8, cnt = render_both(pkg, ora, reg, w, p, width, height, svo=svo, use_world=True)
+    assert_frames_match(got, got8, want, want8)
+    st = svo.frame_stats(0)
+    for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+        assert st[k] == cnt[k], (k, st, cnt)
+    svo.close()
+    exp = helpers.e2e_expected()
+    diff = helpers.diff_images(got8[::-1], exp)
+    m = np.abs(got8[::-1][..., :3].astype(int) - exp[..., :3].astype(int)).max(-1)
+    print(f"end-to-end world (fmt {fmt}): diff vs the reference's PNG {diff:.6f}, identical {(m == 0).mean():.4f}, within 1 LSB {(m <= 1).mean():.4f}")
+    assert diff < 0.001, diff
+    assert (m <= 1).mean() > 0.98
+
+
 @pytest.fixture(scope="module")
 def terrain(pkg):
     """Generated-terrain world of the named shape at a small radius (configs 2/3 shrunk for the oracle)."""

@@ -151,6 +151,27 @@ def test_render_expected_png(pkg, ora):
     assert diff < 0.001, diff
 
 
+def test_world_end_to_end_png(pkg, ora):
+    """tests::end_to_end, src/gamelogic/world.rs:461-498: the reference's generated world (Perlin terrain, radius 15, LOD), 1024x768,
+    shadows — oracle frame vs the reference's committed image with the reference's metric and default threshold (0.001).
+    Pins, against real output of the reference: the worldgen restatement, chunk LOD + ESVO serialization, traversal, shading, shadow
+    rays, and the mip-mapped (trilinear) texture path incl. the mip-chain rounding (oracle.cpp build_mips)."""
+    import ctypes as C
+    w = helpers.e2e_world(pkg)
+    reg = pkg.content_registry(pkg.load_atlas())
+    p = helpers.e2e_params(pkg)
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+    q.cam_pos = (C.c_float * 3)(*w.cnv_block_pos(tuple(p.cam_pos)))   # worldsvo.rs:393-404: camera in SVO space
+    img, cnt = helpers.oracle_scene(ora, w, reg).render(pkg.to_vx_render_params(q), *helpers.E2E_SIZE)
+    img8 = ora.to_rgba8(img)[::-1]
+    exp = helpers.e2e_expected()
+    diff = helpers.diff_images(img8, exp)
+    m = np.abs(img8[..., :3].astype(int) - exp[..., :3].astype(int)).max(-1)
+    print("oracle vs reference end-to-end PNG: diff =", diff, "identical", (m == 0).mean(), "within 1 LSB", (m <= 1).mean(), cnt)
+    assert diff < 0.001, diff
+    assert (m <= 1).mean() > 0.98 and (m > 40).mean() < 5e-4   # silhouettes and shadow edges: a handful of pixels
+
+
 # ------------------------------------------------------------------------------------------------------------- CSVO --
 
 def test_csvo_shader_svo_traversal(pkg, ora, reg):

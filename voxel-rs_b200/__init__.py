@@ -209,6 +209,9 @@ def host():
         "vxh_world_header_bytes": ([P], u64),
         "vxh_world_generate": ([P, i32, i32, C.c_int], u64),
         "vxh_world_height_at": ([P, i32, i32], i32),
+        "vxh_world_set_terrain": ([P, C.c_int], None),
+        "vxh_kat_worldgen_noise": ([u32, C.c_float, C.c_int, C.c_double, C.c_double], C.c_double),
+        "vxh_kat_spline": ([C.POINTER(C.c_float), C.c_int, C.c_double], C.c_double),
         "vxh_world_chunk_count": ([P], u64),
         "vxh_world_set_leaf_blocks": ([P, u32, u32, u32, u64, P, u32, C.c_uint8, C.c_int], C.c_int),
         "vxh_world_set_leaf_dense": ([P, u32, u32, u32, u64, P, C.c_uint8], C.c_int),
@@ -295,8 +298,11 @@ class VxError(RuntimeError):
 class World:
     """systems::worldsvo::Svo's CPU half: Esvo of SerializedChunks + SVO coordinate space (+ synthetic terrain)."""
 
-    def __init__(self, radius=0, center=(0, 0, 0), seed=1, no_lod=False, fmt=FORMAT_ESVO):
+    def __init__(self, radius=0, center=(0, 0, 0), seed=1, no_lod=False, fmt=FORMAT_ESVO, terrain="standin"):
+        """terrain: "reference" = the reference's generator (noise 0.8.2 Perlin + splines, gamelogic/worldgen.rs), "standin" = hash-gradient
+        noise of the same shape (the world the round-1 profiles were taken on)."""
         self.h = host().vxh_world_new(radius, center[0], center[1], center[2], seed, int(no_lod))
+        host().vxh_world_set_terrain(self.h, {"standin": 0, "reference": 1}[terrain])
         self.radius, self.center, self.fmt = radius, tuple(center), fmt
         host().vxh_world_set_format(self.h, fmt)
 

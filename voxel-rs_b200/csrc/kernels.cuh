@@ -622,7 +622,8 @@ __global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsign
 // unorm[b] = b / 255.0f with an IEEE division (what unpacking an RGBA8 texel means), once per context
 __global__ void unorm_kernel(float* table) { table[threadIdx.x] = (float)threadIdx.x / 255.0f; }
 
-// glGenerateMipmap stand-in: level l+1 texel = rounded mean of the 2x2 block below (texture_array.rs:258-260)
+// glGenerateMipmap stand-in (texture_array.rs:258-260): level l+1 texel = floor(mean of the 2x2 block below + 1/4), the rounding that
+// reproduces the reference's golden image of the mip-mapped far field
 __global__ void mip_kernel(const uint32_t* src, uint32_t* dst, uint32_t pw, uint32_t ph, uint32_t cw, uint32_t ch, uint32_t layers) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cw * ch * layers) return;
@@ -633,7 +634,7 @@ __global__ void mip_kernel(const uint32_t* src, uint32_t* dst, uint32_t pw, uint
     uint32_t out = 0;
     for (int c = 0; c < 4; ++c) {
         const uint32_t sum = ((t00 >> (8 * c)) & 0xff) + ((t10 >> (8 * c)) & 0xff) + ((t01 >> (8 * c)) & 0xff) + ((t11 >> (8 * c)) & 0xff);
-        out |= ((sum + 2) >> 2) << (8 * c);
+        out |= ((sum + 1) >> 2) << (8 * c);
     }
     dst[i] = out;
 }

@@ -35,6 +35,15 @@ void vxh_world_set_format(void* w, int format) { ((WorldSvo*)w)->format = format
 int vxh_world_format(void* w) { return (int)((WorldSvo*)w)->format; }
 void vxh_world_free(void* w) { delete (WorldSvo*)w; }
 uint64_t vxh_world_generate(void* w, int32_t y0, int32_t y1, int threads) { return ((WorldSvo*)w)->generate(y0, y1, threads); }
+// terrain kind: 0 = stand-in noise, 1 = the reference's generator (noise 0.8.2 Perlin, gamelogic/worldgen.rs)
+void vxh_world_set_terrain(void* w, int kind) { ((WorldSvo*)w)->terrain.set_kind(kind); }
+// worldgen.rs noise_tests::get (88-101): Noise{frequency, octaves, spline (-1,0)..(1,1)}.get(&Perlin::new(seed), x, z)
+double vxh_kat_worldgen_noise(uint32_t seed, float frequency, int octaves, double x, double z) {
+    static const float PTS[2][2] = {{-1.0f, 0.0f}, {1.0f, 1.0f}};
+    const RefPerlin p(seed);
+    return RefNoise{frequency, octaves, PTS, 2}.get(p, x, z);
+}
+double vxh_kat_spline(const float* pts, int n, double x) { return RefNoise{1.0f, 1, (const float (*)[2])pts, n}.spline(x); }
 int32_t vxh_world_height_at(void* w, int32_t x, int32_t z) { return ((WorldSvo*)w)->terrain.height_at(x, z); }
 uint64_t vxh_world_chunk_count(void* w) { return ((WorldSvo*)w)->leaf_ids.size(); }
 

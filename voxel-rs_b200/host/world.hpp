@@ -96,10 +96,89 @@ inline uint8_t calculate_lod(ChunkPos center, ChunkPos pos) {
     return 2;
 }
 
-// Deterministic stand-in terrain: two fBm layers of hash-gradient noise pushed through the reference's
-// splines (gamelogic/world.rs:56-78).
+// `noise::Perlin` of the noise crate 0.8.2 (Cargo.lock:936-943; the crate source is not part of the reference checkout), restated
+// from its published algorithm and pinned by the reference's own known-answer test `noise_tests::get`
+// (src/gamelogic/worldgen.rs:88-101, tests/test_host_worldgen.py) and end-to-end by `gamelogic_world_end_to_end_expected.png`:
+//   PermutationTable::new(seed): XorShiftRng (rand_xorshift 0.2) seeded with the bytes {1,0,0,0, seed, seed, seed} (little endian),
+//     Fisher-Yates shuffle of 0..255 from the back with rand 0.7.3's `gen_range(0, i + 1)` (widening-multiply rejection sampler);
+//   hash(x, y) = perm[perm[x & 255] ^ (y & 255)];
+//   perlin_2d: gradients (+-1, +-1) chosen by hash & 3, quintic fade, bilinear blend, x sqrt(2), clamped to [-1, 1].
+struct RefPerlin {
+    uint8_t perm[256];
+
+    explicit RefPerlin(uint32_t seed = 0) {
+        uint32_t st[4] = {1u, seed, seed, seed};   // from_seed: four little-endian u32 (never all zero)
+        auto next = [&]() {
+            const uint32_t x = st[0], t = x ^ (x << 11);
+            st[0] = st[1]; st[1] = st[2]; st[2] = st[3];
+            st[3] = st[3] ^ (st[3] >> 19) ^ (t ^ (t >> 8));
+            return st[3];
+        };
+        for (int i = 0; i < 256; ++i) perm[i] = (uint8_t)i;
+        for (uint32_t i = 255; i >= 1; --i) {
+            const uint32_t range = i + 1, zone = (range << __builtin_clz(range)) - 1u;
+            uint32_t j;
+            for (;;) {
+                const uint64_t m = (uint64_t)next() * range;
+                if ((uint32_t)m <= zone) { j = (uint32_t)(m >> 32); break; }
+            }
+            std::swap(perm[i], perm[j]);
+        }
+    }
+    uint32_t hash(int64_t x, int64_t y) const { return perm[perm[x & 255] ^ (uint32_t)(y & 255)]; }
+    static double corner(uint32_t h, double dx, double dy) {
+        switch (h & 3u) {
+            case 0: return dx + dy;
+            case 1: return -dx + dy;
+            case 2: return dx - dy;
+            default: return -dx - dy;
+        }
+    }
+    static double quintic(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
+    double get(double x, double y) const {
+        const double fx = std::floor(x), fy = std::floor(y);
+        const int64_t cx = (int64_t)fx, cy = (int64_t)fy;
+        const double dx = x - fx, dy = y - fy;
+        const double g00 = corner(hash(cx, cy), dx, dy), g10 = corner(hash(cx + 1, cy), dx - 1.0, dy);
+        const double g01 = corner(hash(cx, cy + 1), dx, dy - 1.0), g11 = corner(hash(cx + 1, cy + 1), dx - 1.0, dy - 1.0);
+        const double u = quintic(dx), v = quintic(dy);
+        const double r = (g00 + (g10 - g00) * u + (g01 - g00) * v + (g00 + g11 - g10 - g01) * u * v) * 1.4142135623730951;
+        return r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+    }
+};
+
+// `worldgen::Noise` (src/gamelogic/worldgen.rs:14-77): octaves of Perlin noise pushed through a piecewise-linear spline, with the
+// reference's mixed f32 / f64 arithmetic (f32 frequency and spline points, f64 accumulation, fused multiply-adds).
+struct RefNoise {
+    float frequency; int octaves; const float (*points)[2]; int n_points;
+
+    double value(const RefPerlin& p, double x, double z) const {   // get_noise_value, worldgen.rs:42-54
+        double f = (double)frequency, a = 1.0, v = 0.0;
+        for (int i = 0; i < octaves; ++i) { v += p.get(std::fma(x, f, 0.5), std::fma(z, f, 0.5)) * a; f *= 2.0; a *= 0.5; }
+        return v;
+    }
+    double spline(double x) const {   // interpolate_spline_points, worldgen.rs:56-77
+        if (n_points == 0) return 0.0;
+        int rhs = -1;
+        for (int i = 0; i < n_points; ++i) if ((double)points[i][0] > x) { rhs = i; break; }
+        if (rhs < 0) return (double)points[n_points - 1][1];
+        if (rhs == 0) return (double)points[0][1];
+        const float* l = points[rhs - 1]; const float* r = points[rhs];
+        const float factor = ((float)x - l[0]) / (r[0] - l[0]);
+        return std::fma((double)(r[1] - l[1]), (double)factor, (double)l[1]);
+    }
+    double get(const RefPerlin& p, double x, double z) const { return spline(value(p, x, z)); }
+};
+
+// Terrain height function. kind 1 = the reference's generator (Generator::get_height_at, gamelogic/worldgen.rs:191-199, with the
+// Config of gamelogic/world.rs:54-78 and Perlin::new(seed)); kind 0 = a deterministic stand-in of the same shape: two fBm layers
+// of hash-gradient noise pushed through the reference's splines.
 struct Terrain {
     uint32_t seed = 1;
+    int kind = 0;
+    RefPerlin perlin{1};
+
+    void set_kind(int k) { kind = k; if (k == 1) perlin = RefPerlin(seed); }
 
     static uint32_t hash2(uint32_t x, uint32_t y, uint32_t s) {
         uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u + s * 0xC2B2AE3Du);
@@ -139,6 +218,13 @@ struct Terrain {
         return pts[rhs - 1][1] + (pts[rhs][1] - pts[rhs - 1][1]) * f;
     }
     int32_t height_at(int32_t x, int32_t z) const {   // gamelogic/worldgen.rs:191-199
+        if (kind == 1) {
+            static const float RCONT[6][2] = {{-1.0f, 20.0f}, {0.4f, 50.0f}, {0.6f, 70.0f}, {0.8f, 120.0f}, {0.9f, 190.0f}, {1.0f, 200.0f}};
+            static const float RERO[2][2] = {{-1.0f, -10.0f}, {1.0f, 4.0f}};
+            const RefNoise continentalness{0.001f, 3, RCONT, 6}, erosion{0.01f, 4, RERO, 2};
+            const double h = continentalness.get(perlin, (double)x, (double)z);
+            return (int32_t)(h + erosion.get(perlin, (double)x, (double)z));
+        }
         static const double CONT[6][2] = {{-1.0, 20.0}, {0.4, 50.0}, {0.6, 70.0}, {0.8, 120.0}, {0.9, 190.0}, {1.0, 200.0}};
         static const double ERO[2][2] = {{-1.0, -10.0}, {1.0, 4.0}};
         // the stand-in noise is stretched (x1.5, +0.25) so that mountains like the reference's appear inside a radius-20 disc

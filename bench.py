@@ -52,6 +52,7 @@ def parse():
                     "(default); csvo = the reference's default feature (world::hds::csvo + svo.csvo.glsl)")
     ap.add_argument("--no-shadows", action="store_true")
     ap.add_argument("--refill", type=int, default=0, help="refill threshold of the persistent kernel (lanes still walking)")
+    ap.add_argument("--refill-shadow", type=int, default=0, help="refill threshold of the shadow-ray kernel alone")
     ap.add_argument("--no-l2-window", action="store_true")
     ap.add_argument("--tma", action="store_true", help="shade kernel writes whole framebuffer strips with TMA bulk copies instead of per-thread 16-byte stores (A/B)")
     ap.add_argument("--gather", default="p2p8", choices=["p2p8", "p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render "
@@ -252,6 +253,8 @@ def main():
     svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
     if args.refill:
         svo.set_option(pkg.OPT_REFILL, args.refill)
+    if args.refill_shadow:
+        svo.set_option(pkg.OPT_REFILL_SHADOW, args.refill_shadow)
     if args.ctas_per_sm:
         svo.set_option(pkg.OPT_CTAS_PER_SM, args.ctas_per_sm)
     if args.tma:
@@ -432,7 +435,8 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if n_gpus == 1 and (W, H) == (3840, 2160) and not args.no_shadows:   # the ncu capture is of this exact frame
+        if n_gpus == 1 and (W, H) == (3840, 2160) and not args.no_shadows and args.terrain == "reference" and args.format == "esvo" \
+                and args.radius == 20 and not args.no_lod:   # the ncu capture is of this exact frame
             traffic = tj.get("render_kernel_dram_bytes_per_launch")
             wi = tj.get("warp_instructions_per_frame")
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -678,7 +682,8 @@ def run_picker(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("picker_kernel_dram_bytes_per_launch") if (world_size == 1 and n_total == 1 << 24) else None
+            traffic = json.load(f).get("picker_kernel_dram_bytes_per_launch") if (world_size == 1 and n_total == 1 << 24 and args.terrain == "reference"
+                                                                              and args.format == "esvo" and radius == 40) else None
     except Exception:
         pass
     hits = None

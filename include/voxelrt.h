@@ -352,6 +352,7 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *       the frame bytes (multi-GPU gather, read-back)
  *   9 = TMA write-back of framebuffer tiles in the shade kernel (0/1, default 0: measured 3 % slower): a strip's 4 x 32 RGBA32F pixels are staged in
  *       shared memory and written with four 512-byte bulk async copies instead of 128 16-byte stores
+ *  10 = refill threshold of the shadow-ray kernel alone (0 = follow option 6)
  *   7 = the same for the picker kernel (default 24: incoherent rays differ in length by 100x; 4.85 vs 2.84 Grays/s
  *       against threshold 1 on 16 Mi random rays, profiles/r01_v2_*) */
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);

@@ -367,7 +367,7 @@ def test_full_size_4k_frame_vs_oracle(pkg, ora):
     frame on the host cores in about a second, so this is a direct comparison, not a property test: RGB8 within 1 LSB on
     all 8.3 M pixels, ray / step / push / leaf / texel counters identical, hit mask identical."""
     import bench
-    args = type("A", (), dict(radius=20, no_lod=False, width=3840, height=2160, no_shadows=False))()
+    args = type("A", (), dict(radius=20, no_lod=False, width=3840, height=2160, no_shadows=False, terrain="reference"))()
     world, _ = bench.build_world(pkg, args)
     reg = pkg.content_registry(pkg.load_atlas())
     vxp = bench.frame_params(pkg, world, args)
@@ -391,7 +391,7 @@ def test_full_size_4k_frame_vs_oracle(pkg, ora):
     svo.set_option(pkg.OPT_COUNT, 0)
     svo.render_raw(vxp, W, H)
     assert svo.read_rgba32f().tobytes() == got.tobytes()
-    svo.render_raw(bench.frame_params(pkg, world, type("A", (), dict(radius=20, no_lod=False, width=W, height=H, no_shadows=True))()), W, H)
+    svo.render_raw(bench.frame_params(pkg, world, type("A", (), dict(radius=20, no_lod=False, width=W, height=H, no_shadows=True, terrain="reference"))()), W, H)
     for r in range(8):
         svo.render_raw(vxp, W, H, shard=(r, 8))
     assert svo.read_rgba32f().tobytes() == got.tobytes()
@@ -399,13 +399,13 @@ def test_full_size_4k_frame_vs_oracle(pkg, ora):
 
 
 def test_full_size_16m_picker_rays_vs_oracle(pkg, ora):
-    """BASELINE configs[3] at its real size: 16 Mi random picker rays against the r=40 no-LOD world (1 GB SVO, depth 12).
+    """BASELINE configs[3] at its real size: 16 Mi random picker rays against the r=40 no-LOD world of the reference's generator (0.8 GB SVO, depth 12).
     Every one of the 16 Mi 48-byte results is byte-identical to the oracle's; counters identical."""
     import bench
-    world = pkg.World(radius=40, center=(-1, 2, 5), seed=1, no_lod=True)
+    world = pkg.World(radius=40, center=(-1, 2, 5), seed=1, no_lod=True, terrain="reference")
     world.generate(0, 8)
     world.serialize()
-    assert world.depth == 12 and world.size_bytes > 900_000_000
+    assert world.depth == 12 and world.size_bytes > 700_000_000
     reg = pkg.content_registry(pkg.load_atlas())
     n = 1 << 24
     svo = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=32, max_height=16, max_rays=n)

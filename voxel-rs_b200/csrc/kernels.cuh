@@ -45,6 +45,7 @@ struct RenderArgs {
     uint32_t n_owned;             // macro blocks of [macro0, macro0 + n_macros) owned by this shard
     uint32_t shard_rank, shard_size;
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
+    uint32_t shadow_refill;       // the same for trace_shadow_kernel
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
     uint32_t tma_writeback;       // shade_kernel: stage the strip's pixels in shared memory and write them back with bulk async
                                   // copies (TMA engine, cp.async.bulk -> SASS UBLKCP), one 512-byte row per copy
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.shadow_refill, __popc(busy)));
 
         if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;

@@ -96,7 +96,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -288,6 +288,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 7: ctx->opt_refill_picker = value < 1 ? 1 : (value > 32 ? 32 : value); break;
         case 8: ctx->opt_rgba8_out = value ? 1 : 0; break;
         case 9: ctx->opt_tma = value ? 1 : 0; break;
+        case 10: ctx->opt_refill_shadow = value > 32 ? 32 : value; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -649,6 +650,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.counters = c->d_counters;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
     a.refill_threshold = (uint32_t)c->opt_refill;
+    a.shadow_refill = (uint32_t)(c->opt_refill_shadow ? c->opt_refill_shadow : c->opt_refill);
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->s_render));

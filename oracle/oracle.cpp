@@ -18,11 +18,12 @@
 //
 // Pinning: tests/test_oracle_golden.py checks this oracle against the reference's own golden
 // vectors (src/graphics/svo_shader_tests.rs:293-753 step traces and results, src/graphics/svo.rs:
-// 402-449 picker rays, assets/tests/graphics_svo_render_expected.png at the reference's 0.1 %
-// threshold). Third-party arithmetic that is NOT in the reference checkout (OpenGL driver:
-// textureLod filtering arithmetic, glGenerateMipmap, GLSL built-ins) is restated from the OpenGL 4.5
-// spec (section 8.14) with a 2x2 box-filter mip chain; the trilinear path is pinned only through the
-// expected PNG.
+// 402-449 picker rays, the CSVO goldens :756-1224, and BOTH images the reference commits, each under the reference's own
+// metric and default 0.1 % threshold: assets/tests/graphics_svo_render_expected.png (close-up scene, NEAREST texels) and
+// assets/tests/gamelogic_world_end_to_end_expected.png (the generated world at radius 15: LOD chunks, shadows and the mip-mapped
+// trilinear texture path; diff 0.00045, 98.5 % of the pixels within 1 LSB). Third-party arithmetic that is NOT in the reference
+// checkout (OpenGL driver: textureLod filtering arithmetic, glGenerateMipmap, GLSL built-ins) is restated from the OpenGL 4.5
+// spec (section 8.14) with a 2x2 box-filter mip chain whose rounding is fitted to the second image (build_mips below).
 //
 // Numeric convention (shared with the CUDA kernels, see DESIGN.md "Numerics"): IEEE-754 binary32,
 // round-to-nearest-even, no compiler-chosen contraction (build with -ffp-contract=off); a fused

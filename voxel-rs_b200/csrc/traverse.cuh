@@ -230,7 +230,7 @@ __device__ __forceinline__ bool csvo_has_child(uint32_t hdr, uint32_t depth, uin
 // bytes of the pointers whose 2-bit tags are set in `tags` (sum of (1 << tag) >> 1, :68-87): tag 1 -> 1, 2 -> 2, 3 -> 4
 __device__ __forceinline__ uint32_t csvo_tag_bytes(uint32_t tags) {
     const uint32_t lo = tags & 0x5555u, hi = (tags >> 1) & 0x5555u;
-    return __popc(lo & ~hi) + 2u * __popc(hi & ~lo) + 4u * __popc(hi & lo);
+    return __popc(lo) + 2u * __popc(hi) + __popc(hi & lo);                     // tag 1: 1 + 0 + 0, tag 2: 0 + 2 + 0, tag 3: 1 + 2 + 1
 }
 // read_next_ptr (:53-133) for a child that is known to be present.
 __device__ __forceinline__ uint32_t csvo_next_ptr(const Scene& s, uint32_t ptr, uint32_t depth, uint32_t hdr, uint32_t idx, bool& crossed_boundary) {
@@ -335,6 +335,16 @@ enum : int { ST_MISS = -2, ST_IDLE = -3, ST_LEAF = -4 };
 __device__ __forceinline__ bool state_at_leaf(int st) { return st <= ST_LEAF; }
 __device__ __forceinline__ bool state_missed(int st) { return st == 0 || st == ST_MISS; }
 
+// CSVO stack entries carry the node's header next to its depth, so a POP does not re-read it (the shader re-reads the header of
+// `ptr` every iteration; the buffer is immutable while a frame is traced). depth is kept as a signed 16-bit value: it is a small
+// count, a chunk's lod byte, or — for a ray that started inside a voxel and descends below the leaves — a small negative number.
+__device__ __forceinline__ uint32_t csvo_pack_node(uint32_t depth, uint32_t hdr) { return (depth & 0xffffu) | (hdr << 16); }
+__device__ __forceinline__ void csvo_unpack_node(Walk& w) {
+    const uint32_t packed = w.desc;
+    w.hdr = packed >> 16;
+    w.desc = (uint32_t)(int32_t)(int16_t)(packed & 0xffffu);
+}
+
 // ADVANCE / POP (svo.esvo.glsl:324-391 = svo.csvo.glsl:440-507). Returns 0 when the ray left the octree (:365), 1 after an
 // ADVANCE, 2 after a POP (the node changed: (rec, desc) = the shader's (ptr, parent_octant_idx) resp. (ptr, depth)).
 __device__ __forceinline__ int walk_advance(Walk& w, uint32_t stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
@@ -399,7 +409,8 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
         if (w.t_min <= tv_max) {                                              // :280  PUSH
             if (COUNT) cnt.pushes++;
             if (tc_max < w.h)                                                 // :284-288
-                stack_store(stk, min((uint32_t)(VX_MAX_SCALE - 1 - w.scale), s.stack_levels - 1u), w.rec, w.desc, w.t_max);
+                stack_store(stk, min((uint32_t)(VX_MAX_SCALE - 1 - w.scale), s.stack_levels - 1u), w.rec,
+                            FMT == VX_FMT_CSVO ? csvo_pack_node(w.desc, w.hdr) : w.desc, w.t_max);
             w.h = tc_max;                                                     // :289
             const float half = w.se * 0.5f;                                   // :274
             const float tcx_ = __fmaf_rn(half, w.tcx, tcornx), tcy_ = __fmaf_rn(half, w.tcy, tcorny), tcz_ = __fmaf_rn(half, w.tcz, tcornz);   // :275
@@ -438,7 +449,7 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
     }
     const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
     if (adv == 0) w.state = ST_MISS;
-    else if (FMT == VX_FMT_CSVO && adv == 2) w.hdr = csvo_header(s, w.rec, w.desc);
+    else if (FMT == VX_FMT_CSVO && adv == 2) csvo_unpack_node(w);
 }
 
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
@@ -450,7 +461,7 @@ __device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
     const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
     w.state = adv ? budget : ST_MISS;
-    if (FMT == VX_FMT_CSVO && adv == 2) w.hdr = csvo_header(s, w.rec, w.desc);
+    if (FMT == VX_FMT_CSVO && adv == 2) csvo_unpack_node(w);
 }
 
 template <int FMT>

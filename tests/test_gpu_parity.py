@@ -224,18 +224,17 @@ def test_render_terrain_variants(pkg, ora, terrain):
     svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
     frames = {}
     # (refill threshold, CTAs/SM = register-budget build, TMA bulk-copy write-back of whole framebuffer strips; 270 rows leave a ragged strip)
-    for simple, vec, tma in ((8, 0, 0), (1, 5, 1), (32, 6, 0), (20, 8, 1)):
-        if True:
-            svo.set_option(pkg.OPT_TMA, tma)
-            svo.set_option(pkg.OPT_REFILL, simple)
-            svo.set_option(pkg.OPT_CTAS_PER_SM, vec)
-            svo.set_option(pkg.OPT_COUNT, 1)
-            got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
-            assert_frames_match(got, got8, want, want8)
-            st = svo.frame_stats(0)
-            for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
-                assert st[k] == cnt[k], (simple, vec, k, st, cnt)
-            frames[(simple, vec, tma)] = got
+    for refill, ctas, tma in ((8, 0, 0), (1, 5, 1), (32, 6, 0), (20, 8, 1)):
+        svo.set_option(pkg.OPT_TMA, tma)
+        svo.set_option(pkg.OPT_REFILL, refill)
+        svo.set_option(pkg.OPT_CTAS_PER_SM, ctas)
+        svo.set_option(pkg.OPT_COUNT, 1)
+        got, got8, want, want8, cnt = render_both(pkg, ora, reg, world, p, w, h, svo=svo, use_world=True)
+        assert_frames_match(got, got8, want, want8)
+        st = svo.frame_stats(0)
+        for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
+            assert st[k] == cnt[k], (refill, ctas, k, st, cnt)
+        frames[(refill, ctas, tma)] = got
     base = frames[(8, 0, 0)]
     for k, f in frames.items():
         assert f.tobytes() == base.tobytes(), k

@@ -5,6 +5,7 @@
 // (--fmad=false is part of the numeric contract, see traverse.cuh).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -28,7 +29,7 @@ struct VxCtx {
     int sm_count = 0;
     std::string err;
 
-    cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr, s_copy = nullptr;
+    cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr, s_copy = nullptr, s_pick_in = nullptr;
     cudaEvent_t e_band[16] = {};
     cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
@@ -187,6 +188,7 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaStreamCreateWithFlags(&c->s_upload, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_picker, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->s_pick_in, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CUC(cudaEventCreateWithFlags(&c->e_band[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_upload, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_render, cudaEventDisableTiming));
@@ -262,6 +264,7 @@ void vx_destroy(VxCtx* c) {
     for (cudaEvent_t ev : c->t_wave) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->e_band) if (ev) cudaEventDestroy(ev);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_pick_in) cudaStreamDestroy(c->s_pick_in);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_results) cudaFree(c->d_results);
     if (c->d_counters) cudaFree(c->d_counters);
@@ -771,7 +774,9 @@ int vx_frame_device_ptr(VxCtx* c, void** out_ptr, uint32_t* width, uint32_t* hei
     return VX_OK;
 }
 
-static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4* results_dev) {
+// One launch of the picker kernel over n tasks. A batch that is cut into several launches (vx_raycast's pipelined path) clears the
+// ray counters and starts the timer with its first launch and stops it with its last.
+static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4* results_dev, bool first = true, bool last = true) {
     RaycastArgs a{};
     a.scene = make_scene(c);
     a.tasks = tasks_dev; a.results = results_dev; a.n = n;
@@ -786,16 +791,49 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     if (rc) return rc;
     const uint64_t need = (n + VX_THREADS - 1) / VX_THREADS;
     if ((uint64_t)grid > need) grid = (int)need;
-    CU(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(Counters), c->s_picker));
+    if (first) CU(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(Counters), c->s_picker));
     CU(c, cudaMemsetAsync(c->d_work + 4, 0, sizeof(unsigned long long), c->s_picker));
-    CU(c, cudaEventRecord(c->t0_picker, c->s_picker));
+    if (first) CU(c, cudaEventRecord(c->t0_picker, c->s_picker));
     k<<<grid, VX_THREADS, smem, c->s_picker>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
-    CU(c, cudaEventRecord(c->t1_picker, c->s_picker));
-    CU(c, cudaEventRecord(c->e_picker, c->s_picker));
-    c->raycast_timed = true;
+    if (last) {
+        CU(c, cudaEventRecord(c->t1_picker, c->s_picker));
+        CU(c, cudaEventRecord(c->e_picker, c->s_picker));
+        c->raycast_timed = true;
+    }
     return VX_OK;
+}
+
+// Batches above this many rays are cut into slices: slice i's tasks go up (s_pick_in) while slice i-1 is traced (s_picker) and
+// slice i-2's results come down (s_copy) — PCIe is full duplex, so a large batch costs about max(H2D, D2H) instead of their sum.
+static constexpr uint64_t VX_PICK_SLICE = 1ull << 21;   // 2 Mi rays = 96 MiB each way
+
+static int raycast_pipelined(VxCtx* c, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results) {
+    const uint64_t n_slices = (n + VX_PICK_SLICE - 1) / VX_PICK_SLICE;
+    std::vector<cudaEvent_t> ev(2 * n_slices, nullptr);
+    int rc = VX_OK;
+    for (auto& e : ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = fail(c, VX_E_CUDA, "vx_raycast: cudaEventCreate failed"); break; }
+    for (uint64_t i = 0; i < n_slices && rc == VX_OK; ++i) {
+        const uint64_t off = i * VX_PICK_SLICE, m = std::min(VX_PICK_SLICE, n - off);
+        cudaError_t e = cudaMemcpyAsync(c->d_tasks + off * 3, tasks + off, (size_t)m * 48, cudaMemcpyHostToDevice, c->s_pick_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[2 * i], c->s_pick_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_picker, ev[2 * i], 0);
+        if (e != cudaSuccess) { rc = fail(c, VX_E_CUDA, "vx_raycast: upload of slice %llu: %s", (unsigned long long)i, cudaGetErrorString(e)); break; }
+        rc = launch_raycast(c, c->d_tasks + off * 3, m, c->d_results + off * 3, i == 0, i + 1 == n_slices);
+        if (rc) break;
+        e = cudaEventRecord(ev[2 * i + 1], c->s_picker);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_copy, ev[2 * i + 1], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(results + off, c->d_results + off * 3, (size_t)m * 48, cudaMemcpyDeviceToHost, c->s_copy);
+        if (e != cudaSuccess) { rc = fail(c, VX_E_CUDA, "vx_raycast: read-back of slice %llu: %s", (unsigned long long)i, cudaGetErrorString(e)); break; }
+    }
+    // the fence of the reference (svo.rs:248-249); also on the error path, so that no copy is in flight into the caller's buffers
+    const cudaError_t e0 = cudaStreamSynchronize(c->s_pick_in), e1 = cudaStreamSynchronize(c->s_picker), e2 = cudaStreamSynchronize(c->s_copy);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (rc == VX_OK && (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess))
+        rc = fail(c, VX_E_CUDA, "vx_raycast: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+    return rc;
 }
 
 int vx_raycast(VxCtx* c, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results) {
@@ -806,6 +844,7 @@ int vx_raycast(VxCtx* c, const VxPickerTask* tasks, uint64_t n, VxPickerResult* 
     if (rc) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamWaitEvent(c->s_picker, c->e_upload, 0));
+    if (n > VX_PICK_SLICE) return raycast_pipelined(c, tasks, n, results);
     CU(c, cudaMemcpyAsync(c->d_tasks, tasks, (size_t)n * 48, cudaMemcpyHostToDevice, c->s_picker));
     rc = launch_raycast(c, c->d_tasks, n, c->d_results);
     if (rc) return rc;

@@ -81,7 +81,8 @@ struct VxCtx {
     float4* d_results = nullptr;
 
     Counters* d_counters = nullptr;   // [0] render, [1] raycast
-    unsigned long long* d_work = nullptr;   // [0] render strip counter (low 32 bits used), [1] picker run counter
+    unsigned long long* d_work = nullptr;   // u64[4] picker run counter, u64[6] chunk bump pointer, u64[7] its overflow flag; from byte 64:
+                                            // 16 bands x 8 u32 render counters ([0] primary tiles, [2] shadow runs, [4] shadow list length)
     VxFrameStats last_render{}, last_raycast{};
     bool render_timed = false, raycast_timed = false;
 
@@ -278,9 +279,7 @@ void vx_destroy(VxCtx* c) {
     delete c;
 }
 
-// Runtime knobs for A/B measurements (not part of the reference surface).
-//   3 = count steps/pushes/leaf tests (0/1)   4 = CTAs per SM for the persistent trace kernels (0 = default)
-//   5 = L2 access-policy window (0/1)         6 / 7 = refill threshold of the render / picker trace kernels (1..32 lanes still walking)
+// Runtime knobs for A/B measurements (not part of the reference surface); the list with defaults is in voxelrt.h.
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
     if (!ctx) return VX_E_ARG;
     switch (option) {
@@ -875,11 +874,14 @@ int vx_debug_cast(VxCtx* c, const float pos[3], const float dir[3], float max_ds
     int rc = check_scene(c, "vx_debug_cast");
     if (rc) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
-    VxOctreeResult* d_res = nullptr; VxDebugFrame* d_frames = nullptr; uint32_t* d_n = nullptr;
+    // one scratch block {result | frame count | frames}, freed on every way out
     const uint32_t cap = frames ? frames_cap : 0;
-    CU(c, cudaMalloc(&d_res, sizeof(VxOctreeResult)));
-    CU(c, cudaMalloc(&d_frames, sizeof(VxDebugFrame) * (cap ? cap : 1)));
-    CU(c, cudaMalloc(&d_n, 4));
+    const size_t off_n = (sizeof(VxOctreeResult) + 15) & ~(size_t)15, off_frames = off_n + 16;
+    struct Scratch { uint8_t* p = nullptr; ~Scratch() { if (p) cudaFree(p); } } scratch;
+    CU(c, cudaMalloc(&scratch.p, off_frames + sizeof(VxDebugFrame) * (cap ? cap : 1)));
+    VxOctreeResult* d_res = reinterpret_cast<VxOctreeResult*>(scratch.p);
+    uint32_t* d_n = reinterpret_cast<uint32_t*>(scratch.p + off_n);
+    VxDebugFrame* d_frames = reinterpret_cast<VxDebugFrame*>(scratch.p + off_frames);
     DebugArgs a{};
     a.scene = make_scene(c);
     for (int k = 0; k < 3; ++k) { a.pos[k] = pos[k]; a.dir[k] = dir[k]; }
@@ -896,7 +898,6 @@ int vx_debug_cast(VxCtx* c, const float pos[3], const float dir[3], float max_ds
     if (cap) CU(c, cudaMemcpyAsync(frames, d_frames, sizeof(VxDebugFrame) * cap, cudaMemcpyDeviceToHost, c->s_picker));
     CU(c, cudaStreamSynchronize(c->s_picker));
     if (n_frames) *n_frames = n;
-    cudaFree(d_res); cudaFree(d_frames); cudaFree(d_n);
     return VX_OK;
 }
 

@@ -255,6 +255,12 @@ def host():
         "vxh_rangebuf_new": ([], P), "vxh_rangebuf_free": ([P], None),
         "vxh_rangebuf_insert": ([P, u64, P, u64], u64), "vxh_rangebuf_remove": ([P, u64], None),
         "vxh_rangebuf_bytes": ([P, P, u64], u64), "vxh_rangebuf_ranges": ([P, C.c_int, P, u32], u32),
+        "vxh_rangebuf_with_capacity": ([u64], P), "vxh_rangebuf_ids": ([P, P, u32], u32), "vxh_merge_ranges": ([P, u32], u32),
+        "vxh_octree_new": ([], P), "vxh_octree_free": ([P], None),
+        "vxh_octree_set_leaf": ([P, u32, u32, u32, u32, P], None), "vxh_octree_move_leaf": ([P, u32, u32, u32, u32, u32, P], None),
+        "vxh_octree_remove_leaf": ([P, u32, u32, u32, P], None), "vxh_octree_remove_leaf_by_id": ([P, u32, u32], C.c_int64),
+        "vxh_octree_get_leaf": ([P, u32, u32, u32], C.c_int64), "vxh_octree_compact": ([P], None),
+        "vxh_octree_construct": ([P, u32, P, u32], None), "vxh_octree_dump": ([P, P, P, u32, P, u32], None),
         "vxh_picker_serialize": ([P, u32, P, u32, P, u64], u64),
         "vxh_picker_deserialize": ([P, u32, P, u32, P, u64, P, P], None),
         "vxh_registry_new": ([], P), "vxh_registry_free": ([P], None),

@@ -1,6 +1,7 @@
 // capi.cpp — flat C entry points (vxh_*) over the C++ host mirror so that Python (ctypes) tests and
 // bench.py can drive it. The host mirror is CPU-only code; the only GPU access is through vx_* of
 // libvoxelrt inside vxh::Svo.
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -326,6 +327,79 @@ uint32_t vxh_rangebuf_ranges(void* r, int kind, VxRange* out, uint32_t cap) {
     auto& rs = kind == 0 ? ((RangeBuffer*)r)->free_ranges : ((RangeBuffer*)r)->updated_ranges;
     for (uint32_t i = 0; i < rs.size() && i < cap; ++i) out[i] = VxRange{rs[i].start, rs[i].length};
     return (uint32_t)rs.size();
+}
+
+void* vxh_rangebuf_with_capacity(uint64_t n) { return new RangeBuffer((size_t)n); }
+// id -> range table, sorted by id: out[i] = {id, start, length}
+uint32_t vxh_rangebuf_ids(void* r, uint64_t* out, uint32_t cap) {
+    auto& m = ((RangeBuffer*)r)->id_to_range;
+    std::vector<uint64_t> ids;
+    for (auto& kv : m) ids.push_back(kv.first);
+    std::sort(ids.begin(), ids.end());
+    for (uint32_t i = 0; i < ids.size() && i < cap; ++i) { out[3 * i] = ids[i]; out[3 * i + 1] = m[ids[i]].start; out[3 * i + 2] = m[ids[i]].length; }
+    return (uint32_t)ids.size();
+}
+// RangeBuffer::merge_ranges (internal.rs:252-272) on its own
+uint32_t vxh_merge_ranges(VxRange* ranges, uint32_t n) {
+    std::vector<Range> rs;
+    for (uint32_t i = 0; i < n; ++i) rs.push_back(Range{(size_t)ranges[i].offset, (size_t)ranges[i].length});
+    RangeBuffer::merge(rs);
+    for (uint32_t i = 0; i < rs.size(); ++i) ranges[i] = VxRange{rs[i].start, rs[i].length};
+    return (uint32_t)rs.size();
+}
+
+// ----------------------------------------------------------------- octree --
+// Octree<u32> alone (src/world/hds/octree.rs:508-866 tests). Results: out[0] = parent, out[1] = idx, out[2] = 1 if a value was
+// replaced / removed, out[3] = that value.
+using U32Tree = Octree<uint32_t>;
+void* vxh_octree_new(void) { return new U32Tree(); }
+void vxh_octree_free(void* t) { delete (U32Tree*)t; }
+void vxh_octree_set_leaf(void* t, uint32_t x, uint32_t y, uint32_t z, uint32_t v, int64_t out[4]) {
+    auto r = ((U32Tree*)t)->set_leaf(Position{x, y, z}, v);
+    out[0] = r.first.parent; out[1] = r.first.idx; out[2] = r.second ? 1 : 0; out[3] = r.second ? *r.second : 0;
+}
+void vxh_octree_move_leaf(void* t, uint32_t parent, uint32_t idx, uint32_t x, uint32_t y, uint32_t z, int64_t out[4]) {
+    auto r = ((U32Tree*)t)->move_leaf(LeafId{parent, (uint8_t)idx}, Position{x, y, z});
+    out[0] = r.first.parent; out[1] = r.first.idx; out[2] = r.second ? 1 : 0; out[3] = r.second ? *r.second : 0;
+}
+// out[0] = parent, out[1] = idx (or -1, -1 when nothing was there), out[2] / out[3] = removed value
+void vxh_octree_remove_leaf(void* t, uint32_t x, uint32_t y, uint32_t z, int64_t out[4]) {
+    auto r = ((U32Tree*)t)->remove_leaf(Position{x, y, z});
+    out[0] = r.second ? (int64_t)r.second->parent : -1; out[1] = r.second ? (int64_t)r.second->idx : -1;
+    out[2] = r.first ? 1 : 0; out[3] = r.first ? *r.first : 0;
+}
+int64_t vxh_octree_remove_leaf_by_id(void* t, uint32_t parent, uint32_t idx) {
+    auto r = ((U32Tree*)t)->remove_leaf_by_id(LeafId{parent, (uint8_t)idx});
+    return r ? (int64_t)*r : -1;
+}
+int64_t vxh_octree_get_leaf(void* t, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t* v = ((const U32Tree*)t)->get_leaf(Position{x, y, z});
+    return v ? (int64_t)*v : -1;
+}
+void vxh_octree_compact(void* t) { ((U32Tree*)t)->compact(); }
+// construct_octants_with(depth, f) with f = "value at the listed positions, None elsewhere"; cells = n x {x, y, z, value}
+void vxh_octree_construct(void* t, uint32_t depth, const uint32_t* cells, uint32_t n) {
+    ((U32Tree*)t)->construct_octants_with((uint8_t)depth, [&](Position p) -> std::optional<uint32_t> {
+        for (uint32_t i = 0; i < n; ++i)
+            if (cells[4 * i] == p.x && cells[4 * i + 1] == p.y && cells[4 * i + 2] == p.z) return cells[4 * i + 3];
+        return std::nullopt;
+    });
+}
+// State dump: head = {root or -1, depth, n_octants, n_free}; octants = n x 18 {parent or -1, children_count, kind[8], value[8]}
+// (kind 0 None / 1 Octant / 2 Leaf; value = octant id resp. leaf value); free = the free list in order.
+void vxh_octree_dump(void* t, int64_t head[4], int64_t* octants, uint32_t octants_cap, int64_t* free_ids, uint32_t free_cap) {
+    const U32Tree& tr = *(const U32Tree*)t;
+    head[0] = tr.root ? (int64_t)*tr.root : -1; head[1] = tr.depth(); head[2] = (int64_t)tr.octants.size(); head[3] = (int64_t)tr.free_list().size();
+    for (uint32_t i = 0; i < tr.octants.size() && i < octants_cap; ++i) {
+        const auto& o = tr.octants[i];
+        int64_t* row = octants + 18 * (size_t)i;
+        row[0] = o.parent; row[1] = o.children_count;
+        for (int k = 0; k < 8; ++k) {
+            row[2 + k] = (int64_t)o.kind[k];
+            row[10 + k] = o.kind[k] == ChildKind::Leaf ? (int64_t)*tr.leaf_value(i, (uint8_t)k) : (o.kind[k] == ChildKind::Octant ? (int64_t)o.ref[k] : 0);
+        }
+    }
+    for (uint32_t i = 0; i < tr.free_list().size() && i < free_cap; ++i) free_ids[i] = tr.free_list()[i];
 }
 
 // ----------------------------------------------------------------- picker --

@@ -37,6 +37,12 @@ public:
     std::vector<Range> updated_ranges;
     std::unordered_map<uint64_t, Range> id_to_range;
 
+    RangeBuffer() = default;
+    // with_capacity_in (internal.rs:180-194): zero-filled, one free range over all of it
+    explicit RangeBuffer(size_t initial_capacity) : bytes(initial_capacity, 0) {
+        if (initial_capacity > 0) free_ranges.push_back(Range{0, initial_capacity});
+    }
+
     size_t insert(uint64_t id, const uint8_t* buf, size_t length) {
         remove(id);
         size_t ptr = bytes.size();

@@ -50,6 +50,7 @@ public:
     std::vector<Octant> octants;
 
     uint8_t depth() const { return depth_; }
+    const std::vector<uint32_t>& free_list() const { return free_octants_; }   // octree.rs `free_list` (ids of recycled octants)
 
     void reset() {
         root.reset();

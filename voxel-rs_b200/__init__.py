@@ -256,6 +256,9 @@ def host():
         "vxh_rangebuf_insert": ([P, u64, P, u64], u64), "vxh_rangebuf_remove": ([P, u64], None),
         "vxh_rangebuf_bytes": ([P, P, u64], u64), "vxh_rangebuf_ranges": ([P, C.c_int, P, u32], u32),
         "vxh_rangebuf_with_capacity": ([u64], P), "vxh_rangebuf_ids": ([P, P, u32], u32), "vxh_merge_ranges": ([P, u32], u32),
+        "vxh_kat_shift_chunks": ([P, i32, i32, i32, u32, P, P, u32], u32), "vxh_esvo32_get_leaf": ([P, u32, u32, u32], C.c_int64),
+        "vxh_world_set_center": ([P, i32, i32, i32], C.c_int),
+        "vxh_world_load_chunk": ([P, i32, i32, i32], C.c_int), "vxh_world_remove_chunk": ([P, i32, i32, i32], None),
         "vxh_octree_new": ([], P), "vxh_octree_free": ([P], None),
         "vxh_octree_set_leaf": ([P, u32, u32, u32, u32, P], None), "vxh_octree_move_leaf": ([P, u32, u32, u32, u32, u32, P], None),
         "vxh_octree_remove_leaf": ([P, u32, u32, u32, P], None), "vxh_octree_remove_leaf_by_id": ([P, u32, u32], C.c_int64),
@@ -349,6 +352,27 @@ class World:
 
     def serialize(self):
         host().vxh_world_serialize(self.h)
+
+    def set_center(self, center):
+        """The player entered another chunk (systems::worldsvo::Svo::update, worldsvo.rs:133-137): the SVO window is re-centred and
+        every loaded chunk shifted to its new place in SVO space (shift_chunks, :158-196); chunks outside the window are dropped.
+        Chunk records stay where they are in the buffer. Returns True if the centre changed."""
+        changed = bool(host().vxh_world_set_center(self.h, int(center[0]), int(center[1]), int(center[2])))
+        self.center = tuple(int(v) for v in center)
+        return changed
+
+    def load_chunk(self, c):
+        """(Re)generates and inserts one chunk with the LOD rule (a storage / generator result arriving, worldsvo.rs:90-99)."""
+        return bool(host().vxh_world_load_chunk(self.h, int(c[0]), int(c[1]), int(c[2])))
+
+    def remove_chunk(self, c):
+        host().vxh_world_remove_chunk(self.h, int(c[0]), int(c[1]), int(c[2]))
+
+    def write_changes_to(self, gpu_buffer, reset=True):
+        """graphics::Svo::update's host half on a caller-held image of the GPU buffer (svo.rs:171-189): octree_scale at byte 0, then
+        Esvo::write_changes_to(dst = buffer + 4) = preamble + the dirty ranges only. Returns False where the reference's assert fires."""
+        gpu_buffer[:4] = np.frombuffer(np.float32(2.0 ** -self.depth).tobytes(), dtype=np.uint8)
+        return host().vxh_world_write_changes_to(self.h, C.c_void_p(gpu_buffer.ctypes.data + 4), len(gpu_buffer) - 4, int(reset)) == 0
 
     @property
     def depth(self):

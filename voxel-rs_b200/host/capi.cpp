@@ -348,6 +348,31 @@ uint32_t vxh_merge_ranges(VxRange* ranges, uint32_t n) {
     return (uint32_t)rs.size();
 }
 
+// Svo::shift_chunks on a bare Esvo<u32> (worldsvo.rs:249-375 tests). chunks = n x {x, y, z}, ids = n x {parent, idx} in/out;
+// returns the number of chunks that are still inside the window (their rows come first, in key order).
+uint32_t vxh_kat_shift_chunks(void* e, int32_t cx, int32_t cy, int32_t cz, uint32_t dst, int32_t* chunks, uint32_t* ids, uint32_t n) {
+    std::map<std::tuple<int32_t, int32_t, int32_t>, LeafId> leaf_ids;
+    for (uint32_t i = 0; i < n; ++i) leaf_ids[{chunks[3 * i], chunks[3 * i + 1], chunks[3 * i + 2]}] = LeafId{ids[2 * i], (uint8_t)ids[2 * i + 1]};
+    SvoCoordSpace cs; cs.center = ChunkPos{cx, cy, cz}; cs.dst = dst;
+    shift_chunks(cs, leaf_ids, *(Esvo<U32Leaf>*)e);
+    uint32_t k = 0;
+    for (auto& kv : leaf_ids) {
+        chunks[3 * k] = std::get<0>(kv.first); chunks[3 * k + 1] = std::get<1>(kv.first); chunks[3 * k + 2] = std::get<2>(kv.first);
+        ids[2 * k] = kv.second.parent; ids[2 * k + 1] = kv.second.idx;
+        ++k;
+    }
+    return k;
+}
+int64_t vxh_esvo32_get_leaf(void* e, uint32_t x, uint32_t y, uint32_t z) {
+    const U32Leaf* v = ((Esvo<U32Leaf>*)e)->get_leaf(Position{x, y, z});
+    return v ? (int64_t)v->v : -1;
+}
+// storage / generator results arriving for one chunk (Svo::set_chunk after serialization, worldsvo.rs:90-99) and chunk unloads (:101-108)
+int vxh_world_load_chunk(void* w, int32_t cx, int32_t cy, int32_t cz) { return ((WorldSvo*)w)->regenerate_chunk(ChunkPos{cx, cy, cz}) ? 1 : 0; }
+void vxh_world_remove_chunk(void* w, int32_t cx, int32_t cy, int32_t cz) { ((WorldSvo*)w)->remove_chunk(ChunkPos{cx, cy, cz}); }
+// the player entered another chunk: re-centre the SVO window (1 if the centre changed)
+int vxh_world_set_center(void* w, int32_t cx, int32_t cy, int32_t cz) { return ((WorldSvo*)w)->set_center(ChunkPos{cx, cy, cz}) ? 1 : 0; }
+
 // ----------------------------------------------------------------- octree --
 // Octree<u32> alone (src/world/hds/octree.rs:508-866 tests). Results: out[0] = parent, out[1] = idx, out[2] = 1 if a value was
 // replaced / removed, out[3] = that value.

@@ -153,6 +153,7 @@ public:
         return r;
     }
     std::pair<LeafId, std::optional<CsvoChunk>> move_leaf(LeafId leaf, Position to) { return octree.move_leaf(leaf, to); }
+    const CsvoChunk* get_leaf(Position pos) const { return octree.get_leaf(pos); }
     std::optional<CsvoChunk> remove_leaf(LeafId leaf) {                                                     // csvo.rs:176-183
         std::optional<CsvoChunk> v = octree.remove_leaf_by_id(leaf);
         if (v) add_change(Change{false, v->uid, LeafId{0, 0}});

@@ -19,6 +19,7 @@
 #include <map>
 #include <thread>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "csvo.hpp"
@@ -94,6 +95,42 @@ inline uint8_t calculate_lod(ChunkPos center, ChunkPos pos) {
     if (d <= 12) return 4;
     if (d <= 19) return 3;
     return 2;
+}
+
+// systems::worldsvo::Svo::shift_chunks (worldsvo.rs:158-196): after the SVO coordinate space moved to a new centre chunk, every
+// chunk leaf is moved to its new position in SVO space (replacing whatever sat there) and chunks that fell out of the window are
+// removed. Leaves are moved inside the world octree; their serialized records stay where they are in the buffer, so a shift dirties
+// only the world-root octants. `leaf_ids` is iterated in key order here (the reference iterates an FxHashMap, i.e. in an unspecified
+// order; the bookkeeping of overridden leaves makes the result independent of it).
+template <typename SvoT>
+void shift_chunks(const SvoCoordSpace& cs, std::map<std::tuple<int32_t, int32_t, int32_t>, LeafId>& leaf_ids, SvoT& svo) {
+    using LeafT = typename std::decay<decltype(*svo.get_leaf(Position{0, 0, 0}))>::type;
+    std::map<std::pair<uint32_t, uint8_t>, LeafT> overridden;
+    std::vector<std::tuple<int32_t, int32_t, int32_t>> removed;
+    for (auto& kv : leaf_ids) {
+        LeafId& leaf_id = kv.second;
+        const auto key = std::make_pair(leaf_id.parent, leaf_id.idx);
+        Position np;
+        if (!cs.cnv_chunk_pos(ChunkPos{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first)}, np)) {
+            // remove the leaf unless another moved leaf already took its slot
+            if (!overridden.count(key)) svo.remove_leaf(leaf_id);
+            overridden.erase(key);
+            removed.push_back(kv.first);
+            continue;
+        }
+        std::pair<LeafId, std::optional<LeafT>> r = [&]() {
+            auto it = overridden.find(key);
+            if (it != overridden.end()) {
+                LeafT value = std::move(it->second);
+                overridden.erase(it);
+                return svo.set_leaf(np, std::move(value), false);   // only moved: its record may already be in the buffer
+            }
+            return svo.move_leaf(leaf_id, np);
+        }();
+        leaf_id = r.first;
+        if (r.second) overridden.insert_or_assign(std::make_pair(r.first.parent, r.first.idx), std::move(*r.second));
+    }
+    for (auto& k : removed) leaf_ids.erase(k);
 }
 
 // `noise::Perlin` of the noise crate 0.8.2 (Cargo.lock:936-943; the crate source is not part of the reference checkout), restated
@@ -308,6 +345,14 @@ public:
         if (!space.cnv_chunk_pos(p, sp)) return false;
         auto r = csvo.set_leaf(sp, std::move(cc), true);
         leaf_ids[{p.x, p.y, p.z}] = r.first;
+        return true;
+    }
+
+    // systems::worldsvo::Svo::update (worldsvo.rs:133-137) + on_coord_space_change: the player entered another chunk
+    bool set_center(ChunkPos c) {
+        if (c.x == space.center.x && c.y == space.center.y && c.z == space.center.z) return false;
+        space.center = c;
+        if (format == SvoFormat::Csvo) shift_chunks(space, leaf_ids, csvo); else shift_chunks(space, leaf_ids, esvo);
         return true;
     }
 

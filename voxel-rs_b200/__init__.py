@@ -259,6 +259,9 @@ def host():
         "vxh_kat_shift_chunks": ([P, i32, i32, i32, u32, P, P, u32], u32), "vxh_esvo32_get_leaf": ([P, u32, u32, u32], C.c_int64),
         "vxh_world_set_center": ([P, i32, i32, i32], C.c_int),
         "vxh_world_load_chunk": ([P, i32, i32, i32], C.c_int), "vxh_world_remove_chunk": ([P, i32, i32, i32], None),
+        "vxh_chunkloader_new": ([u32, i32, i32], P), "vxh_chunkloader_free": ([P], None), "vxh_chunkloader_set_radius": ([P, u32], None),
+        "vxh_chunkloader_is_loaded": ([P, i32, i32, i32], C.c_int), "vxh_chunkloader_add_loaded": ([P, i32, i32, i32, u32], None),
+        "vxh_chunkloader_loaded_count": ([P], u64), "vxh_chunkloader_update": ([P, f, f, f, P, u64], u64),
         "vxh_octree_new": ([], P), "vxh_octree_free": ([P], None),
         "vxh_octree_set_leaf": ([P, u32, u32, u32, u32, P], None), "vxh_octree_move_leaf": ([P, u32, u32, u32, u32, u32, P], None),
         "vxh_octree_remove_leaf": ([P, u32, u32, u32, P], None), "vxh_octree_remove_leaf_by_id": ([P, u32, u32], C.c_int64),
@@ -456,6 +459,53 @@ class World:
         o = np.zeros(3, dtype=np.uint32)
         ok = host().vxh_world_cnv_chunk_pos(self.h, c[0], c[1], c[2], _ptr(o))
         return tuple(int(v) for v in o) if ok else None
+
+
+class ChunkLoader:
+    """systems::chunkloader::ChunkLoader (src/systems/chunkloader.rs): update(pos) -> [(kind, (x, y, z), lod)] with kind "load" /
+    "unload" / "lod", nearest chunks first."""
+    KINDS = ("load", "unload", "lod")
+
+    def __init__(self, radius, start_y=0, end_y=8):
+        self.h = host().vxh_chunkloader_new(radius, start_y, end_y)
+        if not self.h:
+            raise VxError("ChunkLoader: start_y < end_y required")   # the reference's assert!, chunkloader.rs:35
+        self.radius = radius
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            host().vxh_chunkloader_free(self.h)
+            self.h = None
+
+    def update(self, pos):
+        r = self.radius
+        cap = (2 * r + 1) ** 2 * 64 + 64
+        out = np.zeros((cap, 5), dtype=np.int32)
+        n = host().vxh_chunkloader_update(self.h, float(pos[0]), float(pos[1]), float(pos[2]), _ptr(out), cap)
+        assert n <= cap
+        return [(self.KINDS[k], (int(x), int(y), int(z)), int(lod)) for k, x, y, z, lod in out[:n]]
+
+    def is_loaded(self, c):
+        return bool(host().vxh_chunkloader_is_loaded(self.h, int(c[0]), int(c[1]), int(c[2])))
+
+    @property
+    def loaded_count(self):
+        return host().vxh_chunkloader_loaded_count(self.h)
+
+
+def follow(world, loader, cam_pos):
+    """One streaming step of gamelogic::World::update (src/gamelogic/world.rs:116-210) without the job system: the chunk loader's events
+    for the new camera position are applied to the world (load = generate + serialize with the LOD rule, unload = remove, LOD change =
+    serialize again) and the SVO window is re-centred on the camera's chunk. Returns the events. Call world.serialize() afterwards."""
+    events = loader.update(cam_pos)
+    center = tuple(int(v) >> 5 for v in cam_pos)            # ChunkPos::from(camera.position), chunk.rs:150-152,175-178
+    world.set_center(center)
+    for kind, c, lod in events:
+        if kind == "unload":
+            world.remove_chunk(c)
+        else:
+            world.load_chunk(c)
+    return events
 
 
 # ---------------------------------------------------------------- registry --

@@ -12,6 +12,7 @@
 #include "picker.hpp"
 #include "svo.hpp"
 #include "world.hpp"
+#include "chunkloader.hpp"
 
 using namespace vxh;
 
@@ -368,10 +369,27 @@ int64_t vxh_esvo32_get_leaf(void* e, uint32_t x, uint32_t y, uint32_t z) {
     return v ? (int64_t)v->v : -1;
 }
 // storage / generator results arriving for one chunk (Svo::set_chunk after serialization, worldsvo.rs:90-99) and chunk unloads (:101-108)
-int vxh_world_load_chunk(void* w, int32_t cx, int32_t cy, int32_t cz) { return ((WorldSvo*)w)->regenerate_chunk(ChunkPos{cx, cy, cz}) ? 1 : 0; }
+int vxh_world_load_chunk(void* w, int32_t cx, int32_t cy, int32_t cz) { return ((WorldSvo*)w)->load_chunk(ChunkPos{cx, cy, cz}) ? 1 : 0; }
 void vxh_world_remove_chunk(void* w, int32_t cx, int32_t cy, int32_t cz) { ((WorldSvo*)w)->remove_chunk(ChunkPos{cx, cy, cz}); }
 // the player entered another chunk: re-centre the SVO window (1 if the centre changed)
 int vxh_world_set_center(void* w, int32_t cx, int32_t cy, int32_t cz) { return ((WorldSvo*)w)->set_center(ChunkPos{cx, cy, cz}) ? 1 : 0; }
+
+// ------------------------------------------------------------ chunk loader --
+// systems::chunkloader::ChunkLoader. Events: rows of {kind (0 Load, 1 Unload, 2 LodChange), x, y, z, lod}.
+void* vxh_chunkloader_new(uint32_t radius, int32_t start_y, int32_t end_y) { return start_y < end_y ? new ChunkLoader(radius, start_y, end_y) : nullptr; }
+void vxh_chunkloader_free(void* l) { delete (ChunkLoader*)l; }
+void vxh_chunkloader_set_radius(void* l, uint32_t r) { ((ChunkLoader*)l)->set_radius(r); }
+int vxh_chunkloader_is_loaded(void* l, int32_t x, int32_t y, int32_t z) { return ((ChunkLoader*)l)->is_loaded(ChunkPos{x, y, z}) ? 1 : 0; }
+void vxh_chunkloader_add_loaded(void* l, int32_t x, int32_t y, int32_t z, uint32_t lod) { ((ChunkLoader*)l)->add_loaded_chunk(ChunkPos{x, y, z}, (uint8_t)lod); }
+uint64_t vxh_chunkloader_loaded_count(void* l) { return ((ChunkLoader*)l)->loaded_count(); }
+// Returns the number of events; the loader's state always advances, `out` receives the first `cap` of them.
+uint64_t vxh_chunkloader_update(void* l, float x, float y, float z, int32_t* out, uint64_t cap) {
+    std::vector<ChunkEvent> ev = ((ChunkLoader*)l)->update(x, y, z);
+    for (uint64_t i = 0; i < ev.size() && i < cap; ++i) {
+        out[5 * i] = ev[i].kind; out[5 * i + 1] = ev[i].pos.x; out[5 * i + 2] = ev[i].pos.y; out[5 * i + 3] = ev[i].pos.z; out[5 * i + 4] = ev[i].lod;
+    }
+    return ev.size();
+}
 
 // ----------------------------------------------------------------- octree --
 // Octree<u32> alone (src/world/hds/octree.rs:508-866 tests). Results: out[0] = parent, out[1] = idx, out[2] = 1 if a value was

@@ -387,6 +387,14 @@ public:
         return set_chunk(p, SerializedChunk::from_dense(p.x, p.y, p.z, chunk_uid(p), blocks.data(), lod_for(p)));
     }
 
+    // A Load / LodChange event for one chunk as the reference handles it: NopStorage has nothing, the generator takes the chunk only if
+    // its column's height span touches it (Generator::is_interested_in, worldgen.rs:270-273), then it is serialized with the LOD rule
+    bool load_chunk(ChunkPos p) {
+        Column col = make_column(p.x, p.z);
+        if (!column_contains(col, p.y) && !edits.count({p.x, p.y, p.z})) { remove_chunk(p); return false; }
+        return regenerate_chunk(p);
+    }
+
     // Loads every chunk of the disc of radius `dst` around `center` for world y-chunks [y0, y1]
     // (ChunkLoader::new(radius, 0, 8), gamelogic/world.rs:85), nearest columns first
     // (chunkloader.rs:116-120). Chunk serialisation runs on `threads` workers like the reference's job

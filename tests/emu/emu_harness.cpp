@@ -1,0 +1,263 @@
+// emu_harness.cpp — runs the product's CUDA kernels (voxel-rs_b200/csrc/kernels.cuh, compiled for the host through the stand-in
+// cuda_runtime.h of this directory) on CPU fibers. TEST INFRASTRUCTURE: tests/test_kernels_emulated.py compares what comes out with
+// the oracle. The host-side sequence below restates launch_wavefront / prepare_render / vx_set_textures / launch_raycast of
+// csrc/voxelrt.cu (which cannot be compiled without nvcc: it uses <<< >>> and the CUDA runtime).
+#include <cuda_runtime.h>   // the stand-in
+
+#include <cstdio>
+#include <functional>
+#include <vector>
+
+#include "../../voxel-rs_b200/csrc/kernels.cuh"
+
+namespace emu {
+Lane* cur = nullptr;
+ucontext_t scheduler;
+char* smem_base = nullptr;
+unsigned long long collectives = 0, switches = 0;
+static std::function<void()> kernel_body;
+static std::vector<char> stacks;
+static const size_t STACK_BYTES = 256 * 1024;
+
+static void fiber_main() {
+    kernel_body();
+    Lane* me = cur;
+    me->done = true;
+    // a lane that leaves while others wait for it would hang them: complete what it was the last one missing from
+    Warp* w = me->warp;
+    if (--w->live && w->arrived == w->live) { std::memcpy(w->out[w->gen & 1u], w->in, sizeof(w->in)); w->arrived = 0; ++w->gen; }
+    Cta* c = me->cta;
+    if (--c->live && c->arrived == c->live) { c->arrived = 0; ++c->gen; }
+    // returning switches to uc_link = the scheduler
+}
+
+// One kernel launch: CTAs run one after the other, the `threads` CUDA threads of a CTA as cooperating fibers.
+static void launch(unsigned grid, unsigned threads, const std::function<void()>& body) {
+    kernel_body = body;
+    if (stacks.size() < (size_t)threads * STACK_BYTES) stacks.resize((size_t)threads * STACK_BYTES);
+    const unsigned n_warps = (threads + 31) / 32;
+    std::vector<Warp> warps(n_warps);
+    std::vector<Lane> lanes(threads);
+    for (unsigned b = 0; b < grid; ++b) {
+        Cta cta;
+        cta.live = threads;
+        for (unsigned w = 0; w < n_warps; ++w) { warps[w] = Warp(); warps[w].live = std::min(32u, threads - 32u * w); }
+        for (unsigned t = 0; t < threads; ++t) {
+            Lane& l = lanes[t];
+            l = Lane();
+            l.tid.x = t; l.bid.x = b; l.bdim.x = threads; l.gdim.x = grid;
+            l.lane = t & 31u; l.warp = &warps[t >> 5]; l.cta = &cta;
+            getcontext(&l.ctx);
+            l.ctx.uc_stack.ss_sp = stacks.data() + (size_t)t * STACK_BYTES;
+            l.ctx.uc_stack.ss_size = STACK_BYTES;
+            l.ctx.uc_link = &scheduler;
+            makecontext(&l.ctx, fiber_main, 0);
+        }
+        for (;;) {
+            bool alive = false, progressed = false;
+            for (Lane& l : lanes) {
+                if (l.done) continue;
+                alive = true;
+                if (l.wait_word && *l.wait_word == l.wait_value) continue;
+                l.wait_word = nullptr;
+                cur = &l;
+                swapcontext(&scheduler, &l.ctx);
+                progressed = true;
+            }
+            if (!alive) break;
+            if (!progressed) { std::fprintf(stderr, "emu: deadlock in CTA %u (a collective not reached by every live lane)\n", b); std::abort(); }
+        }
+    }
+    cur = nullptr;
+}
+}  // namespace emu
+
+namespace vx {
+thread_local uint32_t smem_raw[64 * 1024];   // the CTA's dynamic shared memory (extern __shared__ uint32_t smem_raw[] in the kernels)
+}
+
+using namespace vx;
+
+namespace {
+
+struct Device {   // what VxCtx holds on the GPU
+    std::vector<uint32_t> world;      // 8 bytes of slack in front are not needed here; guard words behind the capacity are
+    size_t capacity = 0;
+    uint32_t fmt = 0, depth = 0;
+    std::vector<Material> materials;
+    std::vector<uint32_t> texels;
+    TexInfo texinfo{};
+    float unorm[256];
+    unsigned long long opaque_materials = 0;
+};
+
+void upload(Device& d, const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
+            const uint8_t* rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels) {
+    d.fmt = (uint32_t)fmt; d.depth = depth;
+    d.capacity = ((size_t)world_bytes + 255) / 4 * 4;
+    d.world.assign(d.capacity / 4 + 16, 0u);                                  // + the zero guard words of vx_create (cap + 64 bytes)
+    std::memcpy(d.world.data(), world, world_bytes);
+    static_assert(sizeof(Material) == sizeof(VxMaterial), "material layout");
+    d.materials.resize(n_materials);
+    std::memcpy(d.materials.data(), materials, n_materials * sizeof(Material));
+    emu::smem_base = reinterpret_cast<char*>(vx::smem_raw);
+    emu::launch(1, 256, [&] { unorm_kernel(d.unorm); });
+    // vx_set_textures: level count, offsets, mip chain and opacity bits (voxelrt.cu)
+    uint32_t m = tw < th ? tw : th, il = 0;
+    while ((m >> (il + 1)) != 0) ++il;
+    uint32_t levels = mip_levels < il ? mip_levels : il;
+    if (levels < 1) levels = 1;
+    if (levels > 16) levels = 16;
+    size_t total = 0;
+    uint32_t off[16] = {};
+    for (uint32_t l = 0; l < levels; ++l) {
+        uint32_t wl = tw >> l, hl = th >> l;
+        wl = wl ? wl : 1; hl = hl ? hl : 1;
+        off[l] = (uint32_t)total;
+        total += (size_t)wl * hl * layers;
+    }
+    d.texels.assign(total, 0u);
+    std::memcpy(d.texels.data(), rgba8, (size_t)tw * th * layers * 4);
+    for (uint32_t l = 1; l < levels; ++l) {
+        uint32_t pw = tw >> (l - 1), ph = th >> (l - 1), cw = tw >> l, ch = th >> l;
+        pw = pw ? pw : 1; ph = ph ? ph : 1; cw = cw ? cw : 1; ch = ch ? ch : 1;
+        const uint32_t n = cw * ch * layers;
+        emu::launch((n + 255) / 256, 256, [&] { mip_kernel(d.texels.data() + off[l - 1], d.texels.data() + off[l], pw, ph, cw, ch, layers); });
+    }
+    d.texinfo = TexInfo{};
+    d.texinfo.texels = d.texels.data(); d.texinfo.w = tw; d.texinfo.h = th; d.texinfo.layers = layers; d.texinfo.levels = levels;
+    for (int i = 0; i < 16; ++i) d.texinfo.off[i] = off[i];
+    d.texinfo.opaque_layers = layers >= 64 ? ~0ull : ((1ull << layers) - 1ull);
+    for (uint32_t l = 0; l < levels; ++l) {
+        uint32_t wl = tw >> l, hl = th >> l;
+        wl = wl ? wl : 1; hl = hl ? hl : 1;
+        const uint32_t n = wl * hl * layers;
+        emu::launch((n + 255) / 256, 256, [&] { opaque_kernel(d.texels.data() + off[l], wl * hl, layers, &d.texinfo.opaque_layers); });
+    }
+    d.opaque_materials = 0;   // update_opaque_materials
+    for (size_t i = 0; i < d.materials.size() && i < 64; ++i) {
+        const int ids[3] = {d.materials[i].tex_top, d.materials[i].tex_side, d.materials[i].tex_bottom};
+        bool ok = true;
+        for (int id : ids) {
+            const int layer = id < 0 ? 0 : (id >= (int)layers ? (int)layers - 1 : id);
+            ok = ok && layer < 64 && ((d.texinfo.opaque_layers >> layer) & 1ull);
+        }
+        if (ok) d.opaque_materials |= 1ull << i;
+    }
+}
+
+Scene make_scene(const Device& d) {   // voxelrt.cu make_scene
+    Scene s{};
+    const size_t desc_off = d.fmt == VX_FMT_CSVO ? 8 : 4;
+    s.desc = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(d.world.data()) + desc_off);
+    s.desc_words = (uint32_t)((d.capacity - desc_off) / 4);
+    s.format = d.fmt;
+    s.max_rec = s.desc_words - 12;
+    s.opaque_materials = d.opaque_materials;
+    s.materials = d.materials.data(); s.n_materials = (uint32_t)d.materials.size();
+    s.tex = &d.texinfo;
+    s.unorm = d.unorm;
+    const uint32_t levels = d.depth + (d.fmt == VX_FMT_CSVO ? 3 : 1);
+    s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
+    return s;
+}
+
+}  // namespace
+
+// The library is built with -fvisibility=hidden -Wl,-Bsymbolic: its kernels carry the same C++ names as the host-side launch stubs
+// that nvcc puts into libvoxelrt.so (loaded RTLD_GLOBAL by the package), and must not be interposed by them.
+#define EMU_API __attribute__((visibility("default")))
+
+extern "C" {
+
+// One frame through trace_primary_kernel -> shade_kernel -> trace_shadow_kernel exactly as vx_render issues them.
+// options: [0] refill threshold, [1] shadow refill (0 = same), [2] CTAs of the persistent kernels, [3] count, [4] RGBA8 output,
+// [5] TMA-style tile write-back, [6] shard rank, [7] shard size
+EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
+               const uint8_t* tex_rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels, const VxRenderParams* p, uint32_t width,
+               uint32_t height, const uint32_t options[8], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
+    Device d;
+    upload(d, world, world_bytes, fmt, depth, materials, n_materials, tex_rgba8, tw, th, layers, mip_levels);
+    RenderArgs a{};
+    a.scene = make_scene(d);
+    std::memcpy(a.u.view, p->view, sizeof(a.u.view));
+    a.u.tan_half_fov = tanf(p->fov_y_rad * 0.5f);
+    a.u.aspect = p->aspect_ratio; a.u.ambient = p->ambient_intensity;
+    a.u.lx = p->light_dir[0]; a.u.ly = p->light_dir[1]; a.u.lz = p->light_dir[2];
+    a.u.cx = p->cam_pos[0]; a.u.cy = p->cam_pos[1]; a.u.cz = p->cam_pos[2];
+    a.u.hx = p->highlight_pos[0]; a.u.hy = p->highlight_pos[1]; a.u.hz = p->highlight_pos[2];
+    a.u.render_shadows = p->render_shadows; a.u.shadow_distance = p->shadow_distance;
+    a.u.width = width; a.u.height = height;
+    a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
+    const size_t slots = (size_t)a.macro_x * a.macro_y * 512;
+    std::vector<float4> hit0(slots), hit1(slots), sh0(slots), sh1(slots), frame((size_t)width * height, float4{-1, -1, -1, -1});
+    std::vector<uint32_t> sh_pix(slots), frame8((size_t)width * height, 0xdeadbeefu);
+    Counters counters{};
+    unsigned int work[8] = {};
+    a.frame = frame.data();
+    a.frame8 = options[4] ? frame8.data() : nullptr;
+    a.hit0 = hit0.data(); a.hit1 = hit1.data(); a.sh0 = sh0.data(); a.sh1 = sh1.data(); a.sh_pix = sh_pix.data();
+    a.counters = &counters;
+    a.shard_rank = options[6]; a.shard_size = options[7] ? options[7] : 1;
+    a.refill_threshold = options[0] ? options[0] : 1;
+    a.shadow_refill = options[1] ? options[1] : a.refill_threshold;
+    a.tma_writeback = options[5];
+    // launch_wavefront over the whole frame
+    a.macro0 = 0; a.n_macros = a.macro_x * a.macro_y;
+    a.first_owned = a.macro0 + ((a.shard_rank + a.shard_size - (a.macro0 % a.shard_size)) % a.shard_size);
+    const uint32_t band_end = a.macro0 + a.n_macros;
+    const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + a.shard_size - 1) / a.shard_size : 0;
+    a.n_owned = owned;
+    a.shadow_count = work + 4;
+    a.fetch_tiles = 1;
+    const bool count = options[3] != 0, csvo = fmt == VX_FMT_CSVO;
+    const unsigned grid = options[2] ? options[2] : 3;
+    if (owned) {
+        a.work_counter = work;
+        emu::launch(grid, VX_THREADS, [&] {
+            if (csvo) { if (count) trace_primary_kernel<VX_FMT_CSVO, true, 8>(a); else trace_primary_kernel<VX_FMT_CSVO, false, 8>(a); }
+            else { if (count) trace_primary_kernel<VX_FMT_ESVO, true, 8>(a); else trace_primary_kernel<VX_FMT_ESVO, false, 8>(a); }
+        });
+        emu::launch(owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true>(a); else shade_kernel<false>(a); });
+        if (p->render_shadows) {
+            a.work_counter = work + 2;
+            emu::launch(grid, VX_THREADS, [&] {
+                if (csvo) { if (count) trace_shadow_kernel<VX_FMT_CSVO, true, 8>(a); else trace_shadow_kernel<VX_FMT_CSVO, false, 8>(a); }
+                else { if (count) trace_shadow_kernel<VX_FMT_ESVO, true, 8>(a); else trace_shadow_kernel<VX_FMT_ESVO, false, 8>(a); }
+            });
+        }
+    }
+    if (frame_out) std::memcpy(frame_out, frame.data(), frame.size() * sizeof(float4));
+    if (frame8_out) std::memcpy(frame8_out, frame8.data(), frame8.size() * 4);
+    if (counters_out) std::memcpy(counters_out, &counters, sizeof(Counters));
+    return 0;
+}
+
+// vx_raycast: one trace_picker_kernel launch over n tasks. options: [0] refill threshold, [2] CTAs, [3] count
+EMU_API int emu_raycast(const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
+                const uint8_t* tex_rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels, const VxPickerTask* tasks, uint64_t n,
+                VxPickerResult* results, const uint32_t options[8], uint64_t counters_out[6]) {
+    Device d;
+    upload(d, world, world_bytes, fmt, depth, materials, n_materials, tex_rgba8, tw, th, layers, mip_levels);
+    RaycastArgs a{};
+    a.scene = make_scene(d);
+    a.tasks = reinterpret_cast<const float4*>(tasks);
+    a.results = reinterpret_cast<float4*>(results);
+    a.n = n;
+    Counters counters{};
+    unsigned long long work = 0;
+    a.counters = &counters;
+    a.work_counter = &work;
+    a.refill_threshold = options[0] ? options[0] : 24;
+    const bool count = options[3] != 0, csvo = fmt == VX_FMT_CSVO;
+    emu::launch(options[2] ? options[2] : 3, VX_THREADS, [&] {
+        if (csvo) { if (count) trace_picker_kernel<VX_FMT_CSVO, true>(a); else trace_picker_kernel<VX_FMT_CSVO, false>(a); }
+        else { if (count) trace_picker_kernel<VX_FMT_ESVO, true>(a); else trace_picker_kernel<VX_FMT_ESVO, false>(a); }
+    });
+    if (counters_out) std::memcpy(counters_out, &counters, sizeof(Counters));
+    return 0;
+}
+
+EMU_API void emu_stats(uint64_t out[2]) { out[0] = emu::collectives; out[1] = emu::switches; }
+
+}  // extern "C"

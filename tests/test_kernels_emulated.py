@@ -1,0 +1,161 @@
+"""The product's CUDA kernels run on the CPU. tests/emu compiles voxel-rs_b200/csrc/{traverse,kernels}.cuh with g++ (a stand-in
+cuda_runtime.h: every CUDA thread a fiber, warp collectives and __syncthreads as rendezvous, one CTA at a time) and issues the same
+kernel sequence as vx_render / vx_raycast. What comes out is compared with the oracle like the -m gpu tests do on the B200, so the
+logic of the kernels (warp-level work fetch, refill, hit records, shadow-list compaction, traversal, shading, both SVO formats) is
+checked on every CPU run. It says nothing about timing, the memory model or the PTX paths (those stay with the GPU tests); the GPU
+build is unaffected: the only source difference is behind `#ifdef VX_HOST_EMULATION`, which nvcc never defines."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emu(pkg):
+    src = [os.path.join(EMU, "emu_harness.cpp"), os.path.join(EMU, "cuda_runtime.h"), os.path.join(ROOT, "include", "voxelrt.h"),
+           os.path.join(ROOT, "voxel-rs_b200", "csrc", "kernels.cuh"), os.path.join(ROOT, "voxel-rs_b200", "csrc", "traverse.cuh")]
+    out = os.path.join(EMU, "libkernels_emu.so")
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read().split() else []
+        # the numeric contract of the CUDA build (--fmad=false, IEEE) and of the oracle: no contraction, no fast-math
+        subprocess.check_call([cxx, "-O1", "-std=c++17", "-fPIC", "-shared", *fma, "-ffp-contract=off", "-fno-fast-math", "-fno-extern-tls-init", "-fvisibility=hidden", "-Wl,-Bsymbolic",
+                               "-Wno-unknown-pragmas",
+                               "-I", EMU, "-o", out, src[0]])
+    lib = C.CDLL(out)
+    lib.emu_render.restype = C.c_int
+    lib.emu_raycast.restype = C.c_int
+    return lib
+
+
+def scene_args(world, reg):
+    buf = world.gpu_buffer()
+    mats = reg.materials()
+    tex, mips = reg.textures()
+    tex = np.ascontiguousarray(tex)
+    layers, th, tw = tex.shape[0], tex.shape[1], tex.shape[2]
+    keep = (buf, mats, tex)
+    return keep, [C.c_void_p(buf.ctypes.data), C.c_uint64(len(buf)), C.c_int(world.fmt), C.c_uint32(world.depth), C.c_void_p(mats.ctypes.data),
+                  C.c_uint32(len(mats)), C.c_void_p(tex.ctypes.data), C.c_uint32(tw), C.c_uint32(th), C.c_uint32(layers), C.c_uint32(mips)]
+
+
+def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1):
+    return (C.c_uint32 * 8)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size)
+
+
+def emu_render(emu, pkg, world, reg, vxp, w, h, **kw):
+    keep, args = scene_args(world, reg)
+    frame = np.zeros((h, w, 4), np.float32)
+    frame8 = np.zeros((h, w, 4), np.uint8)
+    cnt = (C.c_uint64 * 6)()
+    rc = emu.emu_render(*args, C.byref(vxp), C.c_uint32(w), C.c_uint32(h), opts(**kw), C.c_void_p(frame.ctypes.data), C.c_void_p(frame8.ctypes.data), cnt)
+    assert rc == 0
+    names = ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")
+    return frame, frame8, dict(zip(names, [int(v) for v in cnt]))
+
+
+def oracle_render(pkg, ora, world, reg, vxp, w, h):
+    img, cnt = helpers.oracle_scene(ora, world, reg).render(vxp, w, h)
+    return img, ora.to_rgba8(img), cnt
+
+
+def world_params(pkg, world, w, h, shadows=True, selected=None):
+    p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, -0.3, 0.0), fov_y_deg=72.0, aspect=w / h, render_shadows=shadows,
+                          selected_voxel=selected)
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+    q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+    if selected is not None:
+        q.selected_voxel = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.selected_voxel)))
+    return pkg.to_vx_render_params(q)
+
+
+@pytest.fixture(scope="module")
+def terrains(pkg):
+    out = {}
+    for fmt in (0, 1):
+        w = pkg.World(radius=5, center=(-1, 2, 5), seed=1, fmt=fmt)
+        w.generate(0, 8)
+        w.serialize()
+        out[fmt] = w
+    return out, pkg.content_registry(pkg.load_atlas())
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_emulated_frame_equals_oracle(emu, pkg, ora, terrains, fmt):
+    """Terrain frame with LOD chunks, the trilinear texture path, shadows and the highlighted voxel through the three kernels: float
+    frame, RGBA8 frame and all six counters equal the oracle's — for refill thresholds 1 / 8 / 32, 1 and 5 persistent CTAs."""
+    worlds, reg = terrains
+    world = worlds[fmt]
+    w, h = 72, 44                                  # ragged: 3 macro columns (one partial), 3 macro rows (one partial)
+    vxp = world_params(pkg, world, w, h, selected=(-20.0, 50.0, 174.0))
+    want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
+    assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]
+    for refill, ctas in ((1, 3), (8, 1), (32, 5)):
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, ctas=ctas)
+        assert got.tobytes() == want.tobytes(), (fmt, refill, float(np.abs(got - want).max()))
+        assert c == cnt, (fmt, refill, c, cnt)
+    # RGBA8 output mode (vx_set_option 8 / vx_render_read_rgba8) and the staged tile write-back (vx_set_option 9)
+    _, got8, _ = emu_render(emu, pkg, world, reg, vxp, w, h, rgba8=1)
+    assert got8.tobytes() == want8.tobytes()
+    got, _, _ = emu_render(emu, pkg, world, reg, vxp, w, h, tma=1)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_emulated_shards_tile_the_frame(emu, pkg, ora, terrains):
+    """Image-space shards (macro block m belongs to rank m % size): every pixel is written by exactly one of the 3 ranks, with the
+    value of the unsharded frame; rays are counted once."""
+    worlds, reg = terrains
+    world = worlds[0]
+    w, h = 100, 40
+    vxp = world_params(pkg, world, w, h)
+    want, _, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
+    union = np.full((h, w, 4), -1.0, np.float32)
+    total = {k: 0 for k in cnt}
+    for rank in range(3):
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, rank=rank, size=3)
+        mine = got[..., 3] != -1.0                 # untouched pixels keep the harness's -1 fill (alpha is never negative)
+        assert not (mine & (union[..., 3] != -1.0)).any()
+        union[mine] = got[mine]
+        for k in c:
+            total[k] += c[k]
+    assert union.tobytes() == want.tobytes() and total == cnt
+
+
+def test_emulated_reference_scene(emu, pkg, ora):
+    """svo_tests::render's scene (src/graphics/svo.rs:342-399) at a quarter of its size: normal maps, specular, shadows, highlight."""
+    reg = helpers.svo_render_test_registry(pkg, pkg.load_atlas())
+    world = pkg.World()
+    world.set_leaf_blocks((0, 0, 0), helpers.svo_render_test_blocks(), compact=False)
+    world.serialize()
+    w, h = 160, 122
+    vxp = pkg.to_vx_render_params(helpers.svo_render_test_params(pkg, w, h))
+    want, _, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
+    got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h)
+    assert got.tobytes() == want.tobytes() and c == cnt
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_emulated_picker_equals_oracle(emu, pkg, ora, terrains, fmt):
+    """trace_picker_kernel (picker.glsl): 3000 random rays (ragged last run), unlimited and max_dst = 30, refill 24 and 1."""
+    import bench
+    worlds, reg = terrains
+    world = worlds[fmt]
+    scene = helpers.oracle_scene(ora, world, reg)
+    keep, args = scene_args(world, reg)
+    for max_dst, refill in ((-1.0, 24), (30.0, 1)):
+        tasks = bench.picker_tasks(pkg, world, 5, 3000, seed=3, max_dst=max_dst)
+        want, cnt = scene.raycast(tasks)
+        got = np.zeros(len(tasks), dtype=pkg.RESULT_DTYPE)
+        c = (C.c_uint64 * 6)()
+        assert emu.emu_raycast(*args, C.c_void_p(tasks.ctypes.data), C.c_uint64(len(tasks)), C.c_void_p(got.ctypes.data), opts(refill=refill), c) == 0
+        assert got.tobytes() == want.tobytes(), (fmt, max_dst)
+        assert (int(c[2]), int(c[3]), int(c[4])) == (cnt["steps"], cnt["pushes"], cnt["leaf_tests"])
+        assert 0 < int((got["dst"] > 0).sum()) < len(tasks)

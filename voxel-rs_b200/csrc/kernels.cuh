@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
             else store_pixel(a, pix, outc);
         }
     }
+#ifndef VX_HOST_EMULATION
     if (tile_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the async (TMA) proxy
+#endif
     // compact the shadow rays of this strip into the global list: one atomicAdd per CTA, strip order kept inside it
     const unsigned m = __ballot_sync(0xffffffffu, want_shadow);
     if (lane == 0) s_warp_count[warp] = __popc(m);
@@ -325,10 +327,14 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     if (tile_store && threadIdx.x >= 32 && threadIdx.x < 36) {   // one bulk copy per row of the tile (lanes 0-3 of warp 1; warp 0 does the atomic)
         const uint32_t row = threadIdx.x - 32u;
         const float4* dst = a.frame + (size_t)(y0 + row) * a.u.width + x0;
+#ifndef VX_HOST_EMULATION
         const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_tile + row * 32u);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(dst), "r"(src) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#else
+        for (uint32_t k = 0; k < 32u; ++k) const_cast<float4*>(dst)[k] = s_tile[row * 32u + k];   // what the bulk copy moves
+#endif
     }
     __syncthreads();
     if (want_shadow) {
@@ -600,7 +606,11 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
 // reached `value`; gives up after ~2 s and records it in flags[63] so that a lost peer shows up as an error, not as a hang.
 __global__ void flag_signal_kernel(unsigned int* flag, unsigned int value) {
     __threadfence_system();
+#ifndef VX_HOST_EMULATION
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+#else
+    *flag = value;
+#endif
 }
 __global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsigned int count, unsigned int value, unsigned int* error_word) {
     const unsigned int i = threadIdx.x;
@@ -608,7 +618,11 @@ __global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsign
         unsigned int v = 0;
         unsigned int spins = 0;
         for (;;) {
+#ifndef VX_HOST_EMULATION
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + first + i) : "memory");
+#else
+            v = flags[first + i];
+#endif
             if ((int)(v - value) >= 0) break;
             __nanosleep(200);
             if (++spins > (1u << 23)) { atomicAdd(error_word, 1u); break; }

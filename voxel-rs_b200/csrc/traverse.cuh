@@ -314,17 +314,27 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
 // Per-thread traversal stack access. `stk` is the SHARED-space byte address of this thread's column (Smem::stack_addr),
 // kept in one register and made opaque to the compiler (it otherwise re-derives it from %tid and the CTA's shared window
 // in every loop iteration: 6 instructions, 6 % of the trace kernels — profiles/r01_v3_frame_wavefront.md).
+// (VX_HOST_EMULATION: tests/emu compiles these headers with g++ and runs the kernels on CPU fibers against the oracle; the PTX is
+// then replaced by the same accesses on the emulated shared window. nvcc never defines it.)
 __device__ __forceinline__ void stack_store(uint32_t stk, uint32_t lvl, uint32_t rec, uint32_t desc, float t_max) {
     const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+#ifndef VX_HOST_EMULATION
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(rec) : "memory");
     asm volatile("st.shared.u32 [%0+512], %1;" ::"r"(a), "r"(desc) : "memory");
     asm volatile("st.shared.f32 [%0+1024], %1;" ::"r"(a), "f"(t_max) : "memory");
+#else
+    vx_emu_shared_u32(a) = rec; vx_emu_shared_u32(a + 512u) = desc; vx_emu_shared_u32(a + 1024u) = __float_as_uint(t_max);
+#endif
 }
 __device__ __forceinline__ void stack_load(uint32_t stk, uint32_t lvl, uint32_t& rec, uint32_t& desc, float& t_max) {
     const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+#ifndef VX_HOST_EMULATION
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rec) : "r"(a) : "memory");
     asm volatile("ld.shared.u32 %0, [%1+512];" : "=r"(desc) : "r"(a) : "memory");
     asm volatile("ld.shared.f32 %0, [%1+1024];" : "=f"(t_max) : "r"(a) : "memory");
+#else
+    rec = vx_emu_shared_u32(a); desc = vx_emu_shared_u32(a + 512u); t_max = __uint_as_float(vx_emu_shared_u32(a + 1024u));
+#endif
 }
 static_assert(VX_THREADS == 128, "stack_store/stack_load hard-code the 512-byte word stride of a 128-thread CTA");
 

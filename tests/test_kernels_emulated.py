@@ -159,3 +159,69 @@ def test_emulated_picker_equals_oracle(emu, pkg, ora, terrains, fmt):
         assert got.tobytes() == want.tobytes(), (fmt, max_dst)
         assert (int(c[2]), int(c[3]), int(c[4])) == (cnt["steps"], cnt["pushes"], cnt["leaf_tests"])
         assert 0 < int((got["dst"] > 0).sum()) < len(tasks)
+
+
+def emu_raycast(emu, pkg, world, reg, tasks, **kw):
+    keep, args = scene_args(world, reg)
+    got = np.zeros(max(len(tasks), 1), dtype=pkg.RESULT_DTYPE)
+    c = (C.c_uint64 * 6)()
+    assert emu.emu_raycast(*args, C.c_void_p(tasks.ctypes.data if len(tasks) else got.ctypes.data), C.c_uint64(len(tasks)), C.c_void_p(got.ctypes.data),
+                           opts(**kw), c) == 0
+    return got[:len(tasks)], {"steps": int(c[2]), "pushes": int(c[3]), "leaf_tests": int(c[4])}
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_emulated_translucent_world(emu, pkg, ora, fmt):
+    """The bundled Minecraft world fixture (water, leaves: texels with alpha 0): primary and shadow rays pass through translucent
+    leaves by the rule of svo.esvo.glsl:241-242 / 264-265 — render_leaf, translucent_leaf_accepts and walk_skip_leaf in both kernels."""
+    reg = pkg.content_registry(pkg.load_atlas())
+    world = helpers.mc_world(pkg, fmt)
+    w, h = 96, 54
+    p = helpers.mc_params(pkg, w, h, shadows=True)
+    q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+    q.cam_pos = (C.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+    vxp = pkg.to_vx_render_params(q)
+    want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
+    assert cnt["leaf_tests"] > 1.3 * (cnt["primary_rays"] + cnt["shadow_rays"]) * 0.5      # leaves are tested and passed through
+    for refill in (1, 12):
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill)
+        assert got.tobytes() == want.tobytes() and c == cnt, (fmt, refill, c, cnt)
+
+
+def test_emulated_edge_cases(emu, pkg, ora):
+    """The degenerate inputs of the GPU edge-case test, on the emulated kernels: no rays, single pathological rays, 1-pixel frames, and
+    the MAX_STEPS budget (svo.esvo.glsl:152,392) running out in the middle of a batch."""
+    reg = helpers.shader_test_registry(pkg)
+    world = helpers.shader_test_world(pkg, [(x, 0, z, 1) for x in range(32) for z in range(32)] + [(5, 5, 5, 2), (31, 31, 31, 1)])
+    scene = helpers.oracle_scene(ora, world, reg)
+    got, _ = emu_raycast(emu, pkg, world, reg, np.zeros(0, dtype=pkg.TASK_DTYPE))
+    assert len(got) == 0
+    cases = [((16.0, 40.0, 16.0), (0.0, -1.0, 0.0), -1.0), ((-50.0, 10.0, 16.0), (-1.0, 0.0, 0.0), -1.0), ((16.0, 1.5, 16.0), (1.0, 0.0, 0.0), -1.0),
+             ((5.5, 5.5, 5.5), (0.0, 1.0, 0.0), -1.0), ((16.0, 40.0, 16.0), (0.0, -1.0, 0.0), 0.0), ((1e6, 1e6, 1e6), (-1.0, -1.0, -1.0), -1.0),
+             ((16.0, float("nan"), 16.0), (0.0, -1.0, 0.0), -1.0)]
+    t = np.zeros(len(cases), dtype=pkg.TASK_DTYPE)
+    for i, (pos, d, md) in enumerate(cases):
+        t["pos"][i], t["dir"][i], t["max_dst"][i] = pos, np.array(d, np.float32) / np.linalg.norm(d), md
+    want, _ = scene.raycast(t)
+    got, _ = emu_raycast(emu, pkg, world, reg, t)
+    assert got.tobytes() == want.tobytes()          # same libm, same NaN: byte-identical even for the NaN origin
+    for (fw, fh) in ((1, 1), (1, 40), (40, 1), (33, 17)):
+        vxp = pkg.to_vx_render_params(pkg.render_params(cam_pos=(16.0, 20.0, 50.0), cam_fwd=(0.0, -0.4, -1.0), fov_y_deg=72.0, aspect=fw / fh))
+        want, _, cnt = oracle_render(pkg, ora, world, reg, vxp, fw, fh)
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, fw, fh)
+        assert got.tobytes() == want.tobytes() and c == cnt, (fw, fh)
+    # budget: a row of "dust" chunks makes a skimming ray descend to voxel level every other cell
+    w2 = pkg.World()
+    dust = [(x, 0, z, 1) for x in range(0, 32, 2) for z in range(0, 32, 2)]
+    for cx in range(32):
+        w2.set_leaf_blocks((cx, 0, 0), list(dust) + ([(31, y, z, 2) for y in range(4) for z in range(4)] if cx == 31 else []), uid=100 + cx, lod=5, compact=True)
+    w2.serialize()
+    n = 256
+    tasks = np.zeros(n, dtype=pkg.TASK_DTYPE)
+    tasks["max_dst"] = -1.0
+    tasks["pos"] = np.stack([np.linspace(0.5, 1000.5, n), np.full(n, 0.5), 1.5 + 2.0 * (np.arange(n) % 16)], axis=1)
+    tasks["dir"] = (1.0, 0.0, 0.0)
+    want, cnt = helpers.oracle_scene(ora, w2, reg).raycast(tasks)
+    got, c = emu_raycast(emu, pkg, w2, reg, tasks)
+    assert got.tobytes() == want.tobytes() and c["steps"] == cnt["steps"] and cnt["steps"] > 500 * n
+    assert 0 < (got["dst"] > 0).sum() < n

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../voxel-rs_b200/csrc/kernels.cuh"
+#include "../../voxel-rs_b200/csrc/chunks.cuh"
 
 namespace emu {
 Lane* cur = nullptr;
@@ -74,6 +75,7 @@ static void launch(unsigned grid, unsigned threads, const std::function<void()>&
 
 namespace vx {
 thread_local uint32_t smem_raw[64 * 1024];   // the CTA's dynamic shared memory (extern __shared__ uint32_t smem_raw[] in the kernels)
+thread_local __attribute__((aligned(16))) unsigned char chunk_smem_raw[sizeof(ChunkSmem) + 64];   // ... of serialize_chunks_kernel
 }
 
 using namespace vx;
@@ -256,6 +258,48 @@ EMU_API int emu_raycast(const uint8_t* world, uint64_t world_bytes, int fmt, uin
     });
     if (counters_out) std::memcpy(counters_out, &counters, sizeof(Counters));
     return 0;
+}
+
+// vx_serialize_chunks_esvo: one CTA of VX_CHUNK_THREADS threads per chunk, bump-allocated output (voxelrt.cu)
+EMU_API int emu_serialize_chunks(const uint32_t* blocks, uint32_t n_chunks, const uint8_t* lods, VxChunkInfo* infos_out, void* records_out,
+                                 uint64_t records_capacity, uint64_t* total_bytes) {
+    static_assert(sizeof(ChunkOut) == sizeof(VxChunkInfo), "VxChunkInfo layout");
+    std::vector<uint32_t> out((size_t)n_chunks * 4681 * 12);
+    std::vector<ChunkOut> infos(n_chunks);
+    unsigned long long bump[2] = {0, 0};
+    emu::launch(n_chunks, VX_CHUNK_THREADS, [&] {
+        serialize_chunks_kernel(blocks, lods, n_chunks, out.data(), (unsigned long long)out.size(), bump, infos.data(), reinterpret_cast<unsigned int*>(bump + 1));
+    });
+    std::memcpy(infos_out, infos.data(), n_chunks * sizeof(ChunkOut));
+    if ((unsigned int)bump[1]) return VX_E_CAPACITY;
+    const uint64_t total = bump[0] * 4ull;
+    if (total_bytes) *total_bytes = total;
+    if (records_out) {
+        if (total > records_capacity) return VX_E_CAPACITY;
+        std::memcpy(records_out, out.data(), total);
+    }
+    return 0;
+}
+
+// scatter_ranges_kernel (vx_svo_commit's staged path / vx_svo_commit_packed_device): packed = [n VxRange | head | range bytes...]
+EMU_API int emu_scatter_ranges(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, uint64_t payload_bytes, uint32_t head_bytes, uint32_t blocks) {
+    emu::launch(blocks ? blocks : 1, 256, [&] { scatter_ranges_kernel(world, packed, n_ranges, payload_bytes, head_bytes / 4); });
+    return 0;
+}
+
+// vx_pack_shard / vx_unpack_shard and Framebuffer::read_pixels' conversion
+EMU_API int emu_shard_copy(float* frame, float* packed, uint32_t width, uint32_t height, uint32_t rank, uint32_t size, int pack) {
+    const uint32_t macro_x = (width + 31) / 32, n_macros = macro_x * ((height + 15) / 16);
+    const uint32_t owned = n_macros > rank ? (n_macros - rank + size - 1) / size : 0;
+    if (!owned) return 0;
+    emu::launch(owned, 128, [&] {
+        if (pack) shard_copy_kernel<true>(reinterpret_cast<float4*>(frame), reinterpret_cast<float4*>(packed), width, height, macro_x, n_macros, rank, size);
+        else shard_copy_kernel<false>(reinterpret_cast<float4*>(frame), reinterpret_cast<float4*>(packed), width, height, macro_x, n_macros, rank, size);
+    });
+    return (int)owned;
+}
+EMU_API void emu_rgba8(const float* frame, uint32_t* out, uint64_t n) {
+    emu::launch((unsigned)((n + 255) / 256), 256, [&] { rgba8_kernel(reinterpret_cast<const float4*>(frame), out, n); });
 }
 
 EMU_API void emu_stats(uint64_t out[2]) { out[0] = emu::collectives; out[1] = emu::switches; }

@@ -21,7 +21,8 @@ ROOT = os.path.dirname(HERE)
 @pytest.fixture(scope="module")
 def emu(pkg):
     src = [os.path.join(EMU, "emu_harness.cpp"), os.path.join(EMU, "cuda_runtime.h"), os.path.join(ROOT, "include", "voxelrt.h"),
-           os.path.join(ROOT, "voxel-rs_b200", "csrc", "kernels.cuh"), os.path.join(ROOT, "voxel-rs_b200", "csrc", "traverse.cuh")]
+           os.path.join(ROOT, "voxel-rs_b200", "csrc", "kernels.cuh"), os.path.join(ROOT, "voxel-rs_b200", "csrc", "traverse.cuh"),
+           os.path.join(ROOT, "voxel-rs_b200", "csrc", "chunks.cuh")]
     out = os.path.join(EMU, "libkernels_emu.so")
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -225,3 +226,82 @@ def test_emulated_edge_cases(emu, pkg, ora):
     got, c = emu_raycast(emu, pkg, w2, reg, tasks)
     assert got.tobytes() == want.tobytes() and c["steps"] == cnt["steps"] and cnt["steps"] > 500 * n
     assert 0 < (got["dst"] > 0).sum() < n
+
+
+def test_emulated_chunk_serialization(emu, pkg):
+    """serialize_chunks_kernel on the emulator against the host serializer: random chunks of every density at every LOD,
+    the reference's KAT chunk, and the chunks of a small generated world against the bytes in the host's RangeBuffer."""
+    rng = np.random.default_rng(21)
+    blocks, lods = [], []
+    for density in (0.0, 0.0005, 0.02, 0.3, 1.0):
+        for lod in (0, 1, 2, 3, 4, 5):
+            blocks.append(((rng.random(32768) < density) * rng.integers(1, 1 << 20, 32768)).astype(np.uint32))
+            lods.append(lod)
+    corner = np.zeros(32768, np.uint32); corner[31] = 1; corner[31 * 32] = 2; corner[31 * 1024] = 3
+    blocks.append(corner); lods.append(5)
+
+    def serialize(blocks, lods):
+        blocks = np.ascontiguousarray(np.stack(blocks), dtype=np.uint32)
+        lods_a = np.ascontiguousarray(lods, dtype=np.uint8)
+        infos = np.zeros(len(blocks), dtype=pkg.CHUNK_INFO_DTYPE)
+        rec = np.zeros(len(blocks) * 4681 * 48, dtype=np.uint8)
+        total = C.c_uint64()
+        assert emu.emu_serialize_chunks(C.c_void_p(blocks.ctypes.data), C.c_uint32(len(blocks)), C.c_void_p(lods_a.ctypes.data), C.c_void_p(infos.ctypes.data),
+                                        C.c_void_p(rec.ctypes.data), C.c_uint64(len(rec)), C.byref(total)) == 0
+        return infos, rec[:total.value]
+
+    infos, rec = serialize(blocks, lods)
+    assert sum(int(l) for l in infos["length_bytes"]) == len(rec)
+    out = np.zeros(4681 * 12, dtype=np.uint32)
+    res = (C.c_uint8 * 3)()
+    for i in range(len(blocks)):
+        n = pkg.host().vxh_serialize_dense(blocks[i].ctypes.data, lods[i], out.ctypes.data, len(out), res)
+        o, l = int(infos["offset_bytes"][i]), int(infos["length_bytes"][i])
+        assert l == n * 4 and rec[o:o + l].tobytes() == out[:n].tobytes(), (i, lods[i])
+        assert (infos["child_mask"][i], infos["leaf_mask"][i], infos["depth"][i]) == tuple(res), (i, lods[i])
+    world = pkg.World(radius=7, center=(-1, 2, 5), seed=1, terrain="reference")     # LOD 5 and LOD 4 chunks
+    world.generate(0, 8)
+    world.serialize()
+    image, chunks = world.range_bytes(), world.chunks()[::3]
+    cb = [world.chunk_blocks(c) for c in chunks]
+    assert len({l for _, l in cb}) > 1
+    infos, rec = serialize([b for b, _ in cb], [l for _, l in cb])
+    for c, info in zip(chunks, infos):
+        off, length = world.chunk_range(c)
+        assert int(info["length_bytes"]) == length
+        assert rec[int(info["offset_bytes"]):int(info["offset_bytes"]) + length].tobytes() == image[off:off + length].tobytes(), tuple(c)
+
+
+def test_emulated_dirty_scatter_and_shard_copy(emu, pkg):
+    """scatter_ranges_kernel applies a packed dirty set exactly like the host reference of voxelrs_b200.sharded; shard_copy_kernel packs the
+    macro blocks of a rank and puts them back; rgba8_kernel is Framebuffer::read_pixels' rounding."""
+    from importlib import import_module
+    sharded = import_module(pkg.__name__ + ".sharded")
+    rng = np.random.default_rng(5)
+    head = 24
+    mirror = rng.integers(0, 256, 4096 + head, dtype=np.uint8)
+    ranges = [(0, 48), (96, 480), (1024, 4), (4000, 96)]
+    packed = np.ascontiguousarray(sharded.pack_dirty_host(mirror, ranges))
+    replica = np.zeros_like(mirror)
+    want = replica.copy()
+    sharded.apply_packed_host(want, packed, len(ranges))
+    payload = len(packed) - 16 * len(ranges)
+    emu.emu_scatter_ranges(C.c_void_p(replica.ctypes.data), C.c_void_p(packed.ctypes.data), C.c_uint32(len(ranges)), C.c_uint64(payload), C.c_uint32(head), C.c_uint32(3))
+    assert replica.tobytes() == want.tobytes()
+    for off, ln in ranges:
+        assert replica[head + off:head + off + ln].tobytes() == mirror[head + off:head + off + ln].tobytes()
+    w, h, size = 70, 40, 3
+    frame = rng.random((h, w, 4), dtype=np.float32)
+    rebuilt = np.zeros_like(frame)
+    for rank in range(size):
+        n_macros = ((w + 31) // 32) * ((h + 15) // 16)
+        owned = (n_macros - rank + size - 1) // size
+        buf = np.zeros((owned, 512, 4), np.float32)
+        assert emu.emu_shard_copy(C.c_void_p(frame.ctypes.data), C.c_void_p(buf.ctypes.data), C.c_uint32(w), C.c_uint32(h), C.c_uint32(rank), C.c_uint32(size), 1) == owned
+        assert emu.emu_shard_copy(C.c_void_p(rebuilt.ctypes.data), C.c_void_p(buf.ctypes.data), C.c_uint32(w), C.c_uint32(h), C.c_uint32(rank), C.c_uint32(size), 0) == owned
+    assert rebuilt.tobytes() == frame.tobytes()
+    f = np.array([[0.0, 1.0, 0.5, 2.0], [-1.0, 0.25, 1e-9, np.nan], [0.499 / 255, 0.5 / 255, 254.5 / 255, 1.0]], np.float32)
+    out = np.zeros(3, np.uint32)
+    emu.emu_rgba8(C.c_void_p(f.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(3))
+    want = np.floor(np.clip(np.nan_to_num(f, nan=0.0), 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint32)
+    assert [int(v) for v in out] == [int(r[0] | r[1] << 8 | r[2] << 16 | r[3] << 24) for r in want]

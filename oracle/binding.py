@@ -74,6 +74,7 @@ def lib():
     L.vxo_render.argtypes = scene + [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, P, C.POINTER(Counters), C.c_int]
     L.vxo_render.restype = None
     L.vxo_primary_hits.argtypes = scene + [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_int]; L.vxo_primary_hits.restype = None
+    L.vxo_render_steps.argtypes = scene + [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, P, C.c_int]; L.vxo_render_steps.restype = None
     L.vxo_to_rgba8.argtypes = [P, C.c_uint64, P]; L.vxo_to_rgba8.restype = None
     L.vxo_max_threads.argtypes = []; L.vxo_max_threads.restype = C.c_int
     _lib = L
@@ -142,6 +143,13 @@ class Scene:
         p = RenderParams.from_buffer_copy(bytes(params))
         lib().vxo_render(*self._args(), C.byref(p), width, height, y0, y1, _ptr(out), C.byref(cnt), threads)
         return out, cnt.as_dict()
+
+    def render_steps(self, params, width, height, threads=0):
+        """Per pixel: loop iterations of the primary ray and of the shadow ray (0 = none) — for offline scheduling analysis."""
+        a, b = np.zeros((height, width), dtype=np.uint32), np.zeros((height, width), dtype=np.uint32)
+        p = RenderParams.from_buffer_copy(bytes(params))
+        lib().vxo_render_steps(*self._args(), C.byref(p), width, height, _ptr(a), _ptr(b), threads)
+        return a, b
 
     def primary_hits(self, params, width, height, threads=0):
         out = np.zeros((height, width), dtype=HIT_DTYPE)

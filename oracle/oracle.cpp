@@ -920,6 +920,29 @@ void vxo_primary_hits(const uint8_t* world, uint64_t world_len, const void* mate
         }
 }
 
+// Analysis aid (tests/analysis/warp_efficiency.py): loop iterations (svo.esvo.glsl:152) of every pixel's primary ray and of its
+// shadow ray (0 = none cast), so that warp-level scheduling policies can be compared offline.
+void vxo_render_steps(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex, int svo_format,
+                      const vxo::RenderParams* params, uint32_t w, uint32_t h, uint32_t* primary_steps, uint32_t* shadow_steps, int threads) {
+    vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
+    const float tan_half_fov = tanf(params->fov_y_rad * 0.5f);
+    vxo::RenderParams no_shadows = *params;
+    no_shadows.render_shadows = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < (int64_t)h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            float px[4];
+            vxo::Counters a{}, b{};
+            vxo::render_pixel(s, no_shadows, tan_half_fov, x, (uint32_t)y, w, h, px, &a);
+            vxo::render_pixel(s, *params, tan_half_fov, x, (uint32_t)y, w, h, px, &b);
+            primary_steps[(size_t)y * w + x] = (uint32_t)a.steps;
+            shadow_steps[(size_t)y * w + x] = (uint32_t)(b.steps - a.steps);
+        }
+}
+
 // glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) of an RGBA32F attachment (framebuffer.rs:97-105)
 void vxo_to_rgba8(const float* rgba32f, uint64_t n_pixels, uint8_t* out) {
     for (uint64_t i = 0; i < n_pixels * 4; ++i) {

@@ -172,6 +172,19 @@ def test_world_end_to_end_png(pkg, ora):
     assert (m <= 1).mean() > 0.98 and (m > 40).mean() < 5e-4   # silhouettes and shadow edges: a handful of pixels
 
 
+def test_render_steps_add_up(pkg, ora):
+    """The per-pixel iteration counts behind tests/analysis/warp_efficiency.py are the frame's step counter, split by ray."""
+    reg = helpers.svo_render_test_registry(pkg, pkg.load_atlas())
+    w = pkg.World()
+    w.set_leaf_blocks((0, 0, 0), helpers.svo_render_test_blocks(), compact=False)
+    w.serialize()
+    s = helpers.oracle_scene(ora, w, reg)
+    p = pkg.to_vx_render_params(helpers.svo_render_test_params(pkg, 96, 72))
+    _, cnt = s.render(p, 96, 72)
+    prim, shad = s.render_steps(p, 96, 72)
+    assert int(prim.sum()) + int(shad.sum()) == cnt["steps"] and int((shad > 0).sum()) == cnt["shadow_rays"] and (prim > 0).all()
+
+
 # ------------------------------------------------------------------------------------------------------------- CSVO --
 
 def test_csvo_shader_svo_traversal(pkg, ora, reg):

@@ -174,10 +174,10 @@ extern "C" {
 
 // One frame through trace_primary_kernel -> shade_kernel -> trace_shadow_kernel exactly as vx_render issues them.
 // options: [0] refill threshold, [1] shadow refill (0 = same), [2] CTAs of the persistent kernels, [3] count, [4] RGBA8 output,
-// [5] TMA-style tile write-back, [6] shard rank, [7] shard size
+// [5] TMA-style tile write-back, [6] shard rank, [7] shard size, [8] bands (vx_render_read_rgba8's banded wavefront; 0/1 = whole frame)
 EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
                const uint8_t* tex_rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels, const VxRenderParams* p, uint32_t width,
-               uint32_t height, const uint32_t options[8], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
+               uint32_t height, const uint32_t options[9], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
     Device d;
     upload(d, world, world_bytes, fmt, depth, materials, n_materials, tex_rgba8, tw, th, layers, mip_levels);
     RenderArgs a{};
@@ -195,7 +195,6 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     std::vector<float4> hit0(slots), hit1(slots), sh0(slots), sh1(slots), frame((size_t)width * height, float4{-1, -1, -1, -1});
     std::vector<uint32_t> sh_pix(slots), frame8((size_t)width * height, 0xdeadbeefu);
     Counters counters{};
-    unsigned int work[8] = {};
     a.frame = frame.data();
     a.frame8 = options[4] ? frame8.data() : nullptr;
     a.hit0 = hit0.data(); a.hit1 = hit1.data(); a.sh0 = sh0.data(); a.sh1 = sh1.data(); a.sh_pix = sh_pix.data();
@@ -204,17 +203,41 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     a.refill_threshold = options[0] ? options[0] : 1;
     a.shadow_refill = options[1] ? options[1] : a.refill_threshold;
     a.tma_writeback = options[5];
-    // launch_wavefront over the whole frame
-    a.macro0 = 0; a.n_macros = a.macro_x * a.macro_y;
-    a.first_owned = a.macro0 + ((a.shard_rank + a.shard_size - (a.macro0 % a.shard_size)) % a.shard_size);
-    const uint32_t band_end = a.macro0 + a.n_macros;
-    const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + a.shard_size - 1) / a.shard_size : 0;
-    a.n_owned = owned;
-    a.shadow_count = work + 4;
-    a.fetch_tiles = 1;
+    // bands of macro-block rows, top of the image first, sizes shrinking by 0.6 (vx_render_read_rgba8); one band = vx_render
+    uint32_t bands = options[8] ? options[8] : 1;
+    if (bands > 16) bands = 16;
+    if (bands > a.macro_y) bands = a.macro_y;
+    const double ratio = 0.6;
+    double wsum = 0.0, wk = 1.0;
+    for (uint32_t k = 0; k < bands; ++k) { wsum += wk; wk *= ratio; }
+    uint32_t edge[17];
+    {
+        double acc = 0.0; wk = 1.0;
+        edge[0] = a.macro_y;
+        for (uint32_t k = 0; k < bands; ++k) {
+            acc += wk; wk *= ratio;
+            uint32_t e = a.macro_y - (uint32_t)((double)a.macro_y * acc / wsum + 0.5);
+            if (k + 1 == bands) e = 0;
+            if (e > edge[k]) e = edge[k];
+            edge[k + 1] = e;
+        }
+    }
+    unsigned int work_all[16 * 8] = {};
     const bool count = options[3] != 0, csvo = fmt == VX_FMT_CSVO;
     const unsigned grid = options[2] ? options[2] : 3;
-    if (owned) {
+    for (uint32_t b = 0; b < bands; ++b) {
+        const uint32_t row0 = edge[b + 1], row1 = edge[b];
+        if (row1 == row0) continue;
+        // launch_wavefront(c, a, shadows, band b, row0, row1)
+        unsigned int* work = work_all + b * 8;
+        a.macro0 = row0 * a.macro_x; a.n_macros = (row1 - row0) * a.macro_x;
+        a.first_owned = a.macro0 + ((a.shard_rank + a.shard_size - (a.macro0 % a.shard_size)) % a.shard_size);
+        const uint32_t band_end = a.macro0 + a.n_macros;
+        const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + a.shard_size - 1) / a.shard_size : 0;
+        a.n_owned = owned;
+        a.shadow_count = work + 4;
+        a.fetch_tiles = 1;
+        if (!owned) continue;
         a.work_counter = work;
         emu::launch(grid, VX_THREADS, [&] {
             if (csvo) { if (count) trace_primary_kernel<VX_FMT_CSVO, true, 8>(a); else trace_primary_kernel<VX_FMT_CSVO, false, 8>(a); }

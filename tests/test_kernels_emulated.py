@@ -48,8 +48,8 @@ def scene_args(world, reg):
                   C.c_uint32(len(mats)), C.c_void_p(tex.ctypes.data), C.c_uint32(tw), C.c_uint32(th), C.c_uint32(layers), C.c_uint32(mips)]
 
 
-def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1):
-    return (C.c_uint32 * 8)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size)
+def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1, bands=1):
+    return (C.c_uint32 * 9)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size, bands)
 
 
 def emu_render(emu, pkg, world, reg, vxp, w, h, **kw):
@@ -108,6 +108,15 @@ def test_emulated_frame_equals_oracle(emu, pkg, ora, terrains, fmt):
     assert got8.tobytes() == want8.tobytes()
     got, _, _ = emu_render(emu, pkg, world, reg, vxp, w, h, tma=1)
     assert got.tobytes() == want.tobytes()
+    # the banded wavefront of vx_render_read_rgba8 (per-band macro-block ranges and work counters), also sharded
+    _, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, rgba8=1, bands=3)
+    assert got8.tobytes() == want8.tobytes() and c == cnt
+    union = np.zeros((h, w, 4), np.uint8)
+    for rank in range(2):
+        _, part, _ = emu_render(emu, pkg, world, reg, vxp, w, h, rgba8=1, bands=2, rank=rank, size=2)
+        mine = part.view(np.uint32)[..., 0] != 0xdeadbeef
+        union[mine] = part[mine]
+    assert union.tobytes() == want8.tobytes()
 
 
 def test_emulated_shards_tile_the_frame(emu, pkg, ora, terrains):

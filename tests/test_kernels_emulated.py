@@ -314,3 +314,35 @@ def test_emulated_dirty_scatter_and_shard_copy(emu, pkg):
     emu.emu_rgba8(C.c_void_p(f.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(3))
     want = np.floor(np.clip(np.nan_to_num(f, nan=0.0), 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint32)
     assert [int(v) for v in out] == [int(r[0] | r[1] << 8 | r[2] << 16 | r[3] << 24) for r in want]
+
+
+def test_emulated_random_configurations(emu, pkg, ora, terrains):
+    """Seeded sweep over what the host can ask of the frame kernels: ragged frame sizes, shard counts, bands, refill thresholds, numbers of
+    persistent CTAs, both formats, shadows on/off, float and RGBA8 output. The union of the shards always equals the oracle's frame."""
+    worlds, reg = terrains
+    rng = np.random.default_rng(2024)
+    for case in range(14):
+        fmt = int(rng.integers(0, 2))
+        world = worlds[fmt]
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 60))
+        size = int(rng.choice([1, 1, 2, 3, 5]))
+        bands = int(rng.choice([1, 2, 4, 16]))
+        refill, ctas = int(rng.integers(1, 33)), int(rng.integers(1, 5))
+        shadow_refill = int(rng.choice([0, 1, 7, 32]))
+        shadows, rgba8 = bool(rng.integers(0, 2)), int(rng.integers(0, 2))
+        vxp = world_params(pkg, world, w, h, shadows=shadows, selected=(-20.0, 50.0, 174.0) if case % 2 else None)
+        want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
+        union = np.full((h, w, 4), -1.0, np.float32)
+        union8 = np.zeros((h, w, 4), np.uint8)
+        total = {k: 0 for k in cnt}
+        for rank in range(size):
+            got, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, shadow_refill=shadow_refill, ctas=ctas, rgba8=rgba8, rank=rank,
+                                      size=size, bands=bands)
+            mine = (got8.view(np.uint32)[..., 0] != 0xdeadbeef) if rgba8 else (got[..., 3] != -1.0)
+            union[mine] = got[mine]
+            union8[mine] = got8[mine]
+            for k in c:
+                total[k] += c[k]
+        cfg = dict(case=case, fmt=fmt, w=w, h=h, size=size, bands=bands, refill=refill, ctas=ctas, shadows=shadows, rgba8=rgba8)
+        assert (union8.tobytes() == want8.tobytes()) if rgba8 else (union.tobytes() == want.tobytes()), cfg
+        assert total == cnt, (cfg, total, cnt)

@@ -161,6 +161,7 @@ Scene make_scene(const Device& d) {   // voxelrt.cu make_scene
     s.unorm = d.unorm;
     const uint32_t levels = d.depth + (d.fmt == VX_FMT_CSVO ? 3 : 1);
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
+    s.stack_max_off = (s.stack_levels - 1u) * VX_STACK_STRIDE;
     return s;
 }
 

@@ -31,6 +31,19 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def build_variant(name, defines, verbose=False):
+    """A/B build of libvoxelrt with extra -D defines into voxel-rs_b200/variants/<name>/libvoxelrt.so (tools/ab_kernels.py swaps
+    it in for one measurement). Not loaded by anything else."""
+    src = os.path.join(PKG, "csrc", "voxelrt.cu")
+    out_dir = os.path.join(PKG, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libvoxelrt.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, src]
+    subprocess.run(cmd, check=True, cwd=os.path.join(PKG, "csrc"))
+    return out
+
+
 def build_cuda(force=False, verbose=False):
     src = os.path.join(PKG, "csrc", "voxelrt.cu")
     deps = [src, os.path.join(PKG, "csrc", "traverse.cuh"), os.path.join(PKG, "csrc", "kernels.cuh"), os.path.join(PKG, "csrc", "chunks.cuh"), os.path.join(ROOT, "include", "voxelrt.h")]

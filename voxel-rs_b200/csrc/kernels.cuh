@@ -99,43 +99,48 @@ __device__ __forceinline__ float lod_of_dst(float dst) {   // svo.esvo.glsl:235
 // Translucency rule of a render ray at a leaf whose material is not known to be opaque (svo.esvo.glsl:227-242, 264-265):
 // samples the texel and applies "alpha > 0 and first of its kind". Out of line and rare (glass, leaves, water).
 __device__ __noinline__ bool translucent_leaf_accepts(const TexInfo* tex, const Material* materials, uint32_t n_materials, const float* unorm,
-                                                      uint32_t value, int face_id, float u, float v, float dst, uint32_t last_leaf) {
+                                                      uint32_t value, int face_id, float u, float v, float dst, bool first_of_kind) {
     const Material* m = materials + (value < n_materials ? value : n_materials - 1);
     int tex_id = __ldg(&m->tex_side);
     if (face_id == 3) tex_id = __ldg(&m->tex_top);
     else if (face_id == 2) tex_id = __ldg(&m->tex_bottom);
     uint32_t nf = 0;
     const float4 c = texture_lod<4>(tex, unorm, u, v, tex_id, lod_of_dst(dst), &nf);
-    const bool first_of_kind = value != last_leaf;   // adjacent_leaf_count == 0 <=> last_leaf == 0xffffffff (never a block id)
     return c.w > 0.0f && first_of_kind;
 }
 
 // Render-ray leaf candidate (cast_translucent = true). Returns true when the leaf is the hit; fills g (and value).
 template <int FMT, bool COUNT>
-__device__ __forceinline__ bool render_leaf(const Walk& w, const Scene& s, const Smem& sm, float inv_scale, uint32_t& last_leaf, Leaf& g, Counters& cnt) {
+__device__ __forceinline__ bool render_leaf(Walk& w, const Scene& s, const Smem& sm, float inv_scale, uint32_t& last_leaf, Leaf& g, Counters& cnt) {
     g.value = leaf_value<FMT>(w, s);
     if (COUNT) { cnt.leaf_tests++; cnt.tex_fetches += logical_texels(s.tex, lod_of_dst(w.t_min * inv_scale)); }
     const bool opaque = g.value < 64u && ((s.opaque_materials >> g.value) & 1ull);
     const float* c = sm.cold;
     leaf_geom(w, c[0], c[VX_THREADS], c[2 * VX_THREADS], c[3 * VX_THREADS], c[4 * VX_THREADS], c[5 * VX_THREADS], inv_scale, g);
     if (opaque) return true;
-    if (translucent_leaf_accepts(s.tex, s.materials, s.n_materials, sm.unorm, g.value, g.face_id, g.u, g.v, g.dst, last_leaf)) return true;
-    last_leaf = g.value;                                                      // :264-265
+    const bool first_of_kind = !(w.flags & VX_FLAG_ADJACENT) || g.value != last_leaf;   // :241
+    if (translucent_leaf_accepts(s.tex, s.materials, s.n_materials, sm.unorm, g.value, g.face_id, g.u, g.v, g.dst, first_of_kind)) return true;
+    last_leaf = g.value; w.flags |= VX_FLAG_ADJACENT;                         // :264-265
     return false;
 }
 
 // The walk loop of a warp: every lane with a live ray steps it; the warp leaves the loop when fewer than `thresh` lanes are
 // still walking. thresh == 1 (run every ray of the warp to its end, then refill all 32 lanes at once) needs no population
 // count and gets its own copy of the loop.
+#ifdef VX_STEP_PLAIN   // A/B build: the shader-ordered step in the hot loop (tools/ab_kernels.py)
+#define VX_HOT_STEP walk_step_plain
+#else
+#define VX_HOT_STEP walk_step
+#endif
 template <int FMT, bool LIMITED, bool COUNT>
-__device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt, int thresh) {
+__device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, Counters& cnt, int thresh) {
     if (thresh <= 1) {
         do {
-            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+            if (w.state > 0) VX_HOT_STEP<FMT, LIMITED, COUNT>(w, s, stk, cnt);
         } while (__any_sync(0xffffffffu, w.state > 0));
     } else {
         do {
-            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, last_leaf, cnt);
+            if (w.state > 0) VX_HOT_STEP<FMT, LIMITED, COUNT>(w, s, stk, cnt);
         } while (__popc(__ballot_sync(0xffffffffu, w.state > 0)) >= thresh);
     }
 }
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
                     walk_init<FMT>(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
+                    walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         if (state_at_leaf(w.state)) {
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 w.state = ST_IDLE;
             } else {
                 walk_skip_leaf<FMT>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
+                walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
             }
         } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -382,6 +389,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 const float4 s0 = __ldcs(a.sh0 + entry);
                 float rox, roy, roz, rdx, rdy, rdz;
                 walk_init<FMT>(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
+                walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 lit = s0.w;
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.shadow_refill, __popc(busy)));
+        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.shadow_refill, __popc(busy)));
 
         if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                     shadow = 0.0f;
                 } else {
                     walk_skip_leaf<FMT>(w, a.scene, sm.stack);
+                    walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                     done = false;
                 }
             }
@@ -471,6 +480,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
                 float rox, roy, roz, rdx, rdy, rdz;
                 walk_init<FMT>(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
+                walk_degenerate<FMT, true, COUNT>(w, a.scene, sm.stack, cnt);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 if (COUNT) cnt.primary_rays++;
@@ -480,7 +490,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, last_leaf, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
         if (w.state <= 0 && w.state != ST_IDLE) {
             // cast_translucent = false: the first leaf is the hit whatever its texel is (svo.esvo.glsl:241-242); the picker
             // never reads value or colour (picker.glsl:40-44), so neither the leaf word nor the texture is fetched.
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                     float px, py, pz;
                     leaf_pos(w.t_min, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS],
                              g, inv_scale, px, py, pz);
-                    o0.x = g.dst; o0.y = __uint_as_float((w.idx >> 8) & 1u);
+                    o0.x = g.dst; o0.y = __uint_as_float((w.flags >> 8) & 1u);
                     o1 = make_float4(px, py, pz, 0.0f);
                     const int axis = g.face_id >> 1;
                     const float sgn = (g.face_id & 1) ? 1.0f : -1.0f;      // FACE_NORMALS, svo.glsl:2-9
@@ -540,14 +550,14 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     bool hit = false;
     Leaf g; float tex_lod = 0.0f; float4 color = make_float4(0, 0, 0, 0);
     for (;;) {
-        const uint32_t oi = (w.idx ^ (w.idx >> 4)) & 7u;
-        const int scale_before = w.scale;
+        const uint32_t oi = w.ci;
+        const int scale_before = walk_scale(w);
         const uint32_t rec_before = w.rec;
         // the frame the shader emits at :175 for this iteration (if it gets past :152-156)
         if (w.state > 0 && !(w.t_min > w.limit)) {
             if (n < a.frames_cap) {
                 VxDebugFrame& f = a.frames[n];
-                f.t_min = w.t_min * inv_scale; f.idx = oi; f.scale = w.scale;
+                f.t_min = w.t_min * inv_scale; f.idx = oi; f.scale = scale_before;
                 if (FMT == VX_FMT_CSVO) {   // svo.csvo.glsl:246: (ptr, depth) ride in (ptr, parent_octant_idx); next_ptr is INVALID_PTR for no child
                     const bool child = csvo_has_child(w.hdr, w.desc, oi);
                     bool crossed = false;
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         const float tcx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcy = __fmaf_rn(w.py, w.tcy, -w.tby), tcz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
         const float tc_max = tmin2(tmin2(tcx, tcy), tcz);
         if (w.state <= 0) break;                      // MAX_STEPS used up (:152)
-        walk_step<FMT, true, false>(w, s, sm.stack, last_leaf, cnt);
+        walk_step_plain<FMT, true, false>(w, s, sm.stack, cnt);
         if (state_at_leaf(w.state)) {
             g.value = leaf_value<FMT>(w, s);
             leaf_geom(w, rox, roy, roz, rdx, rdy, rdz, inv_scale, g);
@@ -575,22 +585,23 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
             leaf_texture(s, g, tex_id, tex_lod);
             uint32_t nf = 0;
             color = texture_lod<4>(s.tex, sm.unorm, g.u, g.v, tex_id, tex_lod, &nf);   // the shader samples in both modes (:237)
-            const bool first_of_kind = g.value != last_leaf;
+            const bool first_of_kind = !(w.flags & VX_FLAG_ADJACENT) || g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
-            last_leaf = g.value;
+            last_leaf = g.value; w.flags |= VX_FLAG_ADJACENT;
             walk_skip_leaf<FMT>(w, s, sm.stack);
         }
         if (w.state == ST_MISS) break;
-        if (w.scale == scale_before - 1) {            // PUSH happened
+        const int scale_after = walk_scale(w);
+        if (scale_after == scale_before - 1) {        // PUSH happened
             if (tc_max < h_before) { ptr_stack[scale_before] = ptr; pidx_stack[scale_before] = pidx; }
             ptr = rec_before; pidx = oi;
-        } else if (w.scale > scale_before) {          // POP happened
-            ptr = ptr_stack[w.scale]; pidx = pidx_stack[w.scale];
+        } else if (scale_after > scale_before) {      // POP happened
+            ptr = ptr_stack[scale_after]; pidx = pidx_stack[scale_after];
         }
     }
     VxOctreeResult& o = *a.result;
     o.t = -1.0f; o.value = 0; o.face_id = 0; o.pos[0] = o.pos[1] = o.pos[2] = 0; o.uv[0] = o.uv[1] = 0;
-    o.color[0] = o.color[1] = o.color[2] = o.color[3] = 0; o.lod = 0; o.inside_voxel = (w.idx >> 8) & 1u;
+    o.color[0] = o.color[1] = o.color[2] = o.color[3] = 0; o.lod = 0; o.inside_voxel = (w.flags >> 8) & 1u;
     if (hit) {
         o.t = g.dst; o.value = g.value; o.face_id = g.face_id;
         leaf_pos(w.t_min, rox, roy, roz, rdx, rdy, rdz, g, inv_scale, o.pos[0], o.pos[1], o.pos[2]);

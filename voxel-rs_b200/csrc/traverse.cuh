@@ -68,6 +68,7 @@ struct Scene {
     const TexInfo* __restrict__ tex;
     const float* __restrict__ unorm;     // 256-entry b / 255.0f table in global memory (copied into shared memory per CTA)
     uint32_t stack_levels;               // entries of the per-thread traversal stack (= SVO depth + 1, <= 23)
+    uint32_t stack_max_off;              // (stack_levels - 1) * VX_STACK_STRIDE: byte offset of the last stack slot (Walk::soff clamp)
     unsigned long long opaque_materials; // bit m set (m < 64): every texel of the three face textures of material m has alpha > 0,
                                          // so a leaf of that material is accepted by the translucency rule (:241-242) without sampling
 };
@@ -179,16 +180,24 @@ struct Walk {
     float tbx, tby, tbz;      // t_bias
     float px, py, pz;         // pos (mirrored space, [1,2))
     float t_min, t_max, h;
-    float se;                 // scale_exp2 = 2^(scale-23)
+    float se;                 // scale_exp2 = 2^(scale-23); the shader's integer `scale` is its exponent (walk_scale)
     float limit;              // max_dst in [1,2) space, +inf when unlimited (:153)
     uint32_t rec, desc;       // ESVO: record of the current octant, child/leaf masks of its children (bits 0-7 leaf, 8-15 child)
                               // CSVO: byte pointer of the current node, remaining depth (the shader's ptr / depth)
     uint32_t hdr;             // CSVO: the node's header (u16 when depth > 3, else u8), re-read whenever (ptr, depth) changes
     uint32_t mat_ptr, preleaf;   // CSVO: material_section_ptr, pre_leaf_pointer (svo.csvo.glsl:222-223; not stacked, like the shader)
-    uint32_t idx;             // bits 0-2: child index in mirrored space; bits 4-6: octant_mask; bit 8: inside_voxel
-    int scale;
+    uint32_t ci;              // slot of the current cell in its parent, UN-mirrored: the shader's `idx ^ octant_mask` (:164), 0..7.
+                              // Kept instead of idx: the node decode of every iteration uses it as it is, and idx is one xor away.
+    uint32_t flags;           // bits 0-2: octant_mask; bit 8: inside_voxel; bit 9: the previous leaf candidate was rejected
+                              // (adjacent_leaf_count > 0, its value is in the caller's last_leaf); bit 10: degenerate ray (walk_init)
+    uint32_t soff;            // byte offset of the traversal-stack slot of the current level, = min(22 - scale, levels - 1) * VX_STACK_STRIDE
     int state;                // see ST_*: > 0 walking (iterations left of MAX_STEPS), 0 budget used up, < 0 stopped
 };
+#define VX_FLAG_INSIDE 0x100u
+#define VX_FLAG_ADJACENT 0x200u
+#define VX_FLAG_DEGENERATE 0x400u
+#define VX_STACK_STRIDE (3u * VX_THREADS * 4u)   // bytes between two levels of one thread's stack column
+__device__ __forceinline__ int walk_scale(const Walk& w) { return (int)((__float_as_uint(w.se) >> 23) & 0xffu) - 104; }   // se = 2^(scale-23)
 
 // Geometry of a leaf candidate (svo.esvo.glsl:190-224, 233)
 struct Leaf {
@@ -291,9 +300,14 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
     if (w.t_min < 1.5f * w.tcx - w.tbx) { idx ^= 1; w.px = 1.5f; }
     if (w.t_min < 1.5f * w.tcy - w.tby) { idx ^= 2; w.py = 1.5f; }
     if (w.t_min < 1.5f * w.tcz - w.tbz) { idx ^= 4; w.pz = 1.5f; }
-    w.idx = idx | (octant_mask << 4);
+    w.ci = idx ^ octant_mask;
+    // A ray whose coefficients hold a NaN (NaN / infinite inputs) is walked by the plain step only (walk_plain_loop): the merged
+    // step of the hot loop states the ADVANCE comparison `tc_max >= t_corner` as `!(tc_max < t_corner)`, which is the same thing for
+    // every ordered pair. (A sum is NaN if a term is; inf - inf false positives just take the slow path too.)
+    const float nan_probe = ((w.tcx + w.tcy) + w.tcz) + ((w.tbx + w.tby) + w.tbz) + w.t_min;
+    w.flags = octant_mask | ((nan_probe == nan_probe && fabsf(nan_probe) != __int_as_float(0x7f800000)) ? 0u : VX_FLAG_DEGENERATE);
 
-    w.scale = VX_MAX_SCALE - 1;
+    w.soff = 0;          // scale = MAX_SCALE - 1
     w.se = 0.5f;
     w.state = VX_MAX_STEPS;
 
@@ -311,13 +325,12 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
     w.rec = root < s.max_rec ? root : s.max_rec;
 }
 
-// Per-thread traversal stack access. `stk` is the SHARED-space byte address of this thread's column (Smem::stack_addr),
-// kept in one register and made opaque to the compiler (it otherwise re-derives it from %tid and the CTA's shared window
-// in every loop iteration: 6 instructions, 6 % of the trace kernels — profiles/r01_v3_frame_wavefront.md).
+// Per-thread traversal stack access. `a` is the SHARED-space byte address of the slot: the thread's column (Smem::stack, kept in
+// one register and made opaque to the compiler — it otherwise re-derives it from %tid and the CTA's shared window in every loop
+// iteration: 6 instructions, 6 % of the trace kernels, profiles/r01_v3_frame_wavefront.md) plus Walk::soff.
 // (VX_HOST_EMULATION: tests/emu compiles these headers with g++ and runs the kernels on CPU fibers against the oracle; the PTX is
 // then replaced by the same accesses on the emulated shared window. nvcc never defines it.)
-__device__ __forceinline__ void stack_store(uint32_t stk, uint32_t lvl, uint32_t rec, uint32_t desc, float t_max) {
-    const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+__device__ __forceinline__ void stack_store(uint32_t a, uint32_t rec, uint32_t desc, float t_max) {
 #ifndef VX_HOST_EMULATION
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(rec) : "memory");
     asm volatile("st.shared.u32 [%0+512], %1;" ::"r"(a), "r"(desc) : "memory");
@@ -326,8 +339,7 @@ __device__ __forceinline__ void stack_store(uint32_t stk, uint32_t lvl, uint32_t
     vx_emu_shared_u32(a) = rec; vx_emu_shared_u32(a + 512u) = desc; vx_emu_shared_u32(a + 1024u) = __float_as_uint(t_max);
 #endif
 }
-__device__ __forceinline__ void stack_load(uint32_t stk, uint32_t lvl, uint32_t& rec, uint32_t& desc, float& t_max) {
-    const uint32_t a = stk + lvl * (3u * VX_THREADS * 4u);
+__device__ __forceinline__ void stack_load(uint32_t a, uint32_t& rec, uint32_t& desc, float& t_max) {
 #ifndef VX_HOST_EMULATION
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rec) : "r"(a) : "memory");
     asm volatile("ld.shared.u32 %0, [%1+512];" : "=r"(desc) : "r"(a) : "memory");
@@ -355,111 +367,187 @@ __device__ __forceinline__ void csvo_unpack_node(Walk& w) {
     w.desc = (uint32_t)(int32_t)(int16_t)(packed & 0xffffu);
 }
 
-// ADVANCE / POP (svo.esvo.glsl:324-391 = svo.csvo.glsl:440-507). Returns 0 when the ray left the octree (:365), 1 after an
-// ADVANCE, 2 after a POP (the node changed: (rec, desc) = the shader's (ptr, parent_octant_idx) resp. (ptr, depth)).
-__device__ __forceinline__ int walk_advance(Walk& w, uint32_t stk, uint32_t stack_levels, float tcornx, float tcorny, float tcornz, float tc_max) {
+// POP (svo.esvo.glsl:335-391 = svo.csvo.glsl:451-507) after an ADVANCE along the axes of step_mask that left the parent.
+// Returns false when the ray left the octree (:365); otherwise the node changed: (rec, desc) = the shader's
+// (ptr, parent_octant_idx) resp. (ptr, depth) come back from the stack.
+template <int FMT>
+__device__ __forceinline__ bool walk_pop(Walk& w, uint32_t stk, uint32_t stack_max_off, uint32_t step_mask) {
+    uint32_t differing_bits = 0;                                              // :347-350
+    if (step_mask & 1) differing_bits |= __float_as_uint(w.px) ^ __float_as_uint(w.px + w.se);
+    if (step_mask & 2) differing_bits |= __float_as_uint(w.py) ^ __float_as_uint(w.py + w.se);
+    if (step_mask & 4) differing_bits |= __float_as_uint(w.pz) ^ __float_as_uint(w.pz + w.se);
+    const int scale = 31 - __clz(differing_bits);                             // :360 findMSB
+    w.se = __int_as_float((scale + (127 - VX_MAX_SCALE)) << 23);              // :361 exp2(scale - 23)
+    if (scale >= VX_MAX_SCALE) return false;                                  // :365
+    w.soff = min((uint32_t)(VX_MAX_SCALE - 1 - scale) * VX_STACK_STRIDE, stack_max_off);   // :370-372
+    stack_load(stk + w.soff, w.rec, w.desc, w.t_max);
+    const uint32_t keep = 0xffffffffu << scale;                               // :377-382 floor(pos) at the new scale
+    const uint32_t bx = __float_as_uint(w.px), by = __float_as_uint(w.py), bz = __float_as_uint(w.pz);
+    w.px = __uint_as_float(bx & keep); w.py = __uint_as_float(by & keep); w.pz = __uint_as_float(bz & keep);
+    const uint32_t idx = ((bx >> scale) & 1u) | (((by >> scale) & 1u) << 1) | (((bz >> scale) & 1u) << 2);   // :388
+    w.ci = idx ^ (w.flags & 7u);
+    w.h = 0.0f;                                                               // :390
+    if (FMT == VX_FMT_CSVO) csvo_unpack_node(w);
+    return true;
+}
+
+// ADVANCE / POP (svo.esvo.glsl:324-391 = svo.csvo.glsl:440-507) as the shader writes them. Returns false when the ray left the octree.
+template <int FMT>
+__device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t stack_max_off, float tcornx, float tcorny, float tcornz, float tc_max) {
     uint32_t step_mask = 0;                                                   // :324-327  ADVANCE
     if (tc_max >= tcornx) { step_mask ^= 1; w.px -= w.se; }
     if (tc_max >= tcorny) { step_mask ^= 2; w.py -= w.se; }
     if (tc_max >= tcornz) { step_mask ^= 4; w.pz -= w.se; }
     w.t_min = tc_max;                                                         // :330
-    w.idx ^= step_mask;                                                       // :331
-    if ((w.idx & step_mask) != 0) {                                           // :335  POP
-        uint32_t differing_bits = 0;                                          // :347-350
-        if (step_mask & 1) differing_bits |= __float_as_uint(w.px) ^ __float_as_uint(w.px + w.se);
-        if (step_mask & 2) differing_bits |= __float_as_uint(w.py) ^ __float_as_uint(w.py + w.se);
-        if (step_mask & 4) differing_bits |= __float_as_uint(w.pz) ^ __float_as_uint(w.pz + w.se);
-        const int scale = 31 - __clz(differing_bits);                         // :360 findMSB
-        w.scale = scale;
-        w.se = __int_as_float((scale - VX_MAX_SCALE + 127) << 23);            // :361 exp2(scale - 23)
-        if (scale >= VX_MAX_SCALE) return 0;                                  // :365
-        const uint32_t lvl = min((uint32_t)(VX_MAX_SCALE - 1 - scale), stack_levels - 1u);   // :370-372
-        stack_load(stk, lvl, w.rec, w.desc, w.t_max);
-        const uint32_t keep = 0xffffffffu << scale;                           // :377-382 floor(pos) at the new scale
-        const uint32_t bx = __float_as_uint(w.px), by = __float_as_uint(w.py), bz = __float_as_uint(w.pz);
-        w.px = __uint_as_float(bx & keep); w.py = __uint_as_float(by & keep); w.pz = __uint_as_float(bz & keep);
-        w.idx = (w.idx & ~7u) | ((bx >> scale) & 1u) | (((by >> scale) & 1u) << 1) | (((bz >> scale) & 1u) << 2);   // :388
-        w.h = 0.0f;                                                           // :390
-        return 2;
-    }
-    return 1;
+    w.ci ^= step_mask;                                                        // :331
+    if (((w.ci ^ w.flags) & step_mask) != 0) return walk_pop<FMT>(w, stk, stack_max_off, step_mask);   // :335 (idx & step_mask)
+    return true;
 }
 
-// One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate. Call only with
-// w.state > 0. On return w.state is: the remaining budget (keep stepping while > 0), ST_LEAF (the current child is a leaf
-// with t_min > 0, :185 — the caller evaluates it and either finishes the ray or calls walk_skip_leaf(), the ADVANCE/POP tail
-// of THIS iteration, and goes on stepping), or ST_MISS.
-// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
-// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
+// Node decode of the current cell (svo.esvo.glsl:164-173 / svo.csvo.glsl:239-245): is there a child in slot ci, is it a leaf.
+template <int FMT>
+__device__ __forceinline__ void walk_decode(Walk& w, bool& is_child, bool& is_leaf) {
+    if (FMT == VX_FMT_CSVO) {
+        is_child = csvo_has_child(w.hdr, w.desc, w.ci);                       // svo.csvo.glsl:239-241
+        is_leaf = w.desc < 2u;                                                // (only looked at when is_child)
+        if (w.desc == 2u) w.preleaf = w.rec;                                  // :243-245
+    } else {
+        const uint32_t d = w.desc >> w.ci;                                    // bit 0: is_leaf, bit 8: is_child (:172-173)
+        is_child = (d & 0x100u) != 0u;
+        is_leaf = (d & 1u) != 0u;
+    }
+}
+
+// The node part of a PUSH into child slot w.ci of the current node (svo.esvo.glsl:292 + the :168 read of the following iterations /
+// svo.csvo.glsl:395-411): (rec, desc[, hdr, mat_ptr]) become the child's.
+template <int FMT>
+__device__ __forceinline__ void walk_descend(Walk& w, const Scene& s) {
+    const uint32_t ci = w.ci;
+    if (FMT == VX_FMT_CSVO) {
+        bool crossed;
+        uint32_t np = csvo_next_ptr(s, w.rec, w.desc, w.hdr, ci, crossed);
+        uint32_t nd = w.desc - 1u;                                            // svo.csvo.glsl:401-402 (unsigned: wraps like the shader's uint)
+        if (crossed) {                                                        // :404-411 entering a chunk record
+            const uint32_t child_lod = csvo_read_byte(s, np);
+            const uint32_t material_bytes = csvo_read_uint(s, np + 1u);
+            np += 5u;
+            w.mat_ptr = np;
+            np += material_bytes;
+            nd = child_lod;
+        }
+        w.rec = np; w.desc = nd;
+        w.hdr = csvo_header(s, np, nd);
+    } else {
+        const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));              // child masks of the new octant (the :168 read of later iterations)
+        const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));                // :292 get_octant_ptr
+        w.desc = wh >> ((ci & 1u) << 4);                                      // bits above 15 are never looked at
+        const uint32_t nr = (wb & 0x7fffffffu) + (((int32_t)wb < 0) ? (w.rec + 4u + ci) : 0u);   // relative (bit 31) or absolute
+        w.rec = min(nr, s.max_rec);
+    }
+}
+
+// One iteration of the loop at svo.esvo.glsl:152-392 exactly as the shader orders it, minus the evaluation of a leaf candidate
+// (see walk_step). Used outside the hot loop: degenerate rays (walk_plain_loop) and the debug cast.
 template <int FMT, bool LIMITED, bool COUNT>
-__device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, uint32_t& last_leaf, Counters& cnt) {
+__device__ __forceinline__ void walk_step_plain(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
     --w.state;                                                                // :152
     if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
     if (COUNT) cnt.steps++;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
-    const uint32_t ci = (w.idx ^ (w.idx >> 4)) & 7u;                          // :164  idx ^ octant_mask
     bool is_child, is_leaf;
-    if (FMT == VX_FMT_CSVO) {
-        is_child = csvo_has_child(w.hdr, w.desc, ci);                         // svo.csvo.glsl:239-241
-        is_leaf = w.desc < 2u;                                                // (only looked at when is_child)
-        if (w.desc == 2u) w.preleaf = w.rec;                                  // :243-245
-    } else {
-        const uint32_t d = w.desc >> ci;                                      // bit 0: is_leaf, bit 8: is_child (:172-173)
-        is_child = (d & 0x100u) != 0u;
-        is_leaf = (d & 1u) != 0u;
-    }
+    walk_decode<FMT>(w, is_child, is_leaf);
     if (is_child && w.t_min <= w.t_max) {                                     // :178
         if (is_leaf) {
             if (w.t_min > 0.0f) { w.state = ST_LEAF - w.state; return; }      // :185
-            if (w.t_min == 0.0f) w.idx |= 0x100u;                             // :180 inside_voxel
+            if (w.t_min == 0.0f) w.flags |= VX_FLAG_INSIDE;                   // :180 inside_voxel
         }
         // :266-312 — also taken by a leaf at t_min == 0 (origin inside a voxel), see SURVEY Appendix B
         const float tv_max = tmin2(w.t_max, tc_max);                          // :278
         if (w.t_min <= tv_max) {                                              // :280  PUSH
             if (COUNT) cnt.pushes++;
             if (tc_max < w.h)                                                 // :284-288
-                stack_store(stk, min((uint32_t)(VX_MAX_SCALE - 1 - w.scale), s.stack_levels - 1u), w.rec,
-                            FMT == VX_FMT_CSVO ? csvo_pack_node(w.desc, w.hdr) : w.desc, w.t_max);
+                stack_store(stk + w.soff, w.rec, FMT == VX_FMT_CSVO ? csvo_pack_node(w.desc, w.hdr) : w.desc, w.t_max);
             w.h = tc_max;                                                     // :289
             const float half = w.se * 0.5f;                                   // :274
             const float tcx_ = __fmaf_rn(half, w.tcx, tcornx), tcy_ = __fmaf_rn(half, w.tcy, tcorny), tcz_ = __fmaf_rn(half, w.tcz, tcornz);   // :275
-            if (FMT == VX_FMT_CSVO) {
-                bool crossed;
-                uint32_t np = csvo_next_ptr(s, w.rec, w.desc, w.hdr, ci, crossed);
-                uint32_t nd = w.desc - 1u;                                    // svo.csvo.glsl:401-402 (unsigned: wraps like the shader's uint)
-                if (crossed) {                                                // :404-411 entering a chunk record
-                    const uint32_t child_lod = csvo_read_byte(s, np);
-                    const uint32_t material_bytes = csvo_read_uint(s, np + 1u);
-                    np += 5u;
-                    w.mat_ptr = np;
-                    np += material_bytes;
-                    nd = child_lod;
-                }
-                w.rec = np; w.desc = nd;
-                w.hdr = csvo_header(s, np, nd);
-            } else {
-                const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));      // child masks of the new octant (the :168 read of later iterations)
-                const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));        // :292 get_octant_ptr
-                w.desc = wh >> ((ci & 1u) << 4);                              // bits above 15 are never looked at
-                const uint32_t nr = (wb & 0x80000000u) ? (w.rec + 4u + ci + (wb & 0x7fffffffu)) : wb;
-                w.rec = min(nr, s.max_rec);
-            }
-            --w.scale; w.se = half;                                           // :295-297
+            walk_descend<FMT>(w, s);
+            w.soff = min(w.soff + VX_STACK_STRIDE, s.stack_max_off);          // --scale (:295)
+            w.se = half;                                                      // :297
             uint32_t idx = 0;                                                 // :301-304
             if (w.t_min < tcx_) { idx ^= 1; w.px += half; }
             if (w.t_min < tcy_) { idx ^= 2; w.py += half; }
             if (w.t_min < tcz_) { idx ^= 4; w.pz += half; }
-            w.idx = (w.idx & ~7u) | idx;
+            w.ci = idx ^ (w.flags & 7u);
             w.t_max = tv_max;                                                 // :307
             return;                                                           // :310
         }
     } else {
-        last_leaf = 0xffffffffu;                                              // :315-316 (adjacent_leaf_count = 0)
+        w.flags &= ~VX_FLAG_ADJACENT;                                         // :315-316 (adjacent_leaf_count = 0)
     }
-    const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
-    if (adv == 0) w.state = ST_MISS;
-    else if (FMT == VX_FMT_CSVO && adv == 2) csvo_unpack_node(w);
+    if (!walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
+}
+
+// The same iteration for the hot loop of the persistent kernels. Call only with w.state > 0 and a non-degenerate ray. On return
+// w.state is: the remaining budget (keep stepping while > 0), <= ST_LEAF (the current child is a leaf with t_min > 0, :185 — the
+// caller evaluates it and either finishes the ray or calls walk_skip_leaf(), the ADVANCE/POP tail of THIS iteration, and goes on
+// stepping), or ST_MISS.
+// A warp's lanes sit in different phases (about half PUSH, half ADVANCE, a third of those POP) and SIMT runs the phases present in
+// a warp one after the other. So what PUSH (child selection, :301-304) and ADVANCE (:324-327) have in common — three comparisons
+// against per-axis plane times, a conditional move of pos along each axis, three bits collected — is stated ONCE, on operands
+// selected per lane, and runs for all lanes together; only the PUSH tail (stack write, the two node loads) and the POP diverge:
+//     PUSH     bit_k = t_min <  fma(half, t_coef_k, t_corner_k)     pos_k += half     idx  = bits
+//     ADVANCE  bit_k = tc_max >= t_corner_k = fma(0, t_coef_k, t_corner_k)   pos_k += -se    idx ^= bits
+// fma(0, c, x) is x exactly for finite c; `a >= b` is `!(a < b)` for ordered operands (degenerate rays never get here);
+// x - se and x + (-se) are the same IEEE operation. Every value the shader computes is computed by the same operation on the
+// same operands, so the walk stays bit-exact (golden step traces, tests/test_gpu_parity.py).
+// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
+// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
+template <int FMT, bool LIMITED, bool COUNT>
+__device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
+    --w.state;                                                                // :152
+    if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
+    if (COUNT) cnt.steps++;
+    const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
+    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
+    bool is_child, is_leaf;
+    walk_decode<FMT>(w, is_child, is_leaf);
+    const bool in = is_child && w.t_min <= w.t_max;                           // :178
+    if (in) {
+        if (is_leaf) {
+            if (w.t_min > 0.0f) { w.state = ST_LEAF - w.state; return; }      // :185
+            if (w.t_min == 0.0f) w.flags |= VX_FLAG_INSIDE;                   // :180 inside_voxel
+        }
+    } else {
+        w.flags &= ~VX_FLAG_ADJACENT;                                         // :315-316 (adjacent_leaf_count = 0)
+    }
+    const float tv_max = tmin2(w.t_max, tc_max);                              // :278
+    const bool push = in && w.t_min <= tv_max;                                // :280
+    const float half = w.se * 0.5f;                                           // :274
+    const float hs = push ? half : 0.0f;
+    const float a = push ? w.t_min : tc_max;
+    const float delta = push ? half : -w.se;
+    const float cx = __fmaf_rn(hs, w.tcx, tcornx), cy = __fmaf_rn(hs, w.tcy, tcorny), cz = __fmaf_rn(hs, w.tcz, tcornz);   // :275 / t_corner
+    uint32_t bits = 0;                                                        // :301-304 / :324-327
+    if ((a < cx) == push) { bits ^= 1; w.px += delta; }
+    if ((a < cy) == push) { bits ^= 2; w.py += delta; }
+    if ((a < cz) == push) { bits ^= 4; w.pz += delta; }
+    if (push) {                                                               // :280-310
+        if (COUNT) cnt.pushes++;
+        if (tc_max < w.h)                                                     // :284-288
+            stack_store(stk + w.soff, w.rec, FMT == VX_FMT_CSVO ? csvo_pack_node(w.desc, w.hdr) : w.desc, w.t_max);
+        w.h = tc_max;                                                         // :289
+        walk_descend<FMT>(w, s);                                              // child slot: still the parent's w.ci
+        w.soff = min(w.soff + VX_STACK_STRIDE, s.stack_max_off);              // --scale (:295)
+        w.se = half;                                                          // :297
+        w.ci = bits ^ (w.flags & 7u);
+        w.t_max = tv_max;                                                     // :307
+    } else {                                                                  // :324-391
+        w.t_min = tc_max;                                                     // :330
+        w.ci ^= bits;                                                         // :331
+        if (((w.ci ^ w.flags) & bits) != 0)                                   // :335
+            if (!walk_pop<FMT>(w, stk, s.stack_max_off, bits)) w.state = ST_MISS;
+    }
 }
 
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
@@ -469,21 +557,37 @@ __device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t
     const int budget = ST_LEAF - w.state;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
-    const int adv = walk_advance(w, stk, s.stack_levels, tcornx, tcorny, tcornz, tc_max);
-    w.state = adv ? budget : ST_MISS;
-    if (FMT == VX_FMT_CSVO && adv == 2) csvo_unpack_node(w);
+    w.state = walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
+}
+
+// Degenerate rays (VX_FLAG_DEGENERATE: a NaN among the ray coefficients) are walked here, outside the hot loop, by the plain step
+// until they stop (leaf candidate / miss / budget). Call after walk_init and after walk_skip_leaf; a no-op for every other ray.
+// Out of line and on a copy, so that the caller's Walk stays in registers.
+template <int FMT, bool LIMITED, bool COUNT>
+__device__ __noinline__ void walk_plain_loop(Walk* w, const Scene* s, uint32_t stk, Counters* cnt) {
+    while (w->state > 0) walk_step_plain<FMT, LIMITED, COUNT>(*w, *s, stk, *cnt);
+}
+template <int FMT, bool LIMITED, bool COUNT>
+__device__ __forceinline__ void walk_degenerate(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
+    if ((w.flags & VX_FLAG_DEGENERATE) && w.state > 0) {
+        Walk tmp = w;
+        Scene sc = s;
+        Counters c = cnt;
+        walk_plain_loop<FMT, LIMITED, COUNT>(&tmp, &sc, stk, &c);
+        w = tmp;
+        cnt = c;
+    }
 }
 
 template <int FMT>
 __device__ __forceinline__ uint32_t leaf_value(const Walk& w, const Scene& s) {   // svo.esvo.glsl:190-194 / svo.csvo.glsl:259
-    const uint32_t ci = (w.idx ^ (w.idx >> 4)) & 7u;
-    if (FMT == VX_FMT_CSVO) return csvo_read_leaf(s, w.mat_ptr, w.preleaf, w.rec, ci);
-    return __ldg(s.desc + (w.rec + 4u + ci));
+    if (FMT == VX_FMT_CSVO) return csvo_read_leaf(s, w.mat_ptr, w.preleaf, w.rec, w.ci);
+    return __ldg(s.desc + (w.rec + 4u + w.ci));
 }
 
 // HIT block geometry, svo.esvo.glsl:197-224 + :233, for the leaf candidate walk_step stopped at.
 __device__ __forceinline__ void leaf_geom(const Walk& w, float rox, float roy, float roz, float rdx, float rdy, float rdz, float inv_octree_scale, Leaf& g) {
-    const uint32_t octant_mask = (w.idx >> 4) & 7u;
+    const uint32_t octant_mask = w.flags & 7u;
     const float se = w.se;
     const float tnx = __fmaf_rn(w.px + se, w.tcx, -w.tbx), tny = __fmaf_rn(w.py + se, w.tcy, -w.tby), tnz = __fmaf_rn(w.pz + se, w.tcz, -w.tbz);   // :197
     const float tc_min = tmax2(tmax2(tnx, tny), tnz);                         // :199

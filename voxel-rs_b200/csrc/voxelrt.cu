@@ -129,6 +129,7 @@ static Scene make_scene(const VxCtx* c) {
     s.unorm = c->d_unorm;
     uint32_t levels = c->stats.depth + (c->fmt == VX_FMT_CSVO ? 3 : 1);   // CSVO: the oracle's stack policy for out-of-spec descents
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
+    s.stack_max_off = (s.stack_levels - 1u) * VX_STACK_STRIDE;
     return s;
 }
 static size_t stack_smem_bytes(const Scene& s) { return smem_bytes(s.stack_levels); }

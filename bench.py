@@ -184,18 +184,31 @@ def cpu_render_sample(scene, vxp, args, threads, budget_s, frac=0.1, min_s=0.0):
     return rays / t_used, f"{what} ({rays} rays, {t_used:.1f} s on {threads} threads)", rays, t_used
 
 
+def host_threads():
+    """Threads the CPU arms run on: every core this process may use. NOT omp_get_max_threads(): torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which made the round-1 reference arm run single-threaded at N>1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
-    """--impl reference: the CPU port of the reference shaders (oracle/), all host threads, bounded sample per step."""
+    """--impl reference: the CPU port of the reference shaders (oracle/), all host threads, bounded sample per step.
+    The process never maps the product library: the world is built with libvoxelrs_world.so (VOXELRS_WORLD_ONLY)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["VOXELRS_WORLD_ONLY"] = "1"
     pkg, ora = graft.load_pkg(), graft.load_oracle()
     world, _ = build_world(pkg, args)
     reg = pkg.content_registry(pkg.load_atlas())
     tex, mips = reg.textures()
     scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
     vxp = frame_params(pkg, world, args)
-    threads = ora.max_threads()
+    threads = host_threads()
+    with open("/proc/self/maps") as f:
+        assert "libvoxelrt" not in f.read(), "the reference arm must not map the product library"
     # one step = the whole frame on all host threads (about a third of a second at 4K on 16 threads); if the box is so slow
     # that K+W frames would take more than ~3 minutes, fall back to a 10 % row sample per step
     t0 = time.time()
@@ -398,6 +411,26 @@ def main():
     kernel_ms = float(np.mean(kms))
     split_ms = dict(zip(("trace_primary", "shade", "trace_shadow"), (round(float(v), 4) for v in np.mean(np.array(parts), axis=0))))
 
+    # ---- N > 1: the gathered frame must be the frame. One sharded step, then rank 0 renders the same frame alone and compares
+    # byte for byte (RGBA8 in p2p8 mode, RGBA32F otherwise). A mismatch voids the line: the run stops.
+    parity_check = None
+    if n_gpus > 1:
+        read = svo.read_rgba8 if args.gather == "p2p8" else svo.read_rgba32f
+        step_resident()
+        barrier()
+        got = read() if rank == 0 else None
+        barrier()
+        if rank == 0:
+            svo.render_raw(vxp, W, H, shard=None)
+            want = read()
+            same = got.tobytes() == want.tobytes()
+            parity_check = (f"frame gathered from {n_gpus} GPUs == rank 0's unsharded render, byte for byte ({got.nbytes} bytes, "
+                            f"{'RGBA8' if args.gather == 'p2p8' else 'RGBA32F'})") if same else "MISMATCH"
+        flag = torch.tensor([1 if (rank != 0 or parity_check != "MISMATCH") else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise SystemExit("bench.py: the gathered multi-GPU frame differs from the single-GPU frame — no number reported")
+
     # ---- the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total, launches, t0, t1 = timed(step_resident, args.steps, args.warmup)
@@ -414,6 +447,12 @@ def main():
                         "RGBA8 D2H copy into pinned host memory)" % args.bands) if n_gpus == 1 else
                        "host dirty ranges -> pack -> H2D -> NCCL broadcast -> scatter -> sharded render -> tiles to GPU 0 -> vx_read_frame_rgba8 (D2H)"}
 
+    if n_gpus > 1:
+        # a frame-flag wait that timed out (lost / slow peer) means torn frames: the numbers above would be of garbage
+        errs = torch.tensor([svo.frame_sync_errors()], device=dev)
+        dist.all_reduce(errs)
+        if int(errs.item()):
+            raise SystemExit(f"bench.py: {int(errs.item())} frame-flag waits timed out during the run — no number reported")
     if rank != 0:
         if n_gpus > 1:
             dist.barrier()
@@ -463,7 +502,7 @@ def main():
             "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 160 MiB device fill (> 126 MB L2) inside the timed region",
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)", "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
-            "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2),
+            "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
                                ("finished pixels stored by the shade/shadow kernels straight into GPU 0's %s framebuffer over NVLink peer memory, "
                                 "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"
@@ -488,7 +527,7 @@ def main():
         ora = graft.load_oracle()
         tex, mips = reg.textures()
         scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
-        threads = ora.max_threads()
+        threads = host_threads()
         rps, desc, _, _ = cpu_render_sample(scene, vxp, args, threads, args.cpu_seconds, frac=1.0, min_s=min(1.5, args.cpu_seconds))
         line["cpu_baseline"] = {"value": rps / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
     print(json.dumps(line), flush=True)
@@ -714,7 +753,7 @@ def run_picker(args):
         ora = graft.load_oracle()
         tex, mips = reg.textures()
         scene = ora.Scene(world.gpu_buffer(), reg.materials().tobytes(), tex, mips, fmt=world.fmt)
-        threads = ora.max_threads()
+        threads = host_threads()
         m = min(n, 1 << 18)
         scene.raycast(tasks[:4096], threads=threads)
         tc = time.time()

@@ -227,6 +227,10 @@ int vx_svo_commit_packed_device(VxCtx* ctx, const void* packed_dev, uint32_t n_d
 /* Rank-0 helper: pack mirror ranges into `out` (host, pinned or not) in the layout above.
  * Returns bytes written or a negative error; call with out==NULL to query the size. */
 int64_t vx_svo_pack_dirty(VxCtx* ctx, const VxRange* dirty, uint32_t n_dirty, void* out, uint64_t out_cap);
+/* Ranges of packed dirty sets that the scatter kernel refused so far because offset + length would leave the buffer (the headers
+ * of vx_svo_commit_packed_device live in device memory, so they are checked there; a refused range is skipped, never written out
+ * of bounds). Waits for the upload stream. 0 in a healthy run. */
+int vx_svo_scatter_errors(VxCtx* ctx, uint32_t* out);
 
 int vx_stats(const VxCtx* ctx, VxStats* out);
 
@@ -255,6 +259,21 @@ int vx_read_frame_rgba32f(VxCtx* ctx, float* rgba32f_out);
 /* Device pointer of the RGBA32F framebuffer of the last render (for zero-copy consumers /
  * NCCL tile gather). Valid until vx_destroy. */
 int vx_frame_device_ptr(VxCtx* ctx, void** out_ptr, uint32_t* width, uint32_t* height);
+
+/* Parity instrument: what intersect_octree (svo.esvo.glsl:50-393) returned for the PRIMARY ray of every pixel of the last
+ * vx_render — the OctreeResult fields world.glsl reads (:131-137), before any shading. out = width * height records, row 0 =
+ * bottom, like the frame. A miss has t = -1 and zeros. Pixels of macro blocks another shard owns are not filled (t = -2).
+ * The reference keeps these values in shader registers; here they are the hit records the wavefront hands from
+ * trace_primary_kernel to shade_kernel, so the bit-exactness bar of the hit voxel / material / face / distance can be tested
+ * directly instead of through colours. */
+typedef struct VxHitRecord {
+    float    t;          /* res.t (voxel units), -1 = miss */
+    uint32_t value;      /* res.value: block id */
+    int32_t  face_id;    /* res.face_id 0..5 */
+    float    pos[3];     /* res.pos */
+    float    uv[2];      /* res.uv */
+} VxHitRecord;
+int vx_read_hit_records(VxCtx* ctx, VxHitRecord* out);
 
 /* graphics::Svo::raycast (svo.rs:233-255) = picker.glsl main(): tasks/results are HOST arrays of n
  * records; synchronous like the reference (fence place+wait, svo.rs:248-249). n is not capped at
@@ -332,6 +351,9 @@ int vx_frame_signal(VxCtx* ctx, uint32_t slot, uint32_t value);
 int vx_frame_wait(VxCtx* ctx, uint32_t first_slot, uint32_t n_slots, uint32_t value);
 int vx_frame_gate(VxCtx* ctx, uint32_t slot, uint32_t value);
 int vx_frame_sync_errors(VxCtx* ctx, uint32_t* out);
+/* Zeroes this context's frame flags (and error counters) after waiting for its render stream. The root calls it — followed by a
+ * barrier among the ranks — before a new sequence of frames starts counting from 1 again. */
+int vx_frame_flags_reset(VxCtx* ctx);
 
 /* Run this context's work on caller-owned CUDA streams (cudaStream_t passed as void*) so that it orders
  * with the caller's collectives without host synchronisation. NULL keeps the library's own stream. */

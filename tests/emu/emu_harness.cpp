@@ -306,8 +306,9 @@ EMU_API int emu_serialize_chunks(const uint32_t* blocks, uint32_t n_chunks, cons
 }
 
 // scatter_ranges_kernel (vx_svo_commit's staged path / vx_svo_commit_packed_device): packed = [n VxRange | head | range bytes...]
-EMU_API int emu_scatter_ranges(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, uint64_t payload_bytes, uint32_t head_bytes, uint32_t blocks) {
-    emu::launch(blocks ? blocks : 1, 256, [&] { scatter_ranges_kernel(world, packed, n_ranges, payload_bytes, head_bytes / 4); });
+EMU_API int emu_scatter_ranges(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, uint64_t payload_bytes, uint32_t head_bytes, uint32_t blocks,
+                               uint64_t capacity, unsigned int* errors) {
+    emu::launch(blocks ? blocks : 1, 256, [&] { scatter_ranges_kernel(world, packed, n_ranges, payload_bytes, head_bytes, capacity, errors); });
     return 0;
 }
 

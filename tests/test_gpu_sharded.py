@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H = 1000, 562
 
 
-def _worker(rank, world_size, port, out_dir):
+def _worker(rank, world_size, port, out_dir, fmt=0):
     sys.path.insert(0, ROOT)
     import ctypes
     import torch
@@ -25,19 +25,25 @@ def _worker(rank, world_size, port, out_dir):
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world_size, device_id=dev)
     try:
         reg = pkg.content_registry(pkg.load_atlas())
-        world = pkg.World(radius=5, center=(-1, 2, 5), seed=1)
+        world = pkg.World(radius=5, center=(-1, 2, 5), seed=1, fmt=fmt)
         world.generate(0, 8)
         world.serialize()
-        svo = pkg.Svo(reg, size_mb=world.size_bytes // 1_000_000 + 16, max_width=W, max_height=H, max_rays=16, device=rank)
+        HB = world.header_bytes
+        svo = pkg.Svo(reg, size_mb=world.size_bytes // 1_000_000 + 16, max_width=W, max_height=H, max_rays=16, device=rank, flags=world.svo_flags)
         stream = torch.cuda.Stream(device=dev)
         torch.cuda.set_stream(stream)
         svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
         world.mark_all_dirty()
         svo.update(world)          # every replica starts from the same SVO
-        p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=(1.0, -0.3, 0.0), fov_y_deg=72.0, aspect=W / H)
-        q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
-        q.cam_pos = (ctypes.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
-        vxp = pkg.to_vx_render_params(q)
+        # a different view every frame: a root that reads its framebuffer too early (stale frame flags, a lost gate) gets pixels of
+        # the previous view and the comparison below fails — with identical frames it could not
+        views = []
+        for fwd in ((1.0, -0.3, 0.0), (0.6, -0.35, 0.5), (0.2, -0.25, -1.0)):
+            p = pkg.render_params(cam_pos=(-24.0, 80.0, 174.0), cam_fwd=fwd, fov_y_deg=72.0, aspect=W / H)
+            q = pkg.VxhRenderParams.from_buffer_copy(bytes(p))
+            q.cam_pos = (ctypes.c_float * 3)(*world.cnv_block_pos(tuple(p.cam_pos)))
+            views.append(pkg.to_vx_render_params(q))
+        vxp = views[-1]
 
         # rank 0 edits the world; the other replicas only ever see the broadcast
         meta = [None]
@@ -51,9 +57,15 @@ def _worker(rank, world_size, port, out_dir):
             mirror = svo.host_mirror(len(new))
             old = mirror.copy()
             mirror[:] = new
-            diff = np.nonzero(new[24:len(old)] != old[24:])[0]
-            lo, hi = int(diff.min()) // 4 * 4, (int(diff.max()) // 4 + 1) * 4
+            diff = np.nonzero(new[HB:len(old)] != old[HB:])[0]
+            lo, hi = int(diff.min()), int(diff.max()) + 1
+            if fmt == 0:
+                lo, hi = lo // 4 * 4, (hi + 3) // 4 * 4
+            elif lo % 4 == 0 and lo > 0:
+                lo -= 1                                                  # CSVO: make sure the unaligned path of the scatter kernel runs
             ranges = [(lo, hi - lo)]
+            if len(new) > len(old):
+                ranges.append((len(old) - HB, len(new) - len(old)))
             n = svo.pack_dirty(ranges, None)
             packed_host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             svo.pack_dirty(ranges, packed_host.numpy())
@@ -72,7 +84,7 @@ def _worker(rank, world_size, port, out_dir):
                 sf.apply_dirty()
                 if i < 2:
                     sf.prefetch_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
-                sf.render(vxp)
+                sf.render(views[i])
                 sf.finish()
                 if rank == 0 and i == 2:
                     svo.width, svo.height = W, H
@@ -95,7 +107,8 @@ def _worker(rank, world_size, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_gpus_sharded_frame(pkg, tmp_path):
+@pytest.mark.parametrize("fmt", [0, 1], ids=["esvo", "csvo"])
+def test_two_gpus_sharded_frame(pkg, tmp_path, fmt):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -104,7 +117,7 @@ def test_two_gpus_sharded_frame(pkg, tmp_path):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), fmt), nprocs=2, join=True)
     full = np.load(tmp_path / "full.npy")
     assert np.isfinite(full).all()
     for k in ("p2p", "nccl"):

@@ -287,18 +287,33 @@ def test_emulated_dirty_scatter_and_shard_copy(emu, pkg):
     from importlib import import_module
     sharded = import_module(pkg.__name__ + ".sharded")
     rng = np.random.default_rng(5)
-    head = 24
-    mirror = rng.integers(0, 256, 4096 + head, dtype=np.uint8)
-    ranges = [(0, 48), (96, 480), (1024, 4), (4000, 96)]
-    packed = np.ascontiguousarray(sharded.pack_dirty_host(mirror, ranges))
-    replica = np.zeros_like(mirror)
+    # ESVO: 24-byte head, word-aligned ranges; CSVO: 8-byte head, ranges at arbitrary byte offsets and of arbitrary length (tails of
+    # 1-3 bytes, a 1-byte range, two ranges sharing a word)
+    for head, ranges in ((24, [(0, 48), (96, 480), (1024, 4), (4000, 96)]), (8, [(0, 13), (13, 1), (14, 5), (101, 479), (1023, 6), (3001, 1003)])):
+        mirror = rng.integers(0, 256, 4096 + head, dtype=np.uint8)
+        packed = np.ascontiguousarray(sharded.pack_dirty_host(mirror, ranges, head=head))
+        replica = np.zeros_like(mirror)
+        want = replica.copy()
+        assert sharded.apply_packed_host(want, packed, len(ranges), head=head) == (len(packed), 0)
+        payload = len(packed) - 16 * len(ranges)
+        errors = C.c_uint(0)
+        emu.emu_scatter_ranges(C.c_void_p(replica.ctypes.data), C.c_void_p(packed.ctypes.data), C.c_uint32(len(ranges)), C.c_uint64(payload),
+                               C.c_uint32(head), C.c_uint32(3), C.c_uint64(len(replica)), C.byref(errors))
+        assert replica.tobytes() == want.tobytes() and errors.value == 0
+        for off, ln in ranges:
+            assert replica[head + off:head + off + ln].tobytes() == mirror[head + off:head + off + ln].tobytes()
+    # a header that points outside the buffer: that range is skipped and counted, the others are applied, nothing is written out of bounds
+    head, ranges = 24, [(0, 48), (4090, 64), (200, 8)]
+    mirror = rng.integers(0, 256, 8192, dtype=np.uint8)
+    packed = np.ascontiguousarray(sharded.pack_dirty_host(mirror, ranges, head=head))
+    guard = np.zeros(4096 + head + 256, np.uint8)
+    replica = guard[:4096 + head]
     want = replica.copy()
-    sharded.apply_packed_host(want, packed, len(ranges))
-    payload = len(packed) - 16 * len(ranges)
-    emu.emu_scatter_ranges(C.c_void_p(replica.ctypes.data), C.c_void_p(packed.ctypes.data), C.c_uint32(len(ranges)), C.c_uint64(payload), C.c_uint32(head), C.c_uint32(3))
-    assert replica.tobytes() == want.tobytes()
-    for off, ln in ranges:
-        assert replica[head + off:head + off + ln].tobytes() == mirror[head + off:head + off + ln].tobytes()
+    assert sharded.apply_packed_host(want, packed, len(ranges), head=head)[1] == 1
+    errors = C.c_uint(0)
+    emu.emu_scatter_ranges(C.c_void_p(replica.ctypes.data), C.c_void_p(packed.ctypes.data), C.c_uint32(len(ranges)), C.c_uint64(len(packed) - 48),
+                           C.c_uint32(head), C.c_uint32(2), C.c_uint64(len(replica)), C.byref(errors))
+    assert replica.tobytes() == want.tobytes() and errors.value == 1 and not guard[4096 + head:].any()
     w, h, size = 70, 40, 3
     frame = rng.random((h, w, 4), dtype=np.float32)
     rebuilt = np.zeros_like(frame)

@@ -21,8 +21,8 @@ W, H = 100, 70   # ragged: not a multiple of the 32x16 macro block
 class HostEngine:
     """Stand-in with the method surface ShardedFrame uses from voxelrs_b200.Svo, on host memory."""
 
-    def __init__(self, pkg, ora, sharded, world_buffer, reg, width, height):
-        self.pkg, self.ora, self.sharded, self.reg = pkg, ora, sharded, reg
+    def __init__(self, pkg, ora, sharded, world_buffer, reg, width, height, fmt=0, head=24):
+        self.pkg, self.ora, self.sharded, self.reg, self.fmt, self.head = pkg, ora, sharded, reg, fmt, head
         self.world_buffer = world_buffer          # this rank's replica of the GPU world buffer (uint8)
         self.frame = np.zeros((height, width, 4), np.float32)
         self.width, self.height = width, height
@@ -33,12 +33,12 @@ class HostEngine:
 
     def commit_packed_device(self, ptr, n_ranges, payload_bytes, used_bytes, depth):
         packed = self._view(ptr, 16 * n_ranges + payload_bytes)
-        consumed = self.sharded.apply_packed_host(self.world_buffer, packed, n_ranges)
-        assert consumed == 16 * n_ranges + payload_bytes
+        consumed, skipped = self.sharded.apply_packed_host(self.world_buffer, packed, n_ranges, head=self.head)
+        assert consumed == 16 * n_ranges + payload_bytes and skipped == 0
 
     def render_raw(self, vx_params, width, height, shard=None):
         tex, mips = self.reg.textures()
-        scene = self.ora.Scene(self.world_buffer, self.reg.materials().tobytes(), tex, mips)
+        scene = self.ora.Scene(self.world_buffer, self.reg.materials().tobytes(), tex, mips, fmt=self.fmt)
         full, _ = scene.render(vx_params, width, height)
         tiles = self.sharded.TileShards(width, height, shard[1])
         mine = tiles.owner_map() == shard[0]
@@ -54,7 +54,7 @@ class HostEngine:
         tiles.unpack(self.frame, shard[0], self._view(ptr, tiles.shard_bytes(shard[0])).copy())
 
 
-def _worker(rank, world_size, port, result_path):
+def _worker(rank, world_size, port, result_path, fmt=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -69,10 +69,11 @@ def _worker(rank, world_size, port, result_path):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world_size)
     try:
         reg = pkg.content_registry(pkg.load_atlas())
-        world = pkg.World(radius=2, center=(-1, 2, 5), seed=1)
+        world = pkg.World(radius=2, center=(-1, 2, 5), seed=1, fmt=fmt)
         world.generate(0, 8)
         world.serialize()
-        capacity = world.size_bytes + 24 + (1 << 20)
+        HB = world.header_bytes                          # 24 ESVO, 8 CSVO
+        capacity = world.size_bytes + HB + (1 << 20)
         replica = np.zeros(capacity, np.uint8)
         base = world.gpu_buffer()
         replica[:len(base)] = base                       # every rank starts from the same committed SVO
@@ -91,19 +92,21 @@ def _worker(rank, world_size, port, result_path):
             mirror = np.zeros(capacity, np.uint8)
             mirror[:len(new)] = new
             if not ranges:   # dirty list already drained by serialize(): fall back to a diff of the two images
-                diff = np.nonzero(new[24:len(base)] != base[24:])[0]
+                diff = np.nonzero(new[HB:len(base)] != base[HB:])[0]
                 lo, hi = int(diff.min()) // 4 * 4, (int(diff.max()) // 4 + 1) * 4
                 ranges = [(lo, hi - lo)]
                 if len(new) > len(base):
-                    ranges.append((len(base) - 24, len(new) - len(base)))
-            packed = sharded.pack_dirty_host(mirror, ranges)
+                    ranges.append((len(base) - HB, len(new) - len(base)))
+            if fmt == 1:     # CSVO ranges are byte-granular: at least one of them must be unaligned for this test to mean anything
+                assert any(o % 4 or l % 4 for o, l in ranges), ranges
+            packed = sharded.pack_dirty_host(mirror, ranges, head=HB)
             packed_host = torch.from_numpy(packed.copy())
             n_ranges, payload, used, depth = len(ranges), len(packed) - 16 * len(ranges), world.size_bytes, world.depth
         meta = [(n_ranges, payload, used, depth)]
         dist.broadcast_object_list(meta, src=0)
         n_ranges, payload, used, depth = meta[0]
 
-        engine = HostEngine(pkg, ora, sharded, replica, reg, W, H)
+        engine = HostEngine(pkg, ora, sharded, replica, reg, W, H, fmt=fmt, head=HB)
         sf = sharded.ShardedFrame(engine, rank, world_size, dist=dist, torch=torch, device=torch.device("cpu"), gather="nccl")
         sf.configure(W, H, max_dirty_bytes=16 * n_ranges + payload)
         sf.broadcast_dirty(n_ranges, payload, used, depth, packed_host=packed_host)
@@ -123,7 +126,7 @@ def _worker(rank, world_size, port, result_path):
         sf.release()
         if rank == 0:
             tex, mips = reg.textures()
-            full, _ = ora.Scene(replica, reg.materials().tobytes(), tex, mips).render(vxp, W, H)
+            full, _ = ora.Scene(replica, reg.materials().tobytes(), tex, mips, fmt=fmt).render(vxp, W, H)
             # (2) gathered frame == unsharded frame
             assert engine.frame.tobytes() == full.tobytes()
             assert np.isfinite(full).all() and full[..., :3].std() > 0.01
@@ -141,10 +144,11 @@ def _free_port():
     return port
 
 
-def test_two_ranks_over_gloo(pkg, ora, tmp_path):
+@pytest.mark.parametrize("fmt", [0, 1], ids=["esvo", "csvo"])
+def test_two_ranks_over_gloo(pkg, ora, tmp_path, fmt):
     import torch.multiprocessing as mp
     result = tmp_path / "rank0.txt"
-    mp.spawn(_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(result), fmt), nprocs=2, join=True)
     assert result.read_text() == "ok"
 
 

@@ -103,6 +103,8 @@ TASK_DTYPE = np.dtype({"names": ["max_dst", "pos", "dir"], "formats": ["<f4", ("
 RESULT_DTYPE = np.dtype({"names": ["dst", "inside_voxel", "pos", "normal"], "formats": ["<f4", "<u4", ("<f4", 3), ("<f4", 3)],
                          "offsets": [0, 4, 16, 32], "itemsize": 48})
 
+HIT_DTYPE = np.dtype([("t", "<f4"), ("value", "<u4"), ("face_id", "<i4"), ("pos", "<f4", 3), ("uv", "<f4", 2)])   # VxHitRecord, 32 bytes
+
 VX_FLAG_NO_L2_WINDOW = 1
 VX_FLAG_SVO_CSVO = 4
 FORMAT_ESVO, FORMAT_CSVO = 0, 1
@@ -119,6 +121,7 @@ VX_SYMBOLS = [
     "vx_sync_ipc_handle", "vx_open_peer_sync", "vx_close_peer_sync", "vx_frame_signal", "vx_frame_wait", "vx_frame_gate",
     "vx_frame_sync_errors", "vx_frame8_ipc_handle", "vx_open_peer_frame8",
     "vx_serialize_chunks_esvo", "vx_serialize_chunks_result", "vx_svo_write_device",
+    "vx_svo_scatter_errors", "vx_frame_flags_reset", "vx_read_hit_records",
 ]
 
 _lib = None
@@ -188,17 +191,24 @@ def lib():
     L.vx_frame_wait.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32]; L.vx_frame_wait.restype = C.c_int
     L.vx_frame_gate.argtypes = [P, C.c_uint32, C.c_uint32]; L.vx_frame_gate.restype = C.c_int
     L.vx_frame_sync_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_frame_sync_errors.restype = C.c_int
+    L.vx_svo_scatter_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_svo_scatter_errors.restype = C.c_int
+    L.vx_frame_flags_reset.argtypes = [P]; L.vx_frame_flags_reset.restype = C.c_int
+    L.vx_read_hit_records.argtypes = [P, P]; L.vx_read_hit_records.restype = C.c_int
     _lib = L
     return L
 
 
 def host():
-    """libvoxelrs_host.so (C++ host mirror) with argtypes set."""
+    """libvoxelrs_host.so (C++ host mirror) with argtypes set. With VOXELRS_WORLD_ONLY=1 in the environment (bench.py's reference
+    arm) the world-producer half alone, libvoxelrs_world.so, is loaded instead: World / registries work, nothing that needs the GPU
+    library exists, and libvoxelrt.so is never mapped into the process."""
     global _host
     if _host is not None:
         return _host
-    lib()  # dependency, loaded RTLD_GLOBAL first
-    H = _load("libvoxelrs_host.so")
+    world_only = os.environ.get("VOXELRS_WORLD_ONLY") == "1"
+    if not world_only:
+        lib()  # dependency, loaded RTLD_GLOBAL first
+    H = _load("libvoxelrs_world.so" if world_only else "libvoxelrs_host.so")
     P, u8p, u32, u64, i32, f = C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_float
     sig = {
         "vxh_last_error": ([], C.c_char_p),
@@ -286,6 +296,8 @@ def host():
         "vxh_worldsvo_raycast": ([P, P, P, u32, P, u32, P, P], C.c_int),
     }
     for name, (args, res) in sig.items():
+        if world_only and (name.startswith("vxh_svo_") or name.startswith("vxh_worldsvo_")):
+            continue
         fn = getattr(H, name)
         fn.argtypes = args
         fn.restype = res
@@ -677,6 +689,12 @@ class Svo:
         self._check(lib().vx_read_frame_rgba32f(self.ctx, _ptr(out)))
         return out
 
+    def read_hit_records(self):
+        """OctreeResult of every pixel's primary ray of the last render (VxHitRecord, row 0 = bottom)."""
+        out = np.zeros((self.height, self.width), dtype=HIT_DTYPE)
+        self._check(lib().vx_read_hit_records(self.ctx, _ptr(out)))
+        return out
+
     def read_rgba8(self):
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(lib().vx_read_frame_rgba8(self.ctx, _ptr(out)))
@@ -836,6 +854,14 @@ class Svo:
         n = C.c_uint32()
         self._check(lib().vx_frame_sync_errors(self.ctx, C.byref(n)))
         return n.value
+
+    def scatter_errors(self):
+        n = C.c_uint32()
+        self._check(lib().vx_svo_scatter_errors(self.ctx, C.byref(n)))
+        return n.value
+
+    def frame_flags_reset(self):
+        self._check(lib().vx_frame_flags_reset(self.ctx))
 
     def frame_device_ptr(self):
         p, w, h = C.c_void_p(), C.c_uint32(), C.c_uint32()

@@ -2,6 +2,7 @@
 
   libvoxelrt.so        CUDA kernels + C ABI (include/voxelrt.h), nvcc, sm_100a only
   libvoxelrs_host.so   C++ host mirror of the reference's Rust interfaces (links libvoxelrt)
+  libvoxelrs_world.so  the world-producer half of it alone (octree / ESVO / CSVO serializers, terrain generator): no libvoxelrt
 
 The CPU oracle under oracle/ is test infrastructure with its own Makefile; nothing here builds or loads it.
 """
@@ -65,6 +66,11 @@ def build_host(force=False):
         return out
     cmd = [_cxx(), "-O2", "-std=c++17", "-fPIC", "-Wall", "-shared", "-o", out] + srcs + [
         "-L" + PKG, "-lvoxelrt", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=hdir)
+    # the same sources without the graphics::Svo mirror: world producers only, NO dependency on libvoxelrt. bench.py's reference arm
+    # builds its world with this one, so that the CPU baseline process never maps the product library.
+    cmd = [_cxx(), "-O2", "-std=c++17", "-fPIC", "-Wall", "-shared", "-DVXH_WORLD_ONLY", "-Wl,--no-undefined", "-o",
+           os.path.join(PKG, "libvoxelrs_world.so")] + srcs + ["-lpthread"]
     subprocess.run(cmd, check=True, cwd=hdir)
     return out
 

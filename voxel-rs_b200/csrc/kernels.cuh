@@ -700,21 +700,41 @@ __global__ void __launch_bounds__(128) shard_copy_kernel(float4* frame, float4* 
     }
 }
 
-// Applies a packed dirty set (n VxRange headers, then [24 head bytes][range 0 bytes][range 1 bytes]...) to the world
-// buffer of a replica. Word-granular: every range offset/length is a multiple of 4.
-__global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes, uint32_t head_words) {
+// Applies a packed dirty set — n VxRange headers, then the payload [head bytes of the world buffer][range 0 bytes][range 1 bytes]... —
+// to the world buffer of a replica. The payload is byte-packed and ranges may sit at any byte offset (CSVO ranges are not
+// word-aligned): a thread moves one 4-byte group of the payload, as one word when source and destination are both aligned and
+// the group lies inside one range, byte by byte otherwise. A range that does not fit the buffer (offset + length + head >
+// capacity) is skipped and counted in *error_word: a corrupt header must not become an out-of-bounds device write.
+__global__ void scatter_ranges_kernel(uint8_t* world, const uint8_t* packed, uint32_t n_ranges, unsigned long long payload_bytes, uint32_t head_bytes,
+                                      unsigned long long capacity, unsigned int* error_word) {
     const VxRange* hdr = reinterpret_cast<const VxRange*>(packed);
-    const uint32_t* payload = reinterpret_cast<const uint32_t*>(packed + (size_t)n_ranges * sizeof(VxRange));
-    uint32_t* w32 = reinterpret_cast<uint32_t*>(world);
-    const unsigned long long words = payload_bytes / 4;
+    const uint8_t* payload = packed + (size_t)n_ranges * sizeof(VxRange);
+    const unsigned long long groups = (payload_bytes + 3) / 4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
-        if (i < head_words) { w32[i] = payload[i]; continue; }
-        unsigned long long off = head_words;
-        for (uint32_t k = 0; k < n_ranges; ++k) {
-            const unsigned long long len = hdr[k].length / 4;
-            if (i < off + len) { w32[head_words + hdr[k].offset / 4 + (i - off)] = payload[i]; break; }
-            off += len;
+    const bool src_aligned = (reinterpret_cast<unsigned long long>(payload) & 3ull) == 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += stride) {
+        const unsigned long long b0 = i * 4, b1 = (b0 + 4 < payload_bytes) ? b0 + 4 : payload_bytes;
+        if (b1 <= head_bytes) {                                               // the head (scale + preamble / root pointer): word-aligned
+            for (unsigned long long b = b0; b < b1; ++b) world[b] = payload[b];
+            continue;
+        }
+        unsigned long long off = head_bytes;                                  // payload offset of range k
+        uint32_t k = 0;
+        for (unsigned long long b = b0; b < b1; ++b) {
+            if (b < head_bytes) { world[b] = payload[b]; continue; }
+            while (k < n_ranges && b >= off + hdr[k].length) { off += hdr[k].length; ++k; }
+            if (k >= n_ranges) break;                                         // payload_bytes longer than the headers say: ignore the rest
+            const unsigned long long ro = hdr[k].offset, rl = hdr[k].length;
+            if (ro + rl + head_bytes > capacity || ro + rl < ro) {            // would leave the buffer: skip the range, count it once
+                if (b == off) atomicAdd(error_word, 1u);
+                continue;
+            }
+            const unsigned long long dst = head_bytes + ro + (b - off);
+            if (b == b0 && b0 + 4 == b1 && src_aligned && (dst & 3ull) == 0 && b0 + 4 <= off + rl) {
+                *reinterpret_cast<uint32_t*>(world + dst) = *reinterpret_cast<const uint32_t*>(payload + b0);
+                break;
+            }
+            world[dst] = payload[b];
         }
     }
 }

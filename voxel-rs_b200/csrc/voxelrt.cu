@@ -60,9 +60,10 @@ struct VxCtx {
     uint32_t* d_frame8 = nullptr;
     bool frame32_stale = false;       // the last frame was rendered as RGBA8 only (vx_render_read_rgba8 / option 8)
     uint32_t frame_w = 0, frame_h = 0;
+    uint32_t last_shard_rank = 0, last_shard_size = 1;   // shard of the last render (vx_read_hit_records)
     float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_open_peer_frame)
     uint32_t* frame8_target = nullptr;    // RGBA8 output mode (vx_set_option 8): d_frame8, or a peer GPU's RGBA8 frame (vx_open_peer_frame)
-    unsigned int* d_flags = nullptr;      // 64 frame flags of this ctx (the root's are mapped by its peers); [63] = wait timeouts
+    unsigned int* d_flags = nullptr;      // 64 frame flags of this ctx (the root's are mapped by its peers); [63] = wait timeouts, [62] = dirty ranges the scatter kernel refused
     unsigned int* flags_target = nullptr; // the flags this ctx signals / gates on: d_flags, or the root's (vx_open_peer_sync)
     bool gate_armed = false;              // next vx_render: wait for flags_target[gate_slot] >= gate_value between trace and shade
     unsigned int gate_slot = 0, gate_value = 0;
@@ -413,9 +414,8 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
     }
     CU(c, cudaSetDevice(c->cfg.device));
     std::memcpy(c->h_mirror, &octree_scale, 4);                                  // svo.rs:173-175
-    bool word_aligned = true;   // the scatter kernel moves 32-bit words (every range the serializers produce is word-aligned for ESVO)
-    for (uint32_t i = 0; i < n_dirty; ++i) word_aligned = word_aligned && (dirty[i].offset % 4 == 0) && (dirty[i].length % 4 == 0);
-    const bool staged = word_aligned && total + c->head + (uint64_t)n_dirty * sizeof(VxRange) <= c->stage_cap;
+    // (the scatter kernel is byte-granular: CSVO ranges, which are not word-aligned, take the staged path too)
+    const bool staged = total + c->head + (uint64_t)n_dirty * sizeof(VxRange) <= c->stage_cap;
     // the staging block is reused: the previous upload must have drained it (normally long done)
     if (n_dirty && staged) CU(c, cudaStreamSynchronize(c->s_upload));
     // do not tear a frame / ray batch in flight (render_fence.wait(), svo.rs:178) — on the GPU timeline, not the CPU's
@@ -440,7 +440,8 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
             CU(c, cudaMemcpyAsync(c->d_stage, c->h_stage, off, cudaMemcpyHostToDevice, c->s_upload));
             const unsigned long long pb = c->head + total;
             const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
-            scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, c->d_stage, n_dirty, pb, (uint32_t)(c->head / 4));
+            scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, c->d_stage, n_dirty, pb, (uint32_t)c->head,
+                                                                                     c->cfg.svo_capacity_bytes, c->d_flags + 62);
             c->launches++;
             CU(c, cudaGetLastError());
         } else {
@@ -481,9 +482,17 @@ int vx_svo_commit_packed_device(VxCtx* c, const void* packed_dev, uint32_t n_dir
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
-    const unsigned long long pb = payload_bytes;   // 24 head bytes + range bytes
-    const int blocks = (int)((pb + 255) / 256 < 4096 ? (pb + 255) / 256 : 4096);
-    scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, (const uint8_t*)packed_dev, n_dirty, pb, (uint32_t)(c->head / 4));
+    const unsigned long long pb = payload_bytes;   // head bytes + range bytes
+    // what can be checked without the headers (they are in device memory; the kernel checks every range against the capacity and
+    // counts the ones it had to skip: vx_svo_scatter_errors)
+    if (pb < c->head || pb - c->head > c->cfg.svo_capacity_bytes - c->head)
+        return fail(c, VX_E_CAPACITY, "vx_svo_commit_packed_device: payload of %llu bytes does not fit a %llu-byte buffer", pb,
+                    (unsigned long long)c->cfg.svo_capacity_bytes);
+    if ((uint64_t)n_dirty > pb) return fail(c, VX_E_ARG, "vx_svo_commit_packed_device: %u ranges in a %llu-byte payload", n_dirty, pb);
+    if (reinterpret_cast<uintptr_t>(packed_dev) & 7u) return fail(c, VX_E_ARG, "vx_svo_commit_packed_device: packed_dev must be 8-byte aligned (VxRange headers)");
+    const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
+    scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, (const uint8_t*)packed_dev, n_dirty, pb, (uint32_t)c->head,
+                                                                             c->cfg.svo_capacity_bytes, c->d_flags + 62);
     c->launches++;
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
@@ -619,6 +628,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
         CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
         CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
     }
+    c->gate_armed = false;   // a gate belongs to ONE frame: a rank that owns no macro block of it must not carry it into the next
     if (timed) CU(c, cudaEventRecord(c->t_wave[3], c->s_render));
     return VX_OK;
 }
@@ -652,6 +662,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.hit0 = c->d_hit0; a.hit1 = c->d_hit1; a.sh0 = c->d_sh0; a.sh1 = c->d_sh1; a.sh_pix = c->d_sh_pix;
     a.counters = c->d_counters;
     a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
+    c->last_shard_rank = a.shard_rank; c->last_shard_size = a.shard_size;
     a.refill_threshold = (uint32_t)c->opt_refill;
     a.shadow_refill = (uint32_t)(c->opt_refill_shadow ? c->opt_refill_shadow : c->opt_refill);
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
@@ -771,6 +782,35 @@ int vx_frame_device_ptr(VxCtx* c, void** out_ptr, uint32_t* width, uint32_t* hei
     *out_ptr = c->d_frame;
     if (width) *width = c->frame_w;
     if (height) *height = c->frame_h;
+    return VX_OK;
+}
+
+int vx_read_hit_records(VxCtx* c, VxHitRecord* out) {
+    if (!c || !out || !c->frame_w || !c->d_hit0) return fail(c, VX_E_ARG, "vx_read_hit_records: nothing rendered / null");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const uint32_t w = c->frame_w, h = c->frame_h, macro_x = (w + 31) / 32, macro_y = (h + 15) / 16;
+    const size_t slots = (size_t)macro_x * macro_y * 512;
+    std::vector<float4> h0(slots), h1(slots);
+    CU(c, cudaMemcpyAsync(h0.data(), c->d_hit0, slots * sizeof(float4), cudaMemcpyDeviceToHost, c->s_render));
+    CU(c, cudaMemcpyAsync(h1.data(), c->d_hit1, slots * sizeof(float4), cudaMemcpyDeviceToHost, c->s_render));
+    CU(c, cudaStreamSynchronize(c->s_render));
+    const uint32_t size = c->last_shard_size ? c->last_shard_size : 1, rank = c->last_shard_rank;
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const uint32_t macro = (y / 16) * macro_x + x / 32;
+            const size_t slot = ((size_t)macro * 4 + (y % 16) / 4) * 128 + ((x % 32) / 8) * 32 + (y % 4) * 8 + (x % 8);   // kernels.cuh strip_pixel
+            VxHitRecord& o = out[(size_t)y * w + x];
+            std::memset(&o, 0, sizeof(o));
+            if (macro % size != rank) { o.t = -2.0f; continue; }
+            uint32_t flags;
+            std::memcpy(&flags, &h1[slot].w, 4);
+            if (!(flags & 8u)) { o.t = -1.0f; continue; }
+            o.t = h0[slot].x;
+            std::memcpy(&o.value, &h0[slot].y, 4);
+            o.face_id = (int32_t)(flags & 7u);
+            o.pos[0] = h1[slot].x; o.pos[1] = h1[slot].y; o.pos[2] = h1[slot].z;
+            o.uv[0] = h0[slot].z; o.uv[1] = h0[slot].w;
+        }
     return VX_OK;
 }
 
@@ -1109,7 +1149,7 @@ int vx_close_peer_sync(VxCtx* c) {
 }
 
 int vx_frame_signal(VxCtx* c, uint32_t slot, uint32_t value) {
-    if (!c || slot >= 63) return fail(c, VX_E_ARG, "vx_frame_signal: bad slot");
+    if (!c || slot >= 62) return fail(c, VX_E_ARG, "vx_frame_signal: bad slot");
     CU(c, cudaSetDevice(c->cfg.device));
     unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
     flag_signal_kernel<<<1, 1, 0, c->s_render>>>(f + slot, value);
@@ -1119,7 +1159,7 @@ int vx_frame_signal(VxCtx* c, uint32_t slot, uint32_t value) {
 }
 
 int vx_frame_wait(VxCtx* c, uint32_t first_slot, uint32_t n_slots, uint32_t value) {
-    if (!c || n_slots == 0 || n_slots > 32 || first_slot + n_slots > 63) return fail(c, VX_E_ARG, "vx_frame_wait: bad slot range");
+    if (!c || n_slots == 0 || n_slots > 32 || first_slot + n_slots > 62) return fail(c, VX_E_ARG, "vx_frame_wait: bad slot range");
     CU(c, cudaSetDevice(c->cfg.device));
     unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
     flag_wait_kernel<<<1, 32, 0, c->s_render>>>(f, first_slot, n_slots, value, c->d_flags + 63);
@@ -1129,7 +1169,7 @@ int vx_frame_wait(VxCtx* c, uint32_t first_slot, uint32_t n_slots, uint32_t valu
 }
 
 int vx_frame_gate(VxCtx* c, uint32_t slot, uint32_t value) {
-    if (!c || slot >= 63) return fail(c, VX_E_ARG, "vx_frame_gate: bad slot");
+    if (!c || slot >= 62) return fail(c, VX_E_ARG, "vx_frame_gate: bad slot");
     c->gate_armed = true; c->gate_slot = slot; c->gate_value = value;
     return VX_OK;
 }
@@ -1139,6 +1179,23 @@ int vx_frame_sync_errors(VxCtx* c, uint32_t* out) {
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->s_render));
     CU(c, cudaMemcpy(out, c->d_flags + 63, 4, cudaMemcpyDeviceToHost));
+    return VX_OK;
+}
+
+int vx_svo_scatter_errors(VxCtx* c, uint32_t* out) {
+    if (!c || !out) return VX_E_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_upload));
+    CU(c, cudaMemcpy(out, c->d_flags + 62, 4, cudaMemcpyDeviceToHost));
+    return VX_OK;
+}
+
+int vx_frame_flags_reset(VxCtx* c) {
+    if (!c) return VX_E_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_render));
+    CU(c, cudaMemset(c->d_flags, 0, 64 * sizeof(unsigned int)));
+    c->gate_armed = false;
     return VX_OK;
 }
 

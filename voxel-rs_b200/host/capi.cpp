@@ -533,6 +533,7 @@ uint64_t vxh_registry_textures(void* r, uint8_t* out, uint64_t cap, uint32_t dim
 
 void vxh_look_to_rh_inverted(const float eye[3], const float dir[3], const float up[3], float out[16]) { look_to_rh_inverted(eye, dir, up, out); }
 
+#ifndef VXH_WORLD_ONLY   // libvoxelrs_world.so = everything above: the producers of the path's inputs, no dependency on libvoxelrt
 void* vxh_svo_new(void* registry, uint64_t size_mb, uint32_t max_w, uint32_t max_h, uint64_t max_rays, int device, uint32_t flags) {
     VXH_TRY
     return new Svo(*(VoxelRegistry*)registry, size_mb, max_w, max_h, max_rays, device, flags);
@@ -617,5 +618,7 @@ int vxh_worldsvo_raycast(void* s, void* world, const float* rays, uint32_t n_ray
     return 0;
     VXH_CATCH(-1)
 }
+
+#endif  // VXH_WORLD_ONLY
 
 }  // extern "C"

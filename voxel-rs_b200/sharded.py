@@ -17,7 +17,8 @@ itself. `engine` is the object that does the device work — voxelrs_b200.Svo on
 the same methods so the collectives, the packed-range format and the shard layout run under gloo with world_size 2.
 
 Layouts (shared with the CUDA kernels in csrc/kernels.cuh and restated in numpy below for tests):
-  packed dirty set   n VxRange{u64 offset, u64 length} headers | first 24 bytes of the world buffer | range 0 bytes | range 1 bytes ...
+  packed dirty set   n VxRange{u64 offset, u64 length} headers | head bytes of the world buffer (24 ESVO / 8 CSVO) | range 0 bytes | range 1 bytes ...
+                     (byte-packed: CSVO ranges sit at arbitrary byte offsets)
   packed shard       for each owned macro block, in increasing macro index: 16 rows x 32 pixels RGBA32F (zero outside the frame)
 """
 import numpy as np
@@ -62,24 +63,30 @@ class TileShards:
             frame[y0:y0 + h, x0:x0 + w] = packed[k, :h, :w]
 
 
-def pack_dirty_host(world_buffer, ranges):
-    """numpy restatement of vx_svo_pack_dirty. world_buffer: uint8 GPU-buffer image (byte 0 = octree_scale)."""
+def pack_dirty_host(world_buffer, ranges, head=24):
+    """numpy restatement of vx_svo_pack_dirty. world_buffer: uint8 GPU-buffer image (byte 0 = octree_scale); head = bytes in front
+    of the RangeBuffer image: 24 for ESVO (scale + preamble), 8 for CSVO (scale + root pointer) — World.header_bytes."""
     hdr = np.array([[o, l] for o, l in ranges], dtype=np.uint64).reshape(-1, 2)
-    parts = [hdr.view(np.uint8).reshape(-1), world_buffer[:24]] + [world_buffer[24 + o:24 + o + l] for o, l in ranges]
+    parts = [hdr.view(np.uint8).reshape(-1), world_buffer[:head]] + [world_buffer[head + o:head + o + l] for o, l in ranges]
     return np.concatenate(parts)
 
 
-def apply_packed_host(world_buffer, packed, n_ranges):
-    """numpy restatement of scatter_ranges_kernel: applies a packed dirty set to a replica's buffer in place."""
+def apply_packed_host(world_buffer, packed, n_ranges, head=24):
+    """numpy restatement of scatter_ranges_kernel: applies a packed dirty set to a replica's buffer in place. Byte-granular (CSVO
+    ranges are not word-aligned); a range that would leave the buffer is skipped. Returns (bytes consumed, ranges skipped)."""
     packed = np.asarray(packed, dtype=np.uint8)
     hdr = packed[:16 * n_ranges].view(np.uint64).reshape(-1, 2)
-    world_buffer[:24] = packed[16 * n_ranges:16 * n_ranges + 24]
-    off = 16 * n_ranges + 24
+    world_buffer[:head] = packed[16 * n_ranges:16 * n_ranges + head]
+    off = 16 * n_ranges + head
+    skipped = 0
     for o, l in hdr:
         o, l = int(o), int(l)
-        world_buffer[24 + o:24 + o + l] = packed[off:off + l]
+        if head + o + l > len(world_buffer):
+            skipped += 1
+        else:
+            world_buffer[head + o:head + o + l] = packed[off:off + l]
         off += l
-    return off
+    return off, skipped
 
 
 class ShardedFrame:
@@ -117,10 +124,19 @@ class ShardedFrame:
         self.packed_dirty = self.dirty_bufs[0]
         if self._cuda:
             self.side = t.cuda.Stream(device=self.device)
+            # the library's own streams, as torch streams: the scatter kernel runs on ITS upload stream and the shard pack / unpack
+            # kernels on ITS render stream, whatever torch's current stream is — the events below are recorded / waited on exactly those
+            self.up = t.cuda.ExternalStream(self.engine.stream(1), device=self.device)
+            self.rs = t.cuda.ExternalStream(self.engine.stream(0), device=self.device)
             self.ev_staged = [t.cuda.Event() for _ in range(2)]     # broadcast into buffer k finished
             self.ev_applied = [t.cuda.Event() for _ in range(2)]    # scatter out of buffer k finished
+            self.ev_gather = t.cuda.Event()
             for e in self.ev_applied:
-                e.record(t.cuda.current_stream(self.device))
+                e.record(self.up)
+        # a new sequence of frames counts from 1 again: the flags of an earlier ShardedFrame on the same engine must not satisfy it
+        if self.rank == 0 and hasattr(self.engine, "frame_flags_reset"):
+            self.engine.frame_flags_reset()
+        self.dist.barrier()
         if self.gather in ("p2p", "p2p8"):
             eight = self.gather == "p2p8"
             if eight:
@@ -137,7 +153,17 @@ class ShardedFrame:
             self.recv = [t.empty(self.tiles.shard_bytes(r), dtype=t.uint8, device=self.device) for r in range(self.world_size)] \
                 if self.rank == 0 else None
 
+    def check(self):
+        """Raises if a frame-flag wait timed out (lost / slow peer: frames since then may be torn) or the scatter kernel refused a
+        dirty range. Synchronises this rank's streams: call it at the end of a sequence of frames, not every frame."""
+        if self.world_size == 1 or not self._cuda:
+            return
+        lost, refused = self.engine.frame_sync_errors(), self.engine.scatter_errors()
+        if lost or refused:
+            raise RuntimeError(f"ShardedFrame rank {self.rank}: {lost} frame-flag waits timed out, {refused} dirty ranges refused")
+
     def close(self):
+        self.check()
         if self._peer_open:
             self.engine.close_peer_frame()
             self.engine.close_peer_sync()
@@ -175,11 +201,10 @@ class ShardedFrame:
             return
         k, n_ranges, payload_bytes, used_bytes, depth = self._staged.pop(0)
         if self._cuda:
-            cur = self.torch.cuda.current_stream(self.device)
-            cur.wait_event(self.ev_staged[k])
+            self.up.wait_event(self.ev_staged[k])           # the scatter runs on the library's upload stream
         self.engine.commit_packed_device(self.dirty_bufs[k].data_ptr(), n_ranges, payload_bytes, used_bytes, depth)
         if self._cuda:
-            self.ev_applied[k].record(cur)
+            self.ev_applied[k].record(self.up)
 
     def broadcast_dirty(self, n_ranges, payload_bytes, used_bytes, depth, packed_host=None):
         """Collective. prefetch_dirty + apply_dirty back to back (no overlap with the previous frame)."""
@@ -204,13 +229,21 @@ class ShardedFrame:
             else:
                 self.engine.frame_wait(1, self.world_size - 1, self.frame_no)
             return
-        self.engine.pack_shard(self.shard, self.my_pack.data_ptr())
+        self.engine.pack_shard(self.shard, self.my_pack.data_ptr())      # on the library's render stream
+        cur = None
+        if self._cuda:
+            cur = self.torch.cuda.current_stream(self.device)
+            self.ev_gather.record(self.rs)
+            cur.wait_event(self.ev_gather)                               # NCCL (torch's current stream) after the pack
         if self.rank == 0:
             ops = [self.dist.P2POp(self.dist.irecv, self.recv[r], r) for r in range(1, self.world_size)]
         else:
             ops = [self.dist.P2POp(self.dist.isend, self.my_pack, 0)]
         for w in self.dist.batch_isend_irecv(ops):
             w.wait()
+        if self._cuda:
+            self.ev_gather.record(cur)
+            self.rs.wait_event(self.ev_gather)                           # unpack / the next frame's pack after the transfer
         if self.rank == 0:
             for r in range(1, self.world_size):
                 self.engine.unpack_shard((r, self.world_size), self.recv[r].data_ptr())

@@ -44,7 +44,7 @@ def main():
             cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", str(args.warmup), "--skip-cpu",
                    "--skip-e2e"] + args.bench_flags
             t0 = time.time()
-            r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+            r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, VOXELRT_AB_VARIANT=name))
             line = None
             for l in r.stdout.splitlines():
                 if l.startswith("{"):

@@ -191,9 +191,13 @@ def lib():
     L.vx_frame_wait.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32]; L.vx_frame_wait.restype = C.c_int
     L.vx_frame_gate.argtypes = [P, C.c_uint32, C.c_uint32]; L.vx_frame_gate.restype = C.c_int
     L.vx_frame_sync_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_frame_sync_errors.restype = C.c_int
-    L.vx_svo_scatter_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_svo_scatter_errors.restype = C.c_int
-    L.vx_frame_flags_reset.argtypes = [P]; L.vx_frame_flags_reset.restype = C.c_int
-    L.vx_read_hit_records.argtypes = [P, P]; L.vx_read_hit_records.restype = C.c_int
+    try:
+        L.vx_svo_scatter_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_svo_scatter_errors.restype = C.c_int
+        L.vx_frame_flags_reset.argtypes = [P]; L.vx_frame_flags_reset.restype = C.c_int
+        L.vx_read_hit_records.argtypes = [P, P]; L.vx_read_hit_records.restype = C.c_int
+    except AttributeError:
+        if not os.environ.get("VOXELRT_AB_VARIANT"):   # only tools/ab_kernels.py may load an older build of the library
+            raise
     _lib = L
     return L
 

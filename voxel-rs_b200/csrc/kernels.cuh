@@ -127,20 +127,15 @@ __device__ __forceinline__ bool render_leaf(Walk& w, const Scene& s, const Smem&
 // The walk loop of a warp: every lane with a live ray steps it; the warp leaves the loop when fewer than `thresh` lanes are
 // still walking. thresh == 1 (run every ray of the warp to its end, then refill all 32 lanes at once) needs no population
 // count and gets its own copy of the loop.
-#ifdef VX_STEP_PLAIN   // A/B build: the shader-ordered step in the hot loop (tools/ab_kernels.py)
-#define VX_HOT_STEP walk_step_plain
-#else
-#define VX_HOT_STEP walk_step
-#endif
 template <int FMT, bool LIMITED, bool COUNT>
 __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, Counters& cnt, int thresh) {
     if (thresh <= 1) {
         do {
-            if (w.state > 0) VX_HOT_STEP<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
         } while (__any_sync(0xffffffffu, w.state > 0));
     } else {
         do {
-            if (w.state > 0) VX_HOT_STEP<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
         } while (__popc(__ballot_sync(0xffffffffu, w.state > 0)) >= thresh);
     }
 }
@@ -219,7 +214,6 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
                     walk_init<FMT>(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
-                    walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
@@ -248,7 +242,6 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 w.state = ST_IDLE;
             } else {
                 walk_skip_leaf<FMT>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
-                walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
             }
         } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -389,7 +382,6 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 const float4 s0 = __ldcs(a.sh0 + entry);
                 float rox, roy, roz, rdx, rdy, rdz;
                 walk_init<FMT>(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
-                walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 lit = s0.w;
@@ -417,7 +409,6 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                     shadow = 0.0f;
                 } else {
                     walk_skip_leaf<FMT>(w, a.scene, sm.stack);
-                    walk_degenerate<FMT, false, COUNT>(w, a.scene, sm.stack, cnt);
                     done = false;
                 }
             }
@@ -459,7 +450,6 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
     uint32_t next = 128, run_len = 128;
     bool more_work = true;
     unsigned long long my_task = 0;
-    uint32_t last_leaf = 0xffffffffu;
     Walk w;
     w.state = ST_IDLE;
 
@@ -480,7 +470,6 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
                 float rox, roy, roz, rdx, rdy, rdz;
                 walk_init<FMT>(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
-                walk_degenerate<FMT, true, COUNT>(w, a.scene, sm.stack, cnt);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 if (COUNT) cnt.primary_rays++;
@@ -577,7 +566,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
         const float tcx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcy = __fmaf_rn(w.py, w.tcy, -w.tby), tcz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
         const float tc_max = tmin2(tmin2(tcx, tcy), tcz);
         if (w.state <= 0) break;                      // MAX_STEPS used up (:152)
-        walk_step_plain<FMT, true, false>(w, s, sm.stack, cnt);
+        walk_step<FMT, true, false>(w, s, sm.stack, cnt);
         if (state_at_leaf(w.state)) {
             g.value = leaf_value<FMT>(w, s);
             leaf_geom(w, rox, roy, roz, rdx, rdy, rdz, inv_scale, g);

@@ -189,13 +189,12 @@ struct Walk {
     uint32_t ci;              // slot of the current cell in its parent, UN-mirrored: the shader's `idx ^ octant_mask` (:164), 0..7.
                               // Kept instead of idx: the node decode of every iteration uses it as it is, and idx is one xor away.
     uint32_t flags;           // bits 0-2: octant_mask; bit 8: inside_voxel; bit 9: the previous leaf candidate was rejected
-                              // (adjacent_leaf_count > 0, its value is in the caller's last_leaf); bit 10: degenerate ray (walk_init)
+                              // (adjacent_leaf_count > 0, its value is in the caller's last_leaf)
     uint32_t soff;            // byte offset of the traversal-stack slot of the current level, = min(22 - scale, levels - 1) * VX_STACK_STRIDE
     int state;                // see ST_*: > 0 walking (iterations left of MAX_STEPS), 0 budget used up, < 0 stopped
 };
 #define VX_FLAG_INSIDE 0x100u
 #define VX_FLAG_ADJACENT 0x200u
-#define VX_FLAG_DEGENERATE 0x400u
 #define VX_STACK_STRIDE (3u * VX_THREADS * 4u)   // bytes between two levels of one thread's stack column
 __device__ __forceinline__ int walk_scale(const Walk& w) { return (int)((__float_as_uint(w.se) >> 23) & 0xffu) - 104; }   // se = 2^(scale-23)
 
@@ -301,11 +300,7 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
     if (w.t_min < 1.5f * w.tcy - w.tby) { idx ^= 2; w.py = 1.5f; }
     if (w.t_min < 1.5f * w.tcz - w.tbz) { idx ^= 4; w.pz = 1.5f; }
     w.ci = idx ^ octant_mask;
-    // A ray whose coefficients hold a NaN (NaN / infinite inputs) is walked by the plain step only (walk_plain_loop): the merged
-    // step of the hot loop states the ADVANCE comparison `tc_max >= t_corner` as `!(tc_max < t_corner)`, which is the same thing for
-    // every ordered pair. (A sum is NaN if a term is; inf - inf false positives just take the slow path too.)
-    const float nan_probe = ((w.tcx + w.tcy) + w.tcz) + ((w.tbx + w.tby) + w.tbz) + w.t_min;
-    w.flags = octant_mask | ((nan_probe == nan_probe && fabsf(nan_probe) != __int_as_float(0x7f800000)) ? 0u : VX_FLAG_DEGENERATE);
+    w.flags = octant_mask;
 
     w.soff = 0;          // scale = MAX_SCALE - 1
     w.se = 0.5f;
@@ -446,10 +441,18 @@ __device__ __forceinline__ void walk_descend(Walk& w, const Scene& s) {
     }
 }
 
-// One iteration of the loop at svo.esvo.glsl:152-392 exactly as the shader orders it, minus the evaluation of a leaf candidate
-// (see walk_step). Used outside the hot loop: degenerate rays (walk_plain_loop) and the debug cast.
+// One iteration of the loop at svo.esvo.glsl:152-392, minus the evaluation of a leaf candidate. Call only with
+// w.state > 0. On return w.state is: the remaining budget (keep stepping while > 0), <= ST_LEAF (the current child is a leaf
+// with t_min > 0, :185 — the caller evaluates it and either finishes the ray or calls walk_skip_leaf(), the ADVANCE/POP tail of
+// THIS iteration, and goes on stepping), or ST_MISS.
+// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
+// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
+// (Measured and dropped, profiles/r02_step_variants.md: stating what PUSH and ADVANCE have in common — three comparisons against
+// plane times, three conditional moves of pos, three index bits — once on per-lane selected operands so that it runs for both
+// kinds of lanes together. Bit-exact, but 12 % slower: the 32 rays of a warp tile are mostly in the SAME phase, so the extra
+// selects were paid far more often than a serialized block was saved.)
 template <int FMT, bool LIMITED, bool COUNT>
-__device__ __forceinline__ void walk_step_plain(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
+__device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
     --w.state;                                                                // :152
     if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
     if (COUNT) cnt.steps++;
@@ -488,68 +491,6 @@ __device__ __forceinline__ void walk_step_plain(Walk& w, const Scene& s, uint32_
     if (!walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
 }
 
-// The same iteration for the hot loop of the persistent kernels. Call only with w.state > 0 and a non-degenerate ray. On return
-// w.state is: the remaining budget (keep stepping while > 0), <= ST_LEAF (the current child is a leaf with t_min > 0, :185 — the
-// caller evaluates it and either finishes the ray or calls walk_skip_leaf(), the ADVANCE/POP tail of THIS iteration, and goes on
-// stepping), or ST_MISS.
-// A warp's lanes sit in different phases (about half PUSH, half ADVANCE, a third of those POP) and SIMT runs the phases present in
-// a warp one after the other. So what PUSH (child selection, :301-304) and ADVANCE (:324-327) have in common — three comparisons
-// against per-axis plane times, a conditional move of pos along each axis, three bits collected — is stated ONCE, on operands
-// selected per lane, and runs for all lanes together; only the PUSH tail (stack write, the two node loads) and the POP diverge:
-//     PUSH     bit_k = t_min <  fma(half, t_coef_k, t_corner_k)     pos_k += half     idx  = bits
-//     ADVANCE  bit_k = tc_max >= t_corner_k = fma(0, t_coef_k, t_corner_k)   pos_k += -se    idx ^= bits
-// fma(0, c, x) is x exactly for finite c; `a >= b` is `!(a < b)` for ordered operands (degenerate rays never get here);
-// x - se and x + (-se) are the same IEEE operation. Every value the shader computes is computed by the same operation on the
-// same operands, so the walk stays bit-exact (golden step traces, tests/test_gpu_parity.py).
-// The record index `rec` is clamped once per PUSH to max_rec = capacity - 12 words, so every later access into that
-// record (masks, child pointers, leaf values) is in bounds whatever the buffer holds.
-template <int FMT, bool LIMITED, bool COUNT>
-__device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
-    --w.state;                                                                // :152
-    if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
-    if (COUNT) cnt.steps++;
-    const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
-    const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
-    bool is_child, is_leaf;
-    walk_decode<FMT>(w, is_child, is_leaf);
-    const bool in = is_child && w.t_min <= w.t_max;                           // :178
-    if (in) {
-        if (is_leaf) {
-            if (w.t_min > 0.0f) { w.state = ST_LEAF - w.state; return; }      // :185
-            if (w.t_min == 0.0f) w.flags |= VX_FLAG_INSIDE;                   // :180 inside_voxel
-        }
-    } else {
-        w.flags &= ~VX_FLAG_ADJACENT;                                         // :315-316 (adjacent_leaf_count = 0)
-    }
-    const float tv_max = tmin2(w.t_max, tc_max);                              // :278
-    const bool push = in && w.t_min <= tv_max;                                // :280
-    const float half = w.se * 0.5f;                                           // :274
-    const float hs = push ? half : 0.0f;
-    const float a = push ? w.t_min : tc_max;
-    const float delta = push ? half : -w.se;
-    const float cx = __fmaf_rn(hs, w.tcx, tcornx), cy = __fmaf_rn(hs, w.tcy, tcorny), cz = __fmaf_rn(hs, w.tcz, tcornz);   // :275 / t_corner
-    uint32_t bits = 0;                                                        // :301-304 / :324-327
-    if ((a < cx) == push) { bits ^= 1; w.px += delta; }
-    if ((a < cy) == push) { bits ^= 2; w.py += delta; }
-    if ((a < cz) == push) { bits ^= 4; w.pz += delta; }
-    if (push) {                                                               // :280-310
-        if (COUNT) cnt.pushes++;
-        if (tc_max < w.h)                                                     // :284-288
-            stack_store(stk + w.soff, w.rec, FMT == VX_FMT_CSVO ? csvo_pack_node(w.desc, w.hdr) : w.desc, w.t_max);
-        w.h = tc_max;                                                         // :289
-        walk_descend<FMT>(w, s);                                              // child slot: still the parent's w.ci
-        w.soff = min(w.soff + VX_STACK_STRIDE, s.stack_max_off);              // --scale (:295)
-        w.se = half;                                                          // :297
-        w.ci = bits ^ (w.flags & 7u);
-        w.t_max = tv_max;                                                     // :307
-    } else {                                                                  // :324-391
-        w.t_min = tc_max;                                                     // :330
-        w.ci ^= bits;                                                         // :331
-        if (((w.ci ^ w.flags) & bits) != 0)                                   // :335
-            if (!walk_pop<FMT>(w, stk, s.stack_max_off, bits)) w.state = ST_MISS;
-    }
-}
-
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
 // The rejected leaf used up no extra iteration: the budget stored in the leaf state is restored.
 template <int FMT>
@@ -558,25 +499,6 @@ __device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
     w.state = walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
-}
-
-// Degenerate rays (VX_FLAG_DEGENERATE: a NaN among the ray coefficients) are walked here, outside the hot loop, by the plain step
-// until they stop (leaf candidate / miss / budget). Call after walk_init and after walk_skip_leaf; a no-op for every other ray.
-// Out of line and on a copy, so that the caller's Walk stays in registers.
-template <int FMT, bool LIMITED, bool COUNT>
-__device__ __noinline__ void walk_plain_loop(Walk* w, const Scene* s, uint32_t stk, Counters* cnt) {
-    while (w->state > 0) walk_step_plain<FMT, LIMITED, COUNT>(*w, *s, stk, *cnt);
-}
-template <int FMT, bool LIMITED, bool COUNT>
-__device__ __forceinline__ void walk_degenerate(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
-    if ((w.flags & VX_FLAG_DEGENERATE) && w.state > 0) {
-        Walk tmp = w;
-        Scene sc = s;
-        Counters c = cnt;
-        walk_plain_loop<FMT, LIMITED, COUNT>(&tmp, &sc, stk, &c);
-        w = tmp;
-        cnt = c;
-    }
 }
 
 template <int FMT>

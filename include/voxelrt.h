@@ -115,11 +115,15 @@ typedef struct VxRenderParams {
     float    shadow_distance;
 } VxRenderParams;
 
-/* Image-space shard for multi-GPU rendering: this ctx renders only tiles whose Morton-ordered
- * tile index t satisfies t % world_size == rank. {0,1} renders the whole frame. */
+/* Image-space shard for multi-GPU rendering. The frame is cut into macro blocks of 32x16 pixels, row-major; this ctx renders
+ * only the macro blocks m with m % world_size == rank (interleaved blocks: the finest mix of cheap and expensive image regions,
+ * for frames that stay in GPU memory), or — with VX_SHARD_ROWS or'ed into world_size — the macro ROWS r with r % world_size ==
+ * rank (whole 16-pixel-high stripes: a shard's pixels are contiguous runs of the frame, so vx_render_read_rgba8 can DMA them
+ * into a host frame shared by all shards, each GPU over its own PCIe link). {0,1} renders the whole frame. */
+#define VX_SHARD_ROWS 0x80000000u
 typedef struct VxShard {
     uint32_t rank;
-    uint32_t world_size;
+    uint32_t world_size;   /* | VX_SHARD_ROWS */
 } VxShard;
 
 /* Per-frame counters of the last vx_render / vx_raycast (device-accumulated). */
@@ -386,6 +390,48 @@ uint64_t vx_launch_count(const VxCtx* ctx);
 
 /* Library build id string (compile flags, arch). */
 const char* vx_build_info(void);
+
+/* ---- single process, several GPUs ----------------------------------------------------------------------------------------
+ * The reference engine is one process (src/gamelogic/game.rs:102-160) with one graphics::Svo (src/graphics/svo.rs:109-255). A
+ * VxGroup is that Svo spread over the GPUs of one box: one VxCtx per device, the SVO replicated on every device, a frame cut
+ * into image-space shards. The calls mirror the single-GPU ones one to one; a group of one device forwards to them.
+ *   vx_group_create            contexts on `devices`, peer access to devices[0]'s memory, NCCL communicators (ncclCommInitAll;
+ *                              NCCL is opened with dlopen("libnccl.so.2"), a missing / failing NCCL is VX_E_NCCL)
+ *   vx_group_svo_host_mirror   the pinned mirror Esvo::write_changes_to writes into (devices[0]'s)
+ *   vx_group_svo_commit        = vx_svo_commit for every replica: ONE packed H2D copy to devices[0], ncclBroadcast over NVLink to
+ *                              the others' staging buffers, a scatter kernel on each; ordered behind frames / ray batches in
+ *                              flight on every device by events, the CPU does not wait
+ *   vx_group_render            frame for GPU consumers: interleaved macro blocks, every device's shade / shadow kernels store their
+ *                              finished pixels into devices[0]'s RGBA32F framebuffer over NVLink peer memory; afterwards that
+ *                              context's render stream (vx_group_read_frame_*, vx_frame_device_ptr(vx_group_ctx(g, 0))) sees the
+ *                              whole frame. VX_E_STATE if a device cannot map devices[0]'s memory.
+ *   vx_group_render_read_rgba8 frame for the host (Framebuffer::read_pixels): whole 16-pixel stripes per device (VX_SHARD_ROWS),
+ *                              each device DMAs its stripes into rgba8_out itself — one PCIe link per GPU instead of a gather
+ *                              through one. rgba8_out should be pinned AND portable (vx_group_host_frame hands one out).
+ *                              Returns when the whole frame is in rgba8_out.
+ *   vx_group_raycast           contiguous slices of the task array, one per device; synchronous like vx_raycast
+ * Threading: like a VxCtx, calls on one group are serialised by the caller; internally one worker thread per device issues
+ * that device's launches. */
+typedef struct VxGroup VxGroup;
+int vx_group_create(const VxConfig* cfg /* .device ignored */, const int* devices, uint32_t n_devices, VxGroup** out);
+void vx_group_destroy(VxGroup* group);
+const char* vx_group_last_error(const VxGroup* group /* NULL: last vx_group_create failure of this thread */);
+uint32_t vx_group_size(const VxGroup* group);
+VxCtx* vx_group_ctx(VxGroup* group, uint32_t index);   /* the context of devices[index] (statistics, options, zero-copy frame access) */
+int vx_group_set_materials(VxGroup* group, const VxMaterial* materials, uint32_t count);
+int vx_group_set_textures(VxGroup* group, const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t layers, uint32_t mip_levels);
+int vx_group_set_option(VxGroup* group, uint32_t option, uint64_t value);
+uint8_t* vx_group_svo_host_mirror(VxGroup* group);
+int vx_group_svo_set_hot_range(VxGroup* group, uint64_t offset, uint64_t length);
+int vx_group_svo_commit(VxGroup* group, float octree_scale, const VxRange* dirty, uint32_t n_dirty, uint64_t used_bytes, uint32_t depth);
+int vx_group_stats(const VxGroup* group, VxStats* out);
+int vx_group_render(VxGroup* group, const VxRenderParams* params, uint32_t width, uint32_t height);
+int vx_group_wait(VxGroup* group);
+int vx_group_read_frame_rgba8(VxGroup* group, uint8_t* rgba8_out);
+int vx_group_read_frame_rgba32f(VxGroup* group, float* rgba32f_out);
+uint8_t* vx_group_host_frame(VxGroup* group, uint64_t bytes);   /* group-owned pinned portable host memory, at least `bytes` */
+int vx_group_render_read_rgba8(VxGroup* group, const VxRenderParams* params, uint32_t width, uint32_t height, uint8_t* rgba8_out, uint32_t bands);
+int vx_group_raycast(VxGroup* group, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results);
 
 #ifdef __cplusplus
 }

@@ -114,7 +114,10 @@ extern "C" {
     pub fn vx_group_set_materials(group: *mut VxGroup, materials: *const MaterialInstance, count: u32) -> c_int;
     pub fn vx_group_set_textures(group: *mut VxGroup, rgba8: *const u8, width: u32, height: u32, layers: u32, mip_levels: u32) -> c_int;
     pub fn vx_group_svo_commit(group: *mut VxGroup, octree_scale: f32, dirty: *const VxRange, n_dirty: u32, used_bytes: u64, depth: u32) -> c_int;
-    pub fn vx_group_render_read_rgba8(group: *mut VxGroup, params: *const VxRenderParams, width: u32, height: u32, rgba8_out: *mut u8) -> c_int;
+    pub fn vx_group_render(group: *mut VxGroup, params: *const VxRenderParams, width: u32, height: u32) -> c_int;
+    pub fn vx_group_render_read_rgba8(group: *mut VxGroup, params: *const VxRenderParams, width: u32, height: u32, rgba8_out: *mut u8, bands: u32) -> c_int;
+    pub fn vx_group_svo_host_mirror(group: *mut VxGroup) -> *mut u8;
+    pub fn vx_group_host_frame(group: *mut VxGroup, bytes: u64) -> *mut u8;
     pub fn vx_group_raycast(group: *mut VxGroup, tasks: *const PickerTask, n: u64, results: *mut PickerResult) -> c_int;
 }
 

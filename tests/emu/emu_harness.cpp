@@ -200,7 +200,7 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     a.frame8 = options[4] ? frame8.data() : nullptr;
     a.hit0 = hit0.data(); a.hit1 = hit1.data(); a.sh0 = sh0.data(); a.sh1 = sh1.data(); a.sh_pix = sh_pix.data();
     a.counters = &counters;
-    a.shard_rank = options[6]; a.shard_size = options[7] ? options[7] : 1;
+    a.shard_rank = options[6]; a.shard_size = options[7] ? (options[7] & 0x7fffffffu) : 1; a.shard_rows = (options[7] >> 31) & 1u;
     a.refill_threshold = options[0] ? options[0] : 1;
     a.shadow_refill = options[1] ? options[1] : a.refill_threshold;
     a.tma_writeback = options[5];
@@ -231,11 +231,8 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
         if (row1 == row0) continue;
         // launch_wavefront(c, a, shadows, band b, row0, row1)
         unsigned int* work = work_all + b * 8;
-        a.macro0 = row0 * a.macro_x; a.n_macros = (row1 - row0) * a.macro_x;
-        a.first_owned = a.macro0 + ((a.shard_rank + a.shard_size - (a.macro0 % a.shard_size)) % a.shard_size);
-        const uint32_t band_end = a.macro0 + a.n_macros;
-        const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + a.shard_size - 1) / a.shard_size : 0;
-        a.n_owned = owned;
+        shard_band(a, row0, row1);
+        const uint32_t owned = a.n_owned;
         a.shadow_count = work + 4;
         a.fetch_tiles = 1;
         if (!owned) continue;

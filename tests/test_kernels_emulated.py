@@ -127,16 +127,19 @@ def test_emulated_shards_tile_the_frame(emu, pkg, ora, terrains):
     w, h = 100, 40
     vxp = world_params(pkg, world, w, h)
     want, _, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
-    union = np.full((h, w, 4), -1.0, np.float32)
-    total = {k: 0 for k in cnt}
-    for rank in range(3):
-        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, rank=rank, size=3)
-        mine = got[..., 3] != -1.0                 # untouched pixels keep the harness's -1 fill (alpha is never negative)
-        assert not (mine & (union[..., 3] != -1.0)).any()
-        union[mine] = got[mine]
-        for k in c:
-            total[k] += c[k]
-    assert union.tobytes() == want.tobytes() and total == cnt
+    for rows in (0, 0x80000000):                   # interleaved macro blocks / VX_SHARD_ROWS: whole 16-pixel stripes
+        union = np.full((h, w, 4), -1.0, np.float32)
+        total = {k: 0 for k in cnt}
+        for rank in range(3):
+            got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, rank=rank, size=3 | rows, bands=2 if rows else 1)
+            mine = got[..., 3] != -1.0             # untouched pixels keep the harness's -1 fill (alpha is never negative)
+            assert not (mine & (union[..., 3] != -1.0)).any()
+            if rows:                               # a shard's pixels are exactly the stripes y // 16 % 3 == rank
+                assert np.array_equal(mine, np.repeat(((np.arange(h) // 16) % 3 == rank)[:, None], w, axis=1))
+            union[mine] = got[mine]
+            for k in c:
+                total[k] += c[k]
+        assert union.tobytes() == want.tobytes() and total == cnt
 
 
 def test_emulated_reference_scene(emu, pkg, ora):
@@ -341,6 +344,7 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         world = worlds[fmt]
         w, h = int(rng.integers(1, 90)), int(rng.integers(1, 60))
         size = int(rng.choice([1, 1, 2, 3, 5]))
+        rows = int(rng.integers(0, 2)) << 31       # VX_SHARD_ROWS
         bands = int(rng.choice([1, 2, 4, 16]))
         refill, ctas = int(rng.integers(1, 33)), int(rng.integers(1, 5))
         shadow_refill = int(rng.choice([0, 1, 7, 32]))
@@ -352,12 +356,12 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         total = {k: 0 for k in cnt}
         for rank in range(size):
             got, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, shadow_refill=shadow_refill, ctas=ctas, rgba8=rgba8, rank=rank,
-                                      size=size, bands=bands)
+                                      size=size | rows, bands=bands)
             mine = (got8.view(np.uint32)[..., 0] != 0xdeadbeef) if rgba8 else (got[..., 3] != -1.0)
             union[mine] = got[mine]
             union8[mine] = got8[mine]
             for k in c:
                 total[k] += c[k]
-        cfg = dict(case=case, fmt=fmt, w=w, h=h, size=size, bands=bands, refill=refill, ctas=ctas, shadows=shadows, rgba8=rgba8)
+        cfg = dict(case=case, fmt=fmt, w=w, h=h, size=size, rows=bool(rows), bands=bands, refill=refill, ctas=ctas, shadows=shadows, rgba8=rgba8)
         assert (union8.tobytes() == want8.tobytes()) if rgba8 else (union.tobytes() == want.tobytes()), cfg
         assert total == cnt, (cfg, total, cnt)

@@ -122,7 +122,12 @@ VX_SYMBOLS = [
     "vx_frame_sync_errors", "vx_frame8_ipc_handle", "vx_open_peer_frame8",
     "vx_serialize_chunks_esvo", "vx_serialize_chunks_result", "vx_svo_write_device",
     "vx_svo_scatter_errors", "vx_frame_flags_reset", "vx_read_hit_records",
+    "vx_group_create", "vx_group_destroy", "vx_group_last_error", "vx_group_size", "vx_group_ctx", "vx_group_set_materials",
+    "vx_group_set_textures", "vx_group_set_option", "vx_group_svo_host_mirror", "vx_group_svo_set_hot_range", "vx_group_svo_commit",
+    "vx_group_stats", "vx_group_render", "vx_group_wait", "vx_group_read_frame_rgba8", "vx_group_read_frame_rgba32f",
+    "vx_group_host_frame", "vx_group_render_read_rgba8", "vx_group_raycast",
 ]
+VX_SHARD_ROWS = 0x80000000
 
 _lib = None
 _host = None
@@ -195,6 +200,26 @@ def lib():
         L.vx_svo_scatter_errors.argtypes = [P, C.POINTER(C.c_uint32)]; L.vx_svo_scatter_errors.restype = C.c_int
         L.vx_frame_flags_reset.argtypes = [P]; L.vx_frame_flags_reset.restype = C.c_int
         L.vx_read_hit_records.argtypes = [P, P]; L.vx_read_hit_records.restype = C.c_int
+        u32, u64, i32p = C.c_uint32, C.c_uint64, C.POINTER(C.c_int)
+        L.vx_group_create.argtypes = [C.POINTER(VxConfig), i32p, u32, C.POINTER(P)]; L.vx_group_create.restype = C.c_int
+        L.vx_group_destroy.argtypes = [P]; L.vx_group_destroy.restype = None
+        L.vx_group_last_error.argtypes = [P]; L.vx_group_last_error.restype = C.c_char_p
+        L.vx_group_size.argtypes = [P]; L.vx_group_size.restype = u32
+        L.vx_group_ctx.argtypes = [P, u32]; L.vx_group_ctx.restype = P
+        L.vx_group_set_materials.argtypes = [P, C.POINTER(VxMaterial), u32]; L.vx_group_set_materials.restype = C.c_int
+        L.vx_group_set_textures.argtypes = [P, P, u32, u32, u32, u32]; L.vx_group_set_textures.restype = C.c_int
+        L.vx_group_set_option.argtypes = [P, u32, u64]; L.vx_group_set_option.restype = C.c_int
+        L.vx_group_svo_host_mirror.argtypes = [P]; L.vx_group_svo_host_mirror.restype = P
+        L.vx_group_svo_set_hot_range.argtypes = [P, u64, u64]; L.vx_group_svo_set_hot_range.restype = C.c_int
+        L.vx_group_svo_commit.argtypes = [P, C.c_float, C.POINTER(VxRange), u32, u64, u32]; L.vx_group_svo_commit.restype = C.c_int
+        L.vx_group_stats.argtypes = [P, C.POINTER(VxStats)]; L.vx_group_stats.restype = C.c_int
+        L.vx_group_render.argtypes = [P, C.POINTER(VxRenderParams), u32, u32]; L.vx_group_render.restype = C.c_int
+        L.vx_group_wait.argtypes = [P]; L.vx_group_wait.restype = C.c_int
+        L.vx_group_read_frame_rgba8.argtypes = [P, P]; L.vx_group_read_frame_rgba8.restype = C.c_int
+        L.vx_group_read_frame_rgba32f.argtypes = [P, P]; L.vx_group_read_frame_rgba32f.restype = C.c_int
+        L.vx_group_host_frame.argtypes = [P, u64]; L.vx_group_host_frame.restype = P
+        L.vx_group_render_read_rgba8.argtypes = [P, C.POINTER(VxRenderParams), u32, u32, P, u32]; L.vx_group_render_read_rgba8.restype = C.c_int
+        L.vx_group_raycast.argtypes = [P, P, u64, P]; L.vx_group_raycast.restype = C.c_int
     except AttributeError:
         if not os.environ.get("VOXELRT_AB_VARIANT"):   # only tools/ab_kernels.py may load an older build of the library
             raise
@@ -641,6 +666,97 @@ def to_vx_render_params(p):
     q.render_shadows = p.render_shadows
     q.shadow_distance = p.shadow_distance
     return q
+
+
+class SvoGroup:
+    """graphics::Svo spread over several GPUs of ONE process (vx_group_*, include/voxelrt.h): the reference engine's shape — a single
+    process, one Svo — with the SVO replicated per device and frames cut into image-space shards. Straight over the C ABI."""
+
+    def __init__(self, registry, devices, size_mb=10, max_width=1920, max_height=1080, max_rays=100, flags=0):
+        cfg = VxConfig(0, flags, size_mb * 1000 * 1000, max_width, max_height, max_rays)
+        devs = (C.c_int * len(devices))(*devices)
+        g = C.c_void_p()
+        rc = lib().vx_group_create(C.byref(cfg), devs, len(devices), C.byref(g))
+        if rc:
+            raise VxError(f"rc={rc}: {lib().vx_group_last_error(None).decode()}")
+        self.g, self.devices, self.capacity = g, list(devices), size_mb * 1000 * 1000
+        self.width = self.height = 0
+        tex, mips = registry.textures()
+        mats = registry.materials()
+        arr = (VxMaterial * len(mats)).from_buffer_copy(mats.tobytes())
+        self._check(lib().vx_group_set_textures(self.g, _ptr(np.ascontiguousarray(tex)), tex.shape[2], tex.shape[1], tex.shape[0], mips))
+        self._check(lib().vx_group_set_materials(self.g, arr, len(mats)))
+
+    def close(self):
+        if getattr(self, "g", None):
+            lib().vx_group_destroy(self.g)
+            self.g = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise VxError(f"rc={rc}: {lib().vx_group_last_error(self.g).decode()}")
+
+    def __len__(self):
+        return lib().vx_group_size(self.g)
+
+    def ctx(self, i):
+        return C.c_void_p(lib().vx_group_ctx(self.g, i))
+
+    def set_option(self, opt, value):
+        self._check(lib().vx_group_set_option(self.g, opt, value))
+
+    def update(self, world):
+        """graphics::Svo::update (svo.rs:171-189) for every replica: the serializer's write_changes_to goes into device 0's pinned
+        mirror, vx_group_svo_commit moves the dirty ranges (H2D to device 0 -> NCCL broadcast -> scatter kernels)."""
+        hb = world.header_bytes
+        mirror = np.ctypeslib.as_array((C.c_uint8 * self.capacity).from_address(lib().vx_group_svo_host_mirror(self.g)))
+        ranges = world.dirty_ranges()
+        if not world.write_changes_to(mirror):
+            raise VxError("dst is not large enough (esvo.rs:328-331)")
+        arr = (VxRange * max(len(ranges), 1))(*[VxRange(o, l) for o, l in ranges])
+        off, ln = world.root_range()
+        lib().vx_group_svo_set_hot_range(self.g, off, ln)
+        self._check(lib().vx_group_svo_commit(self.g, float(np.float32(2.0 ** -world.depth)), arr, len(ranges), world.size_bytes, world.depth))
+        return hb
+
+    def render_raw(self, vx_params, width, height):
+        self._check(lib().vx_group_render(self.g, C.byref(vx_params), width, height))
+        self.width, self.height = width, height
+
+    def wait(self):
+        self._check(lib().vx_group_wait(self.g))
+
+    def read_rgba32f(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._check(lib().vx_group_read_frame_rgba32f(self.g, _ptr(out)))
+        return out
+
+    def read_rgba8(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._check(lib().vx_group_read_frame_rgba8(self.g, _ptr(out)))
+        return out
+
+    def host_frame(self, width, height):
+        """(height, width, 4) uint8 view of the group's pinned portable host frame."""
+        p = lib().vx_group_host_frame(self.g, width * height * 4)
+        if not p:
+            raise VxError(lib().vx_group_last_error(self.g).decode())
+        return np.ctypeslib.as_array((C.c_uint8 * (width * height * 4)).from_address(p)).reshape(height, width, 4)
+
+    def render_read_rgba8(self, vx_params, width, height, out_ptr, bands=2):
+        self._check(lib().vx_group_render_read_rgba8(self.g, C.byref(vx_params), width, height, C.c_void_p(out_ptr), bands))
+        self.width, self.height = width, height
+
+    def raycast_tasks(self, tasks):
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        res = np.zeros(len(tasks), dtype=RESULT_DTYPE)
+        self._check(lib().vx_group_raycast(self.g, _ptr(tasks), len(tasks), _ptr(res)))
+        return res
+
+    def raycast_ptr(self, tasks_ptr, n, results_ptr):
+        self._check(lib().vx_group_raycast(self.g, C.c_void_p(tasks_ptr), n, C.c_void_p(results_ptr)))
 
 
 class Svo:

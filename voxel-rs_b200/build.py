@@ -47,12 +47,12 @@ def build_variant(name, defines, verbose=False):
 
 def build_cuda(force=False, verbose=False):
     src = os.path.join(PKG, "csrc", "voxelrt.cu")
-    deps = [src, os.path.join(PKG, "csrc", "traverse.cuh"), os.path.join(PKG, "csrc", "kernels.cuh"), os.path.join(PKG, "csrc", "chunks.cuh"), os.path.join(ROOT, "include", "voxelrt.h")]
+    deps = [src] + [os.path.join(PKG, "csrc", f) for f in ("traverse.cuh", "kernels.cuh", "chunks.cuh", "group.inl")] + [os.path.join(ROOT, "include", "voxelrt.h")]
     out = os.path.join(PKG, "libvoxelrt.so")
     if not force and not _newer(out, deps):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, src]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, src, "-ldl"]
     subprocess.run(cmd, check=True, cwd=os.path.join(PKG, "csrc"))
     return out
 

@@ -44,6 +44,9 @@ struct RenderArgs {
     uint32_t first_owned;         // first macro block >= macro0 owned by this shard
     uint32_t n_owned;             // macro blocks of [macro0, macro0 + n_macros) owned by this shard
     uint32_t shard_rank, shard_size;
+    uint32_t shard_rows;          // 0: macro block m belongs to shard m % size (interleaved blocks: the finest mix of cheap and expensive
+                                  // image regions, for frames that stay on a GPU); 1: macro ROW r belongs to shard r % size (every shard's
+                                  // pixels are whole 16-pixel-high stripes of the frame: one strided DMA moves them to a host frame)
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
     uint32_t shadow_refill;       // the same for trace_shadow_kernel
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
@@ -56,9 +59,33 @@ struct RenderArgs {
 // side, and pixel p of a strip is lane p%32 of tile p/32: consecutive work indices, consecutive pixels of a warp and
 // consecutive tiles of a strip are all spatial neighbours (coherent rays, shared nodes in L1).
 // Pixel slot (index into hit0/hit1) = strip * 128 + p.
+__host__ __device__ __forceinline__ bool macro_owned(const RenderArgs& a, uint32_t macro) {
+    if (a.shard_size <= 1) return true;
+    return (a.shard_rows ? (macro / a.macro_x) % a.shard_size : macro % a.shard_size) == a.shard_rank;
+}
+// k-th macro block this shard owns inside the band of the launch (first_owned: its first owned macro block, resp. macro ROW)
+__device__ __forceinline__ uint32_t owned_macro(const RenderArgs& a, uint32_t k) {
+    if (!a.shard_rows) return a.first_owned + k * a.shard_size;
+    const uint32_t j = k / a.macro_x;
+    return (a.first_owned + j * a.shard_size) * a.macro_x + (k - j * a.macro_x);
+}
+// Band [row0, row1) of macro rows: what of it this shard owns. Host side of the launch (voxelrt.cu, and tests/emu's stand-in for it).
+inline void shard_band(RenderArgs& a, uint32_t row0, uint32_t row1) {
+    a.macro0 = row0 * a.macro_x;
+    a.n_macros = (row1 - row0) * a.macro_x;
+    const uint32_t size = a.shard_size, rank = a.shard_rank;
+    if (a.shard_rows) {
+        a.first_owned = row0 + ((rank + size - (row0 % size)) % size);
+        a.n_owned = a.first_owned < row1 ? ((row1 - a.first_owned + size - 1) / size) * a.macro_x : 0;
+    } else {
+        a.first_owned = a.macro0 + ((rank + size - (a.macro0 % size)) % size);
+        const uint32_t band_end = a.macro0 + a.n_macros;
+        a.n_owned = a.first_owned < band_end ? (band_end - a.first_owned + size - 1) / size : 0;
+    }
+}
 __device__ __forceinline__ bool strip_origin(const RenderArgs& a, uint32_t strip, uint32_t& x0, uint32_t& y0) {
     const uint32_t macro = strip >> 2;
-    if (a.shard_size > 1 && (macro % a.shard_size) != a.shard_rank) return false;
+    if (!macro_owned(a, macro)) return false;
     x0 = (macro % a.macro_x) * 32;
     y0 = (macro / a.macro_x) * 16 + (strip & 3u) * 4;
     return x0 < a.u.width && y0 < a.u.height;
@@ -200,7 +227,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     if (work >= n_tiles) { more_work = false; break; }
                 }
                 tile = work++;
-                tile = (a.first_owned + (tile >> 4) * a.shard_size) * 16u + (tile & 15u);
+                tile = owned_macro(a, tile >> 4) * 16u + (tile & 15u);
                 if (!strip_origin(a, tile >> 2, strip_x0, strip_y0)) continue;
                 tile_px0 = (tile & 3u) * 32u;
                 next_px = 0;
@@ -260,7 +287,7 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t strip = ((a.first_owned + (blockIdx.x >> 2) * a.shard_size) << 2) | (blockIdx.x & 3u);
+    const uint32_t strip = (owned_macro(a, blockIdx.x >> 2) << 2) | (blockIdx.x & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
     const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);

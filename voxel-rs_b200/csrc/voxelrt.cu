@@ -60,12 +60,13 @@ struct VxCtx {
     uint32_t* d_frame8 = nullptr;
     bool frame32_stale = false;       // the last frame was rendered as RGBA8 only (vx_render_read_rgba8 / option 8)
     uint32_t frame_w = 0, frame_h = 0;
-    uint32_t last_shard_rank = 0, last_shard_size = 1;   // shard of the last render (vx_read_hit_records)
+    uint32_t last_shard_rank = 0, last_shard_size = 1, last_shard_rows = 0;   // shard of the last render (vx_read_hit_records)
     float4* frame_target = nullptr;   // where finished pixels go: d_frame, or a peer GPU's framebuffer (vx_open_peer_frame)
     uint32_t* frame8_target = nullptr;    // RGBA8 output mode (vx_set_option 8): d_frame8, or a peer GPU's RGBA8 frame (vx_open_peer_frame)
     unsigned int* d_flags = nullptr;      // 64 frame flags of this ctx (the root's are mapped by its peers); [63] = wait timeouts, [62] = dirty ranges the scatter kernel refused
     unsigned int* flags_target = nullptr; // the flags this ctx signals / gates on: d_flags, or the root's (vx_open_peer_sync)
     bool gate_armed = false;              // next vx_render: wait for flags_target[gate_slot] >= gate_value between trace and shade
+    cudaEvent_t gate_event = nullptr;     // next vx_render: wait for this event (another device's, vx_group_render) at the same place
     unsigned int gate_slot = 0, gate_value = 0;
 
     // wavefront buffers of the render path (kernels.cuh), sized for the padded pixel count of the largest frame seen
@@ -203,10 +204,10 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaMalloc(&c->d_world_raw, cap + 64));
     c->d_world = c->d_world_raw + 8;
     CUC(cudaMemsetAsync(c->d_world_raw, 0, cap + 64, c->s_upload));
-    CUC(cudaHostAlloc(&c->h_mirror, cap, cudaHostAllocDefault));
+    CUC(cudaHostAlloc(&c->h_mirror, cap, cudaHostAllocPortable));   // portable: every device of a VxGroup uploads from device 0's mirror
     std::memset(c->h_mirror, 0, cap < (1u << 20) ? cap : (1u << 20));
     c->stage_cap = cap < (64u << 20) ? cap : (64u << 20);
-    CUC(cudaHostAlloc(&c->h_stage, c->stage_cap, cudaHostAllocDefault));
+    CUC(cudaHostAlloc(&c->h_stage, c->stage_cap, cudaHostAllocPortable));
     if (cfg->max_width && cfg->max_height) {
         const size_t px = (size_t)cfg->max_width * cfg->max_height;
         CUC(cudaMalloc(&c->d_frame, px * sizeof(float4)));
@@ -401,6 +402,32 @@ static void install_l2_window(VxCtx* c) {
     cudaGetLastError();   // a refused window is a lost optimisation, not an error
 }
 
+// Bulk (re)load of ranges straight from a pinned mirror (this context's, or — in a VxGroup — device 0's): one DMA per range, then
+// wait, because the caller may rewrite the mirror as soon as the call returns.
+static int vx_svo_commit_from(VxCtx* c, const uint8_t* mirror, float octree_scale, const VxRange* dirty, uint32_t n_dirty, uint64_t used_bytes,
+                              uint32_t depth) {
+    (void)octree_scale;   // already at byte 0 of the mirror
+    CU(c, cudaSetDevice(c->cfg.device));
+    for (uint32_t i = 0; i < n_dirty; ++i)
+        if (dirty[i].offset + dirty[i].length + c->head > c->cfg.svo_capacity_bytes)
+            return fail(c, VX_E_CAPACITY, "dst is not large enough: len=%llu range_start=%llu range_length=%llu", (unsigned long long)c->cfg.svo_capacity_bytes,
+                        (unsigned long long)dirty[i].offset, (unsigned long long)dirty[i].length);
+    CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));
+    CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
+    if (n_dirty) {
+        CU(c, cudaMemcpyAsync(c->d_world, mirror, c->head, cudaMemcpyHostToDevice, c->s_upload));
+        for (uint32_t i = 0; i < n_dirty; ++i)
+            CU(c, cudaMemcpyAsync(c->d_world + c->head + dirty[i].offset, mirror + c->head + dirty[i].offset, dirty[i].length, cudaMemcpyHostToDevice,
+                                  c->s_upload));
+        CU(c, cudaStreamSynchronize(c->s_upload));
+        c->have_svo = true;
+    }
+    CU(c, cudaEventRecord(c->e_upload, c->s_upload));
+    c->stats.used_bytes = used_bytes; c->stats.depth = depth;
+    install_l2_window(c);
+    return VX_OK;
+}
+
 int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n_dirty, uint64_t used_bytes, uint32_t depth) {
     if (!c || (n_dirty && !dirty)) return fail(c, VX_E_ARG, "vx_svo_commit: null argument");
     const uint64_t cap = c->cfg.svo_capacity_bytes;
@@ -563,13 +590,8 @@ static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->
 // One wavefront (trace -> shade -> shadow) over the macro-block rows [row0, row1) of the frame, on the render stream.
 // `band` selects the set of work counters (each band of a frame needs its own zeroed set).
 static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band, uint32_t row0, uint32_t row1, bool timed) {
-    a.macro0 = row0 * a.macro_x;
-    a.n_macros = (row1 - row0) * a.macro_x;
-    const uint32_t size = a.shard_size, rank = a.shard_rank;
-    a.first_owned = a.macro0 + ((rank + size - (a.macro0 % size)) % size);
-    const uint32_t band_end = a.macro0 + a.n_macros;
-    const uint32_t owned = a.first_owned < band_end ? (band_end - a.first_owned + size - 1) / size : 0;
-    a.n_owned = owned;
+    shard_band(a, row0, row1);
+    const uint32_t owned = a.n_owned;
     unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work) + 16 + band * 8;   // [0] primary strips, [2] shadow runs, [4] shadow list length
     a.shadow_count = work + 4;
     const size_t smem = stack_smem_bytes(a.scene);
@@ -609,6 +631,10 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             c->launches++;
             c->gate_armed = false;
         }
+        if (c->gate_event) {   // single-process group: the root's "previous frame consumed" event, no kernel needed
+            CU(c, cudaStreamWaitEvent(c->s_render, c->gate_event, 0));
+            c->gate_event = nullptr;
+        }
         // 2. shading -> final pixels + shadow ray list
         const size_t smem2 = smem_bytes(0, false);
         if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
@@ -629,6 +655,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
         CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
     }
     c->gate_armed = false;   // a gate belongs to ONE frame: a rank that owns no macro block of it must not carry it into the next
+    c->gate_event = nullptr;
     if (timed) CU(c, cudaEventRecord(c->t_wave[3], c->s_render));
     return VX_OK;
 }
@@ -641,7 +668,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     if (!c->d_frame || (uint64_t)width * height > (uint64_t)c->cfg.max_width * c->cfg.max_height)
         return fail(c, VX_E_CAPACITY, "%s: %ux%u exceeds the %ux%u framebuffer reserved at vx_create", who, width, height, c->cfg.max_width,
                     c->cfg.max_height);
-    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return fail(c, VX_E_ARG, "%s: bad shard", who);
+    if (shard && ((shard->world_size & ~VX_SHARD_ROWS) == 0 || shard->rank >= (shard->world_size & ~VX_SHARD_ROWS))) return fail(c, VX_E_ARG, "%s: bad shard", who);
     int rc = check_scene(c, who);
     if (rc) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
@@ -661,8 +688,9 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.frame8 = c->opt_rgba8_out ? (c->frame8_target ? c->frame8_target : c->d_frame8) : nullptr;
     a.hit0 = c->d_hit0; a.hit1 = c->d_hit1; a.sh0 = c->d_sh0; a.sh1 = c->d_sh1; a.sh_pix = c->d_sh_pix;
     a.counters = c->d_counters;
-    a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? shard->world_size : 1;
-    c->last_shard_rank = a.shard_rank; c->last_shard_size = a.shard_size;
+    a.shard_rank = shard ? shard->rank : 0; a.shard_size = shard ? (shard->world_size & ~VX_SHARD_ROWS) : 1;
+    a.shard_rows = shard ? ((shard->world_size & VX_SHARD_ROWS) ? 1u : 0u) : 0u;
+    c->last_shard_rank = a.shard_rank; c->last_shard_size = a.shard_size; c->last_shard_rows = a.shard_rows;
     a.refill_threshold = (uint32_t)c->opt_refill;
     a.shadow_refill = (uint32_t)(c->opt_refill_shadow ? c->opt_refill_shadow : c->opt_refill);
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
@@ -695,8 +723,10 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
 // (bottom to top); as soon as a band is finished it is converted to RGBA8 and copied to the host on the copy stream while the
 // next band is being traced, so only the last band's copy is exposed. rgba8_out should be pinned (cudaHostAlloc /
 // cudaHostRegister) for the overlap to happen. Returns when the whole frame is in rgba8_out.
-int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
-                         uint32_t bands) {
+// Everything of vx_render_read_rgba8 except waiting for the copies (vx_group_render_read_rgba8 issues one of these per device
+// and waits for all of them afterwards).
+static int render_read_rgba8_issue(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
+                                   uint32_t bands) {
     if (!rgba8_out) return fail(c, VX_E_ARG, "vx_render_read_rgba8: null output");
     RenderArgs a{};
     int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
@@ -731,17 +761,45 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
         if (row1 == row0) continue;
         rc = launch_wavefront(c, a, p->render_shadows != 0, b, row0, row1, false);
         if (rc) return rc;
-        const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
-        const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
         CU(c, cudaEventRecord(c->e_band[b], c->s_render));
         CU(c, cudaStreamWaitEvent(c->s_copy, c->e_band[b], 0));
-        CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
+        if (a.shard_rows && a.shard_size > 1) {
+            // this shard's stripes of the band: macro rows first, first + size, ... — each a contiguous run of 16 * width pixels,
+            // a constant stride apart: ONE strided DMA (plus one for a ragged last stripe) into the host frame all shards share
+            RenderArgs t = a;
+            shard_band(t, row0, row1);
+            uint32_t n_rows = t.n_owned / a.macro_x;
+            if (n_rows) {
+                const size_t stripe = (size_t)16 * width * 4, pitch = stripe * a.shard_size, off = (size_t)t.first_owned * stripe;
+                const uint32_t last = t.first_owned + (n_rows - 1) * a.shard_size;
+                if (last * 16 + 16 > height) {   // ragged last stripe of the frame
+                    const size_t lo = (size_t)last * stripe;
+                    CU(c, cudaMemcpyAsync(rgba8_out + lo, reinterpret_cast<const uint8_t*>(c->d_frame8) + lo, (size_t)(height - last * 16) * width * 4,
+                                          cudaMemcpyDeviceToHost, c->s_copy));
+                    --n_rows;
+                }
+                if (n_rows)
+                    CU(c, cudaMemcpy2DAsync(rgba8_out + off, pitch, reinterpret_cast<const uint8_t*>(c->d_frame8) + off, pitch, stripe, n_rows,
+                                            cudaMemcpyDeviceToHost, c->s_copy));
+            }
+        } else {
+            const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
+            const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
+            CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
+        }
     }
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
     c->render_timed = false;
     c->frame32_stale = true;
+    return VX_OK;
+}
+
+int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
+                         uint32_t bands) {
+    int rc = render_read_rgba8_issue(c, p, width, height, shard, rgba8_out, bands);
+    if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->s_copy));
     return VX_OK;
 }
@@ -801,7 +859,7 @@ int vx_read_hit_records(VxCtx* c, VxHitRecord* out) {
             const size_t slot = ((size_t)macro * 4 + (y % 16) / 4) * 128 + ((x % 32) / 8) * 32 + (y % 4) * 8 + (x % 8);   // kernels.cuh strip_pixel
             VxHitRecord& o = out[(size_t)y * w + x];
             std::memset(&o, 0, sizeof(o));
-            if (macro % size != rank) { o.t = -2.0f; continue; }
+            if ((c->last_shard_rows ? (y / 16) % size : macro % size) != rank) { o.t = -2.0f; continue; }
             uint32_t flags;
             std::memcpy(&flags, &h1[slot].w, 4);
             if (!(flags & 8u)) { o.t = -1.0f; continue; }
@@ -959,7 +1017,8 @@ uint64_t vx_shard_bytes(uint32_t width, uint32_t height, const VxShard* shard) {
 
 static int shard_copy(VxCtx* c, const VxShard* shard, void* packed_dev, bool pack) {
     if (!c || !packed_dev || !c->frame_w) return fail(c, VX_E_ARG, "vx_%s_shard: null argument / nothing rendered", pack ? "pack" : "unpack");
-    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size)) return fail(c, VX_E_ARG, "vx_%s_shard: bad shard", pack ? "pack" : "unpack");
+    if (shard && (shard->world_size == 0 || shard->rank >= shard->world_size))   // (VX_SHARD_ROWS shards are not packed: their stripes are contiguous already)
+        return fail(c, VX_E_ARG, "vx_%s_shard: bad shard", pack ? "pack" : "unpack");
     CU(c, cudaSetDevice(c->cfg.device));
     uint32_t mx, n, owned;
     shard_geometry(c->frame_w, c->frame_h, shard, &mx, &n, &owned);
@@ -1247,3 +1306,5 @@ int vx_frame_stats(VxCtx* c, int which, VxFrameStats* out) {
 }
 
 }  // extern "C"
+
+#include "group.inl"

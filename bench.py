@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 METRIC = "Mrays/s (primary+shadow)"
+FLUSH_BYTES = 144 << 20   # L2 flush between steps: a device fill larger than the 126 MB L2
 
 
 def parse():
@@ -66,6 +67,10 @@ def parse():
     ap.add_argument("--workload", default="frame", choices=["frame", "picker", "serialize"], help="frame = BASELINE configs[2] (the metric's config, "
                     "default); picker = configs[3], 16 Mi incoherent picker rays against an r=40 no-LOD world; serialize = SURVEY §8f n3, ESVO "
                     "serialization of every chunk of the r=20 world on the GPU")
+    ap.add_argument("--sim-shard", type=int, default=0, help="diagnostic, 1 GPU: render only shard 0 of N of every frame (what one rank of an "
+                    "N-GPU run does, without the collectives) — for tuning the small-frame regime; not a bench line")
+    ap.add_argument("--group", action="store_true", help="--gpus N from ONE process through vx_group_* (the reference's shape: a single process) "
+                    "instead of one rank per GPU under torchrun")
     ap.add_argument("--rays", type=int, default=1 << 24, help="picker workload: number of rays")
     ap.add_argument("--max-dst", type=float, default=-1.0, help="picker workload: max_dst of every task (-1 = unlimited)")
     return ap.parse_args()
@@ -242,6 +247,8 @@ def main():
         return run_picker(args)
     if args.workload == "serialize":
         return run_serialize(args)
+    if args.group:
+        return run_group(args)
 
     import torch
     import torch.distributed as dist
@@ -281,7 +288,7 @@ def main():
         svo.set_option(pkg.OPT_TMA, 1)
     svo.update(world)
     vxp = frame_params(pkg, world, args)
-    shard = (rank, n_gpus)
+    shard = (rank, n_gpus) if not args.sim_shard else (0, args.sim_shard)
     pixels = W * H
 
     # scripted per-frame dirty set: 4 chunk-sized ranges (half-full LOD-5 chunk ~ 112 KB) + the world root
@@ -295,7 +302,7 @@ def main():
     octree_scale = float(np.float32(2.0 ** -world.depth))
     packed_n = svo.pack_dirty(dirty, None)
     packed_host = torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)
-    flush_buf = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # 160 MiB > the 126 MB L2
+    flush_buf = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)   # > the 126 MB L2
 
     sf = pkg.sharded.ShardedFrame(svo, rank, n_gpus, dist=dist if n_gpus > 1 else None, torch=torch, device=dev, gather=args.gather)
     sf.configure(W, H, max_dirty_bytes=packed_n)
@@ -318,11 +325,42 @@ def main():
         # ahead on a side stream), applied here by a scatter kernel; then the next frame's set starts travelling
         sf.apply_dirty()
         sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth)
+        if args.sim_shard:
+            svo.render_raw(vxp, W, H, shard=shard)
+            return
         sf.render(vxp)
         sf.finish()   # tiles in GPU 0's framebuffer (p2p: stored there by the render kernels; nccl: pack/send/recv/unpack)
         sf.release()
 
-    frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    shm = None
+    if n_gpus > 1:
+        # e2e at N > 1: ONE host frame shared by the ranks (POSIX shared memory, page-locked in every process), every rank DMAs the
+        # stripes it rendered (VX_SHARD_ROWS) into it over its own PCIe link; a word per rank behind the frame says which step's
+        # stripes are in (host-side release / acquire: a plain store after the rank's copy stream drained, rank 0 polls)
+        from multiprocessing import shared_memory
+        name = "vxframe_%s" % os.environ.get("MASTER_PORT", "0")
+        nbytes = W * H * 4 + 4096
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(create=True, size=nbytes, name=name)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name)
+        shm_np = np.ndarray((nbytes,), dtype=np.uint8, buffer=shm.buf)
+        rc = torch.cuda.cudart().cudaHostRegister(shm_np.ctypes.data, nbytes, 1)   # cudaHostRegisterPortable
+        assert int(rc) == 0, f"cudaHostRegister: {rc}"
+        frame8_np = shm_np[:W * H * 4].reshape(H, W, 4)
+        frame8_ptr = shm_np.ctypes.data
+        step_words = shm_np[W * H * 4:W * H * 4 + 256].view(np.uint32)   # [r] = last e2e step whose stripes of rank r are in; [63] = rank 0's ack
+        if rank == 0:
+            step_words[:] = 0
+        dist.barrier()
+    else:
+        frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    e2e_step = [0]
     mirror = svo.host_mirror(HB + world.size_bytes)
     staged = [bytes(mirror[HB + o:HB + o + l]) for o, l in dirty]
 
@@ -344,12 +382,18 @@ def main():
             # render + read-back pipelined by the library: finished bands are copied to the host while the next is traced
             svo.render_read_rgba8(vxp, W, H, frame8.data_ptr(), bands=args.bands)
             return
-        sf.render(vxp)
-        sf.finish()
+        e2e_step[0] += 1
+        k = e2e_step[0]
+        if rank != 0:
+            while step_words[63] < k - 1:      # rank 0 is done with the previous host frame
+                pass
+        # returns when THIS rank's stripes are in the shared host frame (its copy stream drained)
+        svo.render_read_rgba8(vxp, W, H, frame8_ptr, bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        step_words[rank] = k
         if rank == 0:
-            import ctypes as C
-            svo._check(pkg.lib().vx_read_frame_rgba8(svo.ctx, C.c_void_p(frame8.data_ptr())))
-        sf.release()
+            while int(step_words[:n_gpus].min()) < k:   # the frame is whole: every rank's stripes of step k are in host memory
+                pass
+            step_words[63] = k
 
     def barrier():
         if n_gpus > 1:
@@ -445,7 +489,16 @@ def main():
                "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16), "d2h_bytes_per_step": int(W * H * 4),
                "path": ("host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8 (%d bands: trace/shade overlapped with the "
                         "RGBA8 D2H copy into pinned host memory)" % args.bands) if n_gpus == 1 else
-                       "host dirty ranges -> pack -> H2D -> NCCL broadcast -> scatter -> sharded render -> tiles to GPU 0 -> vx_read_frame_rgba8 (D2H)"}
+                       "host dirty ranges -> pack -> H2D -> NCCL broadcast -> scatter -> every rank renders whole 16-pixel stripes "
+                       "(VX_SHARD_ROWS) and DMAs them itself into ONE page-locked host frame shared by the ranks (N PCIe links); rank 0 "
+                       "returns when all stripes of the step are in host memory"}
+        if n_gpus > 1 and rank == 0:
+            # the host frame of the last e2e step against rank 0's own unsharded render: the shared frame is the frame
+            svo.render_raw(vxp, W, H, shard=None)
+            ref8 = svo.read_rgba8()
+            if ref8.tobytes() != frame8_np.tobytes():
+                raise SystemExit("bench.py: the host frame assembled from the ranks' stripes differs from the single-GPU frame")
+            e2e["parity_check"] = "shared host frame == rank 0's unsharded RGBA8 frame, byte for byte"
 
     if n_gpus > 1:
         # a frame-flag wait that timed out (lost / slow peer) means torn frames: the numbers above would be of garbage
@@ -453,9 +506,19 @@ def main():
         dist.all_reduce(errs)
         if int(errs.item()):
             raise SystemExit(f"bench.py: {int(errs.item())} frame-flag waits timed out during the run — no number reported")
+    def release_shm():
+        if shm is not None:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(shm_np.ctypes.data)
+            dist.barrier()
+            shm.close()
+            if rank == 0:
+                shm.unlink()
+
     if rank != 0:
         if n_gpus > 1:
             dist.barrier()
+            release_shm()
             sf.close()
             dist.destroy_process_group()
         return
@@ -499,10 +562,10 @@ def main():
             "workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "svo_format": args.format,
             "chunks": int(world.chunk_count), "rays_per_frame": rays_total, "primary_rays": prim_total, "shadow_rays": shad_total,
             "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
-            "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 160 MiB device fill (> 126 MB L2) inside the timed region",
+            "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 144 MiB device fill (> 126 MB L2) inside the timed region",
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)", "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
-            "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
+            "sim_shard": args.sim_shard or None, "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
                                ("finished pixels stored by the shade/shadow kernels straight into GPU 0's %s framebuffer over NVLink peer memory, "
                                 "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"
@@ -534,8 +597,107 @@ def main():
 
     if n_gpus > 1:
         dist.barrier()
+        release_shm()
         sf.close()
         dist.destroy_process_group()
+
+
+def run_group(args):
+    """--group: the same frame on --gpus N devices driven from ONE process through vx_group_* (the reference engine is a single
+    process; this is the drop-in's own multi-GPU mode). value = resident frames (vx_group_svo_commit of the frame's dirty ranges:
+    packed H2D -> ncclBroadcast -> scatter; vx_group_render: peer-store gather into device 0's RGBA32F frame); e2e = the same
+    dirty ranges + vx_group_render_read_rgba8 into the group's page-locked host frame (every device DMAs its own stripes).
+    Timed on the host around K steps (the work spans N devices; every step ends with all devices idle)."""
+    import ctypes as C
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — no CPU fallback")
+    n = args.gpus
+    graft.build()
+    pkg = graft.load_pkg()
+    world, gen_s = build_world(pkg, args)
+    reg = pkg.content_registry(pkg.load_atlas())
+    W, H = args.width, args.height
+    grp = pkg.SvoGroup(reg, list(range(n)), size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=W, max_height=H, max_rays=1024, flags=world.svo_flags)
+    one = pkg.Svo(reg, size_mb=int(world.size_bytes // 1_000_000 + 64), max_width=W, max_height=H, max_rays=1024, flags=world.svo_flags)
+    world.mark_all_dirty()
+    one.update(world)
+    world.mark_all_dirty()
+    grp.update(world)
+    vxp = frame_params(pkg, world, args)
+    one.set_option(pkg.OPT_COUNT, 1)
+    one.render_raw(vxp, W, H)
+    st = one.frame_stats(0)
+    one.set_option(pkg.OPT_COUNT, 0)
+    want32, want8 = one.read_rgba32f(), one.read_rgba8()
+    rays = st["primary_rays"] + st["shadow_rays"]
+    # parity before timing: both group paths against the single-GPU context
+    grp.render_raw(vxp, W, H)
+    ok32 = grp.read_rgba32f().tobytes() == want32.tobytes()
+    host = grp.host_frame(W, H)
+    grp.render_read_rgba8(vxp, W, H, host.ctypes.data, bands=min(args.bands, 2))
+    ok8 = host.tobytes() == want8.tobytes()
+    if not (ok32 and ok8):
+        raise SystemExit(f"bench.py --group: group frame differs from the single-GPU frame (rgba32f ok={ok32}, rgba8 ok={ok8})")
+    one.close()
+
+    root_off, root_len = world.root_range()
+    chunk_len = 2336 * 48
+    stride = max(chunk_len, ((world.size_bytes - chunk_len) // 4) // 48 * 48)
+    dirty = [(i * stride, min(chunk_len, world.size_bytes - i * stride)) for i in range(4) if i * stride < world.size_bytes] + [(root_off, root_len)]
+    HB = world.header_bytes
+    dirty_bytes = sum(l for _, l in dirty) + HB
+    arr = (pkg.VxRange * len(dirty))(*[pkg.VxRange(o, l) for o, l in dirty])
+    scale = float(np.float32(2.0 ** -world.depth))
+    L = pkg.lib()
+    flush = [torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=torch.device("cuda", i)) for i in range(n)]
+
+    def sync():
+        for i in range(n):
+            torch.cuda.synchronize(i)
+
+    def step(e2e):
+        for b in flush:
+            b.fill_(1)
+        grp._check(L.vx_group_svo_commit(grp.g, scale, arr, len(dirty), world.size_bytes, world.depth))
+        if e2e:
+            grp.render_read_rgba8(vxp, W, H, host.ctypes.data, bands=min(args.bands, 2))
+        else:
+            grp.render_raw(vxp, W, H)
+
+    def timed(e2e):
+        for _ in range(args.warmup):
+            step(e2e)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(e2e)
+        if not e2e:
+            grp.wait()
+        sync()
+        return (time.perf_counter() - t0) * 1e3 / args.steps, t0
+
+    sampler = ClockSampler(0)
+    t_wall0 = time.time()
+    ms, _ = timed(False)
+    clocks = sampler.stop(t_wall0, time.time())
+    ms_e2e, _ = timed(True)
+    line = {
+        "metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "rays_per_frame": rays,
+                   "parallelism": f"ONE process, vx_group_* over {n} GPU(s): SVO replicated, dirty ranges by ncclBroadcast, interleaved macro blocks "
+                                  "stored into device 0's frame over NVLink peer memory (value) / whole stripes DMA'd by every device into one "
+                                  "page-locked host frame (e2e)",
+                   "l2": "flushed between steps: 144 MiB device fill per GPU inside the timed region", "timing": "host clock around K steps, all devices synchronised",
+                   "parity_check": "vx_group_render == single-GPU RGBA32F frame and vx_group_render_read_rgba8 == single-GPU RGBA8 frame, byte for byte",
+                   "world_gen_s": round(gen_s, 2)},
+        "e2e": {"value": rays / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16),
+                "d2h_bytes_per_step": int(W * H * 4), "path": "host dirty ranges -> vx_group_svo_commit -> vx_group_render_read_rgba8 (host frame)"},
+        "clocks": clocks, "gpu_launches": int(sum(L.vx_launch_count(grp.ctx(i)) for i in range(n))),
+    }
+    print(json.dumps(line), flush=True)
+    grp.close()
 
 
 def run_serialize(args):

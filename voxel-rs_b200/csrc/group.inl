@@ -154,16 +154,17 @@ void vx_group_destroy(VxGroup* g) {
     for (uint32_t i = 0; i < g->comms.size(); ++i)
         if (g->comms[i]) g->nccl.CommDestroy(g->comms[i]);
     for (uint32_t i = 0; i < g->ctx.size(); ++i) {
-        if (!g->ctx[i]) continue;
+        if (!g->ctx[i]) { if (i < g->e_done.size() && g->e_done[i]) cudaEventDestroy(g->e_done[i]); continue; }
         g->ctx[i]->frame_target = nullptr;   // plain peer pointers into device 0's frame, not IPC mappings: nothing to close
         g->ctx[i]->gate_event = nullptr;
         cudaSetDevice(g->dev[i]);
         if (i < g->e_done.size() && g->e_done[i]) cudaEventDestroy(g->e_done[i]);
         vx_destroy(g->ctx[i]);
     }
-    if (!g->dev.empty()) cudaSetDevice(g->dev[0]);
+    if (!g->ctx.empty() && g->ctx[0]) cudaSetDevice(g->dev[0]);
     if (g->e_released) cudaEventDestroy(g->e_released);
     if (g->h_frame8) cudaFreeHost(g->h_frame8);
+    cudaGetLastError();   // (a failed vx_group_create must not leave its CUDA error for the next call to trip over)
     delete g;
 }
 

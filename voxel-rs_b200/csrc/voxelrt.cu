@@ -221,10 +221,12 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaMemsetAsync(c->d_flags, 0, 64 * sizeof(unsigned int), c->s_upload));
     CUC(cudaMalloc(&c->d_unorm, 256 * sizeof(float)));
     unorm_kernel<<<1, 256, 0, c->s_upload>>>(c->d_unorm);
-    CUC(cudaMalloc(&c->d_counters, 2 * sizeof(Counters)));
-    CUC(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(Counters), c->s_upload));
-    CUC(cudaMalloc(&c->d_work, 64 + 16 * 32));   // [0..7] u64: picker run counter at [4]; then 16 bands x 8 u32 render counters
-    CUC(cudaMemsetAsync(c->d_work, 0, 64 + 16 * 32, c->s_upload));
+    // one block: [0..7] u64 (picker run counter at [4], chunk bump pointer at [6..7]) | 16 bands x 8 u32 render work counters | the
+    // render Counters | the raycast Counters — the per-frame reset of work counters + render Counters is ONE memset
+    static_assert(sizeof(Counters) == 48, "Counters layout");
+    CUC(cudaMalloc(&c->d_work, 64 + 16 * 32 + 2 * sizeof(Counters)));
+    CUC(cudaMemsetAsync(c->d_work, 0, 64 + 16 * 32 + 2 * sizeof(Counters), c->s_upload));
+    c->d_counters = reinterpret_cast<Counters*>(reinterpret_cast<uint8_t*>(c->d_work) + 64 + 16 * 32);
     CUC(cudaEventRecord(c->e_upload, c->s_upload));
     CUC(cudaStreamSynchronize(c->s_upload));
     c->stats.capacity_bytes = cap;
@@ -271,7 +273,6 @@ void vx_destroy(VxCtx* c) {
     if (c->s_pick_in) cudaStreamDestroy(c->s_pick_in);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_results) cudaFree(c->d_results);
-    if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_work) cudaFree(c->d_work);
     cudaEvent_t evs[] = {c->e_upload, c->e_render, c->e_picker, c->t0_render, c->t1_render, c->t0_picker, c->t1_picker};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
@@ -695,8 +696,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.shadow_refill = (uint32_t)(c->opt_refill_shadow ? c->opt_refill_shadow : c->opt_refill);
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
-    CU(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->s_render));
-    CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32, c->s_render));
+    CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32 + sizeof(Counters), c->s_render));   // work counters + render Counters
     return VX_OK;
 }
 
@@ -731,9 +731,10 @@ static int render_read_rgba8_issue(VxCtx* c, const VxRenderParams* p, uint32_t w
     RenderArgs a{};
     int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
     if (rc) return rc;
-    if (c->frame_target || c->frame8_target) return fail(c, VX_E_STATE, "vx_render_read_rgba8: a peer frame is open (pixels are not written locally)");
-    a.frame8 = c->d_frame8;   // the caller wants RGBA8: the shade / shadow kernels store the rounded pixels themselves (same bytes as
-                              // converting the RGBA32F frame, a quarter of the frame traffic, no conversion pass)
+    a.frame8 = c->d_frame8;   // the caller wants RGBA8 on the host: the shade / shadow kernels store the rounded pixels themselves (same
+                              // bytes as converting the RGBA32F frame, a quarter of the frame traffic, no conversion pass) — into THIS
+                              // device's frame even while a peer frame is open (vx_open_peer_frame*): the copy below reads it
+    a.tma_writeback = 0;
     if (bands < 1) bands = 1;
     if (bands > VX_MAX_BANDS) bands = VX_MAX_BANDS;
     if (bands > a.macro_y) bands = a.macro_y;

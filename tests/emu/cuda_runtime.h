@@ -103,6 +103,8 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((
 static inline uint32_t& vx_emu_shared_u32(uint32_t byte_address) { return *reinterpret_cast<uint32_t*>(emu::smem_base + byte_address); }
 static inline void __syncthreads() { emu::cta_barrier(); }
 static inline void __threadfence_system() {}
+static inline void __threadfence() {}
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline void __nanosleep(unsigned) {}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }

@@ -178,7 +178,7 @@ extern "C" {
 // [5] TMA-style tile write-back, [6] shard rank, [7] shard size, [8] bands (vx_render_read_rgba8's banded wavefront; 0/1 = whole frame)
 EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
                const uint8_t* tex_rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels, const VxRenderParams* p, uint32_t width,
-               uint32_t height, const uint32_t options[9], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
+               uint32_t height, const uint32_t options[10], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
     Device d;
     upload(d, world, world_bytes, fmt, depth, materials, n_materials, tex_rgba8, tw, th, layers, mip_levels);
     RenderArgs a{};
@@ -224,6 +224,11 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
         }
     }
     unsigned int work_all[16 * 8] = {};
+    // options[9]: the overlapped wavefront's strip-completion flags (kernels run one after the other here, so every wait is
+    // already satisfied — what is checked is that producers count exactly what consumers expect)
+    std::vector<unsigned int> strip_done(slots / 128, 0u);
+    unsigned int sync_errors = 0;
+    if (options[9]) { a.strip_done = strip_done.data(); a.sync_errors = &sync_errors; }
     const bool count = options[3] != 0, csvo = fmt == VX_FMT_CSVO;
     const unsigned grid = options[2] ? options[2] : 3;
     for (uint32_t b = 0; b < bands; ++b) {
@@ -253,7 +258,7 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     if (frame_out) std::memcpy(frame_out, frame.data(), frame.size() * sizeof(float4));
     if (frame8_out) std::memcpy(frame8_out, frame8.data(), frame8.size() * 4);
     if (counters_out) std::memcpy(counters_out, &counters, sizeof(Counters));
-    return 0;
+    return sync_errors ? -7 : 0;
 }
 
 // vx_raycast: one trace_picker_kernel launch over n tasks. options: [0] refill threshold, [2] CTAs, [3] count

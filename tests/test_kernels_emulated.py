@@ -48,8 +48,8 @@ def scene_args(world, reg):
                   C.c_uint32(len(mats)), C.c_void_p(tex.ctypes.data), C.c_uint32(tw), C.c_uint32(th), C.c_uint32(layers), C.c_uint32(mips)]
 
 
-def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1, bands=1):
-    return (C.c_uint32 * 9)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size, bands)
+def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1, bands=1, overlap=0):
+    return (C.c_uint32 * 10)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size, bands, overlap)
 
 
 def emu_render(emu, pkg, world, reg, vxp, w, h, **kw):
@@ -108,6 +108,11 @@ def test_emulated_frame_equals_oracle(emu, pkg, ora, terrains, fmt):
     assert got8.tobytes() == want8.tobytes()
     got, _, _ = emu_render(emu, pkg, world, reg, vxp, w, h, tma=1)
     assert got.tobytes() == want.tobytes()
+    # the overlapped wavefront's strip-completion flags: every strip's producers count exactly the pixels its consumer waits for
+    # (emu_render fails if a wait gives up), also with mid-tile refills and on the ragged frame edges
+    for refill in (1, 8):
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, overlap=1)
+        assert got.tobytes() == want.tobytes() and c == cnt
     # the banded wavefront of vx_render_read_rgba8 (per-band macro-block ranges and work counters), also sharded
     _, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, rgba8=1, bands=3)
     assert got8.tobytes() == want8.tobytes() and c == cnt
@@ -349,6 +354,7 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         refill, ctas = int(rng.integers(1, 33)), int(rng.integers(1, 5))
         shadow_refill = int(rng.choice([0, 1, 7, 32]))
         shadows, rgba8 = bool(rng.integers(0, 2)), int(rng.integers(0, 2))
+        overlap = int(rng.integers(0, 2))
         vxp = world_params(pkg, world, w, h, shadows=shadows, selected=(-20.0, 50.0, 174.0) if case % 2 else None)
         want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
         union = np.full((h, w, 4), -1.0, np.float32)
@@ -356,7 +362,7 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         total = {k: 0 for k in cnt}
         for rank in range(size):
             got, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, shadow_refill=shadow_refill, ctas=ctas, rgba8=rgba8, rank=rank,
-                                      size=size | rows, bands=bands)
+                                      size=size | rows, bands=bands, overlap=overlap)
             mine = (got8.view(np.uint32)[..., 0] != 0xdeadbeef) if rgba8 else (got[..., 3] != -1.0)
             union[mine] = got[mine]
             union8[mine] = got8[mine]

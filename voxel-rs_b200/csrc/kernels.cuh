@@ -50,6 +50,10 @@ struct RenderArgs {
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
     uint32_t shadow_refill;       // the same for trace_shadow_kernel
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
+    unsigned int* strip_done;     // non-null: OVERLAPPED wavefront. strip_done[strip] counts the pixels of that 32x4 strip whose hit record is
+                                  // written; shade_kernel runs concurrently with trace_primary_kernel (own stream) and a CTA waits for its
+                                  // strip to be complete instead of for the whole kernel: it fills the SMs the tracing kernel's tail frees
+    unsigned int* sync_errors;    // counts waits of the overlapped wavefront that gave up
     uint32_t tma_writeback;       // shade_kernel: stage the strip's pixels in shared memory and write them back with bulk async
                                   // copies (TMA engine, cp.async.bulk -> SASS UBLKCP), one 512-byte row per copy
 };
@@ -190,6 +194,44 @@ __device__ __forceinline__ void store_pixel(const RenderArgs& a, uint32_t pix, f
     else __stcs(a.frame + pix, c);
 }
 
+// ---- overlapped wavefront: strip completion flags ------------------------------------------------------------------------------
+// Producer side (trace_primary_kernel, after its lanes wrote their hit records): the lanes of the warp that finished a pixel in
+// this round are counted per strip — they normally all belong to one strip, two when a refill straddled tiles. __syncwarp orders
+// the other lanes' stores before the leader's fence; fence + atomic publish them device-wide (release).
+__device__ __forceinline__ void strips_signal(unsigned int* strip_done, bool finished, uint32_t strip) {
+    unsigned fin = __ballot_sync(0xffffffffu, finished);
+    if (!fin) return;
+#ifndef VX_HOST_EMULATION
+    __syncwarp();
+#endif
+    const uint32_t lane = threadIdx.x & 31;
+    while (fin) {
+        const int leader = __ffs(fin) - 1;
+        const uint32_t s = __shfl_sync(0xffffffffu, strip, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, finished && strip == s);
+        if ((int)lane == leader) {
+            __threadfence();
+            atomicAdd(strip_done + s, (unsigned)__popc(same));
+        }
+        fin &= ~same;
+    }
+}
+// Consumer side (shade_kernel, one thread of the CTA): wait until `expected` pixels of the strip are in. Gives up after ~1 s and
+// counts it: a lost producer must show up as an error, never as a hung GPU.
+__device__ __forceinline__ void strip_wait(const unsigned int* strip_done, uint32_t strip, uint32_t expected, unsigned int* sync_errors) {
+    unsigned int v = 0, spins = 0;
+    for (;;) {
+#ifndef VX_HOST_EMULATION
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(strip_done + strip) : "memory");
+#else
+        v = strip_done[strip];
+#endif
+        if (v >= expected) break;
+        __nanosleep(spins < 64 ? 100 : 1000);
+        if (++spins > (1u << 20)) { atomicAdd(sync_errors, 1u); break; }
+    }
+}
+
 // ---- primary rays ------------------------------------------------------------------------------------------------------
 template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
@@ -258,6 +300,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
+        bool finished = false;
         if (state_at_leaf(w.state)) {
             Leaf g;
             if (render_leaf<FMT, COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
@@ -267,13 +310,16 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 __stcs(a.hit0 + slot, make_float4(g.dst, __uint_as_float(g.value), g.u, g.v));
                 __stcs(a.hit1 + slot, make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id)));
                 w.state = ST_IDLE;
+                finished = true;
             } else {
                 walk_skip_leaf<FMT>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
         } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             w.state = ST_IDLE;
+            finished = true;
         }
+        if (a.strip_done) strips_signal(a.strip_done, finished, slot >> 7);
     }
     if (COUNT) flush_counters(a.counters, cnt);
 }
@@ -292,6 +338,11 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
     const bool live = have && gx < a.u.width && gy < a.u.height;
+    if (a.strip_done) {   // overlapped wavefront: this strip's hit records may still be on their way
+        if (threadIdx.x == 0 && have)
+            strip_wait(a.strip_done, strip, min(32u, a.u.width - x0) * min(4u, a.u.height - y0), a.sync_errors);
+        __syncthreads();
+    }
     Counters cnt = {0, 0, 0, 0, 0, 0};
     bool want_shadow = false;
     float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);

@@ -30,6 +30,9 @@ struct VxCtx {
     std::string err;
 
     cudaStream_t s_render = nullptr, s_upload = nullptr, s_picker = nullptr, s_copy = nullptr, s_pick_in = nullptr;
+    cudaStream_t s_aux = nullptr;         // shade_kernel of the overlapped wavefront: runs next to trace_primary_kernel, ordered by strip flags
+    cudaEvent_t e_pre = nullptr, e_k2 = nullptr;
+    unsigned int* d_strip_done = nullptr; // per 32x4-pixel strip: pixels whose hit record is written (overlapped wavefront)
     cudaEvent_t e_band[16] = {};
     cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
@@ -100,7 +103,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 1;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -193,6 +196,9 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaStreamCreateWithFlags(&c->s_picker, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_pick_in, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->e_pre, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->e_k2, cudaEventDisableTiming));
     for (int i = 0; i < 16; ++i) CUC(cudaEventCreateWithFlags(&c->e_band[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_upload, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_render, cudaEventDisableTiming));
@@ -271,6 +277,10 @@ void vx_destroy(VxCtx* c) {
     for (cudaEvent_t ev : c->e_band) if (ev) cudaEventDestroy(ev);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_pick_in) cudaStreamDestroy(c->s_pick_in);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->e_pre) cudaEventDestroy(c->e_pre);
+    if (c->e_k2) cudaEventDestroy(c->e_k2);
+    if (c->d_strip_done) cudaFree(c->d_strip_done);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_results) cudaFree(c->d_results);
     if (c->d_work) cudaFree(c->d_work);
@@ -295,6 +305,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 8: ctx->opt_rgba8_out = value ? 1 : 0; break;
         case 9: ctx->opt_tma = value ? 1 : 0; break;
         case 10: ctx->opt_refill_shadow = value > 32 ? 32 : value; break;
+        case 11: ctx->opt_overlap = value ? 1 : 0; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -581,6 +592,9 @@ static int ensure_wave_buffers(VxCtx* c, size_t slots) {
     if (c->d_sh_pix) cudaFree(c->d_sh_pix);
     c->d_sh_pix = nullptr;
     CU(c, cudaMalloc(&c->d_sh_pix, slots * sizeof(uint32_t)));
+    if (c->d_strip_done) cudaFree(c->d_strip_done);
+    c->d_strip_done = nullptr;
+    CU(c, cudaMalloc(&c->d_strip_done, (slots / 128) * sizeof(unsigned int)));
     c->wave_slots = slots;
     return VX_OK;
 }
@@ -622,26 +636,38 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             const uint64_t per_warp = (uint64_t)owned * 16 / ((uint64_t)(grid < need ? grid : need) * (VX_THREADS / 32));
             a.fetch_tiles = per_warp >= 512 ? 2 : 1;
         }
+        // Overlapped wavefront: the shade kernel goes to its own stream, ordered behind everything BEFORE the tracing kernel but not
+        // behind the tracing kernel itself; its CTAs wait per strip (RenderArgs::strip_done). The tracing kernel's CTAs are all
+        // resident first and fetch work dynamically, so whatever SM slots shade CTAs take, tracing finishes and feeds them.
+        cudaStream_t s2 = a.strip_done ? c->s_aux : c->s_render;
+        if (a.strip_done) {
+            CU(c, cudaEventRecord(c->e_pre, c->s_render));
+            CU(c, cudaStreamWaitEvent(c->s_aux, c->e_pre, 0));
+        }
         k1<<<grid < need ? grid : need, VX_THREADS, smem, c->s_render>>>(a);
         c->launches++;
         if (timed) CU(c, cudaEventRecord(c->t_wave[1], c->s_render));
         // (multi-GPU, peer frame) the pixels go to GPU 0's framebuffer: not before GPU 0 released the previous frame
         if (c->gate_armed) {
             unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
-            flag_wait_kernel<<<1, 32, 0, c->s_render>>>(f, c->gate_slot, 1, c->gate_value, c->d_flags + 63);
+            flag_wait_kernel<<<1, 32, 0, s2>>>(f, c->gate_slot, 1, c->gate_value, c->d_flags + 63);
             c->launches++;
             c->gate_armed = false;
         }
         if (c->gate_event) {   // single-process group: the root's "previous frame consumed" event, no kernel needed
-            CU(c, cudaStreamWaitEvent(c->s_render, c->gate_event, 0));
+            CU(c, cudaStreamWaitEvent(s2, c->gate_event, 0));
             c->gate_event = nullptr;
         }
         // 2. shading -> final pixels + shadow ray list
         const size_t smem2 = smem_bytes(0, false);
-        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
-        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, c->s_render>>>(a);
+        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
+        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
         c->launches++;
-        if (timed) CU(c, cudaEventRecord(c->t_wave[2], c->s_render));
+        if (timed) CU(c, cudaEventRecord(c->t_wave[2], s2));
+        if (a.strip_done) {
+            CU(c, cudaEventRecord(c->e_k2, c->s_aux));
+            CU(c, cudaStreamWaitEvent(c->s_render, c->e_k2, 0));
+        }
         // 3. shadow rays -> final pixels (world.glsl:80-84)
         if (shadows) {
             rc = persistent_grid(c, (const void*)k3, VX_THREADS, smem, &grid);
@@ -697,6 +723,11 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32 + sizeof(Counters), c->s_render));   // work counters + render Counters
+    // overlapped wavefront (vx_set_option 11, default on; needs "finish all 32 rays, then refill" = refill threshold 1 only for its
+    // cost model, the flags themselves count pixels and work with any threshold)
+    a.strip_done = c->opt_overlap ? c->d_strip_done : nullptr;
+    a.sync_errors = c->d_flags + 61;
+    if (a.strip_done) CU(c, cudaMemsetAsync(c->d_strip_done, 0, (size_t)a.macro_x * a.macro_y * 4 * sizeof(unsigned int), c->s_render));
     return VX_OK;
 }
 
@@ -1209,7 +1240,7 @@ int vx_close_peer_sync(VxCtx* c) {
 }
 
 int vx_frame_signal(VxCtx* c, uint32_t slot, uint32_t value) {
-    if (!c || slot >= 62) return fail(c, VX_E_ARG, "vx_frame_signal: bad slot");
+    if (!c || slot >= 61) return fail(c, VX_E_ARG, "vx_frame_signal: bad slot");
     CU(c, cudaSetDevice(c->cfg.device));
     unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
     flag_signal_kernel<<<1, 1, 0, c->s_render>>>(f + slot, value);
@@ -1219,7 +1250,7 @@ int vx_frame_signal(VxCtx* c, uint32_t slot, uint32_t value) {
 }
 
 int vx_frame_wait(VxCtx* c, uint32_t first_slot, uint32_t n_slots, uint32_t value) {
-    if (!c || n_slots == 0 || n_slots > 32 || first_slot + n_slots > 62) return fail(c, VX_E_ARG, "vx_frame_wait: bad slot range");
+    if (!c || n_slots == 0 || n_slots > 32 || first_slot + n_slots > 61) return fail(c, VX_E_ARG, "vx_frame_wait: bad slot range");
     CU(c, cudaSetDevice(c->cfg.device));
     unsigned int* f = c->flags_target ? c->flags_target : c->d_flags;
     flag_wait_kernel<<<1, 32, 0, c->s_render>>>(f, first_slot, n_slots, value, c->d_flags + 63);
@@ -1229,7 +1260,7 @@ int vx_frame_wait(VxCtx* c, uint32_t first_slot, uint32_t n_slots, uint32_t valu
 }
 
 int vx_frame_gate(VxCtx* c, uint32_t slot, uint32_t value) {
-    if (!c || slot >= 62) return fail(c, VX_E_ARG, "vx_frame_gate: bad slot");
+    if (!c || slot >= 61) return fail(c, VX_E_ARG, "vx_frame_gate: bad slot");
     c->gate_armed = true; c->gate_slot = slot; c->gate_value = value;
     return VX_OK;
 }
@@ -1238,7 +1269,9 @@ int vx_frame_sync_errors(VxCtx* c, uint32_t* out) {
     if (!c || !out) return VX_E_ARG;
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->s_render));
-    CU(c, cudaMemcpy(out, c->d_flags + 63, 4, cudaMemcpyDeviceToHost));
+    unsigned int h[3] = {0, 0, 0};   // [61] strip waits of the overlapped wavefront, [62] refused dirty ranges (vx_svo_scatter_errors), [63] frame-flag waits
+    CU(c, cudaMemcpy(h, c->d_flags + 61, sizeof(h), cudaMemcpyDeviceToHost));
+    *out = h[0] + h[2];
     return VX_OK;
 }
 

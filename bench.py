@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--gather", default="p2p8", choices=["p2p8", "p2p", "nccl"], help="N>1: tiles to GPU 0 by peer stores from the render "
                     "kernels as RGBA8 pixels (default) or RGBA32F pixels (p2p), or by pack + NCCL send/recv + unpack (nccl)")
     ap.add_argument("--no-overlap", action="store_true", help="serialized wavefront: shade_kernel starts only after trace_primary_kernel has finished (A/B)")
+    ap.add_argument("--overlap", action="store_true", help="overlapped wavefront whatever the launch size (default: only for small launches)")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--bands", type=int, default=3, help="e2e: bands of vx_render_read_rgba8 (render/read-back overlap)")
@@ -289,6 +290,8 @@ def main():
         svo.set_option(pkg.OPT_TMA, 1)
     if args.no_overlap:
         svo.set_option(pkg.OPT_OVERLAP, 0)
+    if args.overlap:
+        svo.set_option(pkg.OPT_OVERLAP, 1)
     svo.update(world)
     vxp = frame_params(pkg, world, args)
     shard = (rank, n_gpus) if not args.sim_shard else (0, args.sim_shard)
@@ -567,7 +570,7 @@ def main():
             "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
             "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 144 MiB device fill (> 126 MB L2) inside the timed region",
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)" + ("" if args.no_overlap else
-                       "; shade runs next to trace_primary on its own stream, its CTAs wait per 32x4-pixel strip (strip-completion flags)"), "ctas_per_sm": args.ctas_per_sm or 8,
+                       "; for small launches (shards, small frames) shade runs next to trace_primary on its own stream, its CTAs wait per 32x4-pixel strip"), "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
             "sim_shard": args.sim_shard or None, "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +

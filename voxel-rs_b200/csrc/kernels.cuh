@@ -197,7 +197,7 @@ __device__ __forceinline__ void store_pixel(const RenderArgs& a, uint32_t pix, f
 // ---- overlapped wavefront: strip completion flags ------------------------------------------------------------------------------
 // Producer side (trace_primary_kernel, after its lanes wrote their hit records): the lanes of the warp that finished a pixel in
 // this round are counted per strip — they normally all belong to one strip, two when a refill straddled tiles. __syncwarp orders
-// the other lanes' stores before the leader's fence; fence + atomic publish them device-wide (release).
+// the other lanes' stores before the leader's release-reduction, which publishes them device-wide.
 __device__ __forceinline__ void strips_signal(unsigned int* strip_done, bool finished, uint32_t strip) {
     unsigned fin = __ballot_sync(0xffffffffu, finished);
     if (!fin) return;
@@ -210,8 +210,12 @@ __device__ __forceinline__ void strips_signal(unsigned int* strip_done, bool fin
         const uint32_t s = __shfl_sync(0xffffffffu, strip, leader);
         const unsigned same = __ballot_sync(0xffffffffu, finished && strip == s);
         if ((int)lane == leader) {
-            __threadfence();
-            atomicAdd(strip_done + s, (unsigned)__popc(same));
+#ifndef VX_HOST_EMULATION
+            // release-reduction: orders this warp's record stores before the count without the full fence of __threadfence()
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(strip_done + s), "r"((unsigned)__popc(same)) : "memory");
+#else
+            strip_done[s] += (unsigned)__popc(same);
+#endif
         }
         fin &= ~same;
     }

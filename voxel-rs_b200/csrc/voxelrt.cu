@@ -103,7 +103,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 1;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -305,7 +305,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 8: ctx->opt_rgba8_out = value ? 1 : 0; break;
         case 9: ctx->opt_tma = value ? 1 : 0; break;
         case 10: ctx->opt_refill_shadow = value > 32 ? 32 : value; break;
-        case 11: ctx->opt_overlap = value ? 1 : 0; break;
+        case 11: ctx->opt_overlap = value > 2 ? 2 : value; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -688,6 +688,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
 }
 
 #define VX_MAX_BANDS 16
+#define VX_OVERLAP_TILES 24
 
 // Argument checks + everything of RenderArgs that does not depend on the band.
 static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, RenderArgs& a, const char* who) {
@@ -725,7 +726,16 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32 + sizeof(Counters), c->s_render));   // work counters + render Counters
     // overlapped wavefront (vx_set_option 11, default on; needs "finish all 32 rays, then refill" = refill threshold 1 only for its
     // cost model, the flags themselves count pixels and work with any threshold)
-    a.strip_done = c->opt_overlap ? c->d_strip_done : nullptr;
+    // (vx_set_option 11: 0 off, 1 on, 2 = default: on when the launch is small enough for kernel tails to matter — a shard of a
+    // frame, a small frame: fewer than VX_OVERLAP_TILES warp tiles per resident warp; a whole 4K frame on one GPU has 55 and loses
+    // 3 % to the signalling, 1/8 of it has 7 and gains 6 %, profiles/r02_overlap.md)
+    {
+        const uint32_t size = a.shard_size ? a.shard_size : 1;
+        const uint64_t tiles = (uint64_t)a.macro_x * a.macro_y * 16 / size;
+        const uint64_t resident_warps = (uint64_t)c->sm_count * 8 * (VX_THREADS / 32);
+        const bool on = c->opt_overlap == 1 || (c->opt_overlap == 2 && tiles < VX_OVERLAP_TILES * resident_warps);
+        a.strip_done = on ? c->d_strip_done : nullptr;
+    }
     a.sync_errors = c->d_flags + 61;
     if (a.strip_done) CU(c, cudaMemsetAsync(c->d_strip_done, 0, (size_t)a.macro_x * a.macro_y * 4 * sizeof(unsigned int), c->s_render));
     return VX_OK;

@@ -77,6 +77,7 @@ def lib():
     L.vxo_render_steps.argtypes = scene + [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, P, C.c_int]; L.vxo_render_steps.restype = None
     L.vxo_to_rgba8.argtypes = [P, C.c_uint64, P]; L.vxo_to_rgba8.restype = None
     L.vxo_max_threads.argtypes = []; L.vxo_max_threads.restype = C.c_int
+    L.vxo_set_clip.argtypes = [C.c_int]; L.vxo_set_clip.restype = None
     _lib = L
     return L
 
@@ -163,6 +164,12 @@ def to_rgba8(rgba32f):
     out = np.zeros(a.shape, dtype=np.uint8)
     lib().vxo_to_rgba8(_ptr(a), a.size // 4, _ptr(out))
     return out
+
+
+def set_clip(on):
+    """Product extension (off by default = the shader as written): stop a ray once it has left the occupied box of the world, like
+    the CUDA kernels do (vx_set_option 12). Results are unchanged by construction; only the iteration counters follow it."""
+    lib().vxo_set_clip(1 if on else 0)
 
 
 def max_threads():

@@ -200,6 +200,10 @@ struct Scene {
     uint32_t n_materials;
     const Texture* tex;
     int format = 0;              // 0 = ESVO (svo.esvo.glsl), 1 = CSVO (svo.csvo.glsl): the shader's `#define SVO_TYPE`
+    // NOT part of the reference: the product's world-box clipping (traverse.cuh Clip), restated so that iteration counters of
+    // the two can be compared. 0 = off (the shader as written), 1 = box {clo, chi} in [1,2) space, 2 = the world is empty
+    int clip_mode = 0;
+    float clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0};
     float octree_scale() const { float f; std::memcpy(&f, world, 4); return f; }
     uint32_t desc(uint32_t i) const { uint32_t v; std::memcpy(&v, world + 4 + (uint64_t)i * 4, 4); return v; }
     // CSVO: `uint root_ptr` at byte 4, `uint descriptors[]` from byte 8 (svo.csvo.glsl:1-5). A word that does not lie
@@ -237,6 +241,19 @@ static void intersect_octree(const Scene& s, vec3 ro, vec3 rd, float max_dst, bo
     else intersect_octree_esvo(s, ro, rd, max_dst, cast_translucent, res, cnt, trace);
 }
 
+// World-box clipping of the product (NOT in the shader): the ray parameter after which the ray has left the box that holds every
+// voxel. Same operations, in the same order, as walk_init in voxel-rs_b200/csrc/traverse.cuh. +inf when clipping is off.
+static inline float clip_limit(const Scene& s, vec3 ro, vec3 rd, vec3 t_coef) {
+    if (s.clip_mode == 2) return -1.0f;
+    if (s.clip_mode != 1) return i2f(0x7f800000);
+    const float ix = rd.x > 0 ? -t_coef.x : t_coef.x, iy = rd.y > 0 ? -t_coef.y : t_coef.y, iz = rd.z > 0 ? -t_coef.z : t_coef.z;
+    const float ex = fmaxf((s.clo[0] - ro.x) * ix, (s.chi[0] - ro.x) * ix);
+    const float ey = fmaxf((s.clo[1] - ro.y) * iy, (s.chi[1] - ro.y) * iy);
+    const float ez = fmaxf((s.clo[2] - ro.z) * iz, (s.chi[2] - ro.z) * iz);
+    const float te = fminf(fminf(ex, ey), ez);
+    return te * 1.0009765625f + 3.814697265625e-06f;
+}
+
 // svo.esvo.glsl:50-393. `trace` (optional) reproduces OCTREE_RAYTRACE_DEBUG_FN of svo.test.glsl.
 static void intersect_octree_esvo(const Scene& s, vec3 ro, vec3 rd, float max_dst, bool cast_translucent,
                                   OctreeResult& res, Counters* cnt, Trace* trace) {
@@ -269,6 +286,7 @@ static void intersect_octree_esvo(const Scene& s, vec3 ro, vec3 rd, float max_ds
 
     vec3 t_coef = v3(1.0f / -fabsf(rd.x), 1.0f / -fabsf(rd.y), 1.0f / -fabsf(rd.z));   // :105
     vec3 t_bias = v3(t_coef.x * ro.x, t_coef.y * ro.y, t_coef.z * ro.z);               // :106
+    const float clip_t = clip_limit(s, ro, rd, t_coef);                               // (product extension, off by default)
 
     int octant_mask = 0;                                                // :121-124
     if (rd.x > 0) { octant_mask ^= 1; t_bias.x = 3.0f * t_coef.x - t_bias.x; }
@@ -288,6 +306,7 @@ static void intersect_octree_esvo(const Scene& s, vec3 ro, vec3 rd, float max_ds
 
     for (int i = 0; i < MAX_STEPS; ++i) {                               // :152
         if (max_dst >= 0 && t_min > max_dst) return;                    // :153-156
+        if (t_min > clip_t) return;                                     // (product extension: the ray has left the occupied box)
         if (cnt) cnt->steps++;
 
         vec3 t_corner = v3(fmaf(pos.x, t_coef.x, -t_bias.x), fmaf(pos.y, t_coef.y, -t_bias.y), fmaf(pos.z, t_coef.z, -t_bias.z));  // :159 (FMA, :97-99)
@@ -520,6 +539,7 @@ static void intersect_octree_csvo(const Scene& s, vec3 ro, vec3 rd, float max_ds
 
     vec3 t_coef = v3(1.0f / -fabsf(rd.x), 1.0f / -fabsf(rd.y), 1.0f / -fabsf(rd.z));   // :226
     vec3 t_bias = v3(t_coef.x * ro.x, t_coef.y * ro.y, t_coef.z * ro.z);
+    const float clip_t = clip_limit(s, ro, rd, t_coef);                               // (product extension, off by default)
     int octant_mask = 0;                                                // :242-245
     if (rd.x > 0) { octant_mask ^= 1; t_bias.x = 3.0f * t_coef.x - t_bias.x; }
     if (rd.y > 0) { octant_mask ^= 2; t_bias.y = 3.0f * t_coef.y - t_bias.y; }
@@ -542,6 +562,7 @@ static void intersect_octree_csvo(const Scene& s, vec3 ro, vec3 rd, float max_ds
 
     for (int i = 0; i < MAX_STEPS; ++i) {
         if (max_dst >= 0 && t_min > max_dst) return;
+        if (t_min > clip_t) return;                                     // (product extension)
         if (cnt) cnt->steps++;
 
         vec3 t_corner = v3(fmaf(pos.x, t_coef.x, -t_bias.x), fmaf(pos.y, t_coef.y, -t_bias.y), fmaf(pos.z, t_coef.z, -t_bias.z));
@@ -803,12 +824,63 @@ uint64_t vxo_texture_level(const VxoTexture* t, uint32_t level, uint8_t* out) {
     return v.size();
 }
 
+// Occupied box of the world at the granularity of octree level L = min(depth, 6): an independent (recursive, CPU) statement of what
+// svo_bounds_kernel computes on the device. b = {min xyz, max xyz (exclusive)} in voxel units; min > max = nothing found.
+static void bounds_mark(uint32_t b[6], uint32_t depth, uint32_t level, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t cell = 1u << (depth - level);
+    const uint32_t c[3] = {x * cell, y * cell, z * cell};
+    for (int k = 0; k < 3; ++k) { if (c[k] < b[k]) b[k] = c[k]; if (c[k] + cell > b[3 + k]) b[3 + k] = c[k] + cell; }
+}
+static void bounds_walk_esvo(const vxo::Scene& s, uint32_t ptr, uint32_t pidx, uint32_t level, uint32_t x, uint32_t y, uint32_t z, uint32_t depth,
+                             uint32_t L, uint32_t b[6]) {
+    uint32_t d = s.desc(ptr + pidx / 2);
+    if (pidx % 2) d >>= 16;
+    const uint32_t child_mask = (d >> 8) & 0xffu, leaf_mask = d & 0xffu;
+    for (uint32_t i = 0; i < 8; ++i) {
+        if (!((child_mask >> i) & 1u)) continue;
+        const uint32_t cx = x * 2 + (i & 1u), cy = y * 2 + ((i >> 1) & 1u), cz = z * 2 + ((i >> 2) & 1u);
+        if (((leaf_mask >> i) & 1u) || level + 1 == L) { bounds_mark(b, depth, level + 1, cx, cy, cz); continue; }
+        bounds_walk_esvo(s, vxo::get_octant_ptr(s, ptr, pidx), i, level + 1, cx, cy, cz, depth, L, b);
+    }
+}
+static void bounds_walk_csvo(const vxo::Scene& s, uint32_t ptr, uint32_t node_depth, uint32_t level, uint32_t x, uint32_t y, uint32_t z,
+                             uint32_t depth, uint32_t L, uint32_t b[6]) {
+    for (uint32_t i = 0; i < 8; ++i) {
+        bool crossed = false;
+        uint32_t next = vxo::csvo_read_next_ptr(s, ptr, node_depth, i, crossed);
+        if (next == vxo::INVALID_PTR) continue;
+        const uint32_t cx = x * 2 + (i & 1u), cy = y * 2 + ((i >> 1) & 1u), cz = z * 2 + ((i >> 2) & 1u);
+        if (node_depth < 2 || level + 1 == L) { bounds_mark(b, depth, level + 1, cx, cy, cz); continue; }
+        uint32_t nd = node_depth - 1;
+        if (crossed) {                                                  // svo.csvo.glsl:404-411
+            nd = vxo::csvo_read_byte(s, next);
+            next += 5 + vxo::csvo_read_uint(s, next + 1);
+        }
+        bounds_walk_csvo(s, next, nd, level + 1, cx, cy, cz, depth, L, b);
+    }
+}
+static int g_clip = 0;
+void vxo_set_clip(int on) { g_clip = on; }
+
 static vxo::Scene make_scene(const uint8_t* world, uint64_t world_len, const void* materials, uint32_t n_materials, const VxoTexture* tex,
                              int svo_format) {
     vxo::Scene s;
     s.world = world; s.world_len = world_len;
     s.materials = (const vxo::Material*)materials; s.n_materials = n_materials; s.tex = &tex->t;
     s.format = svo_format;
+    if (g_clip) {
+        const float scale = s.octree_scale();
+        uint32_t bits; std::memcpy(&bits, &scale, 4);
+        const uint32_t depth = 127u - ((bits >> 23) & 0xffu);
+        uint32_t b[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+        if (depth >= 1 && depth <= 23) {
+            const uint32_t L = depth < 6 ? depth : 6;
+            if (svo_format == 1) bounds_walk_csvo(s, s.csvo_root_ptr(), depth, 0, 0, 0, 0, depth, L, b);
+            else bounds_walk_esvo(s, 0, 0, 0, 0, 0, 0, depth, L, b);
+            s.clip_mode = (b[0] >= b[3] || b[1] >= b[4] || b[2] >= b[5]) ? 2 : 1;
+            for (int k = 0; k < 3; ++k) { s.clo[k] = (float)b[k] * scale + 1.0f; s.chi[k] = (float)b[3 + k] * scale + 1.0f; }
+        }
+    }
     return s;
 }
 
@@ -817,6 +889,7 @@ void vxo_debug_cast(const uint8_t* world, uint64_t world_len, const void* materi
                     const float pos[3], const float dir[3], float max_dst, uint32_t cast_translucent,
                     vxo::OctreeResult* result, vxo::DebugFrame* frames, uint32_t frames_cap, uint32_t* n_frames) {
     vxo::Scene s = make_scene(world, world_len, materials, n_materials, tex, svo_format);
+    s.clip_mode = 0;   // svo.test.glsl: every iteration of the shader, whatever vxo_set_clip says
     vxo::Trace tr{frames, frames_cap, -1};
     vxo::intersect_octree(s, vxo::v3(pos[0], pos[1], pos[2]), vxo::v3(dir[0], dir[1], dir[2]), max_dst, cast_translucent != 0,
                           *result, nullptr, &tr);

@@ -108,6 +108,8 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline void __nanosleep(unsigned) {}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 static inline unsigned long long atomicAnd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o & v; return o; }
 
 // ---- warp collectives (full masks only, which is all the kernels use) ----

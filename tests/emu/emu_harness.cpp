@@ -91,8 +91,10 @@ struct Device {   // what VxCtx holds on the GPU
     TexInfo texinfo{};
     float unorm[256];
     unsigned long long opaque_materials = 0;
+    uint32_t bounds[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 0, 0};   // svo_bounds_kernel (refresh_bounds in voxelrt.cu)
 };
 
+void refresh_bounds(Device& d);
 void upload(Device& d, const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
             const uint8_t* rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels) {
     d.fmt = (uint32_t)fmt; d.depth = depth;
@@ -146,6 +148,17 @@ void upload(Device& d, const uint8_t* world, uint64_t world_bytes, int fmt, uint
         }
         if (ok) d.opaque_materials |= 1ull << i;
     }
+    refresh_bounds(d);
+}
+
+Scene make_scene(const Device& d);
+void refresh_bounds(Device& d) {      // voxelrt.cu refresh_bounds
+    const uint32_t L = d.depth < 6 ? d.depth : 6;
+    const unsigned blocks = ((1u << (3 * L)) + 255) / 256;
+    Scene s = make_scene(d);
+    emu::launch(blocks ? blocks : 1, 256, [&] {
+        if (d.fmt == VX_FMT_CSVO) svo_bounds_kernel<VX_FMT_CSVO>(s, d.bounds); else svo_bounds_kernel<VX_FMT_ESVO>(s, d.bounds);
+    });
 }
 
 Scene make_scene(const Device& d) {   // voxelrt.cu make_scene
@@ -162,6 +175,7 @@ Scene make_scene(const Device& d) {   // voxelrt.cu make_scene
     const uint32_t levels = d.depth + (d.fmt == VX_FMT_CSVO ? 3 : 1);
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     s.stack_max_off = (s.stack_levels - 1u) * VX_STACK_STRIDE;
+    s.bounds = d.bounds;
     return s;
 }
 

@@ -18,6 +18,17 @@ from test_oracle_golden import check_frames, check_result, close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _oracle_follows_the_products_clip(ora):
+    """The kernels stop a ray once it has left the occupied box of the world (vx_set_option 12, on by default): results are the
+    shader's bit for bit, the iteration counters are smaller. The oracle restates that extension when asked, so that counters can
+    still be compared one to one; it is switched off again for every other test (the oracle's own goldens run the shader as written)."""
+    ora.set_clip(True)
+    yield
+    ora.set_clip(False)
+
+
+
 def make_svo(pkg, reg, world, size_mb=8, w=640, h=490, rays=1 << 20, flags=0):
     svo = pkg.Svo(reg, size_mb=size_mb, max_width=w, max_height=h, max_rays=rays, flags=flags | world.svo_flags)
     world.mark_all_dirty()   # a fresh GPU buffer needs the whole RangeBuffer, not just the changes since the last update

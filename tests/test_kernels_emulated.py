@@ -18,6 +18,16 @@ EMU = os.path.join(HERE, "emu")
 ROOT = os.path.dirname(HERE)
 
 
+@pytest.fixture(autouse=True)
+def _oracle_follows_the_products_clip(ora):
+    """The kernels stop a ray once it has left the occupied box of the world (vx_set_option 12, on by default): results are the
+    shader's bit for bit, the iteration counters are smaller. The oracle restates that extension when asked, so that counters can
+    still be compared one to one; it is switched off again for every other test (the oracle's own goldens run the shader as written)."""
+    ora.set_clip(True)
+    yield
+    ora.set_clip(False)
+
+
 @pytest.fixture(scope="module")
 def emu(pkg):
     src = [os.path.join(EMU, "emu_harness.cpp"), os.path.join(EMU, "cuda_runtime.h"), os.path.join(ROOT, "include", "voxelrt.h"),

@@ -299,6 +299,7 @@ int vx_group_svo_commit(VxGroup* g, float octree_scale, const VxRange* dirty, ui
             c->launches++;
             GCU(g, cudaGetLastError());
             c->have_svo = true;
+            if (refresh_bounds(c, depth)) return gfail(g, VX_E_CUDA, "vx_group_svo_commit: %s", c->err.c_str());
         }
         GCU(g, cudaEventRecord(c->e_upload, c->s_upload));
         c->stats.used_bytes = used_bytes; c->stats.depth = depth;

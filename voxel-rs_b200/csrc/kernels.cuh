@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
+    const Clip clip = load_clip(a.scene, octree_scale);
     float* cold = sm.cold;   // 0-2 origin, 3-5 direction (both in [1,2) space / epsilon-clamped)
     Counters cnt = {0, 0, 0, 0, 0, 0};
 
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 if (gx < a.u.width && gy < a.u.height) {
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-                    walk_init<FMT>(w, a.scene, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
+                    walk_init<FMT>(w, a.scene, clip, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         bool finished = false;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
+    const Clip clip = load_clip(a.scene, octree_scale);
     const uint32_t n = *a.shadow_count;
     float* cold = sm.cold;
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 entry = run_base + next + my_rank;
                 const float4 s0 = __ldcs(a.sh0 + entry);
                 float rox, roy, roz, rdx, rdy, rdz;
-                walk_init<FMT>(w, a.scene, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
+                walk_init<FMT>(w, a.scene, clip, octree_scale, s0.x, s0.y, s0.z, -a.u.lx, -a.u.ly, -a.u.lz, -1.0f, rox, roy, roz, rdx, rdy, rdz);   // world.glsl:82
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 lit = s0.w;
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, false, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.shadow_refill, __popc(busy)));
+        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.shadow_refill, __popc(busy)));
 
         if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = load_octree_scale<FMT>(a.scene);
     const float inv_scale = 1.0f / octree_scale;
+    const Clip clip = load_clip(a.scene, octree_scale);
     float* cold = sm.cold;
     Counters cnt = {0, 0, 0, 0, 0, 0};
     unsigned long long run_base = 0;
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
                 my_task = run_base + next + my_rank;
                 const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
                 float rox, roy, roz, rdx, rdy, rdz;
-                walk_init<FMT>(w, a.scene, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
+                walk_init<FMT>(w, a.scene, clip, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
                 cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                 cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                 if (COUNT) cnt.primary_rays++;
@@ -613,7 +616,8 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
     Walk w;
     Counters cnt = {0, 0, 0, 0, 0, 0};
     float rox, roy, roz, rdx, rdy, rdz;
-    walk_init<FMT>(w, s, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst, rox, roy, roz, rdx, rdy, rdz);
+    Clip no_clip; no_clip.mode = 0;   // the debug cast reproduces every iteration of the shader
+    walk_init<FMT>(w, s, no_clip, octree_scale, a.pos[0], a.pos[1], a.pos[2], a.dir[0], a.dir[1], a.dir[2], a.max_dst, rox, roy, roz, rdx, rdy, rdz);
     uint32_t ptr = 0, pidx = 0;
     uint32_t ptr_stack[VX_MAX_SCALE + 1], pidx_stack[VX_MAX_SCALE + 1];
     for (int i = 0; i <= VX_MAX_SCALE; ++i) { ptr_stack[i] = 0; pidx_stack[i] = 0; }
@@ -712,6 +716,52 @@ __global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsign
     }
     __syncthreads();
     __threadfence_system();
+}
+
+// ---- occupied box of the SVO (Clip) -----------------------------------------------------------------------------------------
+// One thread per cell of the octree level L = min(depth, 6) (chunk granularity for the default world). A thread follows its cell's
+// path from the root and, if the path does not end in an empty child, grows the box by the cell it stopped at: its level-L cell,
+// or the coarser cell of a leaf met on the way. Most threads stop after one or two node reads. bounds = {min xyz = 0xffffffff,
+// max xyz = 0} before the launch. Runs on the upload stream after every change of the world buffer.
+template <int FMT>
+__global__ void __launch_bounds__(256) svo_bounds_kernel(Scene s, uint32_t* bounds) {
+    const float octree_scale = load_octree_scale<FMT>(s);
+    const uint32_t depth = 127u - ((__float_as_uint(octree_scale) >> 23) & 0xffu);
+    if (depth == 0u || depth > 23u) return;
+    const uint32_t L = depth < 6u ? depth : 6u;
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (1u << (3u * L))) return;
+    const uint32_t mask = (1u << L) - 1u;
+    const uint32_t cx = id & mask, cy = (id >> L) & mask, cz = (id >> (2u * L)) & mask;
+    Walk w;
+    w.mat_ptr = 0xffffffffu; w.preleaf = 0xffffffffu; w.hdr = 0;
+    if (FMT == VX_FMT_CSVO) {
+        w.rec = __ldg(s.desc - 1);
+        w.desc = depth;
+        w.hdr = csvo_header(s, w.rec, w.desc);
+    } else {
+        const uint32_t w0 = ld_desc(s, 0), w4 = ld_desc(s, 4);
+        w.desc = w0 & 0xffffu;
+        const uint32_t root = (w4 & 0x80000000u) ? (4u + (w4 & 0x7fffffffu)) : w4;
+        w.rec = root < s.max_rec ? root : s.max_rec;
+    }
+    for (uint32_t k = 1; k <= L; ++k) {
+        const uint32_t sh = L - k;
+        w.ci = ((cx >> sh) & 1u) | (((cy >> sh) & 1u) << 1) | (((cz >> sh) & 1u) << 2);
+        bool is_child, is_leaf;
+        walk_decode<FMT>(w, is_child, is_leaf);
+        if (!is_child) return;
+        if (is_leaf || k == L) {
+            // only ONE thread per stopping cell reports it: the one whose finer coordinates are all zero
+            if (((cx | cy | cz) & ((1u << sh) - 1u)) != 0u) return;
+            const uint32_t cell = 1u << (depth - k);
+            const uint32_t x = (cx >> sh) * cell, y = (cy >> sh) * cell, z = (cz >> sh) * cell;
+            atomicMin(bounds + 0, x); atomicMin(bounds + 1, y); atomicMin(bounds + 2, z);
+            atomicMax(bounds + 3, x + cell); atomicMax(bounds + 4, y + cell); atomicMax(bounds + 5, z + cell);
+            return;
+        }
+        walk_descend<FMT>(w, s);
+    }
 }
 
 // ---- small utility kernels ---------------------------------------------------------------------------------------------

@@ -69,6 +69,8 @@ struct Scene {
     const float* __restrict__ unorm;     // 256-entry b / 255.0f table in global memory (copied into shared memory per CTA)
     uint32_t stack_levels;               // entries of the per-thread traversal stack (= SVO depth + 1, <= 23)
     uint32_t stack_max_off;              // (stack_levels - 1) * VX_STACK_STRIDE: byte offset of the last stack slot (Walk::soff clamp)
+    const uint32_t* __restrict__ bounds; // occupied box of the SVO in voxel units {min x,y,z, max x,y,z (exclusive)}, written by svo_bounds_kernel
+                                         // after every commit; null = rays are not clipped against it
     unsigned long long opaque_materials; // bit m set (m < 64): every texel of the three face textures of material m has alpha > 0,
                                          // so a leaf of that material is accepted by the translucency rule (:241-242) without sampling
 };
@@ -265,11 +267,34 @@ __device__ __forceinline__ uint32_t csvo_read_leaf(const Scene& s, uint32_t mate
     return csvo_read_uint(s, material_section_ptr + material_section_offset * 4u + (__popc(v0) + __popc(v1)) * 4u);
 }
 
+// Occupied box of the world in [1,2) space. A ray is over once it has left the box: nothing it could hit lies outside, so the
+// shader's remaining iterations (through empty cells to the edge of the octree, :152-392) can only end in a miss — the traversal
+// stops there with that miss. Same output bit for bit, fewer iterations (oracle/oracle.cpp restates it to keep the counters
+// comparable; vx_set_option 12 turns it off).
+struct Clip {
+    float lox, loy, loz, hix, hiy, hiz;
+    int mode;   // 0 off, 1 box, 2 the world is empty
+};
+__device__ __forceinline__ Clip load_clip(const Scene& s, float octree_scale) {
+    Clip c;
+    c.mode = 0;
+    c.lox = c.loy = c.loz = c.hix = c.hiy = c.hiz = 0.0f;
+    if (s.bounds) {
+        const uint32_t x0 = __ldg(s.bounds), y0 = __ldg(s.bounds + 1), z0 = __ldg(s.bounds + 2);
+        const uint32_t x1 = __ldg(s.bounds + 3), y1 = __ldg(s.bounds + 4), z1 = __ldg(s.bounds + 5);
+        if (x0 >= x1 || y0 >= y1 || z0 >= z1) { c.mode = 2; return c; }
+        c.mode = 1;
+        c.lox = (float)x0 * octree_scale + 1.0f; c.loy = (float)y0 * octree_scale + 1.0f; c.loz = (float)z0 * octree_scale + 1.0f;
+        c.hix = (float)x1 * octree_scale + 1.0f; c.hiy = (float)y1 * octree_scale + 1.0f; c.hiz = (float)z1 * octree_scale + 1.0f;
+    }
+    return c;
+}
+
 // svo.esvo.glsl:52-149 / svo.csvo.glsl:171-223. (ox,oy,oz) in SVO voxel space. Also returns the [1,2)-space origin and the epsilon-clamped
 // direction (the leaf evaluation needs them, :210-224, :252-258).
 template <int FMT>
-__device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_scale, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          float max_dst, float& rox, float& roy, float& roz, float& rdx, float& rdy, float& rdz) {
+__device__ __forceinline__ void walk_init(Walk& w, const Scene& s, const Clip& clip, float octree_scale, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, float max_dst, float& rox, float& roy, float& roz, float& rdx, float& rdy, float& rdz) {
     rox = ox * octree_scale + 1.0f; roy = oy * octree_scale + 1.0f; roz = oz * octree_scale + 1.0f;
     const float md = max_dst * octree_scale;
     w.limit = (md >= 0.0f) ? md : __int_as_float(0x7f800000);   // "max_dst >= 0 && t_min > max_dst" == "t_min > limit"
@@ -283,6 +308,19 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, float octree_
 
     w.tcx = 1.0f / -fabsf(dx); w.tcy = 1.0f / -fabsf(dy); w.tcz = 1.0f / -fabsf(dz);
     w.tbx = w.tcx * rox; w.tby = w.tcy * roy; w.tbz = w.tcz * roz;
+
+    if (clip.mode == 1) {
+        // exit time of the occupied box (slab test; 1 / d_k = -+t_coef_k), widened by 2^-10 relative + 2^-18 absolute: a voxel at
+        // the very face of the box is entered no later than the box is left, whatever the rounding of the two
+        const float ix = dx > 0 ? -w.tcx : w.tcx, iy = dy > 0 ? -w.tcy : w.tcy, iz = dz > 0 ? -w.tcz : w.tcz;
+        const float ex = fmaxf((clip.lox - rox) * ix, (clip.hix - rox) * ix);
+        const float ey = fmaxf((clip.loy - roy) * iy, (clip.hiy - roy) * iy);
+        const float ez = fmaxf((clip.loz - roz) * iz, (clip.hiz - roz) * iz);
+        const float te = fminf(fminf(ex, ey), ez);
+        w.limit = fminf(w.limit, te * 1.0009765625f + 3.814697265625e-06f);
+    } else if (clip.mode == 2) {
+        w.limit = -1.0f;
+    }
 
     uint32_t octant_mask = 0;
     if (dx > 0) { octant_mask ^= 1; w.tbx = 3.0f * w.tcx - w.tbx; }

@@ -33,6 +33,7 @@ struct VxCtx {
     cudaStream_t s_aux = nullptr;         // shade_kernel of the overlapped wavefront: runs next to trace_primary_kernel, ordered by strip flags
     cudaEvent_t e_pre = nullptr, e_k2 = nullptr;
     unsigned int* d_strip_done = nullptr; // per 32x4-pixel strip: pixels whose hit record is written (overlapped wavefront)
+    uint32_t* d_bounds = nullptr;         // occupied box of the SVO in voxel units (svo_bounds_kernel), read by the trace kernels (Clip)
     cudaEvent_t e_band[16] = {};
     cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
     cudaEvent_t e_upload = nullptr, e_render = nullptr, e_picker = nullptr;
@@ -103,7 +104,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2, opt_clip = 1;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -135,6 +136,7 @@ static Scene make_scene(const VxCtx* c) {
     uint32_t levels = c->stats.depth + (c->fmt == VX_FMT_CSVO ? 3 : 1);   // CSVO: the oracle's stack policy for out-of-spec descents
     s.stack_levels = levels < 2 ? 2 : (levels > VX_MAX_SCALE ? VX_MAX_SCALE : levels);
     s.stack_max_off = (s.stack_levels - 1u) * VX_STACK_STRIDE;
+    s.bounds = c->opt_clip ? c->d_bounds : nullptr;
     return s;
 }
 static size_t stack_smem_bytes(const Scene& s) { return smem_bytes(s.stack_levels); }
@@ -225,6 +227,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     }
     CUC(cudaMalloc(&c->d_flags, 64 * sizeof(unsigned int)));
     CUC(cudaMemsetAsync(c->d_flags, 0, 64 * sizeof(unsigned int), c->s_upload));
+    CUC(cudaMalloc(&c->d_bounds, 8 * sizeof(uint32_t)));
+    CUC(cudaMemsetAsync(c->d_bounds, 0, 8 * sizeof(uint32_t), c->s_upload));   // min = max = 0: an empty world until the first commit
     CUC(cudaMalloc(&c->d_unorm, 256 * sizeof(float)));
     unorm_kernel<<<1, 256, 0, c->s_upload>>>(c->d_unorm);
     // one block: [0..7] u64 (picker run counter at [4], chunk bump pointer at [6..7]) | 16 bands x 8 u32 render work counters | the
@@ -266,6 +270,7 @@ void vx_destroy(VxCtx* c) {
     if (c->d_texels) cudaFree(c->d_texels);
     if (c->d_texinfo) cudaFree(c->d_texinfo);
     if (c->d_unorm) cudaFree(c->d_unorm);
+    if (c->d_bounds) cudaFree(c->d_bounds);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
     if (c->d_hit0) cudaFree(c->d_hit0);
@@ -306,6 +311,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 9: ctx->opt_tma = value ? 1 : 0; break;
         case 10: ctx->opt_refill_shadow = value > 32 ? 32 : value; break;
         case 11: ctx->opt_overlap = value > 2 ? 2 : value; break;
+        case 12: ctx->opt_clip = value ? 1 : 0; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -414,6 +420,26 @@ static void install_l2_window(VxCtx* c) {
     cudaGetLastError();   // a refused window is a lost optimisation, not an error
 }
 
+// The occupied box of the world for ray clipping (traverse.cuh Clip): recomputed on the upload stream after every change of the
+// world buffer, before the upload event that frames and ray batches wait for. 1024 CTAs, most threads stop after a read or two.
+static int refresh_bounds(VxCtx* c, uint32_t depth) {
+    static const uint32_t init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    static uint32_t* pinned = nullptr;   // cudaMemcpyAsync from pageable memory would stage synchronously
+    if (!pinned) {
+        if (cudaHostAlloc(&pinned, sizeof(init), cudaHostAllocPortable) != cudaSuccess) return fail(c, VX_E_CUDA, "refresh_bounds: cudaHostAlloc failed");
+        std::memcpy(pinned, init, sizeof(init));
+    }
+    CU(c, cudaMemcpyAsync(c->d_bounds, pinned, sizeof(init), cudaMemcpyHostToDevice, c->s_upload));
+    Scene s = make_scene(c);
+    const uint32_t L = depth < 6 ? depth : 6;   // (the kernel derives the depth from the buffer's scale itself; this only sizes the grid)
+    const unsigned blocks = depth >= 1 && depth <= 23 ? ((1u << (3 * L)) + 255) / 256 : 1024;
+    if (c->fmt == VX_FMT_CSVO) svo_bounds_kernel<VX_FMT_CSVO><<<blocks, 256, 0, c->s_upload>>>(s, c->d_bounds);
+    else svo_bounds_kernel<VX_FMT_ESVO><<<blocks, 256, 0, c->s_upload>>>(s, c->d_bounds);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return VX_OK;
+}
+
 // Bulk (re)load of ranges straight from a pinned mirror (this context's, or — in a VxGroup — device 0's): one DMA per range, then
 // wait, because the caller may rewrite the mirror as soon as the call returns.
 static int vx_svo_commit_from(VxCtx* c, const uint8_t* mirror, float octree_scale, const VxRange* dirty, uint32_t n_dirty, uint64_t used_bytes,
@@ -433,6 +459,7 @@ static int vx_svo_commit_from(VxCtx* c, const uint8_t* mirror, float octree_scal
                                   c->s_upload));
         CU(c, cudaStreamSynchronize(c->s_upload));
         c->have_svo = true;
+        { const int rb_ = refresh_bounds(c, depth); if (rb_) return rb_; }
     }
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
     c->stats.used_bytes = used_bytes; c->stats.depth = depth;
@@ -491,6 +518,7 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
             CU(c, cudaStreamSynchronize(c->s_upload));   // bulk (re)load straight from the mirror: must finish before the caller reuses it
         }
         c->have_svo = true;
+        { const int rb_ = refresh_bounds(c, depth); if (rb_) return rb_; }
     }
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
     c->stats.used_bytes = used_bytes; c->stats.depth = depth;
@@ -534,6 +562,7 @@ int vx_svo_commit_packed_device(VxCtx* c, const void* packed_dev, uint32_t n_dir
                                                                              c->cfg.svo_capacity_bytes, c->d_flags + 62);
     c->launches++;
     CU(c, cudaGetLastError());
+    { const int rb_ = refresh_bounds(c, depth); if (rb_) return rb_; }
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
     c->stats.used_bytes = used_bytes; c->stats.depth = depth;
     c->have_svo = true;
@@ -1214,6 +1243,7 @@ int vx_svo_write_device(VxCtx* c, uint64_t range_offset, const void* src_dev, ui
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
     CU(c, cudaMemcpyAsync(c->d_world + c->head + range_offset, src_dev, length, cudaMemcpyDeviceToDevice, c->s_upload));
+    { const int rb_ = refresh_bounds(c, c->stats.depth ? c->stats.depth : 23); if (rb_) return rb_; }
     CU(c, cudaEventRecord(c->e_upload, c->s_upload));
     return VX_OK;
 }

@@ -60,6 +60,8 @@ def parse():
                     "kernels as RGBA8 pixels (default) or RGBA32F pixels (p2p), or by pack + NCCL send/recv + unpack (nccl)")
     ap.add_argument("--no-overlap", action="store_true", help="serialized wavefront: shade_kernel starts only after trace_primary_kernel has finished (A/B)")
     ap.add_argument("--overlap", action="store_true", help="overlapped wavefront whatever the launch size (default: only for small launches)")
+    ap.add_argument("--morton", action="store_true", help="A/B: Z-order enumeration of the macro blocks instead of row-major")
+    ap.add_argument("--no-clip", action="store_true", help="A/B: rays are not clipped against the occupied box of the world")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--bands", type=int, default=3, help="e2e: bands of vx_render_read_rgba8 (render/read-back overlap)")
@@ -288,6 +290,10 @@ def main():
         svo.set_option(pkg.OPT_CTAS_PER_SM, args.ctas_per_sm)
     if args.tma:
         svo.set_option(pkg.OPT_TMA, 1)
+    if args.morton:
+        svo.set_option(pkg.OPT_MORTON, 1)
+    if args.no_clip:
+        svo.set_option(pkg.OPT_CLIP, 0)
     if args.no_overlap:
         svo.set_option(pkg.OPT_OVERLAP, 0)
     if args.overlap:
@@ -908,7 +914,7 @@ def run_picker(args):
         "data": "synthetic",
         "config": {"workload": f"{n_total} random-origin random-direction picker rays, generated-terrain ({terrain_name(args)}) r={radius} no-LOD world (BASELINE configs[3])",
                    "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "chunks": int(world.chunk_count), "max_dst": args.max_dst,
-                   "parallelism": f"contiguous ray ranges over {world_size} GPU(s), SVO replicated, no collective", "refill_threshold": args.refill or 24,
+                   "parallelism": f"contiguous ray ranges over {world_size} GPU(s), SVO replicated, no collective", "refill_threshold": args.refill or 20,
                    "l2": "flushed between steps (160 MiB fill in the timed region); the SVO itself is larger than L2", "world_gen_s": round(gen_s, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "trace_picker_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg),

@@ -381,6 +381,8 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *   9 = TMA write-back of framebuffer tiles in the shade kernel (0/1, default 0: measured 3 % slower): a strip's 4 x 32 RGBA32F pixels are staged in
  *       shared memory and written with four 512-byte bulk async copies instead of 128 16-byte stores
  *  10 = refill threshold of the shadow-ray kernel alone (0 = follow option 6)
+ *  13 = A/B of the work order (default 0): enumerate the macro blocks of a whole, unsharded frame along a Z-order curve instead
+ *       of row by row (north_star: "Morton/tile-ordered ray assignment"; measured: profiles/r02_ns1.md)
  *  12 = clip rays against the occupied box of the world (default 1): after every commit a small kernel finds the box that holds
  *       every voxel (chunk granularity); a ray that has left it can only miss, so its traversal stops there instead of walking
  *       the empty cells to the edge of the octree. Results are bit-identical; only the iteration counters shrink. 0 = off

@@ -108,7 +108,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("value", "<u4"), ("face_id", "<i4"), ("pos"
 VX_FLAG_NO_L2_WINDOW = 1
 VX_FLAG_SVO_CSVO = 4
 FORMAT_ESVO, FORMAT_CSVO = 0, 1
-OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER, OPT_RGBA8_OUT, OPT_TMA, OPT_REFILL_SHADOW, OPT_OVERLAP, OPT_CLIP = 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+OPT_COUNT, OPT_CTAS_PER_SM, OPT_L2_WINDOW, OPT_REFILL, OPT_REFILL_PICKER, OPT_RGBA8_OUT, OPT_TMA, OPT_REFILL_SHADOW, OPT_OVERLAP, OPT_CLIP, OPT_MORTON = 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
 
 # every symbol include/voxelrt.h declares (checked by tests/test_abi.py)
 VX_SYMBOLS = [

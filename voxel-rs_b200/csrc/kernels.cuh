@@ -50,6 +50,8 @@ struct RenderArgs {
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
     uint32_t shadow_refill;       // the same for trace_shadow_kernel
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
+    uint32_t morton_bits;         // A/B (vx_set_option 13, whole unsharded frames only): > 0 = enumerate the macro blocks along a Z-order
+                                  // curve over a 2^bits x 2^bits grid (cells outside the frame are skipped) instead of row by row
     unsigned int* strip_done;     // non-null: OVERLAPPED wavefront. strip_done[strip] counts the pixels of that 32x4 strip whose hit record is
                                   // written; shade_kernel runs concurrently with trace_primary_kernel (own stream) and a CTA waits for its
                                   // strip to be complete instead of for the whole kernel: it fills the SMs the tracing kernel's tail frees
@@ -72,6 +74,13 @@ __device__ __forceinline__ uint32_t owned_macro(const RenderArgs& a, uint32_t k)
     if (!a.shard_rows) return a.first_owned + k * a.shard_size;
     const uint32_t j = k / a.macro_x;
     return (a.first_owned + j * a.shard_size) * a.macro_x + (k - j * a.macro_x);
+}
+// k-th cell of the Z-order curve -> macro block, or 0xffffffff when the cell lies outside the frame (A/B of the work order)
+__device__ __forceinline__ uint32_t morton_macro(const RenderArgs& a, uint32_t k) {
+    uint32_t x = k & 0x55555555u, y = (k >> 1) & 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u; x = (x | (x >> 2)) & 0x0f0f0f0fu; x = (x | (x >> 4)) & 0x00ff00ffu; x = (x | (x >> 8)) & 0x0000ffffu;
+    y = (y | (y >> 1)) & 0x33333333u; y = (y | (y >> 2)) & 0x0f0f0f0fu; y = (y | (y >> 4)) & 0x00ff00ffu; y = (y | (y >> 8)) & 0x0000ffffu;
+    return (x < a.macro_x && y < a.macro_y) ? y * a.macro_x + x : 0xffffffffu;
 }
 // Band [row0, row1) of macro rows: what of it this shard owns. Host side of the launch (voxelrt.cu, and tests/emu's stand-in for it).
 inline void shard_band(RenderArgs& a, uint32_t row0, uint32_t row1) {
@@ -237,6 +246,9 @@ __device__ __forceinline__ void strip_wait(const unsigned int* strip_done, uint3
 }
 
 // ---- primary rays ------------------------------------------------------------------------------------------------------
+#ifndef VX_PRIMARY_CLIP
+#define VX_PRIMARY_CLIP true   // world-box clipping of primary rays (A/B: tools/ab_kernels.py builds a variant with false)
+#endif
 template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
     extern __shared__ uint32_t smem_raw[];
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     // counter the bottleneck of the sharded kernel, profiles/r01_scaling_before_owned_tiles.jsonl).
     uint32_t tile = 0, strip_x0 = 0, strip_y0 = 0, next_px = 32, tile_px0 = 0;
     uint32_t work = 0, work_end = 0;   // claimed run of work indices [work, work_end): a.fetch_tiles per atomicAdd
-    const uint32_t n_tiles = a.n_owned * 16u;
+    const uint32_t n_tiles = a.morton_bits ? (16u << (2u * a.morton_bits)) : a.n_owned * 16u;
     bool more_work = true;
     uint32_t slot = 0, last_leaf = 0xffffffffu;
     Walk w;
@@ -274,7 +286,9 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     if (work >= n_tiles) { more_work = false; break; }
                 }
                 tile = work++;
-                tile = owned_macro(a, tile >> 4) * 16u + (tile & 15u);
+                const uint32_t macro = a.morton_bits ? morton_macro(a, tile >> 4) : owned_macro(a, tile >> 4);
+                if (macro == 0xffffffffu) continue;
+                tile = macro * 16u + (tile & 15u);
                 if (!strip_origin(a, tile >> 2, strip_x0, strip_y0)) continue;
                 tile_px0 = (tile & 3u) * 32u;
                 next_px = 0;
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 if (gx < a.u.width && gy < a.u.height) {
                     float ox, oy, oz, dx, dy, dz, rox, roy, roz, rdx, rdy, rdz;
                     primary_ray(a.u, gx, gy, ox, oy, oz, dx, dy, dz);
-                    walk_init<FMT>(w, a.scene, clip, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
+                    walk_init<FMT>(w, a.scene, VX_PRIMARY_CLIP ? clip : Clip{0, 0, 0, 0, 0, 0, 0}, octree_scale, ox, oy, oz, dx, dy, dz, -1.0f, rox, roy, roz, rdx, rdy, rdz);
                     cold[0] = rox; cold[VX_THREADS] = roy; cold[2 * VX_THREADS] = roz;
                     cold[3 * VX_THREADS] = rdx; cold[4 * VX_THREADS] = rdy; cold[5 * VX_THREADS] = rdz;
                     slot = (tile >> 2) * 128u + tile_px0 + next_px + my_rank;
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         bool finished = false;
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 w.state = ST_IDLE;
                 finished = true;
             } else {
-                walk_skip_leaf<FMT>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
+                walk_skip_leaf<FMT, VX_PRIMARY_CLIP>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
         } else if (state_missed(w.state)) {
             __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -338,9 +352,10 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t strip = (owned_macro(a, blockIdx.x >> 2) << 2) | (blockIdx.x & 3u);
+    const uint32_t macro = a.morton_bits ? morton_macro(a, blockIdx.x >> 2) : owned_macro(a, blockIdx.x >> 2);
+    const uint32_t strip = (macro << 2) | (blockIdx.x & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
-    const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
+    const bool have = macro != 0xffffffffu && (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
     const bool live = have && gx < a.u.width && gy < a.u.height;
     if (a.strip_done) {   // overlapped wavefront: this strip's hit records may still be on their way
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
                 } else if (render_leaf<FMT, COUNT>(w, a.scene, sm, inv_scale, last_leaf, g, cnt)) {
                     shadow = 0.0f;
                 } else {
-                    walk_skip_leaf<FMT>(w, a.scene, sm.stack);
+                    walk_skip_leaf<FMT, true>(w, a.scene, sm.stack);
                     done = false;
                 }
             }
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
         if (w.state <= 0 && w.state != ST_IDLE) {
             // cast_translucent = false: the first leaf is the hit whatever its texel is (svo.esvo.glsl:241-242); the picker
             // never reads value or colour (picker.glsl:40-44), so neither the leaf word nor the texture is fetched.
@@ -663,7 +678,7 @@ __global__ void __launch_bounds__(VX_THREADS) debug_cast_kernel(DebugArgs a) {
             const bool first_of_kind = !(w.flags & VX_FLAG_ADJACENT) || g.value != last_leaf;
             if ((color.w > 0.0f || !a.cast_translucent) && first_of_kind) { hit = true; break; }
             last_leaf = g.value; w.flags |= VX_FLAG_ADJACENT;
-            walk_skip_leaf<FMT>(w, s, sm.stack);
+            walk_skip_leaf<FMT, true>(w, s, sm.stack);
         }
         if (w.state == ST_MISS) break;
         const int scale_after = walk_scale(w);

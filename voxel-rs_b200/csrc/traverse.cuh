@@ -267,6 +267,13 @@ __device__ __forceinline__ uint32_t csvo_read_leaf(const Scene& s, uint32_t mate
     return csvo_read_uint(s, material_section_ptr + material_section_offset * 4u + (__popc(v0) + __popc(v1)) * 4u);
 }
 
+// Ray state word (Walk::state): > 0 = walking, value = iterations left of the MAX_STEPS budget (:152);
+// 0 = budget used up (a miss, :392); ST_MISS = left the octree / beyond max_dst; ST_IDLE = no ray in this lane;
+// <= ST_LEAF = stopped at a leaf candidate with (ST_LEAF - state) iterations of budget left.
+enum : int { ST_MISS = -2, ST_IDLE = -3, ST_LEAF = -4 };
+__device__ __forceinline__ bool state_at_leaf(int st) { return st <= ST_LEAF; }
+__device__ __forceinline__ bool state_missed(int st) { return st == 0 || st == ST_MISS; }
+
 // Occupied box of the world in [1,2) space. A ray is over once it has left the box: nothing it could hit lies outside, so the
 // shader's remaining iterations (through empty cells to the edge of the octree, :152-392) can only end in a miss — the traversal
 // stops there with that miss. Same output bit for bit, fewer iterations (oracle/oracle.cpp restates it to keep the counters
@@ -342,7 +349,7 @@ __device__ __forceinline__ void walk_init(Walk& w, const Scene& s, const Clip& c
 
     w.soff = 0;          // scale = MAX_SCALE - 1
     w.se = 0.5f;
-    w.state = VX_MAX_STEPS;
+    w.state = (w.t_min > w.limit) ? ST_MISS : VX_MAX_STEPS;   // :153 at the first iteration
 
     if (FMT == VX_FMT_CSVO) {
         w.rec = __ldg(s.desc - 1);                                             // root_ptr, svo.csvo.glsl:190
@@ -383,13 +390,6 @@ __device__ __forceinline__ void stack_load(uint32_t a, uint32_t& rec, uint32_t& 
 }
 static_assert(VX_THREADS == 128, "stack_store/stack_load hard-code the 512-byte word stride of a 128-thread CTA");
 
-// Ray state word (Walk::state): > 0 = walking, value = iterations left of the MAX_STEPS budget (:152);
-// 0 = budget used up (a miss, :392); ST_MISS = left the octree / beyond max_dst; ST_IDLE = no ray in this lane;
-// <= ST_LEAF = stopped at a leaf candidate with (ST_LEAF - state) iterations of budget left.
-enum : int { ST_MISS = -2, ST_IDLE = -3, ST_LEAF = -4 };
-__device__ __forceinline__ bool state_at_leaf(int st) { return st <= ST_LEAF; }
-__device__ __forceinline__ bool state_missed(int st) { return st == 0 || st == ST_MISS; }
-
 // CSVO stack entries carry the node's header next to its depth, so a POP does not re-read it (the shader re-reads the header of
 // `ptr` every iteration; the buffer is immutable while a frame is traced). depth is kept as a signed 16-bit value: it is a small
 // count, a chunk's lod byte, or — for a ray that started inside a voxel and descends below the leaves — a small negative number.
@@ -425,7 +425,7 @@ __device__ __forceinline__ bool walk_pop(Walk& w, uint32_t stk, uint32_t stack_m
 }
 
 // ADVANCE / POP (svo.esvo.glsl:324-391 = svo.csvo.glsl:440-507) as the shader writes them. Returns false when the ray left the octree.
-template <int FMT>
+template <int FMT, bool LIMITED>
 __device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t stack_max_off, float tcornx, float tcorny, float tcornz, float tc_max) {
     uint32_t step_mask = 0;                                                   // :324-327  ADVANCE
     if (tc_max >= tcornx) { step_mask ^= 1; w.px -= w.se; }
@@ -433,6 +433,10 @@ __device__ __forceinline__ bool walk_advance(Walk& w, uint32_t stk, uint32_t sta
     if (tc_max >= tcornz) { step_mask ^= 4; w.pz -= w.se; }
     w.t_min = tc_max;                                                         // :330
     w.ci ^= step_mask;                                                        // :331
+    // :153 "max_dst >= 0 && t_min > max_dst" of the NEXT iteration, tested here where t_min changes (it changes nowhere else: a PUSH
+    // iteration does not pay for the test). Same outcome — a miss — and the same iteration count: the shader leaves before it
+    // counts the next iteration.
+    if (LIMITED && w.t_min > w.limit) return false;
     if (((w.ci ^ w.flags) & step_mask) != 0) return walk_pop<FMT>(w, stk, stack_max_off, step_mask);   // :335 (idx & step_mask)
     return true;
 }
@@ -471,9 +475,17 @@ __device__ __forceinline__ void walk_descend(Walk& w, const Scene& s) {
         w.rec = np; w.desc = nd;
         w.hdr = csvo_header(s, np, nd);
     } else {
+#ifdef VX_V_HDR128   // A/B build only (north_star: "child-descriptor fetches are 128-bit vectorised loads"): the record's four header words in
+                     // one 16-byte load (records are 16-byte aligned: DESIGN.md §2), then the word of child pair ci / 2 is selected
+        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(s.desc + w.rec));
+        const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));                // :292 get_octant_ptr
+        const uint32_t wh = (ci & 4u) ? ((ci & 2u) ? h4.w : h4.z) : ((ci & 2u) ? h4.y : h4.x);
+        w.desc = wh >> ((ci & 1u) << 4);
+#else
         const uint32_t wh = __ldg(s.desc + (w.rec + (ci >> 1)));              // child masks of the new octant (the :168 read of later iterations)
         const uint32_t wb = __ldg(s.desc + (w.rec + 4u + ci));                // :292 get_octant_ptr
         w.desc = wh >> ((ci & 1u) << 4);                                      // bits above 15 are never looked at
+#endif
         const uint32_t nr = (wb & 0x7fffffffu) + (((int32_t)wb < 0) ? (w.rec + 4u + ci) : 0u);   // relative (bit 31) or absolute
         w.rec = min(nr, s.max_rec);
     }
@@ -491,8 +503,7 @@ __device__ __forceinline__ void walk_descend(Walk& w, const Scene& s) {
 // selects were paid far more often than a serialized block was saved.)
 template <int FMT, bool LIMITED, bool COUNT>
 __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk, Counters& cnt) {
-    --w.state;                                                                // :152
-    if (LIMITED && w.t_min > w.limit) { w.state = ST_MISS; return; }          // :153
+    --w.state;                                                                // :152 (:153 is tested where t_min changes: walk_init, walk_advance)
     if (COUNT) cnt.steps++;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);   // :159
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);                // :161
@@ -526,17 +537,17 @@ __device__ __forceinline__ void walk_step(Walk& w, const Scene& s, uint32_t stk,
     } else {
         w.flags &= ~VX_FLAG_ADJACENT;                                         // :315-316 (adjacent_leaf_count = 0)
     }
-    if (!walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
+    if (!walk_advance<FMT, LIMITED>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max)) w.state = ST_MISS;
 }
 
 // ADVANCE/POP tail of the iteration that stopped at a rejected (translucent / repeated) leaf, svo.esvo.glsl:264-265 + :324.
 // The rejected leaf used up no extra iteration: the budget stored in the leaf state is restored.
-template <int FMT>
+template <int FMT, bool LIMITED>
 __device__ __forceinline__ void walk_skip_leaf(Walk& w, const Scene& s, uint32_t stk) {
     const int budget = ST_LEAF - w.state;
     const float tcornx = __fmaf_rn(w.px, w.tcx, -w.tbx), tcorny = __fmaf_rn(w.py, w.tcy, -w.tby), tcornz = __fmaf_rn(w.pz, w.tcz, -w.tbz);
     const float tc_max = tmin2(tmin2(tcornx, tcorny), tcornz);
-    w.state = walk_advance<FMT>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
+    w.state = walk_advance<FMT, LIMITED>(w, stk, s.stack_max_off, tcornx, tcorny, tcornz, tc_max) ? budget : ST_MISS;
 }
 
 template <int FMT>

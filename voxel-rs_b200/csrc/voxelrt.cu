@@ -104,7 +104,7 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 24, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2, opt_clip = 1;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 20, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2, opt_clip = 1, opt_morton = 0;
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -312,6 +312,7 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 10: ctx->opt_refill_shadow = value > 32 ? 32 : value; break;
         case 11: ctx->opt_overlap = value > 2 ? 2 : value; break;
         case 12: ctx->opt_clip = value ? 1 : 0; break;
+        case 13: ctx->opt_morton = value ? 1 : 0; break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -635,7 +636,14 @@ static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->
 // `band` selects the set of work counters (each band of a frame needs its own zeroed set).
 static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band, uint32_t row0, uint32_t row1, bool timed) {
     shard_band(a, row0, row1);
-    const uint32_t owned = a.n_owned;
+    uint32_t owned = a.n_owned;
+    a.morton_bits = 0;
+    if (c->opt_morton && a.shard_size == 1 && row0 == 0 && row1 == a.macro_y) {   // A/B: Z-order enumeration of a whole frame
+        uint32_t m = a.macro_x > a.macro_y ? a.macro_x : a.macro_y, bits = 0;
+        while ((1u << bits) < m) ++bits;
+        a.morton_bits = bits ? bits : 1;
+        owned = 1u << (2u * a.morton_bits);   // grid sizes below count curve cells, most of them outside the frame for a 16:9 image
+    }
     unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work) + 16 + band * 8;   // [0] primary strips, [2] shadow runs, [4] shadow list length
     a.shadow_count = work + 4;
     const size_t smem = stack_smem_bytes(a.scene);

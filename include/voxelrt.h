@@ -389,7 +389,7 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *  11 = overlapped wavefront (0 off, 1 on, 2 = default: on for launches small enough that kernel tails matter): shade_kernel is launched on its own stream next to trace_primary_kernel and each of its
  *       CTAs waits for the hit records of ITS 32x4-pixel strip (a completion counter per strip) instead of for the whole kernel,
  *       so shading fills the SMs that the tracing kernel's tail leaves idle; 0 = strictly one kernel after the other
- *   7 = the same for the picker kernel (default 24: incoherent rays differ in length by 100x; 4.85 vs 2.84 Grays/s
+ *   7 = the same for the picker kernel (default 20; 16 / 20 / 24 / 28 measured 5.86 / 6.00 / 5.92 / 5.46 Grays/s in round 2: incoherent rays differ in length by 100x; 4.85 vs 2.84 Grays/s
  *       against threshold 1 on 16 Mi random rays, profiles/r01_v2_*) */
 int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value);
 

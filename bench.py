@@ -536,6 +536,9 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
+    # measured read bandwidth of THIS GPU at the two levels the node fetches can be served from (report against both)
+    l2_gbs = svo.probe_read_bandwidth(32 << 20, 64)
+    hbm_read_gbs = svo.probe_read_bandwidth(2 << 30, 1)
     alg_bytes = algorithmic_bytes(st, pixels // n_gpus if n_gpus > 1 else pixels)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     # per kernel: node words + child pointers + leaf words, plus the wavefront records each kernel reads / writes
@@ -589,6 +592,10 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "trace_primary_kernel + shade_kernel + trace_shadow_kernel (one frame; SURVEY §8d formula)",
                      "kernel_ms": kernel_ms, "kernel_ms_split": split_ms, "issue": issue, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "l2": {"bound": "l2", "achieved": achieved, "peak": round(l2_gbs, 1), "unit": "GB/s", "frac": achieved / l2_gbs if l2_gbs else None,
+                            "peak_source": "measured here: vx_probe_read_bandwidth, 32 MiB buffer x 64 passes, ld.global.cg (L2-resident)",
+                            "hbm_read_peak_measured_here": round(hbm_read_gbs, 1),
+                            "note": "the same algorithmic bytes against the L2: the frame touches a few MB of SVO, so node fetches are L1 / L2 hits"},
                      "dominant_kernel": (dict(per_kernel[dom], kernel=dom + "_kernel") if dom else None), "per_kernel": per_kernel,
                      "counts": {k: int(st[k]) for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches")},
                      "note": "latency/divergence-bound pointer chasing: the SVO is L2-resident after first touch, so the HBM fraction is small "

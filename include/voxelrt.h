@@ -236,6 +236,12 @@ int64_t vx_svo_pack_dirty(VxCtx* ctx, const VxRange* dirty, uint32_t n_dirty, vo
  * of bounds). Waits for the upload stream. 0 in a healthy run. */
 int vx_svo_scatter_errors(VxCtx* ctx, uint32_t* out);
 
+/* Measurement aid (no counterpart in the reference): read bandwidth of this GPU in GB/s, best of 5 — every thread streams 16-byte
+ * words of a scratch buffer of `bytes` bytes `passes` times with L2-only caching. bytes well below the L2 size (e.g. 32 MiB)
+ * measures the L2, bytes several times the L2 (e.g. 2 GiB, passes 1) measures HBM: the denominators bench.py reports the ray
+ * caster's node-fetch traffic against ("report against both"). */
+int vx_probe_read_bandwidth(VxCtx* ctx, uint64_t bytes, uint32_t passes, float* gb_per_s);
+
 int vx_stats(const VxCtx* ctx, VxStats* out);
 
 /* graphics::Svo::render (svo.rs:196-229) = world.glsl main(): one primary ray per pixel, shading,

@@ -29,6 +29,7 @@
 
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct uint4 { unsigned x, y, z, w; };
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
 
 namespace emu {
@@ -98,6 +99,7 @@ inline void cta_barrier() {
 // ---- memory ----
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const char*)p - emu::smem_base); }
 static inline uint32_t& vx_emu_shared_u32(uint32_t byte_address) { return *reinterpret_cast<uint32_t*>(emu::smem_base + byte_address); }

@@ -125,7 +125,7 @@ VX_SYMBOLS = [
     "vx_group_create", "vx_group_destroy", "vx_group_last_error", "vx_group_size", "vx_group_ctx", "vx_group_set_materials",
     "vx_group_set_textures", "vx_group_set_option", "vx_group_svo_host_mirror", "vx_group_svo_set_hot_range", "vx_group_svo_commit",
     "vx_group_stats", "vx_group_render", "vx_group_wait", "vx_group_read_frame_rgba8", "vx_group_read_frame_rgba32f",
-    "vx_group_host_frame", "vx_group_render_read_rgba8", "vx_group_raycast",
+    "vx_group_host_frame", "vx_group_render_read_rgba8", "vx_group_raycast", "vx_probe_read_bandwidth",
 ]
 VX_SHARD_ROWS = 0x80000000
 
@@ -220,6 +220,7 @@ def lib():
         L.vx_group_host_frame.argtypes = [P, u64]; L.vx_group_host_frame.restype = P
         L.vx_group_render_read_rgba8.argtypes = [P, C.POINTER(VxRenderParams), u32, u32, P, u32]; L.vx_group_render_read_rgba8.restype = C.c_int
         L.vx_group_raycast.argtypes = [P, P, u64, P]; L.vx_group_raycast.restype = C.c_int
+        L.vx_probe_read_bandwidth.argtypes = [P, u64, u32, C.POINTER(C.c_float)]; L.vx_probe_read_bandwidth.restype = C.c_int
     except AttributeError:
         if not os.environ.get("VOXELRT_AB_VARIANT"):   # only tools/ab_kernels.py may load an older build of the library
             raise
@@ -974,6 +975,12 @@ class Svo:
         n = C.c_uint32()
         self._check(lib().vx_frame_sync_errors(self.ctx, C.byref(n)))
         return n.value
+
+    def probe_read_bandwidth(self, nbytes, passes):
+        """GB/s of a streaming read of an nbytes scratch buffer (fits the L2: L2 bandwidth; several times the L2: HBM)."""
+        g = C.c_float()
+        self._check(lib().vx_probe_read_bandwidth(self.ctx, nbytes, passes, C.byref(g)))
+        return g.value
 
     def scatter_errors(self):
         n = C.c_uint32()

@@ -50,8 +50,8 @@ struct RenderArgs {
     uint32_t refill_threshold;    // leave the walk loop when fewer lanes than this are still walking
     uint32_t shadow_refill;       // the same for trace_shadow_kernel
     uint32_t fetch_tiles;         // warp tiles claimed per work-counter atomicAdd (1..4: fewer same-address atomics on big frames)
-    uint32_t morton_bits;         // A/B (vx_set_option 13, whole unsharded frames only): > 0 = enumerate the macro blocks along a Z-order
-                                  // curve over a 2^bits x 2^bits grid (cells outside the frame are skipped) instead of row by row
+    const uint32_t* work_list;    // A/B (vx_set_option 13, whole unsharded frames only): non-null = the k-th work unit is macro block
+                                  // work_list[k] (a Z-order curve over the frame's macro blocks) instead of the k-th in row-major order
     unsigned int* strip_done;     // non-null: OVERLAPPED wavefront. strip_done[strip] counts the pixels of that 32x4 strip whose hit record is
                                   // written; shade_kernel runs concurrently with trace_primary_kernel (own stream) and a CTA waits for its
                                   // strip to be complete instead of for the whole kernel: it fills the SMs the tracing kernel's tail frees
@@ -74,13 +74,6 @@ __device__ __forceinline__ uint32_t owned_macro(const RenderArgs& a, uint32_t k)
     if (!a.shard_rows) return a.first_owned + k * a.shard_size;
     const uint32_t j = k / a.macro_x;
     return (a.first_owned + j * a.shard_size) * a.macro_x + (k - j * a.macro_x);
-}
-// k-th cell of the Z-order curve -> macro block, or 0xffffffff when the cell lies outside the frame (A/B of the work order)
-__device__ __forceinline__ uint32_t morton_macro(const RenderArgs& a, uint32_t k) {
-    uint32_t x = k & 0x55555555u, y = (k >> 1) & 0x55555555u;
-    x = (x | (x >> 1)) & 0x33333333u; x = (x | (x >> 2)) & 0x0f0f0f0fu; x = (x | (x >> 4)) & 0x00ff00ffu; x = (x | (x >> 8)) & 0x0000ffffu;
-    y = (y | (y >> 1)) & 0x33333333u; y = (y | (y >> 2)) & 0x0f0f0f0fu; y = (y | (y >> 4)) & 0x00ff00ffu; y = (y | (y >> 8)) & 0x0000ffffu;
-    return (x < a.macro_x && y < a.macro_y) ? y * a.macro_x + x : 0xffffffffu;
 }
 // Band [row0, row1) of macro rows: what of it this shard owns. Host side of the launch (voxelrt.cu, and tests/emu's stand-in for it).
 inline void shard_band(RenderArgs& a, uint32_t row0, uint32_t row1) {
@@ -268,7 +261,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
     // counter the bottleneck of the sharded kernel, profiles/r01_scaling_before_owned_tiles.jsonl).
     uint32_t tile = 0, strip_x0 = 0, strip_y0 = 0, next_px = 32, tile_px0 = 0;
     uint32_t work = 0, work_end = 0;   // claimed run of work indices [work, work_end): a.fetch_tiles per atomicAdd
-    const uint32_t n_tiles = a.morton_bits ? (16u << (2u * a.morton_bits)) : a.n_owned * 16u;
+    const uint32_t n_tiles = a.n_owned * 16u;
     bool more_work = true;
     uint32_t slot = 0, last_leaf = 0xffffffffu;
     Walk w;
@@ -286,9 +279,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                     if (work >= n_tiles) { more_work = false; break; }
                 }
                 tile = work++;
-                const uint32_t macro = a.morton_bits ? morton_macro(a, tile >> 4) : owned_macro(a, tile >> 4);
-                if (macro == 0xffffffffu) continue;
-                tile = macro * 16u + (tile & 15u);
+                tile = (a.work_list ? __ldg(a.work_list + (tile >> 4)) : owned_macro(a, tile >> 4)) * 16u + (tile & 15u);
                 if (!strip_origin(a, tile >> 2, strip_x0, strip_y0)) continue;
                 tile_px0 = (tile & 3u) * 32u;
                 next_px = 0;
@@ -352,10 +343,9 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t macro = a.morton_bits ? morton_macro(a, blockIdx.x >> 2) : owned_macro(a, blockIdx.x >> 2);
-    const uint32_t strip = (macro << 2) | (blockIdx.x & 3u);
+    const uint32_t strip = ((a.work_list ? __ldg(a.work_list + (blockIdx.x >> 2)) : owned_macro(a, blockIdx.x >> 2)) << 2) | (blockIdx.x & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
-    const bool have = macro != 0xffffffffu && (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
+    const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
     const bool live = have && gx < a.u.width && gy < a.u.height;
     if (a.strip_done) {   // overlapped wavefront: this strip's hit records may still be on their way
@@ -777,6 +767,20 @@ __global__ void __launch_bounds__(256) svo_bounds_kernel(Scene s, uint32_t* boun
         }
         walk_descend<FMT>(w, s);
     }
+}
+
+// ---- read-bandwidth probe (the roofline denominators: measured, not quoted) ------------------------------------------------------
+// Every thread streams 16-byte words of a buffer, `passes` times; a buffer that fits the L2 measures L2 read bandwidth after the
+// first pass, a buffer several times the L2 measures HBM. The sum goes to `sink` so that the loads cannot be dropped.
+__global__ void __launch_bounds__(256) read_probe_kernel(const uint4* buf, unsigned long long n16, uint32_t passes, uint32_t* sink) {
+    uint32_t acc = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (uint32_t p = 0; p < passes; ++p)
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);   // cache at L2 only: an L1 hit would measure the wrong level
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) *sink = acc;
 }
 
 // ---- small utility kernels ---------------------------------------------------------------------------------------------

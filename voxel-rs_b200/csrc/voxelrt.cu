@@ -33,6 +33,8 @@ struct VxCtx {
     cudaStream_t s_aux = nullptr;         // shade_kernel of the overlapped wavefront: runs next to trace_primary_kernel, ordered by strip flags
     cudaEvent_t e_pre = nullptr, e_k2 = nullptr;
     unsigned int* d_strip_done = nullptr; // per 32x4-pixel strip: pixels whose hit record is written (overlapped wavefront)
+    uint32_t* d_work_list = nullptr;      // Z-order list of macro blocks (vx_set_option 13)
+    uint32_t morton_x = 0, morton_y = 0;
     uint32_t* d_bounds = nullptr;         // occupied box of the SVO in voxel units (svo_bounds_kernel), read by the trace kernels (Clip)
     cudaEvent_t e_band[16] = {};
     cudaStream_t own_streams[3] = {nullptr, nullptr, nullptr};   // the library's own streams while caller streams are installed
@@ -271,6 +273,7 @@ void vx_destroy(VxCtx* c) {
     if (c->d_texinfo) cudaFree(c->d_texinfo);
     if (c->d_unorm) cudaFree(c->d_unorm);
     if (c->d_bounds) cudaFree(c->d_bounds);
+    if (c->d_work_list) cudaFree(c->d_work_list);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
     if (c->d_hit0) cudaFree(c->d_hit0);
@@ -636,13 +639,28 @@ static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->
 // `band` selects the set of work counters (each band of a frame needs its own zeroed set).
 static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band, uint32_t row0, uint32_t row1, bool timed) {
     shard_band(a, row0, row1);
-    uint32_t owned = a.n_owned;
-    a.morton_bits = 0;
+    const uint32_t owned = a.n_owned;
+    a.work_list = nullptr;
     if (c->opt_morton && a.shard_size == 1 && row0 == 0 && row1 == a.macro_y) {   // A/B: Z-order enumeration of a whole frame
-        uint32_t m = a.macro_x > a.macro_y ? a.macro_x : a.macro_y, bits = 0;
-        while ((1u << bits) < m) ++bits;
-        a.morton_bits = bits ? bits : 1;
-        owned = 1u << (2u * a.morton_bits);   // grid sizes below count curve cells, most of them outside the frame for a 16:9 image
+        if (c->morton_x != a.macro_x || c->morton_y != a.macro_y) {
+            // the frame's macro blocks along a Z-order curve: cells of the enclosing 2^b x 2^b grid in curve order, those outside dropped
+            std::vector<uint32_t> list;
+            list.reserve((size_t)a.macro_x * a.macro_y);
+            uint32_t m = a.macro_x > a.macro_y ? a.macro_x : a.macro_y, bits = 0;
+            while ((1u << bits) < m) ++bits;
+            for (uint32_t k = 0; k < (1u << (2 * bits)); ++k) {
+                uint32_t x = 0, y = 0;
+                for (uint32_t b = 0; b < bits; ++b) { x |= ((k >> (2 * b)) & 1u) << b; y |= ((k >> (2 * b + 1)) & 1u) << b; }
+                if (x < a.macro_x && y < a.macro_y) list.push_back(y * a.macro_x + x);
+            }
+            CU(c, cudaStreamSynchronize(c->s_render));
+            if (c->d_work_list) cudaFree(c->d_work_list);
+            c->d_work_list = nullptr;
+            CU(c, cudaMalloc(&c->d_work_list, list.size() * sizeof(uint32_t)));
+            CU(c, cudaMemcpy(c->d_work_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            c->morton_x = a.macro_x; c->morton_y = a.macro_y;
+        }
+        a.work_list = c->d_work_list;
     }
     unsigned int* work = reinterpret_cast<unsigned int*>(c->d_work) + 16 + band * 8;   // [0] primary strips, [2] shadow runs, [4] shadow list length
     a.shadow_count = work + 4;
@@ -1337,6 +1355,39 @@ int vx_frame_flags_reset(VxCtx* c) {
     CU(c, cudaStreamSynchronize(c->s_render));
     CU(c, cudaMemset(c->d_flags, 0, 64 * sizeof(unsigned int)));
     c->gate_armed = false;
+    return VX_OK;
+}
+
+int vx_probe_read_bandwidth(VxCtx* c, uint64_t bytes, uint32_t passes, float* gb_per_s) {
+    if (!c || !gb_per_s || bytes < (1u << 20) || passes == 0) return fail(c, VX_E_ARG, "vx_probe_read_bandwidth: bad argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    uint4* buf = nullptr;
+    uint32_t* sink = nullptr;
+    const unsigned long long n16 = bytes / 16;
+    CU(c, cudaMalloc(&buf, n16 * 16));
+    if (cudaMalloc(&sink, 4) != cudaSuccess) { cudaFree(buf); return fail(c, VX_E_CUDA, "vx_probe_read_bandwidth: cudaMalloc failed"); }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaMemsetAsync(buf, 1, n16 * 16, c->s_render);
+    const int grid = c->sm_count * 8;
+    read_probe_kernel<<<grid, 256, 0, c->s_render>>>(buf, n16, 1, sink);          // warm: the buffer is in the L2 now if it fits
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, c->s_render);
+        read_probe_kernel<<<grid, 256, 0, c->s_render>>>(buf, n16, passes, sink);
+        cudaEventRecord(e1, c->s_render);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const float gbs = ms > 0.0f ? (float)((double)n16 * 16.0 * passes / (ms * 1e-3) / 1e9) : 0.0f;
+        if (gbs > best) best = gbs;
+    }
+    c->launches += 6;
+    const cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess) return fail(c, VX_E_CUDA, "vx_probe_read_bandwidth: %s", cudaGetErrorString(e));
+    *gb_per_s = best;
     return VX_OK;
 }
 

@@ -99,6 +99,7 @@ def _run_group(pkg, devices, fmt):
     for i in range(len(grp)):
         n = C.c_uint32()
         assert pkg.lib().vx_svo_scatter_errors(grp.ctx(i), C.byref(n)) == 0 and n.value == 0
+        assert pkg.lib().vx_frame_sync_errors(grp.ctx(i), C.byref(n)) == 0 and n.value == 0    # no wait of the overlapped wavefront gave up
     grp.close()
     one.close()
 
@@ -147,4 +148,34 @@ def test_row_shards_tile_the_frame(pkg):
             rows = [y for y in range(H) if (y // 16) % 3 == r]
             assert host.numpy()[rows].tobytes() == want[rows].tobytes(), (bands, r)
         assert host.numpy().tobytes() == want.tobytes()
+    svo.close()
+
+
+def test_overlapped_wavefront_with_bands_is_live(pkg):
+    """Regression (round 2): with the overlapped wavefront the shade kernel's CTAs wait for the tracing kernel. At the start of a
+    band both kernels become runnable on an idle GPU at the same instant; when the shade grid won every SM first, no tracing CTA
+    fitted next to it (shared-memory carve-out), every wait timed out and the band came out wrong — about once in 300 frames.
+    The shade kernel now pads its shared memory so that a tracing CTA always fits. 150 banded, sharded frames with the overlap
+    forced on: every frame right, no wait gave up."""
+    reg = pkg.content_registry(pkg.load_atlas())
+    world = _world(pkg)
+    svo = pkg.Svo(reg, size_mb=world.size_bytes // 1_000_000 + 16, max_width=W, max_height=H, max_rays=16)
+    world.mark_all_dirty()
+    svo.update(world)
+    views = _views(pkg, world)
+    svo.set_option(pkg.OPT_OVERLAP, 0)
+    want = []
+    for v in views:
+        svo.render_raw(v, W, H)
+        want.append(svo.read_rgba8())
+    svo.set_option(pkg.OPT_OVERLAP, 1)
+    import torch
+    host = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    for it in range(150):
+        k = it % 3
+        host.fill_(0x5a)
+        for r in range(2):
+            svo.render_read_rgba8(views[k], W, H, host.data_ptr(), bands=2 + (it % 2), shard=(r, 2 | pkg.VX_SHARD_ROWS))
+        assert host.numpy().tobytes() == want[k].tobytes(), it
+    assert svo.frame_sync_errors() == 0
     svo.close()

@@ -714,7 +714,20 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             c->gate_event = nullptr;
         }
         // 2. shading -> final pixels + shadow ray list
-        const size_t smem2 = smem_bytes(0, false);
+        // Overlapped: shade CTAs WAIT for the tracing kernel, so the tracing kernel must be able to run wherever they sit. Launch
+        // order does not guarantee that (two bands measured it: both kernels become runnable on an idle GPU at the same instant, the
+        // shade grid won every SM with its small shared-memory carve-out, no tracing CTA fitted, every wait timed out). So the shade
+        // kernel asks for padding shared memory: at most five of its CTAs fit an SM, and what is left always holds one tracing CTA
+        // (shared memory: 5 x (pad + static + 1 KB) + trace + 1 KB <= 227 KB, a sixth does not fit; registers: 5 x 6 K + 8 K of 64 K). With dynamic work fetch one
+        // resident tracing CTA per SM is enough to finish all tracing work.
+        size_t smem2 = smem_bytes(0, false);
+        if (a.strip_done) {
+            const size_t sm_total = (size_t)227 * 1024, per_cta_extra = 3584;   // shade: ~2.1 KB static + 1 KB the system reserves per CTA (+ slack)
+            const size_t trace_cta = smem + 1024;
+            size_t pad = sm_total > trace_cta + 5 * per_cta_extra ? (sm_total - trace_cta) / 5 - per_cta_extra : 0;
+            pad = pad > 47 * 1024 ? 47 * 1024 : pad / 128 * 128;                 // <= 48 KB: no opt-in attribute needed
+            if (pad > smem2) smem2 = pad;
+        }
         if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
         else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
         c->launches++;

@@ -260,7 +260,9 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
             if (csvo) { if (count) trace_primary_kernel<VX_FMT_CSVO, true, 8>(a); else trace_primary_kernel<VX_FMT_CSVO, false, 8>(a); }
             else { if (count) trace_primary_kernel<VX_FMT_ESVO, true, 8>(a); else trace_primary_kernel<VX_FMT_ESVO, false, 8>(a); }
         });
-        emu::launch(owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true>(a); else shade_kernel<false>(a); });
+        a.shade_blocks = owned * 4;
+        a.shade_counter = options[9] ? work + 6 : nullptr;   // overlapped: persistent shade grid (here: 3 CTAs, one after the other)
+        emu::launch(options[9] ? (owned * 4 < 3 ? owned * 4 : 3) : owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true>(a); else shade_kernel<false>(a); });
         if (p->render_shadows) {
             a.work_counter = work + 2;
             emu::launch(grid, VX_THREADS, [&] {

@@ -56,6 +56,9 @@ struct RenderArgs {
                                   // written; shade_kernel runs concurrently with trace_primary_kernel (own stream) and a CTA waits for its
                                   // strip to be complete instead of for the whole kernel: it fills the SMs the tracing kernel's tail frees
     unsigned int* sync_errors;    // counts waits of the overlapped wavefront that gave up
+    unsigned int* shade_counter;  // overlapped wavefront: shade_kernel is PERSISTENT too — a grid small enough to be resident as a whole (next
+                                  // to the tracing kernel's CTAs), its CTAs claim strips in order from this counter
+    uint32_t shade_blocks;        // strips to shade in this launch (owned macro blocks x 4)
     uint32_t tma_writeback;       // shade_kernel: stage the strip's pixels in shared memory and write them back with bulk async
                                   // copies (TMA engine, cp.async.bulk -> SASS UBLKCP), one 512-byte row per copy
 };
@@ -343,7 +346,18 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
     __shared__ unsigned int s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t strip = ((a.work_list ? __ldg(a.work_list + (blockIdx.x >> 2)) : owned_macro(a, blockIdx.x >> 2)) << 2) | (blockIdx.x & 3u);
+    __shared__ unsigned int s_next;
+    Counters cnt = {0, 0, 0, 0, 0, 0};
+    // static grid: CTA b shades strip b. Overlapped wavefront: the CTAs of a small resident grid claim strips from shade_counter.
+    for (uint32_t blk = blockIdx.x;;) {
+    if (a.shade_counter) {
+        __syncthreads();   // everybody is done with the shared arrays of the previous strip (and with s_next)
+        if (threadIdx.x == 0) s_next = atomicAdd(a.shade_counter, 1u);
+        __syncthreads();
+        blk = s_next;
+    }
+    if (blk >= a.shade_blocks) break;
+    const uint32_t strip = ((a.work_list ? __ldg(a.work_list + (blk >> 2)) : owned_macro(a, blk >> 2)) << 2) | (blk & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
     const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
@@ -353,7 +367,6 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
             strip_wait(a.strip_done, strip, min(32u, a.u.width - x0) * min(4u, a.u.height - y0), a.sync_errors);
         __syncthreads();
     }
-    Counters cnt = {0, 0, 0, 0, 0, 0};
     bool want_shadow = false;
     float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
     const uint32_t pix = gy * a.u.width + gx;
@@ -429,6 +442,8 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
         unsigned off = s_base + __popc(m & ((1u << lane) - 1u));
         for (uint32_t k = 0; k < warp; ++k) off += s_warp_count[k];
         a.sh0[off] = s0; a.sh1[off] = s1; a.sh_pix[off] = pix;
+    }
+    if (!a.shade_counter) break;
     }
     if (COUNT) flush_counters(a.counters, cnt);
 }

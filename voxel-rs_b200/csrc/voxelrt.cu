@@ -714,22 +714,30 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             c->gate_event = nullptr;
         }
         // 2. shading -> final pixels + shadow ray list
-        // Overlapped: shade CTAs WAIT for the tracing kernel, so the tracing kernel must be able to run wherever they sit. Launch
-        // order does not guarantee that (two bands measured it: both kernels become runnable on an idle GPU at the same instant, the
-        // shade grid won every SM with its small shared-memory carve-out, no tracing CTA fitted, every wait timed out). So the shade
-        // kernel asks for padding shared memory: at most five of its CTAs fit an SM, and what is left always holds one tracing CTA
-        // (shared memory: 5 x (pad + static + 1 KB) + trace + 1 KB <= 227 KB, a sixth does not fit; registers: 5 x 6 K + 8 K of 64 K). With dynamic work fetch one
-        // resident tracing CTA per SM is enough to finish all tracing work.
+        // Overlapped: shade CTAs WAIT for the tracing kernel, so the tracing kernel must always be able to run. Nothing orders the
+        // dispatch of two kernels on two streams (measured with bands: both become runnable on an idle GPU at the same instant;
+        // when the block scheduler took the shade grid first, its waiting CTAs filled the SMs and the grid's undispatched rest kept
+        // the tracing kernel out: every wait timed out, once in ~300 frames). So in this mode the shade kernel is persistent as
+        // well: a grid of at most 5 CTAs per SM that is resident AS A WHOLE — nothing of it is ever left to dispatch — and padded
+        // with shared memory so that what remains of every SM always holds one tracing CTA (5 x (pad + static + 1 KB) + trace + 1 KB
+        // <= 227 KB, a sixth does not fit; registers 5 x 6 K + 8 K of 64 K). Its CTAs claim strips in work order from a counter; the
+        // tracing kernel fetches its work dynamically too, so any one resident tracing CTA completes all tracing work.
         size_t smem2 = smem_bytes(0, false);
+        unsigned shade_grid = owned * 4;
+        a.shade_blocks = owned * 4;
+        a.shade_counter = nullptr;
         if (a.strip_done) {
             const size_t sm_total = (size_t)227 * 1024, per_cta_extra = 3584;   // shade: ~2.1 KB static + 1 KB the system reserves per CTA (+ slack)
             const size_t trace_cta = smem + 1024;
             size_t pad = sm_total > trace_cta + 5 * per_cta_extra ? (sm_total - trace_cta) / 5 - per_cta_extra : 0;
             pad = pad > 47 * 1024 ? 47 * 1024 : pad / 128 * 128;                 // <= 48 KB: no opt-in attribute needed
             if (pad > smem2) smem2 = pad;
+            a.shade_counter = work + 6;
+            const unsigned resident = (unsigned)c->sm_count * 5u;
+            if (shade_grid > resident) shade_grid = resident;
         }
-        if (count) shade_kernel<true><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
-        else shade_kernel<false><<<owned * 4, VX_THREADS, smem2, s2>>>(a);
+        if (count) shade_kernel<true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+        else shade_kernel<false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
         c->launches++;
         if (timed) CU(c, cudaEventRecord(c->t_wave[2], s2));
         if (a.strip_done) {

@@ -262,7 +262,8 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
         });
         a.shade_blocks = owned * 4;
         a.shade_counter = options[9] ? work + 6 : nullptr;   // overlapped: persistent shade grid (here: 3 CTAs, one after the other)
-        emu::launch(options[9] ? (owned * 4 < 3 ? owned * 4 : 3) : owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true>(a); else shade_kernel<false>(a); });
+        if (options[9]) emu::launch(owned * 4 < 3 ? owned * 4 : 3, VX_THREADS, [&] { if (count) shade_kernel<true, true>(a); else shade_kernel<false, true>(a); });
+        else emu::launch(owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true, false>(a); else shade_kernel<false, false>(a); });
         if (p->render_shadows) {
             a.work_counter = work + 2;
             emu::launch(grid, VX_THREADS, [&] {

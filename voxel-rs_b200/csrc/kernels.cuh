@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
 
 // ---- shading ---------------------------------------------------------------------------------------------------------------
 // grid = owned strips, block = 128 threads = the 128 pixels of one 32x4 strip (4 warp tiles of 8x4).
-template <bool COUNT>
-__global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
+template <bool COUNT, bool PERSIST>
+__global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(RenderArgs a) {   // static grid: 10 CTAs / SM (<= 51 registers)
     extern __shared__ uint32_t smem_raw[];
     const Smem sm = make_smem(a.scene.unorm, 0, smem_raw, false);
     __shared__ unsigned int s_warp_count[VX_THREADS / 32];
@@ -350,19 +350,19 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
     Counters cnt = {0, 0, 0, 0, 0, 0};
     // static grid: CTA b shades strip b. Overlapped wavefront: the CTAs of a small resident grid claim strips from shade_counter.
     for (uint32_t blk = blockIdx.x;;) {
-    if (a.shade_counter) {
+    if (PERSIST) {
         __syncthreads();   // everybody is done with the shared arrays of the previous strip (and with s_next)
         if (threadIdx.x == 0) s_next = atomicAdd(a.shade_counter, 1u);
         __syncthreads();
         blk = s_next;
+        if (blk >= a.shade_blocks) break;
     }
-    if (blk >= a.shade_blocks) break;
     const uint32_t strip = ((a.work_list ? __ldg(a.work_list + (blk >> 2)) : owned_macro(a, blk >> 2)) << 2) | (blk & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
     const bool have = (strip >> 2) < a.macro0 + a.n_macros && strip_origin(a, strip, x0, y0);
     if (have) strip_pixel(x0, y0, threadIdx.x, gx, gy);
     const bool live = have && gx < a.u.width && gy < a.u.height;
-    if (a.strip_done) {   // overlapped wavefront: this strip's hit records may still be on their way
+    if (PERSIST) {        // overlapped wavefront: this strip's hit records may still be on their way
         if (threadIdx.x == 0 && have)
             strip_wait(a.strip_done, strip, min(32u, a.u.width - x0) * min(4u, a.u.height - y0), a.sync_errors);
         __syncthreads();
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(VX_THREADS) shade_kernel(RenderArgs a) {
         for (uint32_t k = 0; k < warp; ++k) off += s_warp_count[k];
         a.sh0[off] = s0; a.sh1[off] = s1; a.sh_pix[off] = pix;
     }
-    if (!a.shade_counter) break;
+    if (!PERSIST) break;
     }
     if (COUNT) flush_counters(a.counters, cnt);
 }

@@ -736,8 +736,13 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             const unsigned resident = (unsigned)c->sm_count * 5u;
             if (shade_grid > resident) shade_grid = resident;
         }
-        if (count) shade_kernel<true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
-        else shade_kernel<false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+        if (a.shade_counter) {
+            if (count) shade_kernel<true, true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+            else shade_kernel<false, true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+        } else {
+            if (count) shade_kernel<true, false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+            else shade_kernel<false, false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
+        }
         c->launches++;
         if (timed) CU(c, cudaEventRecord(c->t_wave[2], s2));
         if (a.strip_done) {

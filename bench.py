@@ -314,6 +314,7 @@ def main():
     octree_scale = float(np.float32(2.0 ** -world.depth))
     packed_n = svo.pack_dirty(dirty, None)
     packed_host = torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)
+    packed_hosts = [packed_host, torch.empty(packed_n, dtype=torch.uint8, pin_memory=True)]
     flush_buf = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)   # > the 126 MB L2
 
     sf = pkg.sharded.ShardedFrame(svo, rank, n_gpus, dist=dist if n_gpus > 1 else None, torch=torch, device=dev, gather=args.gather)
@@ -379,28 +380,30 @@ def main():
     def step_e2e():
         """The same frame through the C ABI with host buffers: dirty bytes -> pinned mirror -> H2D, render, RGBA8 -> host."""
         flush()
-        if rank == 0:
+        if rank == 0 and n_gpus == 1:
             for (o, l), b in zip(dirty, staged):   # the host-side serializer writing its changes (write_changes_to)
                 mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
-        if n_gpus > 1:
-            # host-resident inputs cannot be sent a frame ahead: pack -> H2D -> broadcast -> scatter sit in front of the frame
-            sf.apply_dirty()          # drain the set the resident loop left in flight (first e2e step only)
-            if rank == 0:
-                svo.pack_dirty(dirty, packed_host.numpy())
-            sf.broadcast_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_host)
-        else:
-            svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
         if n_gpus == 1:
+            svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
             # render + read-back pipelined by the library: finished bands are copied to the host while the next is traced
             svo.render_read_rgba8(vxp, W, H, frame8.data_ptr(), bands=args.bands)
             return
+        # N > 1, software-pipelined by one step like the resident loop: this frame's dirty set was packed, copied to GPU 0 and
+        # broadcast during the previous step; the NEXT frame's set is prepared on the host and sent while this frame renders.
+        # Every step still copies one dirty set host -> device and reads one frame device -> host.
         e2e_step[0] += 1
         k = e2e_step[0]
+        sf.apply_dirty()                       # scatter of the set sent last step (stream-ordered behind the previous frame)
         if rank != 0:
             while step_words[63] < k - 1:      # rank 0 is done with the previous host frame
                 pass
-        # returns when THIS rank's stripes are in the shared host frame (its copy stream drained)
-        svo.render_read_rgba8(vxp, W, H, frame8_ptr, bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptr, bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        if rank == 0:                          # while the GPUs trace: the next frame's inputs
+            for (o, l), b in zip(dirty, staged):
+                mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
+            svo.pack_dirty(dirty, packed_hosts[k & 1].numpy())
+        sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_hosts[k & 1])
+        svo.render_read_rgba8_end()            # THIS rank's stripes are in the shared host frame (its copy stream drained)
         step_words[rank] = k
         if rank == 0:
             while int(step_words[:n_gpus].min()) < k:   # the frame is whole: every rank's stripes of step k are in host memory
@@ -501,7 +504,7 @@ def main():
                "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16), "d2h_bytes_per_step": int(W * H * 4),
                "path": ("host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8 (%d bands: trace/shade overlapped with the "
                         "RGBA8 D2H copy into pinned host memory)" % args.bands) if n_gpus == 1 else
-                       "host dirty ranges -> pack -> H2D -> NCCL broadcast -> scatter -> every rank renders whole 16-pixel stripes "
+                       "host dirty ranges -> pack -> H2D -> NCCL broadcast (sent one step ahead, while the previous frame renders) -> scatter -> every rank renders whole 16-pixel stripes "
                        "(VX_SHARD_ROWS) and DMAs them itself into ONE page-locked host frame shared by the ranks (N PCIe links); rank 0 "
                        "returns when all stripes of the step are in host memory"}
         if n_gpus > 1 and rank == 0:

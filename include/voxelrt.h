@@ -259,6 +259,11 @@ int vx_render(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t
  * (bit-identical to vx_render + vx_read_frame_rgba8); the RGBA32F frame is NOT produced by this call. */
 int vx_render_read_rgba8(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
                          const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
+/* The same in two halves, for a caller that prepares the next frame's inputs while this one renders: _begin returns as soon as
+ * the frame and its band copies are enqueued, _end returns when the whole frame (this shard's stripes) is in rgba8_out. */
+int vx_render_read_rgba8_begin(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
+                               const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
+int vx_render_read_rgba8_end(VxCtx* ctx);
 
 /* Block until the last vx_render finished (the reference's render_fence.wait(), svo.rs:178). */
 int vx_render_wait(VxCtx* ctx);

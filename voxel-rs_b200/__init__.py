@@ -126,6 +126,7 @@ VX_SYMBOLS = [
     "vx_group_set_textures", "vx_group_set_option", "vx_group_svo_host_mirror", "vx_group_svo_set_hot_range", "vx_group_svo_commit",
     "vx_group_stats", "vx_group_render", "vx_group_wait", "vx_group_read_frame_rgba8", "vx_group_read_frame_rgba32f",
     "vx_group_host_frame", "vx_group_render_read_rgba8", "vx_group_raycast", "vx_probe_read_bandwidth",
+    "vx_render_read_rgba8_begin", "vx_render_read_rgba8_end",
 ]
 VX_SHARD_ROWS = 0x80000000
 
@@ -221,6 +222,8 @@ def lib():
         L.vx_group_render_read_rgba8.argtypes = [P, C.POINTER(VxRenderParams), u32, u32, P, u32]; L.vx_group_render_read_rgba8.restype = C.c_int
         L.vx_group_raycast.argtypes = [P, P, u64, P]; L.vx_group_raycast.restype = C.c_int
         L.vx_probe_read_bandwidth.argtypes = [P, u64, u32, C.POINTER(C.c_float)]; L.vx_probe_read_bandwidth.restype = C.c_int
+        L.vx_render_read_rgba8_begin.argtypes = [P, C.POINTER(VxRenderParams), u32, u32, C.POINTER(VxShard), P, u32]; L.vx_render_read_rgba8_begin.restype = C.c_int
+        L.vx_render_read_rgba8_end.argtypes = [P]; L.vx_render_read_rgba8_end.restype = C.c_int
     except AttributeError:
         if not os.environ.get("VOXELRT_AB_VARIANT"):   # only tools/ab_kernels.py may load an older build of the library
             raise
@@ -864,6 +867,15 @@ class Svo:
         self._check(lib().vx_render_read_rgba8(self.ctx, C.byref(vx_params), width, height, C.byref(sh) if sh else None,
                                                C.c_void_p(out_ptr), bands))
         self.width, self.height = width, height
+
+    def render_read_rgba8_begin(self, vx_params, width, height, out_ptr, bands=2, shard=None):
+        sh = VxShard(*shard) if shard else None
+        self._check(lib().vx_render_read_rgba8_begin(self.ctx, C.byref(vx_params), width, height, C.byref(sh) if sh else None,
+                                                     C.c_void_p(out_ptr), bands))
+        self.width, self.height = width, height
+
+    def render_read_rgba8_end(self):
+        self._check(lib().vx_render_read_rgba8_end(self.ctx))
 
     def commit(self, octree_scale, ranges, used_bytes, depth):
         """vx_svo_commit: ranges = [(offset, length)] relative to the RangeBuffer, bytes already in the host mirror."""

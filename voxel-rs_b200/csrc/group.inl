@@ -272,42 +272,38 @@ int vx_group_svo_commit(VxGroup* g, float octree_scale, const VxRange* dirty, ui
             std::memcpy(c0->h_stage + off, c0->h_mirror + c0->head + dirty[i].offset, dirty[i].length);
             off += dirty[i].length;
         }
-        for (uint32_t i = 0; i < g->n; ++i) {
-            VxCtx* c = g->ctx[i];
-            GCU(g, cudaSetDevice(g->dev[i]));
-            if (!c->d_stage) GCU(g, cudaMalloc(&c->d_stage, c->stage_cap));
-            GCU(g, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));             // do not tear a frame / ray batch in flight
-            GCU(g, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
-        }
-        GCU(g, cudaSetDevice(g->dev[0]));
-        GCU(g, cudaMemcpyAsync(c0->d_stage, c0->h_stage, bytes, cudaMemcpyHostToDevice, c0->s_upload));
-        int r = g->nccl.GroupStart();
-        for (uint32_t i = 0; i < g->n && r == 0; ++i)
-            r = g->nccl.Broadcast(c0->d_stage, g->ctx[i]->d_stage, bytes, /*ncclUint8*/ 1, 0, g->comms[i], g->ctx[i]->s_upload);
-        const int r2 = g->nccl.GroupEnd();
-        if (r == 0) r = r2;
-        if (r != 0) return gfail(g, VX_E_NCCL, "vx_group_svo_commit: ncclBroadcast: %s", g->nccl.GetErrorString(r));
     }
-    for (uint32_t i = 0; i < g->n; ++i) {
+    // every device's share — wait for its rays in flight, (device 0: the H2D copy,) its end of the broadcast, scatter, box, event —
+    // is issued by that device's worker thread: eight devices' launches in parallel instead of one after the other
+    const uint64_t hot_off = c0->hot_off, hot_len = c0->hot_len;
+    const int rc = g->run_all([=](uint32_t i) -> int {
         VxCtx* c = g->ctx[i];
-        GCU(g, cudaSetDevice(g->dev[i]));
+        CU(c, cudaSetDevice(g->dev[i]));
         if (n_dirty) {
+            if (!c->d_stage) CU(c, cudaMalloc(&c->d_stage, c->stage_cap));
+            CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));              // do not tear a frame / ray batch in flight
+            CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
+            if (i == 0) CU(c, cudaMemcpyAsync(c->d_stage, c->h_stage, bytes, cudaMemcpyHostToDevice, c->s_upload));
+            const int r = g->nccl.Broadcast(c->d_stage, c->d_stage, bytes, /*ncclUint8*/ 1, 0, g->comms[i], c->s_upload);
+            if (r != 0) return fail(c, VX_E_NCCL, "ncclBroadcast: %s", g->nccl.GetErrorString(r));
             const unsigned long long pb = c->head + total;
             const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
             scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, c->d_stage, n_dirty, pb, (uint32_t)c->head,
                                                                                      c->cfg.svo_capacity_bytes, c->d_flags + 62);
             c->launches++;
-            GCU(g, cudaGetLastError());
+            CU(c, cudaGetLastError());
             c->have_svo = true;
-            if (refresh_bounds(c, depth)) return gfail(g, VX_E_CUDA, "vx_group_svo_commit: %s", c->err.c_str());
+            const int rb = refresh_bounds(c, depth);
+            if (rb) return rb;
         }
-        GCU(g, cudaEventRecord(c->e_upload, c->s_upload));
+        CU(c, cudaEventRecord(c->e_upload, c->s_upload));
         c->stats.used_bytes = used_bytes; c->stats.depth = depth;
-        c->hot_off = c0->hot_off; c->hot_len = c0->hot_len;
+        c->hot_off = hot_off; c->hot_len = hot_len;
         install_l2_window(c);
-    }
-    GCU(g, cudaSetDevice(g->dev[0]));
-    return VX_OK;
+        return VX_OK;
+    });
+    if (rc == VX_E_NCCL) return gfail(g, VX_E_NCCL, "vx_group_svo_commit: %s", g->err.c_str());
+    return rc;
 }
 
 int vx_group_svo_set_hot_range(VxGroup* g, uint64_t offset, uint64_t length) {

@@ -927,6 +927,18 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     return VX_OK;
 }
 
+int vx_render_read_rgba8_begin(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
+                               uint32_t bands) {
+    return render_read_rgba8_issue(c, p, width, height, shard, rgba8_out, bands);
+}
+
+int vx_render_read_rgba8_end(VxCtx* c) {
+    if (!c) return VX_E_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->s_copy));
+    return VX_OK;
+}
+
 int vx_render_wait(VxCtx* c) {
     if (!c) return VX_E_ARG;
     CU(c, cudaSetDevice(c->cfg.device));

@@ -362,6 +362,11 @@ def main():
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name)
+            try:   # rank 0 owns (unlinks) the segment: keep this process' resource tracker from complaining about it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         shm_np = np.ndarray((nbytes,), dtype=np.uint8, buffer=shm.buf)
         rc = torch.cuda.cudart().cudaHostRegister(shm_np.ctypes.data, nbytes, 1)   # cudaHostRegisterPortable
         assert int(rc) == 0, f"cudaHostRegister: {rc}"

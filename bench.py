@@ -379,6 +379,8 @@ def main():
     else:
         frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
     e2e_step = [0]
+    trace_on = bool(os.environ.get("VX_BENCH_TRACE"))   # diagnostic: host-side phase times of the N > 1 e2e step on stderr
+    traces = []
     mirror = svo.host_mirror(HB + world.size_bytes)
     staged = [bytes(mirror[HB + o:HB + o + l]) for o, l in dirty]
 
@@ -398,22 +400,31 @@ def main():
         # Every step still copies one dirty set host -> device and reads one frame device -> host.
         e2e_step[0] += 1
         k = e2e_step[0]
+        tr = [time.perf_counter()] if trace_on else None
         sf.apply_dirty()                       # scatter of the set sent last step (stream-ordered behind the previous frame)
         if rank != 0:
             while step_words[63] < k - 1:      # rank 0 is done with the previous host frame
                 pass
+        if tr: tr.append(time.perf_counter())
         svo.render_read_rgba8_begin(vxp, W, H, frame8_ptr, bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        if tr: tr.append(time.perf_counter())
         if rank == 0:                          # while the GPUs trace: the next frame's inputs
             for (o, l), b in zip(dirty, staged):
                 mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
             svo.pack_dirty(dirty, packed_hosts[k & 1].numpy())
+        if tr: tr.append(time.perf_counter())
         sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_hosts[k & 1])
+        if tr: tr.append(time.perf_counter())
         svo.render_read_rgba8_end()            # THIS rank's stripes are in the shared host frame (its copy stream drained)
+        if tr: tr.append(time.perf_counter())
         step_words[rank] = k
         if rank == 0:
             while int(step_words[:n_gpus].min()) < k:   # the frame is whole: every rank's stripes of step k are in host memory
                 pass
             step_words[63] = k
+        if tr:
+            tr.append(time.perf_counter())
+            traces.append([(b - a) * 1e3 for a, b in zip(tr[:-1], tr[1:])])
 
     def barrier():
         if n_gpus > 1:
@@ -512,6 +523,10 @@ def main():
                        "host dirty ranges -> pack -> H2D -> NCCL broadcast (sent one step ahead, while the previous frame renders) -> scatter -> every rank renders whole 16-pixel stripes "
                        "(VX_SHARD_ROWS) and DMAs them itself into ONE page-locked host frame shared by the ranks (N PCIe links); rank 0 "
                        "returns when all stripes of the step are in host memory"}
+        if trace_on and traces and rank in (0, 1):
+            m = np.mean(np.array(traces[-args.steps:]), axis=0)
+            print(f"[trace rank {rank}] apply+ack-wait {m[0]:.3f} begin {m[1]:.3f} host-prep {m[2]:.3f} prefetch {m[3]:.3f} end {m[4]:.3f} poll {m[5]:.3f} ms",
+                  file=sys.stderr, flush=True)
         if n_gpus > 1 and rank == 0:
             # the host frame of the last e2e step against rank 0's own unsharded render: the shared frame is the frame
             svo.render_raw(vxp, W, H, shard=None)

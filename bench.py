@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true", help="serialized wavefront: shade_kernel starts only after trace_primary_kernel has finished (A/B)")
     ap.add_argument("--overlap", action="store_true", help="overlapped wavefront whatever the launch size (default: only for small launches)")
     ap.add_argument("--morton", action="store_true", help="A/B: Z-order enumeration of the macro blocks instead of row-major")
+    ap.add_argument("--lifo", type=int, default=-1, help="A/B: vx_set_option 14 value (1 order + store policy, +2 shade discards records, +4 shadow kernel discards its list)")
+    ap.add_argument("--no-lifo", action="store_true", help="A/B: streaming stores + producer order for the wavefront buffers instead of the LIFO hand-over (vx_set_option 14)")
     ap.add_argument("--no-clip", action="store_true", help="A/B: rays are not clipped against the occupied box of the world")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -76,6 +78,8 @@ def parse():
     ap.add_argument("--group", action="store_true", help="--gpus N from ONE process through vx_group_* (the reference's shape: a single process) "
                     "instead of one rank per GPU under torchrun")
     ap.add_argument("--rays", type=int, default=1 << 24, help="picker workload: number of rays")
+    ap.add_argument("--bin", type=int, default=-1, help="picker workload: ray binning (vx_set_option 15): bits per axis of the origin cell's Z-order code, "
+                    "+16 = direction octant below it, 0 = trace in task order; default: the library's (0 — binning measured a loss, profiles/r02_picker_binning.md)")
     ap.add_argument("--max-dst", type=float, default=-1.0, help="picker workload: max_dst of every task (-1 = unlimited)")
     return ap.parse_args()
 
@@ -292,6 +296,10 @@ def main():
         svo.set_option(pkg.OPT_TMA, 1)
     if args.morton:
         svo.set_option(pkg.OPT_MORTON, 1)
+    if args.no_lifo:
+        svo.set_option(14, 0)
+    elif args.lifo >= 0:
+        svo.set_option(14, args.lifo)
     if args.no_clip:
         svo.set_option(pkg.OPT_CLIP, 0)
     if args.no_overlap:
@@ -604,7 +612,7 @@ def main():
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)" + ("" if args.no_overlap else
                        "; for small launches (shards, small frames) shade runs next to trace_primary on its own stream, its CTAs wait per 32x4-pixel strip"), "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,
-            "sim_shard": args.sim_shard or None, "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
+            "sim_shard": args.sim_shard or None, "l2_window": not args.no_l2_window, "tma_tile_writeback": args.tma, "lifo_wavefront_buffers": (args.lifo if args.lifo > 0 and not args.no_lifo else 0), "world_gen_s": round(gen_s, 2), "parity_check": parity_check,
             "multi_gpu_step": (None if n_gpus == 1 else "NCCL broadcast of packed dirty ranges + scatter kernel, shard render, " +
                                ("finished pixels stored by the shade/shadow kernels straight into GPU 0's %s framebuffer over NVLink peer memory, "
                                 "frame flags in GPU 0's memory as the barrier; the broadcast of frame i+1 overlaps frame i on a side stream"
@@ -863,6 +871,8 @@ def run_picker(args):
     svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
     if args.refill:
         svo.set_option(pkg.OPT_REFILL_PICKER, args.refill)
+    if args.bin >= 0:
+        svo.set_option(15, args.bin)
     svo.update(world)
     tasks = picker_tasks(pkg, world, radius, n_total, max_dst=args.max_dst)[rank * n:(rank + 1) * n]
     t_host = torch.from_numpy(tasks.view(np.uint8).reshape(-1)).pin_memory()
@@ -945,6 +955,7 @@ def run_picker(args):
         "config": {"workload": f"{n_total} random-origin random-direction picker rays, generated-terrain ({terrain_name(args)}) r={radius} no-LOD world (BASELINE configs[3])",
                    "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "chunks": int(world.chunk_count), "max_dst": args.max_dst,
                    "parallelism": f"contiguous ray ranges over {world_size} GPU(s), SVO replicated, no collective", "refill_threshold": args.refill or 20,
+                   "ray_binning": ("off (task order)" if args.bin <= 0 else f"Z-order of origin cells, {args.bin & 15} bits/axis" + (" + direction octant" if args.bin & 16 else "") + " (bin_count/scan/scatter kernels inside the timed region)"),
                    "l2": "flushed between steps (160 MiB fill in the timed region); the SVO itself is larger than L2", "world_gen_s": round(gen_s, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "trace_picker_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg),

@@ -394,6 +394,19 @@ int vx_frame_stats(VxCtx* ctx, int which, VxFrameStats* out);
  *  10 = refill threshold of the shadow-ray kernel alone (0 = follow option 6)
  *  13 = A/B of the work order (default 0): enumerate the macro blocks of a whole, unsharded frame along a Z-order curve instead
  *       of row by row (north_star: "Morton/tile-ordered ray assignment"; measured: profiles/r02_ns1.md)
+ *  15 = ray binning of picker batches (default 0 = off; SURVEY §2.2 "optional Morton/direction-octant binning for the 16 M incoherent
+ *       config"): batches of at least 64 Ki rays are traced in Z-order of their ORIGIN cells — value & 15 = bits per axis of the cell
+ *       grid over the octree (1..8), + 16 = the ray's direction octant is appended below the cell code; at most 24 key bits. A counting
+ *       sort in one atomic pass (histogram + rank, exclusive scan, scatter: 5 small launches in front of the picker kernel, inside its
+ *       timed region). Results stay in task order and are bit-identical. Measured on configs[3] (16 Mi random rays, 0.8 GB world): a
+ *       LOSS — 4.87 vs 6.37 Grays/s: the pre-pass costs 0.50 ms, and the picker kernel, now gathering tasks and scattering results,
+ *       2.83 instead of 2.57 ms (profiles/r02_picker_binning.md); hence off
+ *  14 = LIFO hand-over of the wavefront buffers (default 0 = off; bit 0: hit records and shadow-list entries are written with the default
+ *       L2 policy instead of streaming stores and the consuming kernel starts with what was written LAST; bit 1: shade_kernel discards
+ *       every record line it has read (discard.global.L2: a dead dirty line needs no write-back) — vx_read_hit_records then refuses;
+ *       bit 2: trace_shadow_kernel discards its list the same way). Pixels are bit-identical. Measured: 1.506 vs 1.471 ms per 4K frame —
+ *       265 MB of records do not fit next to the 33 MB SVO in the 126 MB L2, they push the SVO out and trace_shadow_kernel pays for
+ *       it (0.498 vs 0.469 ms); profiles/r02_lifo.md
  *  12 = clip rays against the occupied box of the world (default 1): after every commit a small kernel finds the box that holds
  *       every voxel (chunk granularity); a ray that has left it can only miss, so its traversal stops there instead of walking
  *       the empty cells to the edge of the octree. Results are bit-identical; only the iteration counters shrink. 0 = off

@@ -185,11 +185,31 @@ Scene make_scene(const Device& d) {   // voxelrt.cu make_scene
 // that nvcc puts into libvoxelrt.so (loaded RTLD_GLOBAL by the package), and must not be interposed by them.
 #define EMU_API __attribute__((visibility("default")))
 
+// The ray-binning pre-pass exactly as launch_raycast issues it (voxelrt.cu): histogram + ranks, in-place exclusive scan, scatter.
+static void bin_order(const float4* tasks, uint64_t n, const uint32_t* scale_word, uint32_t bin, std::vector<uint32_t>& order, std::vector<uint32_t>& keys) {
+    const uint32_t bits_axis = bin & 15u, with_octant = (bin >> 4) & 1u;
+    const uint32_t key_bits = bin_key_bits(bits_axis, with_octant);
+    const size_t bins = (size_t)1 << (key_bits < 12 ? 12 : key_bits);
+    std::vector<uint32_t> hist(bins, 0u), sums(bins / VX_SCAN_TILE, 0u);
+    std::vector<uint2> keyrank(n);
+    order.assign(n, 0xffffffffu);
+    const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 3);
+    emu::launch(g ? g : 1, 256, [&] { bin_count_kernel(tasks, n, scale_word, bits_axis, with_octant, hist.data(), keyrank.data()); });
+    const unsigned n_tiles = (unsigned)(bins / VX_SCAN_TILE);
+    emu::launch(n_tiles, 256, [&] { bin_scan_reduce_kernel(hist.data(), sums.data()); });
+    emu::launch(1, 256, [&] { bin_scan_sums_kernel(sums.data(), n_tiles); });
+    emu::launch(n_tiles, 256, [&] { bin_scan_apply_kernel(hist.data(), sums.data()); });
+    emu::launch(g ? g : 1, 256, [&] { bin_scatter_kernel(keyrank.data(), n, hist.data(), order.data()); });
+    keys.resize(n);
+    for (uint64_t i = 0; i < n; ++i) keys[i] = keyrank[i].x;
+}
+
+
 extern "C" {
 
 // One frame through trace_primary_kernel -> shade_kernel -> trace_shadow_kernel exactly as vx_render issues them.
 // options: [0] refill threshold, [1] shadow refill (0 = same), [2] CTAs of the persistent kernels, [3] count, [4] RGBA8 output,
-// [5] TMA-style tile write-back, [6] shard rank, [7] shard size, [8] bands (vx_render_read_rgba8's banded wavefront; 0/1 = whole frame)
+// [5] bit 0 TMA-style tile write-back, bit 1 LIFO hand-over, [6] shard rank, [7] shard size, [8] bands (vx_render_read_rgba8's banded wavefront; 0/1 = whole frame)
 EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint32_t depth, const VxMaterial* materials, uint32_t n_materials,
                const uint8_t* tex_rgba8, uint32_t tw, uint32_t th, uint32_t layers, uint32_t mip_levels, const VxRenderParams* p, uint32_t width,
                uint32_t height, const uint32_t options[10], float* frame_out, uint32_t* frame8_out, uint64_t counters_out[6]) {
@@ -205,7 +225,7 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     a.u.hx = p->highlight_pos[0]; a.u.hy = p->highlight_pos[1]; a.u.hz = p->highlight_pos[2];
     a.u.render_shadows = p->render_shadows; a.u.shadow_distance = p->shadow_distance;
     a.u.width = width; a.u.height = height;
-    a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
+    set_macro_grid(a, width, height);
     const size_t slots = (size_t)a.macro_x * a.macro_y * 512;
     std::vector<float4> hit0(slots), hit1(slots), sh0(slots), sh1(slots), frame((size_t)width * height, float4{-1, -1, -1, -1});
     std::vector<uint32_t> sh_pix(slots), frame8((size_t)width * height, 0xdeadbeefu);
@@ -217,7 +237,8 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
     a.shard_rank = options[6]; a.shard_size = options[7] ? (options[7] & 0x7fffffffu) : 1; a.shard_rows = (options[7] >> 31) & 1u;
     a.refill_threshold = options[0] ? options[0] : 1;
     a.shadow_refill = options[1] ? options[1] : a.refill_threshold;
-    a.tma_writeback = options[5];
+    a.tma_writeback = options[5] & 1u;
+    a.lifo = ((options[5] >> 1) & 1u) ? 7u : 0u;   // LIFO hand-over of the wavefront buffers (discarded lines are poisoned here)
     // bands of macro-block rows, top of the image first, sizes shrinking by 0.6 (vx_render_read_rgba8); one band = vx_render
     uint32_t bands = options[8] ? options[8] : 1;
     if (bands > 16) bands = 16;
@@ -295,11 +316,28 @@ EMU_API int emu_raycast(const uint8_t* world, uint64_t world_bytes, int fmt, uin
     a.work_counter = &work;
     a.refill_threshold = options[0] ? options[0] : 24;
     const bool count = options[3] != 0, csvo = fmt == VX_FMT_CSVO;
+    std::vector<uint32_t> order;
+    if (options[4]) {   // ray binning (vx_set_option 15), the launches of launch_raycast
+        std::vector<uint32_t> keys;
+        bin_order(a.tasks, n, a.scene.desc - (csvo ? 2 : 1), options[4], order, keys);
+        a.order = order.data();
+    }
     emu::launch(options[2] ? options[2] : 3, VX_THREADS, [&] {
         if (csvo) { if (count) trace_picker_kernel<VX_FMT_CSVO, true>(a); else trace_picker_kernel<VX_FMT_CSVO, false>(a); }
         else { if (count) trace_picker_kernel<VX_FMT_ESVO, true>(a); else trace_picker_kernel<VX_FMT_ESVO, false>(a); }
     });
     if (counters_out) std::memcpy(counters_out, &counters, sizeof(Counters));
+    return 0;
+}
+
+// The binning pre-pass alone: order[] (a permutation of the task indices) and every task's key. scale = the world's octree_scale.
+EMU_API int emu_bin_order(const VxPickerTask* tasks, uint64_t n, float scale, uint32_t bin, uint32_t* order_out, uint32_t* keys_out) {
+    uint32_t scale_word;
+    std::memcpy(&scale_word, &scale, 4);
+    std::vector<uint32_t> order, keys;
+    bin_order(reinterpret_cast<const float4*>(tasks), n, &scale_word, bin, order, keys);
+    std::memcpy(order_out, order.data(), n * 4);
+    std::memcpy(keys_out, keys.data(), n * 4);
     return 0;
 }
 

@@ -132,8 +132,12 @@ def test_picker_random_rays_bit_exact(pkg, ora, reg):
             tasks["dir"][::17, 1] = 0.0          # exercise the epsilon clamp (svo.esvo.glsl:85-89)
             tasks["pos"][::5] = np.floor(tasks["pos"][::5]) + 0.5
             want, ocnt = s.raycast(tasks)
-            for refill in (24, 1, 32):
+            # bin = ray binning (vx_set_option 15: Z-order of the origin cells, bits per axis, +16 direction octant; 0 = task order). 200 k rays
+            # are above its threshold. Results never move: byte-identical in task order.
+            for refill, bin in ((24, 7 | 16), (1, 0), (32, 8), (20, 3 | 16)):
                 svo.set_option(pkg.OPT_REFILL_PICKER, refill)
+                if bin is not None:
+                    svo.set_option(15, bin)
                 svo.set_option(pkg.OPT_COUNT, 1)
                 got = svo.raycast_tasks(tasks)
                 assert got.tobytes() == want.tobytes(), (name, max_dst, refill, int((got["dst"] != want["dst"]).sum()))
@@ -235,7 +239,9 @@ def test_render_terrain_variants(pkg, ora, terrain):
     svo = make_svo(pkg, reg, world, size_mb=world.size_bytes // 1_000_000 + 8, w=w, h=h, rays=16)
     frames = {}
     # (refill threshold, CTAs/SM = register-budget build, TMA bulk-copy write-back of whole framebuffer strips; 270 rows leave a ragged strip)
-    for refill, ctas, tma in ((8, 0, 0), (1, 5, 1), (32, 6, 0), (20, 8, 1)):
+    # and the LIFO hand-over of the wavefront buffers, vx_set_option 14: reverse consumer order + discarded lines vs streaming stores)
+    for refill, ctas, tma, lifo in ((8, 0, 0, 7), (1, 5, 1, 3), (32, 6, 0, 0), (20, 8, 1, 1), (1, 0, 0, 0), (1, 0, 0, 7)):
+        svo.set_option(14, lifo)
         svo.set_option(pkg.OPT_TMA, tma)
         svo.set_option(pkg.OPT_REFILL, refill)
         svo.set_option(pkg.OPT_CTAS_PER_SM, ctas)
@@ -245,8 +251,8 @@ def test_render_terrain_variants(pkg, ora, terrain):
         st = svo.frame_stats(0)
         for k in ("primary_rays", "shadow_rays", "steps", "pushes", "leaf_tests", "tex_fetches"):
             assert st[k] == cnt[k], (refill, ctas, k, st, cnt)
-        frames[(refill, ctas, tma)] = got
-    base = frames[(8, 0, 0)]
+        frames[(refill, ctas, tma, lifo)] = got
+    base = frames[(8, 0, 0, 7)]
     for k, f in frames.items():
         assert f.tobytes() == base.tobytes(), k
     assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]   # trilinear path exercised
@@ -263,6 +269,11 @@ def test_primary_hits_bit_exact(pkg, ora, terrain):
     w, h = 320, 180
     p = terrain_params(pkg, w, h, shadows=False)
     svo = make_svo(pkg, reg, world, size_mb=max(8, world.size_bytes // 1_000_000 + 8), w=w, h=h, rays=16)
+    svo.set_option(14, 7)                                                 # LIFO hand-over: shade_kernel consumes (discards) the records
+    svo.render(p, w, h, world=world)
+    with pytest.raises(pkg.VxError, match="LIFO"):
+        svo.read_hit_records()
+    svo.set_option(14, 0)                                                 # the default keeps them
     svo.render(p, w, h, world=world)
     got = svo.read_hit_records()
     svo.close()
@@ -436,8 +447,9 @@ def test_full_size_16m_picker_rays_vs_oracle(pkg, ora):
     world.mark_all_dirty()
     svo.update(world)
     scene = helpers.oracle_scene(ora, world, reg)
-    for max_dst in (-1.0, 30.0):
+    for max_dst, bin in ((-1.0, 7 | 16), (30.0, 0)):   # binned, and in task order (the default)
         tasks = bench.picker_tasks(pkg, world, 40, n, seed=0, max_dst=max_dst)
+        svo.set_option(15, bin)
         svo.set_option(pkg.OPT_COUNT, 1)
         got = svo.raycast_tasks(tasks)
         st = svo.frame_stats(1)

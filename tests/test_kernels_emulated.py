@@ -58,8 +58,8 @@ def scene_args(world, reg):
                   C.c_uint32(len(mats)), C.c_void_p(tex.ctypes.data), C.c_uint32(tw), C.c_uint32(th), C.c_uint32(layers), C.c_uint32(mips)]
 
 
-def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1, bands=1, overlap=0):
-    return (C.c_uint32 * 10)(refill, shadow_refill, ctas, count, rgba8, tma, rank, size, bands, overlap)
+def opts(refill=1, shadow_refill=0, ctas=3, count=1, rgba8=0, tma=0, rank=0, size=1, bands=1, overlap=0, lifo=1):
+    return (C.c_uint32 * 10)(refill, shadow_refill, ctas, count, rgba8, tma | (lifo << 1), rank, size, bands, overlap)
 
 
 def emu_render(emu, pkg, world, reg, vxp, w, h, **kw):
@@ -109,8 +109,10 @@ def test_emulated_frame_equals_oracle(emu, pkg, ora, terrains, fmt):
     vxp = world_params(pkg, world, w, h, selected=(-20.0, 50.0, 174.0))
     want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
     assert cnt["shadow_rays"] > 0 and cnt["tex_fetches"] > cnt["leaf_tests"]
-    for refill, ctas in ((1, 3), (8, 1), (32, 5)):
-        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, ctas=ctas)
+    # lifo: the LIFO hand-over of the wavefront buffers (vx_set_option 14) — consumers walk the buffers backwards and discard what they
+    # have read; the emulator poisons every discarded line, so a line dropped too early (or somebody else's) changes the frame
+    for refill, ctas, lifo in ((1, 3, 1), (8, 1, 1), (32, 5, 1), (1, 2, 0)):
+        got, _, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, ctas=ctas, lifo=lifo)
         assert got.tobytes() == want.tobytes(), (fmt, refill, float(np.abs(got - want).max()))
         assert c == cnt, (fmt, refill, c, cnt)
     # RGBA8 output mode (vx_set_option 8 / vx_render_read_rgba8) and the staged tile write-back (vx_set_option 9)
@@ -178,15 +180,46 @@ def test_emulated_picker_equals_oracle(emu, pkg, ora, terrains, fmt):
     world = worlds[fmt]
     scene = helpers.oracle_scene(ora, world, reg)
     keep, args = scene_args(world, reg)
-    for max_dst, refill in ((-1.0, 24), (30.0, 1)):
+    # bin = ray binning (vx_set_option 15): the batch is traced in Z-order of the origin cells (bits per axis, +16: direction octant below);
+    # results stay in task order, so nothing changes in the output
+    for max_dst, refill, bin in ((-1.0, 24, 0), (30.0, 1, 0), (-1.0, 20, 7 | 16), (30.0, 24, 8), (-1.0, 1, 2)):
         tasks = bench.picker_tasks(pkg, world, 5, 3000, seed=3, max_dst=max_dst)
         want, cnt = scene.raycast(tasks)
         got = np.zeros(len(tasks), dtype=pkg.RESULT_DTYPE)
         c = (C.c_uint64 * 6)()
-        assert emu.emu_raycast(*args, C.c_void_p(tasks.ctypes.data), C.c_uint64(len(tasks)), C.c_void_p(got.ctypes.data), opts(refill=refill), c) == 0
+        assert emu.emu_raycast(*args, C.c_void_p(tasks.ctypes.data), C.c_uint64(len(tasks)), C.c_void_p(got.ctypes.data), opts(refill=refill, rgba8=bin), c) == 0
         assert got.tobytes() == want.tobytes(), (fmt, max_dst)
         assert (int(c[2]), int(c[3]), int(c[4])) == (cnt["steps"], cnt["pushes"], cnt["leaf_tests"])
         assert 0 < int((got["dst"] > 0).sum()) < len(tasks)
+
+
+def test_emulated_ray_binning_is_a_sorted_permutation(emu, pkg):
+    """bin_count / bin_scan_* / bin_scatter kernels: order[] is a permutation of the task indices, keys are non-decreasing along it, and the
+    key is the Z-order code of the origin cell (+ octant) — also for origins outside the octree, NaN origins and a ragged batch."""
+    rng = np.random.default_rng(5)
+    n = 10_000
+    tasks = np.zeros(n, dtype=pkg.TASK_DTYPE)
+    tasks["pos"] = rng.uniform(-40.0, 300.0, (n, 3)).astype(np.float32)      # octree of 256^3 voxels (scale 2^-8): some origins lie outside
+    tasks["pos"][:7] = np.nan
+    tasks["dir"] = rng.normal(size=(n, 3)).astype(np.float32)
+    emu.emu_bin_order.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
+    emu.emu_bin_order.restype = C.c_int
+    for bits, octant in ((7, 1), (8, 0), (3, 1), (1, 0)):
+        order, keys = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        assert emu.emu_bin_order(tasks.ctypes.data, n, 2.0 ** -8, bits | (octant << 4), order.ctypes.data, keys.ctypes.data) == 0
+        assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+        assert (np.diff(keys[order].astype(np.int64)) >= 0).all()
+        cells = 1 << bits
+        with np.errstate(invalid="ignore"):
+            c = np.clip(np.nan_to_num(tasks["pos"].astype(np.float32) * np.float32(2.0 ** -8 * cells), nan=0.0), 0, cells - 1).astype(np.uint32)
+        want = np.zeros(n, np.uint32)
+        for b in range(bits):
+            for ax in range(3):
+                want |= ((c[:, ax] >> b) & 1) << (3 * b + ax)
+        if octant:
+            d = tasks["dir"]
+            want = (want << 3) | (d[:, 0] > 0) | ((d[:, 1] > 0).astype(np.uint32) << 1) | ((d[:, 2] > 0).astype(np.uint32) << 2)
+        assert np.array_equal(keys, want), (bits, octant)
 
 
 def emu_raycast(emu, pkg, world, reg, tasks, **kw):
@@ -365,6 +398,7 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         shadow_refill = int(rng.choice([0, 1, 7, 32]))
         shadows, rgba8 = bool(rng.integers(0, 2)), int(rng.integers(0, 2))
         overlap = int(rng.integers(0, 2))
+        lifo = case % 3 != 0
         vxp = world_params(pkg, world, w, h, shadows=shadows, selected=(-20.0, 50.0, 174.0) if case % 2 else None)
         want, want8, cnt = oracle_render(pkg, ora, world, reg, vxp, w, h)
         union = np.full((h, w, 4), -1.0, np.float32)
@@ -372,7 +406,7 @@ def test_emulated_random_configurations(emu, pkg, ora, terrains):
         total = {k: 0 for k in cnt}
         for rank in range(size):
             got, got8, c = emu_render(emu, pkg, world, reg, vxp, w, h, refill=refill, shadow_refill=shadow_refill, ctas=ctas, rgba8=rgba8, rank=rank,
-                                      size=size | rows, bands=bands, overlap=overlap)
+                                      size=size | rows, bands=bands, overlap=overlap, lifo=int(lifo))
             mine = (got8.view(np.uint32)[..., 0] != 0xdeadbeef) if rgba8 else (got[..., 3] != -1.0)
             union[mine] = got[mine]
             union8[mine] = got8[mine]

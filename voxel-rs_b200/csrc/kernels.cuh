@@ -40,6 +40,7 @@ struct RenderArgs {
     Counters* counters;
     unsigned int* work_counter;   // persistent kernels: next unclaimed run
     uint32_t macro_x, macro_y;    // frame size in 32x16-pixel macro blocks
+    uint32_t macro_x_magic;       // floor(2^32 / macro_x) + 1: n / macro_x == __umulhi(n, magic) for n * macro_x < 2^32 (set_macro_grid)
     uint32_t macro0, n_macros;    // this launch covers macro blocks [macro0, macro0 + n_macros) (a band of macro rows, or the frame)
     uint32_t first_owned;         // first macro block >= macro0 owned by this shard
     uint32_t n_owned;             // macro blocks of [macro0, macro0 + n_macros) owned by this shard
@@ -61,6 +62,11 @@ struct RenderArgs {
     uint32_t shade_blocks;        // strips to shade in this launch (owned macro blocks x 4)
     uint32_t tma_writeback;       // shade_kernel: stage the strip's pixels in shared memory and write them back with bulk async
                                   // copies (TMA engine, cp.async.bulk -> SASS UBLKCP), one 512-byte row per copy
+    uint32_t lifo;                // bit 0: LIFO hand-over of the wavefront buffers (vx_set_option 14): hit records and shadow-list entries are
+                                  // stored with the default L2 policy, the consuming kernel walks them LAST WRITTEN FIRST (what the
+                                  // producer wrote last is what the 126 MB L2 still holds) and discards every line it has read
+                                  // (discard.global.L2: a dirty line that is dead needs no write-back; bit 1: shade_kernel discards the
+                                  // hit records, bit 2: trace_shadow_kernel discards the shadow list) — see wave_discard()
 };
 
 // Work units. The frame is cut into macro blocks of 32x16 pixels (row-major over the frame; a shard owns every
@@ -68,14 +74,27 @@ struct RenderArgs {
 // side, and pixel p of a strip is lane p%32 of tile p/32: consecutive work indices, consecutive pixels of a warp and
 // consecutive tiles of a strip are all spatial neighbours (coherent rays, shared nodes in L1).
 // Pixel slot (index into hit0/hit1) = strip * 128 + p.
+// Frame size in macro blocks + the multiplier that replaces the kernels' divisions by macro_x (every shade CTA and every work fetch of
+// the tracing kernels turns a macro-block index into a position: an integer division is ~20 instructions, the multiply is one).
+inline void set_macro_grid(RenderArgs& a, uint32_t width, uint32_t height) {
+    a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
+    a.macro_x_magic = a.macro_x > 1 ? (uint32_t)(0x100000000ull / a.macro_x) + 1u : 0u;   // exact while macro blocks x macro_x < 2^32 (a 64K x 64K frame)
+}
+__host__ __device__ __forceinline__ uint32_t div_macro_x(const RenderArgs& a, uint32_t n) {
+#if defined(__CUDA_ARCH__) || defined(VX_HOST_EMULATION)
+    return a.macro_x_magic ? __umulhi(n, a.macro_x_magic) : n;
+#else
+    return n / a.macro_x;
+#endif
+}
 __host__ __device__ __forceinline__ bool macro_owned(const RenderArgs& a, uint32_t macro) {
     if (a.shard_size <= 1) return true;
-    return (a.shard_rows ? (macro / a.macro_x) % a.shard_size : macro % a.shard_size) == a.shard_rank;
+    return (a.shard_rows ? div_macro_x(a, macro) % a.shard_size : macro % a.shard_size) == a.shard_rank;
 }
 // k-th macro block this shard owns inside the band of the launch (first_owned: its first owned macro block, resp. macro ROW)
 __device__ __forceinline__ uint32_t owned_macro(const RenderArgs& a, uint32_t k) {
     if (!a.shard_rows) return a.first_owned + k * a.shard_size;
-    const uint32_t j = k / a.macro_x;
+    const uint32_t j = div_macro_x(a, k);
     return (a.first_owned + j * a.shard_size) * a.macro_x + (k - j * a.macro_x);
 }
 // Band [row0, row1) of macro rows: what of it this shard owns. Host side of the launch (voxelrt.cu, and tests/emu's stand-in for it).
@@ -95,8 +114,9 @@ inline void shard_band(RenderArgs& a, uint32_t row0, uint32_t row1) {
 __device__ __forceinline__ bool strip_origin(const RenderArgs& a, uint32_t strip, uint32_t& x0, uint32_t& y0) {
     const uint32_t macro = strip >> 2;
     if (!macro_owned(a, macro)) return false;
-    x0 = (macro % a.macro_x) * 32;
-    y0 = (macro / a.macro_x) * 16 + (strip & 3u) * 4;
+    const uint32_t row = div_macro_x(a, macro);
+    x0 = (macro - row * a.macro_x) * 32;
+    y0 = row * 16 + (strip & 3u) * 4;
     return x0 < a.u.width && y0 < a.u.height;
 }
 __device__ __forceinline__ void strip_pixel(uint32_t x0, uint32_t y0, uint32_t p, uint32_t& gx, uint32_t& gy) {
@@ -163,11 +183,18 @@ __device__ __forceinline__ bool render_leaf(Walk& w, const Scene& s, const Smem&
 // The walk loop of a warp: every lane with a live ray steps it; the warp leaves the loop when fewer than `thresh` lanes are
 // still walking. thresh == 1 (run every ray of the warp to its end, then refill all 32 lanes at once) needs no population
 // count and gets its own copy of the loop.
-template <int FMT, bool LIMITED, bool COUNT>
+// TWO = two steps per warp vote in the threshold-1 loop. Measured (profiles/r02_step_variants.md, 4K frame): trace_primary_kernel
+// 0.771 -> 0.752 ms, trace_shadow_kernel 0.498 -> 0.544 ms — the lanes of a coherent primary tile stay in the same phase and save the vote,
+// its WARPSYNC and the loop branch every other iteration; shadow rays start in 32 different voxels and the second, nested step runs
+// once per phase group of the first. So the primary kernel (ESVO) instantiates it and the others do not.
+template <int FMT, bool LIMITED, bool COUNT, bool TWO = false>
 __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, Counters& cnt, int thresh) {
     if (thresh <= 1) {
         do {
-            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+            if (w.state > 0) {
+                walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+                if (TWO && w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+            }
         } while (__any_sync(0xffffffffu, w.state > 0));
     } else {
         do {
@@ -197,6 +224,27 @@ __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
 __device__ __forceinline__ void store_pixel(const RenderArgs& a, uint32_t pix, float4 c) {
     if (a.frame8) __stcs(a.frame8 + pix, pack_rgba8(c));
     else __stcs(a.frame + pix, c);
+}
+
+// ---- LIFO hand-over of the wavefront buffers ---------------------------------------------------------------------------------------
+// The hit records (32 B per pixel) and the shadow list (36 B per entry) are written once and read once; as streaming (evict-first)
+// stores behind a frame-sized kernel they all went to HBM and came back (profiles/r02_v5_frame_wavefront.md: 0.78 GB of DRAM traffic
+// per 4K frame against 0.17 GB compulsory). With RenderArgs::lifo the consumer starts at the producer's END, where the lines are
+// still dirty in L2, and tells the L2 that a line it has consumed is dead: no fill from HBM, no write-back to HBM for that part.
+// MEASURED AND OFF BY DEFAULT (profiles/r02_lifo.md): 265 MB of records with normal priority evict the 33 MB SVO from the 126 MB L2;
+// trace_shadow_kernel loses more (0.469 -> 0.498 ms) than shade_kernel could ever gain on a path that is issue-bound, not DRAM-bound.
+// A warp's 32 records are 512 contiguous, 512-byte-aligned bytes of each array = four 128-byte lines: lanes 0-3 drop them.
+__device__ __forceinline__ void wave_discard(const void* line) {
+#ifndef VX_HOST_EMULATION
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+#else
+    std::memset(const_cast<void*>(line), 0xCD, 128);   // the emulator poisons what the product declares dead: a later read would show
+#endif
+}
+// A value that is 0, but only known once `loaded` has arrived in EVERY lane of the warp (the shuffle reads the warp's register):
+// added to the address of a discard it keeps the discard behind the loads of the lines it drops.
+__device__ __forceinline__ uint32_t after_warp_loads(uint32_t loaded) {
+    return loaded - __shfl_sync(0xffffffffu, loaded, (int)(threadIdx.x & 31u));
 }
 
 // ---- overlapped wavefront: strip completion flags ------------------------------------------------------------------------------
@@ -244,6 +292,9 @@ __device__ __forceinline__ void strip_wait(const unsigned int* strip_done, uint3
 // ---- primary rays ------------------------------------------------------------------------------------------------------
 #ifndef VX_PRIMARY_CLIP
 #define VX_PRIMARY_CLIP true   // world-box clipping of primary rays (A/B: tools/ab_kernels.py builds a variant with false)
+#endif
+#ifndef VX_PRIMARY_UNROLL2
+#define VX_PRIMARY_UNROLL2 true   // two steps per vote in the primary kernel's walk loop (A/B: a variant build with false)
 #endif
 template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
@@ -310,7 +361,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT, FMT == VX_FMT_ESVO && VX_PRIMARY_UNROLL2>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         bool finished = false;
@@ -320,15 +371,18 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
                 float px, py, pz;
                 leaf_pos(w.t_min, cold[0], cold[VX_THREADS], cold[2 * VX_THREADS], cold[3 * VX_THREADS], cold[4 * VX_THREADS], cold[5 * VX_THREADS], g,
                          inv_scale, px, py, pz);
-                __stcs(a.hit0 + slot, make_float4(g.dst, __uint_as_float(g.value), g.u, g.v));
-                __stcs(a.hit1 + slot, make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id)));
+                const float4 r0 = make_float4(g.dst, __uint_as_float(g.value), g.u, g.v);
+                const float4 r1 = make_float4(px, py, pz, __uint_as_float(8u | (uint32_t)g.face_id));
+                if (a.lifo) { a.hit0[slot] = r0; a.hit1[slot] = r1; }      // stays in L2 for shade_kernel (LIFO hand-over)
+                else { __stcs(a.hit0 + slot, r0); __stcs(a.hit1 + slot, r1); }
                 w.state = ST_IDLE;
                 finished = true;
             } else {
                 walk_skip_leaf<FMT, VX_PRIMARY_CLIP>(w, a.scene, sm.stack);   // translucent / repeated leaf: finish this iteration at ADVANCE
             }
         } else if (state_missed(w.state)) {
-            __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            if (a.lifo) a.hit1[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            else __stcs(a.hit1 + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             w.state = ST_IDLE;
             finished = true;
         }
@@ -349,7 +403,7 @@ __global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(Ren
     __shared__ unsigned int s_next;
     Counters cnt = {0, 0, 0, 0, 0, 0};
     // static grid: CTA b shades strip b. Overlapped wavefront: the CTAs of a small resident grid claim strips from shade_counter.
-    for (uint32_t blk = blockIdx.x;;) {
+    for (uint32_t blk = (!PERSIST && a.lifo) ? a.shade_blocks - 1u - blockIdx.x : blockIdx.x;;) {   // LIFO: the strips traced last first
     if (PERSIST) {
         __syncthreads();   // everybody is done with the shared arrays of the previous strip (and with s_next)
         if (threadIdx.x == 0) s_next = atomicAdd(a.shade_counter, 1u);
@@ -375,10 +429,17 @@ __global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(Ren
     __shared__ __align__(128) float4 s_tile[VX_THREADS];
     const bool tile_store = a.tma_writeback && !a.frame8 && have && x0 + 32u <= a.u.width && y0 + 4u <= a.u.height;   // CTA-uniform
     float4* const tile_slot = s_tile + ((threadIdx.x >> 3) & 3u) * 32u + (threadIdx.x >> 5) * 8u + (threadIdx.x & 7u);
+    const uint32_t slot = strip * 128u + threadIdx.x;
+    float4 h0 = make_float4(0, 0, 0, 0), h1 = make_float4(0, 0, 0, 0);
     if (live) {
-        const uint32_t slot = strip * 128u + threadIdx.x;
-        const float4 h1 = __ldcs(a.hit1 + slot);
-        const float4 h0 = __ldcs(a.hit0 + slot);   // issued together with h1 (a miss leaves its hit0 slot unwritten: loaded, never used)
+        if (a.lifo) { h1 = __ldcg(a.hit1 + slot); h0 = __ldcg(a.hit0 + slot); }
+        else { h1 = __ldcs(a.hit1 + slot); h0 = __ldcs(a.hit0 + slot); }   // issued together (a miss leaves its hit0 slot unwritten: loaded, never used)
+    }
+    if ((a.lifo & 2u) && have) {   // CTA-uniform. This warp's records are read: their eight lines are dead (lanes 0-3 hit0, 4-7 hit1)
+        const uint32_t zero = after_warp_loads(__float_as_uint(h0.x) ^ __float_as_uint(h1.w));
+        if (lane < 8u) wave_discard(((lane & 4u) ? a.hit1 : a.hit0) + (slot - lane) + (lane & 3u) * 8u + zero);
+    }
+    if (live) {
         const uint32_t flags = __float_as_uint(h1.w);
         if (flags & 8u) {
             Leaf g;
@@ -468,16 +529,30 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
     float lit = 0.0f;
     Walk w;
     w.state = ST_IDLE;
+    // LIFO hand-over (RenderArgs::lifo): runs are claimed from the END of the list (what shade_kernel appended last is still in L2),
+    // and (bit 2 of lifo) a run whose 32 rays are all finished is discarded: 4 lines of sh0, 4 of sh1, 1 of sh_pix (lanes 0-8). Only
+    // with shadow_refill == 1, where a warp claims a new run when — and only when — every ray of the previous one is done.
+    const bool lifo = a.lifo != 0u, lifo_discard = (a.lifo & 4u) && a.shadow_refill <= 1u;
+    const uint32_t n_runs = (n + 31u) / 32u;
+    uint32_t dead_run = 0xffffffffu;
 
     for (;;) {
         unsigned want = __ballot_sync(0xffffffffu, w.state == ST_IDLE);
         while (want && more_work) {
             if (next >= run_len) {
+                if (lifo_discard && dead_run != 0xffffffffu && want == 0xffffffffu) {
+                    if (lane < 4u) wave_discard(a.sh0 + dead_run + lane * 8u);
+                    else if (lane < 8u) wave_discard(a.sh1 + dead_run + (lane - 4u) * 8u);
+                    else if (lane == 8u) wave_discard(a.sh_pix + dead_run);
+                    dead_run = 0xffffffffu;
+                }
                 if (lane == 0) run_base = atomicAdd(a.work_counter, 32u);
                 run_base = __shfl_sync(0xffffffffu, run_base, 0);
                 if (run_base >= n) { more_work = false; break; }
+                if (lifo) run_base = (n_runs - 1u - run_base / 32u) * 32u;
                 run_len = min(32u, n - run_base);
                 next = 0;
+                if (run_len == 32u) dead_run = run_base;   // (a ragged last run shares its lines with nothing, but is not worth a special case)
             }
             const uint32_t n_take = min((uint32_t)__popc(want), run_len - next);
             const uint32_t my_rank = __popc(want & lanemask_lt);
@@ -538,6 +613,7 @@ struct RaycastArgs {
     Counters* counters;
     unsigned long long* work_counter;
     uint32_t refill_threshold;
+    const uint32_t* order;    // non-null: the k-th ray traced is task order[k] (ray binning, see bin_count_kernel); results stay in task order
 };
 
 template <int FMT, bool COUNT>
@@ -572,6 +648,7 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
             const uint32_t my_rank = __popc(want & lanemask_lt);
             if (((want >> lane) & 1u) && my_rank < n_take) {
                 my_task = run_base + next + my_rank;
+                if (a.order) my_task = __ldcs(a.order + my_task);
                 const float4 t0 = __ldcs(a.tasks + 3 * my_task), t1 = __ldcs(a.tasks + 3 * my_task + 1), t2 = __ldcs(a.tasks + 3 * my_task + 2);
                 float rox, roy, roz, rdx, rdy, rdz;
                 walk_init<FMT>(w, a.scene, clip, octree_scale, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, t0.x, rox, roy, roz, rdx, rdy, rdz);
@@ -609,6 +686,106 @@ __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a)
         }
     }
     if (COUNT) flush_counters(a.counters, cnt);
+}
+
+// ---- ray binning for incoherent picker batches ("optional Morton/direction-octant binning for the 16 M incoherent config") ----
+// A batch of random rays starts anywhere in the world; the 32 rays of a warp then descend through 32 unrelated chains of nodes
+// (every node a cache miss) and, refilled at different times, are never in the same phase of the walk. The pre-pass orders the
+// rays along a Z-order curve of their ORIGIN cell (optionally direction octant below it): rays traced together start in the same
+// corner of the octree, so the root-to-origin descent — more than half of a picker ray's iterations — reads the same nodes and
+// runs in lock-step. It is a counting sort in one atomic pass:
+//   bin_count_kernel    key = Morton code of the origin cell [| octant]; rank inside the bin = atomicAdd(hist[key], 1)
+//   bin_scan_*          exclusive prefix sum over the histogram, in place (reduce / scan of the block sums / apply)
+//   bin_scatter_kernel  order[offset[key] + rank] = task index
+// The order inside a bin depends on the atomics' timing; nothing observable does: the picker kernel writes result i for task i.
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // bits 0-9 of v -> bits 0, 3, 6, ... (Morton interleave of one axis)
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t bin_key_bits(uint32_t bits_axis, uint32_t with_octant) { return 3u * bits_axis + (with_octant ? 3u : 0u); }
+__global__ void __launch_bounds__(256) bin_count_kernel(const float4* tasks, unsigned long long n, const uint32_t* scale_word, uint32_t bits_axis,
+                                                        uint32_t with_octant, uint32_t* hist, uint2* keyrank) {
+    const float cells = (float)(1u << bits_axis);
+    const float to_cell = __uint_as_float(__ldg(scale_word)) * cells;          // octree_scale maps SVO voxel space to [0, 1): x cells
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 pos = __ldg(tasks + 3 * i + 1);
+        // fmaxf / fminf return the non-NaN operand: a NaN origin lands in cell 0, an origin outside the octree in the nearest border cell
+        const uint32_t cx = (uint32_t)fminf(fmaxf(pos.x * to_cell, 0.0f), cells - 1.0f);
+        const uint32_t cy = (uint32_t)fminf(fmaxf(pos.y * to_cell, 0.0f), cells - 1.0f);
+        const uint32_t cz = (uint32_t)fminf(fmaxf(pos.z * to_cell, 0.0f), cells - 1.0f);
+        uint32_t key = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+        if (with_octant) {
+            const float4 dir = __ldg(tasks + 3 * i + 2);
+            key = (key << 3) | (dir.x > 0.0f ? 1u : 0u) | (dir.y > 0.0f ? 2u : 0u) | (dir.z > 0.0f ? 4u : 0u);   // octant_mask, svo.esvo.glsl:112-126
+        }
+        const uint32_t rank = atomicAdd(hist + key, 1u);
+        keyrank[i] = make_uint2(key, rank);
+    }
+}
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const uint2* keyrank, unsigned long long n, const uint32_t* offsets, uint32_t* order) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 kr = keyrank[i];
+        order[__ldg(offsets + kr.x) + kr.y] = (uint32_t)i;
+    }
+}
+// Exclusive prefix sum of `data[0, n)` in place, n a multiple of VX_SCAN_TILE: block b owns elements [b * TILE, (b + 1) * TILE), thread t of
+// it the 16 consecutive ones from t * 16.
+#define VX_SCAN_TILE 4096u
+__device__ __forceinline__ uint32_t scan_block_exclusive(uint32_t mine, uint32_t* total) {   // exclusive scan of one value per thread over 256 threads
+    __shared__ uint32_t s_scan[2][256];
+    uint32_t cur = 0;
+    s_scan[0][threadIdx.x] = mine;
+    __syncthreads();
+    for (uint32_t d = 1; d < 256u; d <<= 1) {
+        const uint32_t v = s_scan[cur][threadIdx.x] + (threadIdx.x >= d ? s_scan[cur][threadIdx.x - d] : 0u);
+        s_scan[cur ^ 1u][threadIdx.x] = v;
+        cur ^= 1u;
+        __syncthreads();
+    }
+    const uint32_t incl = s_scan[cur][threadIdx.x];
+    if (total) *total = s_scan[cur][255];
+    __syncthreads();   // the arrays may be reused by the caller's next call
+    return incl - mine;
+}
+__global__ void __launch_bounds__(256) bin_scan_reduce_kernel(const uint32_t* data, uint32_t* block_sums) {
+    const uint4* p = reinterpret_cast<const uint4*>(data + (size_t)blockIdx.x * VX_SCAN_TILE + threadIdx.x * 16u);
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const uint4 v = p[k]; sum += v.x + v.y + v.z + v.w; }
+    uint32_t total;
+    scan_block_exclusive(sum, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) bin_scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks) {   // one CTA: exclusive scan of the block sums
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_blocks; base += 256u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = scan_block_exclusive(v, &total);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(256) bin_scan_apply_kernel(uint32_t* data, const uint32_t* block_sums) {
+    uint4* p = reinterpret_cast<uint4*>(data + (size_t)blockIdx.x * VX_SCAN_TILE + threadIdx.x * 16u);
+    uint4 v[4];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = p[k]; sum += v[k].x + v[k].y + v[k].z + v[k].w; }
+    uint32_t run = block_sums[blockIdx.x] + scan_block_exclusive(sum, nullptr);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint4 o;
+        o.x = run; run += v[k].x; o.y = run; run += v[k].y; o.z = run; run += v[k].z; o.w = run; run += v[k].w;
+        p[k] = o;
+    }
 }
 
 // ---- debug cast: svo.test.glsl main(), one thread, records every iteration --------------------------------------------

@@ -104,7 +104,7 @@ __device__ __forceinline__ Smem make_smem(const float* unorm_table, uint32_t sta
     m.stack = (uint32_t)__cvta_generic_to_shared(base + threadIdx.x);
     asm volatile("" : "+r"(m.stack));   // opaque from here on: one live register instead of a per-iteration recomputation
     float* lut = reinterpret_cast<float*>(base + stack_words);
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __ldg(unorm_table + i);
+    for (uint32_t i = threadIdx.x; i < 256; i += VX_THREADS) lut[i] = __ldg(unorm_table + i);   // (every kernel that calls this runs VX_THREADS threads)
     m.unorm = lut;
     m.cold = lut + 256 + threadIdx.x;
     __syncthreads();
@@ -118,7 +118,13 @@ __device__ __forceinline__ int ifloor_clamped(float x) {
     if (!(x == x)) return 0;
     return (int)floorf(x);
 }
-__device__ __forceinline__ int imod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
+// GL_REPEAT index: a mod n, non-negative. Texture sizes are powers of two in practice (the reference's atlas is 32x32): then it is one AND
+// (two's complement makes it right for negative a too) instead of an integer division — 8 of them per trilinear sample.
+__device__ __forceinline__ int imod(int a, int n) {
+    if ((n & (n - 1)) == 0) return a & (n - 1);
+    int r = a % n;
+    return r < 0 ? r + n : r;
+}
 __device__ __forceinline__ int iclamp(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
 
 __device__ __forceinline__ float4 fetch_texel(const TexInfo* ti, const float* unorm, uint32_t level, uint32_t wl, uint32_t hl, int layer, int i, int j) {

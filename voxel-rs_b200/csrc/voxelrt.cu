@@ -24,6 +24,14 @@ using namespace vx;
 static thread_local std::string g_create_error;
 
 struct GridCacheEntry;
+// Ray binning of picker batches (vx_set_option 15): value = bits per axis of the origin cell's Z-order code (1..8) + 16 to append the
+// direction octant; batches below VX_BIN_MIN_RAYS are traced in task order (the pre-pass is five launches). Default OFF: measured a loss
+// on BASELINE configs[3] (profiles/r02_picker_binning.md: the pre-pass costs 0.50 ms and the picker kernel itself gets 10 % slower).
+#ifndef VX_BIN_DEFAULT
+#define VX_BIN_DEFAULT 0u
+#endif
+static constexpr uint64_t VX_BIN_MIN_RAYS = 1ull << 16;
+
 struct VxCtx {
     VxConfig cfg{};
     int sm_count = 0;
@@ -87,6 +95,10 @@ struct VxCtx {
 
     float4* d_tasks = nullptr;
     float4* d_results = nullptr;
+    // ray binning scratch of the picker path (bin_count_kernel ...), allocated on first use
+    uint32_t* d_bin_hist = nullptr; uint32_t bin_hist_bits = 0;
+    uint32_t* d_bin_sums = nullptr;
+    uint2* d_bin_keyrank = nullptr; uint32_t* d_bin_order = nullptr; uint64_t bin_cap = 0;
 
     Counters* d_counters = nullptr;   // [0] render, [1] raycast
     unsigned long long* d_work = nullptr;   // u64[4] picker run counter, u64[6] chunk bump pointer, u64[7] its overflow flag; from byte 64:
@@ -106,7 +118,8 @@ struct VxCtx {
     std::vector<struct GridCacheEntry> grid_cache;
 
     // options (vx_set_option)
-    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 20, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2, opt_clip = 1, opt_morton = 0;
+    uint64_t opt_count = 0, opt_ctas_per_sm = 0, opt_l2_window = 1, opt_refill = 1, opt_refill_picker = 20, opt_rgba8_out = 0, opt_tma = 0, opt_refill_shadow = 0, opt_overlap = 2, opt_clip = 1, opt_morton = 0, opt_lifo = 0, opt_bin = VX_BIN_DEFAULT;
+    bool hits_discarded = false;      // the last frame's hit records were consumed destructively (LIFO hand-over, vx_set_option 14)
 };
 
 static int fail(VxCtx* ctx, int code, const char* fmt, ...) {
@@ -281,6 +294,10 @@ void vx_destroy(VxCtx* c) {
     if (c->d_sh0) cudaFree(c->d_sh0);
     if (c->d_sh1) cudaFree(c->d_sh1);
     if (c->d_sh_pix) cudaFree(c->d_sh_pix);
+    if (c->d_bin_hist) cudaFree(c->d_bin_hist);
+    if (c->d_bin_sums) cudaFree(c->d_bin_sums);
+    if (c->d_bin_keyrank) cudaFree(c->d_bin_keyrank);
+    if (c->d_bin_order) cudaFree(c->d_bin_order);
     for (cudaEvent_t ev : c->t_wave) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->e_band) if (ev) cudaEventDestroy(ev);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
@@ -316,6 +333,12 @@ int vx_set_option(VxCtx* ctx, uint32_t option, uint64_t value) {
         case 11: ctx->opt_overlap = value > 2 ? 2 : value; break;
         case 12: ctx->opt_clip = value ? 1 : 0; break;
         case 13: ctx->opt_morton = value ? 1 : 0; break;
+        case 14: ctx->opt_lifo = value > 7 ? 7 : value; break;
+        case 15:
+            if (value && ((value & 15u) < 1 || (value & 15u) > 8 || (value >> 5) || bin_key_bits((uint32_t)(value & 15u), (uint32_t)((value >> 4) & 1u)) > 24))
+                return fail(ctx, VX_E_ARG, "vx_set_option 15: bits per axis 1..8 (+16 for the direction octant), at most 24 key bits");
+            ctx->opt_bin = value;
+            break;
         default: return fail(ctx, VX_E_ARG, "vx_set_option: unknown option %u", option);
     }
     return VX_OK;
@@ -632,6 +655,9 @@ static int ensure_wave_buffers(VxCtx* c, size_t slots) {
     return VX_OK;
 }
 
+#ifndef VX_TOP_MINB
+#define VX_TOP_MINB 8   // resident CTAs per SM the default build of the trace kernels is compiled for (64 registers); A/B builds set 9 (56)
+#endif
 // register budget variant of the persistent trace kernels: CTAs/SM the allocator must allow (vx_set_option 4)
 static int pick_minb(const VxCtx* c) { return c->opt_ctas_per_sm == 0 ? 8 : (c->opt_ctas_per_sm <= 5 ? 5 : (c->opt_ctas_per_sm <= 7 ? 6 : 8)); }
 
@@ -669,7 +695,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
     const int minb = pick_minb(c);
     void (*k1)(RenderArgs) = nullptr;
     void (*k3)(RenderArgs) = nullptr;
-#define VX_PICK(K, F, C) (minb == 5 ? K<F, C, 5> : (minb == 6 ? K<F, C, 6> : K<F, C, 8>))
+#define VX_PICK(K, F, C) (minb == 5 ? K<F, C, 5> : (minb == 6 ? K<F, C, 6> : K<F, C, VX_TOP_MINB>))
     if (c->fmt == VX_FMT_CSVO) {
         if (count) { k1 = VX_PICK(trace_primary_kernel, VX_FMT_CSVO, true); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_CSVO, true); }
         else { k1 = VX_PICK(trace_primary_kernel, VX_FMT_CSVO, false); k3 = VX_PICK(trace_shadow_kernel, VX_FMT_CSVO, false); }
@@ -790,7 +816,7 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.u.hx = p->highlight_pos[0]; a.u.hy = p->highlight_pos[1]; a.u.hz = p->highlight_pos[2];
     a.u.render_shadows = p->render_shadows; a.u.shadow_distance = p->shadow_distance;
     a.u.width = width; a.u.height = height;
-    a.macro_x = (width + 31) / 32; a.macro_y = (height + 15) / 16;
+    set_macro_grid(a, width, height);
     rc = ensure_wave_buffers(c, (size_t)a.macro_x * a.macro_y * 512);
     if (rc) return rc;
     a.frame = c->frame_target ? c->frame_target : c->d_frame;
@@ -803,6 +829,8 @@ static int prepare_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uin
     a.refill_threshold = (uint32_t)c->opt_refill;
     a.shadow_refill = (uint32_t)(c->opt_refill_shadow ? c->opt_refill_shadow : c->opt_refill);
     a.tma_writeback = (c->opt_tma && !c->frame_target) ? 1u : 0u;   // bulk stores only into the local framebuffer
+    a.lifo = (uint32_t)c->opt_lifo;
+    c->hits_discarded = (a.lifo & 2u) != 0;
     CU(c, cudaStreamWaitEvent(c->s_render, c->e_upload, 0));
     CU(c, cudaMemsetAsync(reinterpret_cast<unsigned int*>(c->d_work) + 16, 0, VX_MAX_BANDS * 32 + sizeof(Counters), c->s_render));   // work counters + render Counters
     // overlapped wavefront (vx_set_option 11, default on; needs "finish all 32 rays, then refill" = refill threshold 1 only for its
@@ -980,6 +1008,9 @@ int vx_frame_device_ptr(VxCtx* c, void** out_ptr, uint32_t* width, uint32_t* hei
 
 int vx_read_hit_records(VxCtx* c, VxHitRecord* out) {
     if (!c || !out || !c->frame_w || !c->d_hit0) return fail(c, VX_E_ARG, "vx_read_hit_records: nothing rendered / null");
+    if (c->hits_discarded)
+        return fail(c, VX_E_STATE, "vx_read_hit_records: the frame was rendered with the LIFO hand-over, which discards the hit records as "
+                                   "they are shaded; vx_set_option(ctx, 14, 0) before the render keeps them");
     CU(c, cudaSetDevice(c->cfg.device));
     const uint32_t w = c->frame_w, h = c->frame_h, macro_x = (w + 31) / 32, macro_y = (h + 15) / 16;
     const size_t slots = (size_t)macro_x * macro_y * 512;
@@ -1027,6 +1058,44 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     if (first) CU(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(Counters), c->s_picker));
     CU(c, cudaMemsetAsync(c->d_work + 4, 0, sizeof(unsigned long long), c->s_picker));
     if (first) CU(c, cudaEventRecord(c->t0_picker, c->s_picker));
+    // Ray binning (vx_set_option 15): large batches are traced in Z-order of their origin cells. Inside the timed region.
+    if (c->opt_bin && n >= VX_BIN_MIN_RAYS && n < (1ull << 32)) {
+        const uint32_t bits_axis = (uint32_t)(c->opt_bin & 15u), with_octant = (uint32_t)((c->opt_bin >> 4) & 1u);
+        const uint32_t key_bits = bin_key_bits(bits_axis, with_octant);
+        const size_t bins = (size_t)1 << (key_bits < 12 ? 12 : key_bits);   // a multiple of VX_SCAN_TILE
+        if (c->bin_hist_bits < key_bits || !c->d_bin_hist) {
+            CU(c, cudaStreamSynchronize(c->s_picker));
+            if (c->d_bin_hist) cudaFree(c->d_bin_hist);
+            if (c->d_bin_sums) cudaFree(c->d_bin_sums);
+            c->d_bin_hist = nullptr; c->d_bin_sums = nullptr;
+            CU(c, cudaMalloc(&c->d_bin_hist, bins * sizeof(uint32_t)));
+            CU(c, cudaMalloc(&c->d_bin_sums, (bins / VX_SCAN_TILE) * sizeof(uint32_t)));
+            c->bin_hist_bits = key_bits < 12 ? 12 : key_bits;
+        }
+        if (c->bin_cap < n) {
+            CU(c, cudaStreamSynchronize(c->s_picker));
+            if (c->d_bin_keyrank) cudaFree(c->d_bin_keyrank);
+            if (c->d_bin_order) cudaFree(c->d_bin_order);
+            c->d_bin_keyrank = nullptr; c->d_bin_order = nullptr; c->bin_cap = 0;
+            const uint64_t cap = n > c->cfg.max_rays ? n : c->cfg.max_rays;
+            CU(c, cudaMalloc(&c->d_bin_keyrank, cap * sizeof(uint2)));
+            CU(c, cudaMalloc(&c->d_bin_order, cap * sizeof(uint32_t)));
+            c->bin_cap = cap;
+        }
+        const uint32_t n_tiles = (uint32_t)(bins / VX_SCAN_TILE);
+        const int sweep = c->sm_count * 8;
+        const uint64_t blocks = (n + 255) / 256;
+        const int g = blocks < (uint64_t)sweep ? (int)blocks : sweep;
+        CU(c, cudaMemsetAsync(c->d_bin_hist, 0, bins * sizeof(uint32_t), c->s_picker));
+        bin_count_kernel<<<g, 256, 0, c->s_picker>>>(tasks_dev, n, a.scene.desc - (c->fmt == VX_FMT_CSVO ? 2 : 1), bits_axis, with_octant, c->d_bin_hist,
+                                                     c->d_bin_keyrank);
+        bin_scan_reduce_kernel<<<n_tiles, 256, 0, c->s_picker>>>(c->d_bin_hist, c->d_bin_sums);
+        bin_scan_sums_kernel<<<1, 256, 0, c->s_picker>>>(c->d_bin_sums, n_tiles);
+        bin_scan_apply_kernel<<<n_tiles, 256, 0, c->s_picker>>>(c->d_bin_hist, c->d_bin_sums);
+        bin_scatter_kernel<<<g, 256, 0, c->s_picker>>>(c->d_bin_keyrank, n, c->d_bin_hist, c->d_bin_order);
+        c->launches += 5;
+        a.order = c->d_bin_order;
+    }
     k<<<grid, VX_THREADS, smem, c->s_picker>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());

@@ -66,7 +66,9 @@ def parse():
     ap.add_argument("--no-clip", action="store_true", help="A/B: rays are not clipped against the occupied box of the world")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (diagnostic; not a bench line)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--bands", type=int, default=3, help="e2e: bands of vx_render_read_rgba8 (render/read-back overlap)")
+    ap.add_argument("--bands", type=int, default=3, help="e2e: bands of the blocking vx_render_read_rgba8 (render/read-back overlap inside one frame)")
+    ap.add_argument("--bands-pipelined", type=int, default=1, help="e2e: bands per frame of the begin/end loop (the read-back overlaps the NEXT frame there)")
+    ap.add_argument("--e2e-sync", action="store_true", help="e2e through the blocking vx_render_read_rgba8 only (no frame in flight across steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -386,7 +388,9 @@ def main():
         dist.barrier()
     else:
         frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+        frame8_pair = [frame8, torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)]   # double-buffered read-back (one frame in flight per buffer)
     e2e_step = [0]
+    e2e_sync = [args.e2e_sync]
     trace_on = bool(os.environ.get("VX_BENCH_TRACE"))   # diagnostic: host-side phase times of the N > 1 e2e step on stderr
     traces = []
     mirror = svo.host_mirror(HB + world.size_bytes)
@@ -400,8 +404,19 @@ def main():
                 mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
         if n_gpus == 1:
             svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
-            # render + read-back pipelined by the library: finished bands are copied to the host while the next is traced
-            svo.render_read_rgba8(vxp, W, H, frame8.data_ptr(), bands=args.bands)
+            if e2e_sync[0]:
+                # render + read-back in ONE blocking call (the reference's render + glReadPixels): finished bands are copied to the
+                # host while the next band is traced; returns when the whole frame is in host memory
+                svo.render_read_rgba8(vxp, W, H, frame8.data_ptr(), bands=args.bands)
+                return
+            # the render loop of a streaming consumer: frame k is begun (its kernels and band copies enqueued), THEN frame k-1 is
+            # waited for — its read-back ran under this frame's tracing (two device frames, two host frames). Every step still
+            # uploads its own dirty set and reads one whole frame back; the last frame is drained inside the timed region.
+            k = e2e_step[0]
+            e2e_step[0] += 1
+            svo.render_read_rgba8_begin(vxp, W, H, frame8_pair[k & 1].data_ptr(), bands=args.bands_pipelined)
+            if k > 0:
+                svo.render_read_rgba8_end()
             return
         # N > 1, software-pipelined by one step like the resident loop: this frame's dirty set was packed, copied to GPU 0 and
         # broadcast during the previous step; the NEXT frame's set is prepared on the host and sent while this frame renders.
@@ -441,9 +456,17 @@ def main():
 
     issue_ms = []
 
-    def timed(step_fn, steps, warmup, per_step_events=False):
+    def drain_e2e():
+        if n_gpus == 1 and not e2e_sync[0]:
+            while e2e_step[0] > 0:             # whatever is still in flight (at most the last frame): wait until it is in host memory
+                svo.render_read_rgba8_end()
+                e2e_step[0] = 0
+
+    def timed(step_fn, steps, warmup, per_step_events=False, drain=None):
         for _ in range(warmup):
             step_fn()
+        if drain:
+            drain()
         barrier()
         l0 = svo.launch_count()
         evs = []
@@ -452,6 +475,8 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             step_fn()
+        if drain:
+            drain()                             # inside the timed region: the last frame's read-back counts
         e1.record(stream)
         issue_ms.append((time.time() - t0) * 1e3 / steps)   # host time to ISSUE a step (no sync): close to ms/step = launch-bound
         barrier()
@@ -523,14 +548,42 @@ def main():
 
     e2e = None
     if not args.skip_e2e:
-        ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup, drain=drain_e2e)
+        sync_path = ("host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8 (%d bands: trace/shade overlapped with the "
+                     "RGBA8 D2H copy into pinned host memory), one blocking call per frame" % args.bands)
         e2e = {"value": rays_total / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": int(dirty_bytes + len(dirty) * 16), "d2h_bytes_per_step": int(W * H * 4),
-               "path": ("host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8 (%d bands: trace/shade overlapped with the "
-                        "RGBA8 D2H copy into pinned host memory)" % args.bands) if n_gpus == 1 else
+               "path": (sync_path if e2e_sync[0] else
+                        "host dirty ranges -> pinned mirror -> vx_svo_commit (H2D) -> vx_render_read_rgba8_begin(frame k) -> vx_render_read_rgba8_end(frame k-1): "
+                        "two frames in flight (two device RGBA8 frames, two pinned host frames), so frame k-1's D2H copy runs under frame k's tracing; "
+                        "every step uploads its dirty set and reads one whole frame back, the last frame is drained inside the timed region "
+                        "(%d band(s) per frame)" % args.bands_pipelined) if n_gpus == 1 else
                        "host dirty ranges -> pack -> H2D -> NCCL broadcast (sent one step ahead, while the previous frame renders) -> scatter -> every rank renders whole 16-pixel stripes "
                        "(VX_SHARD_ROWS) and DMAs them itself into ONE page-locked host frame shared by the ranks (N PCIe links); rank 0 "
                        "returns when all stripes of the step are in host memory"}
+        if n_gpus == 1:
+            # what the PCIe link of this box gives a frame-sized device -> pinned-host copy on its own (nothing else running): the floor of
+            # any end-to-end loop that returns a whole RGBA8 frame per step
+            src8 = torch.empty(W * H * 4, dtype=torch.uint8, device=dev)
+            dst8 = frame8_pair[1].view(-1)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst8.copy_(src8, non_blocking=True)
+            torch.cuda.synchronize()
+            c0.record(stream)
+            for _ in range(5):
+                dst8.copy_(src8, non_blocking=True)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            copy_ms = c0.elapsed_time(c1) / 5
+            e2e["pcie_d2h"] = {"frame_bytes": int(W * H * 4), "copy_ms": round(copy_ms, 4), "gb_per_s": round(W * H * 4 / (copy_ms * 1e-3) / 1e9, 2),
+                               "note": "a frame-sized D2H copy alone on this box; the pipelined loop cannot go below max(device frame time, this)"}
+            del src8
+        if n_gpus == 1 and not e2e_sync[0]:
+            # the same step through the one blocking call (frame k is in host memory when the call returns): reported beside the pipelined loop
+            e2e_sync[0] = True
+            ms_sync, _, _, _ = timed(step_e2e, args.steps, args.warmup)
+            e2e_sync[0] = False
+            e2e["blocking_call"] = {"value": rays_total / (ms_sync / args.steps * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_sync / args.steps, "path": sync_path}
         if trace_on and traces and rank in (0, 1):
             m = np.mean(np.array(traces[-args.steps:]), axis=0)
             print(f"[trace rank {rank}] apply+ack-wait {m[0]:.3f} begin {m[1]:.3f} host-prep {m[2]:.3f} prefetch {m[3]:.3f} end {m[4]:.3f} poll {m[5]:.3f} ms",

@@ -260,7 +260,11 @@ int vx_render(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t
 int vx_render_read_rgba8(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
                          const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
 /* The same in two halves, for a caller that prepares the next frame's inputs while this one renders: _begin returns as soon as
- * the frame and its band copies are enqueued, _end returns when the whole frame (this shard's stripes) is in rgba8_out. */
+ * the frame and its band copies are enqueued, _end returns when the OLDEST frame begun and not yet ended (this shard's stripes of
+ * it) is in its rgba8_out. Up to TWO frames may be in flight (the PBO-style double-buffered read-back of a render loop):
+ * _begin(k+1) before _end(k) renders frame k+1 into a second device frame while frame k's copy still runs, so a frame's read-back
+ * hides entirely under the next frame's tracing; each frame needs its own host buffer until its _end returned. A third _begin is
+ * VX_E_STATE. vx_render_read_rgba8 waits for everything in flight. */
 int vx_render_read_rgba8_begin(VxCtx* ctx, const VxRenderParams* params, uint32_t width, uint32_t height,
                                const VxShard* shard, uint8_t* rgba8_out, uint32_t bands);
 int vx_render_read_rgba8_end(VxCtx* ctx);

@@ -392,6 +392,37 @@ def test_pipelined_render_readback(pkg, terrain):
         # shard 1 of 3: owned pixels equal the full frame, the others keep what the previous full render left in the device frame
         svo.render_read_rgba8(vxp, w, h, out.data_ptr(), bands=3, shard=(1, 3))
         assert out.numpy().tobytes() == want.tobytes()
+        # two frames in flight (vx_render_read_rgba8_begin x 2 before the first _end): a second camera renders into the second device
+        # frame while the first frame's copies may still run; _end hands the frames back oldest first; a third _begin is refused
+        p2 = terrain_params(pkg, w, h, shadows=False)
+        q2 = pkg.VxhRenderParams.from_buffer_copy(bytes(p2))
+        q2.cam_pos = (C.c_float * 3)(*world.cnv_block_pos((-20.0, 90.0, 170.0)))
+        vxp2 = pkg.to_vx_render_params(q2)
+        svo.render_raw(vxp2, w, h)
+        want2 = svo.read_rgba8()
+        assert want2.tobytes() != want.tobytes()
+        out2 = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        for rounds in range(3):
+            out.fill_(1); out2.fill_(2)
+            svo.render_read_rgba8_begin(vxp, w, h, out.data_ptr(), bands=1 + rounds)
+            svo.render_read_rgba8_begin(vxp2, w, h, out2.data_ptr(), bands=2)
+            with pytest.raises(pkg.VxError, match="in flight"):
+                svo.render_read_rgba8_begin(vxp, w, h, out.data_ptr(), bands=1)
+            svo.render_read_rgba8_end()
+            assert out.numpy().tobytes() == want.tobytes(), (w, h, rounds)
+            svo.render_read_rgba8_end()
+            assert out2.numpy().tobytes() == want2.tobytes(), (w, h, rounds)
+            svo.render_read_rgba8_end()                                   # nothing in flight: a no-op
+        assert svo.read_rgba8().tobytes() == want2.tobytes()              # vx_read_frame_rgba8 follows the frame rendered last
+        # a stream of frames, one in flight across iterations (the bench's e2e loop)
+        outs = (out, out2)
+        for k in range(6):
+            svo.render_read_rgba8_begin(vxp if k % 2 == 0 else vxp2, w, h, outs[k & 1].data_ptr(), bands=1)
+            if k:
+                svo.render_read_rgba8_end()
+                assert outs[(k - 1) & 1].numpy().tobytes() == (want if (k - 1) % 2 == 0 else want2).tobytes(), k
+        svo.render_read_rgba8_end()
+        assert out2.numpy().tobytes() == want2.tobytes()
         svo.close()
 
 

@@ -56,6 +56,10 @@ struct VxCtx {
     uint8_t* h_mirror = nullptr;      // pinned, capacity bytes
     uint8_t* h_stage = nullptr;       // pinned staging block for async dirty uploads
     uint8_t* d_stage = nullptr;       // its device twin (allocated on first use)
+    uint8_t* h_stage_b = nullptr; uint8_t* d_stage_b = nullptr;   // second pair (first use): vx_svo_commit alternates, so a commit never waits
+    cudaEvent_t e_stage[2] = {nullptr, nullptr};                  // for the upload in front of it — only for the one two commits ago
+    bool stage_used[2] = {false, false};
+    uint32_t stage_idx = 1;
     size_t stage_cap = 0;
     uint64_t hot_off = 0, hot_len = 0;
     bool l2_installed = false;
@@ -72,6 +76,12 @@ struct VxCtx {
 
     float4* d_frame = nullptr;
     uint32_t* d_frame8 = nullptr;
+    // vx_render_read_rgba8_begin / _end with two frames in flight: the second RGBA8 device frame (allocated on first use), the frame the
+    // last vx_render_read_rgba8* rendered into, a "frame is in host memory" event per frame in flight, frames issued / waited for
+    uint32_t* d_frame8_b = nullptr;
+    uint32_t* last_frame8 = nullptr;
+    cudaEvent_t e_copied[2] = {nullptr, nullptr};
+    uint64_t rr_issued = 0, rr_waited = 0;
     bool frame32_stale = false;       // the last frame was rendered as RGBA8 only (vx_render_read_rgba8 / option 8)
     uint32_t frame_w = 0, frame_h = 0;
     uint32_t last_shard_rank = 0, last_shard_size = 1, last_shard_rows = 0;   // shard of the last render (vx_read_hit_records)
@@ -218,6 +228,8 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaEventCreateWithFlags(&c->e_k2, cudaEventDisableTiming));
     for (int i = 0; i < 16; ++i) CUC(cudaEventCreateWithFlags(&c->e_band[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_upload, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->e_copied[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->e_stage[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_render, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_picker, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0_render)); CUC(cudaEventCreate(&c->t1_render));
@@ -281,6 +293,9 @@ void vx_destroy(VxCtx* c) {
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
+    if (c->h_stage_b) cudaFreeHost(c->h_stage_b);
+    if (c->d_stage_b) cudaFree(c->d_stage_b);
+    for (cudaEvent_t& e : c->e_stage) if (e) cudaEventDestroy(e);
     if (c->d_materials) cudaFree(c->d_materials);
     if (c->d_texels) cudaFree(c->d_texels);
     if (c->d_texinfo) cudaFree(c->d_texinfo);
@@ -289,6 +304,8 @@ void vx_destroy(VxCtx* c) {
     if (c->d_work_list) cudaFree(c->d_work_list);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_frame8) cudaFree(c->d_frame8);
+    if (c->d_frame8_b) cudaFree(c->d_frame8_b);
+    for (cudaEvent_t& e : c->e_copied) if (e) cudaEventDestroy(e);
     if (c->d_hit0) cudaFree(c->d_hit0);
     if (c->d_hit1) cudaFree(c->d_hit1);
     if (c->d_sh0) cudaFree(c->d_sh0);
@@ -509,8 +526,20 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
     std::memcpy(c->h_mirror, &octree_scale, 4);                                  // svo.rs:173-175
     // (the scatter kernel is byte-granular: CSVO ranges, which are not word-aligned, take the staged path too)
     const bool staged = total + c->head + (uint64_t)n_dirty * sizeof(VxRange) <= c->stage_cap;
-    // the staging block is reused: the previous upload must have drained it (normally long done)
-    if (n_dirty && staged) CU(c, cudaStreamSynchronize(c->s_upload));
+    // Two staging pairs, used alternately: this commit only has to wait for the upload + scatter of the commit BEFORE the previous one
+    // (an event of its own; normally long done), never for the stream — which, when the caller runs everything on one stream
+    // (vx_set_streams), would mean waiting for the frame in flight (the reference's render_fence.wait() stall, svo.rs:178).
+    uint8_t* h_stage = c->h_stage;
+    uint8_t** d_stage_p = &c->d_stage;
+    uint32_t sidx = 0;
+    if (n_dirty && staged) {
+        sidx = (c->stage_idx ^= 1u);
+        if (sidx == 1) {
+            if (!c->h_stage_b) CU(c, cudaHostAlloc(&c->h_stage_b, c->stage_cap, cudaHostAllocPortable));
+            h_stage = c->h_stage_b; d_stage_p = &c->d_stage_b;
+        }
+        if (c->stage_used[sidx]) CU(c, cudaEventSynchronize(c->e_stage[sidx]));
+    }
     // do not tear a frame / ray batch in flight (render_fence.wait(), svo.rs:178) — on the GPU timeline, not the CPU's
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_render, 0));
     CU(c, cudaStreamWaitEvent(c->s_upload, c->e_picker, 0));
@@ -521,22 +550,25 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
             // put the ranges in place (one copy + one launch instead of a DMA per range)
             const size_t hdr_bytes = (size_t)n_dirty * sizeof(VxRange);
             if (hdr_bytes + c->head + total > c->stage_cap) return fail(c, VX_E_CAPACITY, "vx_svo_commit: %u dirty ranges do not fit the staging block", n_dirty);
-            if (!c->d_stage) CU(c, cudaMalloc(&c->d_stage, c->stage_cap));
-            std::memcpy(c->h_stage, dirty, hdr_bytes);
+            if (!*d_stage_p) CU(c, cudaMalloc(d_stage_p, c->stage_cap));
+            uint8_t* const d_stage = *d_stage_p;
+            std::memcpy(h_stage, dirty, hdr_bytes);
             size_t off = hdr_bytes;
-            std::memcpy(c->h_stage + off, c->h_mirror, c->head);
+            std::memcpy(h_stage + off, c->h_mirror, c->head);
             off += c->head;
             for (uint32_t i = 0; i < n_dirty; ++i) {
-                std::memcpy(c->h_stage + off, c->h_mirror + c->head + dirty[i].offset, dirty[i].length);
+                std::memcpy(h_stage + off, c->h_mirror + c->head + dirty[i].offset, dirty[i].length);
                 off += dirty[i].length;
             }
-            CU(c, cudaMemcpyAsync(c->d_stage, c->h_stage, off, cudaMemcpyHostToDevice, c->s_upload));
+            CU(c, cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, c->s_upload));
             const unsigned long long pb = c->head + total;
             const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
-            scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, c->d_stage, n_dirty, pb, (uint32_t)c->head,
+            scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, d_stage, n_dirty, pb, (uint32_t)c->head,
                                                                                      c->cfg.svo_capacity_bytes, c->d_flags + 62);
             c->launches++;
             CU(c, cudaGetLastError());
+            CU(c, cudaEventRecord(c->e_stage[sidx], c->s_upload));
+            c->stage_used[sidx] = true;
         } else {
             CU(c, cudaMemcpyAsync(c->d_world, c->h_mirror, c->head, cudaMemcpyHostToDevice, c->s_upload));
             for (uint32_t i = 0; i < n_dirty; ++i)
@@ -858,6 +890,7 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
     rc = launch_wavefront(c, a, p->render_shadows != 0, 0, 0, a.macro_y, true);
     if (rc) return rc;
     c->frame32_stale = c->opt_rgba8_out != 0;
+    c->last_frame8 = c->d_frame8;
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
     c->frame_w = width; c->frame_h = height;
@@ -878,10 +911,20 @@ int vx_render(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height
 static int render_read_rgba8_issue(VxCtx* c, const VxRenderParams* p, uint32_t width, uint32_t height, const VxShard* shard, uint8_t* rgba8_out,
                                    uint32_t bands) {
     if (!rgba8_out) return fail(c, VX_E_ARG, "vx_render_read_rgba8: null output");
+    if (c->rr_issued - c->rr_waited >= 2)
+        return fail(c, VX_E_STATE, "vx_render_read_rgba8_begin: two frames are in flight already — vx_render_read_rgba8_end first");
     RenderArgs a{};
     int rc = prepare_render(c, p, width, height, shard, a, "vx_render_read_rgba8");
     if (rc) return rc;
-    a.frame8 = c->d_frame8;   // the caller wants RGBA8 on the host: the shade / shadow kernels store the rounded pixels themselves (same
+    // A frame whose copies may still be running keeps its device frame: the next one renders into the other (double buffering; the
+    // kernels of frame k+1 then run under the read-back of frame k with nothing shared between them).
+    uint32_t* frame8 = c->d_frame8;
+    if (c->rr_issued != c->rr_waited && c->last_frame8 == c->d_frame8) {
+        if (!c->d_frame8_b) CU(c, cudaMalloc(&c->d_frame8_b, (size_t)c->cfg.max_width * c->cfg.max_height * 4));
+        frame8 = c->d_frame8_b;
+    }
+    c->last_frame8 = frame8;
+    a.frame8 = frame8;        // the caller wants RGBA8 on the host: the shade / shadow kernels store the rounded pixels themselves (same
                               // bytes as converting the RGBA32F frame, a quarter of the frame traffic, no conversion pass) — into THIS
                               // device's frame even while a peer frame is open (vx_open_peer_frame*): the copy below reads it
     a.tma_writeback = 0;
@@ -925,22 +968,24 @@ static int render_read_rgba8_issue(VxCtx* c, const VxRenderParams* p, uint32_t w
                 const uint32_t last = t.first_owned + (n_rows - 1) * a.shard_size;
                 if (last * 16 + 16 > height) {   // ragged last stripe of the frame
                     const size_t lo = (size_t)last * stripe;
-                    CU(c, cudaMemcpyAsync(rgba8_out + lo, reinterpret_cast<const uint8_t*>(c->d_frame8) + lo, (size_t)(height - last * 16) * width * 4,
+                    CU(c, cudaMemcpyAsync(rgba8_out + lo, reinterpret_cast<const uint8_t*>(frame8) + lo, (size_t)(height - last * 16) * width * 4,
                                           cudaMemcpyDeviceToHost, c->s_copy));
                     --n_rows;
                 }
                 if (n_rows)
-                    CU(c, cudaMemcpy2DAsync(rgba8_out + off, pitch, reinterpret_cast<const uint8_t*>(c->d_frame8) + off, pitch, stripe, n_rows,
+                    CU(c, cudaMemcpy2DAsync(rgba8_out + off, pitch, reinterpret_cast<const uint8_t*>(frame8) + off, pitch, stripe, n_rows,
                                             cudaMemcpyDeviceToHost, c->s_copy));
             }
         } else {
             const uint32_t y0 = row0 * 16, y1 = row1 * 16 < height ? row1 * 16 : height;
             const unsigned long long px0 = (unsigned long long)y0 * width, n = (unsigned long long)(y1 - y0) * width;
-            CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, c->d_frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
+            CU(c, cudaMemcpyAsync(rgba8_out + px0 * 4, frame8 + px0, n * 4, cudaMemcpyDeviceToHost, c->s_copy));
         }
     }
     CU(c, cudaEventRecord(c->t1_render, c->s_render));
     CU(c, cudaEventRecord(c->e_render, c->s_render));
+    CU(c, cudaEventRecord(c->e_copied[c->rr_issued & 1u], c->s_copy));   // behind this frame's last copy
+    c->rr_issued++;
     c->frame_w = width; c->frame_h = height;
     c->render_timed = false;
     c->frame32_stale = true;
@@ -952,6 +997,7 @@ int vx_render_read_rgba8(VxCtx* c, const VxRenderParams* p, uint32_t width, uint
     int rc = render_read_rgba8_issue(c, p, width, height, shard, rgba8_out, bands);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->s_copy));
+    c->rr_waited = c->rr_issued;
     return VX_OK;
 }
 
@@ -963,7 +1009,10 @@ int vx_render_read_rgba8_begin(VxCtx* c, const VxRenderParams* p, uint32_t width
 int vx_render_read_rgba8_end(VxCtx* c) {
     if (!c) return VX_E_ARG;
     CU(c, cudaSetDevice(c->cfg.device));
-    CU(c, cudaStreamSynchronize(c->s_copy));
+    if (c->rr_waited < c->rr_issued) {   // the OLDEST frame in flight
+        CU(c, cudaEventSynchronize(c->e_copied[c->rr_waited & 1u]));
+        c->rr_waited++;
+    }
     return VX_OK;
 }
 
@@ -993,7 +1042,7 @@ int vx_read_frame_rgba8(VxCtx* c, uint8_t* out) {
         c->launches++;
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaMemcpyAsync(out, c->d_frame8, n * 4, cudaMemcpyDeviceToHost, c->s_render));
+    CU(c, cudaMemcpyAsync(out, (c->frame32_stale && c->last_frame8) ? c->last_frame8 : c->d_frame8, n * 4, cudaMemcpyDeviceToHost, c->s_render));
     CU(c, cudaStreamSynchronize(c->s_render));
     return VX_OK;
 }

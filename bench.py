@@ -398,12 +398,14 @@ def main():
 
     def step_e2e():
         """The same frame through the C ABI with host buffers: dirty bytes -> pinned mirror -> H2D, render, RGBA8 -> host."""
+        if trace_on: t_s = time.perf_counter()
         flush()
         if rank == 0 and n_gpus == 1:
             for (o, l), b in zip(dirty, staged):   # the host-side serializer writing its changes (write_changes_to)
                 mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
         if n_gpus == 1:
-            svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
+            if not os.environ.get("VX_BENCH_SKIP_COMMIT"):   # diagnostic only (never a bench line): the loop without its upload
+                svo.commit(octree_scale, dirty, world.size_bytes, world.depth)
             if e2e_sync[0]:
                 # render + read-back in ONE blocking call (the reference's render + glReadPixels): finished bands are copied to the
                 # host while the next band is traced; returns when the whole frame is in host memory
@@ -414,9 +416,13 @@ def main():
             # uploads its own dirty set and reads one whole frame back; the last frame is drained inside the timed region.
             k = e2e_step[0]
             e2e_step[0] += 1
+            if trace_on: t_b = time.perf_counter()
             svo.render_read_rgba8_begin(vxp, W, H, frame8_pair[k & 1].data_ptr(), bands=args.bands_pipelined)
+            if trace_on: t_e = time.perf_counter()
             if k > 0:
                 svo.render_read_rgba8_end()
+            if trace_on:
+                traces.append([(t_b - t_s) * 1e3, (t_e - t_b) * 1e3, (time.perf_counter() - t_e) * 1e3])
             return
         # N > 1, software-pipelined by one step like the resident loop: this frame's dirty set was packed, copied to GPU 0 and
         # broadcast during the previous step; the NEXT frame's set is prepared on the host and sent while this frame renders.
@@ -584,7 +590,10 @@ def main():
             ms_sync, _, _, _ = timed(step_e2e, args.steps, args.warmup)
             e2e_sync[0] = False
             e2e["blocking_call"] = {"value": rays_total / (ms_sync / args.steps * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_sync / args.steps, "path": sync_path}
-        if trace_on and traces and rank in (0, 1):
+        if trace_on and traces and n_gpus == 1:
+            m = np.mean(np.array(traces[-args.steps:]), axis=0)
+            print(f"[trace e2e N=1] flush+mirror+commit {m[0]:.3f} begin {m[1]:.3f} end(k-1) {m[2]:.3f} ms (host time per step)", file=sys.stderr, flush=True)
+        elif trace_on and traces and rank in (0, 1):
             m = np.mean(np.array(traces[-args.steps:]), axis=0)
             print(f"[trace rank {rank}] apply+ack-wait {m[0]:.3f} begin {m[1]:.3f} host-prep {m[2]:.3f} prefetch {m[3]:.3f} end {m[4]:.3f} poll {m[5]:.3f} ms",
                   file=sys.stderr, flush=True)

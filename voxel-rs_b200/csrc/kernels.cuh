@@ -187,18 +187,23 @@ __device__ __forceinline__ bool render_leaf(Walk& w, const Scene& s, const Smem&
 // 0.771 -> 0.752 ms, trace_shadow_kernel 0.498 -> 0.544 ms — the lanes of a coherent primary tile stay in the same phase and save the vote,
 // its WARPSYNC and the loop branch every other iteration; shadow rays start in 32 different voxels and the second, nested step runs
 // once per phase group of the first. So the primary kernel (ESVO) instantiates it and the others do not.
-template <int FMT, bool LIMITED, bool COUNT, bool TWO = false>
+template <int FMT, bool LIMITED, bool COUNT, int TWO = 0>   // TWO: 0 one step per vote, 1 two (the second nested in the first), 2 two (one after the other)
 __device__ __forceinline__ void walk_warp(Walk& w, const Scene& s, uint32_t stk, Counters& cnt, int thresh) {
     if (thresh <= 1) {
         do {
             if (w.state > 0) {
                 walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
-                if (TWO && w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+                if (TWO == 1 && w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
             }
+            if (TWO == 2 && w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
         } while (__any_sync(0xffffffffu, w.state > 0));
     } else {
         do {
             if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+#ifndef VX_V_THRESH_ONE   // two steps per population count in the refilling loop (the picker's): 2.558 -> 2.499 ms per 16 Mi rays; a lane may
+                          // take one step past the moment the warp would have left the loop — the same steps of the same ray, only earlier
+            if (w.state > 0) walk_step<FMT, LIMITED, COUNT>(w, s, stk, cnt);
+#endif
         } while (__popc(__ballot_sync(0xffffffffu, w.state > 0)) >= thresh);
     }
 }
@@ -294,7 +299,13 @@ __device__ __forceinline__ void strip_wait(const unsigned int* strip_done, uint3
 #define VX_PRIMARY_CLIP true   // world-box clipping of primary rays (A/B: tools/ab_kernels.py builds a variant with false)
 #endif
 #ifndef VX_PRIMARY_UNROLL2
-#define VX_PRIMARY_UNROLL2 true   // two steps per vote in the primary kernel's walk loop (A/B: a variant build with false)
+#define VX_PRIMARY_UNROLL2 1      // steps per vote in the primary kernel's walk loop: walk_warp's TWO (A/B builds: 0, 2)
+#endif
+#ifndef VX_CSVO_UNROLL2
+#define VX_CSVO_UNROLL2 true      // ... for the CSVO instantiation too (measured: 1.291 -> 1.255 ms although two copies of its 241-instruction loop
+#endif                            // do not fit the L0 I-cache)
+#ifndef VX_SHADOW_UNROLL2
+#define VX_SHADOW_UNROLL2 0       // the shadow kernel's (measured: 1 is 9 % slower there)
 #endif
 template <int FMT, bool COUNT, int MINB>
 __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderArgs a) {
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
         if (!busy) break;
 
         // ---------------------------------------------------------------- walk
-        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT, FMT == VX_FMT_ESVO && VX_PRIMARY_UNROLL2>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
+        walk_warp<FMT, VX_PRIMARY_CLIP, COUNT, (FMT == VX_FMT_ESVO || VX_CSVO_UNROLL2) ? VX_PRIMARY_UNROLL2 : 0>(w, a.scene, sm.stack, cnt, min((int)a.refill_threshold, __popc(busy)));
 
         // ---------------------------------------------------------------- events
         bool finished = false;
@@ -572,7 +583,7 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_shadow_kernel(RenderAr
         }
         const unsigned busy = __ballot_sync(0xffffffffu, w.state != ST_IDLE);
         if (!busy) break;
-        walk_warp<FMT, true, COUNT>(w, a.scene, sm.stack, cnt, min((int)a.shadow_refill, __popc(busy)));
+        walk_warp<FMT, true, COUNT, VX_SHADOW_UNROLL2>(w, a.scene, sm.stack, cnt, min((int)a.shadow_refill, __popc(busy)));
 
         if (w.state <= 0 && w.state != ST_IDLE) {
             bool done = true;
@@ -920,6 +931,9 @@ __global__ void flag_wait_kernel(unsigned int* flags, unsigned int first, unsign
 // path from the root and, if the path does not end in an empty child, grows the box by the cell it stopped at: its level-L cell,
 // or the coarser cell of a leaf met on the way. Most threads stop after one or two node reads. bounds = {min xyz = 0xffffffff,
 // max xyz = 0} before the launch. Runs on the upload stream after every change of the world buffer.
+__global__ void bounds_init_kernel(uint32_t* bounds) {
+    if (threadIdx.x < 8) bounds[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+}
 template <int FMT>
 __global__ void __launch_bounds__(256) svo_bounds_kernel(Scene s, uint32_t* bounds) {
     const float octree_scale = load_octree_scale<FMT>(s);

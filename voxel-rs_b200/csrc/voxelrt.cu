@@ -58,6 +58,8 @@ struct VxCtx {
     uint8_t* d_stage = nullptr;       // its device twin (allocated on first use)
     uint8_t* h_stage_b = nullptr; uint8_t* d_stage_b = nullptr;   // second pair (first use): vx_svo_commit alternates, so a commit never waits
     cudaEvent_t e_stage[2] = {nullptr, nullptr};                  // for the upload in front of it — only for the one two commits ago
+    cudaStream_t s_stage = nullptr;                               // the staging DMA's own stream (always the library's): the packed dirty set
+    cudaEvent_t e_staged[2] = {nullptr, nullptr};                 // travels while the previous frame still renders; only the scatter waits
     bool stage_used[2] = {false, false};
     uint32_t stage_idx = 1;
     size_t stage_cap = 0;
@@ -224,12 +226,14 @@ int vx_create(const VxConfig* cfg, VxCtx** out) {
     CUC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_pick_in, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->s_stage, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&c->e_pre, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_k2, cudaEventDisableTiming));
     for (int i = 0; i < 16; ++i) CUC(cudaEventCreateWithFlags(&c->e_band[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_upload, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->e_copied[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->e_stage[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->e_staged[i], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_render, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&c->e_picker, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->t0_render)); CUC(cudaEventCreate(&c->t1_render));
@@ -296,6 +300,8 @@ void vx_destroy(VxCtx* c) {
     if (c->h_stage_b) cudaFreeHost(c->h_stage_b);
     if (c->d_stage_b) cudaFree(c->d_stage_b);
     for (cudaEvent_t& e : c->e_stage) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t& e : c->e_staged) if (e) cudaEventDestroy(e);
+    if (c->s_stage) cudaStreamDestroy(c->s_stage);
     if (c->d_materials) cudaFree(c->d_materials);
     if (c->d_texels) cudaFree(c->d_texels);
     if (c->d_texinfo) cudaFree(c->d_texinfo);
@@ -467,13 +473,7 @@ static void install_l2_window(VxCtx* c) {
 // The occupied box of the world for ray clipping (traverse.cuh Clip): recomputed on the upload stream after every change of the
 // world buffer, before the upload event that frames and ray batches wait for. 1024 CTAs, most threads stop after a read or two.
 static int refresh_bounds(VxCtx* c, uint32_t depth) {
-    static const uint32_t init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
-    static uint32_t* pinned = nullptr;   // cudaMemcpyAsync from pageable memory would stage synchronously
-    if (!pinned) {
-        if (cudaHostAlloc(&pinned, sizeof(init), cudaHostAllocPortable) != cudaSuccess) return fail(c, VX_E_CUDA, "refresh_bounds: cudaHostAlloc failed");
-        std::memcpy(pinned, init, sizeof(init));
-    }
-    CU(c, cudaMemcpyAsync(c->d_bounds, pinned, sizeof(init), cudaMemcpyHostToDevice, c->s_upload));
+    bounds_init_kernel<<<1, 32, 0, c->s_upload>>>(c->d_bounds);   // (a kernel, not a 32-byte H2D copy: no copy-engine round trip in front of every frame)
     Scene s = make_scene(c);
     const uint32_t L = depth < 6 ? depth : 6;   // (the kernel derives the depth from the buffer's scale itself; this only sizes the grid)
     const unsigned blocks = depth >= 1 && depth <= 23 ? ((1u << (3 * L)) + 255) / 256 : 1024;
@@ -560,7 +560,12 @@ int vx_svo_commit(VxCtx* c, float octree_scale, const VxRange* dirty, uint32_t n
                 std::memcpy(h_stage + off, c->h_mirror + c->head + dirty[i].offset, dirty[i].length);
                 off += dirty[i].length;
             }
-            CU(c, cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, c->s_upload));
+            // the DMA goes to the staging stream: it does not wait for the frame in flight (nothing reads d_stage but the scatter
+            // below), so it is over long before the upload stream gets to the scatter kernel — and it does not queue behind that
+            // frame's read-back either (measured: in-stream it cost 0.14 ms per frame of the pipelined loop)
+            CU(c, cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, c->s_stage));
+            CU(c, cudaEventRecord(c->e_staged[sidx], c->s_stage));
+            CU(c, cudaStreamWaitEvent(c->s_upload, c->e_staged[sidx], 0));
             const unsigned long long pb = c->head + total;
             const int blocks = (int)((pb / 4 + 255) / 256 < 4096 ? (pb / 4 + 255) / 256 : 4096);
             scatter_ranges_kernel<<<blocks > 0 ? blocks : 1, 256, 0, c->s_upload>>>(c->d_world, d_stage, n_dirty, pb, (uint32_t)c->head,

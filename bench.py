@@ -357,12 +357,13 @@ def main():
 
     shm = None
     if n_gpus > 1:
-        # e2e at N > 1: ONE host frame shared by the ranks (POSIX shared memory, page-locked in every process), every rank DMAs the
-        # stripes it rendered (VX_SHARD_ROWS) into it over its own PCIe link; a word per rank behind the frame says which step's
-        # stripes are in (host-side release / acquire: a plain store after the rank's copy stream drained, rank 0 polls)
+        # e2e at N > 1: host frames shared by the ranks (POSIX shared memory, page-locked in every process; TWO of them, used
+        # alternately, so that frame k can be rendered while frame k-1 is still being read back), every rank DMAs the stripes it
+        # rendered (VX_SHARD_ROWS) into the frame over its own PCIe link; a word per rank behind the frames says which step's
+        # stripes are in (host-side release / acquire: a plain store after the rank's copies of that frame finished, rank 0 polls)
         from multiprocessing import shared_memory
         name = "vxframe_%s" % os.environ.get("MASTER_PORT", "0")
-        nbytes = W * H * 4 + 4096
+        nbytes = 2 * W * H * 4 + 4096
         if rank == 0:
             try:
                 shared_memory.SharedMemory(name=name).unlink()
@@ -380,9 +381,9 @@ def main():
         shm_np = np.ndarray((nbytes,), dtype=np.uint8, buffer=shm.buf)
         rc = torch.cuda.cudart().cudaHostRegister(shm_np.ctypes.data, nbytes, 1)   # cudaHostRegisterPortable
         assert int(rc) == 0, f"cudaHostRegister: {rc}"
-        frame8_np = shm_np[:W * H * 4].reshape(H, W, 4)
-        frame8_ptr = shm_np.ctypes.data
-        step_words = shm_np[W * H * 4:W * H * 4 + 256].view(np.uint32)   # [r] = last e2e step whose stripes of rank r are in; [63] = rank 0's ack
+        frame8_nps = [shm_np[i * W * H * 4:(i + 1) * W * H * 4].reshape(H, W, 4) for i in range(2)]
+        frame8_ptrs = [shm_np.ctypes.data + i * W * H * 4 for i in range(2)]
+        step_words = shm_np[2 * W * H * 4:2 * W * H * 4 + 256].view(np.uint32)   # [r] = last e2e step whose stripes of rank r are in; [63] = rank 0's ack
         if rank == 0:
             step_words[:] = 0
         dist.barrier()
@@ -390,7 +391,25 @@ def main():
         frame8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
         frame8_pair = [frame8, torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)]   # double-buffered read-back (one frame in flight per buffer)
     e2e_step = [0]
+    e2e_pub = [0]                         # N > 1: last frame this rank has published (its stripes are in the host frame)
     e2e_sync = [args.e2e_sync]
+
+    def spin_until(cond, what):
+        t_end = time.time() + 30.0
+        while not cond():
+            if time.time() > t_end:
+                raise SystemExit(f"bench.py: rank {rank} gave up waiting for {what}")
+
+    def publish(j, tr=None):
+        """N > 1: frame j (the oldest in flight) is waited for and announced; rank 0 returns when every rank's stripes of it are in."""
+        svo.render_read_rgba8_end()
+        if tr is not None: tr.append(time.perf_counter())
+        step_words[rank] = j
+        if rank == 0:
+            spin_until(lambda: int(step_words[:n_gpus].min()) >= j, f"the stripes of frame {j}")
+            step_words[63] = j
+        e2e_pub[0] = j
+        if tr is not None: tr.append(time.perf_counter())
     trace_on = bool(os.environ.get("VX_BENCH_TRACE"))   # diagnostic: host-side phase times of the N > 1 e2e step on stderr
     traces = []
     mirror = svo.host_mirror(HB + world.size_bytes)
@@ -424,18 +443,19 @@ def main():
             if trace_on:
                 traces.append([(t_b - t_s) * 1e3, (t_e - t_b) * 1e3, (time.perf_counter() - t_e) * 1e3])
             return
-        # N > 1, software-pipelined by one step like the resident loop: this frame's dirty set was packed, copied to GPU 0 and
-        # broadcast during the previous step; the NEXT frame's set is prepared on the host and sent while this frame renders.
-        # Every step still copies one dirty set host -> device and reads one frame device -> host.
+        # N > 1, software-pipelined like the resident loop AND like the 1-GPU loop: this frame's dirty set was packed, copied to GPU 0
+        # and broadcast during the previous step, the NEXT frame's set is prepared on the host and sent while this frame renders; and
+        # frame k is begun before frame k-1 is waited for (two shared host frames), so a rank's read-back and the cross-process
+        # hand-shake of frame k-1 run under the tracing of frame k. Every step still copies one dirty set host -> device and reads
+        # one frame device -> host; the last frame is drained inside the timed region.
         e2e_step[0] += 1
         k = e2e_step[0]
         tr = [time.perf_counter()] if trace_on else None
         sf.apply_dirty()                       # scatter of the set sent last step (stream-ordered behind the previous frame)
-        if rank != 0:
-            while step_words[63] < k - 1:      # rank 0 is done with the previous host frame
-                pass
+        if rank != 0 and k > 2:
+            spin_until(lambda: step_words[63] >= k - 2, f"rank 0's ack of frame {k - 2}")   # the host frame of parity k & 1 is free again
         if tr: tr.append(time.perf_counter())
-        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptr, bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptrs[k & 1], bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
         if tr: tr.append(time.perf_counter())
         if rank == 0:                          # while the GPUs trace: the next frame's inputs
             for (o, l), b in zip(dirty, staged):
@@ -444,15 +464,11 @@ def main():
         if tr: tr.append(time.perf_counter())
         sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_hosts[k & 1])
         if tr: tr.append(time.perf_counter())
-        svo.render_read_rgba8_end()            # THIS rank's stripes are in the shared host frame (its copy stream drained)
-        if tr: tr.append(time.perf_counter())
-        step_words[rank] = k
-        if rank == 0:
-            while int(step_words[:n_gpus].min()) < k:   # the frame is whole: every rank's stripes of step k are in host memory
-                pass
-            step_words[63] = k
+        if e2e_pub[0] < k - 1:
+            publish(k - 1, tr)                 # frame k-1: this rank's stripes are in; rank 0: the frame is whole
+        elif tr:
+            tr += [time.perf_counter()] * 2
         if tr:
-            tr.append(time.perf_counter())
             traces.append([(b - a) * 1e3 for a, b in zip(tr[:-1], tr[1:])])
 
     def barrier():
@@ -463,6 +479,10 @@ def main():
     issue_ms = []
 
     def drain_e2e():
+        if n_gpus > 1:
+            if e2e_pub[0] < e2e_step[0]:
+                publish(e2e_step[0])
+            return
         if n_gpus == 1 and not e2e_sync[0]:
             while e2e_step[0] > 0:             # whatever is still in flight (at most the last frame): wait until it is in host memory
                 svo.render_read_rgba8_end()
@@ -565,8 +585,9 @@ def main():
                         "every step uploads its dirty set and reads one whole frame back, the last frame is drained inside the timed region "
                         "(%d band(s) per frame)" % args.bands_pipelined) if n_gpus == 1 else
                        "host dirty ranges -> pack -> H2D -> NCCL broadcast (sent one step ahead, while the previous frame renders) -> scatter -> every rank renders whole 16-pixel stripes "
-                       "(VX_SHARD_ROWS) and DMAs them itself into ONE page-locked host frame shared by the ranks (N PCIe links); rank 0 "
-                       "returns when all stripes of the step are in host memory"}
+                       "(VX_SHARD_ROWS) and DMAs them itself into a page-locked host frame shared by the ranks (N PCIe links; two such frames, used alternately: "
+                       "frame k is begun before frame k-1 is waited for); rank 0 returns from a step when all stripes of frame k-1 are in host memory; "
+                       "the last frame is drained inside the timed region"}
         if n_gpus == 1:
             # what the PCIe link of this box gives a frame-sized device -> pinned-host copy on its own (nothing else running): the floor of
             # any end-to-end loop that returns a whole RGBA8 frame per step
@@ -601,7 +622,7 @@ def main():
             # the host frame of the last e2e step against rank 0's own unsharded render: the shared frame is the frame
             svo.render_raw(vxp, W, H, shard=None)
             ref8 = svo.read_rgba8()
-            if ref8.tobytes() != frame8_np.tobytes():
+            if ref8.tobytes() != frame8_nps[e2e_step[0] & 1].tobytes():
                 raise SystemExit("bench.py: the host frame assembled from the ranks' stripes differs from the single-GPU frame")
             e2e["parity_check"] = "shared host frame == rank 0's unsharded RGBA8 frame, byte for byte"
 

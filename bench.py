@@ -455,7 +455,7 @@ def main():
         if rank != 0 and k > 2:
             spin_until(lambda: step_words[63] >= k - 2, f"rank 0's ack of frame {k - 2}")   # the host frame of parity k & 1 is free again
         if tr: tr.append(time.perf_counter())
-        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptrs[k & 1], bands=min(args.bands, 2), shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptrs[k & 1], bands=args.bands_pipelined, shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
         if tr: tr.append(time.perf_counter())
         if rank == 0:                          # while the GPUs trace: the next frame's inputs
             for (o, l), b in zip(dirty, staged):

@@ -101,6 +101,10 @@ extern "C" {
     pub fn vx_read_frame_rgba32f(ctx: *mut VxCtx, rgba32f_out: *mut f32) -> c_int;
     pub fn vx_render_read_rgba8(ctx: *mut VxCtx, params: *const VxRenderParams, width: u32, height: u32, shard: *const VxShard,
                                 rgba8_out: *mut u8, bands: u32) -> c_int;
+    // the same in two halves; up to two frames in flight (frame k+1 renders while frame k is read back)
+    pub fn vx_render_read_rgba8_begin(ctx: *mut VxCtx, params: *const VxRenderParams, width: u32, height: u32, shard: *const VxShard,
+                                      rgba8_out: *mut u8, bands: u32) -> c_int;
+    pub fn vx_render_read_rgba8_end(ctx: *mut VxCtx) -> c_int;
     pub fn vx_frame_device_ptr(ctx: *mut VxCtx, out_ptr: *mut *mut c_void, width: *mut u32, height: *mut u32) -> c_int;
 
     // Svo::raycast (svo.rs:233-255)

@@ -284,7 +284,7 @@ EMU_API int emu_render(const uint8_t* world, uint64_t world_bytes, int fmt, uint
         a.shade_blocks = owned * 4;
         a.shade_counter = options[9] ? work + 6 : nullptr;   // overlapped: persistent shade grid (here: 3 CTAs, one after the other)
         if (options[9]) emu::launch(owned * 4 < 3 ? owned * 4 : 3, VX_THREADS, [&] { if (count) shade_kernel<true, true>(a); else shade_kernel<false, true>(a); });
-        else emu::launch(owned * 4, VX_THREADS, [&] { if (count) shade_kernel<true, false>(a); else shade_kernel<false, false>(a); });
+        else emu::launch((owned * 4 + VX_SHADE_STRIPS - 1) / VX_SHADE_STRIPS, VX_THREADS, [&] { if (count) shade_kernel<true, false>(a); else shade_kernel<false, false>(a); });
         if (p->render_shadows) {
             a.work_counter = work + 2;
             emu::launch(grid, VX_THREADS, [&] {

@@ -403,6 +403,9 @@ __global__ void __launch_bounds__(VX_THREADS, MINB) trace_primary_kernel(RenderA
 }
 
 // ---- shading ---------------------------------------------------------------------------------------------------------------
+#ifndef VX_SHADE_STRIPS
+#define VX_SHADE_STRIPS 4u   // strips one CTA of the static shade grid shades, one after the other (A/B builds: 1, 2, 8)
+#endif
 // grid = owned strips, block = 128 threads = the 128 pixels of one 32x4 strip (4 warp tiles of 8x4).
 template <bool COUNT, bool PERSIST>
 __global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(RenderArgs a) {   // static grid: 10 CTAs / SM (<= 51 registers)
@@ -413,14 +416,22 @@ __global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(Ren
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned int s_next;
     Counters cnt = {0, 0, 0, 0, 0, 0};
-    // static grid: CTA b shades strip b. Overlapped wavefront: the CTAs of a small resident grid claim strips from shade_counter.
-    for (uint32_t blk = (!PERSIST && a.lifo) ? a.shade_blocks - 1u - blockIdx.x : blockIdx.x;;) {   // LIFO: the strips traced last first
+    // static grid: CTA b shades the VX_SHADE_STRIPS strips b * VX_SHADE_STRIPS ... (= the 4 strips of one macro block: the CTA's prologue —
+    // the unorm table, the launch arguments — is paid once per 512 pixels instead of once per 128; it was 15 % of the kernel's
+    // instructions). Overlapped wavefront: the CTAs of a small resident grid claim strips from shade_counter.
+    uint32_t static_i = 0;
+    for (uint32_t blk = 0;;) {
     if (PERSIST) {
         __syncthreads();   // everybody is done with the shared arrays of the previous strip (and with s_next)
         if (threadIdx.x == 0) s_next = atomicAdd(a.shade_counter, 1u);
         __syncthreads();
         blk = s_next;
         if (blk >= a.shade_blocks) break;
+    } else {
+        if (static_i) __syncthreads();   // the shared arrays of the previous strip are free again
+        blk = blockIdx.x * VX_SHADE_STRIPS + static_i;
+        if (static_i++ >= VX_SHADE_STRIPS || blk >= a.shade_blocks) break;
+        if (a.lifo) blk = a.shade_blocks - 1u - blk;   // LIFO: the strips traced last first
     }
     const uint32_t strip = ((a.work_list ? __ldg(a.work_list + (blk >> 2)) : owned_macro(a, blk >> 2)) << 2) | (blk & 3u);
     uint32_t x0 = 0, y0 = 0, gx = 0, gy = 0;
@@ -515,7 +526,6 @@ __global__ void __launch_bounds__(VX_THREADS, PERSIST ? 5 : 10) shade_kernel(Ren
         for (uint32_t k = 0; k < warp; ++k) off += s_warp_count[k];
         a.sh0[off] = s0; a.sh1[off] = s1; a.sh_pix[off] = pix;
     }
-    if (!PERSIST) break;
     }
     if (COUNT) flush_counters(a.counters, cnt);
 }

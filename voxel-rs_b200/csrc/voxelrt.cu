@@ -803,6 +803,7 @@ static int launch_wavefront(VxCtx* c, RenderArgs a, bool shadows, uint32_t band,
             if (count) shade_kernel<true, true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
             else shade_kernel<false, true><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
         } else {
+            shade_grid = (shade_grid + VX_SHADE_STRIPS - 1u) / VX_SHADE_STRIPS;
             if (count) shade_kernel<true, false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
             else shade_kernel<false, false><<<shade_grid, VX_THREADS, smem2, s2>>>(a);
         }

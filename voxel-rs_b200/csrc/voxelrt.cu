@@ -474,6 +474,7 @@ static void install_l2_window(VxCtx* c) {
 // world buffer, before the upload event that frames and ray batches wait for. 1024 CTAs, most threads stop after a read or two.
 static int refresh_bounds(VxCtx* c, uint32_t depth) {
     bounds_init_kernel<<<1, 32, 0, c->s_upload>>>(c->d_bounds);   // (a kernel, not a 32-byte H2D copy: no copy-engine round trip in front of every frame)
+    c->launches++;
     Scene s = make_scene(c);
     const uint32_t L = depth < 6 ? depth : 6;   // (the kernel derives the depth from the buffer's scale itself; this only sizes the grid)
     const unsigned blocks = depth >= 1 && depth <= 23 ? ((1u << (3 * L)) + 255) / 256 : 1024;

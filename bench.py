@@ -412,6 +412,7 @@ def main():
         if tr is not None: tr.append(time.perf_counter())
     trace_on = bool(os.environ.get("VX_BENCH_TRACE"))   # diagnostic: host-side phase times of the N > 1 e2e step on stderr
     traces = []
+    gpu_marks = []
     mirror = svo.host_mirror(HB + world.size_bytes)
     staged = [bytes(mirror[HB + o:HB + o + l]) for o, l in dirty]
 
@@ -451,18 +452,26 @@ def main():
         e2e_step[0] += 1
         k = e2e_step[0]
         tr = [time.perf_counter()] if trace_on else None
+        if trace_on:                           # GPU-side phase marks on the render stream (diagnostic)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            gpu_marks.append(ev)
+            ev[0].record(stream)
         sf.apply_dirty()                       # scatter of the set sent last step (stream-ordered behind the previous frame)
+        if trace_on: ev[1].record(stream)
         if rank != 0 and k > 2:
             spin_until(lambda: step_words[63] >= k - 2, f"rank 0's ack of frame {k - 2}")   # the host frame of parity k & 1 is free again
         if tr: tr.append(time.perf_counter())
-        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptrs[k & 1], bands=args.bands_pipelined, shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
-        if tr: tr.append(time.perf_counter())
-        if rank == 0:                          # while the GPUs trace: the next frame's inputs
+        if rank == 0:                          # the next frame's inputs (host side)
             for (o, l), b in zip(dirty, staged):
                 mirror[HB + o:HB + o + l] = np.frombuffer(b, np.uint8)
             svo.pack_dirty(dirty, packed_hosts[k & 1].numpy())
         if tr: tr.append(time.perf_counter())
+        # the broadcast of the NEXT frame's set is enqueued BEFORE this frame's kernels: launched behind them, the NCCL kernel found
+        # every SM taken by the persistent tracing kernels and ran only in their tails, and the next frame's scatter waited for it
         sf.prefetch_dirty(len(dirty), dirty_bytes, world.size_bytes, world.depth, packed_host=packed_hosts[k & 1])
+        if tr: tr.append(time.perf_counter())
+        svo.render_read_rgba8_begin(vxp, W, H, frame8_ptrs[k & 1], bands=args.bands_pipelined, shard=(rank, n_gpus | pkg.VX_SHARD_ROWS))
+        if trace_on: ev[2].record(stream)
         if tr: tr.append(time.perf_counter())
         if e2e_pub[0] < k - 1:
             publish(k - 1, tr)                 # frame k-1: this rank's stripes are in; rank 0: the frame is whole
@@ -615,8 +624,15 @@ def main():
             m = np.mean(np.array(traces[-args.steps:]), axis=0)
             print(f"[trace e2e N=1] flush+mirror+commit {m[0]:.3f} begin {m[1]:.3f} end(k-1) {m[2]:.3f} ms (host time per step)", file=sys.stderr, flush=True)
         elif trace_on and traces and rank in (0, 1):
+            torch.cuda.synchronize()
+            gm = gpu_marks[-args.steps:]
+            flush_scatter = np.mean([a[0].elapsed_time(a[1]) for a in gm])
+            render = np.mean([a[1].elapsed_time(a[2]) for a in gm])
+            idle = np.mean([a[2].elapsed_time(b[0]) for a, b in zip(gm[:-1], gm[1:])])
+            print(f"[trace rank {rank}] GPU render stream per frame: flush+scatter(+wait for the broadcast) {flush_scatter:.3f}  render {render:.3f}  idle until the next frame's first launch {idle:.3f} ms",
+                  file=sys.stderr, flush=True)
             m = np.mean(np.array(traces[-args.steps:]), axis=0)
-            print(f"[trace rank {rank}] apply+ack-wait {m[0]:.3f} begin {m[1]:.3f} host-prep {m[2]:.3f} prefetch {m[3]:.3f} end {m[4]:.3f} poll {m[5]:.3f} ms",
+            print(f"[trace rank {rank}] apply+ack-wait {m[0]:.3f} host-prep {m[1]:.3f} prefetch {m[2]:.3f} begin {m[3]:.3f} end {m[4]:.3f} poll {m[5]:.3f} ms",
                   file=sys.stderr, flush=True)
         if n_gpus > 1 and rank == 0:
             # the host frame of the last e2e step against rank 0's own unsharded render: the shared frame is the frame

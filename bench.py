@@ -208,6 +208,14 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def shared_config(args):
+    """The `config` object of the bench line: what names the workload, IDENTICAL in both arms (`--impl ours` / `--impl reference`) so that
+    the driver compares like with like; everything that describes how an arm ran goes to `details`."""
+    return {"workload": workload_name(args), "frame": [args.width, args.height], "svo_format": args.format, "shadow_rays": not args.no_shadows,
+            "l2": "GPU arm: " + ("not flushed (--no-flush)" if args.no_flush else "flushed between steps by a 144 MiB device fill (> 126 MB L2) inside the timed region") +
+                  "; CPU arm: host caches as they are (the 33 MB SVO exceeds any private cache of the box)"}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference shaders (oracle/), all host threads, bounded sample per step.
     The process never maps the product library: the world is built with libvoxelrs_world.so (VOXELRS_WORLD_ONLY)."""
@@ -240,8 +248,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(args), "note": "CPU port of the reference GLSL (oracle/), not the Rust+OpenGL "
-                                        "reference itself: no rustc / Mesa in this image (llvmpipe: not measurable on this box)"},
+        "data": "synthetic", "config": shared_config(args),
+        "details": {"note": "CPU port of the reference GLSL (oracle/), not the Rust+OpenGL reference itself: no rustc / Mesa in this image "
+                            "(llvmpipe: not measurable on this box)"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": "per step: " + desc},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -703,11 +712,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": workload_name(args), "frame": [W, H], "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth), "svo_format": args.format,
+        "config": dict(shared_config(args), **({"parity_check": parity_check} if n_gpus > 1 else {})),
+        "details": {
+            "svo_bytes": int(world.size_bytes), "svo_depth": int(world.depth),
             "chunks": int(world.chunk_count), "rays_per_frame": rays_total, "primary_rays": prim_total, "shadow_rays": shad_total,
             "parallelism": f"image tiles (32x16 px macro blocks, interleaved) over {n_gpus} GPU(s), SVO replicated",
-            "l2": "not flushed (--no-flush)" if args.no_flush else "flushed between steps: 144 MiB device fill (> 126 MB L2) inside the timed region",
             "kernels": "wavefront: trace_primary (persistent) -> shade -> trace_shadow (persistent)" + ("" if args.no_overlap else
                        "; for small launches (shards, small frames) shade runs next to trace_primary on its own stream, its CTAs wait per 32x4-pixel strip"), "ctas_per_sm": args.ctas_per_sm or 8,
             "refill_threshold": args.refill or 1,

@@ -23,6 +23,14 @@ def test_reference_arm_line():
     assert d["metric"].startswith("Mrays/s") and d["unit"] == "Mrays/s" and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert "generated-terrain" in d["config"]["workload"] and "320x180" in d["config"]["workload"]
+    # `config` names the workload and is IDENTICAL in both arms (the driver compares them): it is bench.shared_config(args), nothing else
+    import argparse
+    import bench
+    sys_argv, sys.argv = sys.argv, ["bench.py", "--impl", "reference", *SMALL]
+    try:
+        assert d["config"] == bench.shared_config(bench.parse())
+    finally:
+        sys.argv = sys_argv
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

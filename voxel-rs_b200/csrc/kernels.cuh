@@ -640,7 +640,7 @@ struct RaycastArgs {
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(VX_THREADS) trace_picker_kernel(RaycastArgs a) {
     extern __shared__ uint32_t smem_raw[];
-    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw);
+    const Smem sm = make_smem(a.scene.unorm, a.scene.stack_levels, smem_raw, true, false);   // no texture is ever sampled here: no unorm table
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float octree_scale = load_octree_scale<FMT>(a.scene);

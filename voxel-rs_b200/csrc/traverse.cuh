@@ -95,18 +95,21 @@ struct Smem {
     const float* unorm;
     float* cold;
 };
-__host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, bool with_stack = true) {
-    return ((with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0) + 256 + (size_t)VX_COLD_WORDS * VX_THREADS) * 4;
+// with_lut = false: a kernel that never samples a texture (the picker) leaves the unorm table out — the 1 KB is what separates
+// 8 from 9 resident CTAs per SM at the depth-12 world of BASELINE configs[3].
+__host__ __device__ inline size_t smem_bytes(uint32_t stack_levels, bool with_stack = true, bool with_lut = true) {
+    return ((with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0) + (with_lut ? 256 : 0) + (size_t)VX_COLD_WORDS * VX_THREADS) * 4;
 }
-__device__ __forceinline__ Smem make_smem(const float* unorm_table, uint32_t stack_levels, uint32_t* base, bool with_stack = true) {
+__device__ __forceinline__ Smem make_smem(const float* unorm_table, uint32_t stack_levels, uint32_t* base, bool with_stack = true, bool with_lut = true) {
     Smem m;
     const size_t stack_words = with_stack ? (size_t)3 * stack_levels * VX_THREADS : 0;
     m.stack = (uint32_t)__cvta_generic_to_shared(base + threadIdx.x);
     asm volatile("" : "+r"(m.stack));   // opaque from here on: one live register instead of a per-iteration recomputation
     float* lut = reinterpret_cast<float*>(base + stack_words);
-    for (uint32_t i = threadIdx.x; i < 256; i += VX_THREADS) lut[i] = __ldg(unorm_table + i);   // (every kernel that calls this runs VX_THREADS threads)
+    if (with_lut)
+        for (uint32_t i = threadIdx.x; i < 256; i += VX_THREADS) lut[i] = __ldg(unorm_table + i);   // (every kernel that calls this runs VX_THREADS threads)
     m.unorm = lut;
-    m.cold = lut + 256 + threadIdx.x;
+    m.cold = lut + (with_lut ? 256 : 0) + threadIdx.x;
     __syncthreads();
     return m;
 }

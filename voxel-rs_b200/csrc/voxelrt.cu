@@ -1103,7 +1103,7 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
     a.counters = c->d_counters + 1;
     a.work_counter = c->d_work + 4;
     a.refill_threshold = (uint32_t)c->opt_refill_picker;
-    const size_t smem = stack_smem_bytes(a.scene);
+    const size_t smem = smem_bytes(a.scene.stack_levels, true, false);   // the picker kernel has no unorm table
     auto k = c->fmt == VX_FMT_CSVO ? (c->opt_count ? trace_picker_kernel<VX_FMT_CSVO, true> : trace_picker_kernel<VX_FMT_CSVO, false>)
                                    : (c->opt_count ? trace_picker_kernel<VX_FMT_ESVO, true> : trace_picker_kernel<VX_FMT_ESVO, false>);
     int grid = 0;

@@ -8,10 +8,15 @@ Metric (BASELINE.json): Mrays/s of primary + shadow rays actually cast, and ms/f
 reference's generated-terrain world (its own generator restated: Perlin seed 1 + splines; default radius 20 chunks, LOD rule,
 camera (-24,80,174) looking along -z, fov 72 deg, sun (-1,-1,-1)/sqrt3, shadows on) = BASELINE.json configs[2]. A "step" is one frame.
 
-  value        rays/s with everything resident in HBM: per step = L2 flush + vx_render (+ for N>1: NCCL broadcast of the
-               frame's dirty SVO ranges, scatter, shard pack, NCCL gather to GPU 0, unpack)
-  e2e          the same frame through the C ABI with HOST buffers: dirty ranges copied into the pinned mirror and
-               uploaded (vx_svo_commit), vx_render, RGBA8 read-back to host (vx_read_frame_rgba8)
+  value        rays/s with everything resident in HBM: per step = L2 flush + vx_render (+ for N>1: the frame's dirty SVO ranges —
+               NCCL broadcast one frame ahead on a side stream — applied by the scatter kernel, shard render, finished pixels
+               stored by the kernels into GPU 0's RGBA8 frame over NVLink peer memory, frame flags as the barrier)
+  e2e          the same frame through the C ABI with HOST buffers, every step: dirty ranges copied into the pinned mirror and
+               uploaded (vx_svo_commit), vx_render_read_rgba8_begin(frame k), vx_render_read_rgba8_end(frame k-1): one frame's
+               RGBA8 read-back is in flight under the next frame's tracing, the last frame is drained inside the timed region.
+               e2e.blocking_call = the same step through the one blocking vx_render_read_rgba8; e2e.pcie_d2h = a frame-sized
+               D2H copy alone. N>1: every rank DMAs its stripes into one of two host frames shared by the ranks.
+  config       names the workload and is identical in both arms (shared_config); how an arm ran is in `details`
   roofline     algorithmic node/texel/frame bytes per launch (SURVEY §8d formula, counts from a counting launch of the
                same frame) / mean kernel time (CUDA events on the launching stream) vs measured HBM copy bandwidth
   cpu_baseline the CPU oracle (a port of the GLSL, NOT the reference itself) on the host cores over a bounded sample

@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--bands", type=int, default=3, help="e2e: bands of the blocking vx_render_read_rgba8 (render/read-back overlap inside one frame)")
     ap.add_argument("--bands-pipelined", type=int, default=1, help="e2e: bands per frame of the begin/end loop (the read-back overlaps the NEXT frame there)")
+    ap.add_argument("--one-stream", action="store_true", help="A/B: uploads on the render stream too (no overlap of the dirty-range scatter with the L2 flush)")
     ap.add_argument("--e2e-sync", action="store_true", help="e2e through the blocking vx_render_read_rgba8 only (no frame in flight across steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -301,7 +302,10 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    svo.set_streams(stream.cuda_stream, stream.cuda_stream, stream.cuda_stream)
+    # render (and picker) work on the bench's stream, where its events are; the upload stream stays the library's own, so that the
+    # dirty-range scatter + bounds kernels of a step (ordered behind the previous frame by an event, in front of this frame by another)
+    # run next to the L2 flush instead of after it (--one-stream: everything on one stream, the round-1 arrangement)
+    svo.set_streams(stream.cuda_stream, stream.cuda_stream if args.one_stream else None, stream.cuda_stream)
     if args.refill:
         svo.set_option(pkg.OPT_REFILL, args.refill)
     if args.refill_shadow:

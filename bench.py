@@ -1081,7 +1081,7 @@ def run_picker(args):
     }
     if e2e_ms is not None:
         line["e2e"] = {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(48 * n),
-                       "d2h_bytes_per_step": int(48 * n), "path": "vx_raycast: pinned host tasks -> H2D -> trace_picker_kernel -> D2H results, in slices of 2 Mi rays so that upload, tracing and read-back overlap (full-duplex PCIe); returns after the last copy, like the reference's fence"}
+                       "d2h_bytes_per_step": int(48 * n), "path": "vx_raycast: pinned host tasks -> H2D -> trace_picker_kernel -> D2H results, in slices of 1 Mi rays so that upload, tracing and read-back overlap (full-duplex PCIe); returns after the last copy, like the reference's fence"}
     if not args.skip_cpu and world_size == 1:
         ora = graft.load_oracle()
         tex, mips = reg.textures()

@@ -296,7 +296,7 @@ int vx_read_hit_records(VxCtx* ctx, VxHitRecord* out);
 
 /* graphics::Svo::raycast (svo.rs:233-255) = picker.glsl main(): tasks/results are HOST arrays of n
  * records; synchronous like the reference (fence place+wait, svo.rs:248-249). n is not capped at
- * 100 (svo_picker.rs:5) — only by VxConfig.max_rays. Batches above 2 Mi rays are traced in slices so that
+ * 100 (svo_picker.rs:5) — only by VxConfig.max_rays. Batches above 1 Mi rays are traced in slices so that
  * the upload of the tasks, the tracing and the read-back of the results overlap (give it pinned host
  * memory for that); the call still returns only when every result is in `results`. */
 int vx_raycast(VxCtx* ctx, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results);

@@ -1165,7 +1165,11 @@ static int launch_raycast(VxCtx* c, const float4* tasks_dev, uint64_t n, float4*
 
 // Batches above this many rays are cut into slices: slice i's tasks go up (s_pick_in) while slice i-1 is traced (s_picker) and
 // slice i-2's results come down (s_copy) — PCIe is full duplex, so a large batch costs about max(H2D, D2H) instead of their sum.
-static constexpr uint64_t VX_PICK_SLICE = 1ull << 21;   // 2 Mi rays = 96 MiB each way
+#ifndef VX_PICK_SLICE_LOG2
+#define VX_PICK_SLICE_LOG2 20
+#endif
+static constexpr uint64_t VX_PICK_SLICE = 1ull << VX_PICK_SLICE_LOG2;   // 1 Mi rays = 48 MiB each way; 16 Mi rays end to end: 2^19 / 2^20 / 2^21 / 2^22 ->
+                                                                        // 18.90 / 18.78 / 19.97 / 20.90 ms (profiles/r02_step_variants.md)
 
 static int raycast_pipelined(VxCtx* c, const VxPickerTask* tasks, uint64_t n, VxPickerResult* results) {
     const uint64_t n_slices = (n + VX_PICK_SLICE - 1) / VX_PICK_SLICE;
